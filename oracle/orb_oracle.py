@@ -1,0 +1,246 @@
+"""ctypes binding of the CPU oracle (oracle/liborb_oracle.so). TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module. The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liborb_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_ic_angle.restype = C.c_float
+        L.orc_extract_batch_mt.restype = C.c_long
+        L.orc_match_batch_mt.restype = C.c_long
+        _LIB = L
+    return _LIB
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t)
+
+
+class OracleExtractor:
+    """Mirror of ORBextractor (include/ORBextractor.h:93-162) on the CPU oracle."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = C.c_void_p(self.L.orc_create(nfeatures, C.c_float(scale_factor), nlevels, ini_th, min_th))
+        sc = np.zeros(nlevels, np.float32); isc = sc.copy(); s2 = sc.copy(); is2 = sc.copy()
+        per = np.zeros(nlevels, np.int32); umax = np.zeros(16, np.int32)
+        self.L.orc_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2), _p(per), _p(umax))
+        self.scale, self.inv_scale, self.sigma2, self.inv_sigma2 = sc, isc, s2, is2
+        self.per_level, self.umax = per, umax
+
+    def __del__(self):
+        try:
+            self.L.orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def __call__(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        cap = self.nfeatures + 64 * self.nlevels + 1024
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orc_extract(self.h, _p(img), w, h, img.strides[0], _p(kps), _p(desc), cap)
+        assert n <= cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l):
+        """Bordered pyramid level l as (h+38, w+38) array."""
+        w = C.c_int(); h = C.c_int(); s = C.c_int()
+        self.L.orc_level_info(self.h, l, C.byref(w), C.byref(h), C.byref(s))
+        out = np.zeros((h.value + 38, w.value + 38), np.uint8)
+        self.L.orc_level_copy(self.h, l, _p(out))
+        return out
+
+    def blurred(self, l):
+        w = C.c_int(); h = C.c_int(); s = C.c_int()
+        self.L.orc_level_info(self.h, l, C.byref(w), C.byref(h), C.byref(s))
+        out = np.zeros((h.value, w.value), np.uint8)
+        ok = self.L.orc_blur_copy(self.h, l, _p(out))
+        return out if ok else None
+
+    def candidates(self, l):
+        cap = 1 << 20
+        xs = np.zeros(cap, np.int32); ys = xs.copy(); sc = xs.copy()
+        n = self.L.orc_level_candidates(self.h, l, _p(xs), _p(ys), _p(sc), cap)
+        assert n <= cap
+        return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+    def kept(self, l):
+        cap = 1 << 16
+        idx = np.zeros(cap, np.int32)
+        n = self.L.orc_level_kept(self.h, l, _p(idx), cap)
+        return idx[:n].copy()
+
+    def stats(self, l):
+        a = C.c_int(); b = C.c_int(); c = C.c_int()
+        self.L.orc_level_stats(self.h, l, C.byref(a), C.byref(b), C.byref(c))
+        return dict(cells=a.value, fallback=b.value, tie_sensitive=c.value)
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def border101(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.zeros((h + 38, w + 38), np.uint8)
+    lib().orc_border101(_p(src), w, h, src.strides[0], _p(dst))
+    return dst
+
+
+def fast(img, threshold, nms=True):
+    """img may be a non-contiguous 2-D view (row stride honoured)."""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    h, w = img.shape
+    cap = max(w * h, 1)
+    xs = np.zeros(cap, np.int32); ys = xs.copy(); sc = xs.copy()
+    n = lib().orc_fast(C.c_void_p(img.ctypes.data), w, h, img.strides[0], threshold, int(nms), _p(xs), _p(ys), _p(sc), cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def fast_score_map(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((h, w), np.int32)
+    lib().orc_fast_score_map(_p(img), w, h, img.strides[0], _p(out))
+    return out
+
+
+def gauss7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.zeros((h, w), np.uint8)
+    lib().orc_gauss7(_p(src), w, h, src.strides[0], _p(dst), w)
+    return dst
+
+
+def fast_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32); x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(y.shape, np.float32)
+    lib().orc_fast_atan2_many(_p(y), _p(x), _p(out), y.size)
+    return out
+
+
+def brief(img, px, py, angle):
+    img = np.ascontiguousarray(img, np.uint8)
+    d = np.zeros(32, np.uint8)
+    lib().orc_brief(C.c_void_p(img.ctypes.data), img.strides[0], C.c_float(px), C.c_float(py), C.c_float(angle), _p(d))
+    return d
+
+
+def quadtree(xs, ys, score, min_x, max_x, min_y, max_y, N):
+    xs = np.ascontiguousarray(xs, np.float32); ys = np.ascontiguousarray(ys, np.float32)
+    score = np.ascontiguousarray(score, np.int32)
+    kept = np.zeros(len(xs) + 8, np.int32)
+    tie = C.c_int(0)
+    n = lib().orc_quadtree(_p(xs), _p(ys), _p(score), len(xs), min_x, max_x, min_y, max_y, N, _p(kept), len(kept), C.byref(tie))
+    return kept[:n].copy(), tie.value
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_hamming(_p(a), _p(b))
+
+
+def hamming_matrix(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    out = np.zeros((a.shape[0], b.shape[0]), np.int32)
+    lib().orc_hamming_matrix(_p(a), a.shape[0], _p(b), b.shape[0], _p(out))
+    return out
+
+
+def three_maxima(histo):
+    histo = np.ascontiguousarray(histo, np.int32)
+    out = np.zeros(3, np.int32)
+    lib().orc_three_maxima(_p(histo), len(histo), _p(out))
+    return tuple(int(v) for v in out)
+
+
+def search_for_initialization(xy1, oct1, ang1, desc1, xy2, oct2, ang2, desc2, bounds, prev_matched,
+                              window=100, nnratio=0.9, check_ori=True, mode=0):
+    """Mirror of ORBmatcher::SearchForInitialization (ORBmatcher.cc:573).
+
+    mode 0 = reference-faithful windowed search, mode 1 = brute force over all of F2.
+    Returns (nmatches, matches12, prev_matched_updated, best, second)."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    xy1, xy2, ang1, ang2 = f32(xy1), f32(xy2), f32(ang1), f32(ang2)
+    oct1, oct2 = i32(oct1), i32(oct2)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    n1, n2 = len(ang1), len(ang2)
+    prev = f32(prev_matched).copy()
+    b = f32(bounds)
+    m12 = np.full(n1, -1, np.int32)
+    best = np.zeros(n1, np.int32); second = np.zeros(n1, np.int32)
+    n = lib().orc_search_for_initialization(n1, _p(xy1), _p(oct1), _p(ang1), _p(desc1), n2, _p(xy2), _p(oct2),
+                                            _p(ang2), _p(desc2), _p(b), _p(prev), _p(m12), int(window),
+                                            C.c_float(nnratio), int(check_ori), int(mode), _p(best), _p(second))
+    return n, m12, prev, best, second
+
+
+def allpairs_counts(desc, nnratio=0.9, row_begin=0, row_end=None):
+    desc = np.ascontiguousarray(desc, np.uint8)
+    nkf, nd, _ = desc.shape
+    row_end = nkf if row_end is None else row_end
+    out = np.zeros((row_end - row_begin, nkf), np.int32)
+    lib().orc_allpairs_counts(_p(desc), nkf, nd, C.c_float(nnratio), row_begin, row_end, _p(out))
+    return out
+
+
+def extract_batch_mt(imgs, nfeatures, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, nthreads=None):
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    B, h, w = imgs.shape
+    nthreads = nthreads or hardware_threads()
+    counts = np.zeros(B, np.int32)
+    total = lib().orc_extract_batch_mt(nfeatures, C.c_float(scale_factor), nlevels, ini_th, min_th, _p(imgs), B, w, h,
+                                       nthreads, _p(counts))
+    return total, counts
+
+
+def match_batch_mt(desc, angle, nnratio=0.9, nthreads=None):
+    """desc: (2P, n, 32) u8, angle: (2P, n) f32 -> brute-force SearchForInitialization per pair."""
+    desc = np.ascontiguousarray(desc, np.uint8); angle = np.ascontiguousarray(angle, np.float32)
+    P = desc.shape[0] // 2; n = desc.shape[1]
+    nthreads = nthreads or hardware_threads()
+    nm = np.zeros(P, np.int32)
+    total = lib().orc_match_batch_mt(_p(desc), _p(angle), P, n, C.c_float(nnratio), nthreads, _p(nm))
+    return total, nm
+
+
+def hardware_threads():
+    return int(lib().orc_hardware_threads())

@@ -1,0 +1,78 @@
+"""Seeded synthetic 8-bit frames and descriptor sets (SURVEY.md §8d "Synthetic inputs").
+
+numpy only, deterministic for a given (w, h, seed): a low-frequency random field, ~400
+alpha-blended random rectangles (corners and edges for FAST), Gaussian noise sigma 3.
+Used by tests and bench.py; this is workload generation, not part of the hot path.
+"""
+import numpy as np
+
+
+def _upsample_bilinear(low, h, w):
+    lh, lw = low.shape
+    ys = np.linspace(0, lh - 1, h)
+    xs = np.linspace(0, lw - 1, w)
+    y0 = np.floor(ys).astype(np.int64); y1 = np.minimum(y0 + 1, lh - 1); fy = (ys - y0)[:, None]
+    x0 = np.floor(xs).astype(np.int64); x1 = np.minimum(x0 + 1, lw - 1); fx = (xs - x0)[None, :]
+    a = low[y0][:, x0]; b = low[y0][:, x1]; c = low[y1][:, x0]; d = low[y1][:, x1]
+    return (a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy
+
+
+def synth_frame(w, h, seed, n_rect=400, noise_sigma=3.0):
+    rng = np.random.RandomState(seed & 0x7FFFFFFF)
+    low = rng.rand(h // 16 + 2, w // 16 + 2) * 160.0 + 40.0
+    img = _upsample_bilinear(low, h, w)
+    for _ in range(n_rect):
+        rw = int(rng.randint(6, max(8, w // 6))); rh = int(rng.randint(6, max(8, h // 5)))
+        x0 = int(rng.randint(-rw // 2, w)); y0 = int(rng.randint(-rh // 2, h))
+        val = rng.rand() * 255.0; alpha = 0.35 + 0.65 * rng.rand()
+        ys = slice(max(y0, 0), min(y0 + rh, h)); xs = slice(max(x0, 0), min(x0 + rw, w))
+        img[ys, xs] = img[ys, xs] * (1 - alpha) + val * alpha
+    if noise_sigma > 0:
+        img = img + rng.normal(0.0, noise_sigma, img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def synth_batch(w, h, count, seed0=0, unique=None):
+    """(count, h, w) u8. `unique` < count repeats a pool of unique frames (documented by callers)."""
+    unique = count if unique is None else min(unique, count)
+    pool = np.stack([synth_frame(w, h, seed0 + i) for i in range(unique)])
+    if unique == count:
+        return pool
+    reps = (count + unique - 1) // unique
+    return np.concatenate([pool] * reps)[:count].copy()
+
+
+def adversarial_frames(w, h):
+    """Edge-case frames of SURVEY.md §8d: constant, low contrast, checkerboard, uniform noise."""
+    rng = np.random.RandomState(1234)
+    out = {}
+    out["constant"] = np.full((h, w), 128, np.uint8)
+    base = synth_frame(w, h, 99, noise_sigma=0.0).astype(np.float32)
+    out["low_contrast"] = np.clip(np.rint(128 + (base - 128) * 0.12), 0, 255).astype(np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    out["checkerboard"] = (((yy // 8 + xx // 8) % 2) * 200 + 20).astype(np.uint8)
+    out["uniform_noise"] = rng.randint(0, 256, (h, w)).astype(np.uint8)
+    return out
+
+
+def random_descriptors(n, seed):
+    rng = np.random.RandomState(seed & 0x7FFFFFFF)
+    return rng.randint(0, 256, (n, 32)).astype(np.uint8)
+
+
+def correlated_descriptor_pair(n, seed, flip_prob=0.06, outlier_frac=0.3):
+    """Two descriptor sets with realistic match structure: B is a shuffled copy of A with
+    per-bit noise, a fraction replaced by unrelated descriptors. Returns (A, B, angA, angB)."""
+    rng = np.random.RandomState(seed & 0x7FFFFFFF)
+    A = rng.randint(0, 256, (n, 32)).astype(np.uint8)
+    bits = np.unpackbits(A, axis=1)
+    flips = (rng.rand(*bits.shape) < flip_prob).astype(np.uint8)
+    B = np.packbits(bits ^ flips, axis=1)
+    perm = rng.permutation(n)
+    B = B[perm]
+    out = rng.rand(n) < outlier_frac
+    B[out] = rng.randint(0, 256, (int(out.sum()), 32)).astype(np.uint8)
+    angA = (rng.rand(n) * 360.0).astype(np.float32)
+    inv = np.empty(n, np.int64); inv[np.arange(n)] = perm
+    angB = ((angA[perm] - 12.0 + rng.normal(0, 3.0, n)) % 360.0).astype(np.float32)
+    return A, B, angA, angB
