@@ -1,0 +1,189 @@
+/* orb_b200.h — C ABI of the B200-native ORB front-end (liborb_b200.so).
+ *
+ * Drop-in boundary for the reference's feature front-end hot path
+ * (electech6/ORB_SLAM2_detailed_comments). Each entry point names the reference
+ * interface it replaces (file:line under the reference checkout). Plain pointers and
+ * sizes only; no C++/torch types. All functions return an orb_status (0 = ok) and never
+ * abort or throw. One CUDA stream + workspace per handle; distinct handles are
+ * thread-safe against each other, a single handle is not re-entrant (like the
+ * reference extractor, whose pyramid buffers are overwritten per call,
+ * include/ORBextractor.h:162).
+ *
+ * There is NO CPU fallback: every compute entry point runs hand-written sm_100a
+ * kernels and fails with ORB_ERR_CUDA when no device is usable.
+ */
+#ifndef ORB_B200_H_
+#define ORB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum orb_status {
+  ORB_OK = 0,
+  ORB_ERR_INVALID = 1,     /* bad argument (null pointer, non-positive size, ...) */
+  ORB_ERR_CUDA = 2,        /* CUDA runtime error; see orb_last_error() */
+  ORB_ERR_CAPACITY = 3,    /* an output or internal list overflowed its capacity */
+  ORB_ERR_UNSUPPORTED = 4  /* geometry the reference itself cannot process (e.g. level < 2 cells) */
+} orb_status;
+
+/* Binary layout of cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct orb_keypoint {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} orb_keypoint;
+
+/* ORBextractor constructor arguments (include/ORBextractor.h:93, src/ORBextractor.cc:469). */
+typedef struct orb_params {
+  int32_t nfeatures;
+  float scale_factor;
+  int32_t nlevels;
+  int32_t ini_th_fast;
+  int32_t min_th_fast;
+} orb_params;
+
+/* One level of mvImagePyramid (include/ORBextractor.h:162): `data` points at interior pixel
+ * (0,0); at least 19 readable pixels of REFLECT_101 border surround it (Frame.cc:855,967). */
+typedef struct orb_level_view {
+  uint8_t* data;
+  int32_t width, height;
+  int64_t step;
+} orb_level_view;
+
+typedef struct orb_extractor orb_extractor;
+
+const char* orb_last_error(void);
+int orb_device_count(void);
+
+/* ---- ORBextractor ------------------------------------------------------------------- */
+
+/* Replaces ORBextractor::ORBextractor (src/ORBextractor.cc:469-571). `max_batch` bounds the
+ * frames processed per internal chunk (workspace ~5 bytes per pyramid pixel per frame). */
+int orb_create(const orb_params* params, int device, int max_batch, orb_extractor** out);
+int orb_destroy(orb_extractor* h);
+
+/* Replaces GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (include/ORBextractor.h:119-159) and exposes
+ * mnFeaturesPerLevel. Any pointer may be NULL. Arrays hold nlevels entries. */
+int orb_get_scale_tables(const orb_extractor* h, float* scale, float* inv_scale, float* sigma2,
+                         float* inv_sigma2, int32_t* features_per_level);
+
+/* Upper bound on keypoints per frame (nfeatures + 3 per level): size outputs with this. */
+int orb_max_keypoints(const orb_extractor* h);
+
+/* Replaces ORBextractor::operator()(image, mask, keypoints, descriptors)
+ * (src/ORBextractor.cc:1533-1649) for one frame in HOST memory. `image` is CV_8UC1 with row
+ * stride `step`; the mask argument of the reference is ignored there and absent here.
+ * Writes *n keypoints (ascending octave, level-0 coordinates) and n x 32 descriptor bytes.
+ * Empty image (w or h == 0) returns ORB_OK with outputs untouched (:1537). If `pyramid` is
+ * non-NULL it receives nlevels views into host memory owned by the handle (valid until the
+ * next call), i.e. the mvImagePyramid contract. */
+int orb_extract(orb_extractor* h, const uint8_t* image, int width, int height, size_t step,
+                orb_keypoint* keypoints, int capacity, int* n, uint8_t* descriptors,
+                orb_level_view* pyramid);
+
+/* Batch of B same-sized frames in HOST memory (frame b at images + b*frame_stride, rows at
+ * `step`). Outputs are strided by `capacity`: keypoints[b*capacity + i], descriptors
+ * [(b*capacity + i)*32], counts[b]. Host<->device copies happen inside. */
+int orb_extract_batch_host(orb_extractor* h, const uint8_t* images, int batch, int width, int height,
+                           size_t step, size_t frame_stride, orb_keypoint* keypoints, int capacity,
+                           int32_t* counts, uint8_t* descriptors);
+
+/* Same, with inputs and outputs RESIDENT IN DEVICE MEMORY of the handle's device. `stream`
+ * is a cudaStream_t (NULL = the handle's own stream); the call is asynchronous on it. */
+int orb_extract_batch_device(orb_extractor* h, const uint8_t* d_images, int batch, int width, int height,
+                             size_t step, size_t frame_stride, orb_keypoint* d_keypoints, int capacity,
+                             int32_t* d_counts, uint8_t* d_descriptors, void* stream);
+
+/* Blocks until the handle's work (on `stream`, NULL = own stream) is done; reports sticky
+ * capacity overflows of internal candidate lists as ORB_ERR_CAPACITY. */
+int orb_synchronize(orb_extractor* h, void* stream);
+
+/* Number of kernel launches the last batch call issued (for bench accounting). */
+int orb_last_launch_count(const orb_extractor* h);
+
+/* Stage outputs of the last call, for parity tests (frame index inside the last chunk).
+ *   level geometry:           orb_stage_level_size
+ *   bordered pyramid level:   (h+38) x (w+38) tightly packed
+ *   blurred level:            h x w tightly packed
+ *   FAST candidates entering the quadtree (unordered): x, y (level image coords), score
+ *   kept keypoints of a level in list order: x, y, score */
+int orb_stage_level_size(const orb_extractor* h, int level, int* width, int* height);
+int orb_stage_copy_level(orb_extractor* h, int frame, int level, uint8_t* dst);
+int orb_stage_copy_blur(orb_extractor* h, int frame, int level, uint8_t* dst);
+int orb_stage_copy_candidates(orb_extractor* h, int frame, int level, int32_t* xs, int32_t* ys,
+                              int32_t* score, int capacity, int* n);
+int orb_stage_copy_kept(orb_extractor* h, int frame, int level, int32_t* xs, int32_t* ys,
+                        int32_t* score, int capacity, int* n);
+
+/* ---- ORBmatcher --------------------------------------------------------------------- */
+
+/* Replaces ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2083-2103): 256-bit Hamming
+ * distance of two 32-byte descriptors. Host-side (a device round trip per call would be
+ * absurd); the batched kernels below compute the same quantity on the GPU. */
+int orb_descriptor_distance(const uint8_t* a, const uint8_t* b);
+
+/* The slice of Frame that SearchForInitialization reads (Frame.h mvKeysUn, mDescriptors,
+ * grid bounds). For device entry points all pointers are device pointers. */
+typedef struct orb_frame_view {
+  int32_t n;
+  const float* xy;            /* n x 2: mvKeysUn[i].pt */
+  const int32_t* octave;      /* n */
+  const float* angle;         /* n, degrees */
+  const uint8_t* descriptors; /* n x 32 */
+} orb_frame_view;
+
+typedef struct orb_match_params {
+  float nnratio;        /* ORBmatcher::mfNNratio (ORBmatcher.h ctor, default 0.6; 0.9 at Tracking.cc:915) */
+  int32_t check_orientation; /* ORBmatcher::mbCheckOrientation */
+  int32_t window;       /* windowSize (Tracking.cc:926 passes 100); ignored when mode = 1 */
+  int32_t mode;         /* 0 = reference-faithful (octave-0 rows, 64x48 grid cell range + circular
+                           window, Frame.cc:590-670); 1 = brute force over all of frame 2 */
+  float min_x, max_x, min_y, max_y; /* Frame::mnMinX.. (undistorted image bounds) */
+} orb_match_params;
+
+typedef struct orb_matcher orb_matcher;
+
+int orb_matcher_create(int device, int max_pairs, int max_keypoints, orb_matcher** out);
+int orb_matcher_destroy(orb_matcher* m);
+
+/* Replaces ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:573-717) for one frame
+ * pair in HOST memory. prev_matched (n1 x 2 floats) is vbPrevMatched, read and updated;
+ * matches12 (n1 ints, -1 = none) is vnMatches12. *nmatches is the return value of the
+ * reference. best/second (n1 ints each, may be NULL) receive each row's 2-NN distances
+ * (INT_MAX where no candidate). */
+int orb_search_for_initialization(orb_matcher* m, const orb_frame_view* f1, const orb_frame_view* f2,
+                                  const orb_match_params* mp, float* prev_matched, int32_t* matches12,
+                                  int* nmatches, int32_t* best, int32_t* second);
+
+/* Batch of P independent pairs RESIDENT IN DEVICE MEMORY, brute-force mode (mode 1), every
+ * frame holding exactly n keypoints: descriptors (2P x n x 32; pair p = frames 2p, 2p+1),
+ * angles (2P x n). Outputs: matches12 (P x n), nmatches (P). Asynchronous on `stream`. */
+int orb_match_pairs_device(orb_matcher* m, const uint8_t* d_descriptors, const float* d_angles, int pairs,
+                           int n, float nnratio, int check_orientation, int32_t* d_matches12,
+                           int32_t* d_nmatches, void* stream);
+
+/* All-pairs keyframe matching: `d_all` holds n_kf x n_desc descriptors
+ * (all keyframes, e.g. after an all-gather); rows [row_begin,row_end) are this rank's
+ * keyframes. d_counts ((row_end-row_begin) x n_kf ints) receives, per ordered keyframe pair,
+ * the number of row descriptors whose 2-NN passes best <= TH_LOW and best < nnratio*second. */
+int orb_match_allpairs_device(orb_matcher* m, const uint8_t* d_all, int n_kf, int n_desc, int row_begin,
+                              int row_end, float nnratio, int32_t* d_counts, void* stream);
+
+/* Plain Hamming distance matrix (na x nb ints) on the device: parity aid for the kernels. */
+int orb_hamming_matrix_device(orb_matcher* m, const uint8_t* d_a, int na, const uint8_t* d_b, int nb,
+                              int32_t* d_out, void* stream);
+
+int orb_matcher_synchronize(orb_matcher* m, void* stream);
+
+/* Integer-pipe microbenchmark used for the matching roofline: runs `iters` dependent-free
+ * POPC (what=0) or LOP3 (what=1) per thread on a full grid and returns ops/s in *ops_per_s. */
+int orb_int_pipe_peak(int device, int what, double* ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H_ */

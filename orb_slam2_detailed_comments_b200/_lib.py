@@ -1,0 +1,110 @@
+"""ctypes loader for liborb_b200.so (the C ABI of include/orb_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import fails loudly, and
+every compute call fails with the CUDA error when no B200 is visible.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liborb_b200.so")
+
+ORB_OK, ORB_ERR_INVALID, ORB_ERR_CUDA, ORB_ERR_CAPACITY, ORB_ERR_UNSUPPORTED = range(5)
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+class OrbLevelView(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("step", C.c_int64)]
+
+
+class OrbFrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("xy", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),
+                ("descriptors", C.c_void_p)]
+
+
+class OrbMatchParams(C.Structure):
+    _fields_ = [("nnratio", C.c_float), ("check_orientation", C.c_int32), ("window", C.c_int32),
+                ("mode", C.c_int32), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float),
+                ("max_y", C.c_float)]
+
+
+# every symbol include/orb_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "orb_last_error", "orb_device_count", "orb_create", "orb_destroy", "orb_get_scale_tables",
+    "orb_max_keypoints", "orb_extract", "orb_extract_batch_host", "orb_extract_batch_device",
+    "orb_synchronize", "orb_last_launch_count", "orb_stage_level_size", "orb_stage_copy_level",
+    "orb_stage_copy_blur", "orb_stage_copy_candidates", "orb_stage_copy_kept",
+    "orb_descriptor_distance", "orb_matcher_create", "orb_matcher_destroy",
+    "orb_search_for_initialization", "orb_match_pairs_device", "orb_match_allpairs_device",
+    "orb_hamming_matrix_device", "orb_matcher_synchronize", "orb_int_pipe_peak",
+]
+
+_lib = None
+
+
+class OrbError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("orb_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("liborb_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; "
+                              "g.build()'` or `make -C orb_slam2_detailed_comments_b200/csrc`. There is no CPU "
+                              "fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.orb_last_error.restype = C.c_char_p
+        vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+        L.orb_create.argtypes = [C.POINTER(OrbParams), i32, i32, C.POINTER(vp)]
+        L.orb_destroy.argtypes = [vp]
+        L.orb_get_scale_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.orb_max_keypoints.argtypes = [vp]
+        L.orb_extract.argtypes = [vp, vp, i32, i32, sz, vp, i32, C.POINTER(i32), vp, vp]
+        L.orb_extract_batch_host.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp]
+        L.orb_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp, vp]
+        L.orb_synchronize.argtypes = [vp, vp]
+        L.orb_last_launch_count.argtypes = [vp]
+        L.orb_stage_level_size.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.orb_stage_copy_level.argtypes = [vp, i32, i32, vp]
+        L.orb_stage_copy_blur.argtypes = [vp, i32, i32, vp]
+        L.orb_stage_copy_candidates.argtypes = [vp, i32, i32, vp, vp, vp, i32, C.POINTER(i32)]
+        L.orb_stage_copy_kept.argtypes = [vp, i32, i32, vp, vp, vp, i32, C.POINTER(i32)]
+        L.orb_descriptor_distance.argtypes = [vp, vp]
+        L.orb_matcher_create.argtypes = [i32, i32, i32, C.POINTER(vp)]
+        L.orb_matcher_destroy.argtypes = [vp]
+        L.orb_search_for_initialization.argtypes = [vp, C.POINTER(OrbFrameView), C.POINTER(OrbFrameView),
+                                                    C.POINTER(OrbMatchParams), vp, vp, C.POINTER(i32), vp, vp]
+        L.orb_match_pairs_device.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp, vp, vp]
+        L.orb_match_allpairs_device.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, vp]
+        L.orb_hamming_matrix_device.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+        L.orb_matcher_synchronize.argtypes = [vp, vp]
+        L.orb_int_pipe_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != ORB_OK:
+        raise OrbError(status, lib().orb_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """Address of a numpy array or a torch tensor (device or host)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())

@@ -1,0 +1,1163 @@
+// orb_extract.cu — B200 (sm_100a) implementation of ORBextractor::operator()
+// (reference: src/ORBextractor.cc:1533-1649 and the functions it calls).
+//
+// Data layout in HBM, per frame of a chunk (all offsets in LevelGeom):
+//   pyramid slab : nlevels bordered u8 planes, row pitch multiple of 32 B, interior column 0
+//                  at byte 32 of a row (16 B aligned), 19 border rows/cols of REFLECT_101 content
+//   blur slab    : nlevels compact u8 planes (pitch multiple of 32 B)
+//   candidates   : per level a uint2 list {x | y<<16, score} (unordered; order is recovered
+//                  from (x,y) because the reference's candidate order is a function of position)
+//   kept         : per level a uint2 list in the reference's final list order
+// Kernels (one launch each over the whole chunk):
+//   k_level0_border, k_resize_border (x nlevels-1)  ComputePyramid      :1655-1724
+//   k_fast_cells                                    ComputeKeyPointsOctTree + cv::FAST :1037-1142
+//   k_quadtree                                      DistributeOctTree   :688-1033
+//   k_blur7                                         cv::GaussianBlur    :1607-1615
+//   k_describe                                      IC_Angle :94-141, computeOrbDescriptor :153-204,
+//                                                   level->image scaling :1633-1642
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/orb_pattern_data.h"
+#include "orb_common.cuh"
+
+namespace orbb200 {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace orbb200
+
+using namespace orbb200;
+
+namespace {
+
+constexpr int kEdge = 19;       // EDGE_THRESHOLD, ORBextractor.cc:81
+constexpr int kLeftPad = 32;    // bytes left of interior column 0 in a bordered row (>= kEdge)
+constexpr int kMaxLevels = 16;
+constexpr int kHalfPatch = 15;  // HALF_PATCH_SIZE, ORBextractor.cc:80
+constexpr int kQtThreads = 256;
+
+struct LevelGeom {
+  int w, h;               // interior size
+  int pitch;              // bordered plane row pitch
+  long long off;          // byte offset of interior (0,0) inside the frame's pyramid slab
+  int bpitch;             // blurred plane pitch
+  long long boff;         // byte offset of the blurred plane inside the frame's blur slab
+  int wCell, hCell;       // FAST cell size (ORBextractor.cc:1070-1071)
+  int nColsAll;           // nCols of the reference (row stride of the candidate order)
+  int nCols, nRows;       // cells that survive the skip rules (:1083, :1101)
+  int cellBase;           // first block of this level in the k_fast_cells grid
+  int nfeat;              // mnFeaturesPerLevel[level]
+  int nIni;               // quadtree roots (:695)
+  float hX;               // root width (:697)
+  int candOff, candCap;   // candidate list slot inside the per-frame candidate array
+  int keptOff, keptCap;
+  int tapX, tapY;         // offsets of this level's resize taps in the tap table
+  int blurTileBase, blurTilesX, blurTilesY;
+  int borderTileBase, borderTilesX, borderTilesY;
+  float scale;            // mvScaleFactor[level]
+  float patch;            // keypoint size = int(31*scale) (:1164)
+};
+
+struct Geom {
+  int nlevels, W, H;
+  int iniTh, minTh;
+  int totalCells, totalBlurTiles;
+  LevelGeom lv[kMaxLevels];
+};
+
+__constant__ int c_umax[kHalfPatch + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// ------------------------------------------------------------------------------------------
+// Pyramid
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int n) {
+  p = p < 0 ? -p : p;
+  return p >= n ? 2 * (n - 1) - p : p;
+}
+
+// Level 0: copyMakeBorder(image, 19, REFLECT_101)  (ORBextractor.cc:1716)
+__global__ void __launch_bounds__(256) k_level0_border(const Geom g, const u8* __restrict__ img, size_t step,
+                                                       size_t frameStride, u8* __restrict__ pyr,
+                                                       size_t pyrStride) {
+  const LevelGeom& L = g.lv[0];
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int by = blockIdx.y;
+  const int f = blockIdx.z;
+  if (bx >= L.w + 2 * kEdge) return;
+  const int x = reflect101(bx - kEdge, L.w), y = reflect101(by - kEdge, L.h);
+  const u8 v = img[(size_t)f * frameStride + (size_t)y * step + x];
+  pyr[(size_t)f * pyrStride + L.off + (long long)(by - kEdge) * L.pitch + (bx - kEdge)] = v;
+}
+
+// Level l>0: resize(level l-1 -> l, INTER_LINEAR) fused with copyMakeBorder(REFLECT_101 |
+// ISOLATED) (ORBextractor.cc:1677, :1695). Every thread of the BORDERED domain recomputes the
+// interior pixel it mirrors, so the plane is written exactly once, coalesced.
+// taps: {source index, c0 | c1<<16} per destination column / row (11-bit fixed point).
+__global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
+                                                       const int2* __restrict__ taps) {
+  const LevelGeom& D = g.lv[l];
+  const LevelGeom& S = g.lv[l - 1];
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int by = blockIdx.y;
+  const int f = blockIdx.z;
+  if (bx >= D.w + 2 * kEdge) return;
+  const int x = reflect101(bx - kEdge, D.w), y = reflect101(by - kEdge, D.h);
+  const int2 tx = __ldg(taps + D.tapX + x), ty = __ldg(taps + D.tapY + y);
+  const int sx0 = tx.x, sx1 = min(sx0 + 1, S.w - 1);
+  const int sy0 = ty.x, sy1 = min(sy0 + 1, S.h - 1);
+  const int cx0 = (short)(tx.y & 0xffff), cx1 = tx.y >> 16;
+  const int cy0 = (short)(ty.y & 0xffff), cy1 = ty.y >> 16;
+  const u8* src = pyr + (size_t)f * pyrStride + S.off;
+  const u8* r0 = src + (long long)sy0 * S.pitch;
+  const u8* r1 = src + (long long)sy1 * S.pitch;
+  const int h0 = r0[sx0] * cx0 + r0[sx1] * cx1;
+  const int h1 = r1[sx0] * cx0 + r1[sx1] * cx1;
+  int v = (((cy0 * (h0 >> 4)) >> 16) + ((cy1 * (h1 >> 4)) >> 16) + 2) >> 2;
+  v = min(max(v, 0), 255);
+  pyr[(size_t)f * pyrStride + D.off + (long long)(by - kEdge) * D.pitch + (bx - kEdge)] = (u8)v;
+}
+
+// ------------------------------------------------------------------------------------------
+// FAST-9/16 per 30-px cell with iniTh/minTh fallback
+// ------------------------------------------------------------------------------------------
+// Score S(p) = largest threshold for which p is still a FAST-9 corner
+//            = max(max_arcs min d, max_arcs min(-d)) - 1,  d_k = I(p) - I(circle_k).
+// Returns S if S >= minTh else 0. `p` points into a shared-memory tile with row pitch tp.
+__device__ __forceinline__ int fast_score_tile(const u8* p, int tp, int minTh) {
+  const int c = p[0];
+  const u8* rm3 = p - 3 * tp; const u8* rm2 = p - 2 * tp; const u8* rm1 = p - tp;
+  const u8* rp1 = p + tp;     const u8* rp2 = p + 2 * tp; const u8* rp3 = p + 3 * tp;
+  int d[16];
+  d[0] = c - rp3[0];   d[1] = c - rp3[1];   d[2] = c - rp2[2];    d[3] = c - rp1[3];
+  d[4] = c - p[3];     d[5] = c - rm1[3];   d[6] = c - rm2[2];    d[7] = c - rm3[1];
+  d[8] = c - rm3[0];   d[9] = c - rm3[-1];  d[10] = c - rm2[-2];  d[11] = c - rm1[-3];
+  d[12] = c - p[-3];   d[13] = c - rp1[-3]; d[14] = c - rp2[-2];  d[15] = c - rp3[-1];
+  // Necessary condition: every 9-arc holds one pixel of each antipodal pair.
+  int minhi = 512, maxlo = -512;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    minhi = min(minhi, max(d[j], d[j + 8]));
+    maxlo = max(maxlo, min(d[j], d[j + 8]));
+  }
+  if (minhi <= minTh && maxlo >= -minTh) return 0;
+  // Exact: sliding 9-window min / max over the circular sequence via two 3-input stages.
+  int mn3[16], mx3[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    mn3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    mx3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+  }
+  int a = -512, b = 512;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    a = max(a, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
+    b = min(b, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+  }
+  const int s = max(a, -b) - 1;
+  return s >= minTh ? s : 0;
+}
+
+// One CTA per cell. The cell's detection window is x in [19+j*wCell, min(18+(j+1)*wCell, w-20)]
+// (sub-image [iniX,maxX) minus FAST's own 3-px frame), so windows tile the level and the 3x3
+// NMS never sees across a cell boundary (scores outside the window count as 0).
+__global__ void __launch_bounds__(128) k_fast_cells(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
+                                                    uint2* __restrict__ cand, int* __restrict__ candCount,
+                                                    int candTotal) {
+  extern __shared__ u8 smem[];
+  const int f = blockIdx.y;
+  int l = 0;
+#pragma unroll 1
+  while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].cellBase) l++;
+  const LevelGeom& L = g.lv[l];
+  const int cell = blockIdx.x - L.cellBase;
+  const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
+  const int x0 = kEdge + cj * L.wCell, x1 = min(x0 + L.wCell - 1, L.w - kEdge - 1);
+  const int y0 = kEdge + ci * L.hCell, y1 = min(y0 + L.hCell - 1, L.h - kEdge - 1);
+  const int cw = x1 - x0 + 1, ch = y1 - y0 + 1;
+  if (cw <= 0 || ch <= 0) return;
+  const int tp = (cw + 6 + 3) & ~3;       // tile pitch
+  const int sp = cw + 2;                  // score pitch (1-px zero apron)
+  u8* tile = smem;
+  u8* sc = smem + tp * (ch + 6);
+  const u8* src = pyr + (size_t)f * pyrStride + L.off + (long long)(y0 - 3) * L.pitch + (x0 - 3);
+  for (int i = threadIdx.x; i < (cw + 6) * (ch + 6); i += blockDim.x) {
+    const int r = i / (cw + 6), c = i - r * (cw + 6);
+    tile[r * tp + c] = src[(long long)r * L.pitch + c];
+  }
+  for (int i = threadIdx.x; i < sp * (ch + 2); i += blockDim.x) sc[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) {
+    const int r = i / cw, c = i - r * cw;
+    const int s = fast_score_tile(tile + (r + 3) * tp + (c + 3), tp, g.minTh);
+    if (s) sc[(r + 1) * sp + c + 1] = (u8)s;
+  }
+  __syncthreads();
+  int strong = 0;
+  for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) {
+    const int r = i / cw, c = i - r * cw;
+    const u8* q = sc + (r + 1) * sp + c + 1;
+    const int s = q[0];
+    if (s >= g.iniTh) {
+      const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
+      strong |= s > m;
+    }
+  }
+  const int th = __syncthreads_or(strong) ? g.iniTh : g.minTh;
+  int* cnt = candCount + f * g.nlevels + l;
+  uint2* out = cand + (size_t)f * candTotal + L.candOff;
+  for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) {
+    const int r = i / cw, c = i - r * cw;
+    const u8* q = sc + (r + 1) * sp + c + 1;
+    const int s = q[0];
+    if (s >= th) {
+      const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
+      if (s > m) {
+        const int idx = atomicAdd(cnt, 1);
+        if (idx < L.candCap) out[idx] = make_uint2((unsigned)(x0 + c) | ((unsigned)(y0 + r) << 16), (unsigned)s);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Quadtree distribution (DistributeOctTree), one CTA per (level, frame)
+// ------------------------------------------------------------------------------------------
+struct QtNode {
+  short x0, x1, y0, y1;  // [x0,x1) x [y0,y1) relative to the 16-px detection border
+  int count;             // keys inside
+  int seq;               // creation order; list order of the reference == descending seq
+};
+
+__device__ __forceinline__ int qt_quadrant(int xr, int yr, const QtNode& nd) {
+  const int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1);  // UL.x + ceil((UR.x-UL.x)/2)  (:608)
+  const int my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+  return (xr < mx ? 0 : 1) + (yr < my ? 0 : 2);       // n1, n2, n3, n4 (:644-662)
+}
+
+// In-place exclusive scan of a[0..n) in shared memory by the whole CTA; returns the total.
+__device__ int block_scan_excl(int* a, int n, int* tmp /* >= 34 ints */) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
+  const int per = (n + T - 1) / T;
+  const int b = min(tid * per, n), e = min(b + per, n);
+  int s = 0;
+  for (int i = b; i < e; i++) s += a[i];
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) tmp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int v = lane < (T >> 5) ? tmp[lane] : 0;
+    int inc2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc2, o);
+      if (lane >= o) inc2 += t;
+    }
+    tmp[lane] = inc2 - v;
+    if (lane == 31) tmp[33] = inc2;
+  }
+  __syncthreads();
+  int base = tmp[wid] + incl - s;
+  for (int i = b; i < e; i++) {
+    const int t = a[i];
+    a[i] = base;
+    base += t;
+  }
+  const int total = tmp[33];
+  __syncthreads();
+  return total;
+}
+
+// The reference algorithm, restated level-synchronously:
+//  * a "full pass" splits every multi-key node; its result set is order independent;
+//  * the "sorted partial pass" walks multi-key nodes by (count, creation order) descending and
+//    stops the moment the list holds >= N nodes: each split's gain (non-empty children - 1) is
+//    independent of the others, so the stop position is a prefix-sum search;
+//  * every new node is pushed to the list front, so final list order == descending creation seq.
+// Canonical tie rule (the reference sorts by heap address): later-created node first.
+__global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uint2* __restrict__ cand,
+                                                         const int* __restrict__ candCount,
+                                                         unsigned short* __restrict__ keyNode,
+                                                         uint2* __restrict__ kept, int* __restrict__ keptCount,
+                                                         int candTotal, int keptTotal, int nodeCap,
+                                                         int* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char qsm[];
+  __shared__ int s_tmp[34];
+  __shared__ int s_nc, s_nexp, s_cut, s_roots;
+  const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  const LevelGeom& L = g.lv[l];
+  int n = candCount[f * g.nlevels + l];
+  if (n > L.candCap) {
+    n = L.candCap;
+    if (tid == 0) atomicOr(overflow, 1);
+  }
+  if (n == 0) {
+    if (tid == 0) keptCount[f * g.nlevels + l] = 0;
+    return;
+  }
+  const uint2* C = cand + (size_t)f * candTotal + L.candOff;
+  unsigned short* KN = keyNode + (size_t)f * candTotal + L.candOff;
+  uint2* K = kept + (size_t)f * keptTotal + L.keptOff;
+
+  QtNode* nodes = (QtNode*)qsm;
+  QtNode* nodes2 = nodes + nodeCap;
+  int* childCnt = (int*)(nodes2 + nodeCap);
+  int* childIdx = childCnt + 4 * nodeCap;
+  int* slot = childIdx + 4 * nodeCap;
+  int* nodeRank = slot + nodeCap;
+  int* candList = nodeRank + nodeCap;
+  int* byRank = candList + nodeCap;
+  unsigned long long* key64 = (unsigned long long*)(byRank + nodeCap);
+
+  const int N = L.nfeat;
+  const int nIni = L.nIni;
+  const float hX = L.hX;
+  const int Hp = L.h - 32;
+
+  // roots (:700-741); empty roots are erased (:745-763)
+  if (tid < nIni) {
+    QtNode r;
+    r.x0 = (short)(int)__fmul_rn(hX, (float)tid);
+    r.x1 = (short)(int)__fmul_rn(hX, (float)(tid + 1));
+    r.y0 = 0;
+    r.y1 = (short)Hp;
+    r.count = 0;
+    r.seq = nIni - 1 - tid;
+    nodes[tid] = r;
+  }
+  __syncthreads();
+  for (int k = tid; k < n; k += kQtThreads) {
+    const int xr = (int)(C[k].x & 0xffffu) - 16;
+    int r = (int)__fdiv_rn((float)xr, hX);
+    r = min(max(r, 0), nIni - 1);
+    KN[k] = (unsigned short)r;
+    atomicAdd(&nodes[r].count, 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int m = 0;
+    for (int i = 0; i < nIni; i++) {
+      if (nodes[i].count > 0) { slot[i] = m; nodes2[m++] = nodes[i]; }
+      else slot[i] = -1;
+    }
+    s_roots = m;
+  }
+  __syncthreads();
+  for (int k = tid; k < n; k += kQtThreads) KN[k] = (unsigned short)slot[KN[k]];
+  int numNodes = s_roots;
+  { QtNode* t = nodes; nodes = nodes2; nodes2 = t; }
+  int seqCounter = nIni;
+  bool partial = false;
+  __syncthreads();
+
+  for (;;) {
+    const int prev = numNodes;
+    for (int i = tid; i < 4 * numNodes; i += kQtThreads) childCnt[i] = 0;
+    if (tid == 0) { s_nc = 0; s_nexp = 0; s_cut = 0x7fffffff; }
+    __syncthreads();
+    for (int i = tid; i < numNodes; i += kQtThreads) {
+      slot[i] = 1;
+      nodeRank[i] = -1;
+      if (nodes[i].count > 1) candList[atomicAdd(&s_nc, 1)] = i;
+    }
+    for (int k = tid; k < n; k += kQtThreads) {
+      const int nd = KN[k];
+      const QtNode Nd = nodes[nd];
+      if (Nd.count > 1) {
+        const unsigned xy = C[k].x;
+        atomicAdd(&childCnt[4 * nd + qt_quadrant((int)(xy & 0xffffu) - 16, (int)(xy >> 16) - 16, Nd)], 1);
+      }
+    }
+    __syncthreads();
+    const int nc = s_nc;
+    if (nc == 0) break;  // nothing left to split: list size unchanged (:890)
+    for (int i = tid; i < nc; i += kQtThreads) {
+      const QtNode& Nd = nodes[candList[i]];
+      key64[i] = (partial ? ((unsigned long long)(unsigned)Nd.count << 32) : 0ull) | (unsigned)Nd.seq;
+    }
+    __syncthreads();
+    for (int i = tid; i < nc; i += kQtThreads) {
+      const unsigned long long ki = key64[i];
+      int r = 0;
+      for (int j = 0; j < nc; j++) r += key64[j] > ki;
+      const int nd = candList[i];
+      const int ne = (childCnt[4 * nd] > 0) + (childCnt[4 * nd + 1] > 0) + (childCnt[4 * nd + 2] > 0) + (childCnt[4 * nd + 3] > 0);
+      nodeRank[nd] = r;
+      byRank[r] = ne - 1;
+    }
+    __syncthreads();
+    int cut = nc - 1;
+    if (partial) {
+      // first rank at which the running list size reaches N (:982)
+      if (tid < 32) {
+        int running = numNodes;
+        for (int base = 0; base < nc; base += 32) {
+          const int v = base + tid < nc ? byRank[base + tid] : 0;
+          int incl = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += t;
+          }
+          const unsigned hit = __ballot_sync(0xffffffffu, base + tid < nc && running + incl >= N);
+          if (hit) {
+            if (tid == 0) s_cut = base + __ffs(hit) - 1;
+            break;
+          }
+          running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
+      __syncthreads();
+      cut = min(s_cut, nc - 1);
+    }
+    for (int i = tid; i < nc; i += kQtThreads) {
+      const int nd = candList[i];
+      if (nodeRank[nd] <= cut) slot[nd] = byRank[nodeRank[nd]] + 1;
+      else nodeRank[nd] = -1;
+    }
+    __syncthreads();
+    const int total = block_scan_excl(slot, numNodes, s_tmp);
+    for (int i = tid; i < numNodes; i += kQtThreads) {
+      const QtNode Nd = nodes[i];
+      const int base = slot[i], r = nodeRank[i];
+      if (r < 0) {
+        nodes2[base] = Nd;
+      } else {
+        const int mx = Nd.x0 + ((Nd.x1 - Nd.x0 + 1) >> 1), my = Nd.y0 + ((Nd.y1 - Nd.y0 + 1) >> 1);
+        int j = 0, nexp = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int c = childCnt[4 * i + q];
+          if (c > 0) {
+            QtNode ch;
+            ch.x0 = (q & 1) ? (short)mx : Nd.x0;
+            ch.x1 = (q & 1) ? Nd.x1 : (short)mx;
+            ch.y0 = (q & 2) ? (short)my : Nd.y0;
+            ch.y1 = (q & 2) ? Nd.y1 : (short)my;
+            ch.count = c;
+            ch.seq = seqCounter + 4 * r + q;
+            nodes2[base + j] = ch;
+            childIdx[4 * i + q] = base + j;
+            j++;
+            nexp += c > 1;
+          }
+        }
+        if (nexp) atomicAdd(&s_nexp, nexp);
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += kQtThreads) {
+      const int nd = KN[k];
+      if (nodeRank[nd] < 0) {
+        KN[k] = (unsigned short)slot[nd];
+      } else {
+        const unsigned xy = C[k].x;
+        KN[k] = (unsigned short)childIdx[4 * nd + qt_quadrant((int)(xy & 0xffffu) - 16, (int)(xy >> 16) - 16, nodes[nd])];
+      }
+    }
+    __syncthreads();
+    seqCounter += 4 * (cut + 1);
+    numNodes = total;
+    { QtNode* t = nodes; nodes = nodes2; nodes2 = t; }
+    const int nToExpand = s_nexp;
+    __syncthreads();
+    if (numNodes >= N || numNodes == prev) break;                 // :890, :987
+    if (!partial && numNodes + 3 * nToExpand > N) partial = true;  // :908
+  }
+
+  // best response per node, earliest candidate wins ties (:1004-1029); the reference's
+  // candidate order (cell-row-major, row-major inside a cell) is a function of (x,y).
+  for (int i = tid; i < numNodes; i += kQtThreads) key64[i] = 0ull;
+  __syncthreads();
+  for (int k = tid; k < n; k += kQtThreads) {
+    const uint2 c = C[k];
+    const int x = (int)(c.x & 0xffffu) - kEdge, y = (int)(c.x >> 16) - kEdge;
+    const int ci = y / L.hCell, cj = x / L.wCell;
+    const unsigned ord = (unsigned)(((ci * L.nColsAll + cj) * L.hCell + (y - ci * L.hCell)) * L.wCell + (x - cj * L.wCell));
+    const unsigned long long pk = ((unsigned long long)c.y << 56) | ((unsigned long long)(0x7fffffffu - ord) << 24) | (unsigned)k;
+    atomicMax(&key64[KN[k]], pk);
+  }
+  __syncthreads();
+  for (int i = tid; i < numNodes; i += kQtThreads) {
+    const int s = nodes[i].seq;
+    int r = 0;
+    for (int j = 0; j < numNodes; j++) r += nodes[j].seq > s;
+    if (r < L.keptCap) K[r] = C[(int)(key64[i] & 0xffffffu)];
+  }
+  if (tid == 0) {
+    keptCount[f * g.nlevels + l] = min(numNodes, L.keptCap);
+    if (numNodes > L.keptCap) atomicOr(overflow, 2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 7x7 sigma=2 Gaussian blur, OpenCV 4.x 8-bit fixed-point path: k = [18,34,48,56,48,34,18]/256
+// horizontally into u16, vertically (+32768)>>16. Reads the bordered plane, whose border IS the
+// REFLECT_101 content the reference's blur of the clone() re-synthesises.
+// ------------------------------------------------------------------------------------------
+constexpr int kBlurTW = 64, kBlurTH = 32;
+
+__global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
+                                               u8* __restrict__ blur, size_t blurStride) {
+  __shared__ u8 in[(kBlurTH + 6) * (kBlurTW + 8)];
+  __shared__ unsigned short hs[(kBlurTH + 6) * kBlurTW];
+  const int f = blockIdx.y;
+  int l = 0;
+#pragma unroll 1
+  while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blurTileBase) l++;
+  const LevelGeom& L = g.lv[l];
+  const int t = blockIdx.x - L.blurTileBase;
+  const int ty = t / L.blurTilesX, tx = t - ty * L.blurTilesX;
+  const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
+  const u8* src = pyr + (size_t)f * pyrStride + L.off;
+  constexpr int IW = kBlurTW + 6, IP = kBlurTW + 8;
+  for (int i = threadIdx.x; i < IW * (kBlurTH + 6); i += 256) {
+    const int r = i / IW, c = i - r * IW;
+    const int y = min(y0 + r - 3, L.h + 2), x = min(x0 + c - 3, L.w + 2);  // stay inside the border
+    in[r * IP + c] = src[(long long)y * L.pitch + x];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBlurTW * (kBlurTH + 6); i += 256) {
+    const int r = i / kBlurTW, c = i - r * kBlurTW;
+    const u8* p = in + r * IP + c;
+    hs[i] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+  }
+  __syncthreads();
+  u8* dst = blur + (size_t)f * blurStride + L.boff;
+  for (int i = threadIdx.x; i < kBlurTW * kBlurTH; i += 256) {
+    const int r = i / kBlurTW, c = i - r * kBlurTW;
+    const int x = x0 + c, y = y0 + r;
+    if (x < L.w && y < L.h) {
+      const unsigned short* p = hs + r * kBlurTW + c;
+      const unsigned acc = 32768u + 18u * (p[0] + p[6 * kBlurTW]) + 34u * (p[kBlurTW] + p[5 * kBlurTW]) +
+                           48u * (p[2 * kBlurTW] + p[4 * kBlurTW]) + 56u * p[3 * kBlurTW];
+      dst[(long long)y * L.bpitch + x] = (u8)(acc >> 16);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Orientation + descriptor + output record, one warp per kept keypoint
+// ------------------------------------------------------------------------------------------
+// cv::fastAtan2 (float polynomial, no FMA contraction).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float s = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s;
+  const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0.f) a = __fsub_rn(180.f, a);
+  if (y < 0.f) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+__global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
+                                                  const u8* __restrict__ blur, size_t blurStride,
+                                                  const uint2* __restrict__ kept, const int* __restrict__ keptCount,
+                                                  int keptTotal, const signed char* __restrict__ pattern,
+                                                  orb_keypoint* __restrict__ outK, u8* __restrict__ outD,
+                                                  int* __restrict__ outN, int cap, int* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int slotIdx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int f = blockIdx.y;
+  // concatenate levels in ascending octave (:1585-1645)
+  int l = -1, j = 0, total = 0;
+  for (int q = 0; q < g.nlevels; q++) {
+    const int c = keptCount[f * g.nlevels + q];
+    if (l < 0 && slotIdx < total + c) { l = q; j = slotIdx - total; }
+    total += c;
+  }
+  if (slotIdx == 0 && lane == 0) {
+    outN[f] = min(total, cap);
+    if (total > cap) atomicOr(overflow, 4);
+  }
+  if (l < 0 || slotIdx >= cap) return;
+  const LevelGeom& L = g.lv[l];
+  const uint2 rec = kept[(size_t)f * keptTotal + L.keptOff + j];
+  const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
+
+  // IC_Angle: lanes span u in [-15,15], loop over rows v; |u| <= umax[|v|]
+  const u8* c = pyr + (size_t)f * pyrStride + L.off + (long long)y * L.pitch + x;
+  const int u = lane - kHalfPatch;
+  int m10 = 0, m01 = 0;
+#pragma unroll 1
+  for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+    const int d = c_umax[v < 0 ? -v : v];
+    if (lane < 31 && u >= -d && u <= d) {
+      const int val = c[(long long)v * L.pitch + u];
+      m10 += u * val;
+      m01 += v * val;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  }
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+  // steered BRIEF on the blurred level; lane i produces descriptor byte i
+  const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+  const u8* cb = blur + (size_t)f * blurStride + L.boff + (long long)y * L.bpitch + x;
+  const int4* pp = reinterpret_cast<const int4*>(pattern) + lane * 2;
+  const int4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+  const int words[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+  int val = 0;
+#pragma unroll
+  for (int bit = 0; bit < 8; bit++) {
+    const int wd = words[bit];
+    const float x0 = (float)(signed char)(wd & 0xff), y0 = (float)(signed char)((wd >> 8) & 0xff);
+    const float x1 = (float)(signed char)((wd >> 16) & 0xff), y1 = (float)(signed char)((wd >> 24) & 0xff);
+    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+    const int t0 = cb[(long long)r0 * L.bpitch + c0], t1 = cb[(long long)r1 * L.bpitch + c1];
+    val |= (t0 < t1) << bit;
+  }
+  const size_t o = (size_t)f * cap + slotIdx;
+  outD[o * 32 + lane] = (u8)val;
+  if (lane == 0) {
+    orb_keypoint kp;
+    kp.x = l ? __fmul_rn((float)x, L.scale) : (float)x;
+    kp.y = l ? __fmul_rn((float)y, L.scale) : (float)y;
+    kp.size = L.patch;
+    kp.angle = angle;
+    kp.response = (float)rec.y;
+    kp.octave = l;
+    kp.class_id = -1;
+    outK[o] = kp;
+  }
+}
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+}  // namespace
+
+// ==========================================================================================
+// Host side
+// ==========================================================================================
+struct orb_extractor {
+  orb_params p;
+  int device = 0;
+  int maxBatch = 1;
+  std::vector<float> scale, invScale, sigma2, invSigma2;
+  std::vector<int> perLevel;
+  cudaStream_t stream = nullptr;
+
+  // geometry of the current image size
+  Geom g;
+  bool haveGeom = false;
+  size_t pyrStride = 0, blurStride = 0;
+  int candTotal = 0, keptTotal = 0, nodeCap = 0, maxKp = 0;
+  size_t fastSmem = 0, qtSmem = 0;
+  std::vector<int2> taps;
+
+  // device workspace (sized for maxBatch frames of the current geometry)
+  u8* d_pyr = nullptr; u8* d_blur = nullptr;
+  uint2* d_cand = nullptr; int* d_candCount = nullptr; unsigned short* d_keyNode = nullptr;
+  uint2* d_kept = nullptr; int* d_keptCount = nullptr; int2* d_taps = nullptr;
+  signed char* d_pattern = nullptr; int* d_overflow = nullptr;
+  int wsFrames = 0;
+  // staging for the host entry points
+  u8* d_in = nullptr; size_t d_inBytes = 0;
+  orb_keypoint* d_kps = nullptr; u8* d_desc = nullptr; int* d_n = nullptr; int stageFrames = 0, stageCap = 0;
+  std::vector<u8> hostPyr;
+  int lastLaunches = 0;
+  int lastChunkFrames = 0;
+};
+
+namespace {
+
+void build_tables(orb_extractor* e) {
+  // ORBextractor.cc:469-526. scaleFactor is a double member initialised from the float argument.
+  const int nl = e->p.nlevels;
+  const double sf = (double)e->p.scale_factor;
+  e->scale.assign(nl, 1.0f);
+  e->sigma2.assign(nl, 1.0f);
+  for (int i = 1; i < nl; i++) {
+    e->scale[i] = (float)((double)e->scale[i - 1] * sf);
+    e->sigma2[i] = e->scale[i] * e->scale[i];
+  }
+  e->invScale.resize(nl);
+  e->invSigma2.resize(nl);
+  for (int i = 0; i < nl; i++) {
+    e->invScale[i] = 1.0f / e->scale[i];
+    e->invSigma2[i] = 1.0f / e->sigma2[i];
+  }
+  e->perLevel.assign(nl, 0);
+  const float factor = (float)(1.0 / sf);
+  float want = (float)e->p.nfeatures * (1.0f - factor) / (1.0f - (float)std::pow((double)factor, (double)nl));
+  int sum = 0;
+  for (int l = 0; l < nl - 1; l++) {
+    e->perLevel[l] = cv_round_f(want);
+    sum += e->perLevel[l];
+    want *= factor;
+  }
+  e->perLevel[nl - 1] = std::max(e->p.nfeatures - sum, 0);
+}
+
+// resize taps of cv::resize INTER_LINEAR 8-bit (OpenCV 4.x): see DESIGN.md / SURVEY A.2
+void make_taps(int dsize, int ssize, int2* out) {
+  const double scale = 1.0 / ((double)dsize / (double)ssize);
+  for (int d = 0; d < dsize; d++) {
+    float fx = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)std::floor(fx);
+    fx -= (float)s;
+    if (s < 0) { s = 0; fx = 0.f; }
+    if (s >= ssize - 1) { s = ssize - 1; fx = 0.f; }
+    const int c0 = cv_round_f((1.f - fx) * 2048.f), c1 = cv_round_f(fx * 2048.f);
+    out[d].x = s;
+    out[d].y = (c0 & 0xffff) | (c1 << 16);
+  }
+}
+
+int build_geom(orb_extractor* e, int W, int H) {
+  Geom& g = e->g;
+  memset(&g, 0, sizeof g);
+  const int nl = e->p.nlevels;
+  g.nlevels = nl; g.W = W; g.H = H; g.iniTh = e->p.ini_th_fast; g.minTh = e->p.min_th_fast;
+  long long pyrOff = 0, blurOff = 0;
+  int candOff = 0, keptOff = 0, cellBase = 0, blurBase = 0, tapOff = 0;
+  int nodeCap = 0, maxCw = 0, maxCh = 0, maxKp = 0;
+  e->taps.clear();
+  for (int l = 0; l < nl; l++) {
+    LevelGeom& L = g.lv[l];
+    L.w = cv_round_f((float)W * e->invScale[l]);   // :1663
+    L.h = cv_round_f((float)H * e->invScale[l]);
+    if (L.w > 32000 || L.h > 32000) ORB_FAIL(ORB_ERR_UNSUPPORTED, "image larger than 32000 px per side");
+    const int Wp = L.w - 32, Hp = L.h - 32;        // detection window size (:1052-1060)
+    if (Wp < 30 || Hp < 30) ORB_FAIL(ORB_ERR_UNSUPPORTED, "a pyramid level is smaller than one 30-px FAST cell (the reference divides by zero)");
+    L.pitch = round_up(kLeftPad + L.w + kEdge, 32);
+    L.off = pyrOff + (long long)kEdge * L.pitch + kLeftPad;
+    pyrOff += round_up((long long)L.pitch * (L.h + 2 * kEdge), 256LL);
+    L.bpitch = round_up(L.w, 32);
+    L.boff = blurOff;
+    blurOff += round_up((long long)L.bpitch * L.h, 256LL);
+    const float width = (float)Wp, height = (float)Hp;
+    const int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);
+    L.wCell = (int)std::ceil(width / (float)nCols);
+    L.hCell = (int)std::ceil(height / (float)nRows);
+    L.nColsAll = nCols;
+    L.nCols = 0; L.nRows = 0;
+    for (int j = 0; j < nCols; j++) if (16 + j * L.wCell < (L.w - 16) - 6) L.nCols = j + 1;  // :1083
+    for (int i = 0; i < nRows; i++) if (16 + i * L.hCell < (L.h - 16) - 3) L.nRows = i + 1;  // :1101
+    L.cellBase = cellBase;
+    cellBase += L.nCols * L.nRows;
+    maxCw = std::max(maxCw, L.wCell); maxCh = std::max(maxCh, L.hCell);
+    L.nfeat = e->perLevel[l];
+    L.nIni = (int)std::round((float)Wp / (float)Hp);  // :695
+    if (L.nIni < 1) ORB_FAIL(ORB_ERR_UNSUPPORTED, "portrait aspect ratio > 2:1 (the reference divides by zero)");
+    L.hX = (float)Wp / (float)L.nIni;
+    L.candOff = candOff;
+    L.candCap = std::min(1 << 24, std::max(1024, (L.w * L.h) / 6));
+    candOff += round_up(L.candCap, 4);
+    L.keptOff = keptOff;
+    L.keptCap = std::max(L.nfeat + 3, 4 * L.nIni) + 1;
+    keptOff += round_up(L.keptCap, 4);
+    maxKp += L.keptCap;
+    nodeCap = std::max(nodeCap, L.keptCap + 3);
+    L.blurTileBase = blurBase;
+    L.blurTilesX = (L.w + kBlurTW - 1) / kBlurTW;
+    L.blurTilesY = (L.h + kBlurTH - 1) / kBlurTH;
+    blurBase += L.blurTilesX * L.blurTilesY;
+    L.scale = e->scale[l];
+    L.patch = (float)(int)(31.f * e->scale[l]);  // :1164
+    if (l > 0) {
+      L.tapX = tapOff; tapOff += L.w;
+      L.tapY = tapOff; tapOff += L.h;
+      e->taps.resize(tapOff);
+      make_taps(L.w, g.lv[l - 1].w, e->taps.data() + L.tapX);
+      make_taps(L.h, g.lv[l - 1].h, e->taps.data() + L.tapY);
+    }
+  }
+  g.totalCells = cellBase;
+  g.totalBlurTiles = blurBase;
+  e->pyrStride = (size_t)pyrOff;
+  e->blurStride = (size_t)blurOff;
+  e->candTotal = candOff;
+  e->keptTotal = keptOff;
+  e->nodeCap = round_up(nodeCap, 2);
+  e->maxKp = maxKp;
+  e->fastSmem = (size_t)((maxCw + 6 + 3) & ~3) * (maxCh + 6) + (size_t)(maxCw + 2) * (maxCh + 2);
+  e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8);
+  if (e->qtSmem > 220 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "features per level too large for the quadtree kernel's shared memory");
+  if (e->fastSmem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
+  return ORB_OK;
+}
+
+void free_workspace(orb_extractor* e) {
+  cudaFree(e->d_pyr); cudaFree(e->d_blur); cudaFree(e->d_cand); cudaFree(e->d_candCount);
+  cudaFree(e->d_keyNode); cudaFree(e->d_kept); cudaFree(e->d_keptCount); cudaFree(e->d_taps);
+  e->d_pyr = e->d_blur = nullptr; e->d_cand = nullptr; e->d_candCount = nullptr; e->d_keyNode = nullptr;
+  e->d_kept = nullptr; e->d_keptCount = nullptr; e->d_taps = nullptr;
+  e->wsFrames = 0;
+}
+
+int ensure_geom(orb_extractor* e, int W, int H, int frames) {
+  ORB_CUDA(cudaSetDevice(e->device));
+  const bool newGeom = !e->haveGeom || e->g.W != W || e->g.H != H;
+  if (newGeom) {
+    e->haveGeom = false;
+    int st = build_geom(e, W, H);
+    if (st) return st;
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    free_workspace(e);
+    ORB_CUDA(cudaMalloc(&e->d_taps, std::max<size_t>(1, e->taps.size()) * sizeof(int2)));
+    ORB_CUDA(cudaMemcpy(e->d_taps, e->taps.data(), e->taps.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    ORB_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qtSmem));
+    ORB_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->fastSmem));
+    e->haveGeom = true;
+  }
+  frames = std::min(frames, e->maxBatch);
+  if (frames > e->wsFrames) {
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    int2* keepTaps = e->d_taps; e->d_taps = nullptr;
+    free_workspace(e);
+    e->d_taps = keepTaps;
+    const size_t F = (size_t)frames;
+    ORB_CUDA(cudaMalloc(&e->d_pyr, F * e->pyrStride));
+    ORB_CUDA(cudaMalloc(&e->d_blur, F * e->blurStride));
+    ORB_CUDA(cudaMalloc(&e->d_cand, F * e->candTotal * sizeof(uint2)));
+    ORB_CUDA(cudaMalloc(&e->d_keyNode, F * e->candTotal * sizeof(unsigned short)));
+    ORB_CUDA(cudaMalloc(&e->d_candCount, F * kMaxLevels * sizeof(int)));
+    ORB_CUDA(cudaMalloc(&e->d_kept, F * e->keptTotal * sizeof(uint2)));
+    ORB_CUDA(cudaMalloc(&e->d_keptCount, F * kMaxLevels * sizeof(int)));
+    e->wsFrames = frames;
+  }
+  return ORB_OK;
+}
+
+// One chunk (<= wsFrames frames) through the whole pipeline, asynchronous on `s`.
+int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t frameStride, orb_keypoint* d_kps,
+              int cap, int* d_counts, u8* d_desc, cudaStream_t s) {
+  const Geom& g = e->g;
+  const int nl = g.nlevels;
+  int launches = 0;
+  {
+    const LevelGeom& L = g.lv[0];
+    dim3 grid((L.w + 2 * kEdge + 255) / 256, L.h + 2 * kEdge, B);
+    k_level0_border<<<grid, 256, 0, s>>>(g, d_img, step, frameStride, e->d_pyr, e->pyrStride);
+    launches++;
+  }
+  for (int l = 1; l < nl; l++) {
+    const LevelGeom& L = g.lv[l];
+    dim3 grid((L.w + 2 * kEdge + 255) / 256, L.h + 2 * kEdge, B);
+    k_resize_border<<<grid, 256, 0, s>>>(g, l, e->d_pyr, e->pyrStride, e->d_taps);
+    launches++;
+  }
+  ORB_CUDA(cudaMemsetAsync(e->d_candCount, 0, (size_t)B * nl * sizeof(int), s));
+  k_fast_cells<<<dim3(g.totalCells, B), 128, e->fastSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_cand, e->d_candCount,
+                                                              e->candTotal);
+  launches++;
+  k_quadtree<<<dim3(nl, B), kQtThreads, e->qtSmem, s>>>(g, e->d_cand, e->d_candCount, e->d_keyNode, e->d_kept,
+                                                       e->d_keptCount, e->candTotal, e->keptTotal, e->nodeCap,
+                                                       e->d_overflow);
+  launches++;
+  k_blur7<<<dim3(g.totalBlurTiles, B), 256, 0, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride);
+  launches++;
+  const int slots = std::min(cap, e->maxKp);
+  k_describe<<<dim3((slots * 32 + 255) / 256, B), 256, 0, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride,
+                                                              e->d_kept, e->d_keptCount, e->keptTotal, e->d_pattern,
+                                                              d_kps, d_desc, d_counts, cap, e->d_overflow);
+  launches++;
+  ORB_CUDA(cudaGetLastError());
+  e->lastLaunches += launches;
+  e->lastChunkFrames = B;
+  return ORB_OK;
+}
+
+int ensure_stage(orb_extractor* e, size_t inBytes, int frames, int cap) {
+  if (inBytes > e->d_inBytes) {
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_in);
+    e->d_in = nullptr;
+    ORB_CUDA(cudaMalloc(&e->d_in, inBytes));
+    e->d_inBytes = inBytes;
+  }
+  if ((size_t)frames * cap > (size_t)e->stageFrames * e->stageCap || frames > e->stageFrames) {
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_n);
+    e->d_kps = nullptr; e->d_desc = nullptr; e->d_n = nullptr;
+    ORB_CUDA(cudaMalloc(&e->d_kps, (size_t)frames * cap * sizeof(orb_keypoint)));
+    ORB_CUDA(cudaMalloc(&e->d_desc, (size_t)frames * cap * 32));
+    ORB_CUDA(cudaMalloc(&e->d_n, (size_t)frames * sizeof(int)));
+    e->stageFrames = frames;
+    e->stageCap = cap;
+  }
+  return ORB_OK;
+}
+
+int check_overflow(orb_extractor* e, cudaStream_t s) {
+  int flag = 0;
+  ORB_CUDA(cudaMemcpyAsync(&flag, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaStreamSynchronize(s));
+  if (flag) {
+    cudaMemsetAsync(e->d_overflow, 0, sizeof(int), s);
+    ORB_FAIL(ORB_ERR_CAPACITY, flag & 4 ? "keypoint output capacity too small" : "internal candidate/keypoint list overflow");
+  }
+  return ORB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* orb_last_error(void) { return g_last_error.c_str(); }
+
+int orb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int orb_create(const orb_params* params, int device, int max_batch, orb_extractor** out) {
+  if (!params || !out) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (params->nlevels < 1 || params->nlevels > kMaxLevels || params->nfeatures < 1 || !(params->scale_factor > 1.0f) ||
+      params->min_th_fast < 1 || params->ini_th_fast < params->min_th_fast || params->ini_th_fast > 254)
+    ORB_FAIL(ORB_ERR_INVALID, "bad extractor parameters");
+  *out = nullptr;
+  ORB_CUDA(cudaSetDevice(device));
+  orb_extractor* e = new orb_extractor();
+  e->p = *params;
+  e->device = device;
+  e->maxBatch = std::max(1, max_batch);
+  build_tables(e);
+  cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaMalloc(&e->d_pattern, sizeof ORB_BIT_PATTERN_31);
+  if (err == cudaSuccess) err = cudaMemcpy(e->d_pattern, ORB_BIT_PATTERN_31, sizeof ORB_BIT_PATTERN_31, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMalloc(&e->d_overflow, sizeof(int));
+  if (err == cudaSuccess) err = cudaMemset(e->d_overflow, 0, sizeof(int));
+  if (err != cudaSuccess) {
+    delete e;
+    return cuda_fail(err, "orb_create", __FILE__, __LINE__);
+  }
+  *out = e;
+  return ORB_OK;
+}
+
+int orb_destroy(orb_extractor* e) {
+  if (!e) return ORB_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  free_workspace(e);
+  cudaFree(e->d_taps); cudaFree(e->d_pattern); cudaFree(e->d_overflow);
+  cudaFree(e->d_in); cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_n);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return ORB_OK;
+}
+
+int orb_get_scale_tables(const orb_extractor* e, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                         int32_t* per_level) {
+  if (!e) ORB_FAIL(ORB_ERR_INVALID, "null handle");
+  for (int l = 0; l < e->p.nlevels; l++) {
+    if (scale) scale[l] = e->scale[l];
+    if (inv_scale) inv_scale[l] = e->invScale[l];
+    if (sigma2) sigma2[l] = e->sigma2[l];
+    if (inv_sigma2) inv_sigma2[l] = e->invSigma2[l];
+    if (per_level) per_level[l] = e->perLevel[l];
+  }
+  return ORB_OK;
+}
+
+int orb_max_keypoints(const orb_extractor* e) {
+  if (!e) return 0;
+  // nfeatures + 3 per level, and at least 4 roots' worth per level (<= 16 children on the first pass)
+  int m = 0;
+  for (int l = 0; l < e->p.nlevels; l++) m += std::max(e->perLevel[l] + 3, 16) + 1;
+  return m;
+}
+
+int orb_extract_batch_device(orb_extractor* e, const uint8_t* d_images, int batch, int width, int height, size_t step,
+                             size_t frame_stride, orb_keypoint* d_keypoints, int capacity, int32_t* d_counts,
+                             uint8_t* d_descriptors, void* stream) {
+  if (!e || !d_images || !d_keypoints || !d_counts || !d_descriptors) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (batch <= 0 || width <= 0 || height <= 0 || capacity <= 0 || step < (size_t)width) ORB_FAIL(ORB_ERR_INVALID, "bad size");
+  int st = ensure_geom(e, width, height, batch);
+  if (st) return st;
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  e->lastLaunches = 0;
+  for (int b0 = 0; b0 < batch; b0 += e->wsFrames) {
+    const int B = std::min(e->wsFrames, batch - b0);
+    st = run_chunk(e, d_images + (size_t)b0 * frame_stride, B, step, frame_stride, d_keypoints + (size_t)b0 * capacity,
+                   capacity, d_counts + b0, d_descriptors + (size_t)b0 * capacity * 32, s);
+    if (st) return st;
+  }
+  return ORB_OK;
+}
+
+int orb_synchronize(orb_extractor* e, void* stream) {
+  if (!e) ORB_FAIL(ORB_ERR_INVALID, "null handle");
+  ORB_CUDA(cudaSetDevice(e->device));
+  return check_overflow(e, stream ? (cudaStream_t)stream : e->stream);
+}
+
+int orb_last_launch_count(const orb_extractor* e) { return e ? e->lastLaunches : 0; }
+
+int orb_extract_batch_host(orb_extractor* e, const uint8_t* images, int batch, int width, int height, size_t step,
+                           size_t frame_stride, orb_keypoint* keypoints, int capacity, int32_t* counts,
+                           uint8_t* descriptors) {
+  if (!e || !images || !keypoints || !counts || !descriptors) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (batch <= 0 || width <= 0 || height <= 0 || capacity <= 0 || step < (size_t)width) ORB_FAIL(ORB_ERR_INVALID, "bad size");
+  int st = ensure_geom(e, width, height, batch);
+  if (st) return st;
+  const int chunk = e->wsFrames;
+  const size_t dFrame = (size_t)width * height;
+  st = ensure_stage(e, dFrame * chunk, chunk, capacity);
+  if (st) return st;
+  cudaStream_t s = e->stream;
+  e->lastLaunches = 0;
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int B = std::min(chunk, batch - b0);
+    if (step == (size_t)width && frame_stride == dFrame) {
+      ORB_CUDA(cudaMemcpyAsync(e->d_in, images + (size_t)b0 * frame_stride, dFrame * B, cudaMemcpyHostToDevice, s));
+    } else {
+      for (int b = 0; b < B; b++)
+        ORB_CUDA(cudaMemcpy2DAsync(e->d_in + (size_t)b * dFrame, width, images + (size_t)(b0 + b) * frame_stride, step,
+                                   width, height, cudaMemcpyHostToDevice, s));
+    }
+    st = run_chunk(e, e->d_in, B, width, dFrame, e->d_kps, capacity, e->d_n, e->d_desc, s);
+    if (st) return st;
+    ORB_CUDA(cudaMemcpyAsync(counts + b0, e->d_n, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(keypoints + (size_t)b0 * capacity, e->d_kps, (size_t)B * capacity * sizeof(orb_keypoint),
+                             cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(descriptors + (size_t)b0 * capacity * 32, e->d_desc, (size_t)B * capacity * 32,
+                             cudaMemcpyDeviceToHost, s));
+  }
+  return check_overflow(e, s);
+}
+
+int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, size_t step, orb_keypoint* keypoints,
+                int capacity, int* n, uint8_t* descriptors, orb_level_view* pyramid) {
+  if (!e || !n) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (!image || width == 0 || height == 0) return ORB_OK;  // empty image: outputs untouched (:1537)
+  if (!keypoints || !descriptors || capacity <= 0) ORB_FAIL(ORB_ERR_INVALID, "null output");
+  int st = ensure_geom(e, width, height, 1);
+  if (st) return st;
+  const size_t dFrame = (size_t)width * height;
+  st = ensure_stage(e, dFrame, 1, capacity);
+  if (st) return st;
+  cudaStream_t s = e->stream;
+  e->lastLaunches = 0;
+  ORB_CUDA(cudaMemcpy2DAsync(e->d_in, width, image, step, width, height, cudaMemcpyHostToDevice, s));
+  st = run_chunk(e, e->d_in, 1, width, dFrame, e->d_kps, capacity, e->d_n, e->d_desc, s);
+  if (st) return st;
+  int cnt = 0;
+  ORB_CUDA(cudaMemcpyAsync(&cnt, e->d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (pyramid) {
+    e->hostPyr.resize(e->pyrStride);
+    ORB_CUDA(cudaMemcpyAsync(e->hostPyr.data(), e->d_pyr, e->pyrStride, cudaMemcpyDeviceToHost, s));
+  }
+  ORB_CUDA(cudaStreamSynchronize(s));
+  if (cnt > 0) {
+    ORB_CUDA(cudaMemcpyAsync(keypoints, e->d_kps, (size_t)cnt * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(descriptors, e->d_desc, (size_t)cnt * 32, cudaMemcpyDeviceToHost, s));
+  }
+  st = check_overflow(e, s);
+  if (st) return st;
+  *n = cnt;
+  if (pyramid)
+    for (int l = 0; l < e->g.nlevels; l++) {
+      pyramid[l].data = e->hostPyr.data() + e->g.lv[l].off;
+      pyramid[l].width = e->g.lv[l].w;
+      pyramid[l].height = e->g.lv[l].h;
+      pyramid[l].step = e->g.lv[l].pitch;
+    }
+  return ORB_OK;
+}
+
+// ---- stage access (parity tests) ---------------------------------------------------------
+int orb_stage_level_size(const orb_extractor* e, int level, int* width, int* height) {
+  if (!e || !e->haveGeom || level < 0 || level >= e->g.nlevels) ORB_FAIL(ORB_ERR_INVALID, "no geometry / bad level");
+  *width = e->g.lv[level].w;
+  *height = e->g.lv[level].h;
+  return ORB_OK;
+}
+
+static int stage_check(const orb_extractor* e, int frame, int level) {
+  if (!e || !e->haveGeom || level < 0 || level >= e->g.nlevels || frame < 0 || frame >= e->lastChunkFrames)
+    ORB_FAIL(ORB_ERR_INVALID, "no geometry / bad frame or level");
+  return ORB_OK;
+}
+
+int orb_stage_copy_level(orb_extractor* e, int frame, int level, uint8_t* dst) {
+  int st = stage_check(e, frame, level);
+  if (st) return st;
+  ORB_CUDA(cudaSetDevice(e->device));
+  ORB_CUDA(cudaDeviceSynchronize());
+  const LevelGeom& L = e->g.lv[level];
+  const u8* src = e->d_pyr + (size_t)frame * e->pyrStride + L.off - (long long)kEdge * L.pitch - kEdge;
+  ORB_CUDA(cudaMemcpy2D(dst, L.w + 2 * kEdge, src, L.pitch, L.w + 2 * kEdge, L.h + 2 * kEdge, cudaMemcpyDeviceToHost));
+  return ORB_OK;
+}
+
+int orb_stage_copy_blur(orb_extractor* e, int frame, int level, uint8_t* dst) {
+  int st = stage_check(e, frame, level);
+  if (st) return st;
+  ORB_CUDA(cudaSetDevice(e->device));
+  ORB_CUDA(cudaDeviceSynchronize());
+  const LevelGeom& L = e->g.lv[level];
+  ORB_CUDA(cudaMemcpy2D(dst, L.w, e->d_blur + (size_t)frame * e->blurStride + L.boff, L.bpitch, L.w, L.h,
+                        cudaMemcpyDeviceToHost));
+  return ORB_OK;
+}
+
+static int copy_list(orb_extractor* e, const uint2* d_list, int cnt, int32_t* xs, int32_t* ys, int32_t* score,
+                     int capacity) {
+  const int m = std::min(cnt, capacity);
+  if (m <= 0) return ORB_OK;
+  std::vector<uint2> tmp(m);
+  ORB_CUDA(cudaMemcpy(tmp.data(), d_list, (size_t)m * sizeof(uint2), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < m; i++) {
+    xs[i] = (int)(tmp[i].x & 0xffffu);
+    ys[i] = (int)(tmp[i].x >> 16);
+    score[i] = (int)tmp[i].y;
+  }
+  return ORB_OK;
+}
+
+int orb_stage_copy_candidates(orb_extractor* e, int frame, int level, int32_t* xs, int32_t* ys, int32_t* score,
+                              int capacity, int* n) {
+  int st = stage_check(e, frame, level);
+  if (st) return st;
+  ORB_CUDA(cudaSetDevice(e->device));
+  ORB_CUDA(cudaDeviceSynchronize());
+  int cnt = 0;
+  ORB_CUDA(cudaMemcpy(&cnt, e->d_candCount + frame * e->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  cnt = std::min(cnt, e->g.lv[level].candCap);
+  *n = cnt;
+  return copy_list(e, e->d_cand + (size_t)frame * e->candTotal + e->g.lv[level].candOff, cnt, xs, ys, score, capacity);
+}
+
+int orb_stage_copy_kept(orb_extractor* e, int frame, int level, int32_t* xs, int32_t* ys, int32_t* score, int capacity,
+                        int* n) {
+  int st = stage_check(e, frame, level);
+  if (st) return st;
+  ORB_CUDA(cudaSetDevice(e->device));
+  ORB_CUDA(cudaDeviceSynchronize());
+  int cnt = 0;
+  ORB_CUDA(cudaMemcpy(&cnt, e->d_keptCount + frame * e->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  *n = cnt;
+  return copy_list(e, e->d_kept + (size_t)frame * e->keptTotal + e->g.lv[level].keptOff, cnt, xs, ys, score, capacity);
+}
+
+}  // extern "C"

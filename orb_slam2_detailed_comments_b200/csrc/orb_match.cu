@@ -1,0 +1,576 @@
+// orb_match.cu — B200 (sm_100a) implementation of the ORBmatcher hot path
+// (reference: src/ORBmatcher.cc:573-717 SearchForInitialization, :2035 ComputeThreeMaxima,
+//  :2083 DescriptorDistance; candidate window from src/Frame.cc:590-670).
+//
+// Integer-pipe work (LOP3 / POPC / IADD3 / VIMNMX); no tensor cores by design.
+//   k_match_pairs    one CTA per frame pair. The descriptors of frame 2 live in REGISTERS
+//                    (thread t owns candidates t, t+256, ...) together with their
+//                    vMatchedDistance state, so the sequential row walk of the reference
+//                    costs one broadcast load of the row + XOR/POPC + one block reduction.
+//   k_allpairs       one CTA per (row keyframe, column-keyframe span): row descriptors and
+//                    their running (best, second) in registers, column descriptors broadcast
+//                    from shared memory; no cross-thread reduction in the inner loop.
+//   k_hamming_matrix plain distance matrix (parity aid).
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+#include "orb_common.cuh"
+
+using namespace orbb200;
+
+namespace {
+
+constexpr int kMatchThreads = 256;
+constexpr int TH_LOW = 50;        // ORBmatcher.cc:49
+constexpr int HISTO_LENGTH = 30;  // ORBmatcher.cc:51
+constexpr unsigned kNoKey = 0xffffffffu;
+
+// 256-bit Hamming distance. Carry-save form: 7 words are compressed to (ones, twos, fours)
+// with 4 full adders (2 LOP3 each), so only 4 POPC are issued instead of 8.
+__device__ __forceinline__ int hamming8(const unsigned a[8], const unsigned b[8]) {
+#if defined(ORB_NAIVE_POPC)
+  int d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d += __popc(a[i] ^ b[i]);
+  return d;
+#else
+  const unsigned x0 = a[0] ^ b[0], x1 = a[1] ^ b[1], x2 = a[2] ^ b[2], x3 = a[3] ^ b[3];
+  const unsigned x4 = a[4] ^ b[4], x5 = a[5] ^ b[5], x6 = a[6] ^ b[6], x7 = a[7] ^ b[7];
+  const unsigned s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 ^ x1));
+  const unsigned s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 ^ x4));
+  const unsigned ones = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 ^ s2));
+  const unsigned twos = c1 ^ c2 ^ c3, fours = (c1 & c2) | (c3 & (c1 ^ c2));
+  return __popc(ones) + __popc(x7) + 2 * __popc(twos) + 4 * __popc(fours);
+#endif
+}
+
+// two smallest keys of the union of two (k1<=k2) pairs
+__device__ __forceinline__ void merge2(unsigned& k1, unsigned& k2, unsigned o1, unsigned o2) {
+  const unsigned hi = max(k1, o1);
+  k1 = min(k1, o1);
+  k2 = min(hi, min(k2, o2));
+}
+
+// ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2035-2077)
+__device__ void three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  ind1 = ind2 = ind3 = -1;
+  for (int i = 0; i < L; i++) {
+    const int s = histo[i];
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+  else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+}
+
+struct PairArgs {
+  // per-pair strides are implied: every frame holds n1 / n2 keypoints
+  const u8* desc1; const u8* desc2;       // pair p: desc1 + p*stride1*32 ...
+  const float* ang1; const float* ang2;
+  const float* xy1; const float* xy2;     // windowed mode only
+  const int* oct1; const int* oct2;       // windowed mode only
+  float* prev;                            // windowed mode: vbPrevMatched (in/out), n1 x 2
+  int n1, n2;
+  long long stride1, stride2;             // keypoints between consecutive pairs
+  float nnratio; int checkOri; int window;
+  float minX, minY, invW, invH;
+  int* matches12; int* nmatches; int* best; int* second;  // best/second optional
+};
+
+// dynamic smem: m12[n1] int, m21[n2] int, binOf[n1] u8 (4-byte padded)
+template <int CPT, bool WINDOWED>
+__global__ void __launch_bounds__(kMatchThreads) k_match_pairs(const PairArgs A) {
+  extern __shared__ __align__(16) int msm[];
+  __shared__ unsigned s_red[2][kMatchThreads / 32][2];
+  __shared__ int s_hist[HISTO_LENGTH];
+  __shared__ int s_nmatch;
+  __shared__ int s_keep[3];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p = blockIdx.x;
+  const int n1 = A.n1, n2 = A.n2;
+  int* m12 = msm;
+  int* m21 = msm + n1;
+  u8* binOf = (u8*)(m21 + n2);
+  const u8* D1 = A.desc1 + (size_t)p * A.stride1 * 32;
+  const u8* D2 = A.desc2 + (size_t)p * A.stride2 * 32;
+  const float* ang1 = A.ang1 + (size_t)p * A.stride1;
+  const float* ang2 = A.ang2 + (size_t)p * A.stride2;
+
+  // frame-2 descriptors + vMatchedDistance state into registers
+  unsigned b[CPT][8];
+  int md[CPT];
+  float cx[WINDOWED ? CPT : 1], cy[WINDOWED ? CPT : 1];
+  int cg[WINDOWED ? CPT : 1];
+#pragma unroll
+  for (int c = 0; c < CPT; c++) {
+    const int i2 = tid + c * kMatchThreads;
+    md[c] = INT_MAX;
+    if (i2 < n2) {
+      const uint4 lo = __ldg(reinterpret_cast<const uint4*>(D2 + (size_t)i2 * 32));
+      const uint4 hi = __ldg(reinterpret_cast<const uint4*>(D2 + (size_t)i2 * 32) + 1);
+      b[c][0] = lo.x; b[c][1] = lo.y; b[c][2] = lo.z; b[c][3] = lo.w;
+      b[c][4] = hi.x; b[c][5] = hi.y; b[c][6] = hi.z; b[c][7] = hi.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) b[c][k] = 0;
+      md[c] = -1;  // never a candidate: vMatchedDistance <= dist always
+    }
+    if (WINDOWED) {
+      cg[c] = -1;
+      cx[c] = cy[c] = 0.f;
+      if (i2 < n2) {
+        const float* xy2 = A.xy2 + (size_t)p * A.stride2 * 2;
+        const float x = xy2[2 * i2], y = xy2[2 * i2 + 1];
+        cx[c] = x; cy[c] = y;
+        // Frame::PosInGrid (Frame.cc:682-698) + level filter of GetFeaturesInArea(...,0,0)
+        const int gx = (int)roundf(__fmul_rn(__fsub_rn(x, A.minX), A.invW));
+        const int gy = (int)roundf(__fmul_rn(__fsub_rn(y, A.minY), A.invH));
+        const int o = (A.oct2 + (size_t)p * A.stride2)[i2];
+        if (gx >= 0 && gx < 64 && gy >= 0 && gy < 48 && o == 0) cg[c] = gx | (gy << 8);
+      }
+    }
+  }
+  for (int i = tid; i < n1; i += kMatchThreads) { m12[i] = -1; binOf[i] = 255; }
+  for (int i = tid; i < n2; i += kMatchThreads) m21[i] = -1;
+  if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) s_nmatch = 0;
+  __syncthreads();
+
+  const float factor = HISTO_LENGTH / 360.0f;  // this fork: ORBmatcher.cc:585-586
+  int nmatches = 0;                            // tracked by thread 0
+#pragma unroll 1
+  for (int i1 = 0; i1 < n1; i1++) {
+    int gx0 = 0, gx1 = 63, gy0 = 0, gy1 = 47;
+    float qx = 0.f, qy = 0.f, r2 = 0.f;
+    bool rowActive = true;
+    if (WINDOWED) {
+      // level1 > 0 -> continue (:599); Frame::GetFeaturesInArea cell range (Frame.cc:603-634)
+      const int o1 = (A.oct1 + (size_t)p * A.stride1)[i1];
+      const float* pv = A.prev + (size_t)p * A.stride1 * 2;
+      qx = pv[2 * i1]; qy = pv[2 * i1 + 1];
+      const float r = (float)A.window;
+      r2 = __fmul_rn(r, r);
+      gx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(qx, A.minX), r), A.invW)));
+      gx1 = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(qx, A.minX), r), A.invW)));
+      gy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(qy, A.minY), r), A.invH)));
+      gy1 = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(qy, A.minY), r), A.invH)));
+      rowActive = o1 <= 0 && gx0 < 64 && gx1 >= 0 && gy0 < 48 && gy1 >= 0;
+    }
+    unsigned k1 = kNoKey, k2 = kNoKey;
+    if (rowActive) {
+      const uint4 lo = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32));
+      const uint4 hi = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32) + 1);
+      const unsigned a[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+      for (int c = 0; c < CPT; c++) {
+        const int dist = hamming8(a, b[c]);
+        bool ok = md[c] > dist;  // vMatchedDistance[i2] <= dist -> skip (:627)
+        if (WINDOWED) {
+          const int gx = cg[c] & 0xff, gy = cg[c] >> 8;
+          const float dx = __fsub_rn(cx[c], qx), dy = __fsub_rn(cy[c], qy);
+          ok = ok && cg[c] >= 0 && gx >= gx0 && gx <= gx1 && gy >= gy0 && gy <= gy1 &&
+               __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < r2;  // circular window (Frame.cc:664)
+        }
+        const unsigned key = ok ? ((unsigned)dist << 16) | (unsigned)(tid + c * kMatchThreads) : kNoKey;
+        merge2(k1, k2, key, kNoKey);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+      merge2(k1, k2, o1, o2);
+    }
+    const int buf = i1 & 1;
+    if (lane == 0) { s_red[buf][wid][0] = k1; s_red[buf][wid][1] = k2; }
+    __syncthreads();
+    k1 = kNoKey; k2 = kNoKey;
+#pragma unroll
+    for (int w = 0; w < kMatchThreads / 32; w++) merge2(k1, k2, s_red[buf][w][0], s_red[buf][w][1]);
+    const int best = k1 == kNoKey ? INT_MAX : (int)(k1 >> 16);
+    const int second = k2 == kNoKey ? INT_MAX : (int)(k2 >> 16);
+    const int bestIdx = (int)(k1 & 0xffffu);
+    if (tid == 0 && A.best) {
+      A.best[(size_t)p * n1 + i1] = best;
+      A.second[(size_t)p * n1 + i1] = second;
+    }
+    if (best <= TH_LOW && (float)best < __fmul_rn((float)second, A.nnratio)) {  // :644-647
+#pragma unroll
+      for (int c = 0; c < CPT; c++)
+        if (bestIdx == tid + c * kMatchThreads) md[c] = best;  // vMatchedDistance[bestIdx2] = bestDist
+      if (tid == 0) {
+        const int prevOwner = m21[bestIdx];
+        if (prevOwner >= 0) { m12[prevOwner] = -1; nmatches--; }  // :650-654
+        m12[i1] = bestIdx;
+        m21[bestIdx] = i1;
+        nmatches++;
+        if (A.checkOri) {
+          float rot = __fsub_rn(ang1[i1], ang2[bestIdx]);
+          if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+          int bin = (int)roundf(__fmul_rn(rot, factor));
+          if (bin == HISTO_LENGTH) bin = 0;
+          if (bin >= 0 && bin < HISTO_LENGTH) { binOf[i1] = (u8)bin; s_hist[bin]++; }
+        }
+      }
+    }
+  }
+  if (tid == 0) {
+    s_nmatch = nmatches;
+    int a = -1, b2 = -1, c = -1;
+    if (A.checkOri) three_maxima(s_hist, HISTO_LENGTH, a, b2, c);
+    s_keep[0] = a; s_keep[1] = b2; s_keep[2] = c;
+  }
+  __syncthreads();
+  if (A.checkOri) {
+    int dropped = 0;
+    for (int i = tid; i < n1; i += kMatchThreads) {
+      const int bin = binOf[i];
+      if (bin != 255 && bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2] && m12[i] >= 0) {
+        m12[i] = -1;  // :692-706
+        dropped++;
+      }
+    }
+    if (dropped) atomicSub(&s_nmatch, dropped);
+  }
+  __syncthreads();
+  int* out12 = A.matches12 + (size_t)p * n1;
+  for (int i = tid; i < n1; i += kMatchThreads) {
+    const int m = m12[i];
+    out12[i] = m;
+    if (WINDOWED && m >= 0) {  // :712-714
+      float* pv = A.prev + (size_t)p * A.stride1 * 2;
+      const float* xy2 = A.xy2 + (size_t)p * A.stride2 * 2;
+      pv[2 * i] = xy2[2 * m];
+      pv[2 * i + 1] = xy2[2 * m + 1];
+    }
+  }
+  if (tid == 0) A.nmatches[p] = s_nmatch;
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int kApThreads = 256;
+
+// grid: (column spans, row keyframes). Rows of keyframe i in registers (RPT per thread), each
+// column keyframe's descriptors are staged in shared memory and broadcast.
+template <int RPT>
+__global__ void __launch_bounds__(kApThreads) k_allpairs(const u8* __restrict__ all, int nKF, int nDesc, int rowBegin,
+                                                         int colsPerBlock, float nnratio, int* __restrict__ counts) {
+  extern __shared__ __align__(16) uint4 bsm[];  // nDesc x 2 uint4
+  __shared__ int s_cnt[kApThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int i = rowBegin + blockIdx.y;
+  const int j0 = blockIdx.x * colsPerBlock, j1 = min(j0 + colsPerBlock, nKF);
+  unsigned a[RPT][8];
+#pragma unroll
+  for (int r = 0; r < RPT; r++) {
+    const int row = tid + r * kApThreads;
+    if (row < nDesc) {
+      const uint4* src = reinterpret_cast<const uint4*>(all + ((size_t)i * nDesc + row) * 32);
+      const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+      a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = lo.z; a[r][3] = lo.w;
+      a[r][4] = hi.x; a[r][5] = hi.y; a[r][6] = hi.z; a[r][7] = hi.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[r][k] = 0;
+    }
+  }
+  for (int j = j0; j < j1; j++) {
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(all + (size_t)j * nDesc * 32);
+    for (int t = tid; t < nDesc * 2; t += kApThreads) bsm[t] = __ldg(src + t);
+    __syncthreads();
+    int best[RPT], second[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; r++) { best[r] = INT_MAX; second[r] = INT_MAX; }
+#pragma unroll 2
+    for (int c = 0; c < nDesc; c++) {
+      const uint4 lo = bsm[2 * c], hi = bsm[2 * c + 1];
+      const unsigned bb[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+      for (int r = 0; r < RPT; r++) {
+        const int d = hamming8(a[r], bb);
+        second[r] = min(second[r], max(best[r], d));
+        best[r] = min(best[r], d);
+      }
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < RPT; r++)
+      if (tid + r * kApThreads < nDesc && best[r] <= TH_LOW && (float)best[r] < __fmul_rn((float)second[r], nnratio)) cnt++;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_cnt[wid] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < kApThreads / 32; w++) t += s_cnt[w];
+      counts[(size_t)blockIdx.y * nKF + j] = t;
+    }
+  }
+}
+
+__global__ void k_hamming_matrix(const u8* __restrict__ A, int na, const u8* __restrict__ B, int nb, int* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= nb) return;
+  const uint4* pa = reinterpret_cast<const uint4*>(A + (size_t)i * 32);
+  const uint4* pb = reinterpret_cast<const uint4*>(B + (size_t)j * 32);
+  const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+  const unsigned a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const unsigned b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  out[(size_t)i * nb + j] = hamming8(a, b);
+}
+
+// ---- integer pipe microbenchmarks (roofline denominators for matching) -------------------
+template <int WHAT>
+__global__ void __launch_bounds__(256) k_int_pipe(unsigned* out, int iters, unsigned seed) {
+  unsigned x0 = threadIdx.x ^ seed, x1 = x0 * 3u + 1u, x2 = x0 * 5u + 2u, x3 = x0 * 7u + 3u;
+  unsigned x4 = x0 * 11u + 4u, x5 = x0 * 13u + 5u, x6 = x0 * 17u + 6u, x7 = x0 * 19u + 7u;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (WHAT == 0) {  // POPC: 8 independent chains
+        x0 = __popc(x0) + seed; x1 = __popc(x1) + seed; x2 = __popc(x2) + seed; x3 = __popc(x3) + seed;
+        x4 = __popc(x4) + seed; x5 = __popc(x5) + seed; x6 = __popc(x6) + seed; x7 = __popc(x7) + seed;
+      } else {          // LOP3: 8 independent chains of a non-trivial 3-input function
+        x0 = (x0 & x1) ^ seed; x1 = (x1 & x2) ^ seed; x2 = (x2 & x3) ^ seed; x3 = (x3 & x4) ^ seed;
+        x4 = (x4 & x5) ^ seed; x5 = (x5 & x6) ^ seed; x6 = (x6 & x7) ^ seed; x7 = (x7 & x0) ^ seed;
+      }
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+}
+
+template <int CPT, bool W>
+int launch_match(const PairArgs& A, int pairs, size_t smem, cudaStream_t s) {
+  ORB_CUDA(cudaFuncSetAttribute(k_match_pairs<CPT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_match_pairs<CPT, W><<<pairs, kMatchThreads, smem, s>>>(A);
+  ORB_CUDA(cudaGetLastError());
+  return ORB_OK;
+}
+
+template <bool W>
+int dispatch_match(const PairArgs& A, int pairs, cudaStream_t s) {
+  const size_t smem = (size_t)(A.n1 + A.n2) * 4 + round_up((size_t)A.n1, (size_t)16);
+  if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints per frame for the matcher's shared memory");
+  const int cpt = (A.n2 + kMatchThreads - 1) / kMatchThreads;
+  if (cpt <= 1) return launch_match<1, W>(A, pairs, smem, s);
+  if (cpt <= 2) return launch_match<2, W>(A, pairs, smem, s);
+  if (cpt <= 4) return launch_match<4, W>(A, pairs, smem, s);
+  if (cpt <= 8) return launch_match<8, W>(A, pairs, smem, s);
+  if (cpt <= 12) return launch_match<12, W>(A, pairs, smem, s);
+  ORB_FAIL(ORB_ERR_UNSUPPORTED, "more than 3072 keypoints in frame 2");
+}
+
+}  // namespace
+
+struct orb_matcher {
+  int device = 0;
+  int maxPairs = 0, maxKp = 0;
+  cudaStream_t stream = nullptr;
+  // staging for the host single-pair entry point
+  u8* d_desc = nullptr; float* d_xy = nullptr; float* d_ang = nullptr; int* d_oct = nullptr;
+  float* d_prev = nullptr; int* d_m12 = nullptr; int* d_best = nullptr; int* d_second = nullptr; int* d_nm = nullptr;
+};
+
+extern "C" {
+
+int orb_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+  // ORBmatcher.cc:2083-2103 computes the same number with a SWAR popcount on 8 x 32 bits.
+  uint64_t x[4], y[4];
+  memcpy(x, a, 32);
+  memcpy(y, b, 32);
+  return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) + __builtin_popcountll(x[2] ^ y[2]) +
+         __builtin_popcountll(x[3] ^ y[3]);
+}
+
+int orb_matcher_create(int device, int max_pairs, int max_keypoints, orb_matcher** out) {
+  if (!out || max_keypoints <= 0) ORB_FAIL(ORB_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  ORB_CUDA(cudaSetDevice(device));
+  orb_matcher* m = new orb_matcher();
+  m->device = device;
+  m->maxPairs = std::max(1, max_pairs);
+  m->maxKp = max_keypoints;
+  const size_t K = (size_t)max_keypoints;
+  cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_desc, 2 * K * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_xy, 2 * K * 2 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_ang, 2 * K * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_oct, 2 * K * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_prev, K * 2 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_m12, K * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_best, K * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_second, K * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_nm, sizeof(int));
+  if (e != cudaSuccess) {
+    orb_matcher_destroy(m);
+    return cuda_fail(e, "orb_matcher_create", __FILE__, __LINE__);
+  }
+  *out = m;
+  return ORB_OK;
+}
+
+int orb_matcher_destroy(orb_matcher* m) {
+  if (!m) return ORB_OK;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  cudaFree(m->d_desc); cudaFree(m->d_xy); cudaFree(m->d_ang); cudaFree(m->d_oct); cudaFree(m->d_prev);
+  cudaFree(m->d_m12); cudaFree(m->d_best); cudaFree(m->d_second); cudaFree(m->d_nm);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return ORB_OK;
+}
+
+int orb_search_for_initialization(orb_matcher* m, const orb_frame_view* f1, const orb_frame_view* f2,
+                                  const orb_match_params* mp, float* prev_matched, int32_t* matches12, int* nmatches,
+                                  int32_t* best, int32_t* second) {
+  if (!m || !f1 || !f2 || !mp || !matches12 || !nmatches) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  const int n1 = f1->n, n2 = f2->n;
+  if (n1 < 0 || n2 < 0 || n1 > m->maxKp || n2 > m->maxKp) ORB_FAIL(ORB_ERR_INVALID, "keypoint count exceeds matcher capacity");
+  if (mp->mode == 0 && !prev_matched) ORB_FAIL(ORB_ERR_INVALID, "windowed mode needs prev_matched");
+  *nmatches = 0;
+  for (int i = 0; i < n1; i++) {
+    matches12[i] = -1;
+    if (best) best[i] = INT_MAX;
+    if (second) second[i] = INT_MAX;
+  }
+  if (n1 == 0 || n2 == 0) return ORB_OK;
+  ORB_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  const size_t K = (size_t)m->maxKp;
+  ORB_CUDA(cudaMemcpyAsync(m->d_desc, f1->descriptors, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+  ORB_CUDA(cudaMemcpyAsync(m->d_desc + K * 32, f2->descriptors, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+  ORB_CUDA(cudaMemcpyAsync(m->d_ang, f1->angle, (size_t)n1 * 4, cudaMemcpyHostToDevice, s));
+  ORB_CUDA(cudaMemcpyAsync(m->d_ang + K, f2->angle, (size_t)n2 * 4, cudaMemcpyHostToDevice, s));
+  PairArgs A;
+  memset(&A, 0, sizeof A);
+  A.desc1 = m->d_desc; A.desc2 = m->d_desc + K * 32;
+  A.ang1 = m->d_ang; A.ang2 = m->d_ang + K;
+  A.n1 = n1; A.n2 = n2; A.stride1 = 0; A.stride2 = 0;
+  A.nnratio = mp->nnratio; A.checkOri = mp->check_orientation; A.window = mp->window;
+  A.matches12 = m->d_m12; A.nmatches = m->d_nm;
+  A.best = m->d_best; A.second = m->d_second;
+  int st;
+  if (mp->mode == 0) {
+    if (!f1->octave || !f2->octave || !f2->xy) ORB_FAIL(ORB_ERR_INVALID, "windowed mode needs octaves and frame-2 positions");
+    ORB_CUDA(cudaMemcpyAsync(m->d_xy + K * 2, f2->xy, (size_t)n2 * 8, cudaMemcpyHostToDevice, s));
+    ORB_CUDA(cudaMemcpyAsync(m->d_oct, f1->octave, (size_t)n1 * 4, cudaMemcpyHostToDevice, s));
+    ORB_CUDA(cudaMemcpyAsync(m->d_oct + K, f2->octave, (size_t)n2 * 4, cudaMemcpyHostToDevice, s));
+    ORB_CUDA(cudaMemcpyAsync(m->d_prev, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, s));
+    A.xy2 = m->d_xy + K * 2; A.oct1 = m->d_oct; A.oct2 = m->d_oct + K; A.prev = m->d_prev;
+    A.minX = mp->min_x; A.minY = mp->min_y;
+    A.invW = 64.f / (mp->max_x - mp->min_x);  // Frame.cc:184-186
+    A.invH = 48.f / (mp->max_y - mp->min_y);
+    st = dispatch_match<true>(A, 1, s);
+  } else {
+    st = dispatch_match<false>(A, 1, s);
+  }
+  if (st) return st;
+  ORB_CUDA(cudaMemcpyAsync(matches12, m->d_m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(nmatches, m->d_nm, 4, cudaMemcpyDeviceToHost, s));
+  if (best) ORB_CUDA(cudaMemcpyAsync(best, m->d_best, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+  if (second) ORB_CUDA(cudaMemcpyAsync(second, m->d_second, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+  if (mp->mode == 0) ORB_CUDA(cudaMemcpyAsync(prev_matched, m->d_prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaStreamSynchronize(s));
+  return ORB_OK;
+}
+
+int orb_match_pairs_device(orb_matcher* m, const uint8_t* d_descriptors, const float* d_angles, int pairs, int n,
+                           float nnratio, int check_orientation, int32_t* d_matches12, int32_t* d_nmatches,
+                           void* stream) {
+  if (!m || !d_descriptors || !d_angles || !d_matches12 || !d_nmatches || pairs <= 0 || n <= 0)
+    ORB_FAIL(ORB_ERR_INVALID, "bad argument");
+  ORB_CUDA(cudaSetDevice(m->device));
+  PairArgs A;
+  memset(&A, 0, sizeof A);
+  A.desc1 = d_descriptors; A.desc2 = d_descriptors + (size_t)n * 32;
+  A.ang1 = d_angles; A.ang2 = d_angles + n;
+  A.n1 = n; A.n2 = n; A.stride1 = 2LL * n; A.stride2 = 2LL * n;
+  A.nnratio = nnratio; A.checkOri = check_orientation;
+  A.matches12 = d_matches12; A.nmatches = d_nmatches;
+  return dispatch_match<false>(A, pairs, stream ? (cudaStream_t)stream : m->stream);
+}
+
+int orb_match_allpairs_device(orb_matcher* m, const uint8_t* d_all, int n_kf, int n_desc, int row_begin, int row_end,
+                              float nnratio, int32_t* d_counts, void* stream) {
+  if (!m || !d_all || !d_counts || n_kf <= 0 || n_desc <= 0 || row_begin < 0 || row_end > n_kf || row_end <= row_begin)
+    ORB_FAIL(ORB_ERR_INVALID, "bad argument");
+  ORB_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+  const int rows = row_end - row_begin;
+  const size_t smem = (size_t)n_desc * 32;
+  if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "more than 6400 descriptors per keyframe");
+  // enough column spans to fill the machine several times over, but long enough to amortise
+  // the register load of the row keyframe
+  int spans = std::max(1, std::min(n_kf, (148 * 8 + rows - 1) / rows));
+  const int colsPerBlock = (n_kf + spans - 1) / spans;
+  spans = (n_kf + colsPerBlock - 1) / colsPerBlock;
+  const int rpt = (n_desc + kApThreads - 1) / kApThreads;
+  dim3 grid(spans, rows);
+#define ORB_AP(R)                                                                                                  \
+  do {                                                                                                             \
+    ORB_CUDA(cudaFuncSetAttribute(k_allpairs<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    k_allpairs<R><<<grid, kApThreads, smem, s>>>(d_all, n_kf, n_desc, row_begin, colsPerBlock, nnratio, d_counts); \
+  } while (0)
+  if (rpt <= 1) ORB_AP(1);
+  else if (rpt <= 2) ORB_AP(2);
+  else if (rpt <= 4) ORB_AP(4);
+  else if (rpt <= 8) ORB_AP(8);
+  else ORB_FAIL(ORB_ERR_UNSUPPORTED, "more than 2048 descriptors per keyframe");
+#undef ORB_AP
+  ORB_CUDA(cudaGetLastError());
+  return ORB_OK;
+}
+
+int orb_hamming_matrix_device(orb_matcher* m, const uint8_t* d_a, int na, const uint8_t* d_b, int nb, int32_t* d_out,
+                              void* stream) {
+  if (!m || !d_a || !d_b || !d_out || na <= 0 || nb <= 0) ORB_FAIL(ORB_ERR_INVALID, "bad argument");
+  ORB_CUDA(cudaSetDevice(m->device));
+  k_hamming_matrix<<<dim3((nb + 127) / 128, na), 128, 0, stream ? (cudaStream_t)stream : m->stream>>>(d_a, na, d_b, nb, d_out);
+  ORB_CUDA(cudaGetLastError());
+  return ORB_OK;
+}
+
+int orb_matcher_synchronize(orb_matcher* m, void* stream) {
+  if (!m) ORB_FAIL(ORB_ERR_INVALID, "null handle");
+  ORB_CUDA(cudaSetDevice(m->device));
+  ORB_CUDA(cudaStreamSynchronize(stream ? (cudaStream_t)stream : m->stream));
+  return ORB_OK;
+}
+
+int orb_int_pipe_peak(int device, int what, double* ops_per_s) {
+  if (!ops_per_s) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  ORB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ORB_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+  unsigned* d_out = nullptr;
+  ORB_CUDA(cudaMalloc(&d_out, (size_t)blocks * 256 * 4));
+  cudaEvent_t e0, e1;
+  ORB_CUDA(cudaEventCreate(&e0));
+  ORB_CUDA(cudaEventCreate(&e1));
+  float bestMs = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    ORB_CUDA(cudaEventRecord(e0));
+    if (what == 0) k_int_pipe<0><<<blocks, 256>>>(d_out, iters, 0x9e3779b9u + rep);
+    else k_int_pipe<1><<<blocks, 256>>>(d_out, iters, 0x9e3779b9u + rep);
+    ORB_CUDA(cudaEventRecord(e1));
+    ORB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    ORB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) bestMs = std::min(bestMs, ms);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+  // per loop iteration: 8 unrolled x 8 chains of the measured op (plus one dependent add/xor each,
+  // which issues on the other pipe for POPC and is the same op class for LOP3: counted once)
+  const double ops = (double)blocks * 256.0 * iters * 64.0;
+  *ops_per_s = ops / (bestMs * 1e-3);
+  return ORB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+"""Host-side mirror of the reference's ORBextractor (include/ORBextractor.h:93-162) over the C ABI.
+
+Names and argument meaning follow the reference: ORBextractor(nfeatures, scaleFactor, nlevels,
+iniThFAST, minThFAST); calling the object is operator()(image, mask, keypoints, descriptors);
+GetLevels / GetScaleFactor / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+GetInverseScaleSigmaSquares; mvImagePyramid after a call. Batch entry points are additions
+for throughput runs (frames resident in HBM).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, OrbParams, check, lib, ptr
+
+
+class ORBextractor:
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0, max_batch=64):
+        self._L = lib()
+        self._h = C.c_void_p()
+        self.nfeatures, self.scaleFactor, self.nlevels = int(nfeatures), float(scaleFactor), int(nlevels)
+        self.iniThFAST, self.minThFAST = int(iniThFAST), int(minThFAST)
+        self.device = device
+        p = OrbParams(self.nfeatures, self.scaleFactor, self.nlevels, self.iniThFAST, self.minThFAST)
+        check(self._L.orb_create(C.byref(p), device, max_batch, C.byref(self._h)))
+        n = self.nlevels
+        self._scale = np.zeros(n, np.float32); self._inv = np.zeros(n, np.float32)
+        self._s2 = np.zeros(n, np.float32); self._is2 = np.zeros(n, np.float32)
+        self.mnFeaturesPerLevel = np.zeros(n, np.int32)
+        check(self._L.orb_get_scale_tables(self._h, ptr(self._scale), ptr(self._inv), ptr(self._s2), ptr(self._is2),
+                                           ptr(self.mnFeaturesPerLevel)))
+        self.max_keypoints = int(self._L.orb_max_keypoints(self._h))
+        self.mvImagePyramid = []
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.orb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- getters of the reference (include/ORBextractor.h:119-159)
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return self.scaleFactor
+    def GetScaleFactors(self): return self._scale.copy()
+    def GetInverseScaleFactors(self): return self._inv.copy()
+    def GetScaleSigmaSquares(self): return self._s2.copy()
+    def GetInverseScaleSigmaSquares(self): return self._is2.copy()
+
+    # ---- operator()(image, mask, keypoints, descriptors), src/ORBextractor.cc:1533
+    def __call__(self, image, mask=None, want_pyramid=False):
+        """Returns (keypoints[KP_DTYPE], descriptors[N,32] u8). Empty image -> (None, None),
+        the reference's "outputs untouched". `mask` is ignored, as in the reference."""
+        if image is None or image.size == 0:
+            return None, None
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:1543)"
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        cap = self.max_keypoints
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        views = (_lib.OrbLevelView * self.nlevels)() if want_pyramid else None
+        check(self._L.orb_extract(self._h, ptr(image), w, h, image.strides[0], ptr(kps), cap, C.byref(n), ptr(desc),
+                                  C.cast(views, C.c_void_p) if want_pyramid else None))
+        if want_pyramid:
+            self.mvImagePyramid = []
+            for v in views:
+                # interior view with the 19-px border readable around it, like cv::Mat ROI views
+                total = (C.c_uint8 * (v.step * (v.height + 38))).from_address(v.data - 19 * v.step - 32)
+                full = np.frombuffer(total, np.uint8).reshape(v.height + 38, v.step)
+                self.mvImagePyramid.append(full[19:19 + v.height, 32:32 + v.width])
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch_host(self, images):
+        """images: (B,H,W) u8 numpy (pinned or pageable). H2D/D2H inside. Returns (kps[B,cap], desc[B,cap,32], counts[B])."""
+        assert images.dtype == np.uint8 and images.ndim == 3 and images.flags.c_contiguous
+        B, h, w = images.shape
+        cap = self.max_keypoints
+        kps = np.zeros((B, cap), KP_DTYPE)
+        desc = np.zeros((B, cap, 32), np.uint8)
+        counts = np.zeros(B, np.int32)
+        check(self._L.orb_extract_batch_host(self._h, ptr(images), B, w, h, w, w * h, ptr(kps), cap, ptr(counts), ptr(desc)))
+        return kps, desc, counts
+
+    def extract_batch_host_into(self, images, kps, desc, counts):
+        """Same with caller-provided (e.g. pinned) output arrays: no allocation in the timed path."""
+        B, h, w = images.shape
+        check(self._L.orb_extract_batch_host(self._h, ptr(images), B, w, h, w, w * h, ptr(kps), kps.shape[1], ptr(counts),
+                                             ptr(desc)))
+
+    def extract_batch_device(self, d_images, d_kps, d_desc, d_counts, stream=None):
+        """Device-resident batch: torch uint8 tensors. d_images (B,H,W); d_kps (B,cap,28) u8;
+        d_desc (B,cap,32) u8; d_counts (B) int32. Asynchronous on `stream` (a raw cudaStream_t int)."""
+        B, h, w = d_images.shape
+        cap = d_kps.shape[1]
+        check(self._L.orb_extract_batch_device(self._h, ptr(d_images), B, w, h, d_images.stride(1), d_images.stride(0),
+                                               ptr(d_kps), cap, ptr(d_counts), ptr(d_desc), C.c_void_p(stream or 0)))
+
+    def synchronize(self, stream=None):
+        check(self._L.orb_synchronize(self._h, C.c_void_p(stream or 0)))
+
+    def last_launch_count(self):
+        return int(self._L.orb_last_launch_count(self._h))
+
+    # ---- stage outputs of the last call (parity tests)
+    def stage_level(self, frame, level):
+        w = C.c_int(); h = C.c_int()
+        check(self._L.orb_stage_level_size(self._h, level, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value + 38, w.value + 38), np.uint8)
+        check(self._L.orb_stage_copy_level(self._h, frame, level, ptr(out)))
+        return out
+
+    def stage_blur(self, frame, level):
+        w = C.c_int(); h = C.c_int()
+        check(self._L.orb_stage_level_size(self._h, level, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        check(self._L.orb_stage_copy_blur(self._h, frame, level, ptr(out)))
+        return out
+
+    def _stage_list(self, fn, frame, level):
+        cap = 1 << 20
+        xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        check(fn(self._h, frame, level, ptr(xs), ptr(ys), ptr(sc), cap, C.byref(n)))
+        m = min(n.value, cap)
+        return xs[:m].copy(), ys[:m].copy(), sc[:m].copy()
+
+    def stage_candidates(self, frame, level):
+        return self._stage_list(self._L.orb_stage_copy_candidates, frame, level)
+
+    def stage_kept(self, frame, level):
+        return self._stage_list(self._L.orb_stage_copy_kept, frame, level)

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import orb_oracle
+    orb_oracle.lib()  # builds oracle/liborb_oracle.so on first use
+    return orb_oracle
+
+
+CONFIGS = {
+    # name: (width, height, nfeatures)  -- SURVEY.md §8(a), Examples/*/*.yaml of the reference
+    "tum1": (640, 480, 1000),
+    "kitti": (1241, 376, 2000),
+    "euroc": (752, 480, 1200),
+}
