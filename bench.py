@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native ORB front-end.
+
+Metric (BASELINE.json): ORB-extract frames/s @1241x376, 2000 features (KITTI stereo shape), plus
+Hamming comparisons/s of the SearchForInitialization-style brute-force 2-NN matcher.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the extractor over one batch of 1024 stereo pairs (2048 eye-frames,
+955 MB, larger than L2) per GPU. `value` = eye-frames/s with frames resident in HBM; `e2e` =
+the same through the C-ABI host entry point (orb_extract_batch_host) with pinned host buffers,
+H2D and D2H inside the timed region. One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT = 1241, 376, 2000          # Examples/Stereo/KITTI00-02.yaml of the reference
+PAIRS_PER_STEP = 1024                  # stereo pairs per step and GPU (BASELINE.json configs[1])
+UNIQUE_FRAMES = 512                    # unique synthetic frames per rank (241 MB > 126 MB L2), tiled
+MATCH_PAIRS, MATCH_N = 4096, 2000      # BASELINE.json configs[3]
+METRIC = "ORB-extract frames/s @1241x376 2k feats"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def gen_frames(count, seed0):
+    import multiprocessing as mp
+
+    import numpy as np
+
+    from orb_slam2_detailed_comments_b200.synth import synth_frame
+    procs = max(1, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    args = [(W, H, seed0 + i) for i in range(count)]
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            frames = pool.starmap(synth_frame, args, chunksize=8)
+    else:
+        frames = [synth_frame(*a) for a in args]
+    return np.stack(frames)
+
+
+def algorithmic_bytes(levels, mean_kp, mean_cand):
+    """bytes per frame of the whole path and per stage."""
+    in_b = W * H
+    bordered = sum((w + 38) * (h + 38) for w, h in levels)
+    area = sum(w * h for w, h in levels)
+    total = in_b + bordered + 2 * area + mean_kp * (749 + 512) + mean_kp * 56
+    per_stage = {
+        "pyramid": in_b + bordered + sum(w * h for w, h in levels[:-1]),
+        "fast": area + 8 * mean_cand,
+        "quadtree": 8 * mean_cand + 8 * mean_kp,
+        "blur": 2 * area,
+        "describe": mean_kp * (749 + 512) + mean_kp * 60,
+    }
+    return total, per_stage
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            txt = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            return out
+        sm, reasons, smax = [], set(), None
+        for line in txt.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(stage):
+    """dram bytes per launch of a stage's kernel from the committed ncu --set full capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(stage)
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """The reference's CPU implementation of the path (it cannot be compiled in this image, so:
+    the oracle port), all host threads, one frame per thread, on a bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import orb_oracle as O
+    cores = O.hardware_threads()
+    sample = max(64, 8 * cores)
+    frames = gen_frames(min(sample, 256), 0)
+    if len(frames) < sample:
+        import numpy as np
+        frames = np.concatenate([frames] * ((sample + len(frames) - 1) // len(frames)))[:sample]
+    for _ in range(max(1, min(args.warmup, 1))):
+        O.extract_batch_mt(frames[: 2 * cores], NFEAT, nthreads=cores)
+    t0 = time.perf_counter()
+    kp = 0
+    for _ in range(args.steps):
+        total, _ = O.extract_batch_mt(frames, NFEAT, nthreads=cores)
+        kp += total
+    dt = time.perf_counter() - t0
+    fps = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "KITTI-shape 1241x376 eye-frames, ORBextractor(2000,1.2,8,20,7), CPU oracle port of the "
+                               "reference path (reference itself needs OpenCV C++: unbuildable here)",
+                   "frames_per_step": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d frames per step, one frame per thread" % sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mean_keypoints": kp / (args.steps * sample),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from orb_slam2_detailed_comments_b200 import KP_DTYPE, ORBextractor, ORBmatcher, int_pipe_peak
+
+    frames_per_step = 2 * PAIRS_PER_STEP
+    t_gen = time.perf_counter()
+    pool = gen_frames(UNIQUE_FRAMES, 100000 * rank)
+    log("[rank %d] generated %d unique frames in %.1fs" % (rank, len(pool), time.perf_counter() - t_gen))
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ext = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank, max_batch=args.chunk)
+    cap = ext.max_keypoints
+    d_pool = torch.from_numpy(pool).to(dev)
+    d_imgs = d_pool.repeat((frames_per_step + len(pool) - 1) // len(pool), 1, 1)[:frames_per_step].contiguous()
+    d_kps = torch.zeros((frames_per_step, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((frames_per_step, cap, 32), dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros(frames_per_step, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_device():
+        ext.extract_batch_device(d_imgs, d_kps, d_desc, d_counts, stream=stream)
+
+    # ---- device-resident timed region --------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    ext.synchronize(stream)
+    ext.set_profiling(True)
+    ext.stage_times()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    stages = ext.stage_times()
+    ext.set_profiling(False)
+    ext.synchronize(stream)
+    launches_per_step = ext.last_launch_count()
+    counts = d_counts.cpu().numpy()
+    mean_kp = float(counts.mean())
+    fps = world * frames_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host entry point of the C ABI (pinned buffers) -----------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_imgs = torch.empty((frames_per_step, H, W), dtype=torch.uint8, pin_memory=True)
+    h_imgs.copy_(d_imgs)
+    h_kps = torch.empty((frames_per_step, cap, 28), dtype=torch.uint8, pin_memory=True)
+    h_desc = torch.empty((frames_per_step, cap, 32), dtype=torch.uint8, pin_memory=True)
+    h_counts = torch.empty(frames_per_step, dtype=torch.int32, pin_memory=True)
+    np_imgs = h_imgs.numpy(); np_kps = h_kps.numpy().view(KP_DTYPE).reshape(frames_per_step, cap)
+    np_desc = h_desc.numpy(); np_counts = h_counts.numpy()
+    ext.extract_batch_host_into(np_imgs, np_kps, np_desc, np_counts)  # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ext.extract_batch_host_into(np_imgs, np_kps, np_desc, np_counts)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_fps = world * frames_per_step * e2e_steps / e2e_s
+    e2e_launches = ext.last_launch_count() * e2e_steps
+    assert int(np_counts.sum()) == int(counts.sum()), "host path and device path disagree"
+    h2d = frames_per_step * W * H
+    d2h = frames_per_step * (cap * 60 + 4)
+    del h_imgs, h_kps, h_desc
+
+    # ---- matching: SearchForInitialization-style brute force 2-NN, 2000 x 2000 per pair ------
+    from orb_slam2_detailed_comments_b200.synth import correlated_descriptor_pair
+    uniq = 64
+    dsc = np.zeros((2 * uniq, MATCH_N, 32), np.uint8); ang = np.zeros((2 * uniq, MATCH_N), np.float32)
+    for p in range(uniq):
+        A, B, aa, ab = correlated_descriptor_pair(MATCH_N, 7000 + 1000 * rank + p)
+        dsc[2 * p], dsc[2 * p + 1], ang[2 * p], ang[2 * p + 1] = A, B, aa, ab
+    reps = MATCH_PAIRS // uniq
+    d_dsc = torch.from_numpy(dsc).to(dev).repeat(reps, 1, 1).contiguous()
+    d_ang = torch.from_numpy(ang).to(dev).repeat(reps, 1).contiguous()
+    d_m12 = torch.zeros((MATCH_PAIRS, MATCH_N), dtype=torch.int32, device=dev)
+    d_nm = torch.zeros(MATCH_PAIRS, dtype=torch.int32, device=dev)
+    matcher = ORBmatcher(0.9, True, device=local_rank, max_keypoints=MATCH_N)
+    m_steps = max(1, min(args.steps, args.match_steps))
+    for _ in range(min(args.warmup, 2)):
+        matcher.match_pairs_device(d_dsc, d_ang, d_m12, d_nm, stream=stream)
+    barrier()
+    m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(m_steps):
+        matcher.match_pairs_device(d_dsc, d_ang, d_m12, d_nm, stream=stream)
+    m1.record()
+    torch.cuda.synchronize()
+    m_ms = max_over_ranks(m0.elapsed_time(m1))
+    cmp_per_s = world * MATCH_PAIRS * MATCH_N * MATCH_N * m_steps / (m_ms * 1e-3)
+    mean_matches = float(d_nm.float().mean().item())
+    pipes = int_pipe_peak(local_rank)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel + of the whole path ---------------------------------
+    levels = []
+    for l in range(8):
+        levels.append((int(np.rint(np.float32(W) * ext.GetInverseScaleFactors()[l])), int(np.rint(np.float32(H) * ext.GetInverseScaleFactors()[l]))))
+    ext(pool[0])
+    mean_cand = float(sum(len(ext.stage_candidates(0, l)[0]) for l in range(8)))
+    total_b, per_stage_b = algorithmic_bytes(levels, mean_kp, mean_cand)
+    peak, peak_src = measured_hbm_peak()
+    stage_ms = {k: v[0] for k, v in stages.items()}
+    dom = max(stage_ms, key=stage_ms.get)
+    n_launch = max(1, stages[dom][1])
+    frames_total = frames_per_step * args.steps
+    kernels_per_chunk = 8 if dom == "pyramid" else 1
+    frames_per_launch = frames_total / (n_launch / kernels_per_chunk)
+    dom_ms = stage_ms[dom] / n_launch
+    # bytes per launch / average launch duration == stage bytes over all frames / stage time
+    achieved = per_stage_b[dom] * frames_total / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0_border+k_resize_border", "fast": "k_fast_cells", "quadtree": "k_quadtree",
+                                           "blur": "k_blur7", "describe": "k_describe"}[dom],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom),
+                "peak_source": peak_src, "algorithmic_bytes_per_frame": per_stage_b[dom], "frames_per_launch": frames_per_launch,
+                "avg_launch_ms": dom_ms, "share_of_step": stage_ms[dom] / max(1e-9, sum(stage_ms.values()))}
+    path_gbs = (fps / world) * total_b / 1e9
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import orb_oracle as O
+        cores = O.hardware_threads()
+        sample = min(1024, max(64, 64 * cores))
+        frames = np.concatenate([pool] * ((sample + len(pool) - 1) // len(pool)))[:sample]
+        t0 = time.perf_counter()
+        O.extract_batch_mt(frames, NFEAT, nthreads=cores)
+        dt = time.perf_counter() - t0
+        pairs = max(8, 2 * cores)
+        t1 = time.perf_counter()
+        O.match_batch_mt(dsc[: 2 * min(pairs, uniq)], ang[: 2 * min(pairs, uniq)], 0.9, nthreads=cores)
+        dtm = time.perf_counter() - t1
+        cpu = {"value": sample / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d KITTI-shape frames, one frame per thread, CPU oracle (reference needs OpenCV C++: unbuildable here)" % sample,
+               "matching_cmp_per_s": min(pairs, uniq) * MATCH_N * MATCH_N / dtm}
+
+    popc_peak_cmp = pipes["popc"] / 8.0
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "KITTI-shape 1241x376 stereo pairs, ORBextractor(2000,1.2,8,20,7) per eye, "
+                               "%d pairs (%d eye-frames) per step per GPU" % (PAIRS_PER_STEP, frames_per_step),
+                   "frames_per_step_per_gpu": frames_per_step, "unique_frames": UNIQUE_FRAMES, "chunk_frames": args.chunk,
+                   "l2": "inputs larger than L2 (955 MB per step; unique pool 241 MB)", "parallelism": "frames sharded, no collective"},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "orb_extract_batch_host (pinned host buffers)"},
+        "gpu_launches": launches_per_step * args.steps + e2e_launches + m_steps,
+        "clocks": clocks,
+        "roofline": roofline,
+        "path_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": total_b, "achieved": path_gbs, "peak": peak, "unit": "GB/s",
+                          "frac": path_gbs / peak},
+        "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+        "mean_keypoints": mean_kp, "mean_candidates": mean_cand,
+        "matching": {"metric": "Hamming cmp/s (2000x2000 brute-force 2-NN, ratio 0.9, dedup, rotation histogram)",
+                     "value": cmp_per_s, "unit": "cmp/s", "pairs_per_step": MATCH_PAIRS, "steps": m_steps, "ms_per_step": m_ms / m_steps,
+                     "mean_matches_per_pair": mean_matches,
+                     "roofline": {"bound": "int-pipe", "achieved": cmp_per_s / world, "peak": popc_peak_cmp, "unit": "cmp/s",
+                                  "frac": cmp_per_s / world / popc_peak_cmp,
+                                  "peak_def": "measured POPC issue rate / 8 POPC per naive 256-bit comparison (SURVEY 8d)",
+                                  "popc_ops_per_s": pipes["popc"], "lop3_ops_per_s": pipes["lop3"]}},
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("ORB_CHUNK", "128")), help="frames per internal chunk")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--match-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torchrun, one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,6 +105,13 @@ int orb_synchronize(orb_extractor* h, void* stream);
 /* Number of kernel launches the last batch call issued (for bench accounting). */
 int orb_last_launch_count(const orb_extractor* h);
 
+/* Per-stage device timing with CUDA events recorded on the launching stream between the
+ * stages of every chunk (no host synchronisation is added). orb_get_stage_times synchronises,
+ * returns the milliseconds and launch counts accumulated since the previous call for the 5
+ * stages {pyramid, fast, quadtree, blur, describe} and resets them. */
+int orb_set_profiling(orb_extractor* h, int enable);
+int orb_get_stage_times(orb_extractor* h, double* ms5, long long* launches5);
+
 /* Stage outputs of the last call, for parity tests (frame index inside the last chunk).
  *   level geometry:           orb_stage_level_size
  *   bordered pyramid level:   (h+38) x (w+38) tightly packed

@@ -683,6 +683,12 @@ struct orb_extractor {
   std::vector<u8> hostPyr;
   int lastLaunches = 0;
   int lastChunkFrames = 0;
+  // optional per-stage CUDA-event timing (bench roofline): 6 boundary events per chunk
+  bool profile = false;
+  std::vector<cudaEvent_t> evPool;
+  size_t evUsed = 0;
+  double stageMs[5] = {0, 0, 0, 0, 0};
+  long long stageLaunches[5] = {0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -846,12 +852,24 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
   return ORB_OK;
 }
 
+int stage_mark(orb_extractor* e, cudaStream_t s) {
+  if (!e->profile) return ORB_OK;
+  if (e->evUsed == e->evPool.size()) {
+    cudaEvent_t ev;
+    ORB_CUDA(cudaEventCreate(&ev));
+    e->evPool.push_back(ev);
+  }
+  ORB_CUDA(cudaEventRecord(e->evPool[e->evUsed++], s));
+  return ORB_OK;
+}
+
 // One chunk (<= wsFrames frames) through the whole pipeline, asynchronous on `s`.
 int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t frameStride, orb_keypoint* d_kps,
               int cap, int* d_counts, u8* d_desc, cudaStream_t s) {
   const Geom& g = e->g;
   const int nl = g.nlevels;
-  int launches = 0;
+  int launches = 0, st;
+  if ((st = stage_mark(e, s))) return st;
   {
     const LevelGeom& L = g.lv[0];
     dim3 grid((L.w + 2 * kEdge + 255) / 256, L.h + 2 * kEdge, B);
@@ -865,21 +883,29 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     launches++;
   }
   ORB_CUDA(cudaMemsetAsync(e->d_candCount, 0, (size_t)B * nl * sizeof(int), s));
+  if ((st = stage_mark(e, s))) return st;
   k_fast_cells<<<dim3(g.totalCells, B), 128, e->fastSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_cand, e->d_candCount,
                                                               e->candTotal);
   launches++;
+  if ((st = stage_mark(e, s))) return st;
   k_quadtree<<<dim3(nl, B), kQtThreads, e->qtSmem, s>>>(g, e->d_cand, e->d_candCount, e->d_keyNode, e->d_kept,
                                                        e->d_keptCount, e->candTotal, e->keptTotal, e->nodeCap,
                                                        e->d_overflow);
   launches++;
+  if ((st = stage_mark(e, s))) return st;
   k_blur7<<<dim3(g.totalBlurTiles, B), 256, 0, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride);
   launches++;
+  if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);
   k_describe<<<dim3((slots * 32 + 255) / 256, B), 256, 0, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride,
                                                               e->d_kept, e->d_keptCount, e->keptTotal, e->d_pattern,
                                                               d_kps, d_desc, d_counts, cap, e->d_overflow);
   launches++;
+  if ((st = stage_mark(e, s))) return st;
   ORB_CUDA(cudaGetLastError());
+  if (e->profile) {
+    e->stageLaunches[0] += nl; e->stageLaunches[1]++; e->stageLaunches[2]++; e->stageLaunches[3]++; e->stageLaunches[4]++;
+  }
   e->lastLaunches += launches;
   e->lastChunkFrames = B;
   return ORB_OK;
@@ -961,6 +987,7 @@ int orb_destroy(orb_extractor* e) {
   free_workspace(e);
   cudaFree(e->d_taps); cudaFree(e->d_pattern); cudaFree(e->d_overflow);
   cudaFree(e->d_in); cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_n);
+  for (cudaEvent_t ev : e->evPool) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return ORB_OK;
@@ -1012,6 +1039,32 @@ int orb_synchronize(orb_extractor* e, void* stream) {
 }
 
 int orb_last_launch_count(const orb_extractor* e) { return e ? e->lastLaunches : 0; }
+
+int orb_set_profiling(orb_extractor* e, int enable) {
+  if (!e) ORB_FAIL(ORB_ERR_INVALID, "null handle");
+  e->profile = enable != 0;
+  return ORB_OK;
+}
+
+int orb_get_stage_times(orb_extractor* e, double* ms5, long long* launches5) {
+  if (!e || !ms5 || !launches5) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  ORB_CUDA(cudaSetDevice(e->device));
+  ORB_CUDA(cudaDeviceSynchronize());
+  for (size_t i = 0; i + 5 < e->evUsed; i += 6)
+    for (int k = 0; k < 5; k++) {
+      float ms = 0.f;
+      ORB_CUDA(cudaEventElapsedTime(&ms, e->evPool[i + k], e->evPool[i + k + 1]));
+      e->stageMs[k] += ms;
+    }
+  e->evUsed = 0;
+  for (int k = 0; k < 5; k++) {
+    ms5[k] = e->stageMs[k];
+    launches5[k] = e->stageLaunches[k];
+    e->stageMs[k] = 0;
+    e->stageLaunches[k] = 0;
+  }
+  return ORB_OK;
+}
 
 int orb_extract_batch_host(orb_extractor* e, const uint8_t* images, int batch, int width, int height, size_t step,
                            size_t frame_stride, orb_keypoint* keypoints, int capacity, int32_t* counts,

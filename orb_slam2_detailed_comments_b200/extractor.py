@@ -108,6 +108,17 @@ class ORBextractor:
     def last_launch_count(self):
         return int(self._L.orb_last_launch_count(self._h))
 
+    STAGES = ("pyramid", "fast", "quadtree", "blur", "describe")
+
+    def set_profiling(self, enable):
+        check(self._L.orb_set_profiling(self._h, int(bool(enable))))
+
+    def stage_times(self):
+        """{stage: (total_ms, launches)} accumulated since the previous call (CUDA events on the stream)."""
+        ms = np.zeros(5, np.float64); ln = np.zeros(5, np.int64)
+        check(self._L.orb_get_stage_times(self._h, ptr(ms), ptr(ln)))
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(self.STAGES)}
+
     # ---- stage outputs of the last call (parity tests)
     def stage_level(self, frame, level):
         w = C.c_int(); h = C.c_int()
