@@ -178,7 +178,7 @@ def run_ours(args, rank, world, local_rank):
 
     from orb_slam2_detailed_comments_b200 import KP_DTYPE, ORBextractor, ORBmatcher, int_pipe_peak
 
-    frames_per_step = 2 * PAIRS_PER_STEP
+    frames_per_step = 2 * args.pairs
     t_gen = time.perf_counter()
     pool = gen_frames(UNIQUE_FRAMES, 100000 * rank)
     log("[rank %d] generated %d unique frames in %.1fs" % (rank, len(pool), time.perf_counter() - t_gen))
@@ -191,7 +191,12 @@ def run_ours(args, rank, world, local_rank):
     d_kps = torch.zeros((frames_per_step, cap, 28), dtype=torch.uint8, device=dev)
     d_desc = torch.zeros((frames_per_step, cap, 32), dtype=torch.uint8, device=dev)
     d_counts = torch.zeros(frames_per_step, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated non-default stream: the library treats a NULL stream as "the handle's own",
+    # and torch events only see the stream they are recorded on
+    tstream = torch.cuda.Stream(device=dev)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -216,10 +221,10 @@ def run_ours(args, rank, world, local_rank):
     ext.stage_times()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(tstream)
     for _ in range(args.steps):
         step_device()
-    e1.record()
+    e1.record(tstream)
     torch.cuda.synchronize()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     barrier()
@@ -261,24 +266,26 @@ def run_ours(args, rank, world, local_rank):
     for p in range(uniq):
         A, B, aa, ab = correlated_descriptor_pair(MATCH_N, 7000 + 1000 * rank + p)
         dsc[2 * p], dsc[2 * p + 1], ang[2 * p], ang[2 * p + 1] = A, B, aa, ab
-    reps = MATCH_PAIRS // uniq
+    match_pairs = args.match_pairs
+    reps = max(1, match_pairs // uniq)
+    match_pairs = reps * uniq
     d_dsc = torch.from_numpy(dsc).to(dev).repeat(reps, 1, 1).contiguous()
     d_ang = torch.from_numpy(ang).to(dev).repeat(reps, 1).contiguous()
-    d_m12 = torch.zeros((MATCH_PAIRS, MATCH_N), dtype=torch.int32, device=dev)
-    d_nm = torch.zeros(MATCH_PAIRS, dtype=torch.int32, device=dev)
+    d_m12 = torch.zeros((match_pairs, MATCH_N), dtype=torch.int32, device=dev)
+    d_nm = torch.zeros(match_pairs, dtype=torch.int32, device=dev)
     matcher = ORBmatcher(0.9, True, device=local_rank, max_keypoints=MATCH_N)
     m_steps = max(1, min(args.steps, args.match_steps))
     for _ in range(min(args.warmup, 2)):
         matcher.match_pairs_device(d_dsc, d_ang, d_m12, d_nm, stream=stream)
     barrier()
     m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True)
-    m0.record()
+    m0.record(tstream)
     for _ in range(m_steps):
         matcher.match_pairs_device(d_dsc, d_ang, d_m12, d_nm, stream=stream)
-    m1.record()
+    m1.record(tstream)
     torch.cuda.synchronize()
     m_ms = max_over_ranks(m0.elapsed_time(m1))
-    cmp_per_s = world * MATCH_PAIRS * MATCH_N * MATCH_N * m_steps / (m_ms * 1e-3)
+    cmp_per_s = world * match_pairs * MATCH_N * MATCH_N * m_steps / (m_ms * 1e-3)
     mean_matches = float(d_nm.float().mean().item())
     pipes = int_pipe_peak(local_rank)
     clocks = sampler.stop() if sampler else None
@@ -336,9 +343,9 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": "KITTI-shape 1241x376 stereo pairs, ORBextractor(2000,1.2,8,20,7) per eye, "
-                               "%d pairs (%d eye-frames) per step per GPU" % (PAIRS_PER_STEP, frames_per_step),
+                               "%d pairs (%d eye-frames) per step per GPU" % (args.pairs, frames_per_step),
                    "frames_per_step_per_gpu": frames_per_step, "unique_frames": UNIQUE_FRAMES, "chunk_frames": args.chunk,
-                   "l2": "inputs larger than L2 (955 MB per step; unique pool 241 MB)", "parallelism": "frames sharded, no collective"},
+                   "l2": "inputs larger than L2 (%d MB per step; unique pool 241 MB)" % (frames_per_step * W * H // 1000000), "parallelism": "frames sharded, no collective"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "orb_extract_batch_host (pinned host buffers)"},
         "gpu_launches": launches_per_step * args.steps + e2e_launches + m_steps,
@@ -349,7 +356,7 @@ def run_ours(args, rank, world, local_rank):
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "mean_keypoints": mean_kp, "mean_candidates": mean_cand,
         "matching": {"metric": "Hamming cmp/s (2000x2000 brute-force 2-NN, ratio 0.9, dedup, rotation histogram)",
-                     "value": cmp_per_s, "unit": "cmp/s", "pairs_per_step": MATCH_PAIRS, "steps": m_steps, "ms_per_step": m_ms / m_steps,
+                     "value": cmp_per_s, "unit": "cmp/s", "pairs_per_step": match_pairs, "steps": m_steps, "ms_per_step": m_ms / m_steps,
                      "mean_matches_per_pair": mean_matches,
                      "roofline": {"bound": "int-pipe", "achieved": cmp_per_s / world, "peak": popc_peak_cmp, "unit": "cmp/s",
                                   "frac": cmp_per_s / world / popc_peak_cmp,
@@ -373,6 +380,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--match-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP, help="stereo pairs per step per GPU (profiling runs shrink this)")
+    ap.add_argument("--match-pairs", type=int, default=MATCH_PAIRS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
