@@ -175,10 +175,13 @@ int orb_match_pairs_device(orb_matcher* m, const uint8_t* d_descriptors, const f
 
 /* All-pairs keyframe matching: `d_all` holds n_kf x n_desc descriptors
  * (all keyframes, e.g. after an all-gather); rows [row_begin,row_end) are this rank's
- * keyframes. d_counts ((row_end-row_begin) x n_kf ints) receives, per ordered keyframe pair,
- * the number of row descriptors whose 2-NN passes best <= TH_LOW and best < nnratio*second. */
+ * keyframes, [col_begin,col_end) the column keyframes to match against in this call (so that
+ * peers' descriptor blocks can be consumed as they arrive). d_counts is the rank's
+ * (row_end-row_begin) x n_kf int matrix; entry (i-row_begin, j) receives, per ordered keyframe
+ * pair, the number of row descriptors whose 2-NN passes best <= TH_LOW and best < nnratio*second. */
 int orb_match_allpairs_device(orb_matcher* m, const uint8_t* d_all, int n_kf, int n_desc, int row_begin,
-                              int row_end, float nnratio, int32_t* d_counts, void* stream);
+                              int row_end, int col_begin, int col_end, float nnratio, int32_t* d_counts,
+                              void* stream);
 
 /* Plain Hamming distance matrix (na x nb ints) on the device: parity aid for the kernels. */
 int orb_hamming_matrix_device(orb_matcher* m, const uint8_t* d_a, int na, const uint8_t* d_b, int nb,

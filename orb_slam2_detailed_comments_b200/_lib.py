@@ -90,7 +90,7 @@ def lib():
         L.orb_search_for_initialization.argtypes = [vp, C.POINTER(OrbFrameView), C.POINTER(OrbFrameView),
                                                     C.POINTER(OrbMatchParams), vp, vp, C.POINTER(i32), vp, vp]
         L.orb_match_pairs_device.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp, vp, vp]
-        L.orb_match_allpairs_device.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, vp]
+        L.orb_match_allpairs_device.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp]
         L.orb_hamming_matrix_device.argtypes = [vp, vp, i32, vp, i32, vp, vp]
         L.orb_matcher_synchronize.argtypes = [vp, vp]
         L.orb_int_pipe_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]

@@ -80,45 +80,117 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 // Level 0: copyMakeBorder(image, 19, REFLECT_101)  (ORBextractor.cc:1716)
+// One thread writes 16 bytes (one aligned STG.128) of a bordered row. Byte 16*g of a row is
+// interior column 16*(g-2); columns left of -19 / right of w+18 are row padding.
 __global__ void __launch_bounds__(256) k_level0_border(const Geom g, const u8* __restrict__ img, size_t step,
                                                        size_t frameStride, u8* __restrict__ pyr,
                                                        size_t pyrStride) {
   const LevelGeom& L = g.lv[0];
-  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int by = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
-  if (bx >= L.w + 2 * kEdge) return;
-  const int x = reflect101(bx - kEdge, L.w), y = reflect101(by - kEdge, L.h);
-  const u8 v = img[(size_t)f * frameStride + (size_t)y * step + x];
-  pyr[(size_t)f * pyrStride + L.off + (long long)(by - kEdge) * L.pitch + (bx - kEdge)] = v;
+  if (gi * 16 >= L.pitch || by >= L.h + 2 * kEdge) return;
+  const int c0 = 16 * (gi - 2);
+  const int y = reflect101(by - kEdge, L.h);
+  const u8* row = img + (size_t)f * frameStride + (size_t)y * step;
+  uint4 out;
+  if (c0 >= 16 && c0 + 20 <= L.w) {
+    // interior: 5 aligned words + funnel shifts (source rows have arbitrary alignment)
+    const size_t addr = reinterpret_cast<size_t>(row + c0);
+    const unsigned* wp = reinterpret_cast<const unsigned*>(addr & ~(size_t)3);
+    const unsigned sh = (unsigned)(addr & 3) * 8;
+    const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+    out.x = __funnelshift_r(w0, w1, sh);
+    out.y = __funnelshift_r(w1, w2, sh);
+    out.z = __funnelshift_r(w2, w3, sh);
+    out.w = __funnelshift_r(w3, w4, sh);
+  } else {
+    unsigned v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      unsigned acc = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int x = min(max(reflect101(c0 + 4 * q + j, L.w), 0), L.w - 1);
+        acc |= (unsigned)__ldg(row + x) << (8 * j);
+      }
+      v[q] = acc;
+    }
+    out = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  u8* dst = pyr + (size_t)f * pyrStride + L.off + (long long)(by - kEdge) * L.pitch - kLeftPad + 16 * gi;
+  *reinterpret_cast<uint4*>(dst) = out;
 }
 
 // Level l>0: resize(level l-1 -> l, INTER_LINEAR) fused with copyMakeBorder(REFLECT_101 |
 // ISOLATED) (ORBextractor.cc:1677, :1695). Every thread of the BORDERED domain recomputes the
-// interior pixel it mirrors, so the plane is written exactly once, coalesced.
-// taps: {source index, c0 | c1<<16} per destination column / row (11-bit fixed point).
+// interior pixels it mirrors, so the plane is written exactly once, 4 pixels (one aligned
+// STG.32) per thread. taps: {source index, c0 | c1<<16} per destination column / row
+// (11-bit fixed point, cv::resize INTER_LINEAR 8-bit).
+__device__ __forceinline__ unsigned resize_px_slow(const u8* r0, const u8* r1, int2 tx, int sw, int cy0, int cy1) {
+  const int sx0 = tx.x, sx1 = min(sx0 + 1, sw - 1);
+  const int cx0 = tx.y & 0xffff, cx1 = tx.y >> 16;
+  const int h0 = r0[sx0] * cx0 + r0[sx1] * cx1;
+  const int h1 = r1[sx0] * cx0 + r1[sx1] * cx1;
+  const int v = (((cy0 * (h0 >> 4)) >> 16) + ((cy1 * (h1 >> 4)) >> 16) + 2) >> 2;
+  return (unsigned)min(max(v, 0), 255);
+}
+
 __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
                                                        const int2* __restrict__ taps) {
   const LevelGeom& D = g.lv[l];
   const LevelGeom& S = g.lv[l - 1];
-  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int by = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
-  if (bx >= D.w + 2 * kEdge) return;
-  const int x = reflect101(bx - kEdge, D.w), y = reflect101(by - kEdge, D.h);
-  const int2 tx = __ldg(taps + D.tapX + x), ty = __ldg(taps + D.tapY + y);
-  const int sx0 = tx.x, sx1 = min(sx0 + 1, S.w - 1);
+  if (gi * 4 >= D.pitch || by >= D.h + 2 * kEdge) return;
+  const int c0 = 4 * (gi - 8);
+  const int y = reflect101(by - kEdge, D.h);
+  const int2 ty = __ldg(taps + D.tapY + y);
   const int sy0 = ty.x, sy1 = min(sy0 + 1, S.h - 1);
-  const int cx0 = (short)(tx.y & 0xffff), cx1 = tx.y >> 16;
-  const int cy0 = (short)(ty.y & 0xffff), cy1 = ty.y >> 16;
+  const int cy0 = ty.y & 0xffff, cy1 = ty.y >> 16;
   const u8* src = pyr + (size_t)f * pyrStride + S.off;
   const u8* r0 = src + (long long)sy0 * S.pitch;
   const u8* r1 = src + (long long)sy1 * S.pitch;
-  const int h0 = r0[sx0] * cx0 + r0[sx1] * cx1;
-  const int h1 = r1[sx0] * cx0 + r1[sx1] * cx1;
-  int v = (((cy0 * (h0 >> 4)) >> 16) + ((cy1 * (h1 >> 4)) >> 16) + 2) >> 2;
-  v = min(max(v, 0), 255);
-  pyr[(size_t)f * pyrStride + D.off + (long long)(by - kEdge) * D.pitch + (bx - kEdge)] = (u8)v;
+  unsigned out = 0;
+  bool fast = c0 >= 0 && c0 + 3 < D.w;
+  int4 ta, tb;
+  if (fast) {
+    const int4* tp4 = reinterpret_cast<const int4*>(taps + D.tapX + c0);  // tapX and c0 are even: 16 B aligned
+    ta = __ldg(tp4);
+    tb = __ldg(tp4 + 1);
+    fast = tb.z + 1 - ta.x <= 7;  // the 4 pixels' source span fits one 8-byte window
+  }
+  if (fast) {
+    const int a = ta.x;
+    const size_t a0 = reinterpret_cast<size_t>(r0 + a), a1 = reinterpret_cast<size_t>(r1 + a);
+    const unsigned* p0 = reinterpret_cast<const unsigned*>(a0 & ~(size_t)3);
+    const unsigned* p1 = reinterpret_cast<const unsigned*>(a1 & ~(size_t)3);
+    const unsigned s0 = (unsigned)(a0 & 3) * 8, s1 = (unsigned)(a1 & 3) * 8;
+    const unsigned u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
+    const unsigned lo0 = __funnelshift_r(u0, u1, s0), hi0 = __funnelshift_r(u1, u2, s0);
+    const unsigned lo1 = __funnelshift_r(v0, v1, s1), hi1 = __funnelshift_r(v1, v2, s1);
+    const int sx[4] = {ta.x, ta.z, tb.x, tb.z};
+    const unsigned cf[4] = {(unsigned)ta.y, (unsigned)ta.w, (unsigned)tb.y, (unsigned)tb.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned dlt = (unsigned)(sx[j] - a);
+      const unsigned sel = dlt | ((dlt + 1) << 4);          // bytes (dlt, dlt+1) of the window
+      const unsigned q0 = __byte_perm(lo0, hi0, sel), q1 = __byte_perm(lo1, hi1, sel);
+      const int h0 = (int)__dp2a_lo(cf[j], q0, 0u);         // c0*p[sx] + c1*p[sx+1]
+      const int h1 = (int)__dp2a_lo(cf[j], q1, 0u);
+      const int v = (((cy0 * (h0 >> 4)) >> 16) + ((cy1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      out |= (unsigned)min(max(v, 0), 255) << (8 * j);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int x = min(max(reflect101(c0 + j, D.w), 0), D.w - 1);
+      out |= resize_px_slow(r0, r1, __ldg(taps + D.tapX + x), S.w, cy0, cy1) << (8 * j);
+    }
+  }
+  u8* dst = pyr + (size_t)f * pyrStride + D.off + (long long)(by - kEdge) * D.pitch - kLeftPad + 4 * gi;
+  *reinterpret_cast<unsigned*>(dst) = out;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -126,49 +198,75 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
 // ------------------------------------------------------------------------------------------
 // Score S(p) = largest threshold for which p is still a FAST-9 corner
 //            = max(max_arcs min d, max_arcs min(-d)) - 1,  d_k = I(p) - I(circle_k).
-// Returns S if S >= minTh else 0. `p` points into a shared-memory tile with row pitch tp.
-__device__ __forceinline__ int fast_score_tile(const u8* p, int tp, int minTh) {
-  const int c = p[0];
-  const u8* rm3 = p - 3 * tp; const u8* rm2 = p - 2 * tp; const u8* rm1 = p - tp;
-  const u8* rp1 = p + tp;     const u8* rp2 = p + 2 * tp; const u8* rp3 = p + 3 * tp;
-  int d[16];
-  d[0] = c - rp3[0];   d[1] = c - rp3[1];   d[2] = c - rp2[2];    d[3] = c - rp1[3];
-  d[4] = c - p[3];     d[5] = c - rm1[3];   d[6] = c - rm2[2];    d[7] = c - rm3[1];
-  d[8] = c - rm3[0];   d[9] = c - rm3[-1];  d[10] = c - rm2[-2];  d[11] = c - rm1[-3];
-  d[12] = c - p[-3];   d[13] = c - rp1[-3]; d[14] = c - rp2[-2];  d[15] = c - rp3[-1];
-  // Necessary condition: every 9-arc holds one pixel of each antipodal pair.
-  int minhi = 512, maxlo = -512;
+//
+// Two pixels per thread, packed as s16x2 and processed with the DPX min/max instructions
+// (VIMNMX / VIMNMX3 .S16x2). The shared-memory tile is stored "pair interleaved": word j of a
+// tile row holds (T[j], T[j+S]), S = ceil(cw/2), so that the 16 circle samples of the pixel pair
+// (x, x+S) are 16 aligned 32-bit loads. Differences are kept biased, d' = d + 255 in [0,510], so
+// a plain 32-bit subtraction never borrows across the halves.
+struct FastDiffs { unsigned d[16]; };
+
+__device__ __forceinline__ void fast_load_diffs(const unsigned* p, int tp, FastDiffs& D) {
+  const unsigned c = p[0] + 0x00FF00FFu;
+  const unsigned* rm3 = p - 3 * tp; const unsigned* rm2 = p - 2 * tp; const unsigned* rm1 = p - tp;
+  const unsigned* rp1 = p + tp;     const unsigned* rp2 = p + 2 * tp; const unsigned* rp3 = p + 3 * tp;
+  D.d[0] = c - rp3[0];   D.d[1] = c - rp3[1];   D.d[2] = c - rp2[2];    D.d[3] = c - rp1[3];
+  D.d[4] = c - p[3];     D.d[5] = c - rm1[3];   D.d[6] = c - rm2[2];    D.d[7] = c - rm3[1];
+  D.d[8] = c - rm3[0];   D.d[9] = c - rm3[-1];  D.d[10] = c - rm2[-2];  D.d[11] = c - rm1[-3];
+  D.d[12] = c - p[-3];   D.d[13] = c - rp1[-3]; D.d[14] = c - rp2[-2];  D.d[15] = c - rp3[-1];
+}
+
+// Necessary condition for a corner at threshold t: every 9-arc holds one pixel of each
+// antipodal pair (k, k+8). Returns an upper bound of S + 256 in each half.
+__device__ __forceinline__ unsigned fast_bound(const FastDiffs& D) {
+  unsigned hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    minhi = min(minhi, max(d[j], d[j + 8]));
-    maxlo = max(maxlo, min(d[j], d[j + 8]));
+    hi[j] = __vmaxs2(D.d[j], D.d[j + 8]);
+    lo[j] = __vmins2(D.d[j], D.d[j + 8]);
   }
-  if (minhi <= minTh && maxlo >= -minTh) return 0;
-  // Exact: sliding 9-window min / max over the circular sequence via two 3-input stages.
-  int mn3[16], mx3[16];
+  const unsigned minhi = __vimin3_s16x2(__vimin3_s16x2(hi[0], hi[1], hi[2]), __vimin3_s16x2(hi[3], hi[4], hi[5]), __vmins2(hi[6], hi[7]));
+  const unsigned maxlo = __vimax3_s16x2(__vimax3_s16x2(lo[0], lo[1], lo[2]), __vimax3_s16x2(lo[3], lo[4], lo[5]), __vmaxs2(lo[6], lo[7]));
+  return __vmaxs2(minhi, 0x01FE01FEu - maxlo);
+}
+
+// Exact S + 256 in each half: sliding 9-window min / max over the circular sequence, two
+// 3-input stages each.
+__device__ __forceinline__ unsigned fast_exact(const FastDiffs& D) {
+  unsigned mn3[16], mx3[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    mn3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    mx3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    mn3[k] = __vimin3_s16x2(D.d[k], D.d[(k + 1) & 15], D.d[(k + 2) & 15]);
+    mx3[k] = __vimax3_s16x2(D.d[k], D.d[(k + 1) & 15], D.d[(k + 2) & 15]);
   }
-  int a = -512, b = 512;
+  unsigned a[16], b[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    a = max(a, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
-    b = min(b, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+    a[k] = __vimin3_s16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+    b[k] = __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
   }
-  const int s = max(a, -b) - 1;
-  return s >= minTh ? s : 0;
+  unsigned A = __vimax3_s16x2(__vimax3_s16x2(a[0], a[1], a[2]), __vimax3_s16x2(a[3], a[4], a[5]), __vimax3_s16x2(a[6], a[7], a[8]));
+  A = __vimax3_s16x2(A, __vimax3_s16x2(a[9], a[10], a[11]), __vimax3_s16x2(a[12], a[13], a[14]));
+  A = __vmaxs2(A, a[15]);
+  unsigned B = __vimin3_s16x2(__vimin3_s16x2(b[0], b[1], b[2]), __vimin3_s16x2(b[3], b[4], b[5]), __vimin3_s16x2(b[6], b[7], b[8]));
+  B = __vimin3_s16x2(B, __vimin3_s16x2(b[9], b[10], b[11]), __vimin3_s16x2(b[12], b[13], b[14]));
+  B = __vmins2(B, b[15]);
+  return __vmaxs2(A, 0x01FE01FEu - B);
 }
 
 // One CTA per cell. The cell's detection window is x in [19+j*wCell, min(18+(j+1)*wCell, w-20)]
 // (sub-image [iniX,maxX) minus FAST's own 3-px frame), so windows tile the level and the 3x3
 // NMS never sees across a cell boundary (scores outside the window count as 0).
-__global__ void __launch_bounds__(128) k_fast_cells(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
-                                                    uint2* __restrict__ cand, int* __restrict__ candCount,
-                                                    int candTotal) {
-  extern __shared__ u8 smem[];
-  const int f = blockIdx.y;
+// Phases: tile -> prefilter (queue the pairs that may hold a corner) -> exact score on the queue
+// (dense, no divergence) -> 3x3 NMS on the hit list -> iniTh / minTh decision -> emit.
+constexpr int kFastThreads = 128;
+
+__global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
+                                                             uint2* __restrict__ cand, int* __restrict__ candCount,
+                                                             int candTotal) {
+  extern __shared__ __align__(16) u8 smem[];
+  __shared__ int s_nq, s_nh;
+  const int f = blockIdx.y, tid = threadIdx.x;
   int l = 0;
 #pragma unroll 1
   while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].cellBase) l++;
@@ -179,43 +277,75 @@ __global__ void __launch_bounds__(128) k_fast_cells(const Geom g, const u8* __re
   const int y0 = kEdge + ci * L.hCell, y1 = min(y0 + L.hCell - 1, L.h - kEdge - 1);
   const int cw = x1 - x0 + 1, ch = y1 - y0 + 1;
   if (cw <= 0 || ch <= 0) return;
-  const int tp = (cw + 6 + 3) & ~3;       // tile pitch
+  const int S = (cw + 1) >> 1;            // pair stride
+  const int tp = S + 6;                   // tile pitch in words
   const int sp = cw + 2;                  // score pitch (1-px zero apron)
-  u8* tile = smem;
-  u8* sc = smem + tp * (ch + 6);
+  unsigned* tile = reinterpret_cast<unsigned*>(smem);
+  unsigned short* queue = reinterpret_cast<unsigned short*>(tile + tp * (ch + 6));  // pair items to score exactly
+  unsigned short* hits = queue + ((S * ch + 1) & ~1);                                // pixels with S >= minTh
+  u8* sc = reinterpret_cast<u8*>(hits + ((cw * ch + 1) & ~1));
+  if (tid == 0) { s_nq = 0; s_nh = 0; }
   const u8* src = pyr + (size_t)f * pyrStride + L.off + (long long)(y0 - 3) * L.pitch + (x0 - 3);
-  for (int i = threadIdx.x; i < (cw + 6) * (ch + 6); i += blockDim.x) {
-    const int r = i / (cw + 6), c = i - r * (cw + 6);
-    tile[r * tp + c] = src[(long long)r * L.pitch + c];
+  for (int i = tid; i < tp * (ch + 6); i += kFastThreads) {
+    const int r = i / tp, j = i - r * tp;
+    const u8* row = src + (long long)r * L.pitch;
+    const unsigned lo = row[j];
+    const unsigned hi = j + S < cw + 6 ? row[j + S] : 0u;
+    tile[i] = lo | (hi << 16);
   }
-  for (int i = threadIdx.x; i < sp * (ch + 2); i += blockDim.x) sc[i] = 0;
+  for (int i = tid; i < (sp * (ch + 2) + 3) / 4; i += kFastThreads) reinterpret_cast<unsigned*>(sc)[i] = 0u;
   __syncthreads();
-  for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) {
-    const int r = i / cw, c = i - r * cw;
-    const int s = fast_score_tile(tile + (r + 3) * tp + (c + 3), tp, g.minTh);
-    if (s) sc[(r + 1) * sp + c + 1] = (u8)s;
+  // bit 15 of a half is set iff its bound exceeds minTh + 255, i.e. a corner at minTh is possible
+  const unsigned K = 0x7FFF7FFFu - (unsigned)(g.minTh + 255) * 0x00010001u;
+  for (int i = tid; i < S * ch; i += kFastThreads) {
+    const int r = i / S, x = i - r * S;
+    FastDiffs D;
+    fast_load_diffs(tile + (r + 3) * tp + (x + 3), tp, D);
+    if ((fast_bound(D) + K) & 0x80008000u) queue[atomicAdd(&s_nq, 1)] = (unsigned short)i;
   }
   __syncthreads();
-  int strong = 0;
-  for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) {
-    const int r = i / cw, c = i - r * cw;
-    const u8* q = sc + (r + 1) * sp + c + 1;
-    const int s = q[0];
-    if (s >= g.iniTh) {
-      const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
-      strong |= s > m;
+  const int nq = s_nq;
+  for (int e = tid; e < nq; e += kFastThreads) {
+    const int i = queue[e];
+    const int r = i / S, x = i - r * S;
+    FastDiffs D;
+    fast_load_diffs(tile + (r + 3) * tp + (x + 3), tp, D);
+    const unsigned s2 = fast_exact(D);
+    const int sLo = (int)(s2 & 0xffffu) - 256, sHi = (int)(s2 >> 16) - 256;
+    if (sLo >= g.minTh) {
+      sc[(r + 1) * sp + x + 1] = (u8)sLo;
+      hits[atomicAdd(&s_nh, 1)] = (unsigned short)(r * cw + x);
+    }
+    if (x + S < cw && sHi >= g.minTh) {
+      sc[(r + 1) * sp + x + S + 1] = (u8)sHi;
+      hits[atomicAdd(&s_nh, 1)] = (unsigned short)(r * cw + x + S);
     }
   }
+  __syncthreads();
+  const int nh = s_nh;
+  int strong = 0;
+  for (int e = tid; e < nh; e += kFastThreads) {
+    const int p = hits[e];
+    const int r = p / cw, c = p - r * cw;
+    const u8* q = sc + (r + 1) * sp + c + 1;
+    const int s = q[0];
+    const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
+    if (s > m) {  // strict 3x3 maximum inside the cell
+      hits[e] = (unsigned short)(p | 0x8000);
+      strong |= s >= g.iniTh;
+    }
+  }
+  // cv::FAST(iniTh) result non-empty -> keep it, else the minTh result (:1111-1124)
   const int th = __syncthreads_or(strong) ? g.iniTh : g.minTh;
   int* cnt = candCount + f * g.nlevels + l;
   uint2* out = cand + (size_t)f * candTotal + L.candOff;
-  for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) {
-    const int r = i / cw, c = i - r * cw;
-    const u8* q = sc + (r + 1) * sp + c + 1;
-    const int s = q[0];
-    if (s >= th) {
-      const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
-      if (s > m) {
+  for (int e = tid; e < nh; e += kFastThreads) {
+    const int p = hits[e];
+    if (p & 0x8000) {
+      const int pp = p & 0x7fff;
+      const int r = pp / cw, c = pp - r * cw;
+      const int s = sc[(r + 1) * sp + c + 1];
+      if (s >= th) {
         const int idx = atomicAdd(cnt, 1);
         if (idx < L.candCap) out[idx] = make_uint2((unsigned)(x0 + c) | ((unsigned)(y0 + r) << 16), (unsigned)s);
       }
@@ -503,13 +633,20 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
 // horizontally into u16, vertically (+32768)>>16. Reads the bordered plane, whose border IS the
 // REFLECT_101 content the reference's blur of the clone() re-synthesises.
 // ------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 64, kBlurTH = 32;
+// Integer dot-product instructions do the taps: the horizontal pass is two IDP.4A per pixel on
+// byte windows built with funnel shifts, the vertical pass four IDP.2A per pixel on u16 pairs
+// (two tile rows interleaved per 32-bit word). One CTA blurs a 128 x 32 tile.
+constexpr int kBlurTW = 128, kBlurTH = 32;
+constexpr int kBlurInW = (kBlurTW + 8) / 4;   // words per input tile row: image x0-4 .. x0+131
+constexpr int kBlurInP = kBlurInW + 1;        // padded pitch (words)
+constexpr int kBlurRows = kBlurTH + 6;        // input rows y0-3 .. y0+34
+constexpr int kBlurPairs = kBlurRows / 2;
 
 __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                u8* __restrict__ blur, size_t blurStride) {
-  __shared__ u8 in[(kBlurTH + 6) * (kBlurTW + 8)];
-  __shared__ unsigned short hs[(kBlurTH + 6) * kBlurTW];
-  const int f = blockIdx.y;
+  __shared__ unsigned in[kBlurRows * kBlurInP];
+  __shared__ __align__(16) unsigned hp[kBlurPairs * kBlurTW];  // (H[2p][x], H[2p+1][x]) as u16 pairs
+  const int f = blockIdx.y, tid = threadIdx.x;
   int l = 0;
 #pragma unroll 1
   while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blurTileBase) l++;
@@ -518,29 +655,65 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
   const int ty = t / L.blurTilesX, tx = t - ty * L.blurTilesX;
   const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
   const u8* src = pyr + (size_t)f * pyrStride + L.off;
-  constexpr int IW = kBlurTW + 6, IP = kBlurTW + 8;
-  for (int i = threadIdx.x; i < IW * (kBlurTH + 6); i += 256) {
-    const int r = i / IW, c = i - r * IW;
-    const int y = min(y0 + r - 3, L.h + 2), x = min(x0 + c - 3, L.w + 2);  // stay inside the border
-    in[r * IP + c] = src[(long long)y * L.pitch + x];
+  const int xmax = (L.w + 16) & ~3;  // last word that still lies inside the 19-px border
+  for (int i = tid; i < kBlurRows * kBlurInW; i += 256) {
+    const int r = i / kBlurInW, c = i - r * kBlurInW;
+    const int y = min(y0 + r - 3, L.h + kEdge - 1), x = min(x0 - 4 + 4 * c, xmax);
+    in[r * kBlurInP + c] = *reinterpret_cast<const unsigned*>(src + (long long)y * L.pitch + x);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kBlurTW * (kBlurTH + 6); i += 256) {
-    const int r = i / kBlurTW, c = i - r * kBlurTW;
-    const u8* p = in + r * IP + c;
-    hs[i] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-  }
-  __syncthreads();
-  u8* dst = blur + (size_t)f * blurStride + L.boff;
-  for (int i = threadIdx.x; i < kBlurTW * kBlurTH; i += 256) {
-    const int r = i / kBlurTW, c = i - r * kBlurTW;
-    const int x = x0 + c, y = y0 + r;
-    if (x < L.w && y < L.h) {
-      const unsigned short* p = hs + r * kBlurTW + c;
-      const unsigned acc = 32768u + 18u * (p[0] + p[6 * kBlurTW]) + 34u * (p[kBlurTW] + p[5 * kBlurTW]) +
-                           48u * (p[2 * kBlurTW] + p[4 * kBlurTW]) + 56u * p[3 * kBlurTW];
-      dst[(long long)y * L.bpitch + x] = (u8)(acc >> 16);
+  // horizontal: k = [18,34,48,56,48,34,18]; output x needs tile bytes (x+1 .. x+7)
+  for (int i = tid; i < kBlurPairs * (kBlurTW / 4); i += 256) {
+    const int rp = i / (kBlurTW / 4), xg = i - rp * (kBlurTW / 4);
+    unsigned hrow[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const unsigned* p = in + (2 * rp + q) * kBlurInP + xg;
+      const unsigned w0 = p[0], w1 = p[1], w2 = p[2];
+      const unsigned a0 = __funnelshift_r(w0, w1, 8), b0 = __funnelshift_r(w1, w2, 8);
+      const unsigned a1 = __funnelshift_r(w0, w1, 16), b1 = __funnelshift_r(w1, w2, 16);
+      const unsigned a2 = __funnelshift_r(w0, w1, 24), b2 = __funnelshift_r(w1, w2, 24);
+      hrow[q][0] = __dp4a(a0, 0x38302212u, __dp4a(b0, 0x00122230u, 0u));
+      hrow[q][1] = __dp4a(a1, 0x38302212u, __dp4a(b1, 0x00122230u, 0u));
+      hrow[q][2] = __dp4a(a2, 0x38302212u, __dp4a(b2, 0x00122230u, 0u));
+      hrow[q][3] = __dp4a(w1, 0x38302212u, __dp4a(w2, 0x00122230u, 0u));
     }
+    uint4 o;
+    o.x = hrow[0][0] | (hrow[1][0] << 16);
+    o.y = hrow[0][1] | (hrow[1][1] << 16);
+    o.z = hrow[0][2] | (hrow[1][2] << 16);
+    o.w = hrow[0][3] | (hrow[1][3] << 16);
+    *reinterpret_cast<uint4*>(hp + rp * kBlurTW + 4 * xg) = o;
+  }
+  __syncthreads();
+  // vertical: out rows 2yp, 2yp+1 need tile rows 2yp .. 2yp+7 = row pairs yp .. yp+3
+  u8* dst = blur + (size_t)f * blurStride + L.boff;
+  for (int i = tid; i < (kBlurTH / 2) * (kBlurTW / 4); i += 256) {
+    const int yp = i / (kBlurTW / 4), xg = i - yp * (kBlurTW / 4);
+    const int x = x0 + 4 * xg, y = y0 + 2 * yp;
+    if (x >= L.w || y >= L.h) continue;
+    const uint4 q0 = *reinterpret_cast<const uint4*>(hp + (yp + 0) * kBlurTW + 4 * xg);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(hp + (yp + 1) * kBlurTW + 4 * xg);
+    const uint4 q2 = *reinterpret_cast<const uint4*>(hp + (yp + 2) * kBlurTW + 4 * xg);
+    const uint4 q3 = *reinterpret_cast<const uint4*>(hp + (yp + 3) * kBlurTW + 4 * xg);
+    const unsigned c0[4] = {q0.x, q0.y, q0.z, q0.w}, c1[4] = {q1.x, q1.y, q1.z, q1.w};
+    const unsigned c2[4] = {q2.x, q2.y, q2.z, q2.w}, c3[4] = {q3.x, q3.y, q3.z, q3.w};
+    unsigned o0 = 0, o1 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      unsigned e = __dp2a_lo(c0[j], 0x2212u, 32768u);   // rows 0,1 x (k0,k1)
+      e = __dp2a_lo(c1[j], 0x3830u, e);                 // rows 2,3 x (k2,k3)
+      e = __dp2a_lo(c2[j], 0x2230u, e);                 // rows 4,5 x (k4,k5)
+      e = __dp2a_lo(c3[j], 0x0012u, e);                 // row 6 x k6
+      unsigned o = __dp2a_lo(c0[j], 0x1200u, 32768u);   // row 1 x k0
+      o = __dp2a_lo(c1[j], 0x3022u, o);                 // rows 2,3 x (k1,k2)
+      o = __dp2a_lo(c2[j], 0x3038u, o);                 // rows 4,5 x (k3,k4)
+      o = __dp2a_lo(c3[j], 0x1222u, o);                 // rows 6,7 x (k5,k6)
+      o0 |= (e >> 16) << (8 * j);
+      o1 |= (o >> 16) << (8 * j);
+    }
+    *reinterpret_cast<unsigned*>(dst + (long long)y * L.bpitch + x) = o0;
+    if (y + 1 < L.h) *reinterpret_cast<unsigned*>(dst + (long long)(y + 1) * L.bpitch + x) = o1;
   }
 }
 
@@ -568,83 +741,140 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
+constexpr int kPatchWords = 11;   // 44 bytes per staged patch row: 37 + alignment slack
+constexpr int kDescSlots = 32;    // keypoint slots per CTA (8 warps x 4)
+
+// One CTA handles 32 consecutive output slots of a frame. Phase A: one warp per keypoint sums
+// the intensity-centroid moments (IC_Angle) and evaluates fastAtan2. Phase B: ONE thread per
+// keypoint evaluates cos/sin in double precision and rounds to float (matches glibc's cosf/sinf,
+// which are correctly rounded in all but vanishing cases; doing this per warp would issue the
+// same FP64 instruction stream 32 times more often). Phase C: one warp per keypoint stages the
+// 37-row blurred patch in shared memory (aligned word loads; sampling global memory directly
+// costs one L1 wavefront per sample) and evaluates the 256 steered-BRIEF comparisons.
 __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                   const u8* __restrict__ blur, size_t blurStride,
                                                   const uint2* __restrict__ kept, const int* __restrict__ keptCount,
                                                   int keptTotal, const signed char* __restrict__ pattern,
                                                   orb_keypoint* __restrict__ outK, u8* __restrict__ outD,
                                                   int* __restrict__ outN, int cap, int* __restrict__ overflow) {
-  const int lane = threadIdx.x & 31;
-  const int slotIdx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  __shared__ unsigned s_patch[8][37 * kPatchWords];
+  __shared__ int s_lvl[kDescSlots], s_xy[kDescSlots], s_resp[kDescSlots];
+  __shared__ float s_angle[kDescSlots], s_cos[kDescSlots], s_sin[kDescSlots];
+  __shared__ int s_prefix[kMaxLevels + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = blockIdx.y;
+  const int slot0 = blockIdx.x * kDescSlots;
   // concatenate levels in ascending octave (:1585-1645)
-  int l = -1, j = 0, total = 0;
-  for (int q = 0; q < g.nlevels; q++) {
-    const int c = keptCount[f * g.nlevels + q];
-    if (l < 0 && slotIdx < total + c) { l = q; j = slotIdx - total; }
-    total += c;
-  }
-  if (slotIdx == 0 && lane == 0) {
-    outN[f] = min(total, cap);
-    if (total > cap) atomicOr(overflow, 4);
-  }
-  if (l < 0 || slotIdx >= cap) return;
-  const LevelGeom& L = g.lv[l];
-  const uint2 rec = kept[(size_t)f * keptTotal + L.keptOff + j];
-  const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
-
-  // IC_Angle: lanes span u in [-15,15], loop over rows v; |u| <= umax[|v|]
-  const u8* c = pyr + (size_t)f * pyrStride + L.off + (long long)y * L.pitch + x;
-  const int u = lane - kHalfPatch;
-  int m10 = 0, m01 = 0;
-#pragma unroll 1
-  for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
-    const int d = c_umax[v < 0 ? -v : v];
-    if (lane < 31 && u >= -d && u <= d) {
-      const int val = c[(long long)v * L.pitch + u];
-      m10 += u * val;
-      m01 += v * val;
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int q = 0; q < g.nlevels; q++) {
+      s_prefix[q] = total;
+      total += keptCount[f * g.nlevels + q];
+    }
+    s_prefix[g.nlevels] = total;
+    if (blockIdx.x == 0) {
+      outN[f] = min(total, cap);
+      if (total > cap) atomicOr(overflow, 4);
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-  }
-  const float angle = fast_atan2_deg((float)m01, (float)m10);
+  __syncthreads();
+  const int total = min(s_prefix[g.nlevels], cap);
+  if (slot0 >= total) return;
 
-  // steered BRIEF on the blurred level; lane i produces descriptor byte i
-  const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
-  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-  const u8* cb = blur + (size_t)f * blurStride + L.boff + (long long)y * L.bpitch + x;
+  // ---- phase A: moments + fastAtan2
+#pragma unroll 1
+  for (int k = 0; k < kDescSlots / 8; k++) {
+    const int sl = wid + 8 * k, slotIdx = slot0 + sl;
+    if (slotIdx >= total) { if (lane == 0) s_lvl[sl] = -1; continue; }
+    int l = 0;
+    while (l + 1 < g.nlevels && slotIdx >= s_prefix[l + 1]) l++;
+    const LevelGeom& L = g.lv[l];
+    const uint2 rec = kept[(size_t)f * keptTotal + L.keptOff + (slotIdx - s_prefix[l])];
+    const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
+    // IC_Angle: lanes span u in [-15,15], loop over rows v; |u| <= umax[|v|]
+    const u8* c = pyr + (size_t)f * pyrStride + L.off + (long long)y * L.pitch + x;
+    const int u = lane - kHalfPatch;
+    int m10 = 0, m01 = 0;
+#pragma unroll 4
+    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+      const int d = c_umax[v < 0 ? -v : v];
+      if (lane < 31 && u >= -d && u <= d) {
+        const int val = c[(long long)v * L.pitch + u];
+        m10 += u * val;
+        m01 += v * val;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    if (lane == 0) {
+      s_lvl[sl] = l;
+      s_xy[sl] = (int)rec.x;
+      s_resp[sl] = (int)rec.y;
+      s_angle[sl] = fast_atan2_deg((float)m01, (float)m10);
+    }
+  }
+  __syncthreads();
+  // ---- phase B: cos / sin, one thread per keypoint
+  if (threadIdx.x < kDescSlots && s_lvl[threadIdx.x] >= 0) {
+    const float ang = __fmul_rn(s_angle[threadIdx.x], (float)(3.14159265358979323846 / 180.f));
+    double sn, cs;
+    sincos((double)ang, &sn, &cs);
+    s_cos[threadIdx.x] = (float)cs;
+    s_sin[threadIdx.x] = (float)sn;
+  }
+  __syncthreads();
+  // ---- phase C: steered BRIEF on the blurred level; lane i produces descriptor byte i
   const int4* pp = reinterpret_cast<const int4*>(pattern) + lane * 2;
   const int4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
   const int words[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-  int val = 0;
+  unsigned* pw = s_patch[wid];
+#pragma unroll 1
+  for (int k = 0; k < kDescSlots / 8; k++) {
+    const int sl = wid + 8 * k, slotIdx = slot0 + sl;
+    const int l = s_lvl[sl];
+    if (l < 0) continue;
+    const LevelGeom& L = g.lv[l];
+    const int x = s_xy[sl] & 0xffff, y = (int)((unsigned)s_xy[sl] >> 16);
+    const float a = s_cos[sl], b = s_sin[sl];
+    const int xa = (x - 18) & ~3;
+    const u8* cb0 = blur + (size_t)f * blurStride + L.boff + (long long)(y - 18) * L.bpitch + xa;
+    __syncwarp();
+#pragma unroll 13
+    for (int i = lane; i < 37 * kPatchWords; i += 32) {
+      const int r = i / kPatchWords, wd = i - r * kPatchWords;
+      pw[i] = *reinterpret_cast<const unsigned*>(cb0 + (long long)r * L.bpitch + 4 * wd);
+    }
+    __syncwarp();
+    const u8* cb = reinterpret_cast<const u8*>(pw) + 18 * (4 * kPatchWords) + (x - xa);
+    int val = 0;
 #pragma unroll
-  for (int bit = 0; bit < 8; bit++) {
-    const int wd = words[bit];
-    const float x0 = (float)(signed char)(wd & 0xff), y0 = (float)(signed char)((wd >> 8) & 0xff);
-    const float x1 = (float)(signed char)((wd >> 16) & 0xff), y1 = (float)(signed char)((wd >> 24) & 0xff);
-    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    const int t0 = cb[(long long)r0 * L.bpitch + c0], t1 = cb[(long long)r1 * L.bpitch + c1];
-    val |= (t0 < t1) << bit;
-  }
-  const size_t o = (size_t)f * cap + slotIdx;
-  outD[o * 32 + lane] = (u8)val;
-  if (lane == 0) {
-    orb_keypoint kp;
-    kp.x = l ? __fmul_rn((float)x, L.scale) : (float)x;
-    kp.y = l ? __fmul_rn((float)y, L.scale) : (float)y;
-    kp.size = L.patch;
-    kp.angle = angle;
-    kp.response = (float)rec.y;
-    kp.octave = l;
-    kp.class_id = -1;
-    outK[o] = kp;
+    for (int bit = 0; bit < 8; bit++) {
+      const int wd = words[bit];
+      const float x0 = (float)(signed char)(wd & 0xff), y0 = (float)(signed char)((wd >> 8) & 0xff);
+      const float x1 = (float)(signed char)((wd >> 16) & 0xff), y1 = (float)(signed char)((wd >> 24) & 0xff);
+      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+      const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+      const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+      const int t0 = cb[r0 * (4 * kPatchWords) + c0], t1 = cb[r1 * (4 * kPatchWords) + c1];
+      val |= (t0 < t1) << bit;
+    }
+    const size_t o = (size_t)f * cap + slotIdx;
+    outD[o * 32 + lane] = (u8)val;
+    if (lane == 0) {
+      orb_keypoint kp;
+      kp.x = l ? __fmul_rn((float)x, L.scale) : (float)x;
+      kp.y = l ? __fmul_rn((float)y, L.scale) : (float)y;
+      kp.size = L.patch;
+      kp.angle = s_angle[sl];
+      kp.response = (float)s_resp[sl];
+      kp.octave = l;
+      kp.class_id = -1;
+      outK[o] = kp;
+    }
   }
 }
 
@@ -788,8 +1018,8 @@ int build_geom(orb_extractor* e, int W, int H) {
     L.scale = e->scale[l];
     L.patch = (float)(int)(31.f * e->scale[l]);  // :1164
     if (l > 0) {
-      L.tapX = tapOff; tapOff += L.w;
-      L.tapY = tapOff; tapOff += L.h;
+      L.tapX = tapOff; tapOff += round_up(L.w, 2) + 8;  // even offsets: int4 loads of two taps; slack for 8-tap reads
+      L.tapY = tapOff; tapOff += round_up(L.h, 2);
       e->taps.resize(tapOff);
       make_taps(L.w, g.lv[l - 1].w, e->taps.data() + L.tapX);
       make_taps(L.h, g.lv[l - 1].h, e->taps.data() + L.tapY);
@@ -803,7 +1033,12 @@ int build_geom(orb_extractor* e, int W, int H) {
   e->keptTotal = keptOff;
   e->nodeCap = round_up(nodeCap, 2);
   e->maxKp = maxKp;
-  e->fastSmem = (size_t)((maxCw + 6 + 3) & ~3) * (maxCh + 6) + (size_t)(maxCw + 2) * (maxCh + 2);
+  {
+    const size_t S = (maxCw + 1) / 2;
+    e->fastSmem = 4 * (S + 6) * (maxCh + 6) + 2 * ((S * maxCh + 1) & ~(size_t)1) + 2 * (((size_t)maxCw * maxCh + 1) & ~(size_t)1) +
+                  (size_t)(maxCw + 2) * (maxCh + 2) + 16;
+    if ((size_t)maxCw * maxCh >= 32768) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
+  }
   e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8);
   if (e->qtSmem > 220 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "features per level too large for the quadtree kernel's shared memory");
   if (e->fastSmem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
@@ -872,19 +1107,19 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   if ((st = stage_mark(e, s))) return st;
   {
     const LevelGeom& L = g.lv[0];
-    dim3 grid((L.w + 2 * kEdge + 255) / 256, L.h + 2 * kEdge, B);
-    k_level0_border<<<grid, 256, 0, s>>>(g, d_img, step, frameStride, e->d_pyr, e->pyrStride);
+    dim3 grid((L.pitch / 16 + 31) / 32, (L.h + 2 * kEdge + 7) / 8, B);
+    k_level0_border<<<grid, dim3(32, 8), 0, s>>>(g, d_img, step, frameStride, e->d_pyr, e->pyrStride);
     launches++;
   }
   for (int l = 1; l < nl; l++) {
     const LevelGeom& L = g.lv[l];
-    dim3 grid((L.w + 2 * kEdge + 255) / 256, L.h + 2 * kEdge, B);
-    k_resize_border<<<grid, 256, 0, s>>>(g, l, e->d_pyr, e->pyrStride, e->d_taps);
+    dim3 grid((L.pitch / 4 + 31) / 32, (L.h + 2 * kEdge + 7) / 8, B);
+    k_resize_border<<<grid, dim3(32, 8), 0, s>>>(g, l, e->d_pyr, e->pyrStride, e->d_taps);
     launches++;
   }
   ORB_CUDA(cudaMemsetAsync(e->d_candCount, 0, (size_t)B * nl * sizeof(int), s));
   if ((st = stage_mark(e, s))) return st;
-  k_fast_cells<<<dim3(g.totalCells, B), 128, e->fastSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_cand, e->d_candCount,
+  k_fast_cells<<<dim3(g.totalCells, B), kFastThreads, e->fastSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_cand, e->d_candCount,
                                                               e->candTotal);
   launches++;
   if ((st = stage_mark(e, s))) return st;
@@ -897,7 +1132,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   launches++;
   if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);
-  k_describe<<<dim3((slots * 32 + 255) / 256, B), 256, 0, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride,
+  k_describe<<<dim3((slots + kDescSlots - 1) / kDescSlots, B), 256, 0, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride,
                                                               e->d_kept, e->d_keptCount, e->keptTotal, e->d_pattern,
                                                               d_kps, d_desc, d_counts, cap, e->d_overflow);
   launches++;

@@ -258,12 +258,13 @@ constexpr int kApThreads = 256;
 // column keyframe's descriptors are staged in shared memory and broadcast.
 template <int RPT>
 __global__ void __launch_bounds__(kApThreads) k_allpairs(const u8* __restrict__ all, int nKF, int nDesc, int rowBegin,
-                                                         int colsPerBlock, float nnratio, int* __restrict__ counts) {
+                                                         int colBegin, int colEnd, int colsPerBlock, float nnratio,
+                                                         int* __restrict__ counts) {
   extern __shared__ __align__(16) uint4 bsm[];  // nDesc x 2 uint4
   __shared__ int s_cnt[kApThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int i = rowBegin + blockIdx.y;
-  const int j0 = blockIdx.x * colsPerBlock, j1 = min(j0 + colsPerBlock, nKF);
+  const int j0 = colBegin + blockIdx.x * colsPerBlock, j1 = min(j0 + colsPerBlock, colEnd);
   unsigned a[RPT][8];
 #pragma unroll
   for (int r = 0; r < RPT; r++) {
@@ -497,8 +498,9 @@ int orb_match_pairs_device(orb_matcher* m, const uint8_t* d_descriptors, const f
 }
 
 int orb_match_allpairs_device(orb_matcher* m, const uint8_t* d_all, int n_kf, int n_desc, int row_begin, int row_end,
-                              float nnratio, int32_t* d_counts, void* stream) {
-  if (!m || !d_all || !d_counts || n_kf <= 0 || n_desc <= 0 || row_begin < 0 || row_end > n_kf || row_end <= row_begin)
+                              int col_begin, int col_end, float nnratio, int32_t* d_counts, void* stream) {
+  if (!m || !d_all || !d_counts || n_kf <= 0 || n_desc <= 0 || row_begin < 0 || row_end > n_kf || row_end <= row_begin ||
+      col_begin < 0 || col_end > n_kf || col_end <= col_begin)
     ORB_FAIL(ORB_ERR_INVALID, "bad argument");
   ORB_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
@@ -507,15 +509,16 @@ int orb_match_allpairs_device(orb_matcher* m, const uint8_t* d_all, int n_kf, in
   if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "more than 6400 descriptors per keyframe");
   // enough column spans to fill the machine several times over, but long enough to amortise
   // the register load of the row keyframe
-  int spans = std::max(1, std::min(n_kf, (148 * 8 + rows - 1) / rows));
-  const int colsPerBlock = (n_kf + spans - 1) / spans;
-  spans = (n_kf + colsPerBlock - 1) / colsPerBlock;
+  const int ncols = col_end - col_begin;
+  int spans = std::max(1, std::min(ncols, (148 * 8 + rows - 1) / rows));
+  const int colsPerBlock = (ncols + spans - 1) / spans;
+  spans = (ncols + colsPerBlock - 1) / colsPerBlock;
   const int rpt = (n_desc + kApThreads - 1) / kApThreads;
   dim3 grid(spans, rows);
 #define ORB_AP(R)                                                                                                  \
   do {                                                                                                             \
     ORB_CUDA(cudaFuncSetAttribute(k_allpairs<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-    k_allpairs<R><<<grid, kApThreads, smem, s>>>(d_all, n_kf, n_desc, row_begin, colsPerBlock, nnratio, d_counts); \
+    k_allpairs<R><<<grid, kApThreads, smem, s>>>(d_all, n_kf, n_desc, row_begin, col_begin, col_end, colsPerBlock, nnratio, d_counts); \
   } while (0)
   if (rpt <= 1) ORB_AP(1);
   else if (rpt <= 2) ORB_AP(2);

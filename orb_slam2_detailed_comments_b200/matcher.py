@@ -90,11 +90,13 @@ class ORBmatcher:
                                              int(self.mbCheckOrientation), ptr(d_matches12), ptr(d_nmatches),
                                              C.c_void_p(stream or 0)))
 
-    def match_allpairs_device(self, d_all, row_begin, row_end, d_counts, stream=None):
-        """d_all (nKF,nDesc,32) u8 holding ALL keyframes; d_counts (row_end-row_begin, nKF) i32."""
+    def match_allpairs_device(self, d_all, row_begin, row_end, d_counts, stream=None, col_begin=0, col_end=None):
+        """d_all (nKF,nDesc,32) u8 holding ALL keyframes; d_counts (row_end-row_begin, nKF) i32.
+        Only columns [col_begin, col_end) are computed by this call."""
         nkf, nd = d_all.shape[0], d_all.shape[1]
-        check(self._L.orb_match_allpairs_device(self._h, ptr(d_all), nkf, nd, row_begin, row_end, self.mfNNratio,
-                                                ptr(d_counts), C.c_void_p(stream or 0)))
+        col_end = nkf if col_end is None else col_end
+        check(self._L.orb_match_allpairs_device(self._h, ptr(d_all), nkf, nd, row_begin, row_end, col_begin, col_end,
+                                                self.mfNNratio, ptr(d_counts), C.c_void_p(stream or 0)))
 
     def hamming_matrix_device(self, d_a, d_b, d_out, stream=None):
         check(self._L.orb_hamming_matrix_device(self._h, ptr(d_a), d_a.shape[0], ptr(d_b), d_b.shape[0], ptr(d_out),

@@ -151,8 +151,12 @@ def test_allpairs_counts(oracle):
     d_all = torch.from_numpy(all_desc).cuda()
     d_counts = torch.zeros((nkf, nkf), dtype=torch.int32, device="cuda")
     m.match_allpairs_device(d_all, 0, nkf, d_counts)
+    d_cols = torch.zeros((nkf, nkf), dtype=torch.int32, device="cuda")
+    m.match_allpairs_device(d_all, 0, nkf, d_cols, col_begin=0, col_end=4)
+    m.match_allpairs_device(d_all, 0, nkf, d_cols, col_begin=4, col_end=nkf)
     m.synchronize()
     assert np.array_equal(d_counts.cpu().numpy(), ref)
+    assert np.array_equal(d_cols.cpu().numpy(), ref)     # same matrix assembled from two column blocks
     # a row block, as one rank of the sharded workload computes it
     d_part = torch.zeros((3, nkf), dtype=torch.int32, device="cuda")
     m.match_allpairs_device(d_all, 4, 7, d_part)
