@@ -22,6 +22,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_pipeline.h>
+
 #include "../../include/orb_pattern_data.h"
 #include "orb_common.cuh"
 
@@ -144,11 +146,15 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
   const int by = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
   if (gi * 4 >= D.pitch || by >= D.h + 2 * kEdge) return;
-  const int c0 = 4 * (gi - 8);
+  // interior 4-px groups first (fast path, homogeneous warps), then the 8 left-border groups, then
+  // the right border / padding groups
+  const int nInt = D.w >> 2;
+  const int c0 = gi < nInt ? 4 * gi : (gi - nInt < 8 ? 4 * (gi - nInt) - kLeftPad : 4 * (gi - 8));
   const int y = reflect101(by - kEdge, D.h);
   const int2 ty = __ldg(taps + D.tapY + y);
   const int sy0 = ty.x, sy1 = min(sy0 + 1, S.h - 1);
   const int cy0 = ty.y & 0xffff, cy1 = ty.y >> 16;
+  const unsigned cy0s = (unsigned)cy0 << 16, cy1s = (unsigned)cy1 << 16;
   const u8* src = pyr + (size_t)f * pyrStride + S.off;
   const u8* r0 = src + (long long)sy0 * S.pitch;
   const u8* r1 = src + (long long)sy1 * S.pitch;
@@ -177,10 +183,11 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
       const unsigned dlt = (unsigned)(sx[j] - a);
       const unsigned sel = dlt | ((dlt + 1) << 4);          // bytes (dlt, dlt+1) of the window
       const unsigned q0 = __byte_perm(lo0, hi0, sel), q1 = __byte_perm(lo1, hi1, sel);
-      const int h0 = (int)__dp2a_lo(cf[j], q0, 0u);         // c0*p[sx] + c1*p[sx+1]
-      const int h1 = (int)__dp2a_lo(cf[j], q1, 0u);
-      const int v = (((cy0 * (h0 >> 4)) >> 16) + ((cy1 * (h1 >> 4)) >> 16) + 2) >> 2;
-      out |= (unsigned)min(max(v, 0), 255) << (8 * j);
+      const unsigned h0 = __dp2a_lo(cf[j], q0, 0u);         // c0*p[sx] + c1*p[sx+1]  (<= 255*2048)
+      const unsigned h1 = __dp2a_lo(cf[j], q1, 0u);
+      // ((cy*(h>>4))>>16) == umulhi(cy<<16, h>>4); the sum is <= 1020, so the result needs no clamp
+      const unsigned v = (__umulhi(cy0s, h0 >> 4) + __umulhi(cy1s, h1 >> 4) + 2u) >> 2;
+      out |= v << (8 * j);
     }
   } else {
 #pragma unroll
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
       out |= resize_px_slow(r0, r1, __ldg(taps + D.tapX + x), S.w, cy0, cy1) << (8 * j);
     }
   }
-  u8* dst = pyr + (size_t)f * pyrStride + D.off + (long long)(by - kEdge) * D.pitch - kLeftPad + 4 * gi;
+  u8* dst = pyr + (size_t)f * pyrStride + D.off + (long long)(by - kEdge) * D.pitch + c0;
   *reinterpret_cast<unsigned*>(dst) = out;
 }
 
@@ -216,17 +223,17 @@ __device__ __forceinline__ void fast_load_diffs(const unsigned* p, int tp, FastD
   D.d[12] = c - p[-3];   D.d[13] = c - rp1[-3]; D.d[14] = c - rp2[-2];  D.d[15] = c - rp3[-1];
 }
 
-// Necessary condition for a corner at threshold t: every 9-arc holds one pixel of each
-// antipodal pair (k, k+8). Returns an upper bound of S + 256 in each half.
-__device__ __forceinline__ unsigned fast_bound(const FastDiffs& D) {
-  unsigned hi[8], lo[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    hi[j] = __vmaxs2(D.d[j], D.d[j + 8]);
-    lo[j] = __vmins2(D.d[j], D.d[j + 8]);
-  }
-  const unsigned minhi = __vimin3_s16x2(__vimin3_s16x2(hi[0], hi[1], hi[2]), __vimin3_s16x2(hi[3], hi[4], hi[5]), __vmins2(hi[6], hi[7]));
-  const unsigned maxlo = __vimax3_s16x2(__vimax3_s16x2(lo[0], lo[1], lo[2]), __vimax3_s16x2(lo[3], lo[4], lo[5]), __vmaxs2(lo[6], lo[7]));
+// Cheap necessary condition for a corner at threshold t, on 8 of the 16 circle pixels: every
+// 9-arc holds one pixel of each antipodal pair (k, k+8); here the 4 pairs of the even positions.
+// Returns an upper bound of S + 256 in each half.
+__device__ __forceinline__ unsigned fast_bound4(const unsigned* p, int tp) {
+  const unsigned c = p[0] + 0x00FF00FFu;
+  const unsigned d0 = c - p[3 * tp], d8 = c - p[-3 * tp];
+  const unsigned d4 = c - p[3], d12 = c - p[-3];
+  const unsigned d2 = c - p[2 * tp + 2], d10 = c - p[-2 * tp - 2];
+  const unsigned d6 = c - p[-2 * tp + 2], d14 = c - p[2 * tp - 2];
+  const unsigned minhi = __vmins2(__vimin3_s16x2(__vmaxs2(d0, d8), __vmaxs2(d4, d12), __vmaxs2(d2, d10)), __vmaxs2(d6, d14));
+  const unsigned maxlo = __vmaxs2(__vimax3_s16x2(__vmins2(d0, d8), __vmins2(d4, d12), __vmins2(d2, d10)), __vmins2(d6, d14));
   return __vmaxs2(minhi, 0x01FE01FEu - maxlo);
 }
 
@@ -254,102 +261,219 @@ __device__ __forceinline__ unsigned fast_exact(const FastDiffs& D) {
   return __vmaxs2(A, 0x01FE01FEu - B);
 }
 
-// One CTA per cell. The cell's detection window is x in [19+j*wCell, min(18+(j+1)*wCell, w-20)]
-// (sub-image [iniX,maxX) minus FAST's own 3-px frame), so windows tile the level and the 3x3
-// NMS never sees across a cell boundary (scores outside the window count as 0).
-// Phases: tile -> prefilter (queue the pairs that may hold a corner) -> exact score on the queue
-// (dense, no divergence) -> 3x3 NMS on the hit list -> iniTh / minTh decision -> emit.
-constexpr int kFastThreads = 128;
+// One WARP per cell, persistent warps striding over all (frame, level, cell) items of the chunk.
+// The cell's detection window is x in [19+j*wCell, min(18+(j+1)*wCell, w-20)] (sub-image
+// [iniX,maxX) minus FAST's own 3-px frame), so windows tile the level and the 3x3 NMS never sees
+// across a cell boundary (scores outside the window count as 0).
+// Per cell: raw bytes arrive by cp.async (prefetched while the previous cell is being scored) ->
+// pair-interleaved tile -> 8-pixel prefilter with ballot compaction -> exact score on the queue
+// (dense, no divergence) -> 3x3 NMS on the hit list -> iniTh / minTh decision -> one atomicAdd
+// per cell reserves the output range. Only __syncwarp() is needed: warps run out of phase and
+// hide each other's latencies.
+constexpr int kFastWarps = 4;
+constexpr int kFastThreads = 32 * kFastWarps;
+
+struct FastSmemLayout {   // per-warp shared memory carve-up (in bytes), sized for the largest cell
+  int rawPitchWords, rawBytes, tileBytes, queueBytes, hitsBytes, scBytes, total;
+};
+
+struct CellDesc {
+  const u8* src;          // 4-byte aligned address at or left of tile byte (0,0) = image (x0-3, y0-3)
+  int ox;                 // tile column 0 sits `ox` bytes into a raw row
+  int pitch, cw, ch, x0, y0, l, f, rw;
+};
+
+__device__ __forceinline__ bool fast_cell_desc(const Geom& g, const u8* pyr, size_t pyrStride, int item, CellDesc& c) {
+  const int f = item / g.totalCells;
+  const int cc = item - f * g.totalCells;
+  int l = 0;
+#pragma unroll 1
+  while (l + 1 < g.nlevels && cc >= g.lv[l + 1].cellBase) l++;
+  const LevelGeom& L = g.lv[l];
+  const int cell = cc - L.cellBase;
+  const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
+  c.x0 = kEdge + cj * L.wCell;
+  c.y0 = kEdge + ci * L.hCell;
+  c.cw = min(c.x0 + L.wCell - 1, L.w - kEdge - 1) - c.x0 + 1;
+  c.ch = min(c.y0 + L.hCell - 1, L.h - kEdge - 1) - c.y0 + 1;
+  c.l = l;
+  c.f = f;
+  c.pitch = L.pitch;
+  const int xs = (c.x0 - 3) & ~3;
+  c.ox = (c.x0 - 3) - xs;
+  c.rw = (c.ox + c.cw + 6 + 3) >> 2;
+  c.src = pyr + (size_t)f * pyrStride + L.off + (long long)(c.y0 - 3) * L.pitch + xs;
+  return c.cw > 0 && c.ch > 0;
+}
+
+__device__ __forceinline__ void fast_prefetch(const CellDesc& c, unsigned* raw, int rawPitchWords, int lane) {
+  // (ch+6) rows x rw words, 32 words per step
+  const int n = (c.ch + 6) * c.rw;
+  int r = lane / c.rw, wd = lane - r * c.rw;
+  const int dr = 32 / c.rw, dw = 32 - dr * c.rw;
+  for (int i = lane; i < n; i += 32) {
+    __pipeline_memcpy_async(raw + r * rawPitchWords + wd, c.src + (r * c.pitch + 4 * wd), 4);
+    wd += dw;
+    r += dr;
+    if (wd >= c.rw) { wd -= c.rw; r++; }
+  }
+  __pipeline_commit();
+}
 
 __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                              uint2* __restrict__ cand, int* __restrict__ candCount,
-                                                             int candTotal) {
+                                                             int candTotal, int nItems, const FastSmemLayout lay) {
   extern __shared__ __align__(16) u8 smem[];
-  __shared__ int s_nq, s_nh;
-  const int f = blockIdx.y, tid = threadIdx.x;
-  int l = 0;
-#pragma unroll 1
-  while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].cellBase) l++;
-  const LevelGeom& L = g.lv[l];
-  const int cell = blockIdx.x - L.cellBase;
-  const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
-  const int x0 = kEdge + cj * L.wCell, x1 = min(x0 + L.wCell - 1, L.w - kEdge - 1);
-  const int y0 = kEdge + ci * L.hCell, y1 = min(y0 + L.hCell - 1, L.h - kEdge - 1);
-  const int cw = x1 - x0 + 1, ch = y1 - y0 + 1;
-  if (cw <= 0 || ch <= 0) return;
-  const int S = (cw + 1) >> 1;            // pair stride
-  const int tp = S + 6;                   // tile pitch in words
-  const int sp = cw + 2;                  // score pitch (1-px zero apron)
-  unsigned* tile = reinterpret_cast<unsigned*>(smem);
-  unsigned short* queue = reinterpret_cast<unsigned short*>(tile + tp * (ch + 6));  // pair items to score exactly
-  unsigned short* hits = queue + ((S * ch + 1) & ~1);                                // pixels with S >= minTh
-  u8* sc = reinterpret_cast<u8*>(hits + ((cw * ch + 1) & ~1));
-  if (tid == 0) { s_nq = 0; s_nh = 0; }
-  const u8* src = pyr + (size_t)f * pyrStride + L.off + (long long)(y0 - 3) * L.pitch + (x0 - 3);
-  for (int i = tid; i < tp * (ch + 6); i += kFastThreads) {
-    const int r = i / tp, j = i - r * tp;
-    const u8* row = src + (long long)r * L.pitch;
-    const unsigned lo = row[j];
-    const unsigned hi = j + S < cw + 6 ? row[j + S] : 0u;
-    tile[i] = lo | (hi << 16);
-  }
-  for (int i = tid; i < (sp * (ch + 2) + 3) / 4; i += kFastThreads) reinterpret_cast<unsigned*>(sc)[i] = 0u;
-  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  u8* base = smem + wid * lay.total;
+  unsigned* raw = reinterpret_cast<unsigned*>(base);
+  unsigned* tile = reinterpret_cast<unsigned*>(base + lay.rawBytes);
+  unsigned short* queue = reinterpret_cast<unsigned short*>(base + lay.rawBytes + lay.tileBytes);
+  unsigned short* hits = reinterpret_cast<unsigned short*>(base + lay.rawBytes + lay.tileBytes + lay.queueBytes);
+  u8* sc = base + lay.rawBytes + lay.tileBytes + lay.queueBytes + lay.hitsBytes;
+  const unsigned ltmask = (1u << lane) - 1u;
   // bit 15 of a half is set iff its bound exceeds minTh + 255, i.e. a corner at minTh is possible
   const unsigned K = 0x7FFF7FFFu - (unsigned)(g.minTh + 255) * 0x00010001u;
-  for (int i = tid; i < S * ch; i += kFastThreads) {
-    const int r = i / S, x = i - r * S;
-    FastDiffs D;
-    fast_load_diffs(tile + (r + 3) * tp + (x + 3), tp, D);
-    if ((fast_bound(D) + K) & 0x80008000u) queue[atomicAdd(&s_nq, 1)] = (unsigned short)i;
-  }
-  __syncthreads();
-  const int nq = s_nq;
-  for (int e = tid; e < nq; e += kFastThreads) {
-    const int i = queue[e];
-    const int r = i / S, x = i - r * S;
-    FastDiffs D;
-    fast_load_diffs(tile + (r + 3) * tp + (x + 3), tp, D);
-    const unsigned s2 = fast_exact(D);
-    const int sLo = (int)(s2 & 0xffffu) - 256, sHi = (int)(s2 >> 16) - 256;
-    if (sLo >= g.minTh) {
-      sc[(r + 1) * sp + x + 1] = (u8)sLo;
-      hits[atomicAdd(&s_nh, 1)] = (unsigned short)(r * cw + x);
+
+  const int nWarps = gridDim.x * kFastWarps;
+  int item = blockIdx.x * kFastWarps + wid;
+  CellDesc c;
+  bool have = false;
+  while (item < nItems && !(have = fast_cell_desc(g, pyr, pyrStride, item, c))) item += nWarps;
+  if (have) fast_prefetch(c, raw, lay.rawPitchWords, lane);
+
+  while (have) {
+    const int cw = c.cw, ch = c.ch;
+    const int S = (cw + 1) >> 1;            // pair stride
+    const int tp = S + 6;                   // tile pitch in words
+    const int sp = cw + 2;                  // score pitch (1-px zero apron)
+    __pipeline_wait_prior(0);
+    __syncwarp();
+    // raw bytes -> pair-interleaved tile: word (r, j) = (T[r][j], T[r][j+S])
+    {
+      const u8* rb = reinterpret_cast<const u8*>(raw) + c.ox;
+      const int rp = lay.rawPitchWords * 4;
+      const int n = (ch + 6) * tp;
+      int r = lane / tp, j = lane - r * tp;
+      const int dr = 32 / tp, dj = 32 - dr * tp;
+      const int jmax = cw + 6 - S;   // pixels j+S beyond the tile are zero
+      for (int i = lane; i < n; i += 32) {
+        const u8* q = rb + r * rp + j;
+        const unsigned lo = q[0];
+        const unsigned hi = j < jmax ? q[S] : 0u;
+        tile[i] = lo | (hi << 16);
+        j += dj;
+        r += dr;
+        if (j >= tp) { j -= tp; r++; }
+      }
+      for (int i = lane; i < (sp * (ch + 2) + 3) / 4; i += 32) reinterpret_cast<unsigned*>(sc)[i] = 0u;
     }
-    if (x + S < cw && sHi >= g.minTh) {
-      sc[(r + 1) * sp + x + S + 1] = (u8)sHi;
-      hits[atomicAdd(&s_nh, 1)] = (unsigned short)(r * cw + x + S);
-    }
-  }
-  __syncthreads();
-  const int nh = s_nh;
-  int strong = 0;
-  for (int e = tid; e < nh; e += kFastThreads) {
-    const int p = hits[e];
-    const int r = p / cw, c = p - r * cw;
-    const u8* q = sc + (r + 1) * sp + c + 1;
-    const int s = q[0];
-    const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
-    if (s > m) {  // strict 3x3 maximum inside the cell
-      hits[e] = (unsigned short)(p | 0x8000);
-      strong |= s >= g.iniTh;
-    }
-  }
-  // cv::FAST(iniTh) result non-empty -> keep it, else the minTh result (:1111-1124)
-  const int th = __syncthreads_or(strong) ? g.iniTh : g.minTh;
-  int* cnt = candCount + f * g.nlevels + l;
-  uint2* out = cand + (size_t)f * candTotal + L.candOff;
-  for (int e = tid; e < nh; e += kFastThreads) {
-    const int p = hits[e];
-    if (p & 0x8000) {
-      const int pp = p & 0x7fff;
-      const int r = pp / cw, c = pp - r * cw;
-      const int s = sc[(r + 1) * sp + c + 1];
-      if (s >= th) {
-        const int idx = atomicAdd(cnt, 1);
-        if (idx < L.candCap) out[idx] = make_uint2((unsigned)(x0 + c) | ((unsigned)(y0 + r) << 16), (unsigned)s);
+    __syncwarp();
+    // the raw buffer is free again: prefetch the next cell of this warp
+    const CellDesc cur = c;
+    item += nWarps;
+    have = false;
+    while (item < nItems && !(have = fast_cell_desc(g, pyr, pyrStride, item, c))) item += nWarps;
+    if (have) fast_prefetch(c, raw, lay.rawPitchWords, lane);
+
+    // ---- prefilter: lanes cover one row (S > 16) or two rows (S <= 16) per step
+    int nq = 0;
+    {
+      const int two = S <= 16;
+      const int x = two ? (lane & 15) : lane;
+      const int rsub = two ? (lane >> 4) : 0, rstep = two ? 2 : 1;
+      for (int r0 = 0; r0 < ch; r0 += rstep) {
+        const int r = r0 + rsub;
+        bool pass = false;
+        if (x < S && r < ch) pass = ((fast_bound4(tile + (r + 3) * tp + (x + 3), tp) + K) & 0x80008000u) != 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (pass) queue[nq + __popc(m & ltmask)] = (unsigned short)((r << 6) | x);
+        nq += __popc(m);
       }
     }
+    __syncwarp();
+    // ---- exact score of the queued pairs
+    int nh = 0;
+    for (int e0 = 0; e0 < nq; e0 += 32) {
+      const int e = e0 + lane;
+      int sLo = 0, sHi = 0, r = 0, x = 0;
+      if (e < nq) {
+        const int i = queue[e];
+        r = i >> 6; x = i & 63;
+        FastDiffs D;
+        fast_load_diffs(tile + (r + 3) * tp + (x + 3), tp, D);
+        const unsigned s2 = fast_exact(D);
+        sLo = (int)(s2 & 0xffffu) - 256;
+        sHi = x + S < cw ? (int)(s2 >> 16) - 256 : 0;
+      }
+      const bool hLo = sLo >= g.minTh, hHi = sHi >= g.minTh;
+      const unsigned mLo = __ballot_sync(0xffffffffu, hLo), mHi = __ballot_sync(0xffffffffu, hHi);
+      if (hLo) {
+        sc[(r + 1) * sp + x + 1] = (u8)sLo;
+        hits[nh + __popc(mLo & ltmask)] = (unsigned short)((r << 6) | x);
+      }
+      nh += __popc(mLo);
+      if (hHi) {
+        sc[(r + 1) * sp + x + S + 1] = (u8)sHi;
+        hits[nh + __popc(mHi & ltmask)] = (unsigned short)((r << 6) | (x + S));
+      }
+      nh += __popc(mHi);
+    }
+    __syncwarp();
+    // ---- strict 3x3 maximum inside the cell; does cv::FAST(iniTh) find anything? (:1111-1124)
+    bool strong = false;
+    for (int e = lane; e < nh; e += 32) {
+      const int p = hits[e];
+      const int r = p >> 6, cx = p & 63;
+      const u8* q = sc + (r + 1) * sp + cx + 1;
+      const int s = q[0];
+      const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
+      if (s > m) {
+        hits[e] = (unsigned short)(p | 0x8000);
+        strong |= s >= g.iniTh;
+      }
+    }
+    const int th = __any_sync(0xffffffffu, strong) ? g.iniTh : g.minTh;
+    // ---- emit: count, reserve with one atomic, write
+    const LevelGeom& L = g.lv[cur.l];
+    int* cnt = candCount + cur.f * g.nlevels + cur.l;
+    uint2* out = cand + (size_t)cur.f * candTotal + L.candOff;
+    int total = 0;
+    for (int e0 = 0; e0 < nh; e0 += 32) {   // pass 1: count survivors
+      const int e = e0 + lane;
+      bool keep = false;
+      if (e < nh) {
+        const int p = hits[e];
+        if (p & 0x8000) keep = sc[(((p >> 6) & 0x1ff) + 1) * sp + (p & 63) + 1] >= th;
+      }
+      total += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (total > 0) {
+      int basei = 0;
+      if (lane == 0) basei = atomicAdd(cnt, total);
+      basei = __shfl_sync(0xffffffffu, basei, 0);
+      int done = 0;
+      for (int e0 = 0; e0 < nh; e0 += 32) {   // pass 2: write
+        const int e = e0 + lane;
+        bool keep = false;
+        int r = 0, cx = 0, s = 0;
+        if (e < nh) {
+          const int p = hits[e];
+          if (p & 0x8000) {
+            r = (p >> 6) & 0x1ff; cx = p & 63;
+            s = sc[(r + 1) * sp + cx + 1];
+            keep = s >= th;
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int idx = basei + done + __popc(m & ltmask);
+          if (idx < L.candCap) out[idx] = make_uint2((unsigned)(cur.x0 + cx) | ((unsigned)(cur.y0 + r) << 16), (unsigned)s);
+        }
+        done += __popc(m);
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -637,14 +761,14 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
 // byte windows built with funnel shifts, the vertical pass four IDP.2A per pixel on u16 pairs
 // (two tile rows interleaved per 32-bit word). One CTA blurs a 128 x 32 tile.
 constexpr int kBlurTW = 128, kBlurTH = 32;
-constexpr int kBlurInW = (kBlurTW + 8) / 4;   // words per input tile row: image x0-4 .. x0+131
-constexpr int kBlurInP = kBlurInW + 1;        // padded pitch (words)
+constexpr int kBlurChunks = (kBlurTW + 32) / 16;  // 16-byte chunks per input tile row: image x0-16 .. x0+143
+constexpr int kBlurInP = kBlurChunks * 4 + 4;     // tile pitch in words (16-B aligned rows, 4 words pad)
 constexpr int kBlurRows = kBlurTH + 6;        // input rows y0-3 .. y0+34
 constexpr int kBlurPairs = kBlurRows / 2;
 
 __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                u8* __restrict__ blur, size_t blurStride) {
-  __shared__ unsigned in[kBlurRows * kBlurInP];
+  __shared__ __align__(16) unsigned in[kBlurRows * kBlurInP];
   __shared__ __align__(16) unsigned hp[kBlurPairs * kBlurTW];  // (H[2p][x], H[2p+1][x]) as u16 pairs
   const int f = blockIdx.y, tid = threadIdx.x;
   int l = 0;
@@ -655,12 +779,14 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
   const int ty = t / L.blurTilesX, tx = t - ty * L.blurTilesX;
   const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
   const u8* src = pyr + (size_t)f * pyrStride + L.off;
-  const int xmax = (L.w + 16) & ~3;  // last word that still lies inside the 19-px border
-  for (int i = tid; i < kBlurRows * kBlurInW; i += 256) {
-    const int r = i / kBlurInW, c = i - r * kBlurInW;
-    const int y = min(y0 + r - 3, L.h + kEdge - 1), x = min(x0 - 4 + 4 * c, xmax);
-    in[r * kBlurInP + c] = *reinterpret_cast<const unsigned*>(src + (long long)y * L.pitch + x);
+  const int xlast = L.pitch - kLeftPad - 16;  // last 16-byte chunk of a bordered row (covers col w+18)
+  for (int i = tid; i < kBlurRows * kBlurChunks; i += 256) {
+    const int r = i / kBlurChunks, c = i - r * kBlurChunks;
+    const int y = min(y0 + r - 3, L.h + kEdge - 1), x = min(x0 - 16 + 16 * c, xlast);
+    __pipeline_memcpy_async(in + r * kBlurInP + 4 * c, src + (long long)y * L.pitch + x, 16);
   }
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
   __syncthreads();
   // horizontal: k = [18,34,48,56,48,34,18]; output x needs tile bytes (x+1 .. x+7)
   for (int i = tid; i < kBlurPairs * (kBlurTW / 4); i += 256) {
@@ -668,7 +794,7 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
     unsigned hrow[2][4];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-      const unsigned* p = in + (2 * rp + q) * kBlurInP + xg;
+      const unsigned* p = in + (2 * rp + q) * kBlurInP + xg + 3;  // image x0+4xg-4 = tile byte 4xg+12
       const unsigned w0 = p[0], w1 = p[1], w2 = p[2];
       const unsigned a0 = __funnelshift_r(w0, w1, 8), b0 = __funnelshift_r(w1, w2, 8);
       const unsigned a1 = __funnelshift_r(w0, w1, 16), b1 = __funnelshift_r(w1, w2, 16);
@@ -741,29 +867,49 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-constexpr int kPatchWords = 11;   // 44 bytes per staged patch row: 37 + alignment slack
+constexpr int kPatchWords = 11;   // blurred patch: 37 rows x 44 bytes (37 + alignment slack)
+constexpr int kMomWords = 9;      // unblurred patch: 31 rows x 36 bytes (31 + alignment slack)
 constexpr int kDescSlots = 32;    // keypoint slots per CTA (8 warps x 4)
+constexpr int kDescPerWarp = kDescSlots / 8;
+constexpr int kPatchBufWords = 37 * kPatchWords;  // one buffer holds either patch
+constexpr int kDescSmem = 8 * kDescPerWarp * kPatchBufWords * 4;
 
-// One CTA handles 32 consecutive output slots of a frame. Phase A: one warp per keypoint sums
-// the intensity-centroid moments (IC_Angle) and evaluates fastAtan2. Phase B: ONE thread per
-// keypoint evaluates cos/sin in double precision and rounds to float (matches glibc's cosf/sinf,
-// which are correctly rounded in all but vanishing cases; doing this per warp would issue the
-// same FP64 instruction stream 32 times more often). Phase C: one warp per keypoint stages the
-// 37-row blurred patch in shared memory (aligned word loads; sampling global memory directly
-// costs one L1 wavefront per sample) and evaluates the 256 steered-BRIEF comparisons.
+__device__ __forceinline__ void stage_patch(unsigned* dst, const u8* src, int pitch, int rows, int words, int lane) {
+  // rows x words 4-byte cp.async copies, 32 per step
+  int r = lane / words, wd = lane - r * words;
+  const int dr = 32 / words, dw = 32 - dr * words;
+  const int n = rows * words;
+  for (int i = lane; i < n; i += 32) {
+    __pipeline_memcpy_async(dst + i, src + (r * pitch + 4 * wd), 4);
+    wd += dw;
+    r += dr;
+    if (wd >= words) { wd -= words; r++; }
+  }
+  __pipeline_commit();
+}
+
+// One CTA handles 32 consecutive output slots of a frame, 4 per warp.
+//  A  each warp streams the 31x31 unblurred patches of its keypoints into shared memory
+//     (cp.async) and sums the intensity-centroid moments with IDP.4A: lane <-> patch row, the
+//     disc mask and the u weights live in registers; then fastAtan2 (IC_Angle :94-141).
+//  B  ONE thread per keypoint evaluates cos/sin in double precision and rounds to float (matches
+//     glibc's cosf/sinf; per warp this would issue the same FP64 stream 32 times more often).
+//  C  each warp streams the 37-row blurred patches (issued before B, so the copies overlap it)
+//     and evaluates the 256 steered-BRIEF comparisons from shared memory (:153-204).
 __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                   const u8* __restrict__ blur, size_t blurStride,
                                                   const uint2* __restrict__ kept, const int* __restrict__ keptCount,
                                                   int keptTotal, const signed char* __restrict__ pattern,
                                                   orb_keypoint* __restrict__ outK, u8* __restrict__ outD,
                                                   int* __restrict__ outN, int cap, int* __restrict__ overflow) {
-  __shared__ unsigned s_patch[8][37 * kPatchWords];
-  __shared__ int s_lvl[kDescSlots], s_xy[kDescSlots], s_resp[kDescSlots];
+  extern __shared__ __align__(16) unsigned s_buf[];   // [8 warps][kDescPerWarp][kPatchBufWords]
+  __shared__ int s_lvl[kDescSlots];
   __shared__ float s_angle[kDescSlots], s_cos[kDescSlots], s_sin[kDescSlots];
   __shared__ int s_prefix[kMaxLevels + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = blockIdx.y;
   const int slot0 = blockIdx.x * kDescSlots;
+  unsigned* wbuf = s_buf + wid * (kDescPerWarp * kPatchBufWords);
   // concatenate levels in ascending octave (:1585-1645)
   if (threadIdx.x == 0) {
     int total = 0;
@@ -777,44 +923,91 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
       if (total > cap) atomicOr(overflow, 4);
     }
   }
+  // disc mask / (u+15) weights of this lane's patch row v = lane-15: 8 words of 4 bytes
+  unsigned w1[8], wu[8];
+  {
+    const int v = lane - kHalfPatch;
+    const int d = lane < 31 ? c_umax[v < 0 ? -v : v] : -1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      unsigned a = 0, b = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int u = 4 * k + j - kHalfPatch;
+        const bool in = (u < 0 ? -u : u) <= d;
+        a |= (in ? 1u : 0u) << (8 * j);
+        b |= (in ? (unsigned)(u + kHalfPatch) : 0u) << (8 * j);
+      }
+      w1[k] = a;
+      wu[k] = b;
+    }
+  }
   __syncthreads();
   const int total = min(s_prefix[g.nlevels], cap);
   if (slot0 >= total) return;
 
-  // ---- phase A: moments + fastAtan2
-#pragma unroll 1
-  for (int k = 0; k < kDescSlots / 8; k++) {
-    const int sl = wid + 8 * k, slotIdx = slot0 + sl;
-    if (slotIdx >= total) { if (lane == 0) s_lvl[sl] = -1; continue; }
-    int l = 0;
-    while (l + 1 < g.nlevels && slotIdx >= s_prefix[l + 1]) l++;
-    const LevelGeom& L = g.lv[l];
-    const uint2 rec = kept[(size_t)f * keptTotal + L.keptOff + (slotIdx - s_prefix[l])];
-    const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
-    // IC_Angle: lanes span u in [-15,15], loop over rows v; |u| <= umax[|v|]
-    const u8* c = pyr + (size_t)f * pyrStride + L.off + (long long)y * L.pitch + x;
-    const int u = lane - kHalfPatch;
-    int m10 = 0, m01 = 0;
-#pragma unroll 4
-    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
-      const int d = c_umax[v < 0 ? -v : v];
-      if (lane < 31 && u >= -d && u <= d) {
-        const int val = c[(long long)v * L.pitch + u];
-        m10 += u * val;
-        m01 += v * val;
-      }
-    }
+  // ---- phase A: stage unblurred patches, moments, fastAtan2
+  int lvl[kDescPerWarp], px[kDescPerWarp], py[kDescPerWarp], resp[kDescPerWarp];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  for (int k = 0; k < kDescPerWarp; k++) {
+    const int slotIdx = slot0 + wid * kDescPerWarp + k;
+    lvl[k] = -1; px[k] = py[k] = resp[k] = 0;
+    if (slotIdx < total) {
+      int l = 0;
+      while (l + 1 < g.nlevels && slotIdx >= s_prefix[l + 1]) l++;
+      const LevelGeom& L = g.lv[l];
+      const uint2 rec = kept[(size_t)f * keptTotal + L.keptOff + (slotIdx - s_prefix[l])];
+      lvl[k] = l; px[k] = (int)(rec.x & 0xffffu); py[k] = (int)(rec.x >> 16); resp[k] = (int)rec.y;
+      const int xa = (px[k] - kHalfPatch) & ~3;
+      stage_patch(wbuf + k * kPatchBufWords, pyr + (size_t)f * pyrStride + L.off + (long long)(py[k] - kHalfPatch) * L.pitch + xa,
+                  L.pitch, 31, kMomWords, lane);
+    } else {
+      __pipeline_commit();
     }
-    if (lane == 0) {
-      s_lvl[sl] = l;
-      s_xy[sl] = (int)rec.x;
-      s_resp[sl] = (int)rec.y;
-      s_angle[sl] = fast_atan2_deg((float)m01, (float)m10);
+  }
+  float angle[kDescPerWarp];
+#pragma unroll
+  for (int k = 0; k < kDescPerWarp; k++) {
+    angle[k] = 0.f;
+    __pipeline_wait_prior(kDescPerWarp - 1 - k);
+    __syncwarp();
+    if (lvl[k] >= 0) {
+      const unsigned* row = wbuf + k * kPatchBufWords + (lane < 31 ? lane : 30) * kMomWords;
+      const unsigned sh = (unsigned)((px[k] - kHalfPatch) & 3) * 8;
+      unsigned s1 = 0, s2 = 0;
+      unsigned prev = row[0];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const unsigned nxt = row[q + 1];
+        const unsigned wv = __funnelshift_r(prev, nxt, sh);   // patch bytes 4q .. 4q+3 of this row
+        s1 = __dp4a(wv, w1[q], s1);
+        s2 = __dp4a(wv, wu[q], s2);
+        prev = nxt;
+      }
+      int m10 = (int)s2 - kHalfPatch * (int)s1;               // sum u*I
+      int m01 = (lane - kHalfPatch) * (int)s1;                // sum v*I
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+      }
+      angle[k] = fast_atan2_deg((float)m01, (float)m10);
     }
+  }
+  __syncwarp();
+  // the buffers are free: start streaming the blurred patches, then publish the angles
+#pragma unroll
+  for (int k = 0; k < kDescPerWarp; k++) {
+    const int sl = wid * kDescPerWarp + k;
+    if (lvl[k] >= 0) {
+      const LevelGeom& L = g.lv[lvl[k]];
+      const int xa = (px[k] - 18) & ~3;
+      stage_patch(wbuf + k * kPatchBufWords, blur + (size_t)f * blurStride + L.boff + (long long)(py[k] - 18) * L.bpitch + xa,
+                  L.bpitch, 37, kPatchWords, lane);
+    } else {
+      __pipeline_commit();
+    }
+    if (lane == 0) { s_lvl[sl] = lvl[k]; s_angle[sl] = angle[k]; }
   }
   __syncthreads();
   // ---- phase B: cos / sin, one thread per keypoint
@@ -826,29 +1019,20 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
     s_sin[threadIdx.x] = (float)sn;
   }
   __syncthreads();
-  // ---- phase C: steered BRIEF on the blurred level; lane i produces descriptor byte i
+  // ---- phase C: steered BRIEF on the blurred patch; lane i produces descriptor byte i
   const int4* pp = reinterpret_cast<const int4*>(pattern) + lane * 2;
   const int4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
   const int words[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-  unsigned* pw = s_patch[wid];
-#pragma unroll 1
-  for (int k = 0; k < kDescSlots / 8; k++) {
-    const int sl = wid + 8 * k, slotIdx = slot0 + sl;
-    const int l = s_lvl[sl];
-    if (l < 0) continue;
-    const LevelGeom& L = g.lv[l];
-    const int x = s_xy[sl] & 0xffff, y = (int)((unsigned)s_xy[sl] >> 16);
+#pragma unroll
+  for (int k = 0; k < kDescPerWarp; k++) {
+    __pipeline_wait_prior(kDescPerWarp - 1 - k);
+    __syncwarp();
+    if (lvl[k] < 0) continue;
+    const int sl = wid * kDescPerWarp + k, slotIdx = slot0 + sl;
+    const LevelGeom& L = g.lv[lvl[k]];
+    const int x = px[k], y = py[k];
     const float a = s_cos[sl], b = s_sin[sl];
-    const int xa = (x - 18) & ~3;
-    const u8* cb0 = blur + (size_t)f * blurStride + L.boff + (long long)(y - 18) * L.bpitch + xa;
-    __syncwarp();
-#pragma unroll 13
-    for (int i = lane; i < 37 * kPatchWords; i += 32) {
-      const int r = i / kPatchWords, wd = i - r * kPatchWords;
-      pw[i] = *reinterpret_cast<const unsigned*>(cb0 + (long long)r * L.bpitch + 4 * wd);
-    }
-    __syncwarp();
-    const u8* cb = reinterpret_cast<const u8*>(pw) + 18 * (4 * kPatchWords) + (x - xa);
+    const u8* cb = reinterpret_cast<const u8*>(wbuf + k * kPatchBufWords) + 18 * (4 * kPatchWords) + (x - ((x - 18) & ~3));
     int val = 0;
 #pragma unroll
     for (int bit = 0; bit < 8; bit++) {
@@ -866,12 +1050,12 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
     outD[o * 32 + lane] = (u8)val;
     if (lane == 0) {
       orb_keypoint kp;
-      kp.x = l ? __fmul_rn((float)x, L.scale) : (float)x;
-      kp.y = l ? __fmul_rn((float)y, L.scale) : (float)y;
+      kp.x = lvl[k] ? __fmul_rn((float)x, L.scale) : (float)x;
+      kp.y = lvl[k] ? __fmul_rn((float)y, L.scale) : (float)y;
       kp.size = L.patch;
-      kp.angle = s_angle[sl];
-      kp.response = (float)s_resp[sl];
-      kp.octave = l;
+      kp.angle = angle[k];
+      kp.response = (float)resp[k];
+      kp.octave = lvl[k];
       kp.class_id = -1;
       outK[o] = kp;
     }
@@ -899,6 +1083,8 @@ struct orb_extractor {
   size_t pyrStride = 0, blurStride = 0;
   int candTotal = 0, keptTotal = 0, nodeCap = 0, maxKp = 0;
   size_t fastSmem = 0, qtSmem = 0;
+  FastSmemLayout fastLay;
+  int fastBlocks = 0;
   std::vector<int2> taps;
 
   // device workspace (sized for maxBatch frames of the current geometry)
@@ -907,9 +1093,13 @@ struct orb_extractor {
   uint2* d_kept = nullptr; int* d_keptCount = nullptr; int2* d_taps = nullptr;
   signed char* d_pattern = nullptr; int* d_overflow = nullptr;
   int wsFrames = 0;
-  // staging for the host entry points
-  u8* d_in = nullptr; size_t d_inBytes = 0;
-  orb_keypoint* d_kps = nullptr; u8* d_desc = nullptr; int* d_n = nullptr; int stageFrames = 0, stageCap = 0;
+  // staging for the host entry points: two sets, so that the H2D copy of chunk i+1 and the D2H
+  // copy of chunk i-1 overlap the kernels of chunk i (copy streams + events)
+  u8* d_in[2] = {nullptr, nullptr}; size_t d_inBytes = 0;
+  orb_keypoint* d_kps[2] = {nullptr, nullptr}; u8* d_desc[2] = {nullptr, nullptr}; int* d_n[2] = {nullptr, nullptr};
+  int stageFrames = 0, stageCap = 0;
+  cudaStream_t sIn = nullptr, sOut = nullptr;
+  cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
   std::vector<u8> hostPyr;
   int lastLaunches = 0;
   int lastChunkFrames = 0;
@@ -1034,10 +1224,17 @@ int build_geom(orb_extractor* e, int W, int H) {
   e->nodeCap = round_up(nodeCap, 2);
   e->maxKp = maxKp;
   {
-    const size_t S = (maxCw + 1) / 2;
-    e->fastSmem = 4 * (S + 6) * (maxCh + 6) + 2 * ((S * maxCh + 1) & ~(size_t)1) + 2 * (((size_t)maxCw * maxCh + 1) & ~(size_t)1) +
-                  (size_t)(maxCw + 2) * (maxCh + 2) + 16;
-    if ((size_t)maxCw * maxCh >= 32768) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
+    if (maxCw > 60 || maxCh > 60) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell larger than 60 px");
+    const int S = (maxCw + 1) / 2;
+    FastSmemLayout& y = e->fastLay;
+    y.rawPitchWords = (3 + maxCw + 6 + 3) / 4;
+    y.rawBytes = round_up(y.rawPitchWords * 4 * (maxCh + 6), 16);
+    y.tileBytes = round_up(4 * (S + 6) * (maxCh + 6), 16);
+    y.queueBytes = round_up(2 * S * maxCh, 16);
+    y.hitsBytes = round_up(2 * maxCw * maxCh, 16);
+    y.scBytes = round_up((maxCw + 2) * (maxCh + 2) + 4, 16);
+    y.total = y.rawBytes + y.tileBytes + y.queueBytes + y.hitsBytes + y.scBytes;
+    e->fastSmem = (size_t)y.total * kFastWarps;
   }
   e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8);
   if (e->qtSmem > 220 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "features per level too large for the quadtree kernel's shared memory");
@@ -1066,6 +1263,14 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
     ORB_CUDA(cudaMemcpy(e->d_taps, e->taps.data(), e->taps.size() * sizeof(int2), cudaMemcpyHostToDevice));
     ORB_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qtSmem));
     ORB_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->fastSmem));
+    ORB_CUDA(cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescSmem));
+    {
+      int perSM = 0, dev = 0, sms = 0;
+      ORB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_fast_cells, kFastThreads, e->fastSmem));
+      ORB_CUDA(cudaGetDevice(&dev));
+      ORB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      e->fastBlocks = std::max(1, perSM) * std::max(1, sms);
+    }
     e->haveGeom = true;
   }
   frames = std::min(frames, e->maxBatch);
@@ -1119,8 +1324,12 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   }
   ORB_CUDA(cudaMemsetAsync(e->d_candCount, 0, (size_t)B * nl * sizeof(int), s));
   if ((st = stage_mark(e, s))) return st;
-  k_fast_cells<<<dim3(g.totalCells, B), kFastThreads, e->fastSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_cand, e->d_candCount,
-                                                              e->candTotal);
+  {
+    const int nItems = g.totalCells * B;
+    const int blocks = std::min(e->fastBlocks, (nItems + kFastWarps - 1) / kFastWarps);
+    k_fast_cells<<<blocks, kFastThreads, e->fastSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_cand, e->d_candCount,
+                                                          e->candTotal, nItems, e->fastLay);
+  }
   launches++;
   if ((st = stage_mark(e, s))) return st;
   k_quadtree<<<dim3(nl, B), kQtThreads, e->qtSmem, s>>>(g, e->d_cand, e->d_candCount, e->d_keyNode, e->d_kept,
@@ -1132,7 +1341,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   launches++;
   if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);
-  k_describe<<<dim3((slots + kDescSlots - 1) / kDescSlots, B), 256, 0, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride,
+  k_describe<<<dim3((slots + kDescSlots - 1) / kDescSlots, B), 256, kDescSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride,
                                                               e->d_kept, e->d_keptCount, e->keptTotal, e->d_pattern,
                                                               d_kps, d_desc, d_counts, cap, e->d_overflow);
   launches++;
@@ -1147,20 +1356,33 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
 }
 
 int ensure_stage(orb_extractor* e, size_t inBytes, int frames, int cap) {
+  if (!e->sIn) {
+    ORB_CUDA(cudaStreamCreateWithFlags(&e->sIn, cudaStreamNonBlocking));
+    ORB_CUDA(cudaStreamCreateWithFlags(&e->sOut, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+      ORB_CUDA(cudaEventCreateWithFlags(&e->evIn[b], cudaEventDisableTiming));
+      ORB_CUDA(cudaEventCreateWithFlags(&e->evDone[b], cudaEventDisableTiming));
+      ORB_CUDA(cudaEventCreateWithFlags(&e->evOut[b], cudaEventDisableTiming));
+    }
+  }
   if (inBytes > e->d_inBytes) {
-    ORB_CUDA(cudaStreamSynchronize(e->stream));
-    cudaFree(e->d_in);
-    e->d_in = nullptr;
-    ORB_CUDA(cudaMalloc(&e->d_in, inBytes));
+    ORB_CUDA(cudaDeviceSynchronize());
+    for (int b = 0; b < 2; b++) {
+      cudaFree(e->d_in[b]);
+      e->d_in[b] = nullptr;
+      ORB_CUDA(cudaMalloc(&e->d_in[b], inBytes));
+    }
     e->d_inBytes = inBytes;
   }
   if ((size_t)frames * cap > (size_t)e->stageFrames * e->stageCap || frames > e->stageFrames) {
-    ORB_CUDA(cudaStreamSynchronize(e->stream));
-    cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_n);
-    e->d_kps = nullptr; e->d_desc = nullptr; e->d_n = nullptr;
-    ORB_CUDA(cudaMalloc(&e->d_kps, (size_t)frames * cap * sizeof(orb_keypoint)));
-    ORB_CUDA(cudaMalloc(&e->d_desc, (size_t)frames * cap * 32));
-    ORB_CUDA(cudaMalloc(&e->d_n, (size_t)frames * sizeof(int)));
+    ORB_CUDA(cudaDeviceSynchronize());
+    for (int b = 0; b < 2; b++) {
+      cudaFree(e->d_kps[b]); cudaFree(e->d_desc[b]); cudaFree(e->d_n[b]);
+      e->d_kps[b] = nullptr; e->d_desc[b] = nullptr; e->d_n[b] = nullptr;
+      ORB_CUDA(cudaMalloc(&e->d_kps[b], (size_t)frames * cap * sizeof(orb_keypoint)));
+      ORB_CUDA(cudaMalloc(&e->d_desc[b], (size_t)frames * cap * 32));
+      ORB_CUDA(cudaMalloc(&e->d_n[b], (size_t)frames * sizeof(int)));
+    }
     e->stageFrames = frames;
     e->stageCap = cap;
   }
@@ -1221,7 +1443,14 @@ int orb_destroy(orb_extractor* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   free_workspace(e);
   cudaFree(e->d_taps); cudaFree(e->d_pattern); cudaFree(e->d_overflow);
-  cudaFree(e->d_in); cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_n);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(e->d_in[b]); cudaFree(e->d_kps[b]); cudaFree(e->d_desc[b]); cudaFree(e->d_n[b]);
+    if (e->evIn[b]) cudaEventDestroy(e->evIn[b]);
+    if (e->evDone[b]) cudaEventDestroy(e->evDone[b]);
+    if (e->evOut[b]) cudaEventDestroy(e->evOut[b]);
+  }
+  if (e->sIn) cudaStreamDestroy(e->sIn);
+  if (e->sOut) cudaStreamDestroy(e->sOut);
   for (cudaEvent_t ev : e->evPool) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -1314,23 +1543,36 @@ int orb_extract_batch_host(orb_extractor* e, const uint8_t* images, int batch, i
   if (st) return st;
   cudaStream_t s = e->stream;
   e->lastLaunches = 0;
-  for (int b0 = 0; b0 < batch; b0 += chunk) {
+  int ci = 0;
+  for (int b0 = 0; b0 < batch; b0 += chunk, ci++) {
     const int B = std::min(chunk, batch - b0);
+    const int b = ci & 1;
+    // H2D of this chunk: its staging buffer must no longer be read by the kernels of chunk ci-2
+    if (ci >= 2) ORB_CUDA(cudaStreamWaitEvent(e->sIn, e->evDone[b], 0));
     if (step == (size_t)width && frame_stride == dFrame) {
-      ORB_CUDA(cudaMemcpyAsync(e->d_in, images + (size_t)b0 * frame_stride, dFrame * B, cudaMemcpyHostToDevice, s));
+      ORB_CUDA(cudaMemcpyAsync(e->d_in[b], images + (size_t)b0 * frame_stride, dFrame * B, cudaMemcpyHostToDevice, e->sIn));
     } else {
-      for (int b = 0; b < B; b++)
-        ORB_CUDA(cudaMemcpy2DAsync(e->d_in + (size_t)b * dFrame, width, images + (size_t)(b0 + b) * frame_stride, step,
-                                   width, height, cudaMemcpyHostToDevice, s));
+      for (int k = 0; k < B; k++)
+        ORB_CUDA(cudaMemcpy2DAsync(e->d_in[b] + (size_t)k * dFrame, width, images + (size_t)(b0 + k) * frame_stride, step,
+                                   width, height, cudaMemcpyHostToDevice, e->sIn));
     }
-    st = run_chunk(e, e->d_in, B, width, dFrame, e->d_kps, capacity, e->d_n, e->d_desc, s);
+    ORB_CUDA(cudaEventRecord(e->evIn[b], e->sIn));
+    // kernels: wait for the input, and for the D2H of chunk ci-2 that still reads the output buffers
+    ORB_CUDA(cudaStreamWaitEvent(s, e->evIn[b], 0));
+    if (ci >= 2) ORB_CUDA(cudaStreamWaitEvent(s, e->evOut[b], 0));
+    st = run_chunk(e, e->d_in[b], B, width, dFrame, e->d_kps[b], capacity, e->d_n[b], e->d_desc[b], s);
     if (st) return st;
-    ORB_CUDA(cudaMemcpyAsync(counts + b0, e->d_n, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
-    ORB_CUDA(cudaMemcpyAsync(keypoints + (size_t)b0 * capacity, e->d_kps, (size_t)B * capacity * sizeof(orb_keypoint),
-                             cudaMemcpyDeviceToHost, s));
-    ORB_CUDA(cudaMemcpyAsync(descriptors + (size_t)b0 * capacity * 32, e->d_desc, (size_t)B * capacity * 32,
-                             cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaEventRecord(e->evDone[b], s));
+    // D2H on its own stream
+    ORB_CUDA(cudaStreamWaitEvent(e->sOut, e->evDone[b], 0));
+    ORB_CUDA(cudaMemcpyAsync(counts + b0, e->d_n[b], (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, e->sOut));
+    ORB_CUDA(cudaMemcpyAsync(keypoints + (size_t)b0 * capacity, e->d_kps[b], (size_t)B * capacity * sizeof(orb_keypoint),
+                             cudaMemcpyDeviceToHost, e->sOut));
+    ORB_CUDA(cudaMemcpyAsync(descriptors + (size_t)b0 * capacity * 32, e->d_desc[b], (size_t)B * capacity * 32,
+                             cudaMemcpyDeviceToHost, e->sOut));
+    ORB_CUDA(cudaEventRecord(e->evOut[b], e->sOut));
   }
+  ORB_CUDA(cudaStreamSynchronize(e->sOut));
   return check_overflow(e, s);
 }
 
@@ -1346,19 +1588,19 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
   if (st) return st;
   cudaStream_t s = e->stream;
   e->lastLaunches = 0;
-  ORB_CUDA(cudaMemcpy2DAsync(e->d_in, width, image, step, width, height, cudaMemcpyHostToDevice, s));
-  st = run_chunk(e, e->d_in, 1, width, dFrame, e->d_kps, capacity, e->d_n, e->d_desc, s);
+  ORB_CUDA(cudaMemcpy2DAsync(e->d_in[0], width, image, step, width, height, cudaMemcpyHostToDevice, s));
+  st = run_chunk(e, e->d_in[0], 1, width, dFrame, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], s);
   if (st) return st;
   int cnt = 0;
-  ORB_CUDA(cudaMemcpyAsync(&cnt, e->d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(&cnt, e->d_n[0], sizeof(int), cudaMemcpyDeviceToHost, s));
   if (pyramid) {
     e->hostPyr.resize(e->pyrStride);
     ORB_CUDA(cudaMemcpyAsync(e->hostPyr.data(), e->d_pyr, e->pyrStride, cudaMemcpyDeviceToHost, s));
   }
   ORB_CUDA(cudaStreamSynchronize(s));
   if (cnt > 0) {
-    ORB_CUDA(cudaMemcpyAsync(keypoints, e->d_kps, (size_t)cnt * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
-    ORB_CUDA(cudaMemcpyAsync(descriptors, e->d_desc, (size_t)cnt * 32, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(keypoints, e->d_kps[0], (size_t)cnt * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(descriptors, e->d_desc[0], (size_t)cnt * 32, cudaMemcpyDeviceToHost, s));
   }
   st = check_overflow(e, s);
   if (st) return st;
