@@ -287,6 +287,32 @@ def run_ours(args, rank, world, local_rank):
     m_ms = max_over_ranks(m0.elapsed_time(m1))
     cmp_per_s = world * match_pairs * MATCH_N * MATCH_N * m_steps / (m_ms * 1e-3)
     mean_matches = float(d_nm.float().mean().item())
+    # ---- all-pairs keyframe matching (BASELINE.json configs[4], scaled down): NCCL exchange of the
+    # descriptor blocks, consumed block by block (distributed.allpairs_match_counts)
+    allpairs = None
+    if args.allpairs_kf > 0:
+        from orb_slam2_detailed_comments_b200.distributed import allpairs_match_counts, shard_range
+        n_kf, n_desc = args.allpairs_kf, 1000
+        rb, re = shard_range(n_kf, rank, world)
+        g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+        local = torch.randint(0, 256, (re - rb, n_desc, 32), dtype=torch.uint8, device=dev, generator=g)
+
+        def compute_block(all_desc, r0, r1, c0, c1, out):
+            matcher.match_allpairs_device(all_desc, r0, r1, out, stream=stream, col_begin=c0, col_end=c1)
+
+        with torch.cuda.stream(tstream):
+            allpairs_match_counts(local, n_kf, compute_block)   # warm-up
+            barrier()
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record(tstream)
+            allpairs_match_counts(local, n_kf, compute_block)
+            a1.record(tstream)
+            torch.cuda.synchronize()
+        ap_ms = max_over_ranks(a0.elapsed_time(a1))
+        allpairs = {"keyframes": n_kf, "descriptors_per_keyframe": n_desc, "ms": ap_ms,
+                    "value": float(n_kf) * n_kf * n_desc * n_desc / (ap_ms * 1e-3), "unit": "cmp/s",
+                    "exchange": "nccl broadcast per block, overlapped" if world > 1 else "none (1 GPU)",
+                    "note": "BASELINE config 5 uses 4096 keyframes; scaled down to bound the run"}
     pipes = int_pipe_peak(local_rank)
     clocks = sampler.stop() if sampler else None
 
@@ -348,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs larger than L2 (%d MB per step; unique pool 241 MB)" % (frames_per_step * W * H // 1000000), "parallelism": "frames sharded, no collective"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "orb_extract_batch_host (pinned host buffers)"},
-        "gpu_launches": launches_per_step * args.steps + e2e_launches + m_steps,
+        "gpu_launches": launches_per_step * args.steps + e2e_launches + m_steps + (2 * world if allpairs else 0),
         "clocks": clocks,
         "roofline": roofline,
         "path_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": total_b, "achieved": path_gbs, "peak": peak, "unit": "GB/s",
@@ -363,6 +389,9 @@ def run_ours(args, rank, world, local_rank):
                                   "peak_def": "measured POPC issue rate / 8 POPC per naive 256-bit comparison (SURVEY 8d)",
                                   "popc_ops_per_s": pipes["popc"], "lop3_ops_per_s": pipes["lop3"]}},
     }
+    if allpairs:
+        allpairs["roofline_frac"] = allpairs["value"] / world / popc_peak_cmp
+        line["allpairs"] = allpairs
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -376,12 +405,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("ORB_CHUNK", "128")), help="frames per internal chunk")
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("ORB_CHUNK", "256")), help="frames per internal chunk")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--match-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP, help="stereo pairs per step per GPU (profiling runs shrink this)")
     ap.add_argument("--match-pairs", type=int, default=MATCH_PAIRS)
+    ap.add_argument("--allpairs-kf", type=int, default=512, help="keyframes of the all-pairs workload (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -138,24 +138,13 @@ __device__ __forceinline__ unsigned resize_px_slow(const u8* r0, const u8* r1, i
   return (unsigned)min(max(v, 0), 255);
 }
 
-__global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
-                                                       const int2* __restrict__ taps) {
-  const LevelGeom& D = g.lv[l];
-  const LevelGeom& S = g.lv[l - 1];
-  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y * blockDim.y + threadIdx.y;
-  const int f = blockIdx.z;
-  if (gi * 4 >= D.pitch || by >= D.h + 2 * kEdge) return;
-  // interior 4-px groups first (fast path, homogeneous warps), then the 8 left-border groups, then
-  // the right border / padding groups
-  const int nInt = D.w >> 2;
-  const int c0 = gi < nInt ? 4 * gi : (gi - nInt < 8 ? 4 * (gi - nInt) - kLeftPad : 4 * (gi - 8));
-  const int y = reflect101(by - kEdge, D.h);
+// one 4-pixel word of bordered row (interior row index y already reflected)
+__device__ __forceinline__ unsigned resize_row_word(const LevelGeom& D, const LevelGeom& S, const u8* src,
+                                                    const int2* __restrict__ taps, int c0, int y) {
   const int2 ty = __ldg(taps + D.tapY + y);
   const int sy0 = ty.x, sy1 = min(sy0 + 1, S.h - 1);
   const int cy0 = ty.y & 0xffff, cy1 = ty.y >> 16;
   const unsigned cy0s = (unsigned)cy0 << 16, cy1s = (unsigned)cy1 << 16;
-  const u8* src = pyr + (size_t)f * pyrStride + S.off;
   const u8* r0 = src + (long long)sy0 * S.pitch;
   const u8* r1 = src + (long long)sy1 * S.pitch;
   unsigned out = 0;
@@ -180,8 +169,7 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
     const unsigned cf[4] = {(unsigned)ta.y, (unsigned)ta.w, (unsigned)tb.y, (unsigned)tb.w};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const unsigned dlt = (unsigned)(sx[j] - a);
-      const unsigned sel = dlt | ((dlt + 1) << 4);          // bytes (dlt, dlt+1) of the window
+      const unsigned sel = (unsigned)(sx[j] - a) * 0x11u + 0x10u;   // bytes (d, d+1) of the window
       const unsigned q0 = __byte_perm(lo0, hi0, sel), q1 = __byte_perm(lo1, hi1, sel);
       const unsigned h0 = __dp2a_lo(cf[j], q0, 0u);         // c0*p[sx] + c1*p[sx+1]  (<= 255*2048)
       const unsigned h1 = __dp2a_lo(cf[j], q1, 0u);
@@ -196,8 +184,77 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
       out |= resize_px_slow(r0, r1, __ldg(taps + D.tapX + x), S.w, cy0, cy1) << (8 * j);
     }
   }
-  u8* dst = pyr + (size_t)f * pyrStride + D.off + (long long)(by - kEdge) * D.pitch + c0;
-  *reinterpret_cast<unsigned*>(dst) = out;
+  return out;
+}
+
+// Thread = 4 columns x 4 rows of the bordered plane. Interior blocks share the horizontal pass:
+// the 4 output rows read at most 6 consecutive source rows (scale <= 4/3), each filtered once.
+__global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
+                                                       const int2* __restrict__ taps) {
+  const LevelGeom& D = g.lv[l];
+  const LevelGeom& S = g.lv[l - 1];
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int by0 = 4 * (blockIdx.y * blockDim.y + threadIdx.y);
+  const int f = blockIdx.z;
+  if (gi * 4 >= D.pitch || by0 >= D.h + 2 * kEdge) return;
+  // interior 4-px groups first (fast path, homogeneous warps), then the 8 left-border groups, then
+  // the right border / padding groups
+  const int nInt = D.w >> 2;
+  const int c0 = gi < nInt ? 4 * gi : (gi - nInt < 8 ? 4 * (gi - nInt) - kLeftPad : 4 * (gi - 8));
+  const u8* src = pyr + (size_t)f * pyrStride + S.off;
+  u8* dst = pyr + (size_t)f * pyrStride + D.off + (long long)(by0 - kEdge) * D.pitch + c0;
+  const int nrows = min(4, D.h + 2 * kEdge - by0);
+  bool blockFast = c0 >= 0 && c0 + 3 < D.w && by0 >= kEdge && by0 + 3 < D.h + kEdge;
+  int4 ta, tb;
+  int2 ty[4];
+  if (blockFast) {
+    const int4* tp4 = reinterpret_cast<const int4*>(taps + D.tapX + c0);
+    ta = __ldg(tp4);
+    tb = __ldg(tp4 + 1);
+    const int y0 = by0 - kEdge;
+#pragma unroll
+    for (int k = 0; k < 4; k++) ty[k] = __ldg(taps + D.tapY + y0 + k);
+    // source rows advance by 1 or 2 per output row; the block must fit rows base .. base+5
+    blockFast = tb.z + 1 - ta.x <= 7 && ty[1].x - ty[0].x >= 1 && ty[2].x - ty[1].x >= 1 && ty[3].x - ty[2].x >= 1 &&
+                ty[3].x - ty[0].x <= 4;
+  }
+  if (blockFast) {
+    const int a = ta.x, base = ty[0].x;
+    const int sx[4] = {ta.x, ta.z, tb.x, tb.z};
+    const unsigned cf[4] = {(unsigned)ta.y, (unsigned)ta.w, (unsigned)tb.y, (unsigned)tb.w};
+    unsigned sel[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) sel[j] = (unsigned)(sx[j] - a) * 0x11u + 0x10u;
+    unsigned hq[6][4];   // horizontal pass of source rows base..base+5, already >> 4
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const size_t ad = reinterpret_cast<size_t>(src + (long long)min(base + i, S.h - 1) * S.pitch + a);
+      const unsigned* p = reinterpret_cast<const unsigned*>(ad & ~(size_t)3);
+      const unsigned sh = (unsigned)(ad & 3) * 8;
+      const unsigned u0 = p[0], u1 = p[1], u2 = p[2];
+      const unsigned lo = __funnelshift_r(u0, u1, sh), hi = __funnelshift_r(u1, u2, sh);
+#pragma unroll
+      for (int j = 0; j < 4; j++) hq[i][j] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const bool e = ty[k].x - base > k;           // source row index is base+k or base+k+1
+      const unsigned cy0s = (unsigned)(ty[k].y & 0xffff) << 16, cy1s = (unsigned)(ty[k].y >> 16) << 16;
+      unsigned out = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned h0 = e ? hq[k + 1][j] : hq[k][j];
+        const unsigned h1 = e ? hq[k + 2][j] : hq[k + 1][j];
+        out |= ((__umulhi(cy0s, h0) + __umulhi(cy1s, h1) + 2u) >> 2) << (8 * j);
+      }
+      *reinterpret_cast<unsigned*>(dst + (long long)k * D.pitch) = out;
+    }
+  } else {
+    for (int k = 0; k < nrows; k++) {
+      const int y = reflect101(by0 + k - kEdge, D.h);
+      *reinterpret_cast<unsigned*>(dst + (long long)k * D.pitch) = resize_row_word(D, S, src, taps, c0, y);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -357,6 +414,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
       int r = lane / tp, j = lane - r * tp;
       const int dr = 32 / tp, dj = 32 - dr * tp;
       const int jmax = cw + 6 - S;   // pixels j+S beyond the tile are zero
+#pragma unroll 4
       for (int i = lane; i < n; i += 32) {
         const u8* q = rb + r * rp + j;
         const unsigned lo = q[0];
@@ -382,6 +440,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
       const int two = S <= 16;
       const int x = two ? (lane & 15) : lane;
       const int rsub = two ? (lane >> 4) : 0, rstep = two ? 2 : 1;
+#pragma unroll 2
       for (int r0 = 0; r0 < ch; r0 += rstep) {
         const int r = r0 + rsub;
         bool pass = false;
@@ -1318,7 +1377,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   }
   for (int l = 1; l < nl; l++) {
     const LevelGeom& L = g.lv[l];
-    dim3 grid((L.pitch / 4 + 31) / 32, (L.h + 2 * kEdge + 7) / 8, B);
+    dim3 grid((L.pitch / 4 + 31) / 32, (L.h + 2 * kEdge + 31) / 32, B);
     k_resize_border<<<grid, dim3(32, 8), 0, s>>>(g, l, e->d_pyr, e->pyrStride, e->d_taps);
     launches++;
   }
