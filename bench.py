@@ -32,6 +32,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout must carry exactly ONE JSON line: keep the real stdout aside and point fd 1 at stderr, so
+# that anything a library prints to stdout (e.g. NCCL's version banner) cannot pollute it
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def gen_frames(count, seed0):
     import multiprocessing as mp
 
@@ -160,7 +170,7 @@ def run_reference(args, rank):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mean_keypoints": kp / (args.steps * sample),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -394,7 +404,7 @@ def run_ours(args, rank, world, local_rank):
         line["allpairs"] = allpairs
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
