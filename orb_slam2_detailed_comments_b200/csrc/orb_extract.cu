@@ -187,8 +187,19 @@ __device__ __forceinline__ unsigned resize_row_word(const LevelGeom& D, const Le
   return out;
 }
 
-// Thread = 4 columns x 4 rows of the bordered plane. Interior blocks share the horizontal pass:
-// the 4 output rows read at most 6 consecutive source rows (scale <= 4/3), each filtered once.
+// 4 consecutive bordered positions p0..p0+3 (interior coordinates, may be negative or >= n) map,
+// under REFLECT_101, to 4 consecutive interior positions, ascending (inside) or descending (in the
+// border), unless the group straddles a turning point. Returns false for such mixed groups.
+__device__ __forceinline__ bool reflect_group(int p0, int n, int& lo, bool& rev) {
+  if (p0 >= 0 && p0 + 3 < n) { lo = p0; rev = false; return true; }
+  if (p0 + 3 < 0) { lo = -p0 - 3; rev = true; return -p0 < n; }
+  if (p0 >= n) { lo = 2 * (n - 1) - p0 - 3; rev = true; return lo >= 0; }
+  return false;
+}
+
+// Thread = 4 columns x 4 rows of the bordered plane. Blocks that do not straddle a reflection
+// turning point share the horizontal pass: the 4 output rows read at most 6 consecutive source
+// rows (scale <= 4/3), each filtered once; border blocks are the mirrored copy of such a block.
 __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
                                                        const int2* __restrict__ taps) {
   const LevelGeom& D = g.lv[l];
@@ -197,44 +208,40 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
   const int by0 = 4 * (blockIdx.y * blockDim.y + threadIdx.y);
   const int f = blockIdx.z;
   if (gi * 4 >= D.pitch || by0 >= D.h + 2 * kEdge) return;
-  // interior 4-px groups first (fast path, homogeneous warps), then the 8 left-border groups, then
-  // the right border / padding groups
-  const int nInt = D.w >> 2;
-  const int c0 = gi < nInt ? 4 * gi : (gi - nInt < 8 ? 4 * (gi - nInt) - kLeftPad : 4 * (gi - 8));
+  const int c0 = 4 * gi - kLeftPad;
   const u8* src = pyr + (size_t)f * pyrStride + S.off;
   u8* dst = pyr + (size_t)f * pyrStride + D.off + (long long)(by0 - kEdge) * D.pitch + c0;
   const int nrows = min(4, D.h + 2 * kEdge - by0);
-  bool blockFast = c0 >= 0 && c0 + 3 < D.w && by0 >= kEdge && by0 + 3 < D.h + kEdge;
-  int4 ta, tb;
-  int2 ty[4];
+  int xlo = 0, ylo = 0;
+  bool revX = false, revY = false;
+  bool blockFast = nrows == 4 && reflect_group(c0, D.w, xlo, revX) && reflect_group(by0 - kEdge, D.h, ylo, revY);
+  int2 tx[4], ty[4];
   if (blockFast) {
-    const int4* tp4 = reinterpret_cast<const int4*>(taps + D.tapX + c0);
-    ta = __ldg(tp4);
-    tb = __ldg(tp4 + 1);
-    const int y0 = by0 - kEdge;
 #pragma unroll
-    for (int k = 0; k < 4; k++) ty[k] = __ldg(taps + D.tapY + y0 + k);
-    // source rows advance by 1 or 2 per output row; the block must fit rows base .. base+5
-    blockFast = tb.z + 1 - ta.x <= 7 && ty[1].x - ty[0].x >= 1 && ty[2].x - ty[1].x >= 1 && ty[3].x - ty[2].x >= 1 &&
+    for (int k = 0; k < 4; k++) {
+      tx[k] = __ldg(taps + D.tapX + xlo + k);
+      ty[k] = __ldg(taps + D.tapY + ylo + k);
+    }
+    // the 4 pixels' source span must fit one 8-byte window; source rows advance by 1 or 2 per
+    // output row and the block must fit rows base .. base+5
+    blockFast = tx[3].x + 1 - tx[0].x <= 7 && ty[1].x - ty[0].x >= 1 && ty[2].x - ty[1].x >= 1 && ty[3].x - ty[2].x >= 1 &&
                 ty[3].x - ty[0].x <= 4;
   }
   if (blockFast) {
-    const int a = ta.x, base = ty[0].x;
-    const int sx[4] = {ta.x, ta.z, tb.x, tb.z};
-    const unsigned cf[4] = {(unsigned)ta.y, (unsigned)ta.w, (unsigned)tb.y, (unsigned)tb.w};
+    const int a = tx[0].x, base = ty[0].x;
     unsigned sel[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) sel[j] = (unsigned)(sx[j] - a) * 0x11u + 0x10u;
+    for (int j = 0; j < 4; j++) sel[j] = (unsigned)(tx[j].x - a) * 0x11u + 0x10u;   // bytes (d, d+1) of the window
     unsigned hq[6][4];   // horizontal pass of source rows base..base+5, already >> 4
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      const size_t ad = reinterpret_cast<size_t>(src + (long long)min(base + i, S.h - 1) * S.pitch + a);
-      const unsigned* p = reinterpret_cast<const unsigned*>(ad & ~(size_t)3);
-      const unsigned sh = (unsigned)(ad & 3) * 8;
+      const u8* q = src + (long long)min(base + i, S.h - 1) * S.pitch + a;
+      const unsigned mis = (unsigned)(reinterpret_cast<size_t>(q) & 3);
+      const unsigned* p = reinterpret_cast<const unsigned*>(q - mis);
       const unsigned u0 = p[0], u1 = p[1], u2 = p[2];
-      const unsigned lo = __funnelshift_r(u0, u1, sh), hi = __funnelshift_r(u1, u2, sh);
+      const unsigned lo = __funnelshift_r(u0, u1, mis * 8), hi = __funnelshift_r(u1, u2, mis * 8);
 #pragma unroll
-      for (int j = 0; j < 4; j++) hq[i][j] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;
+      for (int j = 0; j < 4; j++) hq[i][j] = __dp2a_lo((unsigned)tx[j].y, __byte_perm(lo, hi, sel[j]), 0u) >> 4;
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -245,9 +252,11 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
       for (int j = 0; j < 4; j++) {
         const unsigned h0 = e ? hq[k + 1][j] : hq[k][j];
         const unsigned h1 = e ? hq[k + 2][j] : hq[k + 1][j];
+        // ((cy*(h>>4))>>16) == umulhi(cy<<16, h>>4); the sum is <= 1020, so the result needs no clamp
         out |= ((__umulhi(cy0s, h0) + __umulhi(cy1s, h1) + 2u) >> 2) << (8 * j);
       }
-      *reinterpret_cast<unsigned*>(dst + (long long)k * D.pitch) = out;
+      if (revX) out = __byte_perm(out, 0u, 0x0123);
+      *reinterpret_cast<unsigned*>(dst + (long long)(revY ? 3 - k : k) * D.pitch) = out;
     }
   } else {
     for (int k = 0; k < nrows; k++) {
@@ -329,6 +338,7 @@ __device__ __forceinline__ unsigned fast_exact(const FastDiffs& D) {
 // hide each other's latencies.
 constexpr int kFastWarps = 4;
 constexpr int kFastThreads = 32 * kFastWarps;
+constexpr int kFastRun = 16;   // consecutive cells a warp grabs per atomic
 
 struct FastSmemLayout {   // per-warp shared memory carve-up (in bytes), sized for the largest cell
   int rawPitchWords, rawBytes, tileBytes, queueBytes, hitsBytes, scBytes, total;
@@ -340,63 +350,117 @@ struct CellDesc {
   int pitch, cw, ch, x0, y0, l, f, rw;
 };
 
-__device__ __forceinline__ bool fast_cell_desc(const Geom& g, const u8* pyr, size_t pyrStride, int item, CellDesc& c) {
-  const int f = item / g.totalCells;
-  const int cc = item - f * g.totalCells;
+// Walks the (frame, level, cell-row, cell-column) items of a contiguous item range without
+// divisions after the first item.
+struct CellCursor {
+  int f, l, ci, cj;
+};
+
+__device__ __forceinline__ void cursor_init(const Geom& g, int item, CellCursor& k) {
+  k.f = item / g.totalCells;
+  const int cc = item - k.f * g.totalCells;
   int l = 0;
 #pragma unroll 1
   while (l + 1 < g.nlevels && cc >= g.lv[l + 1].cellBase) l++;
-  const LevelGeom& L = g.lv[l];
-  const int cell = cc - L.cellBase;
-  const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
-  c.x0 = kEdge + cj * L.wCell;
-  c.y0 = kEdge + ci * L.hCell;
+  const int cell = cc - g.lv[l].cellBase;
+  k.l = l;
+  k.ci = cell / g.lv[l].nCols;
+  k.cj = cell - k.ci * g.lv[l].nCols;
+}
+
+__device__ __forceinline__ void cursor_next(const Geom& g, CellCursor& k) {
+  if (++k.cj == g.lv[k.l].nCols) {
+    k.cj = 0;
+    if (++k.ci == g.lv[k.l].nRows) {
+      k.ci = 0;
+      if (++k.l == g.nlevels) { k.l = 0; k.f++; }
+    }
+  }
+}
+
+__device__ __forceinline__ bool fast_cell_desc(const Geom& g, const u8* pyr, size_t pyrStride, const CellCursor& k, CellDesc& c) {
+  const LevelGeom& L = g.lv[k.l];
+  c.x0 = kEdge + k.cj * L.wCell;
+  c.y0 = kEdge + k.ci * L.hCell;
   c.cw = min(c.x0 + L.wCell - 1, L.w - kEdge - 1) - c.x0 + 1;
   c.ch = min(c.y0 + L.hCell - 1, L.h - kEdge - 1) - c.y0 + 1;
-  c.l = l;
-  c.f = f;
+  c.l = k.l;
+  c.f = k.f;
   c.pitch = L.pitch;
   const int xs = (c.x0 - 3) & ~3;
   c.ox = (c.x0 - 3) - xs;
   c.rw = (c.ox + c.cw + 6 + 3) >> 2;
-  c.src = pyr + (size_t)f * pyrStride + L.off + (long long)(c.y0 - 3) * L.pitch + xs;
+  c.src = pyr + (size_t)k.f * pyrStride + L.off + (long long)(c.y0 - 3) * L.pitch + xs;
   return c.cw > 0 && c.ch > 0;
 }
 
 __device__ __forceinline__ void fast_prefetch(const CellDesc& c, unsigned* raw, int rawPitchWords, int lane) {
-  // (ch+6) rows x rw words, 32 words per step
-  const int n = (c.ch + 6) * c.rw;
-  int r = lane / c.rw, wd = lane - r * c.rw;
-  const int dr = 32 / c.rw, dw = 32 - dr * c.rw;
-  for (int i = lane; i < n; i += 32) {
-    __pipeline_memcpy_async(raw + r * rawPitchWords + wd, c.src + (r * c.pitch + 4 * wd), 4);
-    wd += dw;
-    r += dr;
-    if (wd >= c.rw) { wd -= c.rw; r++; }
+  // (ch+6) rows x rw (<= 18) words: two rows per step when rw <= 16, one otherwise
+  const int rows = c.ch + 6;
+  if (c.rw <= 16) {
+    const int wd = lane & 15;
+    if (wd < c.rw) {
+      const u8* s = c.src + ((lane >> 4) * c.pitch + 4 * wd);
+      unsigned* d = raw + (lane >> 4) * rawPitchWords + wd;
+      for (int r = lane >> 4; r < rows; r += 2) {
+        __pipeline_memcpy_async(d, s, 4);
+        s += 2 * c.pitch;
+        d += 2 * rawPitchWords;
+      }
+    }
+  } else if (lane < c.rw) {
+    const u8* s = c.src + 4 * lane;
+    unsigned* d = raw + lane;
+    for (int r = 0; r < rows; r++) {
+      __pipeline_memcpy_async(d, s, 4);
+      s += c.pitch;
+      d += rawPitchWords;
+    }
   }
   __pipeline_commit();
 }
 
 __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                              uint2* __restrict__ cand, int* __restrict__ candCount,
-                                                             int candTotal, int nItems, const FastSmemLayout lay) {
+                                                             int candTotal, int nItems, const FastSmemLayout lay,
+                                                             int* __restrict__ workCounter) {
   extern __shared__ __align__(16) u8 smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   u8* base = smem + wid * lay.total;
   unsigned* raw = reinterpret_cast<unsigned*>(base);
   unsigned* tile = reinterpret_cast<unsigned*>(base + lay.rawBytes);
-  unsigned short* queue = reinterpret_cast<unsigned short*>(base + lay.rawBytes + lay.tileBytes);
-  unsigned short* hits = reinterpret_cast<unsigned short*>(base + lay.rawBytes + lay.tileBytes + lay.queueBytes);
-  u8* sc = base + lay.rawBytes + lay.tileBytes + lay.queueBytes + lay.hitsBytes;
+  // hits (produced, from the front) and the queue (consumed, stored at the back) share one buffer
+  // of 2*S*ch entries: a batch of 32 queue items yields at most 64 hits, so writes never reach
+  // the unread part of the queue (2*(e0+32) <= 2*S*ch - nq + e0 + 32 whenever nq <= S*ch)
+  unsigned short* hits = reinterpret_cast<unsigned short*>(base + lay.rawBytes + lay.tileBytes);
+  u8* sc = base + lay.rawBytes + lay.tileBytes + lay.hitsBytes;
   const unsigned ltmask = (1u << lane) - 1u;
   // bit 15 of a half is set iff its bound exceeds minTh + 255, i.e. a corner at minTh is possible
   const unsigned K = 0x7FFF7FFFu - (unsigned)(g.minTh + 255) * 0x00010001u;
 
-  const int nWarps = gridDim.x * kFastWarps;
-  int item = blockIdx.x * kFastWarps + wid;
+  // work distribution: a warp grabs runs of kFastRun consecutive cells from a global counter
   CellDesc c;
+  CellCursor cur_k;
+  int left = 0;          // cells left in the current run
   bool have = false;
-  while (item < nItems && !(have = fast_cell_desc(g, pyr, pyrStride, item, c))) item += nWarps;
+  auto advance = [&]() {
+    // moves to the next cell with a non-empty detection window; false when the work is exhausted
+    for (;;) {
+      if (left == 0) {
+        int start = 0;
+        if (lane == 0) start = atomicAdd(workCounter, kFastRun);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (start >= nItems) return false;
+        left = min(kFastRun, nItems - start);
+        cursor_init(g, start, cur_k);
+      } else {
+        cursor_next(g, cur_k);
+      }
+      left--;
+      if (fast_cell_desc(g, pyr, pyrStride, cur_k, c)) return true;
+    }
+  };
+  have = advance();
   if (have) fast_prefetch(c, raw, lay.rawPitchWords, lane);
 
   while (have) {
@@ -410,31 +474,39 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
     {
       const u8* rb = reinterpret_cast<const u8*>(raw) + c.ox;
       const int rp = lay.rawPitchWords * 4;
-      const int n = (ch + 6) * tp;
-      int r = lane / tp, j = lane - r * tp;
-      const int dr = 32 / tp, dj = 32 - dr * tp;
       const int jmax = cw + 6 - S;   // pixels j+S beyond the tile are zero
+      if (lane < tp) {               // tp = S+6 <= 36: one row per step, a second sweep for wide cells
+        const u8* q = rb + lane;
+        unsigned* t = tile + lane;
+        const bool hasHi = lane < jmax;
 #pragma unroll 4
-      for (int i = lane; i < n; i += 32) {
-        const u8* q = rb + r * rp + j;
-        const unsigned lo = q[0];
-        const unsigned hi = j < jmax ? q[S] : 0u;
-        tile[i] = lo | (hi << 16);
-        j += dj;
-        r += dr;
-        if (j >= tp) { j -= tp; r++; }
+        for (int r = 0; r < ch + 6; r++) {
+          *t = (unsigned)q[0] | ((hasHi ? (unsigned)q[S] : 0u) << 16);
+          q += rp;
+          t += tp;
+        }
+      }
+      if (tp > 32 && lane + 32 < tp) {
+        const int j = lane + 32;
+        const u8* q = rb + j;
+        unsigned* t = tile + j;
+        const bool hasHi = j < jmax;
+        for (int r = 0; r < ch + 6; r++) {
+          *t = (unsigned)q[0] | ((hasHi ? (unsigned)q[S] : 0u) << 16);
+          q += rp;
+          t += tp;
+        }
       }
       for (int i = lane; i < (sp * (ch + 2) + 3) / 4; i += 32) reinterpret_cast<unsigned*>(sc)[i] = 0u;
     }
     __syncwarp();
     // the raw buffer is free again: prefetch the next cell of this warp
     const CellDesc cur = c;
-    item += nWarps;
-    have = false;
-    while (item < nItems && !(have = fast_cell_desc(g, pyr, pyrStride, item, c))) item += nWarps;
+    have = advance();
     if (have) fast_prefetch(c, raw, lay.rawPitchWords, lane);
 
     // ---- prefilter: lanes cover one row (S > 16) or two rows (S <= 16) per step
+    unsigned short* queue = hits + S * ch;   // the queue fills [S*ch, S*ch + nq), hits grow from 0
     int nq = 0;
     {
       const int two = S <= 16;
@@ -819,7 +891,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
 // Integer dot-product instructions do the taps: the horizontal pass is two IDP.4A per pixel on
 // byte windows built with funnel shifts, the vertical pass four IDP.2A per pixel on u16 pairs
 // (two tile rows interleaved per 32-bit word). One CTA blurs a 128 x 32 tile.
-constexpr int kBlurTW = 128, kBlurTH = 32;
+constexpr int kBlurTW = 128, kBlurTH = 64;
 constexpr int kBlurChunks = (kBlurTW + 32) / 16;  // 16-byte chunks per input tile row: image x0-16 .. x0+143
 constexpr int kBlurInP = kBlurChunks * 4 + 4;     // tile pitch in words (16-B aligned rows, 4 words pad)
 constexpr int kBlurRows = kBlurTH + 6;        // input rows y0-3 .. y0+34
@@ -854,13 +926,12 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       const unsigned* p = in + (2 * rp + q) * kBlurInP + xg + 3;  // image x0+4xg-4 = tile byte 4xg+12
+      // output x+j needs tile bytes (1+j .. 7+j) of (w0,w1,w2): the taps are applied with
+      // pre-shifted coefficient words instead of shifting the data
       const unsigned w0 = p[0], w1 = p[1], w2 = p[2];
-      const unsigned a0 = __funnelshift_r(w0, w1, 8), b0 = __funnelshift_r(w1, w2, 8);
-      const unsigned a1 = __funnelshift_r(w0, w1, 16), b1 = __funnelshift_r(w1, w2, 16);
-      const unsigned a2 = __funnelshift_r(w0, w1, 24), b2 = __funnelshift_r(w1, w2, 24);
-      hrow[q][0] = __dp4a(a0, 0x38302212u, __dp4a(b0, 0x00122230u, 0u));
-      hrow[q][1] = __dp4a(a1, 0x38302212u, __dp4a(b1, 0x00122230u, 0u));
-      hrow[q][2] = __dp4a(a2, 0x38302212u, __dp4a(b2, 0x00122230u, 0u));
+      hrow[q][0] = __dp4a(w0, 0x30221200u, __dp4a(w1, 0x12223038u, 0u));
+      hrow[q][1] = __dp4a(w0, 0x22120000u, __dp4a(w1, 0x22303830u, __dp4a(w2, 0x00000012u, 0u)));
+      hrow[q][2] = __dp4a(w0, 0x12000000u, __dp4a(w1, 0x30383022u, __dp4a(w2, 0x00001222u, 0u)));
       hrow[q][3] = __dp4a(w1, 0x38302212u, __dp4a(w2, 0x00122230u, 0u));
     }
     uint4 o;
@@ -1150,7 +1221,7 @@ struct orb_extractor {
   u8* d_pyr = nullptr; u8* d_blur = nullptr;
   uint2* d_cand = nullptr; int* d_candCount = nullptr; unsigned short* d_keyNode = nullptr;
   uint2* d_kept = nullptr; int* d_keptCount = nullptr; int2* d_taps = nullptr;
-  signed char* d_pattern = nullptr; int* d_overflow = nullptr;
+  signed char* d_pattern = nullptr; int* d_overflow = nullptr; int* d_work = nullptr;
   int wsFrames = 0;
   // staging for the host entry points: two sets, so that the H2D copy of chunk i+1 and the D2H
   // copy of chunk i-1 overlap the kernels of chunk i (copy streams + events)
@@ -1289,8 +1360,8 @@ int build_geom(orb_extractor* e, int W, int H) {
     y.rawPitchWords = (3 + maxCw + 6 + 3) / 4;
     y.rawBytes = round_up(y.rawPitchWords * 4 * (maxCh + 6), 16);
     y.tileBytes = round_up(4 * (S + 6) * (maxCh + 6), 16);
-    y.queueBytes = round_up(2 * S * maxCh, 16);
-    y.hitsBytes = round_up(2 * maxCw * maxCh, 16);
+    y.queueBytes = 0;
+    y.hitsBytes = round_up(2 * (2 * S * maxCh), 16);   // hits + queue share it (see k_fast_cells)
     y.scBytes = round_up((maxCw + 2) * (maxCh + 2) + 4, 16);
     y.total = y.rawBytes + y.tileBytes + y.queueBytes + y.hitsBytes + y.scBytes;
     e->fastSmem = (size_t)y.total * kFastWarps;
@@ -1382,12 +1453,13 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     launches++;
   }
   ORB_CUDA(cudaMemsetAsync(e->d_candCount, 0, (size_t)B * nl * sizeof(int), s));
+  ORB_CUDA(cudaMemsetAsync(e->d_work, 0, sizeof(int), s));
   if ((st = stage_mark(e, s))) return st;
   {
     const int nItems = g.totalCells * B;
     const int blocks = std::min(e->fastBlocks, (nItems + kFastWarps - 1) / kFastWarps);
     k_fast_cells<<<blocks, kFastThreads, e->fastSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_cand, e->d_candCount,
-                                                          e->candTotal, nItems, e->fastLay);
+                                                          e->candTotal, nItems, e->fastLay, e->d_work);
   }
   launches++;
   if ((st = stage_mark(e, s))) return st;
@@ -1487,6 +1559,7 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
   if (err == cudaSuccess) err = cudaMalloc(&e->d_pattern, sizeof ORB_BIT_PATTERN_31);
   if (err == cudaSuccess) err = cudaMemcpy(e->d_pattern, ORB_BIT_PATTERN_31, sizeof ORB_BIT_PATTERN_31, cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_overflow, sizeof(int));
+  if (err == cudaSuccess) err = cudaMalloc(&e->d_work, sizeof(int));
   if (err == cudaSuccess) err = cudaMemset(e->d_overflow, 0, sizeof(int));
   if (err != cudaSuccess) {
     delete e;
@@ -1501,7 +1574,7 @@ int orb_destroy(orb_extractor* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   free_workspace(e);
-  cudaFree(e->d_taps); cudaFree(e->d_pattern); cudaFree(e->d_overflow);
+  cudaFree(e->d_taps); cudaFree(e->d_pattern); cudaFree(e->d_overflow); cudaFree(e->d_work);
   for (int b = 0; b < 2; b++) {
     cudaFree(e->d_in[b]); cudaFree(e->d_kps[b]); cudaFree(e->d_desc[b]); cudaFree(e->d_n[b]);
     if (e->evIn[b]) cudaEventDestroy(e->evIn[b]);
