@@ -397,7 +397,11 @@ def run_ours(args, rank, world, local_rank):
                      "roofline": {"bound": "int-pipe", "achieved": cmp_per_s / world, "peak": popc_peak_cmp, "unit": "cmp/s",
                                   "frac": cmp_per_s / world / popc_peak_cmp,
                                   "peak_def": "measured POPC issue rate / 8 POPC per naive 256-bit comparison (SURVEY 8d)",
-                                  "popc_ops_per_s": pipes["popc"], "lop3_ops_per_s": pipes["lop3"]}},
+                                  "popc_ops_per_s": pipes["popc"], "lop3_ops_per_s": pipes["lop3"],
+                                  "mix_units_per_s": pipes["mix_popc_4lop3"],
+                                  "frac_of_mix_peak": cmp_per_s / world / (pipes["mix_popc_4lop3"] / 4.0),
+                                  "mix_peak_def": "kernel issues 4 POPC + 16 LOP3 per comparison (carry-save adders); "
+                                                  "peak = measured rate of that mix (POPC and LOP3 share the ALU pipe) / 4"}},
     }
     if allpairs:
         allpairs["roofline_frac"] = allpairs["value"] / world / popc_peak_cmp

@@ -189,8 +189,9 @@ int orb_hamming_matrix_device(orb_matcher* m, const uint8_t* d_a, int na, const 
 
 int orb_matcher_synchronize(orb_matcher* m, void* stream);
 
-/* Integer-pipe microbenchmark used for the matching roofline: runs `iters` dependent-free
- * POPC (what=0) or LOP3 (what=1) per thread on a full grid and returns ops/s in *ops_per_s. */
+/* Integer-pipe microbenchmark used for the matching roofline: independent chains of POPC
+ * (what=0), LOP3 (what=1) or the matcher's own mix of 1 POPC per 4 LOP3 (what=2, reported in
+ * units of (1 POPC + 4 LOP3) per second) on a full grid; returns ops/s in *ops_per_s. */
 int orb_int_pipe_peak(int device, int what, double* ops_per_s);
 
 #ifdef __cplusplus

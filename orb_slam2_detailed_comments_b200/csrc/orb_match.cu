@@ -337,9 +337,13 @@ __global__ void __launch_bounds__(256) k_int_pipe(unsigned* out, int iters, unsi
       if (WHAT == 0) {  // POPC: 8 independent chains
         x0 = __popc(x0) + seed; x1 = __popc(x1) + seed; x2 = __popc(x2) + seed; x3 = __popc(x3) + seed;
         x4 = __popc(x4) + seed; x5 = __popc(x5) + seed; x6 = __popc(x6) + seed; x7 = __popc(x7) + seed;
-      } else {          // LOP3: 8 independent chains of a non-trivial 3-input function
+      } else if (WHAT == 1) {  // LOP3: 8 independent chains of a non-trivial 3-input function
         x0 = (x0 & x1) ^ seed; x1 = (x1 & x2) ^ seed; x2 = (x2 & x3) ^ seed; x3 = (x3 & x4) ^ seed;
         x4 = (x4 & x5) ^ seed; x5 = (x5 & x6) ^ seed; x6 = (x6 & x7) ^ seed; x7 = (x7 & x0) ^ seed;
+      } else {                 // the matcher's mix: 1 POPC per 4 LOP3 (2 POPC + 8 LOP3 per step)
+        x0 = __popc(x0) + seed; x1 = (x1 & x2) ^ seed; x2 = (x2 & x3) ^ seed; x3 = (x3 & x5) ^ seed;
+        x5 = (x5 & x6) ^ seed; x4 = __popc(x4) + seed; x6 = (x6 & x7) ^ seed; x7 = (x7 & x1) ^ seed;
+        x1 = (x1 ^ x3) & seed; x2 = (x2 ^ x5) | seed;
       }
     }
   }
@@ -561,7 +565,8 @@ int orb_int_pipe_peak(int device, int what, double* ops_per_s) {
   for (int rep = 0; rep < 5; rep++) {
     ORB_CUDA(cudaEventRecord(e0));
     if (what == 0) k_int_pipe<0><<<blocks, 256>>>(d_out, iters, 0x9e3779b9u + rep);
-    else k_int_pipe<1><<<blocks, 256>>>(d_out, iters, 0x9e3779b9u + rep);
+    else if (what == 1) k_int_pipe<1><<<blocks, 256>>>(d_out, iters, 0x9e3779b9u + rep);
+    else k_int_pipe<2><<<blocks, 256>>>(d_out, iters, 0x9e3779b9u + rep);
     ORB_CUDA(cudaEventRecord(e1));
     ORB_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
@@ -571,7 +576,8 @@ int orb_int_pipe_peak(int device, int what, double* ops_per_s) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
   // per loop iteration: 8 unrolled x 8 chains of the measured op (plus one dependent add/xor each,
   // which issues on the other pipe for POPC and is the same op class for LOP3: counted once)
-  const double ops = (double)blocks * 256.0 * iters * 64.0;
+  // what = 2 reports "mix units" per second: one unit = 1 POPC + 4 LOP3 (16 units per loop iteration)
+  const double ops = (double)blocks * 256.0 * iters * (what == 2 ? 16.0 : 64.0);
   *ops_per_s = ops / (bestMs * 1e-3);
   return ORB_OK;
 }

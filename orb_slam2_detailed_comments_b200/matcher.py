@@ -109,7 +109,7 @@ class ORBmatcher:
 def int_pipe_peak(device=0):
     """Measured POPC and LOP3 issue rates (ops/s) of the device: matching roofline denominators."""
     out = {}
-    for name, what in (("popc", 0), ("lop3", 1)):
+    for name, what in (("popc", 0), ("lop3", 1), ("mix_popc_4lop3", 2)):
         v = C.c_double(0)
         check(lib().orb_int_pipe_peak(device, what, C.byref(v)))
         out[name] = v.value
