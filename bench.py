@@ -246,6 +246,33 @@ def run_ours(args, rank, world, local_rank):
     mean_kp = float(counts.mean())
     fps = world * frames_per_step * args.steps / (ms_total * 1e-3)
 
+    # ---- stereo front-end: both eyes + Frame::ComputeStereoMatches, device resident ---------------
+    d_ur = torch.zeros((frames_per_step // 2, cap), dtype=torch.float32, device=dev)
+    d_dp = torch.zeros((frames_per_step // 2, cap), dtype=torch.float32, device=dev)
+    # a rectified pair with real disparity: right eye = left eye shifted by 16 px (synthetic)
+    d_st = d_imgs.clone()
+    d_st[1::2, :, :-16] = d_imgs[0::2, :, 16:]
+    d_st[1::2, :, -16:] = d_imgs[0::2, :, -16:]
+    kitti_bf, kitti_fx = 386.1448, 718.856                      # Examples/Stereo/KITTI00-02.yaml
+    s_steps = max(1, min(args.steps, args.e2e_steps))
+    ext.extract_stereo_batch_device(d_st, d_kps, d_desc, d_counts, d_ur, d_dp, kitti_bf, kitti_bf / kitti_fx, stream=stream)
+    ext.synchronize(stream)
+    barrier()
+    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+    s0.record(tstream)
+    for _ in range(s_steps):
+        ext.extract_stereo_batch_device(d_st, d_kps, d_desc, d_counts, d_ur, d_dp, kitti_bf, kitti_bf / kitti_fx, stream=stream)
+    s1.record(tstream)
+    torch.cuda.synchronize()
+    st_ms = max_over_ranks(s0.elapsed_time(s1))
+    ext.synchronize(stream)
+    stereo_launches = ext.last_launch_count() * s_steps
+    stereo = {"value": world * (frames_per_step // 2) * s_steps / (st_ms * 1e-3), "unit": "stereo pairs/s",
+              "ms_per_step": st_ms / s_steps, "steps": s_steps,
+              "mean_stereo_points": float((d_ur >= 0).float().sum(dim=1).mean().item()),
+              "what": "orb_extract_stereo_batch_device: extraction of both eyes + ComputeStereoMatches (Frame.cc:831)"}
+    del d_st
+
     # ---- end to end through the host entry point of the C ABI (pinned buffers) -----------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h_imgs = torch.empty((frames_per_step, H, W), dtype=torch.uint8, pin_memory=True)
@@ -384,7 +411,8 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs larger than L2 (%d MB per step; unique pool 241 MB)" % (frames_per_step * W * H // 1000000), "parallelism": "frames sharded, no collective"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "orb_extract_batch_host (pinned host buffers)"},
-        "gpu_launches": launches_per_step * args.steps + e2e_launches + m_steps + (2 * world if allpairs else 0),
+        "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + m_steps + (2 * world if allpairs else 0),
+        "stereo": stereo,
         "clocks": clocks,
         "roofline": roofline,
         "path_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": total_b, "achieved": path_gbs, "peak": peak, "unit": "GB/s",

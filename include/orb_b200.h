@@ -98,6 +98,26 @@ int orb_extract_batch_device(orb_extractor* h, const uint8_t* d_images, int batc
                              size_t step, size_t frame_stride, orb_keypoint* d_keypoints, int capacity,
                              int32_t* d_counts, uint8_t* d_descriptors, void* stream);
 
+/* Stereo front-end of Frame::Frame(imLeft, imRight, ...) (src/Frame.cc:121-158): extraction of both
+ * eyes (the reference runs two extractor threads, :146-154) followed by
+ * Frame::ComputeStereoMatches (src/Frame.cc:831-1082): row-band candidates, best Hamming within one
+ * octave and the disparity range [0, mbf/mb), 11x11 SAD slide of +-5 px on the keypoint's pyramid
+ * level with parabola sub-pixel fit, 1.5*1.4*median SAD outlier cut. uright / depth receive
+ * mvuRight / mvDepth for the n_left left keypoints (-1 = no stereo match). The handle must have been
+ * created with max_batch >= 2. */
+int orb_extract_stereo(orb_extractor* h, const uint8_t* left, const uint8_t* right, int width, int height,
+                       size_t step, float mbf, float mb, orb_keypoint* kps_left, int capacity, int* n_left,
+                       uint8_t* desc_left, orb_keypoint* kps_right, int* n_right, uint8_t* desc_right,
+                       float* uright, float* depth);
+
+/* Same for `pairs` stereo pairs RESIDENT IN DEVICE MEMORY, frames interleaved L0,R0,L1,R1,...;
+ * d_keypoints / d_descriptors / d_counts as in orb_extract_batch_device over 2*pairs frames,
+ * d_uright / d_depth are pairs x capacity floats. Asynchronous on `stream`. */
+int orb_extract_stereo_batch_device(orb_extractor* h, const uint8_t* d_images, int pairs, int width, int height,
+                                    size_t step, size_t frame_stride, orb_keypoint* d_keypoints, int capacity,
+                                    int32_t* d_counts, uint8_t* d_descriptors, float mbf, float mb,
+                                    float* d_uright, float* d_depth, void* stream);
+
 /* Blocks until the handle's work (on `stream`, NULL = own stream) is done; reports sticky
  * capacity overflows of internal candidate lists as ORB_ERR_CAPACITY. */
 int orb_synchronize(orb_extractor* h, void* stream);

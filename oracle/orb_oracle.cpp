@@ -727,6 +727,97 @@ int search_for_initialization(const FrameView& F1, const FrameView& F2, const fl
   return nmatches;
 }
 
+// ---------------------------------------------------------------- stereo
+// Frame::ComputeStereoMatches, Frame.cc:831-1082. Uses the pyramids the two extractors hold from
+// their last run (mpORBextractorLeft/Right->mvImagePyramid). Returns the number of stereo points.
+int compute_stereo_matches(const Extractor& EL, const Extractor& ER, const KeyPoint* kpL, int N, const u8* descL,
+                           const KeyPoint* kpR, int Nr, const u8* descR, float mbf, float mb, float* uRight,
+                           float* depth) {
+  const int TH_HIGH = 100, TH_LOW = 50;
+  for (int i = 0; i < N; i++) { uRight[i] = -1.0f; depth[i] = -1.0f; }
+  const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+  const int nRows = EL.pyr[0].h;
+  std::vector<std::vector<int>> rowIdx(nRows);
+  for (int iR = 0; iR < Nr; iR++) {
+    const float kpY = kpR[iR].y;
+    const float r = 2.0f * EL.p.scale[kpR[iR].octave];
+    const int maxr = (int)std::ceil(kpY + r), minr = (int)std::floor(kpY - r);
+    for (int yi = minr; yi <= maxr; yi++)
+      if (yi >= 0 && yi < nRows) rowIdx[yi].push_back(iR);   // the reference does not bounds-check
+  }
+  const float minZ = mb, minD = 0, maxD = mbf / minZ;
+  std::vector<std::pair<int, int>> distIdx;
+  for (int iL = 0; iL < N; iL++) {
+    const int levelL = kpL[iL].octave;
+    const float vL = kpL[iL].y, uL = kpL[iL].x;
+    const int row = (int)vL;
+    if (row < 0 || row >= nRows) continue;
+    const std::vector<int>& cands = rowIdx[row];
+    if (cands.empty()) continue;
+    const float minU = uL - maxD, maxU = uL - minD;
+    if (maxU < 0) continue;
+    int bestDist = TH_HIGH, bestIdxR = 0;
+    for (int iR : cands) {
+      if (kpR[iR].octave < levelL - 1 || kpR[iR].octave > levelL + 1) continue;
+      const float uR = kpR[iR].x;
+      if (uR >= minU && uR <= maxU) {
+        const int d = hamming256(descL + (size_t)iL * 32, descR + (size_t)iR * 32);
+        if (d < bestDist) { bestDist = d; bestIdxR = iR; }
+      }
+    }
+    if (bestDist >= thOrbDist) continue;
+    const float uR0 = kpR[bestIdxR].x;
+    const float sf = EL.p.invScale[levelL];
+    const float scaleduL = std::round(kpL[iL].x * sf), scaledvL = std::round(kpL[iL].y * sf);
+    const float scaleduR0 = std::round(uR0 * sf);
+    const int w = 5, L = 5;
+    const Image& IL = EL.pyr[levelL];
+    const Image& IR = ER.pyr[levelL];
+    const int cvL = (int)scaledvL, cuL = (int)scaleduL, cuR = (int)scaleduR0;
+    const float iniu = scaleduR0 - L - w, endu = scaleduR0 + L + w + 1;
+    if (iniu < 0 || endu >= IR.w) continue;
+    int best = INT_MAX, bestinc = 0;
+    float vd[2 * 5 + 1];
+    const float cL = (float)IL.row(cvL)[cuL];
+    for (int inc = -L; inc <= L; inc++) {
+      const float cR = (float)IR.row(cvL)[cuR + inc];
+      float dist = 0;
+      for (int dy = -w; dy <= w; dy++)
+        for (int dx = -w; dx <= w; dx++) {
+          const float a = (float)IL.row(cvL + dy)[cuL + dx] - cL;
+          const float b = (float)IR.row(cvL + dy)[cuR + inc + dx] - cR;
+          dist += std::fabs(a - b);
+        }
+      if (dist < best) { best = (int)dist; bestinc = inc; }
+      vd[L + inc] = dist;
+    }
+    if (bestinc == -L || bestinc == L) continue;
+    const float d1 = vd[L + bestinc - 1], d2 = vd[L + bestinc], d3 = vd[L + bestinc + 1];
+    const float deltaR = (d1 - d3) / (2.0f * (d1 + d3 - 2.0f * d2));
+    if (deltaR < -1 || deltaR > 1) continue;
+    float bestuR = EL.p.scale[levelL] * ((float)scaleduR0 + (float)bestinc + deltaR);
+    float disparity = uL - bestuR;
+    if (disparity >= minD && disparity < maxD) {
+      if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+      depth[iL] = mbf / disparity;
+      uRight[iL] = bestuR;
+      distIdx.push_back(std::make_pair(best, iL));
+    }
+  }
+  if (distIdx.empty()) return 0;   // the reference indexes an empty vector here
+  std::sort(distIdx.begin(), distIdx.end());
+  const float median = (float)distIdx[distIdx.size() / 2].first;
+  const float thDist = 1.5f * 1.4f * median;
+  int kept = (int)distIdx.size();
+  for (int i = (int)distIdx.size() - 1; i >= 0; i--) {
+    if (distIdx[i].first < thDist) break;
+    uRight[distIdx[i].second] = -1;
+    depth[distIdx[i].second] = -1;
+    kept--;
+  }
+  return kept;
+}
+
 }  // namespace
 
 // ==================================================================== C ABI (ctypes)
@@ -837,6 +928,12 @@ int orc_quadtree(const float* xs, const float* ys, const int* score, int n, int 
   std::vector<int> r = distribute_quadtree(c, minX, maxX, minY, maxY, N, tie_sensitive);
   for (int i = 0; i < std::min((int)r.size(), cap); i++) kept[i] = r[i];
   return (int)r.size();
+}
+
+int orc_stereo_matches(void* hL, void* hR, const void* kpL, int nL, const u8* descL, const void* kpR, int nR,
+                       const u8* descR, float mbf, float mb, float* uRight, float* depth) {
+  return compute_stereo_matches(*(Extractor*)hL, *(Extractor*)hR, (const KeyPoint*)kpL, nL, descL, (const KeyPoint*)kpR, nR,
+                                descR, mbf, mb, uRight, depth);
 }
 
 // ---- matcher

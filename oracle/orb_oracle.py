@@ -108,6 +108,17 @@ class OracleExtractor:
         return dict(cells=a.value, fallback=b.value, tie_sensitive=c.value)
 
 
+def stereo_matches(ext_left, ext_right, kps_l, desc_l, kps_r, desc_r, mbf, mb):
+    """Mirror of Frame::ComputeStereoMatches (Frame.cc:831) on the pyramids the two oracle extractors
+    hold from their last call. Returns (mvuRight, mvDepth, n_kept)."""
+    kps_l = np.ascontiguousarray(kps_l); kps_r = np.ascontiguousarray(kps_r)
+    desc_l = np.ascontiguousarray(desc_l, np.uint8); desc_r = np.ascontiguousarray(desc_r, np.uint8)
+    ur = np.zeros(len(kps_l), np.float32); dp = np.zeros(len(kps_l), np.float32)
+    n = lib().orc_stereo_matches(ext_left.h, ext_right.h, _p(kps_l), len(kps_l), _p(desc_l), _p(kps_r), len(kps_r),
+                                 _p(desc_r), C.c_float(mbf), C.c_float(mb), _p(ur), _p(dp))
+    return ur, dp, n
+
+
 def resize_linear(src, dw, dh):
     src = np.ascontiguousarray(src, np.uint8)
     dst = np.zeros((dh, dw), np.uint8)

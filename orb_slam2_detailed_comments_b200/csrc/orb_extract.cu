@@ -1192,6 +1192,162 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Frame::ComputeStereoMatches (Frame.cc:831-1082): one CTA per stereo pair (frames 2p, 2p+1 of the
+// chunk), one warp per left keypoint.
+//   coarse : best Hamming among right keypoints whose row band (+-2*scale) holds the left row, within
+//            one octave and the disparity range (first wins = lowest right index) (:867-948)
+//   refine : 11x11 SAD slide of +-5 px on the keypoint's pyramid level, parabola fit (:951-1064)
+//   prune  : drop matches whose SAD is >= 1.5*1.4*median (:1069-1081)
+// ------------------------------------------------------------------------------------------
+constexpr int kStereoThreads = 256;
+
+__device__ __forceinline__ int hamming_words(const unsigned a[8], const uint4 lo, const uint4 hi) {
+  return __popc(a[0] ^ lo.x) + __popc(a[1] ^ lo.y) + __popc(a[2] ^ lo.z) + __popc(a[3] ^ lo.w) + __popc(a[4] ^ hi.x) +
+         __popc(a[5] ^ hi.y) + __popc(a[6] ^ hi.z) + __popc(a[7] ^ hi.w);
+}
+
+__global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
+                                                           const orb_keypoint* __restrict__ kps, const u8* __restrict__ desc,
+                                                           const int* __restrict__ counts, int cap, float mbf, float mb,
+                                                           const float* __restrict__ invScale, float* __restrict__ uRight,
+                                                           float* __restrict__ depth) {
+  extern __shared__ __align__(16) unsigned char ssm[];
+  __shared__ int s_n;
+  __shared__ float s_median;
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fL = 2 * pair, fR = 2 * pair + 1;
+  const int N = counts[fL], Nr = counts[fR];
+  float* rx = reinterpret_cast<float*>(ssm);                       // right keypoint x
+  int* rband = reinterpret_cast<int*>(rx + cap);                   // minr | maxr << 16
+  int2* sad = reinterpret_cast<int2*>(rband + cap);                // (SAD best, left index)
+  u8* roct = reinterpret_cast<u8*>(sad + cap);
+  const orb_keypoint* KL = kps + (size_t)fL * cap;
+  const orb_keypoint* KR = kps + (size_t)fR * cap;
+  const u8* DL = desc + (size_t)fL * cap * 32;
+  const u8* DR = desc + (size_t)fR * cap * 32;
+  float* uR = uRight + (size_t)pair * cap;
+  float* dp = depth + (size_t)pair * cap;
+  for (int i = tid; i < cap; i += kStereoThreads) { uR[i] = -1.0f; dp[i] = -1.0f; }
+  for (int i = tid; i < Nr; i += kStereoThreads) {
+    const orb_keypoint k = KR[i];
+    const float r = __fmul_rn(2.0f, g.lv[k.octave].scale);         // :858
+    const int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));
+    rx[i] = k.x;
+    rband[i] = (max(minr, 0) & 0xffff) | (min(maxr, 0xffff) << 16);
+    roct[i] = (u8)k.octave;
+  }
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  const float maxD = __fdiv_rn(mbf, mb);   // minZ = mb, minD = 0 (:885-887)
+  const int TH_HIGH = 100, thOrbDist = 75;
+  for (int iL = wid; iL < N; iL += kStereoThreads / 32) {
+    const orb_keypoint kl = KL[iL];
+    const int levelL = kl.octave, row = (int)kl.y;
+    const float uL = kl.x, minU = __fsub_rn(uL, maxD), maxU = uL;
+    if (maxU < 0.f) continue;
+    const uint4* dl = reinterpret_cast<const uint4*>(DL + (size_t)iL * 32);
+    const uint4 dlo = __ldg(dl), dhi = __ldg(dl + 1);
+    const unsigned a[8] = {dlo.x, dlo.y, dlo.z, dlo.w, dhi.x, dhi.y, dhi.z, dhi.w};
+    unsigned key = 0xffffffffu;
+    for (int iR = lane; iR < Nr; iR += 32) {
+      const int band = rband[iR], o = roct[iR];
+      const float x = rx[iR];
+      if (row >= (band & 0xffff) && row <= (band >> 16) && o >= levelL - 1 && o <= levelL + 1 && x >= minU && x <= maxU) {
+        const uint4* dr = reinterpret_cast<const uint4*>(DR + (size_t)iR * 32);
+        const int d = hamming_words(a, __ldg(dr), __ldg(dr + 1));
+        if (d < TH_HIGH) key = min(key, ((unsigned)d << 16) | (unsigned)iR);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if (key == 0xffffffffu || (int)(key >> 16) >= thOrbDist) continue;
+    const int bestIdxR = (int)(key & 0xffffu);
+    // ---- SAD refinement on pyramid level levelL
+    const LevelGeom& L = g.lv[levelL];
+    const float sf = invScale[levelL];
+    const float scaleduL = roundf(__fmul_rn(kl.x, sf)), scaledvL = roundf(__fmul_rn(kl.y, sf));
+    const float scaleduR0 = roundf(__fmul_rn(rx[bestIdxR], sf));
+    const float iniu = scaleduR0 - 10.f, endu = scaleduR0 + 11.f;   // L + w = 10 (this fork: :990-992)
+    if (iniu < 0.f || endu >= (float)L.w) continue;
+    const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+    const u8* IL = pyr + (size_t)fL * pyrStride + L.off + (long long)cv * L.pitch + cu;
+    const u8* IR = pyr + (size_t)fR * pyrStride + L.off + (long long)cv * L.pitch + cr;
+    const int cL = IL[0];
+    int acc[11];
+#pragma unroll
+    for (int q = 0; q < 11; q++) acc[q] = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int pI = lane + 32 * t;
+      if (pI < 121) {
+        const int dy = pI / 11 - 5, dx = pI % 11 - 5;
+        const int av = (int)IL[dy * L.pitch + dx] - cL;
+        const u8* rrow = IR + dy * L.pitch + dx;
+#pragma unroll
+        for (int q = 0; q < 11; q++) {
+          const int bv = (int)rrow[q - 5] - (int)IR[q - 5];
+          acc[q] += abs(av - bv);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 11; q++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
+    if (lane == 0) {
+      int best = 0x7fffffff, bestinc = 0;
+#pragma unroll
+      for (int q = 0; q < 11; q++)
+        if (acc[q] < best) { best = acc[q]; bestinc = q - 5; }
+      if (bestinc != -5 && bestinc != 5) {
+        float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+        for (int q = 1; q < 10; q++)
+          if (q - 5 == bestinc) { d1 = (float)acc[q - 1]; d2 = (float)acc[q]; d3 = (float)acc[q + 1]; }
+        const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+        if (!(deltaR < -1.f || deltaR > 1.f)) {
+          float bestuR = __fmul_rn(L.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+          float disparity = __fsub_rn(uL, bestuR);
+          if (disparity >= 0.f && disparity < maxD) {
+            if (disparity <= 0.f) {
+              disparity = (float)0.01;
+              bestuR = (float)((double)uL - 0.01);
+            }
+            dp[iL] = __fdiv_rn(mbf, disparity);
+            uR[iL] = bestuR;
+            sad[atomicAdd(&s_n, 1)] = make_int2(best, iL);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n == 0) return;
+  // median of the SAD values = element n/2 of the sorted list (only the value matters)
+  const int kth = n / 2;
+  for (int i = tid; i < n; i += kStereoThreads) {
+    const int v = sad[i].x;
+    int less = 0, leq = 0;
+    for (int j = 0; j < n; j++) {
+      const int u = sad[j].x;
+      less += u < v;
+      leq += u <= v;
+    }
+    if (less <= kth && kth < leq) s_median = (float)v;
+  }
+  __syncthreads();
+  const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), s_median);
+  for (int i = tid; i < n; i += kStereoThreads) {
+    if (!((float)sad[i].x < thDist)) {
+      uR[sad[i].y] = -1.0f;
+      dp[sad[i].y] = -1.0f;
+    }
+  }
+}
+
 inline int cv_round_f(float v) { return (int)lrintf(v); }
 
 }  // namespace
@@ -1233,6 +1389,8 @@ struct orb_extractor {
   std::vector<u8> hostPyr;
   int lastLaunches = 0;
   int lastChunkFrames = 0;
+  float* d_invScale = nullptr;          // mvInvScaleFactor on the device (stereo refinement)
+  float* d_uRight[2] = {nullptr, nullptr}; float* d_depth[2] = {nullptr, nullptr};  // host-path staging
   // optional per-stage CUDA-event timing (bench roofline): 6 boundary events per chunk
   bool profile = false;
   std::vector<cudaEvent_t> evPool;
@@ -1486,6 +1644,21 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   return ORB_OK;
 }
 
+// Frame::ComputeStereoMatches for the B/2 stereo pairs of the chunk that was just extracted
+// (frames 2p = left, 2p+1 = right; the chunk's pyramids are still in the workspace).
+int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, const int* d_counts, const u8* d_desc, float mbf,
+               float mb, float* d_uRight, float* d_depth, cudaStream_t s) {
+  const size_t smem = round_up((size_t)cap * (4 + 4 + 8 + 1), (size_t)16);
+  if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints per frame for the stereo kernel's shared memory");
+  if (cap > 65535) ORB_FAIL(ORB_ERR_UNSUPPORTED, "stereo matching supports at most 65535 keypoints per frame");
+  ORB_CUDA(cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_stereo<<<B / 2, kStereoThreads, smem, s>>>(e->g, e->d_pyr, e->pyrStride, d_kps, d_desc, d_counts, cap, mbf, mb, e->d_invScale,
+                                                d_uRight, d_depth);
+  ORB_CUDA(cudaGetLastError());
+  e->lastLaunches++;
+  return ORB_OK;
+}
+
 int ensure_stage(orb_extractor* e, size_t inBytes, int frames, int cap) {
   if (!e->sIn) {
     ORB_CUDA(cudaStreamCreateWithFlags(&e->sIn, cudaStreamNonBlocking));
@@ -1560,6 +1733,8 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
   if (err == cudaSuccess) err = cudaMemcpy(e->d_pattern, ORB_BIT_PATTERN_31, sizeof ORB_BIT_PATTERN_31, cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_overflow, sizeof(int));
   if (err == cudaSuccess) err = cudaMalloc(&e->d_work, sizeof(int));
+  if (err == cudaSuccess) err = cudaMalloc(&e->d_invScale, kMaxLevels * sizeof(float));
+  if (err == cudaSuccess) err = cudaMemcpy(e->d_invScale, e->invScale.data(), e->invScale.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMemset(e->d_overflow, 0, sizeof(int));
   if (err != cudaSuccess) {
     delete e;
@@ -1574,7 +1749,8 @@ int orb_destroy(orb_extractor* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   free_workspace(e);
-  cudaFree(e->d_taps); cudaFree(e->d_pattern); cudaFree(e->d_overflow); cudaFree(e->d_work);
+  cudaFree(e->d_taps); cudaFree(e->d_pattern); cudaFree(e->d_overflow); cudaFree(e->d_work); cudaFree(e->d_invScale);
+  for (int b = 0; b < 2; b++) { cudaFree(e->d_uRight[b]); cudaFree(e->d_depth[b]); }
   for (int b = 0; b < 2; b++) {
     cudaFree(e->d_in[b]); cudaFree(e->d_kps[b]); cudaFree(e->d_desc[b]); cudaFree(e->d_n[b]);
     if (e->evIn[b]) cudaEventDestroy(e->evIn[b]);
@@ -1744,6 +1920,82 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
       pyramid[l].height = e->g.lv[l].h;
       pyramid[l].step = e->g.lv[l].pitch;
     }
+  return ORB_OK;
+}
+
+int orb_extract_stereo_batch_device(orb_extractor* e, const uint8_t* d_images, int pairs, int width, int height, size_t step,
+                                    size_t frame_stride, orb_keypoint* d_keypoints, int capacity, int32_t* d_counts,
+                                    uint8_t* d_descriptors, float mbf, float mb, float* d_uright, float* d_depth,
+                                    void* stream) {
+  if (!e || !d_images || !d_keypoints || !d_counts || !d_descriptors || !d_uright || !d_depth) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (pairs <= 0 || width <= 0 || height <= 0 || capacity <= 0 || step < (size_t)width || !(mb > 0.f) || !(mbf > 0.f))
+    ORB_FAIL(ORB_ERR_INVALID, "bad size or stereo baseline");
+  int st = ensure_geom(e, width, height, std::max(2, 2 * pairs));
+  if (st) return st;
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  e->lastLaunches = 0;
+  const int chunk = std::max(2, e->wsFrames & ~1);
+  if (chunk > e->wsFrames) ORB_FAIL(ORB_ERR_INVALID, "max_batch must be >= 2 for stereo");
+  const int batch = 2 * pairs;
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int B = std::min(chunk, batch - b0);
+    st = run_chunk(e, d_images + (size_t)b0 * frame_stride, B, step, frame_stride, d_keypoints + (size_t)b0 * capacity,
+                   capacity, d_counts + b0, d_descriptors + (size_t)b0 * capacity * 32, s);
+    if (st) return st;
+    st = run_stereo(e, B, d_keypoints + (size_t)b0 * capacity, capacity, d_counts + b0,
+                    d_descriptors + (size_t)b0 * capacity * 32, mbf, mb, d_uright + (size_t)(b0 / 2) * capacity,
+                    d_depth + (size_t)(b0 / 2) * capacity, s);
+    if (st) return st;
+  }
+  return ORB_OK;
+}
+
+int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* right, int width, int height, size_t step,
+                       float mbf, float mb, orb_keypoint* kps_left, int capacity, int* n_left, uint8_t* desc_left,
+                       orb_keypoint* kps_right, int* n_right, uint8_t* desc_right, float* uright, float* depth) {
+  if (!e || !n_left || !n_right) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (!left || !right || width == 0 || height == 0) return ORB_OK;  // empty image: outputs untouched
+  if (!kps_left || !kps_right || !desc_left || !desc_right || !uright || !depth || capacity <= 0 || !(mb > 0.f) || !(mbf > 0.f))
+    ORB_FAIL(ORB_ERR_INVALID, "null output or bad stereo baseline");
+  if (e->maxBatch < 2) ORB_FAIL(ORB_ERR_INVALID, "max_batch must be >= 2 for stereo");
+  int st = ensure_geom(e, width, height, 2);
+  if (st) return st;
+  const size_t dFrame = (size_t)width * height;
+  st = ensure_stage(e, dFrame * 2, 2, capacity);
+  if (st) return st;
+  if (!e->d_uRight[0] || e->stageCap < capacity) {
+    cudaFree(e->d_uRight[0]); cudaFree(e->d_depth[0]);
+    e->d_uRight[0] = e->d_depth[0] = nullptr;
+  }
+  if (!e->d_uRight[0]) {
+    ORB_CUDA(cudaMalloc(&e->d_uRight[0], (size_t)std::max(capacity, e->stageCap) * sizeof(float)));
+    ORB_CUDA(cudaMalloc(&e->d_depth[0], (size_t)std::max(capacity, e->stageCap) * sizeof(float)));
+  }
+  cudaStream_t s = e->stream;
+  e->lastLaunches = 0;
+  ORB_CUDA(cudaMemcpy2DAsync(e->d_in[0], width, left, step, width, height, cudaMemcpyHostToDevice, s));
+  ORB_CUDA(cudaMemcpy2DAsync(e->d_in[0] + dFrame, width, right, step, width, height, cudaMemcpyHostToDevice, s));
+  st = run_chunk(e, e->d_in[0], 2, width, dFrame, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], s);
+  if (st) return st;
+  st = run_stereo(e, 2, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], mbf, mb, e->d_uRight[0], e->d_depth[0], s);
+  if (st) return st;
+  int cnt[2] = {0, 0};
+  ORB_CUDA(cudaMemcpyAsync(cnt, e->d_n[0], 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaStreamSynchronize(s));
+  if (cnt[0] > 0) {
+    ORB_CUDA(cudaMemcpyAsync(kps_left, e->d_kps[0], (size_t)cnt[0] * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(desc_left, e->d_desc[0], (size_t)cnt[0] * 32, cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(uright, e->d_uRight[0], (size_t)cnt[0] * sizeof(float), cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(depth, e->d_depth[0], (size_t)cnt[0] * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  if (cnt[1] > 0) {
+    ORB_CUDA(cudaMemcpyAsync(kps_right, e->d_kps[0] + capacity, (size_t)cnt[1] * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
+    ORB_CUDA(cudaMemcpyAsync(desc_right, e->d_desc[0] + (size_t)capacity * 32, (size_t)cnt[1] * 32, cudaMemcpyDeviceToHost, s));
+  }
+  st = check_overflow(e, s);
+  if (st) return st;
+  *n_left = cnt[0];
+  *n_right = cnt[1];
   return ORB_OK;
 }
 

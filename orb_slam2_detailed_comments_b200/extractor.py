@@ -102,6 +102,30 @@ class ORBextractor:
         check(self._L.orb_extract_batch_device(self._h, ptr(d_images), B, w, h, d_images.stride(1), d_images.stride(0),
                                                ptr(d_kps), cap, ptr(d_counts), ptr(d_desc), C.c_void_p(stream or 0)))
 
+    # ---- stereo: both eyes + Frame::ComputeStereoMatches (src/Frame.cc:121-158, 831-1082)
+    def extract_stereo(self, left, right, mbf, mb):
+        """Returns (kpsL, descL, kpsR, descR, mvuRight, mvDepth) for one rectified pair."""
+        assert left.shape == right.shape and left.dtype == np.uint8 and right.dtype == np.uint8
+        left = np.ascontiguousarray(left); right = np.ascontiguousarray(right)
+        h, w = left.shape
+        cap = self.max_keypoints
+        kl = np.zeros(cap, KP_DTYPE); kr = np.zeros(cap, KP_DTYPE)
+        dl = np.zeros((cap, 32), np.uint8); dr = np.zeros((cap, 32), np.uint8)
+        ur = np.zeros(cap, np.float32); dp = np.zeros(cap, np.float32)
+        nl = C.c_int(0); nr = C.c_int(0)
+        check(self._L.orb_extract_stereo(self._h, ptr(left), ptr(right), w, h, w, C.c_float(mbf), C.c_float(mb), ptr(kl), cap,
+                                         C.byref(nl), ptr(dl), ptr(kr), C.byref(nr), ptr(dr), ptr(ur), ptr(dp)))
+        a, b = nl.value, nr.value
+        return kl[:a].copy(), dl[:a].copy(), kr[:b].copy(), dr[:b].copy(), ur[:a].copy(), dp[:a].copy()
+
+    def extract_stereo_batch_device(self, d_images, d_kps, d_desc, d_counts, d_uright, d_depth, mbf, mb, stream=None):
+        """d_images (2P,H,W) u8 interleaved L0,R0,...; d_uright / d_depth (P,cap) f32."""
+        B, h, w = d_images.shape
+        cap = d_kps.shape[1]
+        check(self._L.orb_extract_stereo_batch_device(self._h, ptr(d_images), B // 2, w, h, d_images.stride(1), d_images.stride(0),
+                                                      ptr(d_kps), cap, ptr(d_counts), ptr(d_desc), C.c_float(mbf), C.c_float(mb),
+                                                      ptr(d_uright), ptr(d_depth), C.c_void_p(stream or 0)))
+
     def synchronize(self, stream=None):
         check(self._L.orb_synchronize(self._h, C.c_void_p(stream or 0)))
 
