@@ -1200,7 +1200,7 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
 //   refine : 11x11 SAD slide of +-5 px on the keypoint's pyramid level, parabola fit (:951-1064)
 //   prune  : drop matches whose SAD is >= 1.5*1.4*median (:1069-1081)
 // ------------------------------------------------------------------------------------------
-constexpr int kStereoThreads = 256;
+constexpr int kStereoThreads = 512;
 
 __device__ __forceinline__ int hamming_words(const unsigned a[8], const uint4 lo, const uint4 hi) {
   return __popc(a[0] ^ lo.x) + __popc(a[1] ^ lo.y) + __popc(a[2] ^ lo.z) + __popc(a[3] ^ lo.w) + __popc(a[4] ^ hi.x) +
@@ -1211,9 +1211,10 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
                                                            const orb_keypoint* __restrict__ kps, const u8* __restrict__ desc,
                                                            const int* __restrict__ counts, int cap, float mbf, float mb,
                                                            const float* __restrict__ invScale, float* __restrict__ uRight,
-                                                           float* __restrict__ depth) {
+                                                           float* __restrict__ depth, int entCap) {
   extern __shared__ __align__(16) unsigned char ssm[];
   __shared__ int s_n;
+  __shared__ int s_scan[34];
   __shared__ float s_median;
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fL = 2 * pair, fR = 2 * pair + 1;
@@ -1221,7 +1222,10 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
   float* rx = reinterpret_cast<float*>(ssm);                       // right keypoint x
   int* rband = reinterpret_cast<int*>(rx + cap);                   // minr | maxr << 16
   int2* sad = reinterpret_cast<int2*>(rband + cap);                // (SAD best, left index)
-  u8* roct = reinterpret_cast<u8*>(sad + cap);
+  int* rowStart = reinterpret_cast<int*>(sad + cap);               // [nRows + 1] row index of the right keypoints
+  unsigned short* ent = reinterpret_cast<unsigned short*>(rowStart + (g.H + 2));   // vRowIndices, flattened (:846-865)
+  u8* roct = reinterpret_cast<u8*>(ent + entCap);
+  const int nRows = g.H;
   const orb_keypoint* KL = kps + (size_t)fL * cap;
   const orb_keypoint* KR = kps + (size_t)fR * cap;
   const u8* DL = desc + (size_t)fL * cap * 32;
@@ -1237,7 +1241,27 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
     rband[i] = (max(minr, 0) & 0xffff) | (min(maxr, 0xffff) << 16);
     roct[i] = (u8)k.octave;
   }
+  for (int i = tid; i <= nRows; i += kStereoThreads) rowStart[i] = 0;
   if (tid == 0) s_n = 0;
+  __syncthreads();
+  // vRowIndices: count, scan, fill (order inside a row is irrelevant: ties are broken by the packed key)
+  for (int i = tid; i < Nr; i += kStereoThreads) {
+    const int band = rband[i];
+    for (int y = band & 0xffff; y <= min(band >> 16, nRows - 1); y++) atomicAdd(&rowStart[y], 1);
+  }
+  __syncthreads();
+  const int total = block_scan_excl(rowStart, nRows + 1, s_scan);
+  const bool indexed = total <= entCap;     // otherwise fall back to scanning every right keypoint
+  if (indexed) {
+    // rowStart[y] now holds the start of row y; fill using a second cursor array aliased on `sad`
+    int* cursor = reinterpret_cast<int*>(sad);
+    for (int i = tid; i < nRows; i += kStereoThreads) cursor[i] = rowStart[i];
+    __syncthreads();
+    for (int i = tid; i < Nr; i += kStereoThreads) {
+      const int band = rband[i];
+      for (int y = band & 0xffff; y <= min(band >> 16, nRows - 1); y++) ent[atomicAdd(&cursor[y], 1)] = (unsigned short)i;
+    }
+  }
   __syncthreads();
   const float maxD = __fdiv_rn(mbf, mb);   // minZ = mb, minD = 0 (:885-887)
   const int TH_HIGH = 100, thOrbDist = 75;
@@ -1250,13 +1274,27 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
     const uint4 dlo = __ldg(dl), dhi = __ldg(dl + 1);
     const unsigned a[8] = {dlo.x, dlo.y, dlo.z, dlo.w, dhi.x, dhi.y, dhi.z, dhi.w};
     unsigned key = 0xffffffffu;
-    for (int iR = lane; iR < Nr; iR += 32) {
-      const int band = rband[iR], o = roct[iR];
-      const float x = rx[iR];
-      if (row >= (band & 0xffff) && row <= (band >> 16) && o >= levelL - 1 && o <= levelL + 1 && x >= minU && x <= maxU) {
-        const uint4* dr = reinterpret_cast<const uint4*>(DR + (size_t)iR * 32);
-        const int d = hamming_words(a, __ldg(dr), __ldg(dr + 1));
-        if (d < TH_HIGH) key = min(key, ((unsigned)d << 16) | (unsigned)iR);
+    if (indexed) {
+      if (row < 0 || row >= nRows) continue;
+      const int e1 = rowStart[row + 1];
+      for (int e = rowStart[row] + lane; e < e1; e += 32) {
+        const int iR = ent[e], o = roct[iR];
+        const float x = rx[iR];
+        if (o >= levelL - 1 && o <= levelL + 1 && x >= minU && x <= maxU) {
+          const uint4* dr = reinterpret_cast<const uint4*>(DR + (size_t)iR * 32);
+          const int d = hamming_words(a, __ldg(dr), __ldg(dr + 1));
+          if (d < TH_HIGH) key = min(key, ((unsigned)d << 16) | (unsigned)iR);
+        }
+      }
+    } else {
+      for (int iR = lane; iR < Nr; iR += 32) {
+        const int band = rband[iR], o = roct[iR];
+        const float x = rx[iR];
+        if (row >= (band & 0xffff) && row <= (band >> 16) && o >= levelL - 1 && o <= levelL + 1 && x >= minU && x <= maxU) {
+          const uint4* dr = reinterpret_cast<const uint4*>(DR + (size_t)iR * 32);
+          const int d = hamming_words(a, __ldg(dr), __ldg(dr + 1));
+          if (d < TH_HIGH) key = min(key, ((unsigned)d << 16) | (unsigned)iR);
+        }
       }
     }
 #pragma unroll
@@ -1326,19 +1364,39 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
   __syncthreads();
   const int n = s_n;
   if (n == 0) return;
-  // median of the SAD values = element n/2 of the sorted list (only the value matters)
-  const int kth = n / 2;
-  for (int i = tid; i < n; i += kStereoThreads) {
-    const int v = sad[i].x;
-    int less = 0, leq = 0;
-    for (int j = 0; j < n; j++) {
-      const int u = sad[j].x;
-      less += u < v;
-      leq += u <= v;
+  // median of the SAD values = element n/2 of the sorted list (only the value matters): two-pass
+  // radix select on shared-memory histograms (SAD <= 121 * 1020 < 2^17: 9 high bits, then 8 low bits)
+  {
+    int* hist = rowStart;   // the row index is no longer needed; >= 512 ints (nRows + 1 >= 512 is NOT
+                            // guaranteed, so the histogram lives in the (larger) entry array when needed)
+    if (nRows + 1 < 512) hist = reinterpret_cast<int*>(ent);
+    const int kth = n / 2;
+    for (int i = tid; i < 512; i += kStereoThreads) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kStereoThreads) atomicAdd(&hist[min(sad[i].x >> 8, 511)], 1);
+    __syncthreads();
+    if (tid == 0) {
+      int acc = 0, b = 0;
+      for (; b < 512; b++) { if (acc + hist[b] > kth) break; acc += hist[b]; }
+      s_scan[0] = b;          // bin of the median
+      s_scan[1] = kth - acc;  // rank inside the bin
     }
-    if (less <= kth && kth < leq) s_median = (float)v;
+    __syncthreads();
+    const int bin = s_scan[0], rank = s_scan[1];
+    for (int i = tid; i < 256; i += kStereoThreads) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kStereoThreads) {
+      const int v = sad[i].x;
+      if (min(v >> 8, 511) == bin) atomicAdd(&hist[v & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int acc = 0, b = 0;
+      for (; b < 256; b++) { if (acc + hist[b] > rank) break; acc += hist[b]; }
+      s_median = (float)((bin << 8) | b);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), s_median);
   for (int i = tid; i < n; i += kStereoThreads) {
     if (!((float)sad[i].x < thDist)) {
@@ -1648,12 +1706,18 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
 // (frames 2p = left, 2p+1 = right; the chunk's pyramids are still in the workspace).
 int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, const int* d_counts, const u8* d_desc, float mbf,
                float mb, float* d_uRight, float* d_depth, cudaStream_t s) {
-  const size_t smem = round_up((size_t)cap * (4 + 4 + 8 + 1), (size_t)16);
-  if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints per frame for the stereo kernel's shared memory");
+  // right keypoints (x, row band, octave), SAD list, row index (H+2 ints) and up to 12 index entries
+  // per keypoint (more -> the kernel scans all right keypoints instead of using the index)
+  size_t fixed = (size_t)cap * (4 + 4 + 8 + 1) + (size_t)(e->g.H + 2) * 4 + 64;
+  int entCap = std::max(cap * 12, 1024);   // >= 1024 entries: the median histogram may live there
+  if (fixed + (size_t)entCap * 2 > 100 * 1024) entCap = (int)std::max<long long>(0, (100 * 1024 - (long long)fixed) / 2);
+  const size_t smem = round_up(fixed + (size_t)entCap * 2, (size_t)16);
+  if (smem > 200 * 1024 || (size_t)e->g.H * 4 > (size_t)cap * 8)
+    ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints / rows for the stereo kernel's shared memory");
   if (cap > 65535) ORB_FAIL(ORB_ERR_UNSUPPORTED, "stereo matching supports at most 65535 keypoints per frame");
   ORB_CUDA(cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_stereo<<<B / 2, kStereoThreads, smem, s>>>(e->g, e->d_pyr, e->pyrStride, d_kps, d_desc, d_counts, cap, mbf, mb, e->d_invScale,
-                                                d_uRight, d_depth);
+                                                d_uRight, d_depth, entCap);
   ORB_CUDA(cudaGetLastError());
   e->lastLaunches++;
   return ORB_OK;
