@@ -21,7 +21,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, NFEAT = 1241, 376, 2000          # Examples/Stereo/KITTI00-02.yaml of the reference
+# workload shapes of the reference's shipped configs (Examples/*/*.yaml): name -> (W, H, nFeatures, bf, fx)
+WORKLOADS = {"kitti": (1241, 376, 2000, 386.1448, 718.856),       # Examples/Stereo/KITTI00-02.yaml
+             "euroc": (752, 480, 1200, 47.90639384423901, 435.2046959714599),   # Examples/Stereo/EuRoC.yaml
+             "tum1": (640, 480, 1000, 40.0, 517.306408)}           # Examples/Monocular/TUM1.yaml (RGB-D bf)
+W, H, NFEAT = 1241, 376, 2000          # the headline workload (BASELINE.json configs[1]); --workload overrides
 PAIRS_PER_STEP = 1024                  # stereo pairs per step and GPU (BASELINE.json configs[1])
 UNIQUE_FRAMES = 512                    # unique synthetic frames per rank (241 MB > 126 MB L2), tiled
 MATCH_PAIRS, MATCH_N = 4096, 2000      # BASELINE.json configs[3]
@@ -162,7 +166,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "KITTI-shape 1241x376 eye-frames, ORBextractor(2000,1.2,8,20,7), CPU oracle port of the "
+        "config": {"workload": "%s-shape %dx%d eye-frames, ORBextractor(%d,1.2,8,20,7), CPU oracle port of the " % (args.workload, W, H, NFEAT) +
                                "reference path (reference itself needs OpenCV C++: unbuildable here)",
                    "frames_per_step": sample},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -253,7 +257,7 @@ def run_ours(args, rank, world, local_rank):
     d_st = d_imgs.clone()
     d_st[1::2, :, :-16] = d_imgs[0::2, :, 16:]
     d_st[1::2, :, -16:] = d_imgs[0::2, :, -16:]
-    kitti_bf, kitti_fx = 386.1448, 718.856                      # Examples/Stereo/KITTI00-02.yaml
+    kitti_bf, kitti_fx = WORKLOADS[args.workload][3], WORKLOADS[args.workload][4]
     s_steps = max(1, min(args.steps, args.e2e_steps))
     ext.extract_stereo_batch_device(d_st, d_kps, d_desc, d_counts, d_ur, d_dp, kitti_bf, kitti_bf / kitti_fx, stream=stream)
     ext.synchronize(stream)
@@ -397,7 +401,7 @@ def run_ours(args, rank, world, local_rank):
         O.match_batch_mt(dsc[: 2 * min(pairs, uniq)], ang[: 2 * min(pairs, uniq)], 0.9, nthreads=cores)
         dtm = time.perf_counter() - t1
         cpu = {"value": sample / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": "%d KITTI-shape frames, one frame per thread, CPU oracle (reference needs OpenCV C++: unbuildable here)" % sample,
+               "sample": "%d %s-shape frames, one frame per thread, CPU oracle (reference needs OpenCV C++: unbuildable here)" % (sample, args.workload),
                "matching_cmp_per_s": min(pairs, uniq) * MATCH_N * MATCH_N / dtm}
 
     popc_peak_cmp = pipes["popc"] / 8.0
@@ -405,10 +409,10 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "KITTI-shape 1241x376 stereo pairs, ORBextractor(2000,1.2,8,20,7) per eye, "
+        "config": {"workload": "%s-shape %dx%d stereo pairs, ORBextractor(%d,1.2,8,20,7) per eye, " % (args.workload, W, H, NFEAT) +
                                "%d pairs (%d eye-frames) per step per GPU" % (args.pairs, frames_per_step),
                    "frames_per_step_per_gpu": frames_per_step, "unique_frames": UNIQUE_FRAMES, "chunk_frames": args.chunk,
-                   "l2": "inputs larger than L2 (%d MB per step; unique pool 241 MB)" % (frames_per_step * W * H // 1000000), "parallelism": "frames sharded, no collective"},
+                   "l2": "inputs larger than L2 (%d MB per step; unique pool %d MB)" % (frames_per_step * W * H // 1000000, UNIQUE_FRAMES * W * H // 1000000), "parallelism": "frames sharded, no collective"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "orb_extract_batch_host (pinned host buffers)"},
         "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + m_steps + (2 * world if allpairs else 0),
@@ -450,12 +454,17 @@ def main():
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("ORB_CHUNK", "256")), help="frames per internal chunk")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--match-steps", type=int, default=3)
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS), help="frame shape / feature count (default: the headline KITTI shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP, help="stereo pairs per step per GPU (profiling runs shrink this)")
     ap.add_argument("--match-pairs", type=int, default=MATCH_PAIRS)
     ap.add_argument("--allpairs-kf", type=int, default=512, help="keyframes of the all-pairs workload (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global W, H, NFEAT, METRIC
+    W, H, NFEAT = WORKLOADS[args.workload][:3]
+    if args.workload != "kitti":
+        METRIC = "ORB-extract frames/s @%dx%d %d feats" % (W, H, NFEAT)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
