@@ -277,6 +277,21 @@ def run_ours(args, rank, world, local_rank):
               "what": "orb_extract_stereo_batch_device: extraction of both eyes + ComputeStereoMatches (Frame.cc:831)"}
     del d_st
 
+    # ---- drop-in latency: one frame / one stereo pair per call through the reference-shaped entry
+    # points (what Frame::Frame does: H2D, all kernels, D2H, synchronise), host wall clock
+    lat = {}
+    one = pool[0]; two = pool[1]
+    for name, fn in (("orb_extract_ms", lambda: ext(one)),
+                     ("orb_extract_with_pyramid_ms", lambda: ext(one, want_pyramid=True)),
+                     ("orb_extract_stereo_ms", lambda: ext.extract_stereo(one, two, kitti_bf, kitti_bf / kitti_fx))):
+        for _ in range(5):
+            fn()
+        ts_ = []
+        for _ in range(30):
+            t0 = time.perf_counter(); fn(); ts_.append(time.perf_counter() - t0)
+        ts_.sort()
+        lat[name] = {"median": 1e3 * ts_[len(ts_) // 2], "p90": 1e3 * ts_[int(len(ts_) * 0.9)]}
+
     # ---- end to end through the host entry point of the C ABI (pinned buffers) -----------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h_imgs = torch.empty((frames_per_step, H, W), dtype=torch.uint8, pin_memory=True)
@@ -417,6 +432,7 @@ def run_ours(args, rank, world, local_rank):
                 "api": "orb_extract_batch_host (pinned host buffers)"},
         "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + m_steps + (2 * world if allpairs else 0),
         "stereo": stereo,
+        "latency": lat,
         "clocks": clocks,
         "roofline": roofline,
         "path_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": total_b, "achieved": path_gbs, "peak": peak, "unit": "GB/s",
