@@ -130,6 +130,11 @@ int orb_last_launch_count(const orb_extractor* h);
  * returns the milliseconds and launch counts accumulated since the previous call for the 5
  * stages {pyramid, fast, quadtree, blur, describe} and resets them. */
 int orb_set_profiling(orb_extractor* h, int enable);
+
+/* Number of workspace lanes (1 or 2, default 2): with 2, consecutive chunks of a batch call run on
+ * two internal streams so that latency-bound kernels of one chunk overlap issue-bound kernels of
+ * the other. Results are identical; per-stage timings are only meaningful with 1 lane. */
+int orb_set_lanes(orb_extractor* h, int lanes);
 int orb_get_stage_times(orb_extractor* h, double* ms5, long long* launches5);
 
 /* Stage outputs of the last call, for parity tests (frame index inside the last chunk).

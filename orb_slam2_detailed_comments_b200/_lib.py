@@ -43,7 +43,7 @@ EXPORTS = [
     "orb_last_error", "orb_device_count", "orb_create", "orb_destroy", "orb_get_scale_tables",
     "orb_max_keypoints", "orb_extract", "orb_extract_batch_host", "orb_extract_batch_device",
     "orb_extract_stereo", "orb_extract_stereo_batch_device",
-    "orb_synchronize", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_times", "orb_stage_level_size", "orb_stage_copy_level",
+    "orb_synchronize", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_times", "orb_set_lanes", "orb_stage_level_size", "orb_stage_copy_level",
     "orb_stage_copy_blur", "orb_stage_copy_candidates", "orb_stage_copy_kept",
     "orb_descriptor_distance", "orb_matcher_create", "orb_matcher_destroy",
     "orb_search_for_initialization", "orb_match_pairs_device", "orb_match_allpairs_device",
@@ -81,6 +81,7 @@ def lib():
         L.orb_synchronize.argtypes = [vp, vp]
         L.orb_last_launch_count.argtypes = [vp]
         L.orb_set_profiling.argtypes = [vp, i32]
+        L.orb_set_lanes.argtypes = [vp, i32]
         L.orb_get_stage_times.argtypes = [vp, vp, vp]
         L.orb_stage_level_size.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
         L.orb_stage_copy_level.argtypes = [vp, i32, i32, vp]

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -1437,6 +1438,11 @@ struct orb_extractor {
   uint2* d_kept = nullptr; int* d_keptCount = nullptr; int2* d_taps = nullptr;
   signed char* d_pattern = nullptr; int* d_overflow = nullptr; int* d_work = nullptr;
   int wsFrames = 0;
+  // two workspace lanes: consecutive chunks run on two streams so that the latency-bound kernels of
+  // one chunk (quadtree, describe, stereo) overlap the issue-bound kernels of the other
+  int lanes = 2, lastLane = 0;
+  cudaStream_t laneStream[2] = {nullptr, nullptr};
+  cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
   // staging for the host entry points: two sets, so that the H2D copy of chunk i+1 and the D2H
   // copy of chunk i-1 overlap the kernels of chunk i (copy streams + events)
   u8* d_in[2] = {nullptr, nullptr}; size_t d_inBytes = 0;
@@ -1588,6 +1594,24 @@ int build_geom(orb_extractor* e, int W, int H) {
   return ORB_OK;
 }
 
+struct Lane {   // the workspace slice of one lane
+  u8* pyr; u8* blur; uint2* cand; int* candCount; unsigned short* keyNode; uint2* kept; int* keptCount; int* work;
+};
+
+Lane lane_of(const orb_extractor* e, int lane) {
+  const size_t F = (size_t)e->wsFrames * lane;
+  Lane L;
+  L.pyr = e->d_pyr + F * e->pyrStride;
+  L.blur = e->d_blur + F * e->blurStride;
+  L.cand = e->d_cand + F * e->candTotal;
+  L.candCount = e->d_candCount + F * kMaxLevels;
+  L.keyNode = e->d_keyNode + F * e->candTotal;
+  L.kept = e->d_kept + F * e->keptTotal;
+  L.keptCount = e->d_keptCount + F * kMaxLevels;
+  L.work = e->d_work + lane;
+  return L;
+}
+
 void free_workspace(orb_extractor* e) {
   cudaFree(e->d_pyr); cudaFree(e->d_blur); cudaFree(e->d_cand); cudaFree(e->d_candCount);
   cudaFree(e->d_keyNode); cudaFree(e->d_kept); cudaFree(e->d_keptCount); cudaFree(e->d_taps);
@@ -1603,7 +1627,7 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
     e->haveGeom = false;
     int st = build_geom(e, W, H);
     if (st) return st;
-    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    ORB_CUDA(cudaDeviceSynchronize());
     free_workspace(e);
     ORB_CUDA(cudaMalloc(&e->d_taps, std::max<size_t>(1, e->taps.size()) * sizeof(int2)));
     ORB_CUDA(cudaMemcpy(e->d_taps, e->taps.data(), e->taps.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -1621,11 +1645,11 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
   }
   frames = std::min(frames, e->maxBatch);
   if (frames > e->wsFrames) {
-    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    ORB_CUDA(cudaDeviceSynchronize());
     int2* keepTaps = e->d_taps; e->d_taps = nullptr;
     free_workspace(e);
     e->d_taps = keepTaps;
-    const size_t F = (size_t)frames;
+    const size_t F = (size_t)frames * e->lanes;
     ORB_CUDA(cudaMalloc(&e->d_pyr, F * e->pyrStride));
     ORB_CUDA(cudaMalloc(&e->d_blur, F * e->blurStride));
     ORB_CUDA(cudaMalloc(&e->d_cand, F * e->candTotal * sizeof(uint2)));
@@ -1651,45 +1675,47 @@ int stage_mark(orb_extractor* e, cudaStream_t s) {
 
 // One chunk (<= wsFrames frames) through the whole pipeline, asynchronous on `s`.
 int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t frameStride, orb_keypoint* d_kps,
-              int cap, int* d_counts, u8* d_desc, cudaStream_t s) {
+              int cap, int* d_counts, u8* d_desc, cudaStream_t s, int lane = 0) {
   const Geom& g = e->g;
+  const Lane W = lane_of(e, lane);
+  e->lastLane = lane;
   const int nl = g.nlevels;
   int launches = 0, st;
   if ((st = stage_mark(e, s))) return st;
   {
     const LevelGeom& L = g.lv[0];
     dim3 grid((L.pitch / 16 + 31) / 32, (L.h + 2 * kEdge + 7) / 8, B);
-    k_level0_border<<<grid, dim3(32, 8), 0, s>>>(g, d_img, step, frameStride, e->d_pyr, e->pyrStride);
+    k_level0_border<<<grid, dim3(32, 8), 0, s>>>(g, d_img, step, frameStride, W.pyr, e->pyrStride);
     launches++;
   }
   for (int l = 1; l < nl; l++) {
     const LevelGeom& L = g.lv[l];
     dim3 grid((L.pitch / 4 + 31) / 32, (L.h + 2 * kEdge + 31) / 32, B);
-    k_resize_border<<<grid, dim3(32, 8), 0, s>>>(g, l, e->d_pyr, e->pyrStride, e->d_taps);
+    k_resize_border<<<grid, dim3(32, 8), 0, s>>>(g, l, W.pyr, e->pyrStride, e->d_taps);
     launches++;
   }
-  ORB_CUDA(cudaMemsetAsync(e->d_candCount, 0, (size_t)B * nl * sizeof(int), s));
-  ORB_CUDA(cudaMemsetAsync(e->d_work, 0, sizeof(int), s));
+  ORB_CUDA(cudaMemsetAsync(W.candCount, 0, (size_t)B * nl * sizeof(int), s));
+  ORB_CUDA(cudaMemsetAsync(W.work, 0, sizeof(int), s));
   if ((st = stage_mark(e, s))) return st;
   {
     const int nItems = g.totalCells * B;
     const int blocks = std::min(e->fastBlocks, (nItems + kFastWarps - 1) / kFastWarps);
-    k_fast_cells<<<blocks, kFastThreads, e->fastSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_cand, e->d_candCount,
-                                                          e->candTotal, nItems, e->fastLay, e->d_work);
+    k_fast_cells<<<blocks, kFastThreads, e->fastSmem, s>>>(g, W.pyr, e->pyrStride, W.cand, W.candCount,
+                                                          e->candTotal, nItems, e->fastLay, W.work);
   }
   launches++;
   if ((st = stage_mark(e, s))) return st;
-  k_quadtree<<<dim3(nl, B), kQtThreads, e->qtSmem, s>>>(g, e->d_cand, e->d_candCount, e->d_keyNode, e->d_kept,
-                                                       e->d_keptCount, e->candTotal, e->keptTotal, e->nodeCap,
+  k_quadtree<<<dim3(nl, B), kQtThreads, e->qtSmem, s>>>(g, W.cand, W.candCount, W.keyNode, W.kept,
+                                                       W.keptCount, e->candTotal, e->keptTotal, e->nodeCap,
                                                        e->d_overflow);
   launches++;
   if ((st = stage_mark(e, s))) return st;
-  k_blur7<<<dim3(g.totalBlurTiles, B), 256, 0, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride);
+  k_blur7<<<dim3(g.totalBlurTiles, B), 256, 0, s>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride);
   launches++;
   if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);
-  k_describe<<<dim3((slots + kDescSlots - 1) / kDescSlots, B), 256, kDescSmem, s>>>(g, e->d_pyr, e->pyrStride, e->d_blur, e->blurStride,
-                                                              e->d_kept, e->d_keptCount, e->keptTotal, e->d_pattern,
+  k_describe<<<dim3((slots + kDescSlots - 1) / kDescSlots, B), 256, kDescSmem, s>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride,
+                                                              W.kept, W.keptCount, e->keptTotal, e->d_pattern,
                                                               d_kps, d_desc, d_counts, cap, e->d_overflow);
   launches++;
   if ((st = stage_mark(e, s))) return st;
@@ -1705,7 +1731,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
 // Frame::ComputeStereoMatches for the B/2 stereo pairs of the chunk that was just extracted
 // (frames 2p = left, 2p+1 = right; the chunk's pyramids are still in the workspace).
 int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, const int* d_counts, const u8* d_desc, float mbf,
-               float mb, float* d_uRight, float* d_depth, cudaStream_t s) {
+               float mb, float* d_uRight, float* d_depth, cudaStream_t s, int lane = 0) {
   // right keypoints (x, row band, octave), SAD list, row index (H+2 ints) and up to 12 index entries
   // per keypoint (more -> the kernel scans all right keypoints instead of using the index)
   size_t fixed = (size_t)cap * (4 + 4 + 8 + 1) + (size_t)(e->g.H + 2) * 4 + 64;
@@ -1716,10 +1742,27 @@ int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, cons
     ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints / rows for the stereo kernel's shared memory");
   if (cap > 65535) ORB_FAIL(ORB_ERR_UNSUPPORTED, "stereo matching supports at most 65535 keypoints per frame");
   ORB_CUDA(cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_stereo<<<B / 2, kStereoThreads, smem, s>>>(e->g, e->d_pyr, e->pyrStride, d_kps, d_desc, d_counts, cap, mbf, mb, e->d_invScale,
+  k_stereo<<<B / 2, kStereoThreads, smem, s>>>(e->g, lane_of(e, lane).pyr, e->pyrStride, d_kps, d_desc, d_counts, cap, mbf, mb, e->d_invScale,
                                                 d_uRight, d_depth, entCap);
   ORB_CUDA(cudaGetLastError());
   e->lastLaunches++;
+  return ORB_OK;
+}
+
+// Fork the caller's stream into the lane streams / join them back (used when a call spans
+// several chunks; a single chunk runs directly on the caller's stream).
+int lanes_fork(orb_extractor* e, cudaStream_t s, int nChunks) {
+  if (e->lanes < 2 || nChunks < 2) return ORB_OK;
+  ORB_CUDA(cudaEventRecord(e->evFork, s));
+  for (int l = 0; l < 2; l++) ORB_CUDA(cudaStreamWaitEvent(e->laneStream[l], e->evFork, 0));
+  return ORB_OK;
+}
+int lanes_join(orb_extractor* e, cudaStream_t s, int nChunks) {
+  if (e->lanes < 2 || nChunks < 2) return ORB_OK;
+  for (int l = 0; l < 2; l++) {
+    ORB_CUDA(cudaEventRecord(e->evJoin[l], e->laneStream[l]));
+    ORB_CUDA(cudaStreamWaitEvent(s, e->evJoin[l], 0));
+  }
   return ORB_OK;
 }
 
@@ -1792,11 +1835,17 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
   e->device = device;
   e->maxBatch = std::max(1, max_batch);
   build_tables(e);
+  if (const char* ev = getenv("ORB_B200_LANES")) e->lanes = atoi(ev) >= 2 ? 2 : 1;
   cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  for (int l = 0; l < 2 && err == cudaSuccess; l++) {
+    err = cudaStreamCreateWithFlags(&e->laneStream[l], cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evJoin[l], cudaEventDisableTiming);
+  }
+  if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_pattern, sizeof ORB_BIT_PATTERN_31);
   if (err == cudaSuccess) err = cudaMemcpy(e->d_pattern, ORB_BIT_PATTERN_31, sizeof ORB_BIT_PATTERN_31, cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_overflow, sizeof(int));
-  if (err == cudaSuccess) err = cudaMalloc(&e->d_work, sizeof(int));
+  if (err == cudaSuccess) err = cudaMalloc(&e->d_work, 2 * sizeof(int));
   if (err == cudaSuccess) err = cudaMalloc(&e->d_invScale, kMaxLevels * sizeof(float));
   if (err == cudaSuccess) err = cudaMemcpy(e->d_invScale, e->invScale.data(), e->invScale.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMemset(e->d_overflow, 0, sizeof(int));
@@ -1824,6 +1873,11 @@ int orb_destroy(orb_extractor* e) {
   if (e->sIn) cudaStreamDestroy(e->sIn);
   if (e->sOut) cudaStreamDestroy(e->sOut);
   for (cudaEvent_t ev : e->evPool) cudaEventDestroy(ev);
+  for (int l = 0; l < 2; l++) {
+    if (e->laneStream[l]) cudaStreamDestroy(e->laneStream[l]);
+    if (e->evJoin[l]) cudaEventDestroy(e->evJoin[l]);
+  }
+  if (e->evFork) cudaEventDestroy(e->evFork);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return ORB_OK;
@@ -1859,13 +1913,18 @@ int orb_extract_batch_device(orb_extractor* e, const uint8_t* d_images, int batc
   if (st) return st;
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   e->lastLaunches = 0;
-  for (int b0 = 0; b0 < batch; b0 += e->wsFrames) {
+  const int nChunks = (batch + e->wsFrames - 1) / e->wsFrames;
+  const bool multi = e->lanes >= 2 && nChunks >= 2;
+  if ((st = lanes_fork(e, s, nChunks))) return st;
+  int ci = 0;
+  for (int b0 = 0; b0 < batch; b0 += e->wsFrames, ci++) {
     const int B = std::min(e->wsFrames, batch - b0);
+    const int lane = multi ? (ci & 1) : 0;
     st = run_chunk(e, d_images + (size_t)b0 * frame_stride, B, step, frame_stride, d_keypoints + (size_t)b0 * capacity,
-                   capacity, d_counts + b0, d_descriptors + (size_t)b0 * capacity * 32, s);
+                   capacity, d_counts + b0, d_descriptors + (size_t)b0 * capacity * 32, multi ? e->laneStream[lane] : s, lane);
     if (st) return st;
   }
-  return ORB_OK;
+  return lanes_join(e, s, nChunks);
 }
 
 int orb_synchronize(orb_extractor* e, void* stream) {
@@ -1875,6 +1934,20 @@ int orb_synchronize(orb_extractor* e, void* stream) {
 }
 
 int orb_last_launch_count(const orb_extractor* e) { return e ? e->lastLaunches : 0; }
+
+int orb_set_lanes(orb_extractor* e, int lanes) {
+  if (!e || lanes < 1 || lanes > 2) ORB_FAIL(ORB_ERR_INVALID, "lanes must be 1 or 2");
+  ORB_CUDA(cudaSetDevice(e->device));
+  ORB_CUDA(cudaDeviceSynchronize());
+  if (lanes != e->lanes) {
+    // the workspace is sized per lane count: drop it, it is re-allocated by the next call
+    int2* keepTaps = e->d_taps; e->d_taps = nullptr;
+    free_workspace(e);
+    e->d_taps = keepTaps;
+    e->lanes = lanes;
+  }
+  return ORB_OK;
+}
 
 int orb_set_profiling(orb_extractor* e, int enable) {
   if (!e) ORB_FAIL(ORB_ERR_INVALID, "null handle");
@@ -1929,12 +2002,15 @@ int orb_extract_batch_host(orb_extractor* e, const uint8_t* images, int batch, i
                                    width, height, cudaMemcpyHostToDevice, e->sIn));
     }
     ORB_CUDA(cudaEventRecord(e->evIn[b], e->sIn));
-    // kernels: wait for the input, and for the D2H of chunk ci-2 that still reads the output buffers
-    ORB_CUDA(cudaStreamWaitEvent(s, e->evIn[b], 0));
-    if (ci >= 2) ORB_CUDA(cudaStreamWaitEvent(s, e->evOut[b], 0));
-    st = run_chunk(e, e->d_in[b], B, width, dFrame, e->d_kps[b], capacity, e->d_n[b], e->d_desc[b], s);
+    // kernels (lane b of the workspace, on its own stream): wait for the input, and for the D2H of
+    // chunk ci-2 that still reads the output buffers
+    cudaStream_t cs = e->lanes >= 2 ? e->laneStream[b] : s;
+    const int lane = e->lanes >= 2 ? b : 0;
+    ORB_CUDA(cudaStreamWaitEvent(cs, e->evIn[b], 0));
+    if (ci >= 2) ORB_CUDA(cudaStreamWaitEvent(cs, e->evOut[b], 0));
+    st = run_chunk(e, e->d_in[b], B, width, dFrame, e->d_kps[b], capacity, e->d_n[b], e->d_desc[b], cs, lane);
     if (st) return st;
-    ORB_CUDA(cudaEventRecord(e->evDone[b], s));
+    ORB_CUDA(cudaEventRecord(e->evDone[b], cs));
     // D2H on its own stream
     ORB_CUDA(cudaStreamWaitEvent(e->sOut, e->evDone[b], 0));
     ORB_CUDA(cudaMemcpyAsync(counts + b0, e->d_n[b], (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, e->sOut));
@@ -1945,6 +2021,7 @@ int orb_extract_batch_host(orb_extractor* e, const uint8_t* images, int batch, i
     ORB_CUDA(cudaEventRecord(e->evOut[b], e->sOut));
   }
   ORB_CUDA(cudaStreamSynchronize(e->sOut));
+  for (int l = 0; l < 2; l++) ORB_CUDA(cudaStreamSynchronize(e->laneStream[l]));
   return check_overflow(e, s);
 }
 
@@ -2001,17 +2078,23 @@ int orb_extract_stereo_batch_device(orb_extractor* e, const uint8_t* d_images, i
   const int chunk = std::max(2, e->wsFrames & ~1);
   if (chunk > e->wsFrames) ORB_FAIL(ORB_ERR_INVALID, "max_batch must be >= 2 for stereo");
   const int batch = 2 * pairs;
-  for (int b0 = 0; b0 < batch; b0 += chunk) {
+  const int nChunks = (batch + chunk - 1) / chunk;
+  const bool multi = e->lanes >= 2 && nChunks >= 2;
+  if ((st = lanes_fork(e, s, nChunks))) return st;
+  int ci = 0;
+  for (int b0 = 0; b0 < batch; b0 += chunk, ci++) {
     const int B = std::min(chunk, batch - b0);
+    const int lane = multi ? (ci & 1) : 0;
+    cudaStream_t ls = multi ? e->laneStream[lane] : s;
     st = run_chunk(e, d_images + (size_t)b0 * frame_stride, B, step, frame_stride, d_keypoints + (size_t)b0 * capacity,
-                   capacity, d_counts + b0, d_descriptors + (size_t)b0 * capacity * 32, s);
+                   capacity, d_counts + b0, d_descriptors + (size_t)b0 * capacity * 32, ls, lane);
     if (st) return st;
     st = run_stereo(e, B, d_keypoints + (size_t)b0 * capacity, capacity, d_counts + b0,
                     d_descriptors + (size_t)b0 * capacity * 32, mbf, mb, d_uright + (size_t)(b0 / 2) * capacity,
-                    d_depth + (size_t)(b0 / 2) * capacity, s);
+                    d_depth + (size_t)(b0 / 2) * capacity, ls, lane);
     if (st) return st;
   }
-  return ORB_OK;
+  return lanes_join(e, s, nChunks);
 }
 
 int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* right, int width, int height, size_t step,
@@ -2083,7 +2166,7 @@ int orb_stage_copy_level(orb_extractor* e, int frame, int level, uint8_t* dst) {
   ORB_CUDA(cudaSetDevice(e->device));
   ORB_CUDA(cudaDeviceSynchronize());
   const LevelGeom& L = e->g.lv[level];
-  const u8* src = e->d_pyr + (size_t)frame * e->pyrStride + L.off - (long long)kEdge * L.pitch - kEdge;
+  const u8* src = lane_of(e, e->lastLane).pyr + (size_t)frame * e->pyrStride + L.off - (long long)kEdge * L.pitch - kEdge;
   ORB_CUDA(cudaMemcpy2D(dst, L.w + 2 * kEdge, src, L.pitch, L.w + 2 * kEdge, L.h + 2 * kEdge, cudaMemcpyDeviceToHost));
   return ORB_OK;
 }
@@ -2094,7 +2177,7 @@ int orb_stage_copy_blur(orb_extractor* e, int frame, int level, uint8_t* dst) {
   ORB_CUDA(cudaSetDevice(e->device));
   ORB_CUDA(cudaDeviceSynchronize());
   const LevelGeom& L = e->g.lv[level];
-  ORB_CUDA(cudaMemcpy2D(dst, L.w, e->d_blur + (size_t)frame * e->blurStride + L.boff, L.bpitch, L.w, L.h,
+  ORB_CUDA(cudaMemcpy2D(dst, L.w, lane_of(e, e->lastLane).blur + (size_t)frame * e->blurStride + L.boff, L.bpitch, L.w, L.h,
                         cudaMemcpyDeviceToHost));
   return ORB_OK;
 }
@@ -2120,10 +2203,10 @@ int orb_stage_copy_candidates(orb_extractor* e, int frame, int level, int32_t* x
   ORB_CUDA(cudaSetDevice(e->device));
   ORB_CUDA(cudaDeviceSynchronize());
   int cnt = 0;
-  ORB_CUDA(cudaMemcpy(&cnt, e->d_candCount + frame * e->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  ORB_CUDA(cudaMemcpy(&cnt, lane_of(e, e->lastLane).candCount + frame * e->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
   cnt = std::min(cnt, e->g.lv[level].candCap);
   *n = cnt;
-  return copy_list(e, e->d_cand + (size_t)frame * e->candTotal + e->g.lv[level].candOff, cnt, xs, ys, score, capacity);
+  return copy_list(e, lane_of(e, e->lastLane).cand + (size_t)frame * e->candTotal + e->g.lv[level].candOff, cnt, xs, ys, score, capacity);
 }
 
 int orb_stage_copy_kept(orb_extractor* e, int frame, int level, int32_t* xs, int32_t* ys, int32_t* score, int capacity,
@@ -2133,9 +2216,9 @@ int orb_stage_copy_kept(orb_extractor* e, int frame, int level, int32_t* xs, int
   ORB_CUDA(cudaSetDevice(e->device));
   ORB_CUDA(cudaDeviceSynchronize());
   int cnt = 0;
-  ORB_CUDA(cudaMemcpy(&cnt, e->d_keptCount + frame * e->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  ORB_CUDA(cudaMemcpy(&cnt, lane_of(e, e->lastLane).keptCount + frame * e->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
   *n = cnt;
-  return copy_list(e, e->d_kept + (size_t)frame * e->keptTotal + e->g.lv[level].keptOff, cnt, xs, ys, score, capacity);
+  return copy_list(e, lane_of(e, e->lastLane).kept + (size_t)frame * e->keptTotal + e->g.lv[level].keptOff, cnt, xs, ys, score, capacity);
 }
 
 }  // extern "C"

@@ -134,6 +134,9 @@ class ORBextractor:
 
     STAGES = ("pyramid", "fast", "quadtree", "blur", "describe")
 
+    def set_lanes(self, lanes):
+        check(self._L.orb_set_lanes(self._h, int(lanes)))
+
     def set_profiling(self, enable):
         check(self._L.orb_set_profiling(self._h, int(bool(enable))))
 
