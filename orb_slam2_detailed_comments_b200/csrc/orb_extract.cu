@@ -8,13 +8,16 @@
 //   candidates   : per level a uint2 list {x | y<<16, score} (unordered; order is recovered
 //                  from (x,y) because the reference's candidate order is a function of position)
 //   kept         : per level a uint2 list in the reference's final list order
-// Kernels (one launch each over the whole chunk):
+// Kernels (one launch each over a whole chunk of frames):
 //   k_level0_border, k_resize_border (x nlevels-1)  ComputePyramid      :1655-1724
 //   k_fast_cells                                    ComputeKeyPointsOctTree + cv::FAST :1037-1142
 //   k_quadtree                                      DistributeOctTree   :688-1033
 //   k_blur7                                         cv::GaussianBlur    :1607-1615
 //   k_describe                                      IC_Angle :94-141, computeOrbDescriptor :153-204,
 //                                                   level->image scaling :1633-1642
+//   k_stereo (stereo entry points only)             Frame::ComputeStereoMatches, src/Frame.cc:831-1082
+// A batch call cuts the batch into chunks of max_batch frames; consecutive chunks alternate between
+// two workspace lanes / streams so that kernels of neighbouring chunks overlap.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -342,7 +345,7 @@ constexpr int kFastThreads = 32 * kFastWarps;
 constexpr int kFastRun = 16;   // consecutive cells a warp grabs per atomic
 
 struct FastSmemLayout {   // per-warp shared memory carve-up (in bytes), sized for the largest cell
-  int rawPitchWords, rawBytes, tileBytes, queueBytes, hitsBytes, scBytes, total;
+  int rawPitchWords, rawBytes, tileBytes, hitsBytes, scBytes, total;
 };
 
 struct CellDesc {
@@ -1582,10 +1585,9 @@ int build_geom(orb_extractor* e, int W, int H) {
     y.rawPitchWords = (3 + maxCw + 6 + 3) / 4;
     y.rawBytes = round_up(y.rawPitchWords * 4 * (maxCh + 6), 16);
     y.tileBytes = round_up(4 * (S + 6) * (maxCh + 6), 16);
-    y.queueBytes = 0;
     y.hitsBytes = round_up(2 * (2 * S * maxCh), 16);   // hits + queue share it (see k_fast_cells)
     y.scBytes = round_up((maxCw + 2) * (maxCh + 2) + 4, 16);
-    y.total = y.rawBytes + y.tileBytes + y.queueBytes + y.hitsBytes + y.scBytes;
+    y.total = y.rawBytes + y.tileBytes + y.hitsBytes + y.scBytes;
     e->fastSmem = (size_t)y.total * kFastWarps;
   }
   e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8);

@@ -189,3 +189,21 @@ def test_idempotent_and_deterministic(oracle):
     for b in range(8):
         assert counts[b] == len(k1)
         assert kps[b, :counts[b]].tobytes() == k1.tobytes() and desc[b, :counts[b]].tobytes() == d1.tobytes()
+
+
+def test_lanes_do_not_change_results(oracle):
+    """Two workspace lanes (chunks overlapping on two streams) and one lane give byte-identical
+    outputs, and both match the oracle's keypoint counts."""
+    from orb_slam2_detailed_comments_b200.synth import synth_batch
+    w, h, nfeat = CONFIGS["tum1"]
+    gpu, orc = _extractors(oracle, nfeat, max_batch=2)    # 7 frames -> 4 chunks alternating between lanes
+    imgs = synth_batch(w, h, 7, seed0=500)
+    gpu.set_lanes(2)
+    k2, d2, c2 = gpu.extract_batch_host(imgs)
+    gpu.set_lanes(1)
+    k1, d1, c1 = gpu.extract_batch_host(imgs)
+    assert np.array_equal(c1, c2)
+    for b in range(len(imgs)):
+        n = c1[b]
+        assert k1[b, :n].tobytes() == k2[b, :n].tobytes() and d1[b, :n].tobytes() == d2[b, :n].tobytes()
+        assert n == len(orc(imgs[b])[0])
