@@ -340,7 +340,7 @@ __device__ __forceinline__ unsigned fast_exact(const FastDiffs& D) {
 // (dense, no divergence) -> 3x3 NMS on the hit list -> iniTh / minTh decision -> one atomicAdd
 // per cell reserves the output range. Only __syncwarp() is needed: warps run out of phase and
 // hide each other's latencies.
-constexpr int kFastWarps = 4;
+constexpr int kFastWarps = 11;  // upper bound; the host picks the warps per CTA that pack an SM's shared memory best
 constexpr int kFastThreads = 32 * kFastWarps;
 constexpr int kFastRun = 16;   // consecutive cells a warp grabs per atomic
 
@@ -1432,7 +1432,7 @@ struct orb_extractor {
   int candTotal = 0, keptTotal = 0, nodeCap = 0, maxKp = 0;
   size_t fastSmem = 0, qtSmem = 0;
   FastSmemLayout fastLay;
-  int fastBlocks = 0;
+  int fastBlocks = 0, fastWarps = 4;
   std::vector<int2> taps;
 
   // device workspace (sized for maxBatch frames of the current geometry)
@@ -1588,7 +1588,16 @@ int build_geom(orb_extractor* e, int W, int H) {
     y.hitsBytes = round_up(2 * (2 * S * maxCh), 16);   // hits + queue share it (see k_fast_cells)
     y.scBytes = round_up((maxCw + 2) * (maxCh + 2) + 4, 16);
     y.total = y.rawBytes + y.tileBytes + y.hitsBytes + y.scBytes;
-    e->fastSmem = (size_t)y.total * kFastWarps;
+    // warps per CTA: maximise resident warps per SM under 227 KB (1 KB reserved per CTA)
+    int bestW = 1, bestResident = 0;
+    for (int w = 1; w <= kFastWarps; w++) {
+      const long long perCta = (long long)y.total * w + 1024;
+      const int resident = (int)std::min<long long>(32, (227 * 1024) / perCta) * w;
+      if (perCta <= 200 * 1024 && resident > bestResident) { bestResident = resident; bestW = w; }
+    }
+    if (bestResident == 0) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
+    e->fastWarps = bestW;
+    e->fastSmem = (size_t)y.total * bestW;
   }
   e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8);
   if (e->qtSmem > 220 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "features per level too large for the quadtree kernel's shared memory");
@@ -1638,7 +1647,7 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
     ORB_CUDA(cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescSmem));
     {
       int perSM = 0, dev = 0, sms = 0;
-      ORB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_fast_cells, kFastThreads, e->fastSmem));
+      ORB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_fast_cells, 32 * e->fastWarps, e->fastSmem));
       ORB_CUDA(cudaGetDevice(&dev));
       ORB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       e->fastBlocks = std::max(1, perSM) * std::max(1, sms);
@@ -1701,8 +1710,8 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   if ((st = stage_mark(e, s))) return st;
   {
     const int nItems = g.totalCells * B;
-    const int blocks = std::min(e->fastBlocks, (nItems + kFastWarps - 1) / kFastWarps);
-    k_fast_cells<<<blocks, kFastThreads, e->fastSmem, s>>>(g, W.pyr, e->pyrStride, W.cand, W.candCount,
+    const int blocks = std::min(e->fastBlocks, (nItems + e->fastWarps - 1) / e->fastWarps);
+    k_fast_cells<<<blocks, 32 * e->fastWarps, e->fastSmem, s>>>(g, W.pyr, e->pyrStride, W.cand, W.candCount,
                                                           e->candTotal, nItems, e->fastLay, W.work);
   }
   launches++;
