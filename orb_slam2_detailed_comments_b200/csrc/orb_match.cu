@@ -252,6 +252,210 @@ __global__ void __launch_bounds__(kMatchThreads) k_match_pairs(const PairArgs A)
 }
 
 // ------------------------------------------------------------------------------------------
+// Brute-force SearchForInitialization, throughput form. The reference's row walk is sequential only
+// through vMatchedDistance (:627) and the steal (:650-654); the distances themselves are not. So:
+//   phase 1  every thread owns RPT rows of frame 1 (descriptors + the two smallest keys in
+//            registers) and streams frame 2's descriptors from shared memory (broadcast loads): no
+//            cross-thread reduction, no barrier in the inner loop. Keys = dist << 16 | index.
+//   phase 2  one thread walks the rows in order. A row's top-2 is still exact if neither candidate
+//            has meanwhile been matched with a distance <= the row's (the reference would skip it).
+//            Otherwise the decision is often still forced (best > TH_LOW: reject; best < ratio *
+//            lower bound of second: accept); only the remaining rows are recomputed exactly against
+//            the current vMatchedDistance by the whole CTA.
+// Results are identical to the sequential algorithm; when the caller asks for the per-row best /
+// second distances every non-exact row is recomputed.
+// ------------------------------------------------------------------------------------------
+constexpr int kBfThreads = 512;
+constexpr int kBfMaxN = 2048;
+
+template <int RPT>
+__global__ void __launch_bounds__(kBfThreads, 2) k_match_pairs_bf(const PairArgs A) {
+  extern __shared__ __align__(16) unsigned char bfsm[];
+  __shared__ unsigned s_red[kBfThreads / 32][2];
+  __shared__ int s_hist[HISTO_LENGTH];
+  __shared__ int s_nmatch, s_row, s_need, s_exact;
+  __shared__ int s_keep[3];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p = blockIdx.x;
+  const int n1 = A.n1, n2 = A.n2;
+  // region 0: frame-2 descriptors (phase 1), then the rows' top-2 keys (phase 2)
+  const size_t region0 = (size_t)(n2 * 32 > n1 * 8 ? n2 * 32 : n1 * 8);
+  uint4* bdesc = reinterpret_cast<uint4*>(bfsm);
+  uint2* keys = reinterpret_cast<uint2*>(bfsm);
+  unsigned short* md = reinterpret_cast<unsigned short*>(bfsm + region0);   // vMatchedDistance (0xffff = INT_MAX)
+  short* m12 = reinterpret_cast<short*>(md + n2);
+  short* m21 = m12 + n1;
+  short* accIdx = m21 + n2;   // frame-2 index a row was matched to when it was accepted (-1: never)
+  u8* binOf = reinterpret_cast<u8*>(accIdx + n1);
+  const u8* D1 = A.desc1 + (size_t)p * A.stride1 * 32;
+  const u8* D2 = A.desc2 + (size_t)p * A.stride2 * 32;
+  const float* ang1 = A.ang1 + (size_t)p * A.stride1;
+  const float* ang2 = A.ang2 + (size_t)p * A.stride2;
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(D2);
+    for (int t = tid; t < n2 * 2; t += kBfThreads) bdesc[t] = __ldg(src + t);
+  }
+  for (int i = tid; i < n2; i += kBfThreads) { md[i] = 0xffffu; m21[i] = -1; }
+  for (int i = tid; i < n1; i += kBfThreads) { m12[i] = -1; accIdx[i] = -1; binOf[i] = 255; }
+  if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) { s_nmatch = 0; s_row = 0; s_need = -1; s_exact = -1; }
+  unsigned a[RPT][8];
+  unsigned k1[RPT], k2[RPT];
+#pragma unroll
+  for (int r = 0; r < RPT; r++) {
+    const int row = tid + r * kBfThreads;
+    k1[r] = kNoKey; k2[r] = kNoKey;
+    if (row < n1) {
+      const uint4* src = reinterpret_cast<const uint4*>(D1 + (size_t)row * 32);
+      const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+      a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = lo.z; a[r][3] = lo.w;
+      a[r][4] = hi.x; a[r][5] = hi.y; a[r][6] = hi.z; a[r][7] = hi.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[r][k] = 0;
+    }
+  }
+  __syncthreads();
+  // ---- phase 1: two smallest keys of every row over all of frame 2
+#pragma unroll 2
+  for (int c = 0; c < n2; c++) {
+    const uint4 lo = bdesc[2 * c], hi = bdesc[2 * c + 1];
+    const unsigned bb[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+      const unsigned x = ((unsigned)hamming8(a[r], bb) << 16) + (unsigned)c;
+      k2[r] = min(k2[r], max(k1[r], x));
+      k1[r] = min(k1[r], x);
+    }
+  }
+  __syncthreads();   // everybody is done with the descriptors: region 0 becomes the key table
+#pragma unroll
+  for (int r = 0; r < RPT; r++) {
+    const int row = tid + r * kBfThreads;
+    if (row < n1) keys[row] = make_uint2(k1[r], k2[r]);
+  }
+  __syncthreads();
+
+  // ---- phase 2: sequential commit (thread 0) with cooperative exact recomputation on demand
+  const float factor = HISTO_LENGTH / 360.0f;  // this fork: ORBmatcher.cc:585-586
+  const bool wantDist = A.best != nullptr;
+  for (;;) {
+    if (tid == 0) {
+      int row = s_row, nmatches = s_nmatch, need = -1;
+      const int exactRow = s_exact;
+      for (; row < n1; row++) {
+        const uint2 kk = keys[row];
+        int best, second, bestIdx;
+        bool decided = false, accept = false;
+        const int d1 = kk.x == kNoKey ? INT_MAX : (int)(kk.x >> 16), c1 = (int)(kk.x & 0xffffu);
+        const int d2 = kk.y == kNoKey ? INT_MAX : (int)(kk.y >> 16), c2 = (int)(kk.y & 0xffffu);
+        best = d1; second = d2; bestIdx = c1;
+        if (row == exactRow) {
+          decided = true;   // computed against the current vMatchedDistance
+        } else {
+          const bool s1 = kk.x != kNoKey && (int)md[c1] <= d1;   // would the reference skip it? (:627)
+          const bool s2 = kk.y != kNoKey && (int)md[c2] <= d2;
+          if (!s1 && !s2) decided = true;
+          else if (!wantDist) {
+            if (!s1) {                       // best stands, second >= d2
+              if (d1 > TH_LOW) { decided = true; best = INT_MAX; }
+              else if ((float)d1 < __fmul_rn((float)d2, A.nnratio)) { decided = true; accept = true; }
+            } else if (!s2) {                // the best is the old runner-up, second >= d2 unknown
+              if (d2 > TH_LOW) { decided = true; best = INT_MAX; }
+            } else {                         // both taken: best >= d2
+              if (d2 > TH_LOW) { decided = true; best = INT_MAX; }
+            }
+          }
+        }
+        if (!decided) { need = row; break; }
+        if (wantDist) {
+          A.best[(size_t)p * n1 + row] = best;
+          A.second[(size_t)p * n1 + row] = second;
+        }
+        if (!accept) accept = best <= TH_LOW && (float)best < __fmul_rn((float)second, A.nnratio);  // :644-647
+        if (accept) {
+          const int prevOwner = m21[bestIdx];
+          if (prevOwner >= 0) { m12[prevOwner] = -1; nmatches--; }  // :650-654
+          m12[row] = (short)bestIdx;
+          m21[bestIdx] = (short)row;
+          md[bestIdx] = (unsigned short)best;
+          nmatches++;
+          accIdx[row] = (short)bestIdx;   // the rotation bin is filled in afterwards, in parallel
+        }
+      }
+      s_row = row; s_nmatch = nmatches; s_need = need;
+    }
+    __syncthreads();
+    const int need = s_need;
+    if (need < 0) break;
+    // exact 2-NN of row `need` against the current vMatchedDistance, by the whole CTA
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(D1 + (size_t)need * 32);
+      const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+      const unsigned ar[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      unsigned q1 = kNoKey, q2 = kNoKey;
+      for (int c = tid; c < n2; c += kBfThreads) {
+        const uint4* bs = reinterpret_cast<const uint4*>(D2 + (size_t)c * 32);
+        const uint4 blo = __ldg(bs), bhi = __ldg(bs + 1);
+        const unsigned bb[8] = {blo.x, blo.y, blo.z, blo.w, bhi.x, bhi.y, bhi.z, bhi.w};
+        const int d = hamming8(ar, bb);
+        if ((int)md[c] > d || md[c] == 0xffffu) merge2(q1, q2, ((unsigned)d << 16) | (unsigned)c, kNoKey);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned o1 = __shfl_xor_sync(0xffffffffu, q1, o), o2 = __shfl_xor_sync(0xffffffffu, q2, o);
+        merge2(q1, q2, o1, o2);
+      }
+      if (lane == 0) { s_red[wid][0] = q1; s_red[wid][1] = q2; }
+      __syncthreads();
+      if (tid == 0) {
+        q1 = kNoKey; q2 = kNoKey;
+        for (int w = 0; w < kBfThreads / 32; w++) merge2(q1, q2, s_red[w][0], s_red[w][1]);
+        keys[need] = make_uint2(q1, q2);
+        s_exact = need;
+      }
+      __syncthreads();
+    }
+  }
+  // rotation histogram (:663-677): every row that was accepted counts, also if it was robbed later
+  if (A.checkOri) {
+    for (int i = tid; i < n1; i += kBfThreads) {
+      const int j = accIdx[i];
+      if (j >= 0) {
+        float rot = __fsub_rn(ang1[i], ang2[j]);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == HISTO_LENGTH) bin = 0;
+        if (bin >= 0 && bin < HISTO_LENGTH) { binOf[i] = (u8)bin; atomicAdd(&s_hist[bin], 1); }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int x = -1, y = -1, z = -1;
+    if (A.checkOri) three_maxima(s_hist, HISTO_LENGTH, x, y, z);
+    s_keep[0] = x; s_keep[1] = y; s_keep[2] = z;
+  }
+  __syncthreads();
+  if (A.checkOri) {
+    int dropped = 0;
+    for (int i = tid; i < n1; i += kBfThreads) {
+      const int bin = binOf[i];
+      if (bin != 255 && bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2] && m12[i] >= 0) {
+        m12[i] = -1;  // :692-706
+        dropped++;
+      }
+    }
+    if (dropped) atomicSub(&s_nmatch, dropped);
+  }
+  __syncthreads();
+  int* out12 = A.matches12 + (size_t)p * n1;
+  for (int i = tid; i < n1; i += kBfThreads) out12[i] = m12[i];
+  if (tid == 0) A.nmatches[p] = s_nmatch;
+}
+
+// ------------------------------------------------------------------------------------------
 constexpr int kApThreads = 256;
 
 // grid: (column spans, row keyframes). Rows of keyframe i in registers (RPT per thread), each
@@ -358,8 +562,26 @@ int launch_match(const PairArgs& A, int pairs, size_t smem, cudaStream_t s) {
   return ORB_OK;
 }
 
+template <int RPT>
+int launch_match_bf(const PairArgs& A, int pairs, size_t smem, cudaStream_t s) {
+  ORB_CUDA(cudaFuncSetAttribute(k_match_pairs_bf<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_match_pairs_bf<RPT><<<pairs, kBfThreads, smem, s>>>(A);
+  ORB_CUDA(cudaGetLastError());
+  return ORB_OK;
+}
+
+int dispatch_match_bf(const PairArgs& A, int pairs, cudaStream_t s) {
+  const size_t region0 = (size_t)std::max(A.n2 * 32, A.n1 * 8);
+  const size_t smem = round_up(region0 + (size_t)A.n2 * 2 + (size_t)A.n1 * 2 + (size_t)A.n2 * 2 + (size_t)A.n1 * 2 + (size_t)A.n1 + 16, (size_t)16);
+  const int rpt = (A.n1 + kBfThreads - 1) / kBfThreads;
+  if (rpt <= 1) return launch_match_bf<1>(A, pairs, smem, s);
+  if (rpt <= 2) return launch_match_bf<2>(A, pairs, smem, s);
+  return launch_match_bf<4>(A, pairs, smem, s);
+}
+
 template <bool W>
 int dispatch_match(const PairArgs& A, int pairs, cudaStream_t s) {
+  if (!W && A.n1 <= kBfMaxN && A.n2 <= kBfMaxN && A.n1 > 0 && A.n2 > 0) return dispatch_match_bf(A, pairs, s);
   const size_t smem = (size_t)(A.n1 + A.n2) * 4 + round_up((size_t)A.n1, (size_t)16);
   if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints per frame for the matcher's shared memory");
   const int cpt = (A.n2 + kMatchThreads - 1) / kMatchThreads;
