@@ -196,8 +196,8 @@ __device__ __forceinline__ unsigned resize_row_word(const LevelGeom& D, const Le
 // border), unless the group straddles a turning point. Returns false for such mixed groups.
 __device__ __forceinline__ bool reflect_group(int p0, int n, int& lo, bool& rev) {
   if (p0 >= 0 && p0 + 3 < n) { lo = p0; rev = false; return true; }
-  if (p0 + 3 < 0) { lo = -p0 - 3; rev = true; return -p0 < n; }
-  if (p0 >= n) { lo = 2 * (n - 1) - p0 - 3; rev = true; return lo >= 0; }
+  if (p0 + 3 <= 0) { lo = -p0 - 3; rev = true; return -p0 < n; }                  // p = 0 mirrors onto itself
+  if (p0 >= n - 1) { lo = 2 * (n - 1) - p0 - 3; rev = true; return lo >= 0; }     // so does p = n-1
   return false;
 }
 
@@ -439,8 +439,6 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
   unsigned short* hits = reinterpret_cast<unsigned short*>(base + lay.rawBytes + lay.tileBytes);
   u8* sc = base + lay.rawBytes + lay.tileBytes + lay.hitsBytes;
   const unsigned ltmask = (1u << lane) - 1u;
-  // bit 15 of a half is set iff its bound exceeds minTh + 255, i.e. a corner at minTh is possible
-  const unsigned K = 0x7FFF7FFFu - (unsigned)(g.minTh + 255) * 0x00010001u;
 
   // work distribution: a warp grabs runs of kFastRun consecutive cells from a global counter
   CellDesc c;
@@ -509,66 +507,77 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
     have = advance();
     if (have) fast_prefetch(c, raw, lay.rawPitchWords, lane);
 
-    // ---- prefilter: lanes cover one row (S > 16) or two rows (S <= 16) per step
+    // Two threshold passes like the reference (:1111-1124): cv::FAST(iniTh) first; only if its
+    // result (after NMS) is empty, cv::FAST(minTh). Scoring pixels at iniTh first keeps the exact
+    // scoring away from the many weak corners of the ~97 % of cells that have a strong one.
     unsigned short* queue = hits + S * ch;   // the queue fills [S*ch, S*ch + nq), hits grow from 0
-    int nq = 0;
-    {
-      const int two = S <= 16;
-      const int x = two ? (lane & 15) : lane;
-      const int rsub = two ? (lane >> 4) : 0, rstep = two ? 2 : 1;
+    int th = g.iniTh, nh = 0;
+#pragma unroll 1
+    for (;;) {
+      // bit 15 of a half is set iff its bound exceeds th + 255, i.e. a corner at th is possible
+      const unsigned K = 0x7FFF7FFFu - (unsigned)(th + 255) * 0x00010001u;
+      // ---- prefilter: lanes cover one row (S > 16) or two rows (S <= 16) per step
+      int nq = 0;
+      {
+        const int two = S <= 16;
+        const int x = two ? (lane & 15) : lane;
+        const int rsub = two ? (lane >> 4) : 0, rstep = two ? 2 : 1;
 #pragma unroll 2
-      for (int r0 = 0; r0 < ch; r0 += rstep) {
-        const int r = r0 + rsub;
-        bool pass = false;
-        if (x < S && r < ch) pass = ((fast_bound4(tile + (r + 3) * tp + (x + 3), tp) + K) & 0x80008000u) != 0u;
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (pass) queue[nq + __popc(m & ltmask)] = (unsigned short)((r << 6) | x);
-        nq += __popc(m);
+        for (int r0 = 0; r0 < ch; r0 += rstep) {
+          const int r = r0 + rsub;
+          bool pass = false;
+          if (x < S && r < ch) pass = ((fast_bound4(tile + (r + 3) * tp + (x + 3), tp) + K) & 0x80008000u) != 0u;
+          const unsigned m = __ballot_sync(0xffffffffu, pass);
+          if (pass) queue[nq + __popc(m & ltmask)] = (unsigned short)((r << 6) | x);
+          nq += __popc(m);
+        }
       }
+      __syncwarp();
+      // ---- exact score of the queued pairs
+      nh = 0;
+      for (int e0 = 0; e0 < nq; e0 += 32) {
+        const int e = e0 + lane;
+        int sLo = 0, sHi = 0, r = 0, x = 0;
+        if (e < nq) {
+          const int i = queue[e];
+          r = i >> 6; x = i & 63;
+          FastDiffs D;
+          fast_load_diffs(tile + (r + 3) * tp + (x + 3), tp, D);
+          const unsigned s2 = fast_exact(D);
+          sLo = (int)(s2 & 0xffffu) - 256;
+          sHi = x + S < cw ? (int)(s2 >> 16) - 256 : 0;
+        }
+        const bool hLo = sLo >= th, hHi = sHi >= th;
+        const unsigned mLo = __ballot_sync(0xffffffffu, hLo), mHi = __ballot_sync(0xffffffffu, hHi);
+        if (hLo) {
+          sc[(r + 1) * sp + x + 1] = (u8)sLo;
+          hits[nh + __popc(mLo & ltmask)] = (unsigned short)((r << 6) | x);
+        }
+        nh += __popc(mLo);
+        if (hHi) {
+          sc[(r + 1) * sp + x + S + 1] = (u8)sHi;
+          hits[nh + __popc(mHi & ltmask)] = (unsigned short)((r << 6) | (x + S));
+        }
+        nh += __popc(mHi);
+      }
+      __syncwarp();
+      // ---- strict 3x3 maximum inside the cell (scores below th count as 0, as in cv::FAST)
+      bool found = false;
+      for (int e = lane; e < nh; e += 32) {
+        const int p = hits[e];
+        const int r = p >> 6, cx = p & 63;
+        const u8* q = sc + (r + 1) * sp + cx + 1;
+        const int s = q[0];
+        const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
+        if (s > m) {
+          hits[e] = (unsigned short)(p | 0x8000);
+          found = true;
+        }
+      }
+      if (__any_sync(0xffffffffu, found) || th == g.minTh) break;
+      th = g.minTh;   // nothing at iniTh: redo the cell at minTh (the scores already written stay valid)
+      __syncwarp();
     }
-    __syncwarp();
-    // ---- exact score of the queued pairs
-    int nh = 0;
-    for (int e0 = 0; e0 < nq; e0 += 32) {
-      const int e = e0 + lane;
-      int sLo = 0, sHi = 0, r = 0, x = 0;
-      if (e < nq) {
-        const int i = queue[e];
-        r = i >> 6; x = i & 63;
-        FastDiffs D;
-        fast_load_diffs(tile + (r + 3) * tp + (x + 3), tp, D);
-        const unsigned s2 = fast_exact(D);
-        sLo = (int)(s2 & 0xffffu) - 256;
-        sHi = x + S < cw ? (int)(s2 >> 16) - 256 : 0;
-      }
-      const bool hLo = sLo >= g.minTh, hHi = sHi >= g.minTh;
-      const unsigned mLo = __ballot_sync(0xffffffffu, hLo), mHi = __ballot_sync(0xffffffffu, hHi);
-      if (hLo) {
-        sc[(r + 1) * sp + x + 1] = (u8)sLo;
-        hits[nh + __popc(mLo & ltmask)] = (unsigned short)((r << 6) | x);
-      }
-      nh += __popc(mLo);
-      if (hHi) {
-        sc[(r + 1) * sp + x + S + 1] = (u8)sHi;
-        hits[nh + __popc(mHi & ltmask)] = (unsigned short)((r << 6) | (x + S));
-      }
-      nh += __popc(mHi);
-    }
-    __syncwarp();
-    // ---- strict 3x3 maximum inside the cell; does cv::FAST(iniTh) find anything? (:1111-1124)
-    bool strong = false;
-    for (int e = lane; e < nh; e += 32) {
-      const int p = hits[e];
-      const int r = p >> 6, cx = p & 63;
-      const u8* q = sc + (r + 1) * sp + cx + 1;
-      const int s = q[0];
-      const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
-      if (s > m) {
-        hits[e] = (unsigned short)(p | 0x8000);
-        strong |= s >= g.iniTh;
-      }
-    }
-    const int th = __any_sync(0xffffffffu, strong) ? g.iniTh : g.minTh;
     // ---- emit: count, reserve with one atomic, write
     const LevelGeom& L = g.lv[cur.l];
     int* cnt = candCount + cur.f * g.nlevels + cur.l;
