@@ -1,11 +1,14 @@
 # Collects the round's evidence: parity tests, bench lines (ours + reference arm), the ncu launch
-# list of the bench command and one ncu --set full capture of the dominant kernels.
+# list of the bench command and ncu --set full captures of the dominant kernels.
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -5 > gpurun_out/pytest_gpu.txt; cat gpurun_out/pytest_gpu.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --pairs 256 --match-pairs 512 --allpairs-kf 64 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_fast_cells|k_match_pairs|k_allpairs" -s 3 -c 3 -o gpurun_out/prof_dominant python bench.py --steps 1 --warmup 3 --pairs 128 --chunk 256 --match-pairs 512 --allpairs-kf 64 --no-cpu-baseline > gpurun_out/ncu_dominant.log 2>&1
+python bench.py --workload euroc --no-cpu-baseline --allpairs-kf 0 --match-pairs 64 > gpurun_out/bench_euroc.json 2> gpurun_out/bench_euroc.err
+python bench.py --workload tum1 --no-cpu-baseline --allpairs-kf 0 --match-pairs 64 > gpurun_out/bench_tum1.json 2> gpurun_out/bench_tum1.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --pairs 256 --match-pairs 512 --allpairs-kf 64 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_fast_cells -s 3 -c 1 -o gpurun_out/prof_fast python bench.py --steps 1 --warmup 3 --pairs 128 --chunk 256 --match-pairs 64 --allpairs-kf 0 --no-cpu-baseline > gpurun_out/ncu_fast.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_match_pairs_bf|k_allpairs" -s 1 -c 2 -o gpurun_out/prof_match python bench.py --steps 1 --warmup 3 --pairs 64 --chunk 128 --match-pairs 1024 --allpairs-kf 128 --no-cpu-baseline > gpurun_out/ncu_match.log 2>&1
 ls -la gpurun_out
