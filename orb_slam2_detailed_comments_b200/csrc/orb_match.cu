@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(kBfThreads, 2) k_match_pairs_bf(const PairArgs
   short* m12 = reinterpret_cast<short*>(md + n2);
   short* m21 = m12 + n1;
   short* accIdx = m21 + n2;   // frame-2 index a row was matched to when it was accepted (-1: never)
-  u8* binOf = reinterpret_cast<u8*>(accIdx + n1);
+  int* tag = reinterpret_cast<int*>(accIdx + n1);   // byte offset region0 + 4*(n1+n2): 4-byte aligned;   // lowest lane of the current step matched to a candidate
+  u8* binOf = reinterpret_cast<u8*>(tag + n2);
   const u8* D1 = A.desc1 + (size_t)p * A.stride1 * 32;
   const u8* D2 = A.desc2 + (size_t)p * A.stride2 * 32;
   const float* ang1 = A.ang1 + (size_t)p * A.stride1;
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kBfThreads, 2) k_match_pairs_bf(const PairArgs
     const uint4* src = reinterpret_cast<const uint4*>(D2);
     for (int t = tid; t < n2 * 2; t += kBfThreads) bdesc[t] = __ldg(src + t);
   }
-  for (int i = tid; i < n2; i += kBfThreads) { md[i] = 0xffffu; m21[i] = -1; }
+  for (int i = tid; i < n2; i += kBfThreads) { md[i] = 0xffffu; m21[i] = -1; tag[i] = INT_MAX; }
   for (int i = tid; i < n1; i += kBfThreads) { m12[i] = -1; accIdx[i] = -1; binOf[i] = 255; }
   if (tid < HISTO_LENGTH) s_hist[tid] = 0;
   if (tid == 0) { s_nmatch = 0; s_row = 0; s_need = -1; s_exact = -1; }
@@ -337,54 +338,73 @@ __global__ void __launch_bounds__(kBfThreads, 2) k_match_pairs_bf(const PairArgs
   }
   __syncthreads();
 
-  // ---- phase 2: sequential commit (thread 0) with cooperative exact recomputation on demand
+  // ---- phase 2: in-order commit by warp 0, 32 rows per step, with cooperative exact recomputation
+  // on demand. The 32 rows are decided in parallel against the state before the step; the longest
+  // prefix in which no row touches a candidate that an EARLIER row of the step has just been matched
+  // to is committed (those commits are independent of each other), the rest is re-evaluated.
   const float factor = HISTO_LENGTH / 360.0f;  // this fork: ORBmatcher.cc:585-586
   const bool wantDist = A.best != nullptr;
   for (;;) {
-    if (tid == 0) {
-      int row = s_row, nmatches = s_nmatch, need = -1;
+    if (wid == 0) {
+      int row0 = s_row, nmatches = s_nmatch, need = -1;
       const int exactRow = s_exact;
-      for (; row < n1; row++) {
-        const uint2 kk = keys[row];
-        int best, second, bestIdx;
-        bool decided = false, accept = false;
+      while (row0 < n1) {
+        const int row = row0 + lane;
+        const bool active = row < n1;
+        const uint2 kk = active ? keys[row] : make_uint2(kNoKey, kNoKey);
         const int d1 = kk.x == kNoKey ? INT_MAX : (int)(kk.x >> 16), c1 = (int)(kk.x & 0xffffu);
         const int d2 = kk.y == kNoKey ? INT_MAX : (int)(kk.y >> 16), c2 = (int)(kk.y & 0xffffu);
-        best = d1; second = d2; bestIdx = c1;
-        if (row == exactRow) {
-          decided = true;   // computed against the current vMatchedDistance
-        } else {
-          const bool s1 = kk.x != kNoKey && (int)md[c1] <= d1;   // would the reference skip it? (:627)
-          const bool s2 = kk.y != kNoKey && (int)md[c2] <= d2;
-          if (!s1 && !s2) decided = true;
-          else if (!wantDist) {
-            if (!s1) {                       // best stands, second >= d2
-              if (d1 > TH_LOW) { decided = true; best = INT_MAX; }
-              else if ((float)d1 < __fmul_rn((float)d2, A.nnratio)) { decided = true; accept = true; }
-            } else if (!s2) {                // the best is the old runner-up, second >= d2 unknown
-              if (d2 > TH_LOW) { decided = true; best = INT_MAX; }
-            } else {                         // both taken: best >= d2
-              if (d2 > TH_LOW) { decided = true; best = INT_MAX; }
+        int best = d1, second = d2, bestIdx = c1;
+        bool decided = !active, accept = false;
+        if (active) {
+          if (row == exactRow) {
+            decided = true;   // computed against the current vMatchedDistance
+          } else {
+            const bool s1 = kk.x != kNoKey && (int)md[c1] <= d1;   // would the reference skip it? (:627)
+            const bool s2 = kk.y != kNoKey && (int)md[c2] <= d2;
+            if (!s1 && !s2) decided = true;
+            else if (!wantDist) {
+              if (!s1) {                       // best stands, second >= d2
+                if (d1 > TH_LOW) { decided = true; best = INT_MAX; }
+                else if ((float)d1 < __fmul_rn((float)d2, A.nnratio)) { decided = true; accept = true; }
+              } else if (d2 > TH_LOW) {        // best >= d2 > TH_LOW whichever candidate it is
+                decided = true; best = INT_MAX;
+              }
             }
           }
+          if (decided && !accept) accept = best <= TH_LOW && (float)best < __fmul_rn((float)second, A.nnratio);  // :644-647
         }
-        if (!decided) { need = row; break; }
-        if (wantDist) {
-          A.best[(size_t)p * n1 + row] = best;
-          A.second[(size_t)p * n1 + row] = second;
+        // which rows depend on a match made by an earlier row of this step?
+        if (accept) atomicMin(&tag[bestIdx], lane);
+        __syncwarp();
+        const bool conflict = active && ((kk.x != kNoKey && tag[c1] < lane) || (kk.y != kNoKey && tag[c2] < lane));
+        __syncwarp();
+        if (accept) tag[bestIdx] = INT_MAX;
+        const unsigned undecided = __ballot_sync(0xffffffffu, active && !decided);
+        const unsigned bad = undecided | __ballot_sync(0xffffffffu, conflict);
+        const int P = min(bad ? __ffs(bad) - 1 : 32, n1 - row0);
+        const bool commit = lane < P;
+        int stolen = 0;
+        if (commit) {
+          if (wantDist) {
+            A.best[(size_t)p * n1 + row] = best;
+            A.second[(size_t)p * n1 + row] = second;
+          }
+          if (accept) {
+            const int prevOwner = m21[bestIdx];
+            if (prevOwner >= 0) { m12[prevOwner] = -1; stolen = 1; }  // :650-654
+            m12[row] = (short)bestIdx;
+            m21[bestIdx] = (short)row;
+            md[bestIdx] = (unsigned short)best;
+            accIdx[row] = (short)bestIdx;   // the rotation bin is filled in afterwards, in parallel
+          }
         }
-        if (!accept) accept = best <= TH_LOW && (float)best < __fmul_rn((float)second, A.nnratio);  // :644-647
-        if (accept) {
-          const int prevOwner = m21[bestIdx];
-          if (prevOwner >= 0) { m12[prevOwner] = -1; nmatches--; }  // :650-654
-          m12[row] = (short)bestIdx;
-          m21[bestIdx] = (short)row;
-          md[bestIdx] = (unsigned short)best;
-          nmatches++;
-          accIdx[row] = (short)bestIdx;   // the rotation bin is filled in afterwards, in parallel
-        }
+        nmatches += __popc(__ballot_sync(0xffffffffu, commit && accept)) - __popc(__ballot_sync(0xffffffffu, stolen != 0));
+        __syncwarp();
+        row0 += P;
+        if (P < 32 && row0 < n1 && ((undecided >> P) & 1u)) { need = row0; break; }
       }
-      s_row = row; s_nmatch = nmatches; s_need = need;
+      if (lane == 0) { s_row = row0; s_nmatch = nmatches; s_need = need; }
     }
     __syncthreads();
     const int need = s_need;
@@ -572,7 +592,7 @@ int launch_match_bf(const PairArgs& A, int pairs, size_t smem, cudaStream_t s) {
 
 int dispatch_match_bf(const PairArgs& A, int pairs, cudaStream_t s) {
   const size_t region0 = (size_t)std::max(A.n2 * 32, A.n1 * 8);
-  const size_t smem = round_up(region0 + (size_t)A.n2 * 2 + (size_t)A.n1 * 2 + (size_t)A.n2 * 2 + (size_t)A.n1 * 2 + (size_t)A.n1 + 16, (size_t)16);
+  const size_t smem = round_up(region0 + (size_t)A.n2 * 2 + (size_t)A.n1 * 2 + (size_t)A.n2 * 2 + (size_t)A.n1 * 2 + 4 + (size_t)A.n2 * 4 + (size_t)A.n1 + 16, (size_t)16);
   const int rpt = (A.n1 + kBfThreads - 1) / kBfThreads;
   if (rpt <= 1) return launch_match_bf<1>(A, pairs, smem, s);
   if (rpt <= 2) return launch_match_bf<2>(A, pairs, smem, s);
