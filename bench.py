@@ -297,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
     # points (what Frame::Frame does: H2D, all kernels, D2H, synchronise), host wall clock
     lat = {}
     one = pool[0]; two = pool[1]
-    for name, fn in (("orb_extract_ms", lambda: ext(one)),
+    for name, fn in () if args.no_latency else (("orb_extract_ms", lambda: ext(one)),
                      ("orb_extract_with_pyramid_ms", lambda: ext(one, want_pyramid=True)),
                      ("orb_extract_stereo_ms", lambda: ext.extract_stereo(one, two, kitti_bf, kitti_bf / kitti_fx))):
         for _ in range(5):
@@ -490,6 +490,7 @@ def main():
     ap.add_argument("--match-steps", type=int, default=3)
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS), help="frame shape / feature count (default: the headline KITTI shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-call latency loops (profiling runs)")
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP, help="stereo pairs per step per GPU (profiling runs shrink this)")
     ap.add_argument("--match-pairs", type=int, default=MATCH_PAIRS)
     ap.add_argument("--allpairs-kf", type=int, default=512, help="keyframes of the all-pairs workload (0 = skip)")
