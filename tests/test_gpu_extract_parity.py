@@ -207,3 +207,25 @@ def test_lanes_do_not_change_results(oracle):
         n = c1[b]
         assert k1[b, :n].tobytes() == k2[b, :n].tobytes() and d1[b, :n].tobytes() == d2[b, :n].tobytes()
         assert n == len(orc(imgs[b])[0])
+
+
+@pytest.mark.parametrize("params", [(500, 1.5, 4, 30, 10), (1500, 1.1, 12, 15, 5), (300, 2.0, 3, 20, 7), (800, 1.2, 1, 20, 20)])
+def test_other_extractor_parameters(oracle, params):
+    """Generality: other feature budgets, scale factors (incl. > 4/3, where the resize kernel leaves
+    its shared-row fast path), level counts and FAST thresholds (incl. iniTh == minTh)."""
+    from orb_slam2_detailed_comments_b200 import ORBextractor
+    from orb_slam2_detailed_comments_b200.synth import synth_frame
+    nf, sf, nl, ini, mn = params
+    gpu = ORBextractor(nf, sf, nl, ini, mn)
+    orc = oracle.OracleExtractor(nf, sf, nl, ini, mn)
+    assert np.array_equal(gpu.GetScaleFactors(), orc.scale) and np.array_equal(gpu.mnFeaturesPerLevel, orc.per_level)
+    img = synth_frame(800, 600, 17)
+    kps, desc = gpu(img)
+    okps, odesc = orc(img)
+    for l in range(nl):
+        assert np.array_equal(gpu.stage_level(0, l), orc.level(l)), "pyramid level %d differs" % l
+    assert len(kps) == len(okps) > 0
+    for f in ("x", "y", "size", "response", "octave"):
+        assert np.array_equal(kps[f], okps[f]), f
+    assert np.abs(kps["angle"] - okps["angle"]).max() <= ANGLE_TOL_DEG
+    assert (desc == odesc).all(1).mean() >= MIN_IDENTICAL_DESC

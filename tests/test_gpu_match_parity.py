@@ -62,7 +62,7 @@ def test_search_for_initialization_reference_mode(oracle, window):
     assert n2 == n2_ref and np.array_equal(m2, m2_ref) and np.array_equal(prev_gpu, prev2_ref)
 
 
-@pytest.mark.parametrize("n", [2000, 1000, 777, 130])
+@pytest.mark.parametrize("n", [2600, 2048, 2000, 1000, 777, 130, 33])
 @pytest.mark.parametrize("check_ori", [True, False])
 def test_bruteforce_single_pair(oracle, n, check_ori):
     from orb_slam2_detailed_comments_b200 import FrameView, ORBmatcher
