@@ -16,8 +16,8 @@
 //   k_describe                                      IC_Angle :94-141, computeOrbDescriptor :153-204,
 //                                                   level->image scaling :1633-1642
 //   k_stereo (stereo entry points only)             Frame::ComputeStereoMatches, src/Frame.cc:831-1082
-// A batch call cuts the batch into chunks of max_batch frames; consecutive chunks alternate between
-// two workspace lanes / streams so that kernels of neighbouring chunks overlap.
+// A batch call cuts the batch into chunks of max_batch frames (optionally alternating between two
+// workspace lanes / streams, see orb_set_lanes).
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -1010,23 +1010,25 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-constexpr int kPatchWords = 11;   // blurred patch: 37 rows x 44 bytes (37 + alignment slack)
-constexpr int kMomWords = 9;      // unblurred patch: 31 rows x 36 bytes (31 + alignment slack)
-constexpr int kDescSlots = 32;    // keypoint slots per CTA (8 warps x 4)
+constexpr int kPatchWords = 12;   // blurred patch: 37 rows x 48 bytes (37 + 8-byte alignment slack), 6 chunks of 8 B
+constexpr int kMomWords = 10;     // unblurred patch: 31 rows x 40 bytes (31 + 8-byte alignment slack), 5 chunks of 8 B
+constexpr int kDescSlots = 16;    // keypoint slots per CTA (8 warps x 2: 28 KB of patches per CTA keeps 8 CTAs per SM)
 constexpr int kDescPerWarp = kDescSlots / 8;
 constexpr int kPatchBufWords = 37 * kPatchWords;  // one buffer holds either patch
 constexpr int kDescSmem = 8 * kDescPerWarp * kPatchBufWords * 4;
 
-__device__ __forceinline__ void stage_patch(unsigned* dst, const u8* src, int pitch, int rows, int words, int lane) {
-  // rows x words 4-byte cp.async copies, 32 per step
-  int r = lane / words, wd = lane - r * words;
-  const int dr = 32 / words, dw = 32 - dr * words;
-  const int n = rows * words;
-  for (int i = lane; i < n; i += 32) {
-    __pipeline_memcpy_async(dst + i, src + (r * pitch + 4 * wd), 4);
-    wd += dw;
-    r += dr;
-    if (wd >= words) { wd -= words; r++; }
+template <int ROWS, int WORDS>
+__device__ __forceinline__ void stage_patch(unsigned* dst, const u8* src, int pitch, int lane) {
+  // ROWS x WORDS/2 8-byte cp.async copies (the LDGSTS issue rate, not bytes, bounds this kernel),
+  // 32 per step; (row, chunk) of every step is a compile-time function of the lane
+  constexpr int CH = WORDS / 2, N = ROWS * CH;
+#pragma unroll
+  for (int k = 0; k < (N + 31) / 32; k++) {
+    const int i = lane + 32 * k;
+    if (32 * (k + 1) <= N || i < N) {
+      const int r = i / CH, c = i - r * CH;
+      __pipeline_memcpy_async(dst + 2 * i, src + (r * pitch + 8 * c), 8);
+    }
   }
   __pipeline_commit();
 }
@@ -1101,9 +1103,9 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
       const LevelGeom& L = g.lv[l];
       const uint2 rec = kept[(size_t)f * keptTotal + L.keptOff + (slotIdx - s_prefix[l])];
       lvl[k] = l; px[k] = (int)(rec.x & 0xffffu); py[k] = (int)(rec.x >> 16); resp[k] = (int)rec.y;
-      const int xa = (px[k] - kHalfPatch) & ~3;
-      stage_patch(wbuf + k * kPatchBufWords, pyr + (size_t)f * pyrStride + L.off + (long long)(py[k] - kHalfPatch) * L.pitch + xa,
-                  L.pitch, 31, kMomWords, lane);
+      const int xa = (px[k] - kHalfPatch) & ~7;
+      stage_patch<31, kMomWords>(wbuf + k * kPatchBufWords,
+                                 pyr + (size_t)f * pyrStride + L.off + (long long)(py[k] - kHalfPatch) * L.pitch + xa, L.pitch, lane);
     } else {
       __pipeline_commit();
     }
@@ -1115,8 +1117,9 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
     __pipeline_wait_prior(kDescPerWarp - 1 - k);
     __syncwarp();
     if (lvl[k] >= 0) {
-      const unsigned* row = wbuf + k * kPatchBufWords + (lane < 31 ? lane : 30) * kMomWords;
-      const unsigned sh = (unsigned)((px[k] - kHalfPatch) & 3) * 8;
+      const int mis = (px[k] - kHalfPatch) & 7;   // patch byte 0 sits `mis` bytes into the staged row
+      const unsigned* row = wbuf + k * kPatchBufWords + (lane < 31 ? lane : 30) * kMomWords + (mis >> 2);
+      const unsigned sh = (unsigned)(mis & 3) * 8;
       unsigned s1 = 0, s2 = 0;
       unsigned prev = row[0];
 #pragma unroll
@@ -1144,9 +1147,9 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
     const int sl = wid * kDescPerWarp + k;
     if (lvl[k] >= 0) {
       const LevelGeom& L = g.lv[lvl[k]];
-      const int xa = (px[k] - 18) & ~3;
-      stage_patch(wbuf + k * kPatchBufWords, blur + (size_t)f * blurStride + L.boff + (long long)(py[k] - 18) * L.bpitch + xa,
-                  L.bpitch, 37, kPatchWords, lane);
+      const int xa = (px[k] - 18) & ~7;
+      stage_patch<37, kPatchWords>(wbuf + k * kPatchBufWords,
+                                   blur + (size_t)f * blurStride + L.boff + (long long)(py[k] - 18) * L.bpitch + xa, L.bpitch, lane);
     } else {
       __pipeline_commit();
     }
@@ -1175,7 +1178,7 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
     const LevelGeom& L = g.lv[lvl[k]];
     const int x = px[k], y = py[k];
     const float a = s_cos[sl], b = s_sin[sl];
-    const u8* cb = reinterpret_cast<const u8*>(wbuf + k * kPatchBufWords) + 18 * (4 * kPatchWords) + (x - ((x - 18) & ~3));
+    const u8* cb = reinterpret_cast<const u8*>(wbuf + k * kPatchBufWords) + 18 * (4 * kPatchWords) + (x - ((x - 18) & ~7));
     int val = 0;
 #pragma unroll
     for (int bit = 0; bit < 8; bit++) {
@@ -1450,9 +1453,10 @@ struct orb_extractor {
   uint2* d_kept = nullptr; int* d_keptCount = nullptr; int2* d_taps = nullptr;
   signed char* d_pattern = nullptr; int* d_overflow = nullptr; int* d_work = nullptr;
   int wsFrames = 0;
-  // two workspace lanes: consecutive chunks run on two streams so that the latency-bound kernels of
-  // one chunk (quadtree, describe, stereo) overlap the issue-bound kernels of the other
-  int lanes = 2, lastLane = 0;
+  // optional second workspace lane (orb_set_lanes / ORB_B200_LANES=2): consecutive chunks then run on
+  // two streams. It paid while some kernels were latency-bound; with the current kernels every stage
+  // saturates the SMs and one lane is as fast, so 1 is the default.
+  int lanes = 1, lastLane = 0;
   cudaStream_t laneStream[2] = {nullptr, nullptr};
   cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
   // staging for the host entry points: two sets, so that the H2D copy of chunk i+1 and the D2H
@@ -1599,7 +1603,9 @@ int build_geom(orb_extractor* e, int W, int H) {
     y.total = y.rawBytes + y.tileBytes + y.hitsBytes + y.scBytes;
     // warps per CTA: maximise resident warps per SM under 227 KB (1 KB reserved per CTA)
     int bestW = 1, bestResident = 0;
-    for (int w = 1; w <= kFastWarps; w++) {
+    int maxW = kFastWarps;
+    if (const char* ev = getenv("ORB_B200_FAST_WARPS")) maxW = std::max(1, std::min(kFastWarps, atoi(ev)));
+    for (int w = 1; w <= maxW; w++) {
       const long long perCta = (long long)y.total * w + 1024;
       const int resident = (int)std::min<long long>(32, (227 * 1024) / perCta) * w;
       if (perCta <= 200 * 1024 && resident > bestResident) { bestResident = resident; bestW = w; }
