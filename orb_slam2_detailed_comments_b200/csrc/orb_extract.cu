@@ -192,13 +192,20 @@ __device__ __forceinline__ unsigned resize_row_word(const LevelGeom& D, const Le
 }
 
 // 4 consecutive bordered positions p0..p0+3 (interior coordinates, may be negative or >= n) map,
-// under REFLECT_101, to 4 consecutive interior positions, ascending (inside) or descending (in the
-// border), unless the group straddles a turning point. Returns false for such mixed groups.
-__device__ __forceinline__ bool reflect_group(int p0, int n, int& lo, bool& rev) {
-  if (p0 >= 0 && p0 + 3 < n) { lo = p0; rev = false; return true; }
-  if (p0 + 3 <= 0) { lo = -p0 - 3; rev = true; return -p0 < n; }                  // p = 0 mirrors onto itself
-  if (p0 >= n - 1) { lo = 2 * (n - 1) - p0 - 3; rev = true; return lo >= 0; }     // so does p = n-1
-  return false;
+// under REFLECT_101, into a window of 4 consecutive interior positions [lo, lo+3]: ascending
+// (inside), descending (in the border) or, where the group straddles the far turning point, a
+// mix. perm holds, per position j, the index 0..3 inside the window (nibble j) - directly a PRMT
+// selector for the 4 output bytes. Returns false where no such window exists.
+__device__ __forceinline__ bool reflect_group(int p0, int n, int& lo, unsigned& perm) {
+  if (p0 >= 0 && p0 + 3 < n) { lo = p0; perm = 0x3210u; return true; }
+  if (p0 + 3 <= 0) { lo = -p0 - 3; perm = 0x0123u; return -p0 < n; }                  // p = 0 mirrors onto itself
+  if (p0 >= n - 1) { lo = 2 * (n - 1) - p0 - 3; perm = 0x0123u; return lo >= 0; }     // so does p = n-1
+  if (p0 < 0 || n < 4) return false;
+  lo = n - 4;                                                                         // p0 < n-1 < p0+3
+  perm = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) perm |= (unsigned)(reflect101(p0 + j, n) - lo) << (4 * j);
+  return true;
 }
 
 // Thread = 4 columns x 4 rows of the bordered plane. Blocks that do not straddle a reflection
@@ -217,8 +224,8 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
   u8* dst = pyr + (size_t)f * pyrStride + D.off + (long long)(by0 - kEdge) * D.pitch + c0;
   const int nrows = min(4, D.h + 2 * kEdge - by0);
   int xlo = 0, ylo = 0;
-  bool revX = false, revY = false;
-  bool blockFast = nrows == 4 && reflect_group(c0, D.w, xlo, revX) && reflect_group(by0 - kEdge, D.h, ylo, revY);
+  unsigned permX = 0x3210u, permY = 0x3210u;
+  bool blockFast = nrows == 4 && reflect_group(c0, D.w, xlo, permX) && reflect_group(by0 - kEdge, D.h, ylo, permY);
   int2 tx[4], ty[4];
   if (blockFast) {
 #pragma unroll
@@ -247,6 +254,7 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
 #pragma unroll
       for (int j = 0; j < 4; j++) hq[i][j] = __dp2a_lo((unsigned)tx[j].y, __byte_perm(lo, hi, sel[j]), 0u) >> 4;
     }
+    unsigned orow[4];   // window rows ylo .. ylo+3, bytes already in bordered column order
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const bool e = ty[k].x - base > k;           // source row index is base+k or base+k+1
@@ -259,8 +267,13 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
         // ((cy*(h>>4))>>16) == umulhi(cy<<16, h>>4); the sum is <= 1020, so the result needs no clamp
         out |= ((__umulhi(cy0s, h0) + __umulhi(cy1s, h1) + 2u) >> 2) << (8 * j);
       }
-      if (revX) out = __byte_perm(out, 0u, 0x0123);
-      *reinterpret_cast<unsigned*>(dst + (long long)(revY ? 3 - k : k) * D.pitch) = out;
+      orow[k] = __byte_perm(out, 0u, permX);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned sel = (permY >> (4 * k)) & 3u;   // which window row lands on bordered row by0+k
+      const unsigned v = sel == 0 ? orow[0] : (sel == 1 ? orow[1] : (sel == 2 ? orow[2] : orow[3]));
+      *reinterpret_cast<unsigned*>(dst + (long long)k * D.pitch) = v;
     }
   } else {
     for (int k = 0; k < nrows; k++) {
