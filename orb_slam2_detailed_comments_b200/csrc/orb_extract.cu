@@ -306,6 +306,16 @@ __device__ __forceinline__ void fast_load_diffs(const unsigned* p, int tp, FastD
   D.d[12] = c - p[-3];   D.d[13] = c - rp1[-3]; D.d[14] = c - rp2[-2];  D.d[15] = c - rp3[-1];
 }
 
+// Cheapest necessary condition: the two antipodal pairs on the axes (4 loads).
+__device__ __forceinline__ unsigned fast_bound2(const unsigned* p, int tp) {
+  const unsigned c = p[0] + 0x00FF00FFu;
+  const unsigned d0 = c - p[3 * tp], d8 = c - p[-3 * tp];
+  const unsigned d4 = c - p[3], d12 = c - p[-3];
+  const unsigned minhi = __vmins2(__vmaxs2(d0, d8), __vmaxs2(d4, d12));
+  const unsigned maxlo = __vmaxs2(__vmins2(d0, d8), __vmins2(d4, d12));
+  return __vmaxs2(minhi, 0x01FE01FEu - maxlo);
+}
+
 // Cheap necessary condition for a corner at threshold t, on 8 of the 16 circle pixels: every
 // 9-arc holds one pixel of each antipodal pair (k, k+8); here the 4 pairs of the even positions.
 // Returns an upper bound of S + 256 in each half.
@@ -404,34 +414,24 @@ __device__ __forceinline__ bool fast_cell_desc(const Geom& g, const u8* pyr, siz
   c.l = k.l;
   c.f = k.f;
   c.pitch = L.pitch;
-  const int xs = (c.x0 - 3) & ~3;
+  const int xs = (c.x0 - 3) & ~7;                 // 8-byte aligned: rows are fetched in 8-byte chunks
   c.ox = (c.x0 - 3) - xs;
-  c.rw = (c.ox + c.cw + 6 + 3) >> 2;
+  c.rw = (c.ox + c.cw + 6 + 7) >> 3;              // chunks per row (<= 10)
   c.src = pyr + (size_t)k.f * pyrStride + L.off + (long long)(c.y0 - 3) * L.pitch + xs;
   return c.cw > 0 && c.ch > 0;
 }
 
 __device__ __forceinline__ void fast_prefetch(const CellDesc& c, unsigned* raw, int rawPitchWords, int lane) {
-  // (ch+6) rows x rw (<= 18) words: two rows per step when rw <= 16, one otherwise
+  // (ch+6) rows x rw (<= 10) 8-byte chunks: two rows per step (16 lanes each)
   const int rows = c.ch + 6;
-  if (c.rw <= 16) {
-    const int wd = lane & 15;
-    if (wd < c.rw) {
-      const u8* s = c.src + ((lane >> 4) * c.pitch + 4 * wd);
-      unsigned* d = raw + (lane >> 4) * rawPitchWords + wd;
-      for (int r = lane >> 4; r < rows; r += 2) {
-        __pipeline_memcpy_async(d, s, 4);
-        s += 2 * c.pitch;
-        d += 2 * rawPitchWords;
-      }
-    }
-  } else if (lane < c.rw) {
-    const u8* s = c.src + 4 * lane;
-    unsigned* d = raw + lane;
-    for (int r = 0; r < rows; r++) {
-      __pipeline_memcpy_async(d, s, 4);
-      s += c.pitch;
-      d += rawPitchWords;
+  const int cx = lane & 15;
+  if (cx < c.rw) {
+    const u8* s = c.src + ((lane >> 4) * c.pitch + 8 * cx);
+    unsigned* d = raw + (lane >> 4) * rawPitchWords + 2 * cx;
+    for (int r = lane >> 4; r < rows; r += 2) {
+      __pipeline_memcpy_async(d, s, 8);
+      s += 2 * c.pitch;
+      d += 2 * rawPitchWords;
     }
   }
   __pipeline_commit();
@@ -529,7 +529,8 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
     for (;;) {
       // bit 15 of a half is set iff its bound exceeds th + 255, i.e. a corner at th is possible
       const unsigned K = 0x7FFF7FFFu - (unsigned)(th + 255) * 0x00010001u;
-      // ---- prefilter: lanes cover one row (S > 16) or two rows (S <= 16) per step
+      // ---- prefilter, stage 0 (2 pairs, every pixel pair): lanes cover one row (S > 16) or two
+      // rows (S <= 16) per step; stage 1 (4 pairs) runs on the compacted survivors, in place
       int nq = 0;
       {
         const int two = S <= 16;
@@ -539,11 +540,28 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
         for (int r0 = 0; r0 < ch; r0 += rstep) {
           const int r = r0 + rsub;
           bool pass = false;
-          if (x < S && r < ch) pass = ((fast_bound4(tile + (r + 3) * tp + (x + 3), tp) + K) & 0x80008000u) != 0u;
+          if (x < S && r < ch) pass = ((fast_bound2(tile + (r + 3) * tp + (x + 3), tp) + K) & 0x80008000u) != 0u;
           const unsigned m = __ballot_sync(0xffffffffu, pass);
           if (pass) queue[nq + __popc(m & ltmask)] = (unsigned short)((r << 6) | x);
           nq += __popc(m);
         }
+      }
+      __syncwarp();
+      {
+        int nq1 = 0;
+        for (int e0 = 0; e0 < nq; e0 += 32) {
+          const int e = e0 + lane;
+          bool pass = false;
+          int i = 0;
+          if (e < nq) {
+            i = queue[e];
+            pass = ((fast_bound4(tile + ((i >> 6) + 3) * tp + ((i & 63) + 3), tp) + K) & 0x80008000u) != 0u;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, pass);   // every lane has read its entry by now
+          if (pass) queue[nq1 + __popc(m & ltmask)] = (unsigned short)i;
+          nq1 += __popc(m);
+        }
+        nq = nq1;
       }
       __syncwarp();
       // ---- exact score of the queued pairs
@@ -1608,7 +1626,7 @@ int build_geom(orb_extractor* e, int W, int H) {
     if (maxCw > 60 || maxCh > 60) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell larger than 60 px");
     const int S = (maxCw + 1) / 2;
     FastSmemLayout& y = e->fastLay;
-    y.rawPitchWords = (3 + maxCw + 6 + 3) / 4;
+    y.rawPitchWords = 2 * ((7 + maxCw + 6 + 7) / 8);   // 8-byte chunks
     y.rawBytes = round_up(y.rawPitchWords * 4 * (maxCh + 6), 16);
     y.tileBytes = round_up(4 * (S + 6) * (maxCh + 6), 16);
     y.hitsBytes = round_up(2 * (2 * S * maxCh), 16);   // hits + queue share it (see k_fast_cells)
