@@ -45,6 +45,7 @@ constexpr int kLeftPad = 32;    // bytes left of interior column 0 in a bordered
 constexpr int kMaxLevels = 16;
 constexpr int kHalfPatch = 15;  // HALF_PATCH_SIZE, ORBextractor.cc:80
 constexpr int kQtThreads = 256;
+constexpr int kQtSmemKeys = 4096;   // candidates of a level cached in shared memory by k_quadtree
 
 struct LevelGeom {
   int w, h;               // interior size
@@ -745,6 +746,22 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
   int* candList = nodeRank + nodeCap;
   int* byRank = candList + nodeCap;
   unsigned long long* key64 = (unsigned long long*)(byRank + nodeCap);
+  // positions and node ids of up to kQtSmemKeys candidates live in shared memory (they are re-read
+  // in every refinement round); larger levels fall back to the global scratch
+  unsigned* s_xy = (unsigned*)(key64 + nodeCap);
+  unsigned short* s_kn = (unsigned short*)(s_xy + kQtSmemKeys);
+  const bool inSmem = n <= kQtSmemKeys;
+  const unsigned* XY;          // generic pointers: shared or global
+  unsigned short* KNp;
+  if (inSmem) {
+    for (int k = tid; k < n; k += kQtThreads) s_xy[k] = C[k].x;
+    XY = s_xy;
+    KNp = s_kn;
+  } else {
+    XY = nullptr;
+    KNp = KN;
+  }
+  __syncthreads();
 
   const int N = L.nfeat;
   const int nIni = L.nIni;
@@ -764,10 +781,10 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
   }
   __syncthreads();
   for (int k = tid; k < n; k += kQtThreads) {
-    const int xr = (int)(C[k].x & 0xffffu) - 16;
+    const int xr = (int)((inSmem ? XY[k] : C[k].x) & 0xffffu) - 16;
     int r = (int)__fdiv_rn((float)xr, hX);
     r = min(max(r, 0), nIni - 1);
-    KN[k] = (unsigned short)r;
+    KNp[k] = (unsigned short)r;
     atomicAdd(&nodes[r].count, 1);
   }
   __syncthreads();
@@ -780,7 +797,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
     s_roots = m;
   }
   __syncthreads();
-  for (int k = tid; k < n; k += kQtThreads) KN[k] = (unsigned short)slot[KN[k]];
+  for (int k = tid; k < n; k += kQtThreads) KNp[k] = (unsigned short)slot[KNp[k]];
   int numNodes = s_roots;
   { QtNode* t = nodes; nodes = nodes2; nodes2 = t; }
   int seqCounter = nIni;
@@ -798,10 +815,10 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
       if (nodes[i].count > 1) candList[atomicAdd(&s_nc, 1)] = i;
     }
     for (int k = tid; k < n; k += kQtThreads) {
-      const int nd = KN[k];
+      const int nd = KNp[k];
       const QtNode Nd = nodes[nd];
       if (Nd.count > 1) {
-        const unsigned xy = C[k].x;
+        const unsigned xy = inSmem ? XY[k] : C[k].x;
         atomicAdd(&childCnt[4 * nd + qt_quadrant((int)(xy & 0xffffu) - 16, (int)(xy >> 16) - 16, Nd)], 1);
       }
     }
@@ -884,12 +901,12 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
     }
     __syncthreads();
     for (int k = tid; k < n; k += kQtThreads) {
-      const int nd = KN[k];
+      const int nd = KNp[k];
       if (nodeRank[nd] < 0) {
-        KN[k] = (unsigned short)slot[nd];
+        KNp[k] = (unsigned short)slot[nd];
       } else {
-        const unsigned xy = C[k].x;
-        KN[k] = (unsigned short)childIdx[4 * nd + qt_quadrant((int)(xy & 0xffffu) - 16, (int)(xy >> 16) - 16, nodes[nd])];
+        const unsigned xy = inSmem ? XY[k] : C[k].x;
+        KNp[k] = (unsigned short)childIdx[4 * nd + qt_quadrant((int)(xy & 0xffffu) - 16, (int)(xy >> 16) - 16, nodes[nd])];
       }
     }
     __syncthreads();
@@ -912,7 +929,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
     const int ci = y / L.hCell, cj = x / L.wCell;
     const unsigned ord = (unsigned)(((ci * L.nColsAll + cj) * L.hCell + (y - ci * L.hCell)) * L.wCell + (x - cj * L.wCell));
     const unsigned long long pk = ((unsigned long long)c.y << 56) | ((unsigned long long)(0x7fffffffu - ord) << 24) | (unsigned)k;
-    atomicMax(&key64[KN[k]], pk);
+    atomicMax(&key64[KNp[k]], pk);
   }
   __syncthreads();
   for (int i = tid; i < numNodes; i += kQtThreads) {
@@ -1645,7 +1662,7 @@ int build_geom(orb_extractor* e, int W, int H) {
     e->fastWarps = bestW;
     e->fastSmem = (size_t)y.total * bestW;
   }
-  e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8);
+  e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8) + (size_t)kQtSmemKeys * 6;
   if (e->qtSmem > 220 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "features per level too large for the quadtree kernel's shared memory");
   if (e->fastSmem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
   return ORB_OK;
