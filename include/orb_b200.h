@@ -151,6 +151,46 @@ int orb_stage_copy_candidates(orb_extractor* h, int frame, int level, int32_t* x
 int orb_stage_copy_kept(orb_extractor* h, int frame, int level, int32_t* xs, int32_t* ys,
                         int32_t* score, int capacity, int* n);
 
+/* ---- Frame: undistortion and the 64x48 keypoint grid (device resident) ------------------ */
+
+/* mK / mDistCoef of Frame (src/Frame.cc:88-118 read them from the settings file). */
+typedef struct orb_camera {
+  float fx, fy, cx, cy;
+  float k1, k2, p1, p2, k3;
+} orb_camera;
+
+/* One Frame::GetFeaturesInArea call (src/Frame.cc:590): keypoints of `frame` within the circular
+ * window of radius r around (x, y), octave in [min_level, max_level] (max_level < 0: no upper bound). */
+typedef struct orb_area_query {
+  int32_t frame;
+  float x, y, r;
+  int32_t min_level, max_level;
+} orb_area_query;
+
+/* Replaces Frame::ComputeImageBounds (src/Frame.cc:779-829): bounds4 = {mnMinX, mnMaxX, mnMinY,
+ * mnMaxY}. Host side (four points); same arithmetic as the device path. */
+int orb_compute_image_bounds(const orb_camera* cam, int width, int height, float* bounds4);
+
+/* Replaces Frame::UndistortKeyPoints (src/Frame.cc:724-776), i.e. cv::undistortPoints(K, dist, P=K),
+ * for `batch` frames of extraction output (capacity-strided). Only pt changes; identity if k1 == 0. */
+int orb_undistort_keypoints_device(int device, const orb_keypoint* d_keypoints, const int32_t* d_counts, int batch,
+                                   int capacity, const orb_camera* cam, orb_keypoint* d_keypoints_un, void* stream);
+
+/* Replaces Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:399-423, 682-698): mGrid as CSR.
+ * d_cell_start: batch x 3073 ints (cell = ix*48 + iy), d_cell_items: batch x capacity keypoint
+ * indices, in insertion order inside every cell. */
+int orb_assign_features_to_grid_device(int device, const orb_keypoint* d_keypoints_un, const int32_t* d_counts, int batch,
+                                       int capacity, const float* bounds4, int32_t* d_cell_start,
+                                       int32_t* d_cell_items, void* stream);
+
+/* Replaces Frame::GetFeaturesInArea (src/Frame.cc:590-670) for n_queries queries: d_out
+ * (n_queries x out_capacity) receives the indices in the reference's order (ix outer, iy inner,
+ * cell order), d_out_counts the number found (may exceed out_capacity: then the list is truncated). */
+int orb_get_features_in_area_device(int device, const orb_keypoint* d_keypoints_un, int capacity, const float* bounds4,
+                                    const int32_t* d_cell_start, const int32_t* d_cell_items,
+                                    const orb_area_query* d_queries, int n_queries, int32_t* d_out, int out_capacity,
+                                    int32_t* d_out_counts, void* stream);
+
 /* ---- ORBmatcher --------------------------------------------------------------------- */
 
 /* Replaces ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2083-2103): 256-bit Hamming

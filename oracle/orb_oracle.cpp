@@ -818,6 +818,44 @@ int compute_stereo_matches(const Extractor& EL, const Extractor& ER, const KeyPo
   return kept;
 }
 
+// ---------------------------------------------------------------- undistortion + grid
+// cv::undistortPoints(src, dst, K, dist, Mat(), K) as called by Frame::UndistortKeyPoints
+// (Frame.cc:724-776) and Frame::ComputeImageBounds (:779-829): OpenCV's iterative inverse of the
+// (k1,k2,p1,p2,k3) model, 5 fixed iterations in double (default TermCriteria(COUNT,5,0.01)),
+// re-projected with P = K. cam = {fx, fy, cx, cy, k1, k2, p1, p2, k3} (floats, like mK/mDistCoef).
+void undistort_point(const float* cam, float u, float v, float& ou, float& ov) {
+  const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+  const double k1 = cam[4], k2 = cam[5], p1 = cam[6], p2 = cam[7], k3 = cam[8];
+  const double ifx = 1. / fx, ify = 1. / fy;
+  double x = ((double)u - cx) * ifx, y = ((double)v - cy) * ify;
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; j++) {
+    const double r2 = x * x + y * y;
+    const double icdist = (1 + ((0 * r2 + 0) * r2 + 0) * r2) / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+    if (icdist < 0) { x = ((double)u - cx) * ifx; y = ((double)v - cy) * ify; break; }
+    const double dX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + 0 * r2 + 0 * r2 * r2;
+    const double dY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + 0 * r2 + 0 * r2 * r2;
+    x = (x0 - dX) * icdist;
+    y = (y0 - dY) * icdist;
+  }
+  const double xx = fx * x + 0 * y + cx, yy = 0 * x + fy * y + cy, ww = 1. / (0 * x + 0 * y + 1.);
+  ou = (float)(xx * ww);
+  ov = (float)(yy * ww);
+}
+
+// Frame::ComputeImageBounds
+void image_bounds(const float* cam, int w, int h, float* b /* minX maxX minY maxY */) {
+  if (cam[4] != 0.0f) {
+    float x[4], y[4];
+    const float px[4] = {0.f, (float)w, 0.f, (float)w}, py[4] = {0.f, 0.f, (float)h, (float)h};
+    for (int i = 0; i < 4; i++) undistort_point(cam, px[i], py[i], x[i], y[i]);
+    b[0] = std::min(x[0], x[2]); b[1] = std::max(x[1], x[3]);
+    b[2] = std::min(y[0], y[1]); b[3] = std::max(y[2], y[3]);
+  } else {
+    b[0] = 0.f; b[1] = (float)w; b[2] = 0.f; b[3] = (float)h;
+  }
+}
+
 }  // namespace
 
 // ==================================================================== C ABI (ctypes)
@@ -934,6 +972,49 @@ int orc_stereo_matches(void* hL, void* hR, const void* kpL, int nL, const u8* de
                        const u8* descR, float mbf, float mb, float* uRight, float* depth) {
   return compute_stereo_matches(*(Extractor*)hL, *(Extractor*)hR, (const KeyPoint*)kpL, nL, descL, (const KeyPoint*)kpR, nR,
                                 descR, mbf, mb, uRight, depth);
+}
+
+// Frame::UndistortKeyPoints: only pt changes; identity when k1 == 0
+void orc_undistort_keypoints(const void* kin, int n, const float* cam9, void* kout) {
+  const KeyPoint* a = (const KeyPoint*)kin;
+  KeyPoint* o = (KeyPoint*)kout;
+  for (int i = 0; i < n; i++) {
+    o[i] = a[i];
+    if (cam9[4] != 0.0f) undistort_point(cam9, a[i].x, a[i].y, o[i].x, o[i].y);
+  }
+}
+void orc_image_bounds(const float* cam9, int w, int h, float* bounds4) { image_bounds(cam9, w, h, bounds4); }
+
+// Frame::AssignFeaturesToGrid (Frame.cc:399-423) as CSR: cell = ix*48 + iy, items in insertion order
+void orc_assign_grid(const void* kps, int n, const float* bounds4, int* cellStart /*3073*/, int* items /*n*/) {
+  const KeyPoint* k = (const KeyPoint*)kps;
+  std::vector<float> xy(2 * (size_t)n);
+  std::vector<int> oct(n, 0);
+  for (int i = 0; i < n; i++) { xy[2 * i] = k[i].x; xy[2 * i + 1] = k[i].y; }
+  FrameView f{n, xy.data(), oct.data(), nullptr, nullptr};
+  Grid g(f, bounds4[0], bounds4[1], bounds4[2], bounds4[3]);
+  int pos = 0;
+  for (int ix = 0; ix < 64; ix++)
+    for (int iy = 0; iy < 48; iy++) {
+      cellStart[ix * 48 + iy] = pos;
+      for (int idx : g.cell[ix][iy]) items[pos++] = idx;
+    }
+  cellStart[64 * 48] = pos;
+}
+
+// Frame::GetFeaturesInArea (Frame.cc:590-670): indices in the reference's order
+int orc_features_in_area(const void* kps, int n, const float* bounds4, float x, float y, float r, int minLevel,
+                         int maxLevel, int* out, int cap) {
+  const KeyPoint* k = (const KeyPoint*)kps;
+  std::vector<float> xy(2 * (size_t)n);
+  std::vector<int> oct(n);
+  for (int i = 0; i < n; i++) { xy[2 * i] = k[i].x; xy[2 * i + 1] = k[i].y; oct[i] = k[i].octave; }
+  FrameView f{n, xy.data(), oct.data(), nullptr, nullptr};
+  Grid g(f, bounds4[0], bounds4[1], bounds4[2], bounds4[3]);
+  std::vector<int> res;
+  g.query(f, x, y, r, minLevel, maxLevel, res);
+  for (int i = 0; i < std::min((int)res.size(), cap); i++) out[i] = res[i];
+  return (int)res.size();
 }
 
 // ---- matcher

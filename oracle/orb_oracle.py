@@ -119,6 +119,35 @@ def stereo_matches(ext_left, ext_right, kps_l, desc_l, kps_r, desc_r, mbf, mb):
     return ur, dp, n
 
 
+def undistort_keypoints(kps, cam9):
+    """Frame::UndistortKeyPoints (Frame.cc:724): cam9 = (fx, fy, cx, cy, k1, k2, p1, p2, k3)."""
+    kps = np.ascontiguousarray(kps); cam = np.ascontiguousarray(cam9, np.float32)
+    out = np.zeros(len(kps), KP_DTYPE)
+    lib().orc_undistort_keypoints(_p(kps), len(kps), _p(cam), _p(out))
+    return out
+
+
+def image_bounds(cam9, w, h):
+    cam = np.ascontiguousarray(cam9, np.float32); b = np.zeros(4, np.float32)
+    lib().orc_image_bounds(_p(cam), w, h, _p(b))
+    return b
+
+
+def assign_grid(kps, bounds):
+    kps = np.ascontiguousarray(kps); b = np.ascontiguousarray(bounds, np.float32)
+    start = np.zeros(64 * 48 + 1, np.int32); items = np.zeros(max(len(kps), 1), np.int32)
+    lib().orc_assign_grid(_p(kps), len(kps), _p(b), _p(start), _p(items))
+    return start, items[:start[-1]].copy()
+
+
+def features_in_area(kps, bounds, x, y, r, min_level=-1, max_level=-1):
+    kps = np.ascontiguousarray(kps); b = np.ascontiguousarray(bounds, np.float32)
+    out = np.zeros(max(len(kps), 1), np.int32)
+    n = lib().orc_features_in_area(_p(kps), len(kps), _p(b), C.c_float(x), C.c_float(y), C.c_float(r), min_level,
+                                   max_level, _p(out), len(out))
+    return out[:n].copy()
+
+
 def resize_linear(src, dw, dh):
     src = np.ascontiguousarray(src, np.uint8)
     dst = np.zeros((dh, dw), np.uint8)

@@ -6,3 +6,4 @@ The compute path is hand-written sm_100a CUDA behind the C ABI of include/orb_b2
 from ._lib import KP_DTYPE, LIB_PATH, OrbError, lib  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
 from .matcher import FrameView, ORBmatcher, int_pipe_peak  # noqa: F401
+from . import frame  # noqa: F401,E402

@@ -27,6 +27,15 @@ class OrbLevelView(C.Structure):
     _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("step", C.c_int64)]
 
 
+class OrbCamera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("k1", C.c_float),
+                ("k2", C.c_float), ("p1", C.c_float), ("p2", C.c_float), ("k3", C.c_float)]
+
+
+AREA_QUERY_DTYPE = np.dtype([("frame", "<i4"), ("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"),
+                             ("max_level", "<i4")])
+
+
 class OrbFrameView(C.Structure):
     _fields_ = [("n", C.c_int32), ("xy", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),
                 ("descriptors", C.c_void_p)]
@@ -45,6 +54,8 @@ EXPORTS = [
     "orb_extract_stereo", "orb_extract_stereo_batch_device",
     "orb_synchronize", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_times", "orb_set_lanes", "orb_stage_level_size", "orb_stage_copy_level",
     "orb_stage_copy_blur", "orb_stage_copy_candidates", "orb_stage_copy_kept",
+    "orb_compute_image_bounds", "orb_undistort_keypoints_device", "orb_assign_features_to_grid_device",
+    "orb_get_features_in_area_device",
     "orb_descriptor_distance", "orb_matcher_create", "orb_matcher_destroy",
     "orb_search_for_initialization", "orb_match_pairs_device", "orb_match_allpairs_device",
     "orb_hamming_matrix_device", "orb_matcher_synchronize", "orb_int_pipe_peak",
@@ -88,6 +99,10 @@ def lib():
         L.orb_stage_copy_blur.argtypes = [vp, i32, i32, vp]
         L.orb_stage_copy_candidates.argtypes = [vp, i32, i32, vp, vp, vp, i32, C.POINTER(i32)]
         L.orb_stage_copy_kept.argtypes = [vp, i32, i32, vp, vp, vp, i32, C.POINTER(i32)]
+        L.orb_compute_image_bounds.argtypes = [C.POINTER(OrbCamera), i32, i32, vp]
+        L.orb_undistort_keypoints_device.argtypes = [i32, vp, vp, i32, i32, C.POINTER(OrbCamera), vp, vp]
+        L.orb_assign_features_to_grid_device.argtypes = [i32, vp, vp, i32, i32, vp, vp, vp, vp]
+        L.orb_get_features_in_area_device.argtypes = [i32, vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp]
         L.orb_descriptor_distance.argtypes = [vp, vp]
         L.orb_matcher_create.argtypes = [i32, i32, i32, C.POINTER(vp)]
         L.orb_matcher_destroy.argtypes = [vp]
