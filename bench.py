@@ -293,6 +293,61 @@ def run_ours(args, rank, world, local_rank):
               "what": "orb_extract_stereo_batch_device: extraction of both eyes + ComputeStereoMatches (Frame.cc:831)"}
     del d_st
 
+    # ---- Frame helpers after extraction: UndistortKeyPoints + AssignFeaturesToGrid,
+    # then one GetFeaturesInArea query per keypoint (window 15 px * scale of its level, as the
+    # projection matchers ask), all on the keypoints the stereo step left in HBM
+    from orb_slam2_detailed_comments_b200 import frame as F
+    from orb_slam2_detailed_comments_b200._lib import AREA_QUERY_DTYPE
+    cam = F.camera(kitti_fx, kitti_fx, W / 2.0 - 0.5, H / 2.0 - 0.5, -0.2834, 0.0739, 0.00019, 1.76e-05, 0.0)
+    bounds = F.ComputeImageBounds(cam, W, H)
+    d_un = torch.zeros_like(d_kps)
+    d_cs = torch.zeros((frames_per_step, 64 * 48 + 1), dtype=torch.int32, device=dev)
+    d_ci = torch.zeros((frames_per_step, cap), dtype=torch.int32, device=dev)
+
+    def frame_step():
+        F.UndistortKeyPoints(d_kps, d_counts, cam, d_un, device=local_rank, stream=stream)
+        F.AssignFeaturesToGrid(d_un, d_counts, bounds, d_cs, d_ci, device=local_rank, stream=stream)
+
+    frame_step()
+    hk = d_un.cpu().numpy().view(KP_DTYPE).reshape(frames_per_step, cap)
+    hc = d_counts.cpu().numpy()
+    qf = np.repeat(np.arange(frames_per_step, dtype=np.int32), hc)
+    qsel = np.concatenate([hk[f, : hc[f]] for f in range(frames_per_step)])
+    sf = ext.GetScaleFactors()
+    q = F.make_queries(qf, qsel["x"], qsel["y"], 15.0 * sf[qsel["octave"]], np.maximum(qsel["octave"] - 1, 0), qsel["octave"] + 1)
+    d_q = torch.from_numpy(q.view(np.uint8).reshape(len(q), AREA_QUERY_DTYPE.itemsize)).to(dev)
+    area_cap = 256
+    d_ao = torch.zeros((len(q), area_cap), dtype=torch.int32, device=dev)
+    d_ac = torch.zeros(len(q), dtype=torch.int32, device=dev)
+
+    def area_step():
+        F.GetFeaturesInArea(d_un, bounds, d_cs, d_ci, d_q, d_ao, d_ac, device=local_rank, stream=stream)
+
+    area_step()
+    torch.cuda.synchronize()
+    fh = {}
+    for name, fn in (("undistort_grid", frame_step), ("features_in_area", area_step)):
+        barrier()
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        f0.record(tstream)
+        for _ in range(s_steps):
+            fn()
+        f1.record(tstream)
+        torch.cuda.synchronize()
+        fh[name] = max_over_ranks(f0.elapsed_time(f1)) / s_steps
+    n_kp_total = int(hc.sum())
+    frame_helpers = {
+        "what": "UndistortKeyPoints + AssignFeaturesToGrid (Frame.cc:724, :399), then one GetFeaturesInArea (Frame.cc:590) per keypoint, device resident",
+        "camera": "KITTI focal length with EuRoC-like distortion (k1=-0.2834 k2=0.0739 p1=1.9e-4 p2=1.76e-5) so that the 5-iteration undistortion runs",
+        "undistort_grid": {"ms_per_step": fh["undistort_grid"], "frames_per_s": world * frames_per_step / (fh["undistort_grid"] * 1e-3),
+                           "keypoints_per_s": world * n_kp_total / (fh["undistort_grid"] * 1e-3),
+                           "hbm_GBps": n_kp_total * (28 + 28 + 28 + 8) / (fh["undistort_grid"] * 1e-3) / 1e9},
+        "features_in_area": {"ms_per_step": fh["features_in_area"], "queries_per_s": world * len(q) / (fh["features_in_area"] * 1e-3),
+                             "mean_results_per_query": float(d_ac.float().mean().item()), "overflowed_queries": int((d_ac > area_cap).sum().item())},
+    }
+    frame_launches = 3 * s_steps + 3
+    del d_q, d_ao, d_ac, d_un, d_cs, d_ci
+
     # ---- drop-in latency: one frame / one stereo pair per call through the reference-shaped entry
     # points (what Frame::Frame does: H2D, all kernels, D2H, synchronise), host wall clock
     lat = {}
@@ -446,8 +501,9 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs larger than L2 (%d MB per step; unique pool %d MB)" % (frames_per_step * W * H // 1000000, UNIQUE_FRAMES * W * H // 1000000), "parallelism": "frames sharded, no collective"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "orb_extract_batch_host (pinned host buffers)"},
-        "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + m_steps + (2 * world if allpairs else 0),
+        "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + frame_launches + m_steps + (2 * world if allpairs else 0),
         "stereo": stereo,
+        "frame_helpers": frame_helpers,
         "latency": lat,
         "clocks": clocks,
         "roofline": roofline,
