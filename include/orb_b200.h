@@ -254,6 +254,89 @@ int orb_hamming_matrix_device(orb_matcher* m, const uint8_t* d_a, int na, const 
 
 int orb_matcher_synchronize(orb_matcher* m, void* stream);
 
+/* ---- ORBmatcher: ordered candidate-set searches (tracking) ----------------------------
+ * SearchByProjection (local map, src/ORBmatcher.cc:72-169; last frame, :1710-1860) and SearchByBoW
+ * (keyframe -> frame, :247-420) share one structure: map points are visited IN ORDER, each takes its
+ * best (and second best) candidate among the keypoints that no earlier map point occupies, an accepted
+ * match occupies its keypoint. The device path scores all queries in parallel (four best candidates
+ * each) and then commits them in order, re-scoring only the queries whose candidates were taken. */
+
+/* `batch` current frames as these matchers read them. Device pointers, capacity-strided. */
+typedef struct orb_device_frames {
+  const orb_keypoint* keypoints_un; /* (batch, capacity)      Frame::mvKeysUn */
+  const uint8_t* descriptors;       /* (batch, capacity, 32)  Frame::mDescriptors */
+  const float* uright;              /* (batch, capacity)      Frame::mvuRight, NULL = monocular */
+  const uint8_t* occupied;          /* (batch, capacity)      1 = mvpMapPoints[i] && Observations() > 0; NULL = none */
+  const int32_t* counts;            /* (batch)                Frame::N */
+  const int32_t* cell_start;        /* (batch, 3073)          from orb_assign_features_to_grid_device */
+  const int32_t* cell_items;        /* (batch, capacity) */
+  float bounds[4];                  /* mnMinX, mnMaxX, mnMinY, mnMaxY */
+  int32_t batch, capacity;
+} orb_device_frames;
+
+/* One projected map point (32 bytes). */
+typedef struct orb_proj_query {
+  float u, v;       /* projection in the current frame (mTrackProjX/Y, or u/v of ORBmatcher.cc:1752-1753) */
+  float radius;     /* window radius r * mvScaleFactors[level]; also the tolerance on the right coordinate */
+  float ur;         /* projected right-image coordinate (mTrackProjXR, or u - mbf*invz) */
+  float angle;      /* angle of the source keypoint, for the rotation histogram */
+  int32_t min_level, max_level;  /* GetFeaturesInArea level range (max_level < 0: open) */
+  int32_t flags;    /* bit 0: query is live (mbTrackInView && !isBad / projects inside the image);
+                       bit 1: its map point has Observations() > 0, i.e. a match occupies the keypoint */
+} orb_proj_query;
+
+enum {
+  ORB_SEARCH_BEST = 0,        /* last frame (:1807): bestDist <= th */
+  ORB_SEARCH_RATIO_LEVEL = 1, /* local map (:155-158): bestDist <= th && !(bestLevel == bestLevel2 && bestDist > ratio*bestDist2) */
+  ORB_SEARCH_RATIO = 2        /* BoW (:331-336): bestDist <= th && bestDist < ratio*bestDist2 */
+};
+
+typedef struct orb_search_params {
+  int32_t mode;               /* ORB_SEARCH_* */
+  int32_t th;                 /* TH_HIGH = 100 / TH_LOW = 50 (src/ORBmatcher.cc:47-49) */
+  float nn_ratio;             /* mfNNratio */
+  int32_t check_orientation;  /* mbCheckOrientation: rotation histogram + ComputeThreeMaxima */
+} orb_search_params;
+
+/* Bytes of device scratch the two searches below need (pass the same geometry). */
+size_t orb_search_scratch_bytes(int batch, int query_capacity, int capacity);
+
+/* The projection part of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono)
+ * (src/ORBmatcher.cc:1734-1775): map point i of last frame b (d_world_pos (batch, query_capacity, 3);
+ * d_mp_flags bit 0 = mvpMapPoints[i] && !mvbOutlier[i], bit 1 = Observations() > 0) is moved by
+ * d_Tcw[b] (row-major 4x4) and projected with cam4 = {fx, fy, cx, cy}; radius = th*scale_factors[octave
+ * of mvKeys[i]]; d_direction[b]: 0 = levels octave+-1, 1 = bForward, 2 = bBackward (the caller
+ * evaluates :1723-1730 once per frame). Writes one orb_proj_query per map point. */
+int orb_project_last_frame_device(int device, const float* d_world_pos, const uint8_t* d_mp_flags,
+                                  const orb_keypoint* d_last_keypoints, const int32_t* d_last_counts, int batch,
+                                  int query_capacity, const float* d_Tcw, const int32_t* d_direction, const float* cam4,
+                                  const float* bounds4, float mbf, float th, const float* scale_factors, int nlevels,
+                                  orb_proj_query* d_queries, void* stream);
+
+/* Replaces the search loops of ORBmatcher::SearchByProjection (local map :72-169 with
+ * ORB_SEARCH_RATIO_LEVEL, last frame :1776-1860 with ORB_SEARCH_BEST). d_queries / d_query_descriptors
+ * ((batch, query_capacity[, 32]), the map points' descriptors) are visited in index order.
+ * Outputs: d_match_of_keypoint (batch, capacity) = index of the query assigned to each keypoint
+ * (CurrentFrame.mvpMapPoints) or -1; d_match_of_query (batch, query_capacity) = keypoint or -1;
+ * d_nmatches (batch) = the function's return value. */
+int orb_search_by_projection_device(int device, const orb_device_frames* frames, const orb_proj_query* d_queries,
+                                    const uint8_t* d_query_descriptors, const int32_t* d_query_counts,
+                                    int query_capacity, const orb_search_params* params, void* d_scratch,
+                                    int32_t* d_match_of_keypoint, int32_t* d_match_of_query, int32_t* d_nmatches,
+                                    void* stream);
+
+/* Replaces ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (src/ORBmatcher.cc:247-420).
+ * The DBoW2 FeatureVectors (node id -> feature indices) are passed as the node id of every feature
+ * (d_node1 / d_node2, -1 = none). Keyframe side: (batch, query_capacity) features with d_usable1 = 1
+ * where the feature has a good map point; frame side: `frames` (grid, uright, occupied unused).
+ * d_match_of_keypoint (batch, capacity) = keyframe feature index per frame keypoint
+ * (vpMapPointMatches) or -1; d_match_of_query (batch, query_capacity) = frame keypoint or -1. */
+int orb_search_by_bow_device(int device, const orb_keypoint* d_keypoints1, const uint8_t* d_descriptors1,
+                             const int32_t* d_node1, const uint8_t* d_usable1, const int32_t* d_counts1,
+                             int query_capacity, const orb_device_frames* frames, const int32_t* d_node2,
+                             const orb_search_params* params, void* d_scratch, int32_t* d_match_of_keypoint,
+                             int32_t* d_match_of_query, int32_t* d_nmatches, void* stream);
+
 /* Integer-pipe microbenchmark used for the matching roofline: independent chains of POPC
  * (what=0), LOP3 (what=1) or the matcher's own mix of 1 POPC per 4 LOP3 (what=2, reported in
  * units of (1 POPC + 4 LOP3) per second) on a full grid; returns ops/s in *ops_per_s. */

@@ -33,6 +33,7 @@
 #include <list>
 #include <thread>
 #include <utility>
+#include <map>
 #include <vector>
 
 #include "../include/orb_pattern_data.h"
@@ -859,6 +860,153 @@ void image_bounds(const float* cam, int w, int h, float* b /* minX maxX minY max
 }  // namespace
 
 // ==================================================================== C ABI (ctypes)
+// ------------------------------------------------------------------------------------------
+// Ordered candidate-set matchers: the map points / keyframe features are visited
+// in call order, every one picks its best (and second best) candidate among the keypoints that
+// are not occupied yet, and an accepted match occupies its keypoint for the later ones.
+// ------------------------------------------------------------------------------------------
+struct ProjQuery {   // one projected map point (32 bytes, same layout as orb_proj_query)
+  float u, v;        // projection in the current frame
+  float radius;      // search window, also the tolerance of the right-image coordinate
+  float ur;          // projected right-image coordinate
+  float angle;       // angle of the source keypoint (rotation histogram)
+  int minLevel, maxLevel;
+  int flags;         // bit0: usable; bit1: its map point has Observations() > 0 (occupies the keypoint)
+};
+enum { SEARCH_BEST = 0, SEARCH_RATIO_LEVEL = 1, SEARCH_RATIO = 2 };
+
+struct OrderedSearch {
+  const FrameView& F;
+  const float* uright;          // mvuRight (may be null = monocular)
+  std::vector<u8> occupied;     // F.mvpMapPoints[idx] && Observations() > 0
+  int mode, th, checkOri;
+  float ratio;
+  int* matchOfKp;               // F.mvpMapPoints as query indices
+  int* matchOfQuery;
+  int nmatches = 0;
+  std::vector<int> hist[30], histQ[30];
+
+  // the candidate loop + acceptance of one query; `cands` in the reference's visiting order
+  void visit(int q, const std::vector<int>& cands, const u8* d, float angle, float ur, float radius, bool occupies, bool stereoCheck) {
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int idx : cands) {
+      if (occupied[idx]) continue;
+      if (stereoCheck && uright && uright[idx] > 0) {
+        const float er = std::fabs(ur - uright[idx]);
+        if (er > radius) continue;
+      }
+      const int dist = hamming256(d, F.desc + (size_t)idx * 32);
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = F.octave[idx]; bestIdx = idx; }
+      else if (dist < bestDist2) { bestLevel2 = F.octave[idx]; bestDist2 = dist; }
+    }
+    if (bestDist > th) return;
+    if (mode == SEARCH_RATIO_LEVEL && bestLevel == bestLevel2 && bestDist > ratio * bestDist2) return;   // ORBmatcher.cc:158
+    if (mode == SEARCH_RATIO && !((float)bestDist < ratio * (float)bestDist2)) return;                   // ORBmatcher.cc:336
+    matchOfKp[bestIdx] = q;
+    matchOfQuery[q] = bestIdx;
+    if (occupies) occupied[bestIdx] = 1;
+    nmatches++;
+    if (checkOri) {
+      float rot = angle - F.angle[bestIdx];
+      if (rot < 0.0) rot += 360.0f;
+      int bin = (int)std::round(rot * (30 / 360.0f));
+      if (bin == 30) bin = 0;
+      if (bin >= 0 && bin < 30) { hist[bin].push_back(bestIdx); histQ[bin].push_back(q); }
+    }
+  }
+  int finish() {
+    if (checkOri) {
+      int cnt[30], a, b, c;
+      for (int i = 0; i < 30; i++) cnt[i] = (int)hist[i].size();
+      three_maxima(cnt, 30, a, b, c);
+      for (int i = 0; i < 30; i++) {
+        if (i == a || i == b || i == c) continue;
+        for (size_t j = 0; j < hist[i].size(); j++) { matchOfKp[hist[i][j]] = -1; matchOfQuery[histQ[i][j]] = -1; nmatches--; }
+      }
+    }
+    return nmatches;
+  }
+};
+
+// ORBmatcher::SearchByProjection, local map (ORBmatcher.cc:72-169, mode SEARCH_RATIO_LEVEL, th = TH_HIGH, no
+// orientation check) and last frame (:1710-1860, mode SEARCH_BEST), on queries prepared by the caller.
+int search_by_projection(const FrameView& F, const float* uright, const float bounds[4], const u8* occupied0,
+                         const ProjQuery* Q, const u8* qdesc, int nq, int mode, int th, float ratio, int checkOri,
+                         int* matchOfKp, int* matchOfQuery) {
+  OrderedSearch S{F, uright, std::vector<u8>(occupied0, occupied0 + F.n), mode, th, checkOri, ratio, matchOfKp, matchOfQuery};
+  for (int i = 0; i < F.n; i++) matchOfKp[i] = -1;
+  Grid grid(F, bounds[0], bounds[1], bounds[2], bounds[3]);
+  std::vector<int> cands;
+  for (int q = 0; q < nq; q++) {
+    matchOfQuery[q] = -1;
+    if (!(Q[q].flags & 1)) continue;
+    grid.query(F, Q[q].u, Q[q].v, Q[q].radius, Q[q].minLevel, Q[q].maxLevel, cands);
+    if (cands.empty()) continue;
+    S.visit(q, cands, qdesc + (size_t)q * 32, Q[q].angle, Q[q].ur, Q[q].radius, (Q[q].flags & 2) != 0, true);
+  }
+  return S.finish();
+}
+
+// The projection part of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono), ORBmatcher.cc:1734-1775.
+// x3Dc = Rcw*x3Dw + tcw follows cv::gemm's 3x3 float special case: float products and sums in index order,
+// then the addend (checked against cv2.gemm in tests/test_oracle_search.py). dir: 0 = +-1 level, 1 = forward, 2 = backward.
+void project_last_frame(int n1, const float* Xw, const u8* mpFlags, const int* octave1, const float* angle1, const float* Tcw,
+                        const float* cam4, const float* bounds4, float mbf, float th, const float* scaleFactors, int dir,
+                        ProjQuery* out) {
+  const float fx = cam4[0], fy = cam4[1], cx = cam4[2], cy = cam4[3];
+  for (int i = 0; i < n1; i++) {
+    ProjQuery& q = out[i];
+    q = ProjQuery{0.f, 0.f, 0.f, 0.f, angle1[i], 0, -1, 0};
+    if (!(mpFlags[i] & 1)) continue;
+    const float* X = Xw + 3 * (size_t)i;
+    float c[3];
+    for (int r = 0; r < 3; r++) {
+      const float t = Tcw[4 * r] * X[0] + Tcw[4 * r + 1] * X[1] + Tcw[4 * r + 2] * X[2];
+      c[r] = t + Tcw[4 * r + 3];
+    }
+    const float xc = c[0], yc = c[1];
+    const float invzc = (float)(1.0 / c[2]);
+    if (invzc < 0) continue;
+    const float u = fx * xc * invzc + cx;
+    const float v = fy * yc * invzc + cy;
+    if (u < bounds4[0] || u > bounds4[1]) continue;
+    if (v < bounds4[2] || v > bounds4[3]) continue;
+    const int oct = octave1[i];
+    q.u = u; q.v = v;
+    q.radius = th * scaleFactors[oct];
+    q.ur = u - mbf * invzc;
+    if (dir == 1) { q.minLevel = oct; q.maxLevel = -1; }
+    else if (dir == 2) { q.minLevel = 0; q.maxLevel = oct; }
+    else { q.minLevel = oct - 1; q.maxLevel = oct + 1; }
+    q.flags = 1 | (mpFlags[i] & 2);
+  }
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...), ORBmatcher.cc:247-420. The DBoW2 FeatureVectors are given as
+// the node id of every feature (-1 = none): FeatureVector = std::map<node, indices in feature order>.
+// usable1[i]: KF feature i has a good map point. Output: matchOfKp = vpMapPointMatches as KF feature indices.
+int search_by_bow(const FrameView& KF, const int* node1, const u8* usable1, const FrameView& F, const int* node2, int th,
+                  float ratio, int checkOri, int* matchOfKp, int* matchOfQuery) {
+  OrderedSearch S{F, nullptr, std::vector<u8>(F.n, 0), SEARCH_RATIO, th, checkOri, ratio, matchOfKp, matchOfQuery};
+  for (int i = 0; i < F.n; i++) matchOfKp[i] = -1;
+  for (int i = 0; i < KF.n; i++) matchOfQuery[i] = -1;
+  std::map<int, std::vector<int>> fv1, fv2;
+  for (int i = 0; i < KF.n; i++) if (node1[i] >= 0) fv1[node1[i]].push_back(i);
+  for (int i = 0; i < F.n; i++) if (node2[i] >= 0) fv2[node2[i]].push_back(i);
+  auto it1 = fv1.begin(), it2 = fv2.begin();
+  while (it1 != fv1.end() && it2 != fv2.end()) {
+    if (it1->first == it2->first) {
+      for (int i1 : it1->second) {
+        if (!usable1[i1]) continue;
+        S.visit(i1, it2->second, KF.desc + (size_t)i1 * 32, KF.angle[i1], 0.f, 0.f, true, false);
+      }
+      ++it1; ++it2;
+    } else if (it1->first < it2->first) it1 = fv1.lower_bound(it2->first);
+    else it2 = fv2.lower_bound(it1->first);
+  }
+  return S.finish();
+}
+
 extern "C" {
 
 void* orc_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
@@ -1032,6 +1180,35 @@ int orc_search_for_initialization(int n1, const float* xy1, const int* oct1, con
   FrameView F1{n1, xy1, oct1, ang1, desc1}, F2{n2, xy2, oct2, ang2, desc2};
   return search_for_initialization(F1, F2, bounds4, prevMatched, matches12, windowSize, nnratio, checkOri, mode,
                                    bestOut, secondOut);
+}
+
+// ---- ordered candidate-set matchers
+static FrameView view_of(const void* kps, int n, const u8* desc, std::vector<float>& xy, std::vector<int>& oct, std::vector<float>& ang) {
+  const KeyPoint* k = (const KeyPoint*)kps;
+  xy.resize(2 * (size_t)n); oct.resize(n); ang.resize(n);
+  for (int i = 0; i < n; i++) { xy[2 * i] = k[i].x; xy[2 * i + 1] = k[i].y; oct[i] = k[i].octave; ang[i] = k[i].angle; }
+  return FrameView{n, xy.data(), oct.data(), ang.data(), desc};
+}
+int orc_search_by_projection(const void* kpsUn, int n, const u8* desc, const float* uright, const float* bounds4,
+                             const u8* occupied0, const void* queries, const u8* qdesc, int nq, int mode, int th,
+                             float ratio, int checkOri, int* matchOfKp, int* matchOfQuery) {
+  std::vector<float> xy, ang; std::vector<int> oct;
+  FrameView F = view_of(kpsUn, n, desc, xy, oct, ang);
+  return search_by_projection(F, uright, bounds4, occupied0, (const ProjQuery*)queries, qdesc, nq, mode, th, ratio, checkOri,
+                              matchOfKp, matchOfQuery);
+}
+void orc_project_last_frame(int n1, const float* Xw, const u8* mpFlags, const void* kps1, const float* Tcw, const float* cam4,
+                            const float* bounds4, float mbf, float th, const float* scaleFactors, int dir, void* out) {
+  const KeyPoint* k = (const KeyPoint*)kps1;
+  std::vector<int> oct(n1); std::vector<float> ang(n1);
+  for (int i = 0; i < n1; i++) { oct[i] = k[i].octave; ang[i] = k[i].angle; }
+  project_last_frame(n1, Xw, mpFlags, oct.data(), ang.data(), Tcw, cam4, bounds4, mbf, th, scaleFactors, dir, (ProjQuery*)out);
+}
+int orc_search_by_bow(const void* kps1, int n1, const u8* desc1, const int* node1, const u8* usable1, const void* kps2, int n2,
+                      const u8* desc2, const int* node2, int th, float ratio, int checkOri, int* matchOfKp, int* matchOfQuery) {
+  std::vector<float> xy1, ang1, xy2, ang2; std::vector<int> oct1, oct2;
+  FrameView A = view_of(kps1, n1, desc1, xy1, oct1, ang1), B = view_of(kps2, n2, desc2, xy2, oct2, ang2);
+  return search_by_bow(A, node1, usable1, B, node2, th, ratio, checkOri, matchOfKp, matchOfQuery);
 }
 
 // All-pairs keyframe matching count (config 5): for keyframe pair (i,j), the number of rows

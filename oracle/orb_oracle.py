@@ -253,6 +253,51 @@ def search_for_initialization(xy1, oct1, ang1, desc1, xy2, oct2, ang2, desc2, bo
     return n, m12, prev, best, second
 
 
+PROJ_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("angle", "<f4"),
+                             ("min_level", "<i4"), ("max_level", "<i4"), ("flags", "<i4")])
+SEARCH_BEST, SEARCH_RATIO_LEVEL, SEARCH_RATIO = 0, 1, 2
+
+
+def search_by_projection(kps_un, desc, uright, bounds, occupied0, queries, qdesc, mode, th, ratio=0.0, check_ori=False):
+    """ORBmatcher::SearchByProjection on prepared queries (ORBmatcher.cc:72 local map = SEARCH_RATIO_LEVEL,
+    :1710 last frame = SEARCH_BEST). -> (nmatches, match_of_keypoint, match_of_query)."""
+    kps_un = np.ascontiguousarray(kps_un); desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE); qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    n, nq = len(kps_un), len(queries)
+    ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+    occ = np.ascontiguousarray(occupied0, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32)
+    mk = np.full(max(n, 1), -1, np.int32); mq = np.full(max(nq, 1), -1, np.int32)
+    nm = lib().orc_search_by_projection(_p(kps_un), n, _p(desc), _p(ur) if ur is not None else None, _p(b), _p(occ), _p(queries),
+                                        _p(qdesc), nq, int(mode), int(th), C.c_float(ratio), int(check_ori), _p(mk), _p(mq))
+    return nm, mk[:n], mq[:nq]
+
+
+def project_last_frame(Xw, mp_flags, kps1, Tcw, cam4, bounds, mbf, th, scale_factors, direction):
+    """Projection part of SearchByProjection(CurrentFrame, LastFrame, ...), ORBmatcher.cc:1734-1775 -> queries."""
+    Xw = np.ascontiguousarray(Xw, np.float32); fl = np.ascontiguousarray(mp_flags, np.uint8); kps1 = np.ascontiguousarray(kps1)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16); cam = np.ascontiguousarray(cam4, np.float32)
+    b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    out = np.zeros(len(kps1), PROJ_QUERY_DTYPE)
+    lib().orc_project_last_frame(len(kps1), _p(Xw), _p(fl), _p(kps1), _p(T), _p(cam), _p(b), C.c_float(mbf), C.c_float(th), _p(sf),
+                                 int(direction), _p(out))
+    return out
+
+
+def search_by_bow(kps1, desc1, node1, usable1, kps2, desc2, node2, th=50, ratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...), ORBmatcher.cc:247. -> (nmatches, match_of_keypoint (over frame 2,
+    values = keyframe feature indices), match_of_query (over keyframe features))."""
+    kps1 = np.ascontiguousarray(kps1); kps2 = np.ascontiguousarray(kps2)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    node1 = np.ascontiguousarray(node1, np.int32); node2 = np.ascontiguousarray(node2, np.int32)
+    us = np.ascontiguousarray(usable1, np.uint8)
+    n1, n2 = len(kps1), len(kps2)
+    mk = np.full(max(n2, 1), -1, np.int32); mq = np.full(max(n1, 1), -1, np.int32)
+    nm = lib().orc_search_by_bow(_p(kps1), n1, _p(desc1), _p(node1), _p(us), _p(kps2), n2, _p(desc2), _p(node2), int(th),
+                                 C.c_float(ratio), int(check_ori), _p(mk), _p(mq))
+    return nm, mk[:n2], mq[:n1]
+
+
 def allpairs_counts(desc, nnratio=0.9, row_begin=0, row_end=None):
     desc = np.ascontiguousarray(desc, np.uint8)
     nkf, nd, _ = desc.shape

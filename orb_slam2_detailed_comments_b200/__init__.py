@@ -7,3 +7,4 @@ from ._lib import KP_DTYPE, LIB_PATH, OrbError, lib  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
 from .matcher import FrameView, ORBmatcher, int_pipe_peak  # noqa: F401
 from . import frame  # noqa: F401,E402
+from . import search  # noqa: F401,E402

@@ -36,6 +36,22 @@ AREA_QUERY_DTYPE = np.dtype([("frame", "<i4"), ("x", "<f4"), ("y", "<f4"), ("r",
                              ("max_level", "<i4")])
 
 
+PROJ_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("angle", "<f4"),
+                             ("min_level", "<i4"), ("max_level", "<i4"), ("flags", "<i4")])
+assert PROJ_QUERY_DTYPE.itemsize == 32
+ORB_SEARCH_BEST, ORB_SEARCH_RATIO_LEVEL, ORB_SEARCH_RATIO = 0, 1, 2
+
+
+class OrbDeviceFrames(C.Structure):
+    _fields_ = [("keypoints_un", C.c_void_p), ("descriptors", C.c_void_p), ("uright", C.c_void_p), ("occupied", C.c_void_p),
+                ("counts", C.c_void_p), ("cell_start", C.c_void_p), ("cell_items", C.c_void_p), ("bounds", C.c_float * 4),
+                ("batch", C.c_int32), ("capacity", C.c_int32)]
+
+
+class OrbSearchParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("th", C.c_int32), ("nn_ratio", C.c_float), ("check_orientation", C.c_int32)]
+
+
 class OrbFrameView(C.Structure):
     _fields_ = [("n", C.c_int32), ("xy", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),
                 ("descriptors", C.c_void_p)]
@@ -59,6 +75,8 @@ EXPORTS = [
     "orb_descriptor_distance", "orb_matcher_create", "orb_matcher_destroy",
     "orb_search_for_initialization", "orb_match_pairs_device", "orb_match_allpairs_device",
     "orb_hamming_matrix_device", "orb_matcher_synchronize", "orb_int_pipe_peak",
+    "orb_search_scratch_bytes", "orb_project_last_frame_device", "orb_search_by_projection_device",
+    "orb_search_by_bow_device",
 ]
 
 _lib = None
@@ -113,6 +131,13 @@ def lib():
         L.orb_hamming_matrix_device.argtypes = [vp, vp, i32, vp, i32, vp, vp]
         L.orb_matcher_synchronize.argtypes = [vp, vp]
         L.orb_int_pipe_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
+        L.orb_search_scratch_bytes.restype = sz
+        L.orb_search_scratch_bytes.argtypes = [i32, i32, i32]
+        L.orb_project_last_frame_device.argtypes = [i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, f32, f32, vp, i32, vp, vp]
+        L.orb_search_by_projection_device.argtypes = [i32, C.POINTER(OrbDeviceFrames), vp, vp, vp, i32, C.POINTER(OrbSearchParams),
+                                                      vp, vp, vp, vp, vp]
+        L.orb_search_by_bow_device.argtypes = [i32, vp, vp, vp, vp, vp, i32, C.POINTER(OrbDeviceFrames), vp,
+                                               C.POINTER(OrbSearchParams), vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

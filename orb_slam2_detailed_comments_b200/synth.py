@@ -76,3 +76,54 @@ def correlated_descriptor_pair(n, seed, flip_prob=0.06, outlier_frac=0.3):
     inv = np.empty(n, np.int64); inv[np.arange(n)] = perm
     angB = ((angA[perm] - 12.0 + rng.normal(0, 3.0, n)) % 360.0).astype(np.float32)
     return A, B, angA, angB
+
+
+def tracking_scene(n_cur, n_last, seed, w=1241, h=376, fx=718.856, cx=607.1928, cy=185.2157, bf=386.1448,
+                   noise_px=3.0, flip_bits=24, frac_mapped=0.8, frac_unobserved=0.05, frac_occupied=0.05, nlevels=8):
+    """Synthetic state for the projection / BoW matchers: a current frame of n_cur keypoints and a last
+    frame of n_last keypoints whose map points project close to current keypoints (position noise
+    `noise_px`, descriptor = current descriptor with up to `flip_bits` flipped bits), so that windows
+    hold several candidates, some map points compete for one keypoint and ties occur. numpy only."""
+    from ._lib import KP_DTYPE
+    rng = np.random.RandomState(seed & 0x7FFFFFFF)
+    f32 = np.float32
+    cur = np.zeros(n_cur, KP_DTYPE)
+    cur["x"] = (16 + rng.rand(n_cur) * (w - 32)).astype(f32); cur["y"] = (16 + rng.rand(n_cur) * (h - 32)).astype(f32)
+    cur["octave"] = np.minimum(rng.geometric(0.35, n_cur) - 1, nlevels - 1); cur["angle"] = (rng.rand(n_cur) * 360).astype(f32)
+    cur["size"] = 31; cur["class_id"] = -1
+    cur_desc = rng.randint(0, 256, (n_cur, 32)).astype(np.uint8)
+    depth_cur = (4 + rng.rand(n_cur) * 40).astype(f32)
+    uright = np.where(rng.rand(n_cur) < 0.7, cur["x"] - f32(bf) / depth_cur, -1).astype(f32)
+    occupied0 = (rng.rand(n_cur) < frac_occupied).astype(np.uint8)
+    # pose: small rotation about y, translation mostly along z
+    a = 0.02 * rng.randn()
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    t = np.array([0.05 * rng.randn(), 0.02 * rng.randn(), -0.6 + 0.1 * rng.randn()])
+    Tcw = np.eye(4, dtype=f32); Tcw[:3, :3] = R.astype(f32); Tcw[:3, 3] = t.astype(f32)
+    # last frame: every keypoint follows one current keypoint (several may follow the same one)
+    src = rng.randint(0, n_cur, n_last)
+    last = np.zeros(n_last, KP_DTYPE)
+    last["octave"] = np.clip(cur["octave"][src] + rng.randint(-1, 2, n_last), 0, nlevels - 1)
+    rot = 10.0 * rng.randn() + rng.randn(n_last) * 3.0
+    wild = rng.rand(n_last) < 0.1
+    last["angle"] = np.mod(cur["angle"][src] + rot + wild * rng.rand(n_last) * 360, 360).astype(f32)
+    last["size"] = 31; last["class_id"] = -1
+    u = cur["x"][src] + rng.randn(n_last) * noise_px; v = cur["y"][src] + rng.randn(n_last) * noise_px
+    z = depth_cur[src].astype(np.float64) * (1 + 0.01 * rng.randn(n_last))
+    behind = rng.rand(n_last) < 0.02
+    z = np.where(behind, -z, z)
+    Xc = np.stack([(u - cx) * z / fx, (v - cy) * z / fx, z], 1)
+    Xw = ((Xc - t[None, :]) @ R).astype(f32)           # R^T (Xc - t)
+    last["x"] = u.astype(f32); last["y"] = v.astype(f32)
+    mp_desc = cur_desc[src].copy()
+    nflip = rng.randint(0, flip_bits + 1, n_last)
+    for i in range(n_last):
+        bits = rng.randint(0, 256, nflip[i])
+        np.bitwise_xor.at(mp_desc[i], bits >> 3, (1 << (bits & 7)).astype(np.uint8))
+    dup = rng.rand(n_last) < 0.05                      # exact duplicates: distance ties between candidates
+    mp_desc[dup] = cur_desc[src[dup]]
+    flags = (rng.rand(n_last) < frac_mapped).astype(np.uint8)
+    flags |= ((rng.rand(n_last) >= frac_unobserved).astype(np.uint8) << 1)
+    return {"cur": cur, "cur_desc": cur_desc, "uright": uright, "occupied0": occupied0, "Tcw": Tcw, "last": last, "Xw": Xw,
+            "mp_desc": mp_desc, "mp_flags": flags, "cam4": np.array([fx, fx, cx, cy], f32),
+            "bounds": np.array([0, w, 0, h], f32), "mbf": f32(bf), "mb": f32(bf / fx), "src": src}
