@@ -348,6 +348,65 @@ def run_ours(args, rank, world, local_rank):
     frame_launches = 3 * s_steps + 3
     del d_q, d_ao, d_ac, d_un, d_cs, d_ci
 
+    # ---- tracking matchers: SearchByProjection(CurrentFrame, LastFrame) on 2000 x 2000 frames,
+    # projection + grid + search, device resident; batch throughput and single-frame latency
+    from orb_slam2_detailed_comments_b200 import search as SR
+    from orb_slam2_detailed_comments_b200.synth import tracking_scene
+    tr_B, tr_n = 256, 2000
+    tr_uniq = [tracking_scene(tr_n, tr_n, 4242 + 17 * rank + i, w=W, h=H, distinct=0.97) for i in range(8)]
+    sfs = ext.GetScaleFactors()
+
+    def tile(key, kp=False):
+        a = np.stack([sc_[key].view(np.uint8).reshape(tr_n, 28) if kp else np.ascontiguousarray(sc_[key]) for sc_ in tr_uniq])
+        return torch.from_numpy(a).to(dev).repeat((tr_B // len(tr_uniq),) + (1,) * (a.ndim - 1)).contiguous()
+
+    t_kps = tile("cur", True); t_desc = tile("cur_desc"); t_ur = tile("uright"); t_occ = tile("occupied0")
+    t_last = tile("last", True); t_Xw = tile("Xw"); t_fl = tile("mp_flags"); t_mpd = tile("mp_desc")
+    t_T = torch.from_numpy(np.stack([sc_["Tcw"] for sc_ in tr_uniq])).to(dev).repeat(tr_B // len(tr_uniq), 1, 1).contiguous()
+    t_cnt = torch.full((tr_B,), tr_n, dtype=torch.int32, device=dev)
+    t_dir = torch.zeros(tr_B, dtype=torch.int32, device=dev)
+    t_cs = torch.zeros((tr_B, 64 * 48 + 1), dtype=torch.int32, device=dev); t_ci = torch.zeros((tr_B, tr_n), dtype=torch.int32, device=dev)
+    t_q = torch.zeros((tr_B, tr_n, 32), dtype=torch.uint8, device=dev)
+    t_mk = torch.zeros((tr_B, tr_n), dtype=torch.int32, device=dev); t_mq = torch.zeros((tr_B, tr_n), dtype=torch.int32, device=dev)
+    t_nm = torch.zeros(tr_B, dtype=torch.int32, device=dev)
+    t_scr = torch.zeros(SR.scratch_bytes(tr_B, tr_n, tr_n), dtype=torch.uint8, device=dev)
+    tb = tr_uniq[0]["bounds"]
+
+    def make_track_step(nb):
+        # arguments are prepared once: the timed loop only issues the four C-ABI calls
+        kps_, cnt_, cs_, ci_, Xw_, fl_, last_, T_, dir_, q_ = (t_kps[:nb], t_cnt[:nb], t_cs[:nb], t_ci[:nb], t_Xw[:nb], t_fl[:nb],
+                                                                  t_last[:nb], t_T[:nb], t_dir[:nb], t_q[:nb])
+        mpd_, mk_, mq_, nm_ = t_mpd[:nb], t_mk[:nb], t_mq[:nb], t_nm[:nb]
+        fr = SR.device_frames(kps_, t_desc[:nb], cnt_, tb, cs_, ci_, t_ur[:nb], t_occ[:nb])
+
+        def step():
+            F.AssignFeaturesToGrid(kps_, cnt_, tb, cs_, ci_, device=local_rank, stream=stream)
+            SR.ProjectLastFrame(Xw_, fl_, last_, cnt_, T_, dir_, tr_uniq[0]["cam4"], tb, tr_uniq[0]["mbf"], 15.0, sfs, q_,
+                                device=local_rank, stream=stream)
+            SR.SearchByProjection(fr, q_, mpd_, cnt_, SR.ORB_SEARCH_BEST, SR.TH_HIGH, 0.9, True, t_scr, mk_, mq_, nm_,
+                                  device=local_rank, stream=stream)
+        return step
+
+    tracking = {"what": "AssignFeaturesToGrid + projection of 2000 last-frame map points + SearchByProjection(CurrentFrame, LastFrame, th=15) "
+                        "(ORBmatcher.cc:1710) per frame, device resident; 4 launches per call",
+                "scene": "synthetic: 2000 keypoints, 2000 map points of which 97 % follow a keypoint of their own (3 px noise), 8 unique scenes tiled"}
+    for name, nb, reps in (("batch", tr_B, 5), ("single_frame", 1, 50)):
+        track_step = make_track_step(nb)
+        for _ in range(3):
+            track_step()
+        barrier()
+        k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+        k0.record(tstream)
+        for _ in range(reps):
+            track_step()
+        k1.record(tstream)
+        torch.cuda.synchronize()
+        ms = max_over_ranks(k0.elapsed_time(k1)) / reps
+        tracking[name] = {"frames": nb, "ms": ms, "frames_per_s": world * nb / (ms * 1e-3)}
+    tracking["mean_matches"] = float(t_nm.float().mean().item())
+    track_launches = 4 * (5 + 50 + 6)
+    del t_kps, t_desc, t_last, t_Xw, t_mpd, t_q, t_scr
+
     # ---- drop-in latency: one frame / one stereo pair per call through the reference-shaped entry
     # points (what Frame::Frame does: H2D, all kernels, D2H, synchronise), host wall clock
     lat = {}
@@ -486,6 +545,11 @@ def run_ours(args, rank, world, local_rank):
         t1 = time.perf_counter()
         O.match_batch_mt(dsc[: 2 * min(pairs, uniq)], ang[: 2 * min(pairs, uniq)], 0.9, nthreads=cores)
         dtm = time.perf_counter() - t1
+        t2 = time.perf_counter()
+        for sc_ in tr_uniq[:4]:
+            q_ = O.project_last_frame(sc_["Xw"], sc_["mp_flags"], sc_["last"], sc_["Tcw"], sc_["cam4"], sc_["bounds"], sc_["mbf"], 15.0, sfs, 0)
+            O.search_by_projection(sc_["cur"], sc_["cur_desc"], sc_["uright"], sc_["bounds"], sc_["occupied0"], q_, sc_["mp_desc"], 0, 100, 0.9, True)
+        tracking["cpu_oracle_ms_per_frame_1_thread"] = (time.perf_counter() - t2) / 4 * 1e3
         cpu = {"value": sample / dt, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "%d %s-shape frames, one frame per thread, CPU oracle (reference needs OpenCV C++: unbuildable here)" % (sample, args.workload),
                "matching_cmp_per_s": min(pairs, uniq) * MATCH_N * MATCH_N / dtm}
@@ -501,9 +565,10 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs larger than L2 (%d MB per step; unique pool %d MB)" % (frames_per_step * W * H // 1000000, UNIQUE_FRAMES * W * H // 1000000), "parallelism": "frames sharded, no collective"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "orb_extract_batch_host (pinned host buffers)"},
-        "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + frame_launches + m_steps + (2 * world if allpairs else 0),
+        "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + frame_launches + track_launches + m_steps + (2 * world if allpairs else 0),
         "stereo": stereo,
         "frame_helpers": frame_helpers,
+        "tracking": tracking,
         "latency": lat,
         "clocks": clocks,
         "roofline": roofline,

@@ -4,19 +4,21 @@
 //
 // The reference walks the map points in order; each one takes the best candidate keypoint that no earlier
 // map point occupies. That chain is split in two:
-//   k_search_scan    one WARP per query, all queries of all frames in parallel: the candidates are
-//                    enumerated in the reference's visiting order (lanes = candidates), filtered against the
-//                    frame's initial occupancy / stereo coordinate, and the FOUR smallest keys
-//                    (distance << 22 | visiting rank) are kept (redux.sync min + ballot).
-//   k_search_commit  one warp per frame walks the queries in order, 32 per step. A query whose stored
-//                    candidates lost nothing to earlier commits is final; one that lost candidates falls
-//                    back on its 3rd / 4th stored candidate, and only if those run out is it re-scored
-//                    exactly against the current occupancy. Same-step dependencies are found with a
-//                    shared-memory tag per keypoint (atomicMin of the lane) and resolved in lane order.
+//   k_search_scan    EIGHT lanes per query (windows hold ~5-30 candidates), all queries of all frames in
+//                    parallel: the candidates are enumerated in the reference's visiting order (lanes =
+//                    candidates), filtered against the frame's initial occupancy / stereo coordinate, and
+//                    the FOUR smallest keys (distance << 22 | visiting rank) are kept (redux.sync min on the
+//                    8-lane group; the rank inside the key names the owner lane).
+//   k_search_commit  one CTA per frame solves the in-order dependency as a fixed point: the picks of all
+//                    queries are re-chosen in parallel sweeps against "tag[idx] = smallest occupying query
+//                    that picks idx" until a sweep changes nothing (triangular system: the fixed point is the
+//                    sequential result; 1 + longest displacement chain sweeps). A query that lost stored
+//                    candidates falls back on its 3rd / 4th, and only if those run out is it re-scored.
 // The two smallest keys by (distance, visiting order) are exactly the reference's (best, second best):
 // `dist < bestDist` / `else if (dist < bestDist2)` with demotion keeps the lexicographic top two.
 // Integer-pipe work (LOP3 / POPC / REDUX); no tensor cores by design.
 #include <algorithm>
+#include <climits>
 #include <cstring>
 
 #include "orb_common.cuh"
@@ -65,34 +67,45 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
   return __popc(ones) + __popc(x7) + 2 * __popc(twos) + 4 * __popc(fours);
 }
 
-// The four smallest (distance, visiting rank) keys among candidates t = 0..total-1; idxOf(t) returns the
-// keypoint index or -1 when the candidate is filtered out before the occupancy test.
-template <class IdxFn, class OccFn>
-__device__ __forceinline__ void warp_top4(int total, IdxFn idxOf, OccFn occ, const uint4 q0, const uint4 q1, const u8* desc,
-                                          const float* uright, float ur, float radius, int lane, Top4& T) {
+// Candidate words: bits 0-15 keypoint index, bits 16-23 its octave, bit 30 (first word only) "the query occupies".
+constexpr unsigned kWordIdx = 0xffffu, kWordOccupies = 1u << 30;
+__device__ __forceinline__ int word_idx(int w) { return w & (int)kWordIdx; }
+__device__ __forceinline__ int word_oct(int w) { return (w >> 16) & 0xff; }
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  return G == 32 ? kFull : (((1u << G) - 1u) << (lane & ~(G - 1)));
+}
+
+// The four smallest (distance, visiting rank) keys among candidates t = 0..total-1, G lanes per query;
+// wordOf(t) returns the candidate word or -1 when the candidate is filtered out before the occupancy test.
+template <int G, class WordFn, class OccFn>
+__device__ __forceinline__ void group_top4(int total, WordFn wordOf, OccFn occ, const uint4 q0, const uint4 q1, const u8* desc,
+                                           const float* uright, float ur, float radius, int lane, Top4& T) {
+  const unsigned gm = group_mask<G>(lane);
+  const int gl = lane & (G - 1);
   top4_clear(T);
-  for (int t0 = 0; t0 < total; t0 += 32) {
-    const int t = t0 + lane;
+  for (int t0 = 0; t0 < total; t0 += G) {
+    const int t = t0 + gl;
     unsigned key = kNoKey;
-    int idx = -1;
+    int w = -1;
     if (t < total) {
-      idx = idxOf(t);
-      if (idx >= 0 && !occ(idx)) {
+      w = wordOf(t);
+      if (w >= 0 && !occ(word_idx(w))) {
         bool ok = true;
         if (uright) {   // ORBmatcher.cc:125-130 / :1792-1798
-          const float r = uright[idx];
+          const float r = uright[word_idx(w)];
           if (r > 0.f && fabsf(__fsub_rn(ur, r)) > radius) ok = false;
         }
-        if (ok) key = ((unsigned)hamming256(q0, q1, desc + (size_t)idx * 32) << 22) | (unsigned)t;
+        if (ok) key = ((unsigned)hamming256(q0, q1, desc + (size_t)word_idx(w) * 32) << 22) | (unsigned)t;
       }
     }
     for (;;) {
-      const unsigned m = __reduce_min_sync(kFull, key);
+      const unsigned m = __reduce_min_sync(gm, key);
       if (m >= T.k[3]) break;
-      const int owner = __ffs(__ballot_sync(kFull, key == m)) - 1;
-      const int mi = __shfl_sync(kFull, idx, owner);
-      top4_insert(T, m, mi);
-      if (lane == owner) key = kNoKey;
+      const int mw = __shfl_sync(gm, w, (int)(m & 0x3fffffu) - t0, G);   // the rank in the key names the owner lane
+      top4_insert(T, m, mw);
+      if (key == m) key = kNoKey;
     }
   }
 }
@@ -104,8 +117,11 @@ struct WindowSegs {
   int cum[kMaxCols + 1];   // candidates before column c
 };
 
+template <int G>
 __device__ __forceinline__ int window_setup(const orb_proj_query& Q, const float* B4, float invW, float invH, const int* start,
                                             WindowSegs& W, int lane) {
+  const unsigned gm = group_mask<G>(lane);
+  const int gl = lane & (G - 1);
   const float x = Q.u, y = Q.v, r = Q.radius;
   const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, B4[0]), r), invW)));
   const int cx1 = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, B4[0]), r), invW)));
@@ -114,8 +130,8 @@ __device__ __forceinline__ int window_setup(const orb_proj_query& Q, const float
   if (!(cx0 < kGridCols && cx1 >= 0 && cy0 < kGridRows && cy1 >= 0) || cx1 < cx0 || cy1 < cy0) return 0;
   const int ncols = cx1 - cx0 + 1;
   int run = 0;
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
-    const int c = c0 + lane;
+  for (int c0 = 0; c0 < ncols; c0 += G) {
+    const int c = c0 + gl;
     int b = 0, len = 0;
     if (c < ncols) {
       b = start[(cx0 + c) * kGridRows + cy0];
@@ -123,19 +139,19 @@ __device__ __forceinline__ int window_setup(const orb_proj_query& Q, const float
     }
     int incl = len;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(kFull, incl, o);
-      if (lane >= o) incl += t;
+    for (int o = 1; o < G; o <<= 1) {
+      const int t = __shfl_up_sync(gm, incl, o, G);
+      if (gl >= o) incl += t;
     }
     if (c < ncols) { W.seg[c] = b; W.cum[c] = run + incl - len; }
-    run += __shfl_sync(kFull, incl, 31);
+    run += __shfl_sync(gm, incl, G - 1, G);
   }
-  if (lane == 0) W.cum[ncols] = run;
-  __syncwarp();
+  if (gl == 0) W.cum[ncols] = run;
+  __syncwarp(gm);
   return run;
 }
 
-// candidate t of the window -> keypoint index, or -1 if the level / circle test rejects it
+// candidate t of the window -> candidate word, or -1 if the level / circle test rejects it
 __device__ __forceinline__ int window_candidate(int t, const WindowSegs& W, const int* items, const orb_keypoint* K,
                                                 const orb_proj_query& Q, float r2) {
   int c = 0;
@@ -148,7 +164,7 @@ __device__ __forceinline__ int window_candidate(int t, const WindowSegs& W, cons
     if (Q.max_level >= 0 && oct > Q.max_level) return -1;
   }
   const float dx = __fsub_rn(kx, Q.u), dy = __fsub_rn(ky, Q.v);
-  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < r2 ? idx : -1;
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < r2 ? (idx | ((oct & 0xff) << 16)) : -1;
 }
 
 struct SearchArgs {
@@ -169,11 +185,15 @@ struct SearchArgs {
   int* matchOfKp; int* matchOfQuery; int* nmatches;
 };
 
-// ---- pass 1: score every query against the frame's initial state
+// ---- pass 1: score every query against the frame's initial state, kScanGroup lanes per query
+constexpr int kScanGroup = 8;
+constexpr int kScanQueries = 32 * kScanWarps / kScanGroup;   // queries per CTA
+
 __global__ void __launch_bounds__(32 * kScanWarps) k_search_scan(const SearchArgs A) {
-  __shared__ WindowSegs segs[kScanWarps];
-  const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int q = blockIdx.x * kScanWarps + wid;
+  constexpr int G = kScanGroup;
+  __shared__ WindowSegs segs[kScanQueries];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, grp = threadIdx.x / G, gl = lane & (G - 1);
+  const int q = blockIdx.x * kScanQueries + grp;
   const int nq = A.bow ? A.meta[4 * b] : A.qcounts[b];
   if (q >= nq) return;
   const orb_keypoint* K = A.kps + (size_t)b * A.cap;
@@ -181,18 +201,20 @@ __global__ void __launch_bounds__(32 * kScanWarps) k_search_scan(const SearchArg
   const u8* occ0 = A.occupied ? A.occupied + (size_t)b * A.cap : nullptr;
   Top4 T;
   top4_clear(T);
+  unsigned occupies = kWordOccupies;
   if (!A.bow) {
     const orb_proj_query Q = A.queries[(size_t)b * A.qcap + q];
+    if (!(Q.flags & 2)) occupies = 0;
     if (Q.flags & 1) {
-      const int total = window_setup(Q, A.b4, A.invW, A.invH, A.cellStart + (size_t)b * (kGridCells + 1), segs[wid], lane);
+      WindowSegs& W = segs[grp];
+      const int total = window_setup<G>(Q, A.b4, A.invW, A.invH, A.cellStart + (size_t)b * (kGridCells + 1), W, lane);
       const uint4* qd = reinterpret_cast<const uint4*>(A.qdesc + ((size_t)b * A.qcap + q) * 32);
       const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
       const int* items = A.cellItems + (size_t)b * A.cap;
       const float r2 = __fmul_rn(Q.radius, Q.radius);
-      const WindowSegs& W = segs[wid];
-      warp_top4(total, [&](int t) { return window_candidate(t, W, items, K, Q, r2); },
-                [&](int idx) { return occ0 && occ0[idx]; }, q0, q1, D,
-                A.uright ? A.uright + (size_t)b * A.cap : nullptr, Q.ur, Q.radius, lane, T);
+      group_top4<G>(total, [&](int t) { return window_candidate(t, W, items, K, Q, r2); },
+                    [&](int idx) { return occ0 && occ0[idx]; }, q0, q1, D,
+                    A.uright ? A.uright + (size_t)b * A.cap : nullptr, Q.ur, Q.radius, lane, T);
     }
   } else {
     const int i1 = A.order1[(size_t)b * A.qcap + q];
@@ -201,13 +223,13 @@ __global__ void __launch_bounds__(32 * kScanWarps) k_search_scan(const SearchArg
       const uint4* qd = reinterpret_cast<const uint4*>(A.qdesc + ((size_t)b * A.qcap + i1) * 32);
       const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
       const int* s2 = A.sorted2 + (size_t)b * A.cap;
-      warp_top4(c1 - c0, [&](int t) { return s2[c0 + t]; }, [&](int) { return false; }, q0, q1, D, nullptr, 0.f, 0.f, lane, T);
+      group_top4<G>(c1 - c0, [&](int t) { return s2[c0 + t]; }, [&](int) { return false; }, q0, q1, D, nullptr, 0.f, 0.f, lane, T);
     }
   }
-  if (lane == 0) {
+  if (gl == 0) {
     uint4* o = A.top + ((size_t)b * A.qcap + q) * 2;
     o[0] = make_uint4(T.k[0], T.k[1], T.k[2], T.k[3]);
-    o[1] = make_uint4((unsigned)T.i[0], (unsigned)T.i[1], (unsigned)T.i[2], (unsigned)T.i[3]);
+    o[1] = make_uint4((unsigned)T.i[0] | (T.k[0] != kNoKey ? occupies : 0u), (unsigned)T.i[1], (unsigned)T.i[2], (unsigned)T.i[3]);
   }
 }
 
@@ -233,15 +255,14 @@ __device__ __forceinline__ int rot_bin(float a1, float a2) {   // ORBmatcher.cc:
   return bin;
 }
 
-// acceptance of (best, second) — ORBmatcher.cc:155-158 / :331-336 / :1807
-__device__ __forceinline__ bool accept_match(int mode, int th, float ratio, unsigned kb, int ib, unsigned ks, int is,
-                                             const orb_keypoint* K) {
-  if (ib < 0) return false;
+// acceptance of (best, second) — ORBmatcher.cc:155-158 / :331-336 / :1807; wb / ws = candidate words or -1
+__device__ __forceinline__ bool accept_match(int mode, int th, float ratio, unsigned kb, int wb, unsigned ks, int ws) {
+  if (wb < 0) return false;
   const int bd = (int)(kb >> 22);
   if (bd > th) return false;
-  const int bd2 = is >= 0 ? (int)(ks >> 22) : 256;
+  const int bd2 = ws >= 0 ? (int)(ks >> 22) : 256;
   if (mode == ORB_SEARCH_RATIO_LEVEL) {
-    const int l1 = K[ib].octave, l2 = is >= 0 ? K[is].octave : -1;
+    const int l1 = word_oct(wb), l2 = ws >= 0 ? word_oct(ws) : -1;
     if (l1 == l2 && (float)bd > __fmul_rn(ratio, (float)bd2)) return false;
   } else if (mode == ORB_SEARCH_RATIO) {
     if (!((float)bd < __fmul_rn(ratio, (float)bd2))) return false;
@@ -249,16 +270,29 @@ __device__ __forceinline__ bool accept_match(int mode, int th, float ratio, unsi
   return true;
 }
 
-// ---- pass 2: in-order commit, one warp per frame
-__global__ void __launch_bounds__(32) k_search_commit(const SearchArgs A) {
+// ---- pass 2: the in-order dependency as a fixed point, one CTA per frame.
+// The walk of the reference is the unique solution of  pick(q) = choose(q, {pick(j) : j < q})  where choose takes the
+// first (two) stored candidates that no earlier occupying query picked and applies the acceptance rule. The system is
+// triangular, so Jacobi iteration converges to exactly that solution: every sweep publishes the current picks
+// (tag[idx] = smallest occupying query that picks idx), then all queries re-choose in parallel against the tags
+// (a candidate is taken for q iff tag[idx] < q). After sweep t the first t queries are final; the loop ends when a
+// sweep changes nothing, which takes 1 + (longest chain of queries that actually displace each other) sweeps — a
+// handful on tracking-like input. A query whose four stored candidates ran out is re-scored exactly (warp per
+// query) against the same tags.
+constexpr int kCommitThreads = 512;
+
+__global__ void __launch_bounds__(kCommitThreads) k_search_commit(const SearchArgs A) {
   extern __shared__ __align__(16) unsigned csm[];
-  __shared__ WindowSegs segs;
+  __shared__ WindowSegs segs[kCommitThreads / 32];
   __shared__ int hist[HISTO_LENGTH];
-  const int b = blockIdx.x, lane = threadIdx.x;
+  __shared__ int sAcc, sRem, sChanged, sNres;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = A.counts[b];
   const int nq = A.bow ? A.meta[4 * b] : A.qcounts[b];
-  unsigned* occBits = csm;                               // cap/32 words
-  unsigned* tag = csm + ((A.cap + 31) >> 5);             // cap words: lowest lane that claims the keypoint this step
+  unsigned* occBits = csm;                                        // cap/32 words: the frame's initial occupancy
+  unsigned* tag = occBits + ((A.cap + 31) >> 5);                  // cap words
+  int* pick = reinterpret_cast<int*>(tag + A.cap);                // qcap words: keypoint picked by query q, or -1
+  int* rlist = pick + A.qcap;                                     // qcap words: queries to re-score in this sweep
   const orb_keypoint* K = A.kps + (size_t)b * A.cap;
   const u8* D = A.desc + (size_t)b * A.cap * 32;
   const u8* occ0 = A.occupied ? A.occupied + (size_t)b * A.cap : nullptr;
@@ -266,144 +300,142 @@ __global__ void __launch_bounds__(32) k_search_commit(const SearchArgs A) {
   int* mk = A.matchOfKp + (size_t)b * A.cap;
   int* mq = A.bow ? A.mqP + (size_t)b * A.qcap : A.matchOfQuery + (size_t)b * A.qcap;
   const int* order1 = A.order1 + (size_t)b * A.qcap;
+  const uint4* top = A.top + (size_t)b * A.qcap * 2;
 
-  for (int w = lane; w < ((A.cap + 31) >> 5); w += 32) {
+  for (int w = tid; w < ((A.cap + 31) >> 5); w += kCommitThreads) {
     unsigned bits = 0;
     if (occ0)
-      for (int j = 0; j < 32; j++) {
-        const int i = w * 32 + j;
-        if (i < n && occ0[i]) bits |= 1u << j;
-      }
+      for (int j = 0; j < 32; j++) if (w * 32 + j < n && occ0[w * 32 + j]) bits |= 1u << j;
     occBits[w] = bits;
   }
-  for (int i = lane; i < A.cap; i += 32) { tag[i] = kNoKey; mk[i] = -1; }
-  for (int q = lane; q < A.qcap; q += 32) {
+  for (int i = tid; i < A.cap; i += kCommitThreads) mk[i] = -1;
+  for (int q = tid; q < A.qcap; q += kCommitThreads) {
     mq[q] = -1;
+    pick[q] = -1;
     if (A.bow) A.matchOfQuery[(size_t)b * A.qcap + q] = -1;
   }
-  if (lane < HISTO_LENGTH) hist[lane] = 0;
-  __syncwarp();
+  if (tid < HISTO_LENGTH) hist[tid] = 0;
+  if (tid == 0) { sAcc = 0; sRem = 0; }
+  __syncthreads();
 
   const bool needSecond = A.mode != ORB_SEARCH_BEST;
-  int nacc = 0;
-  auto occ = [&](int idx) { return (occBits[idx >> 5] >> (idx & 31)) & 1u; };
-  auto commit = [&](int q, int idx, bool occupies, float angle) {
-    atomicMax(&mk[idx], q);      // a later query overwrites an earlier one (only possible if that one did not occupy)
-    mq[q] = idx;
-    if (occupies) atomicOr(&occBits[idx >> 5], 1u << (idx & 31));
-    if (A.checkOri) atomicAdd(&hist[rot_bin(angle, K[idx].angle)], 1);
-    nacc++;
-  };
-
-  for (int q0 = 0; q0 < nq; q0 += 32) {
-    const int q = q0 + lane;
-    Top4 T;
-    top4_clear(T);
-    bool occupies = true;
-    float angle = 0.f;
-    if (q < nq) {
-      const uint4* t = A.top + ((size_t)b * A.qcap + q) * 2;
-      const uint4 k4 = t[0], i4 = t[1];
-      T.k[0] = k4.x; T.k[1] = k4.y; T.k[2] = k4.z; T.k[3] = k4.w;
-      T.i[0] = (int)i4.x; T.i[1] = (int)i4.y; T.i[2] = (int)i4.z; T.i[3] = (int)i4.w;
-      if (A.bow) {
-        angle = A.kps1[(size_t)b * A.qcap + order1[q]].angle;
-      } else {
-        const orb_proj_query& Q = A.queries[(size_t)b * A.qcap + q];
-        occupies = (Q.flags & 2) != 0;
-        angle = Q.angle;
-      }
+  const int need = needSecond ? 2 : 1;
+  for (;;) {
+    // ---- publish the picks of the previous sweep
+    for (int i = tid; i < n; i += kCommitThreads) tag[i] = kNoKey;
+    if (tid == 0) { sChanged = 0; sNres = 0; }
+    __syncthreads();
+    for (int q = tid; q < nq; q += kCommitThreads) {
+      const int p = pick[q];
+      if (p >= 0 && (top[2 * q + 1].x & kWordOccupies)) atomicMin(&tag[p], (unsigned)q);
     }
-    bool pending = T.k[0] != kNoKey;
-    while (__any_sync(kFull, pending)) {
-      int ib = -1, is = -1;
+    __syncthreads();
+    // ---- every query chooses again
+    bool changed = false;
+    for (int q = tid; q < nq; q += kCommitThreads) {
+      const uint4 k4 = top[2 * q];
+      if (k4.x == kNoKey) continue;
+      const uint4 i4 = top[2 * q + 1];
+      const unsigned k[4] = {k4.x, k4.y, k4.z, k4.w};
+      const int w[4] = {(int)(i4.x & ~kWordOccupies), (int)i4.y, (int)i4.z, (int)i4.w};
+      int wb = -1, ws = -1, nfree = 0;
       unsigned kb = kNoKey, ks = kNoKey;
 #pragma unroll
       for (int m = 0; m < 4; m++)
-        if (T.k[m] != kNoKey && !occ(T.i[m])) {
-          if (ib < 0) { ib = T.i[m]; kb = T.k[m]; }
-          else if (is < 0) { is = T.i[m]; ks = T.k[m]; }
+        if (k[m] != kNoKey && !(tag[word_idx(w[m])] < (unsigned)q)) {   // not taken by an earlier query
+          if (wb < 0) { wb = w[m]; kb = k[m]; }
+          else if (ws < 0) { ws = w[m]; ks = k[m]; }
+          nfree++;
         }
-      const bool complete = T.k[3] == kNoKey;
-      const bool needFull = pending && !complete && (ib < 0 || (needSecond && is < 0));
-      const bool acc = pending && !needFull && accept_match(A.mode, A.th, A.ratio, kb, ib, ks, is, K);
-      const bool claims = acc && occupies;
-      if (claims) atomicMin(&tag[ib], (unsigned)lane);
-      __syncwarp();
-      bool conflicted = false;
-      if (pending && !needFull) {
-        if (ib >= 0 && tag[ib] < (unsigned)lane) conflicted = true;
-        if (needSecond && is >= 0 && tag[is] < (unsigned)lane) conflicted = true;
+      if (k[3] != kNoKey && nfree < need) {   // more candidates exist than the four stored: exact re-score below
+        rlist[atomicAdd(&sNres, 1)] = q;
+        continue;
       }
-      const unsigned badMask = __ballot_sync(kFull, pending && (needFull || conflicted));
-      const int first = badMask ? __ffs(badMask) - 1 : 32;
-      __syncwarp();
-      if (claims) tag[ib] = kNoKey;
-      if (pending && lane < first) {
-        if (acc) commit(q, ib, occupies, angle);
-        pending = false;
-      }
-      __syncwarp();
-      if (first < 32 && __shfl_sync(kFull, (int)needFull, first)) {
-        // exact re-score of query q0 + first against the current occupancy (its stored candidates ran out)
-        const int qq = q0 + first;
-        Top4 X;
-        if (!A.bow) {
-          const orb_proj_query Q = A.queries[(size_t)b * A.qcap + qq];
-          const int total = window_setup(Q, A.b4, A.invW, A.invH, A.cellStart + (size_t)b * (kGridCells + 1), segs, lane);
-          const uint4* qd = reinterpret_cast<const uint4*>(A.qdesc + ((size_t)b * A.qcap + qq) * 32);
-          const uint4 d0 = __ldg(qd), d1 = __ldg(qd + 1);
-          const int* items = A.cellItems + (size_t)b * A.cap;
-          const float r2 = __fmul_rn(Q.radius, Q.radius);
-          warp_top4(total, [&](int t) { return window_candidate(t, segs, items, K, Q, r2); }, occ, d0, d1, D, UR, Q.ur, Q.radius,
-                    lane, X);
-        } else {
-          const int i1 = order1[qq];
-          const int c0 = A.cb[(size_t)b * A.qcap + qq], c1 = A.ce[(size_t)b * A.qcap + qq];
-          const uint4* qd = reinterpret_cast<const uint4*>(A.qdesc + ((size_t)b * A.qcap + i1) * 32);
-          const uint4 d0 = __ldg(qd), d1 = __ldg(qd + 1);
-          const int* s2 = A.sorted2 + (size_t)b * A.cap;
-          warp_top4(c1 - c0, [&](int t) { return s2[c0 + t]; }, occ, d0, d1, D, nullptr, 0.f, 0.f, lane, X);
-        }
-        if (lane == first) {
-          if (accept_match(A.mode, A.th, A.ratio, X.k[0], X.i[0], X.k[1], X.i[1], K)) commit(q, X.i[0], occupies, angle);
-          pending = false;
-        }
+      const int np = accept_match(A.mode, A.th, A.ratio, kb, wb, ks, ws) ? word_idx(wb) : -1;
+      if (np != pick[q]) { pick[q] = np; changed = true; }
+    }
+    __syncthreads();
+    const int nres = sNres;
+    for (int r = wid; r < nres; r += kCommitThreads / 32) {
+      const int qq = rlist[r];
+      auto taken = [&](int idx) { return ((occBits[idx >> 5] >> (idx & 31)) & 1u) || tag[idx] < (unsigned)qq; };
+      Top4 X;
+      if (!A.bow) {
+        const orb_proj_query Q = A.queries[(size_t)b * A.qcap + qq];
+        WindowSegs& W = segs[wid];
+        const int total = window_setup<32>(Q, A.b4, A.invW, A.invH, A.cellStart + (size_t)b * (kGridCells + 1), W, lane);
+        const uint4* qd = reinterpret_cast<const uint4*>(A.qdesc + ((size_t)b * A.qcap + qq) * 32);
+        const uint4 d0 = __ldg(qd), d1 = __ldg(qd + 1);
+        const int* items = A.cellItems + (size_t)b * A.cap;
+        const float r2 = __fmul_rn(Q.radius, Q.radius);
+        group_top4<32>(total, [&](int t) { return window_candidate(t, W, items, K, Q, r2); }, taken, d0, d1, D, UR, Q.ur, Q.radius,
+                       lane, X);
         __syncwarp();
+      } else {
+        const int i1 = order1[qq];
+        const int c0 = A.cb[(size_t)b * A.qcap + qq], c1 = A.ce[(size_t)b * A.qcap + qq];
+        const uint4* qd = reinterpret_cast<const uint4*>(A.qdesc + ((size_t)b * A.qcap + i1) * 32);
+        const uint4 d0 = __ldg(qd), d1 = __ldg(qd + 1);
+        const int* s2 = A.sorted2 + (size_t)b * A.cap;
+        group_top4<32>(c1 - c0, [&](int t) { return s2[c0 + t]; }, taken, d0, d1, D, nullptr, 0.f, 0.f, lane, X);
+      }
+      if (lane == 0) {
+        const int np = accept_match(A.mode, A.th, A.ratio, X.k[0], X.i[0], X.k[1], X.i[1]) ? word_idx(X.i[0]) : -1;
+        if (np != pick[qq]) { pick[qq] = np; changed = true; }
       }
     }
+    if (changed) sChanged = 1;
+    __syncthreads();
+    if (!sChanged) break;
+    __syncthreads();   // everyone has read sChanged before the next sweep resets it
   }
-  __syncwarp();
+  // ---- the fixed point is the reference's result: write it out
+  int nacc = 0;
+  for (int q = tid; q < nq; q += kCommitThreads) {
+    const int p = pick[q];
+    if (p >= 0) {
+      atomicMax(&mk[p], q);   // a later query overwrites an earlier one (only possible if that one did not occupy)
+      mq[q] = p;
+      nacc++;
+    }
+  }
+  if (nacc) atomicAdd(&sAcc, nacc);
   __threadfence_block();
-  // rotation consistency (ORBmatcher.cc:1830-1855 / :380-417)
-  int nrem = 0;
+  __syncthreads();
+  // rotation consistency (ORBmatcher.cc:1830-1855 / :380-417): histogram of the accepted matches, three maxima,
+  // everything else is removed
   if (A.checkOri) {
+    auto angle_of = [&](int q) {
+      return A.bow ? A.kps1[(size_t)b * A.qcap + order1[q]].angle : A.queries[(size_t)b * A.qcap + q].angle;
+    };
+    for (int q = tid; q < nq; q += kCommitThreads) {
+      const int idx = mq[q];
+      if (idx >= 0) atomicAdd(&hist[rot_bin(angle_of(q), K[idx].angle)], 1);
+    }
+    __syncthreads();
     int i1, i2, i3;
     three_maxima30(hist, i1, i2, i3);
-    for (int q = lane; q < nq; q += 32) {
+    int nrem = 0;
+    for (int q = tid; q < nq; q += kCommitThreads) {
       const int idx = mq[q];
       if (idx < 0) continue;
-      const float a1 = A.bow ? A.kps1[(size_t)b * A.qcap + order1[q]].angle : A.queries[(size_t)b * A.qcap + q].angle;
-      const int bin = rot_bin(a1, K[idx].angle);
+      const int bin = rot_bin(angle_of(q), K[idx].angle);
       if (bin != i1 && bin != i2 && bin != i3) {
         mq[q] = -1;
         mk[idx] = -1;
         nrem++;
       }
     }
+    if (nrem) atomicAdd(&sRem, nrem);
+    __syncthreads();
   }
-  int tot = nacc - nrem;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
-  if (lane == 0) A.nmatches[b] = tot;
+  if (tid == 0) A.nmatches[b] = sAcc - sRem;
   if (A.bow) {   // positions in the (node, index) order -> keyframe feature indices
-    __syncwarp();
-    __threadfence_block();
-    for (int i = lane; i < n; i += 32) {
+    for (int i = tid; i < n; i += kCommitThreads) {
       const int p = mk[i];
       if (p >= 0) mk[i] = order1[p];
     }
-    for (int p = lane; p < nq; p += 32) A.matchOfQuery[(size_t)b * A.qcap + order1[p]] = mq[p];
+    for (int p = tid; p < nq; p += kCommitThreads) A.matchOfQuery[(size_t)b * A.qcap + order1[p]] = mq[p];
   }
 }
 
@@ -576,12 +608,12 @@ int fill_common(SearchArgs& A, const orb_device_frames* F, int qcap, const orb_s
 }
 
 int launch_search(const SearchArgs& A, int batch, cudaStream_t s) {
-  k_search_scan<<<dim3((A.qcap + kScanWarps - 1) / kScanWarps, batch), 32 * kScanWarps, 0, s>>>(A);
+  k_search_scan<<<dim3((A.qcap + kScanQueries - 1) / kScanQueries, batch), 32 * kScanWarps, 0, s>>>(A);
   ORB_CUDA(cudaGetLastError());
-  const size_t smem = ((size_t)((A.cap + 31) >> 5) + (size_t)A.cap) * 4;
+  const size_t smem = ((size_t)((A.cap + 31) >> 5) + (size_t)A.cap + 2 * (size_t)A.qcap) * 4;
   if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "capacity too large for the commit kernel's shared memory");
   if (smem > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_search_commit<<<batch, 32, smem, s>>>(A);
+  k_search_commit<<<batch, kCommitThreads, smem, s>>>(A);
   ORB_CUDA(cudaGetLastError());
   return ORB_OK;
 }

@@ -79,11 +79,12 @@ def correlated_descriptor_pair(n, seed, flip_prob=0.06, outlier_frac=0.3):
 
 
 def tracking_scene(n_cur, n_last, seed, w=1241, h=376, fx=718.856, cx=607.1928, cy=185.2157, bf=386.1448,
-                   noise_px=3.0, flip_bits=24, frac_mapped=0.8, frac_unobserved=0.05, frac_occupied=0.05, nlevels=8):
+                   noise_px=3.0, flip_bits=24, frac_mapped=0.8, frac_unobserved=0.05, frac_occupied=0.05, nlevels=8,
+                   distinct=0.0):
     """Synthetic state for the projection / BoW matchers: a current frame of n_cur keypoints and a last
     frame of n_last keypoints whose map points project close to current keypoints (position noise
     `noise_px`, descriptor = current descriptor with up to `flip_bits` flipped bits), so that windows
-    hold several candidates, some map points compete for one keypoint and ties occur. numpy only."""
+    hold several candidates (`distinct` = fraction of map points that follow a keypoint of their own), some map points compete for one keypoint and ties occur. numpy only."""
     from ._lib import KP_DTYPE
     rng = np.random.RandomState(seed & 0x7FFFFFFF)
     f32 = np.float32
@@ -102,6 +103,9 @@ def tracking_scene(n_cur, n_last, seed, w=1241, h=376, fx=718.856, cx=607.1928, 
     Tcw = np.eye(4, dtype=f32); Tcw[:3, :3] = R.astype(f32); Tcw[:3, 3] = t.astype(f32)
     # last frame: every keypoint follows one current keypoint (several may follow the same one)
     src = rng.randint(0, n_cur, n_last)
+    if distinct > 0:   # tracking-like: most map points follow their own keypoint, a few compete
+        own = np.resize(rng.permutation(n_cur), n_last)
+        src = np.where(rng.rand(n_last) < distinct, own, src)
     last = np.zeros(n_last, KP_DTYPE)
     last["octave"] = np.clip(cur["octave"][src] + rng.randint(-1, 2, n_last), 0, nlevels - 1)
     rot = 10.0 * rng.randn() + rng.randn(n_last) * 3.0
