@@ -348,6 +348,44 @@ def run_ours(args, rank, world, local_rank):
     frame_launches = 3 * s_steps + 3
     del d_q, d_ao, d_ac, d_un, d_cs, d_ci
 
+    # ---- input stage: cvtColor RGB -> gray and remap rectification of the frames of one chunk, plus
+    # ComputeDistinctiveDescriptors over 100 k map points; HBM-bound byte kernels, reported against the measured peak
+    from orb_slam2_detailed_comments_b200 import input as IN
+    in_B = min(256, frames_per_step)
+    d_rgb = torch.randint(0, 256, (in_B, H, W, 3), dtype=torch.uint8, device=dev)
+    d_g = torch.zeros((in_B, H, W), dtype=torch.uint8, device=dev)
+    yy_, xx_ = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=dev), torch.arange(W, dtype=torch.float32, device=dev), indexing="ij")
+    rr_ = ((xx_ - W / 2) ** 2 + (yy_ - H / 2) ** 2) / float(W * W)
+    d_mx = (xx_ + (xx_ - W / 2) * 0.08 * rr_ + 1.3).contiguous(); d_my = (yy_ + (yy_ - H / 2) * 0.08 * rr_ - 0.7).contiguous()
+    d_rect = torch.zeros((in_B, H, W), dtype=torch.uint8, device=dev)
+    mp_counts = np.random.RandomState(5).randint(2, 25, 100000).astype(np.int32)
+    mp_off = torch.from_numpy(np.concatenate([[0], np.cumsum(mp_counts)]).astype(np.int32)).to(dev)
+    mp_desc = torch.randint(0, 256, (int(mp_counts.sum()), 32), dtype=torch.uint8, device=dev)
+    mp_best = torch.zeros(len(mp_counts), dtype=torch.int32, device=dev); mp_bd = torch.zeros((len(mp_counts), 32), dtype=torch.uint8, device=dev)
+    input_stage = {}
+    hbm_peak = measured_hbm_peak()[0]
+    for name, fn, nbytes in (("cvt_rgb2gray", lambda: IN.cvtColorGray(d_rgb, IN.RGB2GRAY, d_g, device=local_rank, stream=stream), in_B * H * W * 4),
+                             ("remap_linear", lambda: IN.remap(d_imgs[:in_B], d_mx, d_my, d_rect, device=local_rank, stream=stream), in_B * H * W * 2 + H * W * 8),
+                             ("distinctive_descriptors", lambda: IN.ComputeDistinctiveDescriptors(mp_desc, mp_off, 32, mp_best, mp_bd, device=local_rank, stream=stream),
+                              int(mp_counts.sum()) * 32 + len(mp_counts) * 40)):
+        for _ in range(3):
+            fn()
+        barrier()
+        i0 = torch.cuda.Event(enable_timing=True); i1 = torch.cuda.Event(enable_timing=True)
+        i0.record(tstream)
+        for _ in range(10):
+            fn()
+        i1.record(tstream)
+        torch.cuda.synchronize()
+        ms = max_over_ranks(i0.elapsed_time(i1)) / 10
+        input_stage[name] = {"ms": ms, "algorithmic_GBps": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / hbm_peak}
+    input_stage["cvt_rgb2gray"]["frames_per_s"] = world * in_B / (input_stage["cvt_rgb2gray"]["ms"] * 1e-3)
+    input_stage["remap_linear"]["frames_per_s"] = world * in_B / (input_stage["remap_linear"]["ms"] * 1e-3)
+    input_stage["distinctive_descriptors"]["map_points_per_s"] = world * len(mp_counts) / (input_stage["distinctive_descriptors"]["ms"] * 1e-3)
+    input_stage["what"] = "%d %dx%d frames per call; 100 k map points with 2..24 observations" % (in_B, W, H)
+    input_launches = 3 * 13
+    del d_rgb, d_g, d_rect, mp_desc
+
     # ---- tracking matchers: SearchByProjection(CurrentFrame, LastFrame) on 2000 x 2000 frames,
     # projection + grid + search, device resident; batch throughput and single-frame latency
     from orb_slam2_detailed_comments_b200 import search as SR
@@ -565,10 +603,11 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs larger than L2 (%d MB per step; unique pool %d MB)" % (frames_per_step * W * H // 1000000, UNIQUE_FRAMES * W * H // 1000000), "parallelism": "frames sharded, no collective"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "orb_extract_batch_host (pinned host buffers)"},
-        "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + frame_launches + track_launches + m_steps + (2 * world if allpairs else 0),
+        "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + frame_launches + track_launches + input_launches + m_steps + (2 * world if allpairs else 0),
         "stereo": stereo,
         "frame_helpers": frame_helpers,
         "tracking": tracking,
+        "input_stage": input_stage,
         "latency": lat,
         "clocks": clocks,
         "roofline": roofline,

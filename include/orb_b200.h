@@ -337,6 +337,34 @@ int orb_search_by_bow_device(int device, const orb_keypoint* d_keypoints1, const
                              const orb_search_params* params, void* d_scratch, int32_t* d_match_of_keypoint,
                              int32_t* d_match_of_query, int32_t* d_nmatches, void* stream);
 
+/* ---- Input stage and map-point descriptors (the callers either side of the path) ------ */
+
+enum { ORB_RGB2GRAY = 0, ORB_BGR2GRAY = 1, ORB_RGBA2GRAY = 2, ORB_BGRA2GRAY = 3 };
+
+/* Replaces cv::cvtColor(im, im, CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) of
+ * Tracking::GrabImage{Stereo,RGBD,Monocular} (src/Tracking.cc:250-276, 310-324, 369-383) for `batch`
+ * interleaved 8-bit frames on the device (OpenCV 4.x 15-bit coefficients, bit-exact vs cv2). */
+int orb_cvt_color_gray_device(int device, const uint8_t* d_src, int width, int height, size_t src_step,
+                              size_t src_frame_stride, int batch, int code, uint8_t* d_gray, size_t gray_step,
+                              size_t gray_frame_stride, void* stream);
+
+/* Replaces cv::remap(src, dst, M1, M2, cv::INTER_LINEAR) with CV_32FC1 maps and BORDER_CONSTANT(0), the
+ * stereo rectification of Examples/Stereo/stereo_euroc.cc:181-188 (maps from initUndistortRectifyMap, computed
+ * once by the caller: dst_height x dst_width floats each, shared by all frames). Bit-exact vs cv2.remap. */
+int orb_remap_linear_device(int device, const uint8_t* d_src, int src_width, int src_height, size_t src_step,
+                            size_t src_frame_stride, int batch, const float* d_map_x, const float* d_map_y,
+                            int dst_width, int dst_height, uint8_t* d_dst, size_t dst_step, size_t dst_frame_stride,
+                            void* stream);
+
+/* Replaces MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:365-448) for n_points map points at once:
+ * the descriptors of map point p's observations are rows d_offsets[p] .. d_offsets[p+1]-1 of d_descriptors
+ * (at most max_observations each). d_best_index[p] = the observation with the smallest median distance to all
+ * observations (first wins), -1 for a map point without observations, -2 if it exceeds max_observations;
+ * d_best_descriptor (n_points x 32, may be NULL) receives that descriptor (MapPoint::mDescriptor). */
+int orb_distinctive_descriptors_device(int device, const uint8_t* d_descriptors, const int32_t* d_offsets, int n_points,
+                                       int max_observations, int32_t* d_best_index, uint8_t* d_best_descriptor,
+                                       void* stream);
+
 /* Integer-pipe microbenchmark used for the matching roofline: independent chains of POPC
  * (what=0), LOP3 (what=1) or the matcher's own mix of 1 POPC per 4 LOP3 (what=2, reported in
  * units of (1 POPC + 4 LOP3) per second) on a full grid; returns ops/s in *ops_per_s. */

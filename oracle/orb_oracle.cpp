@@ -1007,6 +1007,82 @@ int search_by_bow(const FrameView& KF, const int* node1, const u8* usable1, cons
   return S.finish();
 }
 
+// ------------------------------------------------------------------------------------------
+// Input stage and MapPoint::ComputeDistinctiveDescriptors
+// ------------------------------------------------------------------------------------------
+// cv::cvtColor(..., CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) on 8-bit images as Tracking.cc:250-276,
+// 310-324, 369-383 call it. OpenCV 4.x: 15-bit coefficients RY15 = 9798, GY15 = 19235, BY15 = 3735, rounded
+// (checked bit-exactly against cv2.cvtColor in tests/test_oracle_input.py).
+void cvt_gray(const u8* src, int w, int h, size_t step, int channels, int blueFirst, u8* dst, size_t dstep) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const u8* p = src + (size_t)y * step + (size_t)x * channels;
+      const int r = blueFirst ? p[2] : p[0], g = p[1], b = blueFirst ? p[0] : p[2];
+      dst[(size_t)y * dstep + x] = (u8)((r * 9798 + g * 19235 + b * 3735 + (1 << 14)) >> 15);
+    }
+}
+
+// cv::remap(src, dst, mapx, mapy, INTER_LINEAR) with CV_32FC1 maps and the default BORDER_CONSTANT(0), as
+// Examples/Stereo/stereo_euroc.cc:181-188 calls it. OpenCV's fixed point: coordinates rounded to 1/32 px, 2x2
+// weights from the 32x32 table of initInterTab2D (shorts scaled by 2^15, repaired to sum 2^15), result
+// (sum + 2^14) >> 15 (checked bit-exactly against cv2.remap).
+struct RemapTab {
+  short w[32][32][4];
+  RemapTab() {
+    float t1[32][2];
+    for (int i = 0; i < 32; i++) { const float x = (float)i * (1.f / 32); t1[i][0] = 1.f - x; t1[i][1] = x; }
+    for (int i = 0; i < 32; i++)
+      for (int j = 0; j < 32; j++) {
+        short* it = w[i][j];
+        int isum = 0;
+        for (int k1 = 0; k1 < 2; k1++)
+          for (int k2 = 0; k2 < 2; k2++) {
+            const float v = t1[i][k1] * t1[j][k2];
+            long r = lrintf(v * 32768.f);
+            r = std::min(32767L, std::max(-32768L, r));   // saturate_cast<short>
+            it[k1 * 2 + k2] = (short)r;
+            isum += (int)r;
+          }
+        if (isum != 32768) {   // initInterTab2D's repair with ksize = 2: only element [3] is inspected
+          const int diff = isum - 32768;
+          it[3] = (short)(it[3] - diff);
+        }
+      }
+  }
+};
+void remap_linear(const u8* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, int dw, int dh, u8* dst,
+                  size_t dstep) {
+  static const RemapTab tab;
+  for (int y = 0; y < dh; y++)
+    for (int x = 0; x < dw; x++) {
+      const int sx = (int)lrintf(mapx[(size_t)y * dw + x] * 32.f), sy = (int)lrintf(mapy[(size_t)y * dw + x] * 32.f);
+      const int X = std::min(32767, std::max(-32768, sx >> 5)), Y = std::min(32767, std::max(-32768, sy >> 5));
+      const short* wt = tab.w[sy & 31][sx & 31];
+      int acc = 0;
+      for (int k1 = 0; k1 < 2; k1++)
+        for (int k2 = 0; k2 < 2; k2++) {
+          const int yy = Y + k1, xx = X + k2;
+          const int p = (yy >= 0 && yy < sh && xx >= 0 && xx < sw) ? src[(size_t)yy * sstep + xx] : 0;
+          acc += p * wt[k1 * 2 + k2];
+        }
+      dst[(size_t)y * dstep + x] = (u8)std::min(255, std::max(0, (acc + (1 << 14)) >> 15));
+    }
+}
+
+// MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:365-448: the observation whose median distance to all
+// observations (itself included) is smallest; first wins.
+int distinctive_descriptor(const u8* desc, int n) {
+  int bestMedian = INT_MAX, bestIdx = 0;
+  std::vector<int> d(n);
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < n; j++) d[j] = hamming256(desc + (size_t)i * 32, desc + (size_t)j * 32);
+    std::sort(d.begin(), d.end());
+    const int median = d[(int)(0.5 * (n - 1))];
+    if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+  }
+  return bestIdx;
+}
+
 extern "C" {
 
 void* orc_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
@@ -1209,6 +1285,20 @@ int orc_search_by_bow(const void* kps1, int n1, const u8* desc1, const int* node
   std::vector<float> xy1, ang1, xy2, ang2; std::vector<int> oct1, oct2;
   FrameView A = view_of(kps1, n1, desc1, xy1, oct1, ang1), B = view_of(kps2, n2, desc2, xy2, oct2, ang2);
   return search_by_bow(A, node1, usable1, B, node2, th, ratio, checkOri, matchOfKp, matchOfQuery);
+}
+
+// ---- input stage / map point descriptors
+void orc_cvt_gray(const u8* src, int w, int h, size_t step, int channels, int blueFirst, u8* dst) {
+  cvt_gray(src, w, h, step, channels, blueFirst, dst, (size_t)w);
+}
+void orc_remap_linear(const u8* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, int dw, int dh, u8* dst) {
+  remap_linear(src, sw, sh, sstep, mapx, mapy, dw, dh, dst, (size_t)dw);
+}
+void orc_distinctive_descriptors(const u8* desc, const int* offsets, int nPoints, int* bestIdx) {
+  for (int p = 0; p < nPoints; p++) {
+    const int n = offsets[p + 1] - offsets[p];
+    bestIdx[p] = n > 0 ? distinctive_descriptor(desc + (size_t)offsets[p] * 32, n) : -1;
+  }
 }
 
 // All-pairs keyframe matching count (config 5): for keyframe pair (i,j), the number of rows

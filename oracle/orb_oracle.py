@@ -298,6 +298,32 @@ def search_by_bow(kps1, desc1, node1, usable1, kps2, desc2, node2, th=50, ratio=
     return nm, mk[:n2], mq[:n1]
 
 
+def cvt_gray(img, blue_first=False):
+    """cv::cvtColor(img, CV_RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY) (Tracking.cc:250-276)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, c = img.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_cvt_gray(_p(img), w, h, C.c_size_t(img.strides[0]), c, int(blue_first), _p(out))
+    return out
+
+
+def remap_linear(img, mapx, mapy):
+    """cv::remap(img, ., mapx, mapy, INTER_LINEAR), float maps, BORDER_CONSTANT 0 (stereo_euroc.cc:181-188)."""
+    img = np.ascontiguousarray(img, np.uint8); mapx = np.ascontiguousarray(mapx, np.float32); mapy = np.ascontiguousarray(mapy, np.float32)
+    dh, dw = mapx.shape
+    out = np.zeros((dh, dw), np.uint8)
+    lib().orc_remap_linear(_p(img), img.shape[1], img.shape[0], C.c_size_t(img.strides[0]), _p(mapx), _p(mapy), dw, dh, _p(out))
+    return out
+
+
+def distinctive_descriptors(desc, offsets):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:365) for map points with observations desc[offsets[p]:offsets[p+1]]."""
+    desc = np.ascontiguousarray(desc, np.uint8); offsets = np.ascontiguousarray(offsets, np.int32)
+    out = np.zeros(len(offsets) - 1, np.int32)
+    lib().orc_distinctive_descriptors(_p(desc), _p(offsets), len(out), _p(out))
+    return out
+
+
 def allpairs_counts(desc, nnratio=0.9, row_begin=0, row_end=None):
     desc = np.ascontiguousarray(desc, np.uint8)
     nkf, nd, _ = desc.shape

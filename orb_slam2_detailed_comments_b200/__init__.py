@@ -8,3 +8,4 @@ from .extractor import ORBextractor  # noqa: F401
 from .matcher import FrameView, ORBmatcher, int_pipe_peak  # noqa: F401
 from . import frame  # noqa: F401,E402
 from . import search  # noqa: F401,E402
+from . import input  # noqa: F401,E402

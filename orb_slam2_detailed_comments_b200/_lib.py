@@ -77,6 +77,7 @@ EXPORTS = [
     "orb_hamming_matrix_device", "orb_matcher_synchronize", "orb_int_pipe_peak",
     "orb_search_scratch_bytes", "orb_project_last_frame_device", "orb_search_by_projection_device",
     "orb_search_by_bow_device",
+    "orb_cvt_color_gray_device", "orb_remap_linear_device", "orb_distinctive_descriptors_device",
 ]
 
 _lib = None
@@ -131,6 +132,9 @@ def lib():
         L.orb_hamming_matrix_device.argtypes = [vp, vp, i32, vp, i32, vp, vp]
         L.orb_matcher_synchronize.argtypes = [vp, vp]
         L.orb_int_pipe_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
+        L.orb_cvt_color_gray_device.argtypes = [i32, vp, i32, i32, sz, sz, i32, i32, vp, sz, sz, vp]
+        L.orb_remap_linear_device.argtypes = [i32, vp, i32, i32, sz, sz, i32, vp, vp, i32, i32, vp, sz, sz, vp]
+        L.orb_distinctive_descriptors_device.argtypes = [i32, vp, vp, i32, i32, vp, vp, vp]
         L.orb_search_scratch_bytes.restype = sz
         L.orb_search_scratch_bytes.argtypes = [i32, i32, i32]
         L.orb_project_last_frame_device.argtypes = [i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, f32, f32, vp, i32, vp, vp]
