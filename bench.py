@@ -178,6 +178,26 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(props):
+    """N > 1: run this rank on the CPUs next to its GPU, so that its pinned staging memory (first touch) and the
+    copy-engine traffic stay on the GPU's NUMA node instead of crossing the socket link. Best effort."""
+    try:
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -187,7 +207,9 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local_rank))
         dist.init_process_group("nccl", device_id=dev)
 
     from orb_slam2_detailed_comments_b200 import KP_DTYPE, ORBextractor, ORBmatcher, int_pipe_peak
@@ -480,6 +502,15 @@ def run_ours(args, rank, world, local_rank):
     e2e_launches = ext.last_launch_count() * e2e_steps
     assert int(np_counts.sum()) == int(counts.sum()), "host path and device path disagree"
     h2d = frames_per_step * W * H
+    # the copy engine alone on the same pinned buffer: the ceiling of any end-to-end number on this box
+    d_probe = torch.empty_like(d_imgs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d_probe.copy_(h_imgs, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_peak = 3 * h2d / (time.perf_counter() - t0) / 1e9
+    del d_probe
     d2h = frames_per_step * (cap * 60 + 4)
     del h_imgs, h_kps, h_desc
 
@@ -600,9 +631,12 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "%s-shape %dx%d stereo pairs, ORBextractor(%d,1.2,8,20,7) per eye, " % (args.workload, W, H, NFEAT) +
                                "%d pairs (%d eye-frames) per step per GPU" % (args.pairs, frames_per_step),
                    "frames_per_step_per_gpu": frames_per_step, "unique_frames": UNIQUE_FRAMES, "chunk_frames": args.chunk,
-                   "l2": "inputs larger than L2 (%d MB per step; unique pool %d MB)" % (frames_per_step * W * H // 1000000, UNIQUE_FRAMES * W * H // 1000000), "parallelism": "frames sharded, no collective"},
+                   "l2": "inputs larger than L2 (%d MB per step; unique pool %d MB)" % (frames_per_step * W * H // 1000000, UNIQUE_FRAMES * W * H // 1000000), "parallelism": "frames sharded, no collective",
+                   "numa_node_of_rank0": numa},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "orb_extract_batch_host (pinned host buffers)"},
+                "api": "orb_extract_batch_host (pinned host buffers)", "h2d_GBps_in_run": e2e_fps / world * W * H / 1e9,
+                "h2d_GBps_copy_engine_alone": h2d_peak,
+                "ceiling_frames_per_s": h2d_peak * 1e9 / (W * H) * world},
         "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + frame_launches + track_launches + input_launches + m_steps + (2 * world if allpairs else 0),
         "stereo": stereo,
         "frame_helpers": frame_helpers,

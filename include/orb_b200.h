@@ -328,14 +328,41 @@ int orb_search_by_projection_device(int device, const orb_device_frames* frames,
 /* Replaces ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (src/ORBmatcher.cc:247-420).
  * The DBoW2 FeatureVectors (node id -> feature indices) are passed as the node id of every feature
  * (d_node1 / d_node2, -1 = none). Keyframe side: (batch, query_capacity) features with d_usable1 = 1
- * where the feature has a good map point; frame side: `frames` (grid, uright, occupied unused).
+ * where the feature has a good map point; frame side: `frames` (grid and uright unused; `occupied`, if given,
+ * marks keypoints that are not candidates).
  * d_match_of_keypoint (batch, capacity) = keyframe feature index per frame keypoint
- * (vpMapPointMatches) or -1; d_match_of_query (batch, query_capacity) = frame keypoint or -1. */
+ * (vpMapPointMatches) or -1; d_match_of_query (batch, query_capacity) = frame keypoint or -1.
+ * The same call is ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:729-880):
+ * frames = keyframe 2 with occupied[i] = !vpMapPoints2[i] || isBad(), th = TH_LOW - 1 (that variant tests
+ * bestDist1 < TH_LOW), vpMatches12 = d_match_of_query. */
 int orb_search_by_bow_device(int device, const orb_keypoint* d_keypoints1, const uint8_t* d_descriptors1,
                              const int32_t* d_node1, const uint8_t* d_usable1, const int32_t* d_counts1,
                              int query_capacity, const orb_device_frames* frames, const int32_t* d_node2,
                              const orb_search_params* params, void* d_scratch, int32_t* d_match_of_keypoint,
                              int32_t* d_match_of_query, int32_t* d_nmatches, void* stream);
+
+/* Per keyframe pair of SearchForTriangulation. */
+typedef struct orb_triangulation_pair {
+  float F12[9];        /* fundamental matrix, row-major (F12.at<float>(r, c) = F12[3*r + c]) */
+  float ex, ey;        /* epipole: keyframe 1's camera centre projected into keyframe 2 (src/ORBmatcher.cc:897-901) */
+  int32_t only_stereo; /* bOnlyStereo */
+} orb_triangulation_pair;
+
+/* Replaces ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)
+ * (src/ORBmatcher.cc:884-1100) for `batch` keyframe pairs: features of keyframe 1 WITHOUT a map point
+ * (d_has_mappoint1 == 0) are matched inside their vocabulary node against keyframe-2 features without a map
+ * point (frames2->occupied = has a map point), best distance <= TH_LOW, later candidate wins ties, epipole test
+ * for monocular pairs, CheckDistEpipolarLine (:205-227) with level_sigma2 of keyframe 2's octave;
+ * frames2->uright / d_uright1 = mvuRight (>= 0: stereo observation; NULL = monocular). A matched keyframe-2
+ * feature is taken for later features (vbMatched2), rotation consistency as in the other searches.
+ * d_matches12 (batch, query_capacity) = vMatches12 (keyframe-2 index or -1), d_nmatches = return value. */
+int orb_search_for_triangulation_device(int device, const orb_keypoint* d_keypoints1, const uint8_t* d_descriptors1,
+                                        const int32_t* d_node1, const uint8_t* d_has_mappoint1, const float* d_uright1,
+                                        const int32_t* d_counts1, int query_capacity, const orb_device_frames* frames2,
+                                        const int32_t* d_node2, const orb_triangulation_pair* d_pairs,
+                                        const float* scale_factors, const float* level_sigma2, int nlevels,
+                                        int check_orientation, void* d_scratch, int32_t* d_matches12, int32_t* d_nmatches,
+                                        void* stream);
 
 /* ---- Input stage and map-point descriptors (the callers either side of the path) ------ */
 

@@ -985,9 +985,12 @@ void project_last_frame(int n1, const float* Xw, const u8* mpFlags, const int* o
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...), ORBmatcher.cc:247-420. The DBoW2 FeatureVectors are given as
 // the node id of every feature (-1 = none): FeatureVector = std::map<node, indices in feature order>.
 // usable1[i]: KF feature i has a good map point. Output: matchOfKp = vpMapPointMatches as KF feature indices.
-int search_by_bow(const FrameView& KF, const int* node1, const u8* usable1, const FrameView& F, const int* node2, int th,
-                  float ratio, int checkOri, int* matchOfKp, int* matchOfQuery) {
-  OrderedSearch S{F, nullptr, std::vector<u8>(F.n, 0), SEARCH_RATIO, th, checkOri, ratio, matchOfKp, matchOfQuery};
+// unusable2 (may be null): frame-side features that are no candidates — SearchByBoW(KeyFrame*, KeyFrame*), :729-880, skips
+// keyframe-2 features without a good map point (and tests bestDist1 < TH_LOW: pass th = TH_LOW - 1).
+int search_by_bow(const FrameView& KF, const int* node1, const u8* usable1, const FrameView& F, const int* node2, const u8* unusable2,
+                  int th, float ratio, int checkOri, int* matchOfKp, int* matchOfQuery) {
+  OrderedSearch S{F, nullptr, unusable2 ? std::vector<u8>(unusable2, unusable2 + F.n) : std::vector<u8>(F.n, 0), SEARCH_RATIO, th,
+                  checkOri, ratio, matchOfKp, matchOfQuery};
   for (int i = 0; i < F.n; i++) matchOfKp[i] = -1;
   for (int i = 0; i < KF.n; i++) matchOfQuery[i] = -1;
   std::map<int, std::vector<int>> fv1, fv2;
@@ -1081,6 +1084,83 @@ int distinctive_descriptor(const u8* desc, int n) {
     if (median < bestMedian) { bestMedian = median; bestIdx = i; }
   }
   return bestIdx;
+}
+
+// ORBmatcher::SearchForTriangulation, ORBmatcher.cc:884-1100 (with CheckDistEpipolarLine :205-227). FeatureVectors
+// as per-feature node ids; ur1 / ur2 = mvuRight (may be null = monocular); hasMp = "GetMapPoint(idx) != NULL".
+struct TriPair { float F12[9]; float ex, ey; int onlyStereo; };
+static bool check_dist_epipolar_line(float x1, float y1, float x2, float y2, int oct2, const float* F12, const float* sigma2) {
+  const float a = x1 * F12[0] + y1 * F12[3] + F12[6];
+  const float b = x1 * F12[1] + y1 * F12[4] + F12[7];
+  const float c = x1 * F12[2] + y1 * F12[5] + F12[8];
+  const float num = a * x2 + b * y2 + c;
+  const float den = a * a + b * b;
+  if (den == 0) return false;
+  const float dsqr = num * num / den;
+  return dsqr < 3.84 * sigma2[oct2];
+}
+int search_for_triangulation(const FrameView& K1, const int* node1, const u8* hasMp1, const float* ur1, const FrameView& K2,
+                             const int* node2, const u8* hasMp2, const float* ur2, const TriPair& P, const float* sf,
+                             const float* sigma2, int checkOri, int* matches12) {
+  const int TH_LOW = 50;
+  int nmatches = 0;
+  std::vector<u8> matched2(K2.n, 0);
+  for (int i = 0; i < K1.n; i++) matches12[i] = -1;
+  std::vector<int> hist[30];
+  std::map<int, std::vector<int>> fv1, fv2;
+  for (int i = 0; i < K1.n; i++) if (node1[i] >= 0) fv1[node1[i]].push_back(i);
+  for (int i = 0; i < K2.n; i++) if (node2[i] >= 0) fv2[node2[i]].push_back(i);
+  auto it1 = fv1.begin(), it2 = fv2.begin();
+  while (it1 != fv1.end() && it2 != fv2.end()) {
+    if (it1->first == it2->first) {
+      for (int idx1 : it1->second) {
+        if (hasMp1[idx1]) continue;
+        const bool stereo1 = ur1 && ur1[idx1] >= 0;
+        if (P.onlyStereo && !stereo1) continue;
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (int idx2 : it2->second) {
+          if (matched2[idx2] || hasMp2[idx2]) continue;
+          const bool stereo2 = ur2 && ur2[idx2] >= 0;
+          if (P.onlyStereo && !stereo2) continue;
+          const int dist = hamming256(K1.desc + (size_t)idx1 * 32, K2.desc + (size_t)idx2 * 32);
+          if (dist > TH_LOW || dist > bestDist) continue;
+          if (!stereo1 && !stereo2) {
+            const float distex = P.ex - K2.xy[2 * idx2], distey = P.ey - K2.xy[2 * idx2 + 1];
+            if (distex * distex + distey * distey < 100 * sf[K2.octave[idx2]]) continue;
+          }
+          if (check_dist_epipolar_line(K1.xy[2 * idx1], K1.xy[2 * idx1 + 1], K2.xy[2 * idx2], K2.xy[2 * idx2 + 1], K2.octave[idx2],
+                                       P.F12, sigma2)) {
+            bestIdx2 = idx2;
+            bestDist = dist;
+          }
+        }
+        if (bestIdx2 >= 0) {
+          matches12[idx1] = bestIdx2;
+          matched2[bestIdx2] = 1;
+          nmatches++;
+          if (checkOri) {
+            float rot = K1.angle[idx1] - K2.angle[bestIdx2];
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)std::round(rot * (30 / 360.0f));
+            if (bin == 30) bin = 0;
+            if (bin >= 0 && bin < 30) hist[bin].push_back(idx1);
+          }
+        }
+      }
+      ++it1; ++it2;
+    } else if (it1->first < it2->first) it1 = fv1.lower_bound(it2->first);
+    else it2 = fv2.lower_bound(it1->first);
+  }
+  if (checkOri) {
+    int cnt[30], a, b, c;
+    for (int i = 0; i < 30; i++) cnt[i] = (int)hist[i].size();
+    three_maxima(cnt, 30, a, b, c);
+    for (int i = 0; i < 30; i++) {
+      if (i == a || i == b || i == c) continue;
+      for (int idx1 : hist[i]) { matches12[idx1] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
 }
 
 extern "C" {
@@ -1281,10 +1361,19 @@ void orc_project_last_frame(int n1, const float* Xw, const u8* mpFlags, const vo
   project_last_frame(n1, Xw, mpFlags, oct.data(), ang.data(), Tcw, cam4, bounds4, mbf, th, scaleFactors, dir, (ProjQuery*)out);
 }
 int orc_search_by_bow(const void* kps1, int n1, const u8* desc1, const int* node1, const u8* usable1, const void* kps2, int n2,
-                      const u8* desc2, const int* node2, int th, float ratio, int checkOri, int* matchOfKp, int* matchOfQuery) {
+                      const u8* desc2, const int* node2, const u8* unusable2, int th, float ratio, int checkOri, int* matchOfKp,
+                      int* matchOfQuery) {
   std::vector<float> xy1, ang1, xy2, ang2; std::vector<int> oct1, oct2;
   FrameView A = view_of(kps1, n1, desc1, xy1, oct1, ang1), B = view_of(kps2, n2, desc2, xy2, oct2, ang2);
-  return search_by_bow(A, node1, usable1, B, node2, th, ratio, checkOri, matchOfKp, matchOfQuery);
+  return search_by_bow(A, node1, usable1, B, node2, unusable2, th, ratio, checkOri, matchOfKp, matchOfQuery);
+}
+
+int orc_search_for_triangulation(const void* kps1, int n1, const u8* desc1, const int* node1, const u8* hasMp1, const float* ur1,
+                                 const void* kps2, int n2, const u8* desc2, const int* node2, const u8* hasMp2, const float* ur2,
+                                 const void* pair, const float* sf, const float* sigma2, int checkOri, int* matches12) {
+  std::vector<float> xy1, ang1, xy2, ang2; std::vector<int> oct1, oct2;
+  FrameView A = view_of(kps1, n1, desc1, xy1, oct1, ang1), B = view_of(kps2, n2, desc2, xy2, oct2, ang2);
+  return search_for_triangulation(A, node1, hasMp1, ur1, B, node2, hasMp2, ur2, *(const TriPair*)pair, sf, sigma2, checkOri, matches12);
 }
 
 // ---- input stage / map point descriptors

@@ -284,7 +284,7 @@ def project_last_frame(Xw, mp_flags, kps1, Tcw, cam4, bounds, mbf, th, scale_fac
     return out
 
 
-def search_by_bow(kps1, desc1, node1, usable1, kps2, desc2, node2, th=50, ratio=0.7, check_ori=True):
+def search_by_bow(kps1, desc1, node1, usable1, kps2, desc2, node2, th=50, ratio=0.7, check_ori=True, unusable2=None):
     """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...), ORBmatcher.cc:247. -> (nmatches, match_of_keypoint (over frame 2,
     values = keyframe feature indices), match_of_query (over keyframe features))."""
     kps1 = np.ascontiguousarray(kps1); kps2 = np.ascontiguousarray(kps2)
@@ -293,9 +293,31 @@ def search_by_bow(kps1, desc1, node1, usable1, kps2, desc2, node2, th=50, ratio=
     us = np.ascontiguousarray(usable1, np.uint8)
     n1, n2 = len(kps1), len(kps2)
     mk = np.full(max(n2, 1), -1, np.int32); mq = np.full(max(n1, 1), -1, np.int32)
-    nm = lib().orc_search_by_bow(_p(kps1), n1, _p(desc1), _p(node1), _p(us), _p(kps2), n2, _p(desc2), _p(node2), int(th),
+    un2 = None if unusable2 is None else np.ascontiguousarray(unusable2, np.uint8)
+    nm = lib().orc_search_by_bow(_p(kps1), n1, _p(desc1), _p(node1), _p(us), _p(kps2), n2, _p(desc2), _p(node2),
+                                 _p(un2) if un2 is not None else None, int(th),
                                  C.c_float(ratio), int(check_ori), _p(mk), _p(mq))
     return nm, mk[:n2], mq[:n1]
+
+
+TRI_PAIR_DTYPE = np.dtype([("F12", "<f4", (9,)), ("ex", "<f4"), ("ey", "<f4"), ("only_stereo", "<i4")])
+
+
+def search_for_triangulation(kps1, desc1, node1, has_mp1, ur1, kps2, desc2, node2, has_mp2, ur2, pair, scale_factors, level_sigma2,
+                             check_ori=True):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:884). -> (nmatches, matches12)."""
+    c = lambda a, t: np.ascontiguousarray(a, t)
+    kps1, kps2 = np.ascontiguousarray(kps1), np.ascontiguousarray(kps2)
+    desc1, desc2 = c(desc1, np.uint8), c(desc2, np.uint8)
+    node1, node2, has_mp1, has_mp2 = c(node1, np.int32), c(node2, np.int32), c(has_mp1, np.uint8), c(has_mp2, np.uint8)
+    u1 = None if ur1 is None else c(ur1, np.float32); u2 = None if ur2 is None else c(ur2, np.float32)
+    pair = np.ascontiguousarray(pair, TRI_PAIR_DTYPE).reshape(1)
+    sf, s2 = c(scale_factors, np.float32), c(level_sigma2, np.float32)
+    m12 = np.full(max(len(kps1), 1), -1, np.int32)
+    nm = lib().orc_search_for_triangulation(_p(kps1), len(kps1), _p(desc1), _p(node1), _p(has_mp1), _p(u1) if u1 is not None else None,
+                                            _p(kps2), len(kps2), _p(desc2), _p(node2), _p(has_mp2), _p(u2) if u2 is not None else None,
+                                            _p(pair), _p(sf), _p(s2), int(check_ori), _p(m12))
+    return nm, m12[:len(kps1)]
 
 
 def cvt_gray(img, blue_first=False):

@@ -48,6 +48,10 @@ class OrbDeviceFrames(C.Structure):
                 ("batch", C.c_int32), ("capacity", C.c_int32)]
 
 
+TRI_PAIR_DTYPE = np.dtype([("F12", "<f4", (9,)), ("ex", "<f4"), ("ey", "<f4"), ("only_stereo", "<i4")])
+assert TRI_PAIR_DTYPE.itemsize == 48
+
+
 class OrbSearchParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("th", C.c_int32), ("nn_ratio", C.c_float), ("check_orientation", C.c_int32)]
 
@@ -76,7 +80,7 @@ EXPORTS = [
     "orb_search_for_initialization", "orb_match_pairs_device", "orb_match_allpairs_device",
     "orb_hamming_matrix_device", "orb_matcher_synchronize", "orb_int_pipe_peak",
     "orb_search_scratch_bytes", "orb_project_last_frame_device", "orb_search_by_projection_device",
-    "orb_search_by_bow_device",
+    "orb_search_by_bow_device", "orb_search_for_triangulation_device",
     "orb_cvt_color_gray_device", "orb_remap_linear_device", "orb_distinctive_descriptors_device",
 ]
 
@@ -132,6 +136,8 @@ def lib():
         L.orb_hamming_matrix_device.argtypes = [vp, vp, i32, vp, i32, vp, vp]
         L.orb_matcher_synchronize.argtypes = [vp, vp]
         L.orb_int_pipe_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
+        L.orb_search_for_triangulation_device.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(OrbDeviceFrames), vp, vp, vp, vp, i32,
+                                                          i32, vp, vp, vp, vp]
         L.orb_cvt_color_gray_device.argtypes = [i32, vp, i32, i32, sz, sz, i32, i32, vp, sz, sz, vp]
         L.orb_remap_linear_device.argtypes = [i32, vp, i32, i32, sz, sz, i32, vp, vp, i32, i32, vp, sz, sz, vp]
         L.orb_distinctive_descriptors_device.argtypes = [i32, vp, vp, i32, i32, vp, vp, vp]

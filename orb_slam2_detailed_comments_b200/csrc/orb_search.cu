@@ -79,7 +79,8 @@ __device__ __forceinline__ unsigned group_mask(int lane) {
 
 // The four smallest (distance, visiting rank) keys among candidates t = 0..total-1, G lanes per query;
 // wordOf(t) returns the candidate word or -1 when the candidate is filtered out before the occupancy test.
-template <int G, class WordFn, class OccFn>
+// REV: ties go to the LATER candidate (SearchForTriangulation's `dist > bestDist` test), so the rank is stored reversed.
+template <int G, bool REV = false, class WordFn, class OccFn>
 __device__ __forceinline__ void group_top4(int total, WordFn wordOf, OccFn occ, const uint4 q0, const uint4 q1, const u8* desc,
                                            const float* uright, float ur, float radius, int lane, Top4& T) {
   const unsigned gm = group_mask<G>(lane);
@@ -97,13 +98,14 @@ __device__ __forceinline__ void group_top4(int total, WordFn wordOf, OccFn occ, 
           const float r = uright[word_idx(w)];
           if (r > 0.f && fabsf(__fsub_rn(ur, r)) > radius) ok = false;
         }
-        if (ok) key = ((unsigned)hamming256(q0, q1, desc + (size_t)word_idx(w) * 32) << 22) | (unsigned)t;
+        if (ok) key = ((unsigned)hamming256(q0, q1, desc + (size_t)word_idx(w) * 32) << 22) | (unsigned)(REV ? 0x3fffff - t : t);
       }
     }
     for (;;) {
       const unsigned m = __reduce_min_sync(gm, key);
       if (m >= T.k[3]) break;
-      const int mw = __shfl_sync(gm, w, (int)(m & 0x3fffffu) - t0, G);   // the rank in the key names the owner lane
+      const int rk = (int)(m & 0x3fffffu);
+      const int mw = __shfl_sync(gm, w, (REV ? 0x3fffff - rk : rk) - t0, G);   // the rank in the key names the owner lane
       top4_insert(T, m, mw);
       if (key == m) key = kNoKey;
     }
@@ -178,12 +180,66 @@ struct SearchArgs {
   // BoW source (bow != 0): queries are keyframe features in (node, index) order
   int bow;
   const orb_keypoint* kps1; const u8* usable1;
+  // SearchForTriangulation (tri != null, on top of the BoW source): usable1 = "has a map point" (inverted), epipolar filters
+  const orb_triangulation_pair* tri; const float* ur1;
+  float sf[kMaxLevels], sigma2[kMaxLevels];
   // scratch
   uint4* top; int* order1; int* cb; int* ce; int* sorted2; int* node2s; int* mqP; int* meta;
   // params / outputs
   int mode, th, checkOri; float ratio;
   int* matchOfKp; int* matchOfQuery; int* nmatches;
 };
+
+// ORBmatcher::CheckDistEpipolarLine (ORBmatcher.cc:205-227) and the epipole test of SearchForTriangulation (:958-965)
+__device__ __forceinline__ bool tri_candidate_ok(const SearchArgs& A, const orb_triangulation_pair& P, float x1, float y1, bool stereo1,
+                                                 const orb_keypoint& kp2, bool stereo2) {
+  if (P.only_stereo && !stereo2) return false;
+  const int oct = min(max(kp2.octave, 0), kMaxLevels - 1);
+  if (!stereo1 && !stereo2) {
+    const float dx = __fsub_rn(P.ex, kp2.x), dy = __fsub_rn(P.ey, kp2.y);
+    if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, A.sf[oct])) return false;
+  }
+  const float a = __fadd_rn(__fadd_rn(__fmul_rn(x1, P.F12[0]), __fmul_rn(y1, P.F12[3])), P.F12[6]);
+  const float b = __fadd_rn(__fadd_rn(__fmul_rn(x1, P.F12[1]), __fmul_rn(y1, P.F12[4])), P.F12[7]);
+  const float c = __fadd_rn(__fadd_rn(__fmul_rn(x1, P.F12[2]), __fmul_rn(y1, P.F12[5])), P.F12[8]);
+  const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, kp2.x), __fmul_rn(b, kp2.y)), c);
+  const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+  if (den == 0.f) return false;
+  const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+  return (double)dsqr < __dmul_rn(3.84, (double)A.sigma2[oct]);
+}
+
+// One query of the BoW-ordered searches: keyframe feature at position q of the (node, index) order against the
+// frame features of the same vocabulary node.
+template <int G, class OccFn>
+__device__ __forceinline__ void bow_score(const SearchArgs& A, int b, int q, OccFn occ, int lane, Top4& T) {
+  top4_clear(T);
+  const int i1 = A.order1[(size_t)b * A.qcap + q];
+  const int c0 = A.cb[(size_t)b * A.qcap + q], c1 = A.ce[(size_t)b * A.qcap + q];
+  const uint4* qd = reinterpret_cast<const uint4*>(A.qdesc + ((size_t)b * A.qcap + i1) * 32);
+  const int* s2 = A.sorted2 + (size_t)b * A.cap;
+  const u8* D = A.desc + (size_t)b * A.cap * 32;
+  const bool flag = A.usable1[(size_t)b * A.qcap + i1] != 0;
+  if (!A.tri) {
+    if (!flag) return;
+    const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
+    group_top4<G>(c1 - c0, [&](int t) { return s2[c0 + t]; }, occ, q0, q1, D, nullptr, 0.f, 0.f, lane, T);
+  } else {
+    const orb_triangulation_pair P = A.tri[b];
+    const bool stereo1 = A.ur1 && A.ur1[(size_t)b * A.qcap + i1] >= 0.f;
+    if (flag || (P.only_stereo && !stereo1)) return;      // :927-936: has a map point already / monocular feature
+    const orb_keypoint kp1 = A.kps1[(size_t)b * A.qcap + i1];
+    const orb_keypoint* K2 = A.kps + (size_t)b * A.cap;
+    const float* UR2 = A.uright ? A.uright + (size_t)b * A.cap : nullptr;
+    const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
+    group_top4<G, true>(c1 - c0,
+                        [&](int t) {
+                          const int i2 = s2[c0 + t];
+                          return tri_candidate_ok(A, P, kp1.x, kp1.y, stereo1, K2[i2], UR2 && UR2[i2] >= 0.f) ? i2 : -1;
+                        },
+                        occ, q0, q1, D, nullptr, 0.f, 0.f, lane, T);
+  }
+}
 
 // ---- pass 1: score every query against the frame's initial state, kScanGroup lanes per query
 constexpr int kScanGroup = 8;
@@ -217,14 +273,7 @@ __global__ void __launch_bounds__(32 * kScanWarps) k_search_scan(const SearchArg
                     A.uright ? A.uright + (size_t)b * A.cap : nullptr, Q.ur, Q.radius, lane, T);
     }
   } else {
-    const int i1 = A.order1[(size_t)b * A.qcap + q];
-    if (A.usable1[(size_t)b * A.qcap + i1]) {
-      const int c0 = A.cb[(size_t)b * A.qcap + q], c1 = A.ce[(size_t)b * A.qcap + q];
-      const uint4* qd = reinterpret_cast<const uint4*>(A.qdesc + ((size_t)b * A.qcap + i1) * 32);
-      const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
-      const int* s2 = A.sorted2 + (size_t)b * A.cap;
-      group_top4<G>(c1 - c0, [&](int t) { return s2[c0 + t]; }, [&](int) { return false; }, q0, q1, D, nullptr, 0.f, 0.f, lane, T);
-    }
+    bow_score<G>(A, b, q, [&](int idx) { return occ0 && occ0[idx]; }, lane, T);
   }
   if (gl == 0) {
     uint4* o = A.top + ((size_t)b * A.qcap + q) * 2;
@@ -372,12 +421,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_search_commit(const SearchAr
                        lane, X);
         __syncwarp();
       } else {
-        const int i1 = order1[qq];
-        const int c0 = A.cb[(size_t)b * A.qcap + qq], c1 = A.ce[(size_t)b * A.qcap + qq];
-        const uint4* qd = reinterpret_cast<const uint4*>(A.qdesc + ((size_t)b * A.qcap + i1) * 32);
-        const uint4 d0 = __ldg(qd), d1 = __ldg(qd + 1);
-        const int* s2 = A.sorted2 + (size_t)b * A.cap;
-        group_top4<32>(c1 - c0, [&](int t) { return s2[c0 + t]; }, taken, d0, d1, D, nullptr, 0.f, 0.f, lane, X);
+        bow_score<32>(A, b, qq, taken, lane, X);
       }
       if (lane == 0) {
         const int np = accept_match(A.mode, A.th, A.ratio, X.k[0], X.i[0], X.k[1], X.i[1]) ? word_idx(X.i[0]) : -1;
@@ -565,7 +609,7 @@ __global__ void __launch_bounds__(256) k_bow_prepare(const SearchArgs A, const i
 }
 
 struct ScratchLayout {
-  size_t top, order1, cb, ce, sorted2, node2s, mqP, meta, total;
+  size_t top, order1, cb, ce, sorted2, node2s, mqP, mk, meta, total;
 };
 
 ScratchLayout scratch_layout(int batch, int qcap, int cap) {
@@ -579,6 +623,7 @@ ScratchLayout scratch_layout(int batch, int qcap, int cap) {
   L.mqP = take((size_t)batch * qcap * 4);
   L.sorted2 = take((size_t)batch * cap * 4);
   L.node2s = take((size_t)batch * cap * 4);
+  L.mk = take((size_t)batch * cap * 4);
   L.meta = take((size_t)batch * 16);
   L.total = o;
   return L;
@@ -586,7 +631,7 @@ ScratchLayout scratch_layout(int batch, int qcap, int cap) {
 
 int fill_common(SearchArgs& A, const orb_device_frames* F, int qcap, const orb_search_params* P, void* scratch, int32_t* mk,
                 int32_t* mq, int32_t* nm) {
-  if (!F || !P || !scratch || !mk || !mq || !nm) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (!F || !P || !scratch || !mq || !nm) ORB_FAIL(ORB_ERR_INVALID, "null argument");
   if (!F->keypoints_un || !F->descriptors || !F->counts || F->batch <= 0 || F->capacity <= 0 || qcap <= 0)
     ORB_FAIL(ORB_ERR_INVALID, "bad frame description");
   if (P->mode < ORB_SEARCH_BEST || P->mode > ORB_SEARCH_RATIO) ORB_FAIL(ORB_ERR_INVALID, "unknown search mode");
@@ -603,7 +648,7 @@ int fill_common(SearchArgs& A, const orb_device_frames* F, int qcap, const orb_s
   A.top = (uint4*)(s + L.top); A.order1 = (int*)(s + L.order1); A.cb = (int*)(s + L.cb); A.ce = (int*)(s + L.ce);
   A.sorted2 = (int*)(s + L.sorted2); A.node2s = (int*)(s + L.node2s); A.mqP = (int*)(s + L.mqP); A.meta = (int*)(s + L.meta);
   A.mode = P->mode; A.th = P->th; A.ratio = P->nn_ratio; A.checkOri = P->check_orientation;
-  A.matchOfKp = mk; A.matchOfQuery = mq; A.nmatches = nm;
+  A.matchOfKp = mk ? mk : (int*)(s + L.mk); A.matchOfQuery = mq; A.nmatches = nm;
   return ORB_OK;
 }
 
@@ -678,7 +723,7 @@ int orb_search_by_bow_device(int device, const orb_keypoint* d_keypoints1, const
     ORB_FAIL(ORB_ERR_INVALID, "null argument");
   ORB_CUDA(cudaSetDevice(device));
   A.bow = 1; A.kps1 = d_keypoints1; A.usable1 = d_usable1; A.qdesc = d_descriptors1; A.qcounts = d_counts1;
-  A.uright = nullptr; A.occupied = nullptr;
+  A.uright = nullptr;
   int N = 2;
   while (N < std::max(query_capacity, frames->capacity)) N <<= 1;
   const size_t smem = (size_t)N * 8;
@@ -687,6 +732,38 @@ int orb_search_by_bow_device(int device, const orb_keypoint* d_keypoints1, const
   k_bow_prepare<<<frames->batch, 256, smem, (cudaStream_t)stream>>>(A, d_node1, d_counts1, d_node2);
   ORB_CUDA(cudaGetLastError());
   return launch_search(A, frames->batch, (cudaStream_t)stream);
+}
+
+int orb_search_for_triangulation_device(int device, const orb_keypoint* d_keypoints1, const uint8_t* d_descriptors1,
+                                        const int32_t* d_node1, const uint8_t* d_has_mappoint1, const float* d_uright1,
+                                        const int32_t* d_counts1, int query_capacity, const orb_device_frames* frames2,
+                                        const int32_t* d_node2, const orb_triangulation_pair* d_pairs,
+                                        const float* scale_factors, const float* level_sigma2, int nlevels,
+                                        int check_orientation, void* d_scratch, int32_t* d_matches12, int32_t* d_nmatches,
+                                        void* stream) {
+  if (!d_pairs || !scale_factors || !level_sigma2) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (nlevels <= 0 || nlevels > kMaxLevels) ORB_FAIL(ORB_ERR_UNSUPPORTED, "1..16 pyramid levels");
+  orb_search_params sp;
+  sp.mode = ORB_SEARCH_BEST; sp.th = 50 /* TH_LOW, ORBmatcher.cc:49 */; sp.nn_ratio = 0.f; sp.check_orientation = check_orientation;
+  SearchArgs A;
+  const int st = fill_common(A, frames2, query_capacity, &sp, d_scratch, nullptr, d_matches12, d_nmatches);
+  if (st) return st;
+  if (!d_keypoints1 || !d_descriptors1 || !d_node1 || !d_has_mappoint1 || !d_counts1 || !d_node2) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  ORB_CUDA(cudaSetDevice(device));
+  A.bow = 1; A.kps1 = d_keypoints1; A.usable1 = d_has_mappoint1; A.qdesc = d_descriptors1; A.qcounts = d_counts1;
+  A.tri = d_pairs; A.ur1 = d_uright1;
+  for (int i = 0; i < kMaxLevels; i++) {
+    A.sf[i] = scale_factors[std::min(i, nlevels - 1)];
+    A.sigma2[i] = level_sigma2[std::min(i, nlevels - 1)];
+  }
+  int N = 2;
+  while (N < std::max(query_capacity, frames2->capacity)) N <<= 1;
+  const size_t smem = (size_t)N * 8;
+  if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many features for the BoW ordering kernel");
+  if (smem > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_bow_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bow_prepare<<<frames2->batch, 256, smem, (cudaStream_t)stream>>>(A, d_node1, d_counts1, d_node2);
+  ORB_CUDA(cudaGetLastError());
+  return launch_search(A, frames2->batch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import (ORB_SEARCH_BEST, ORB_SEARCH_RATIO, ORB_SEARCH_RATIO_LEVEL, PROJ_QUERY_DTYPE, OrbDeviceFrames,
+from ._lib import (ORB_SEARCH_BEST, ORB_SEARCH_RATIO, ORB_SEARCH_RATIO_LEVEL, PROJ_QUERY_DTYPE, TRI_PAIR_DTYPE, OrbDeviceFrames,
                    OrbSearchParams, check, lib, ptr)
 
 TH_HIGH, TH_LOW = 100, 50   # src/ORBmatcher.cc:47-49
@@ -96,3 +96,25 @@ def SearchByBoW(d_kps1, d_desc1, d_node1, d_usable1, d_counts1, frames, d_node2,
                                          d_kps1.shape[1], C.byref(frames), ptr(d_node2), C.byref(p), ptr(d_scratch),
                                          ptr(d_match_of_keypoint), ptr(d_match_of_query), ptr(d_nmatches),
                                          C.c_void_p(stream or 0)))
+
+
+def epipole(K2_fx, K2_fy, K2_cx, K2_cy, R2w, t2w, Cw):
+    """ex, ey of SearchForTriangulation (ORBmatcher.cc:893-901): keyframe 1's camera centre Cw in keyframe 2's image
+    (float32, cv::gemm order, invz = 1.0f / z in float)."""
+    f = np.float32
+    R, t, C_ = np.asarray(R2w, f), np.asarray(t2w, f).reshape(3), np.asarray(Cw, f).reshape(3)
+    c2 = [f(_mul3(R[r, 0], C_[0], R[r, 1], C_[1], R[r, 2], C_[2]) + t[r]) for r in range(3)]
+    invz = f(f(1.0) / c2[2])
+    return f(f(f(f(K2_fx) * c2[0]) * invz) + f(K2_cx)), f(f(f(f(K2_fy) * c2[1]) * invz) + f(K2_cy))
+
+
+def SearchForTriangulation(d_kps1, d_desc1, d_node1, d_has_mp1, d_uright1, d_counts1, frames2, d_node2, d_pairs, scale_factors,
+                           level_sigma2, check_orientation, d_scratch, d_matches12, d_nmatches, device=0, stream=None):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:884) for a batch of keyframe pairs. frames2 = device_frames(mvKeysUn,
+    mDescriptors, N, bounds (unused), uright = mvuRight, occupied = "has a map point") of keyframe 2; d_pairs: (B, 48) u8 tensor of
+    TRI_PAIR_DTYPE records."""
+    sf = np.ascontiguousarray(scale_factors, np.float32); s2 = np.ascontiguousarray(level_sigma2, np.float32)
+    check(lib().orb_search_for_triangulation_device(device, ptr(d_kps1), ptr(d_desc1), ptr(d_node1), ptr(d_has_mp1), ptr(d_uright1),
+                                                    ptr(d_counts1), d_kps1.shape[1], C.byref(frames2), ptr(d_node2), ptr(d_pairs), ptr(sf),
+                                                    ptr(s2), len(sf), int(bool(check_orientation)), ptr(d_scratch), ptr(d_matches12),
+                                                    ptr(d_nmatches), C.c_void_p(stream or 0)))

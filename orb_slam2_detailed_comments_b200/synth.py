@@ -131,3 +131,28 @@ def tracking_scene(n_cur, n_last, seed, w=1241, h=376, fx=718.856, cx=607.1928, 
     return {"cur": cur, "cur_desc": cur_desc, "uright": uright, "occupied0": occupied0, "Tcw": Tcw, "last": last, "Xw": Xw,
             "mp_desc": mp_desc, "mp_flags": flags, "cam4": np.array([fx, fx, cx, cy], f32),
             "bounds": np.array([0, w, 0, h], f32), "mbf": f32(bf), "mb": f32(bf / fx), "src": src}
+
+
+def triangulation_pair(sc, seed):
+    """A keyframe pair for SearchForTriangulation from a tracking_scene: keyframe 1 = the scene's last frame (at the
+    identity pose), keyframe 2 = its current frame (pose Tcw). Returns the fundamental matrix F12 (x1^T F12 x2 = 0),
+    the epipole of camera 1 in image 2 and random map-point / stereo flags."""
+    rng = np.random.RandomState(seed & 0x7FFFFFFF)
+    f32 = np.float32
+    fx, fy, cx, cy = [float(v) for v in sc["cam4"]]
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    R = sc["Tcw"][:3, :3].astype(np.float64); t = sc["Tcw"][:3, 3].astype(np.float64)
+    # X2 = R X1 + t  ->  E21 = [t]x R with x2^T E21 x1 = 0;  F12 = (K^-T E21 K^-1)^T
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    Kinv = np.linalg.inv(K)
+    F21 = Kinv.T @ (tx @ R) @ Kinv
+    F12 = (F21.T / np.abs(F21).max()).astype(f32)
+    e = K @ t                                        # camera centre 1 (origin) seen from camera 2
+    n1, n2 = len(sc["last"]), len(sc["cur"])
+    kps1 = sc["last"].copy()                         # keyframe 1 sees the world points from the identity pose
+    X = sc["Xw"].astype(np.float64)
+    z = np.where(np.abs(X[:, 2]) > 1e-3, X[:, 2], 1.0)
+    kps1["x"] = (fx * X[:, 0] / z + cx).astype(f32); kps1["y"] = (fy * X[:, 1] / z + cy).astype(f32)
+    return {"kps1": kps1, "F12": F12.reshape(9), "ex": f32(e[0] / e[2]), "ey": f32(e[1] / e[2]),
+            "has_mp1": (rng.rand(n1) < 0.3).astype(np.uint8), "has_mp2": (rng.rand(n2) < 0.3).astype(np.uint8),
+            "ur1": np.where(rng.rand(n1) < 0.5, sc["last"]["x"] - 5, -1).astype(f32)}

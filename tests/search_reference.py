@@ -147,8 +147,9 @@ def search_last_frame(F, occupied0, last_kps, Xw, mp_flags, mp_desc, Tcw, cam4, 
     return nm, match_kp
 
 
-def search_by_bow(k1, d1, node1, usable1, k2, d2, node2, nnratio=0.7, check_ori=True, TH_LOW=50):
-    """ORBmatcher.cc:247-420 with FeatureVectors rebuilt from per-feature node ids."""
+def search_by_bow(k1, d1, node1, usable1, k2, d2, node2, nnratio=0.7, check_ori=True, TH_LOW=50, usable2=None, strict=False):
+    """ORBmatcher.cc:247-420 with FeatureVectors rebuilt from per-feature node ids; usable2 + strict = the
+    keyframe-keyframe variant :729-880 (candidates need a good map point, bestDist1 < TH_LOW)."""
     fv1, fv2 = {}, {}
     for i, n in enumerate(node1):
         if n >= 0: fv1.setdefault(int(n), []).append(i)
@@ -162,11 +163,61 @@ def search_by_bow(k1, d1, node1, usable1, k2, d2, node2, nnratio=0.7, check_ori=
             b1, b2, bi = 256, 256, -1
             for i2 in fv2[node]:
                 if match[i2] >= 0: continue
+                if usable2 is not None and not usable2[i2]: continue
                 d = hamming(d1[i1], d2[i2])
                 if d < b1: b2, b1, bi = b1, d, i2
                 elif d < b2: b2 = d
-            if b1 <= TH_LOW and f32(b1) < f32(f32(nnratio) * f32(b2)):
+            if (b1 < TH_LOW if strict else b1 <= TH_LOW) and f32(b1) < f32(f32(nnratio) * f32(b2)):
                 match[bi] = i1; nm += 1
                 if check_ori: hist[rot_bin(k1["angle"][i1], k2["angle"][bi])].append(bi)
     if check_ori: nm = finish(hist, match, nm)
     return nm, match
+
+
+def search_for_triangulation(k1, d1, node1, has_mp1, ur1, k2, d2, node2, has_mp2, ur2, F12, ex, ey, only_stereo, sf, sigma2,
+                             check_ori=True, TH_LOW=50):
+    """ORBmatcher.cc:884-1100 + CheckDistEpipolarLine :205-227."""
+    fv1, fv2 = {}, {}
+    for i, n in enumerate(node1):
+        if n >= 0: fv1.setdefault(int(n), []).append(i)
+    for i, n in enumerate(node2):
+        if n >= 0: fv2.setdefault(int(n), []).append(i)
+    F = np.asarray(F12, f32).reshape(3, 3)
+    matched2 = [False] * len(k2); m12 = [-1] * len(k1); nm = 0
+    hist = [[] for _ in range(30)]
+    for node in sorted(set(fv1) & set(fv2)):
+        for i1 in fv1[node]:
+            if has_mp1[i1]: continue
+            st1 = ur1 is not None and ur1[i1] >= 0
+            if only_stereo and not st1: continue
+            x1, y1 = f32(k1["x"][i1]), f32(k1["y"][i1])
+            best, bi = TH_LOW, -1
+            for i2 in fv2[node]:
+                if matched2[i2] or has_mp2[i2]: continue
+                st2 = ur2 is not None and ur2[i2] >= 0
+                if only_stereo and not st2: continue
+                d = hamming(d1[i1], d2[i2])
+                if d > TH_LOW or d > best: continue
+                x2, y2, o2 = f32(k2["x"][i2]), f32(k2["y"][i2]), int(k2["octave"][i2])
+                if not st1 and not st2:
+                    dx, dy = f32(f32(ex) - x2), f32(f32(ey) - y2)
+                    if f32(f32(dx * dx) + f32(dy * dy)) < f32(f32(100) * f32(sf[o2])): continue
+                a = f32(f32(f32(x1 * F[0, 0]) + f32(y1 * F[1, 0])) + F[2, 0])
+                b = f32(f32(f32(x1 * F[0, 1]) + f32(y1 * F[1, 1])) + F[2, 1])
+                c = f32(f32(f32(x1 * F[0, 2]) + f32(y1 * F[1, 2])) + F[2, 2])
+                num = f32(f32(f32(a * x2) + f32(b * y2)) + c)
+                den = f32(f32(a * a) + f32(b * b))
+                if den == 0: continue
+                dsqr = f32(f32(num * num) / den)
+                if np.float64(dsqr) < np.float64(3.84) * np.float64(f32(sigma2[o2])):
+                    bi, best = i2, d
+            if bi >= 0:
+                m12[i1] = bi; matched2[bi] = True; nm += 1
+                if check_ori: hist[rot_bin(k1["angle"][i1], k2["angle"][bi])].append(i1)
+    if check_ori:
+        a, b, c = three_maxima([len(h) for h in hist])
+        for i in range(30):
+            if i in (a, b, c): continue
+            for i1 in hist[i]:
+                m12[i1] = -1; nm -= 1
+    return nm, m12

@@ -143,8 +143,88 @@ def test_search_by_bow(oracle, seed, nodes, ori):
     for b, s in enumerate(sc):
         n, m = bt.counts[b], bt.qcounts[b]
         rn, rk, rq = oracle.search_by_bow(s["last"], s["mp_desc"], node1[b, :m], s["mp_flags"] & 1, s["cur"], s["cur_desc"], node2[b, :n],
-                                          50, 0.7, ori)
+                                          50, 0.7, ori, unusable2=s["occupied0"])   # bt.frames carries the occupancy
         assert nm[b] == rn
         assert np.array_equal(mk[b, :n], rk) and np.array_equal(mq[b, :m], rq)
         total += rn
     assert total > 300
+
+
+def test_search_by_bow_keyframe_pair(oracle):
+    """SearchByBoW(KeyFrame*, KeyFrame*) (ORBmatcher.cc:729) through the same entry point: unusable keyframe-2 features
+    as initial occupancy, th = TH_LOW - 1."""
+    import torch
+    from orb_slam2_detailed_comments_b200 import search
+    sc = scenes_ragged(1100, flip_bits=60)
+    bt = Batch(sc, 2100, 2200)
+    B = len(sc)
+    rng = np.random.RandomState(11)
+    node1 = np.full((B, bt.qcap), -1, np.int32); node2 = np.full((B, bt.cap), -1, np.int32)
+    unusable2 = np.zeros((B, bt.cap), np.uint8)
+    for b, s in enumerate(sc):
+        n, m = bt.counts[b], bt.qcounts[b]
+        node2[b, :n] = rng.randint(0, 60, n)
+        if n and m:
+            node1[b, :m] = np.where(rng.rand(m) < 0.85, node2[b, :n][s["src"][:m] % n], rng.randint(0, 60, m))
+        unusable2[b, :n] = rng.rand(n) < 0.3
+    d_n1 = torch.from_numpy(node1).cuda(); d_n2 = torch.from_numpy(node2).cuda()
+    d_us = (bt.d_fl & 1).contiguous()
+    d_un2 = torch.from_numpy(unusable2).cuda()
+    frames = search.device_frames(bt.d_kps, bt.d_desc, bt.d_counts, bt.bounds, None, None, None, d_un2)
+    search.SearchByBoW(bt.d_last, bt.d_mpd, d_n1, d_us, bt.d_qcounts, frames, d_n2, 0.8, True, bt.d_scratch, bt.d_mk, bt.d_mq, bt.d_nm,
+                       th=search.TH_LOW - 1)
+    torch.cuda.synchronize()
+    mk, mq, nm = bt.d_mk.cpu().numpy(), bt.d_mq.cpu().numpy(), bt.d_nm.cpu().numpy()
+    total = 0
+    for b, s in enumerate(sc):
+        n, m = bt.counts[b], bt.qcounts[b]
+        rn, rk, rq = oracle.search_by_bow(s["last"], s["mp_desc"], node1[b, :m], s["mp_flags"] & 1, s["cur"], s["cur_desc"], node2[b, :n],
+                                          49, 0.8, True, unusable2=unusable2[b, :n])
+        assert nm[b] == rn and np.array_equal(mk[b, :n], rk) and np.array_equal(mq[b, :m], rq)
+        total += rn
+    assert total > 200
+
+
+@pytest.mark.parametrize("seed,only_stereo,mono", [(1200, 0, False), (1300, 1, False), (1400, 0, True)])
+def test_search_for_triangulation(oracle, seed, only_stereo, mono):
+    import torch
+    from orb_slam2_detailed_comments_b200 import search
+    from orb_slam2_detailed_comments_b200._lib import TRI_PAIR_DTYPE
+    from orb_slam2_detailed_comments_b200.synth import triangulation_pair
+    sc = scenes_ragged(seed, flip_bits=50, noise_px=1.0)
+    tps = [triangulation_pair(s, seed + i) for i, s in enumerate(sc)]
+    for s, tp in zip(sc, tps):          # keyframe 1 = the scene's map-point side, seen from the identity pose
+        tp["kps1"] = tp["kps1"][:len(s["last"])]; tp["has_mp1"] = tp["has_mp1"][:len(s["last"])]; tp["ur1"] = tp["ur1"][:len(s["last"])]
+        tp["has_mp2"] = tp["has_mp2"][:len(s["cur"])]
+        s["last"] = tp["kps1"]
+    bt = Batch(sc, 2100, 2200)
+    B = len(sc)
+    rng = np.random.RandomState(seed)
+    node1 = np.full((B, bt.qcap), -1, np.int32); node2 = np.full((B, bt.cap), -1, np.int32)
+    has1 = np.zeros((B, bt.qcap), np.uint8); has2 = np.zeros((B, bt.cap), np.uint8); ur1 = np.full((B, bt.qcap), -1, np.float32)
+    pairs = np.zeros(B, TRI_PAIR_DTYPE)
+    for b, (s, tp) in enumerate(zip(sc, tps)):
+        n, m = bt.counts[b], bt.qcounts[b]
+        node2[b, :n] = rng.randint(0, 80, n)
+        if n and m:
+            node1[b, :m] = np.where(rng.rand(m) < 0.85, node2[b, :n][s["src"][:m] % n], rng.randint(0, 80, m))
+        has1[b, :m], has2[b, :n], ur1[b, :m] = tp["has_mp1"], tp["has_mp2"], tp["ur1"]
+        pairs["F12"][b] = tp["F12"]; pairs["ex"][b], pairs["ey"][b], pairs["only_stereo"][b] = tp["ex"], tp["ey"], only_stereo
+    SIG = (SF * SF).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d_has2 = t(has2)
+    frames2 = search.device_frames(bt.d_kps, bt.d_desc, bt.d_counts, bt.bounds, None, None, None if mono else bt.d_ur, d_has2)
+    d_m12 = torch.full((B, bt.qcap), -7, dtype=torch.int32, device="cuda")
+    search.SearchForTriangulation(bt.d_last, bt.d_mpd, t(node1), t(has1), None if mono else t(ur1), bt.d_qcounts, frames2, t(node2),
+                                  t(pairs.view(np.uint8).reshape(B, 48)), SF, SIG, True, bt.d_scratch, d_m12, bt.d_nm)
+    torch.cuda.synchronize()
+    m12, nm = d_m12.cpu().numpy(), bt.d_nm.cpu().numpy()
+    total = 0
+    for b, (s, tp) in enumerate(zip(sc, tps)):
+        n, m = bt.counts[b], bt.qcounts[b]
+        rn, r12 = oracle.search_for_triangulation(s["last"], s["mp_desc"], node1[b, :m], has1[b, :m], None if mono else ur1[b, :m], s["cur"],
+                                                  s["cur_desc"], node2[b, :n], has2[b, :n], None if mono else s["uright"], pairs[b], SF, SIG, True)
+        assert nm[b] == rn, (b, nm[b], rn)
+        assert np.array_equal(m12[b, :m], r12) and np.all(m12[b, m:] == -1)
+        total += rn
+    assert total > (60 if only_stereo else 200), total

@@ -97,3 +97,43 @@ def test_projection_arithmetic_matches_cv2_gemm(oracle):
         v = np.float32(np.float32(np.float32(cam4[1] * c[1, 0]) * invz) + cam4[3])
         assert q["flags"][i] & 1 and q["u"][i] == u and q["v"][i] == v
         assert q["ur"][i] == np.float32(u - np.float32(np.float32(40.0) * invz))
+
+
+def test_search_by_bow_keyframe_pair(oracle):
+    """SearchByBoW(KeyFrame*, KeyFrame*) (ORBmatcher.cc:729): candidates need a map point, strict threshold."""
+    sc = tracking_scene(500, 450, 31, flip_bits=60)
+    rng = np.random.RandomState(31)
+    node2 = rng.randint(0, 30, 500).astype(np.int32)
+    node1 = np.where(rng.rand(450) < 0.85, node2[sc["src"]], rng.randint(0, 30, 450)).astype(np.int32)
+    usable1 = sc["mp_flags"] & 1
+    usable2 = (rng.rand(500) < 0.7).astype(np.uint8)
+    nm, mk, mq = oracle.search_by_bow(sc["last"], sc["mp_desc"], node1, usable1, sc["cur"], sc["cur_desc"], node2, 49, 0.8, True,
+                                      unusable2=1 - usable2)
+    nm_ref, mk_ref = R.search_by_bow(sc["last"], sc["mp_desc"], node1, usable1, sc["cur"], sc["cur_desc"], node2, 0.8, True,
+                                     usable2=usable2, strict=True)
+    assert nm == nm_ref and nm > 20 and mk.tolist() == mk_ref
+    assert np.all(usable2[mq[mq >= 0]] == 1)
+
+
+SIGMA2 = (SF * SF).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed,only_stereo,mono", [(41, 0, False), (42, 1, False), (43, 0, True)])
+def test_search_for_triangulation(oracle, seed, only_stereo, mono):
+    from orb_slam2_detailed_comments_b200.synth import triangulation_pair
+    sc = tracking_scene(500, 450, seed, flip_bits=50, noise_px=1.0)
+    tp = triangulation_pair(sc, seed)
+    rng = np.random.RandomState(seed)
+    node2 = rng.randint(0, 25, 500).astype(np.int32)
+    node1 = np.where(rng.rand(450) < 0.85, node2[sc["src"]], rng.randint(0, 25, 450)).astype(np.int32)
+    ur1 = None if mono else tp["ur1"]; ur2 = None if mono else sc["uright"]
+    pair = np.zeros(1, oracle.TRI_PAIR_DTYPE)
+    pair["F12"][0] = tp["F12"]; pair["ex"], pair["ey"], pair["only_stereo"] = tp["ex"], tp["ey"], only_stereo
+    nm, m12 = oracle.search_for_triangulation(tp["kps1"], sc["mp_desc"], node1, tp["has_mp1"], ur1, sc["cur"], sc["cur_desc"], node2,
+                                              tp["has_mp2"], ur2, pair, SF, SIGMA2, True)
+    nm_ref, m12_ref = R.search_for_triangulation(tp["kps1"], sc["mp_desc"], node1, tp["has_mp1"], ur1, sc["cur"], sc["cur_desc"], node2,
+                                                 tp["has_mp2"], ur2, tp["F12"], tp["ex"], tp["ey"], only_stereo, SF, SIGMA2, True)
+    assert nm == nm_ref and m12.tolist() == m12_ref
+    assert nm > (5 if only_stereo else 15), nm
+    sel = m12[m12 >= 0]
+    assert len(set(sel.tolist())) == len(sel) and not tp["has_mp2"][sel].any() and not tp["has_mp1"][m12 >= 0].any()
