@@ -64,6 +64,7 @@ struct LevelGeom {
   int keptOff, keptCap;
   int tapX, tapY;         // offsets of this level's resize taps in the tap table
   int blurTileBase, blurTilesX, blurTilesY;
+  unsigned blurTilesXMagic;   // ceil(2^32 / blurTilesX): tile row = umulhi(tile, magic)
   int borderTileBase, borderTilesX, borderTilesY;
   float scale;            // mvScaleFactor[level]
   float patch;            // keypoint size = int(31*scale) (:1164)
@@ -366,7 +367,9 @@ __device__ __forceinline__ unsigned fast_exact(const FastDiffs& D) {
 // hide each other's latencies.
 constexpr int kFastWarps = 11;  // upper bound; the host picks the warps per CTA that pack an SM's shared memory best
 constexpr int kFastThreads = 32 * kFastWarps;
-constexpr int kFastRun = 16;   // consecutive cells a warp grabs per atomic
+constexpr int kFastRun = 16;   // consecutive cells a warp grabs per atomic ...
+constexpr int kFastTailRun = 2; // ... except for the last ~one run per warp of the chunk, handed out in short runs so that
+                                // all warps finish together (the kernel is persistent: the tail is pure imbalance)
 
 struct FastSmemLayout {   // per-warp shared memory carve-up (in bytes), sized for the largest cell
   int rawPitchWords, rawBytes, tileBytes, hitsBytes, scBytes, total;
@@ -441,7 +444,7 @@ __device__ __forceinline__ void fast_prefetch(const CellDesc& c, unsigned* raw, 
 __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                              uint2* __restrict__ cand, int* __restrict__ candCount,
                                                              int candTotal, int nItems, const FastSmemLayout lay,
-                                                             int* __restrict__ workCounter) {
+                                                             int* __restrict__ workCounter, int tailRun, int tailMul) {
   extern __shared__ __align__(16) u8 smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   u8* base = smem + wid * lay.total;
@@ -454,7 +457,9 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
   u8* sc = base + lay.rawBytes + lay.tileBytes + lay.hitsBytes;
   const unsigned ltmask = (1u << lane) - 1u;
 
-  // work distribution: a warp grabs runs of kFastRun consecutive cells from a global counter
+  // work distribution: a warp grabs runs of consecutive cells from a global counter of work units
+  const int tailItems = min(nItems, (int)(gridDim.x * (blockDim.x >> 5)) * kFastRun * tailMul);
+  const int longUnits = (nItems - tailItems) / kFastRun;
   CellDesc c;
   CellCursor cur_k;
   int left = 0;          // cells left in the current run
@@ -463,11 +468,12 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
     // moves to the next cell with a non-empty detection window; false when the work is exhausted
     for (;;) {
       if (left == 0) {
-        int start = 0;
-        if (lane == 0) start = atomicAdd(workCounter, kFastRun);
-        start = __shfl_sync(0xffffffffu, start, 0);
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(workCounter, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        const int start = unit < longUnits ? unit * kFastRun : longUnits * kFastRun + (unit - longUnits) * tailRun;
         if (start >= nItems) return false;
-        left = min(kFastRun, nItems - start);
+        left = min(unit < longUnits ? kFastRun : tailRun, nItems - start);
         cursor_init(g, start, cur_k);
       } else {
         cursor_next(g, cur_k);
@@ -968,7 +974,7 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
   while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blurTileBase) l++;
   const LevelGeom& L = g.lv[l];
   const int t = blockIdx.x - L.blurTileBase;
-  const int ty = t / L.blurTilesX, tx = t - ty * L.blurTilesX;
+  const int ty = L.blurTilesX == 1 ? t : (int)__umulhi((unsigned)t, L.blurTilesXMagic), tx = t - ty * L.blurTilesX;   // t < 2^16
   const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
   const u8* src = pyr + (size_t)f * pyrStride + L.off;
   const int xlast = L.pitch - kLeftPad - 16;  // last 16-byte chunk of a bordered row (covers col w+18)
@@ -1015,7 +1021,7 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
     const uint4 q3 = *reinterpret_cast<const uint4*>(hp + (yp + 3) * kBlurTW + 4 * xg);
     const unsigned c0[4] = {q0.x, q0.y, q0.z, q0.w}, c1[4] = {q1.x, q1.y, q1.z, q1.w};
     const unsigned c2[4] = {q2.x, q2.y, q2.z, q2.w}, c3[4] = {q3.x, q3.y, q3.z, q3.w};
-    unsigned o0 = 0, o1 = 0;
+    unsigned ev[4], od[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       unsigned e = __dp2a_lo(c0[j], 0x2212u, 32768u);   // rows 0,1 x (k0,k1)
@@ -1026,11 +1032,15 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
       o = __dp2a_lo(c1[j], 0x3022u, o);                 // rows 2,3 x (k1,k2)
       o = __dp2a_lo(c2[j], 0x3038u, o);                 // rows 4,5 x (k3,k4)
       o = __dp2a_lo(c3[j], 0x1222u, o);                 // rows 6,7 x (k5,k6)
-      o0 |= (e >> 16) << (8 * j);
-      o1 |= (o >> 16) << (8 * j);
+      ev[j] = e;
+      od[j] = o;
     }
-    *reinterpret_cast<unsigned*>(dst + (long long)y * L.bpitch + x) = o0;
-    if (y + 1 < L.h) *reinterpret_cast<unsigned*>(dst + (long long)(y + 1) * L.bpitch + x) = o1;
+    // the result of pixel j is byte 2 of its accumulator (sum / 2^16, < 256): three PRMT pack four of them
+    const unsigned o0 = __byte_perm(__byte_perm(ev[0], ev[1], 0x0062), __byte_perm(ev[2], ev[3], 0x0062), 0x5410);
+    const unsigned o1 = __byte_perm(__byte_perm(od[0], od[1], 0x0062), __byte_perm(od[2], od[3], 0x0062), 0x5410);
+    u8* d0 = dst + (long long)y * L.bpitch + x;
+    *reinterpret_cast<unsigned*>(d0) = o0;
+    if (y + 1 < L.h) *reinterpret_cast<unsigned*>(d0 + L.bpitch) = o1;
   }
 }
 
@@ -1509,6 +1519,7 @@ struct orb_extractor {
   cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
   // staging for the host entry points: two sets, so that the H2D copy of chunk i+1 and the D2H
   // copy of chunk i-1 overlap the kernels of chunk i (copy streams + events)
+  int fastTailRun = kFastTailRun, fastTailMul = 1;
   u8* d_in[2] = {nullptr, nullptr}; size_t d_inBytes = 0;
   orb_keypoint* d_kps[2] = {nullptr, nullptr}; u8* d_desc[2] = {nullptr, nullptr}; int* d_n[2] = {nullptr, nullptr};
   int stageFrames = 0, stageCap = 0;
@@ -1619,6 +1630,7 @@ int build_geom(orb_extractor* e, int W, int H) {
     nodeCap = std::max(nodeCap, L.keptCap + 3);
     L.blurTileBase = blurBase;
     L.blurTilesX = (L.w + kBlurTW - 1) / kBlurTW;
+    L.blurTilesXMagic = L.blurTilesX == 1 ? 0u : (unsigned)((0x100000000ull + L.blurTilesX - 1) / L.blurTilesX);
     L.blurTilesY = (L.h + kBlurTH - 1) / kBlurTH;
     blurBase += L.blurTilesX * L.blurTilesY;
     L.scale = e->scale[l];
@@ -1653,6 +1665,8 @@ int build_geom(orb_extractor* e, int W, int H) {
     int bestW = 1, bestResident = 0;
     int maxW = kFastWarps;
     if (const char* ev = getenv("ORB_B200_FAST_WARPS")) maxW = std::max(1, std::min(kFastWarps, atoi(ev)));
+    if (const char* ev = getenv("ORB_B200_FAST_TAIL_RUN")) e->fastTailRun = std::max(1, std::min(kFastRun, atoi(ev)));
+    if (const char* ev = getenv("ORB_B200_FAST_TAIL_MUL")) e->fastTailMul = std::max(0, std::min(64, atoi(ev)));
     for (int w = 1; w <= maxW; w++) {
       const long long perCta = (long long)y.total * w + 1024;
       const int resident = (int)std::min<long long>(32, (227 * 1024) / perCta) * w;
@@ -1775,7 +1789,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     const int nItems = g.totalCells * B;
     const int blocks = std::min(e->fastBlocks, (nItems + e->fastWarps - 1) / e->fastWarps);
     k_fast_cells<<<blocks, 32 * e->fastWarps, e->fastSmem, s>>>(g, W.pyr, e->pyrStride, W.cand, W.candCount,
-                                                          e->candTotal, nItems, e->fastLay, W.work);
+                                                          e->candTotal, nItems, e->fastLay, W.work, e->fastTailRun, e->fastTailMul);
   }
   launches++;
   if ((st = stage_mark(e, s))) return st;
