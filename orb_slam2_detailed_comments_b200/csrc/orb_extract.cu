@@ -26,6 +26,7 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_pipeline.h>
 
 #include "../../include/orb_pattern_data.h"
@@ -1267,6 +1268,214 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// k_describe_tma: the same computation with the patches fetched by the TMA unit. Every pyramid level (bordered
+// plane) and every blurred level is described by a 3-D tensor map (x, y, frame); ONE lane per keypoint issues
+// cp.async.bulk.tensor for the 32x31 moment patch, later for the 48x37 BRIEF patch, and the warp waits on the
+// keypoint's mbarrier. That replaces ~380 LDGSTS per keypoint (the issue-rate limiter of k_describe) by two
+// instructions. The TMA unit wants the innermost start coordinate on a 16-byte boundary (measured on B200: an
+// unaligned byte coordinate raises "illegal instruction"), so the boxes are 48 / 64 bytes wide and start at the
+// aligned column at or left of x-15 / x-18.
+// ------------------------------------------------------------------------------------------
+struct DescMaps {
+  CUtensorMap pyr[kMaxLevels];
+  CUtensorMap blur[kMaxLevels];
+};
+constexpr int kTmaMomW = 48, kTmaPatchW = 64;   // 31 / 37 px + up to 15 bytes of alignment slack
+constexpr int kTmaMomBytes = kTmaMomW * 31, kTmaPatchBytes = kTmaPatchW * 37;
+constexpr int kTmaBufBytes = 2432;   // 64 x 37 rounded up to a multiple of 128 (TMA destination alignment)
+constexpr int kDescTmaSmem = kDescSlots * kTmaBufBytes + 128;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid_constant__ DescMaps maps,
+                                                      const uint2* __restrict__ kept, const int* __restrict__ keptCount,
+                                                      int keptTotal, const signed char* __restrict__ pattern,
+                                                      orb_keypoint* __restrict__ outK, u8* __restrict__ outD,
+                                                      int* __restrict__ outN, int cap, int* __restrict__ overflow) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[kDescSlots];
+  __shared__ int s_lvl[kDescSlots];
+  __shared__ float s_angle[kDescSlots], s_cos[kDescSlots], s_sin[kDescSlots];
+  __shared__ int s_prefix[kMaxLevels + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = blockIdx.y;
+  const int slot0 = blockIdx.x * kDescSlots;
+  unsigned char* bufs = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(s_raw) + 127) & ~(size_t)127);
+  unsigned char* wbuf = bufs + wid * (kDescPerWarp * kTmaBufBytes);
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int q = 0; q < g.nlevels; q++) {
+      s_prefix[q] = total;
+      total += keptCount[f * g.nlevels + q];
+    }
+    s_prefix[g.nlevels] = total;
+    if (blockIdx.x == 0) {
+      outN[f] = min(total, cap);
+      if (total > cap) atomicOr(overflow, 4);
+    }
+  }
+  if (threadIdx.x < kDescSlots) mbar_init(&s_bar[threadIdx.x], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // disc mask / (u+15) weights of this lane's patch row v = lane-15: 8 words of 4 bytes
+  unsigned w1[8], wu[8];
+  {
+    const int v = lane - kHalfPatch;
+    const int d = lane < 31 ? c_umax[v < 0 ? -v : v] : -1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      unsigned a = 0, b = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int u = 4 * k + j - kHalfPatch;
+        const bool in = (u < 0 ? -u : u) <= d;
+        a |= (in ? 1u : 0u) << (8 * j);
+        b |= (in ? (unsigned)(u + kHalfPatch) : 0u) << (8 * j);
+      }
+      w1[k] = a;
+      wu[k] = b;
+    }
+  }
+  __syncthreads();
+  const int total = min(s_prefix[g.nlevels], cap);
+  if (slot0 >= total) return;
+
+  // ---- phase A: fetch the unblurred patches, moments, fastAtan2
+  int lvl[kDescPerWarp], px[kDescPerWarp], py[kDescPerWarp], resp[kDescPerWarp];
+#pragma unroll
+  for (int k = 0; k < kDescPerWarp; k++) {
+    const int slotIdx = slot0 + wid * kDescPerWarp + k;
+    lvl[k] = -1; px[k] = py[k] = resp[k] = 0;
+    if (slotIdx < total) {
+      int l = 0;
+      while (l + 1 < g.nlevels && slotIdx >= s_prefix[l + 1]) l++;
+      const LevelGeom& L = g.lv[l];
+      const uint2 rec = kept[(size_t)f * keptTotal + L.keptOff + (slotIdx - s_prefix[l])];
+      lvl[k] = l; px[k] = (int)(rec.x & 0xffffu); py[k] = (int)(rec.x >> 16); resp[k] = (int)rec.y;
+      if (lane == 0) {
+        unsigned long long* bar = &s_bar[wid * kDescPerWarp + k];
+        mbar_expect_tx(bar, kTmaMomBytes);
+        tma_load_3d(wbuf + k * kTmaBufBytes, &maps.pyr[l], kLeftPad + ((px[k] - kHalfPatch) & ~15), kEdge + py[k] - kHalfPatch, f, bar);
+      }
+    }
+  }
+  float angle[kDescPerWarp];
+#pragma unroll
+  for (int k = 0; k < kDescPerWarp; k++) {
+    angle[k] = 0.f;
+    if (lvl[k] >= 0) {
+      mbar_wait(&s_bar[wid * kDescPerWarp + k], 0);
+      const int mis = (px[k] - kHalfPatch) & 15;   // patch byte 0 sits `mis` bytes into the fetched row
+      const unsigned* row = reinterpret_cast<const unsigned*>(wbuf + k * kTmaBufBytes + (lane < 31 ? lane : 30) * kTmaMomW) + (mis >> 2);
+      const unsigned sh = (unsigned)(mis & 3) * 8;
+      unsigned s1 = 0, s2 = 0;
+      unsigned prev = row[0];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const unsigned nxt = row[q + 1];
+        const unsigned wv = __funnelshift_r(prev, nxt, sh);   // patch bytes 4q .. 4q+3 of this row
+        s1 = __dp4a(wv, w1[q], s1);
+        s2 = __dp4a(wv, wu[q], s2);
+        prev = nxt;
+      }
+      int m10 = (int)s2 - kHalfPatch * (int)s1;               // sum u*I
+      int m01 = (lane - kHalfPatch) * (int)s1;                // sum v*I
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+      }
+      angle[k] = fast_atan2_deg((float)m01, (float)m10);
+    }
+  }
+  __syncwarp();
+  // the buffers are free: fetch the blurred patches, then publish the angles
+#pragma unroll
+  for (int k = 0; k < kDescPerWarp; k++) {
+    const int sl = wid * kDescPerWarp + k;
+    if (lane == 0) {
+      if (lvl[k] >= 0) {
+        mbar_expect_tx(&s_bar[sl], kTmaPatchBytes);
+        tma_load_3d(wbuf + k * kTmaBufBytes, &maps.blur[lvl[k]], (px[k] - 18) & ~15, py[k] - 18, f, &s_bar[sl]);
+      }
+      s_lvl[sl] = lvl[k];
+      s_angle[sl] = angle[k];
+    }
+  }
+  __syncthreads();
+  // ---- phase B: cos / sin, one thread per keypoint
+  if (threadIdx.x < kDescSlots && s_lvl[threadIdx.x] >= 0) {
+    const float ang = __fmul_rn(s_angle[threadIdx.x], (float)(3.14159265358979323846 / 180.f));
+    double sn, cs;
+    sincos((double)ang, &sn, &cs);
+    s_cos[threadIdx.x] = (float)cs;
+    s_sin[threadIdx.x] = (float)sn;
+  }
+  __syncthreads();
+  // ---- phase C: steered BRIEF on the blurred patch; lane i produces descriptor byte i
+  const int4* pp = reinterpret_cast<const int4*>(pattern) + lane * 2;
+  const int4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+  const int words[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+  for (int k = 0; k < kDescPerWarp; k++) {
+    if (lvl[k] < 0) continue;
+    const int sl = wid * kDescPerWarp + k, slotIdx = slot0 + sl;
+    mbar_wait(&s_bar[sl], 1);
+    const LevelGeom& L = g.lv[lvl[k]];
+    const int x = px[k], y = py[k];
+    const float a = s_cos[sl], b = s_sin[sl];
+    const u8* cb = wbuf + k * kTmaBufBytes + 18 * kTmaPatchW + 18 + ((x - 18) & 15);
+    int val = 0;
+#pragma unroll
+    for (int bit = 0; bit < 8; bit++) {
+      const int wd = words[bit];
+      const float x0 = (float)(signed char)(wd & 0xff), y0 = (float)(signed char)((wd >> 8) & 0xff);
+      const float x1 = (float)(signed char)((wd >> 16) & 0xff), y1 = (float)(signed char)((wd >> 24) & 0xff);
+      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+      const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+      const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+      const int t0 = cb[r0 * kTmaPatchW + c0], t1 = cb[r1 * kTmaPatchW + c1];
+      val |= (t0 < t1) << bit;
+    }
+    const size_t o = (size_t)f * cap + slotIdx;
+    outD[o * 32 + lane] = (u8)val;
+    if (lane == 0) {
+      orb_keypoint kp;
+      kp.x = lvl[k] ? __fmul_rn((float)x, L.scale) : (float)x;
+      kp.y = lvl[k] ? __fmul_rn((float)y, L.scale) : (float)y;
+      kp.size = L.patch;
+      kp.angle = angle[k];
+      kp.response = (float)resp[k];
+      kp.octave = lvl[k];
+      kp.class_id = -1;
+      outK[o] = kp;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Frame::ComputeStereoMatches (Frame.cc:831-1082): one CTA per stereo pair (frames 2p, 2p+1 of the
 // chunk), one warp per left keypoint.
 //   coarse : best Hamming among right keypoints whose row band (+-2*scale) holds the left row, within
@@ -1515,6 +1724,8 @@ struct orb_extractor {
   // two streams. It paid while some kernels were latency-bound; with the current kernels every stage
   // saturates the SMs and one lane is as fast, so 1 is the default.
   int lanes = 1, lastLane = 0;
+  DescMaps descMaps[2];          // TMA tensor maps of the two workspace lanes (k_describe_tma)
+  bool descTma = false;          // maps are valid for the current workspace
   cudaStream_t laneStream[2] = {nullptr, nullptr};
   cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
   // staging for the host entry points: two sets, so that the H2D copy of chunk i+1 and the D2H
@@ -1708,6 +1919,58 @@ void free_workspace(orb_extractor* e) {
   e->wsFrames = 0;
 }
 
+// TMA tensor maps of the workspace (k_describe_tma): per level, the bordered pyramid plane and the blurred plane as
+// (x, y, frame) byte tensors. cuTensorMapEncodeTiled is taken from the driver through the runtime, so the library
+// still links against cudart only.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int build_desc_maps(orb_extractor* e) {
+  e->descTma = false;
+  if (const char* ev = getenv("ORB_B200_DESC_TMA"))
+    if (atoi(ev) == 0) return ORB_OK;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || !sym ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return ORB_OK;   // k_describe (cp.async staging) is used instead
+  }
+  const EncodeTiledFn encode = (EncodeTiledFn)sym;
+  const Geom& g = e->g;
+  for (int lane = 0; lane < e->lanes; lane++) {
+    const Lane W = lane_of(e, lane);
+    for (int l = 0; l < g.nlevels; l++) {
+      const LevelGeom& L = g.lv[l];
+      const cuuint32_t ones[3] = {1, 1, 1};
+      {
+        u8* base = W.pyr + (L.off - (long long)kEdge * L.pitch - kLeftPad);
+        const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)(L.h + 2 * kEdge), (cuuint64_t)e->wsFrames};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)e->pyrStride};
+        const cuuint32_t box[3] = {kTmaMomW, 31, 1};
+        if (encode(&e->descMaps[lane].pyr[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return ORB_OK;
+      }
+      {
+        u8* base = W.blur + L.boff;
+        const cuuint64_t dims[3] = {(cuuint64_t)L.bpitch, (cuuint64_t)L.h, (cuuint64_t)e->wsFrames};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.bpitch, (cuuint64_t)e->blurStride};
+        const cuuint32_t box[3] = {kTmaPatchW, 37, 1};
+        if (encode(&e->descMaps[lane].blur[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return ORB_OK;
+      }
+    }
+  }
+  ORB_CUDA(cudaFuncSetAttribute(k_describe_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescTmaSmem));
+  e->descTma = true;
+  return ORB_OK;
+}
+
 int ensure_geom(orb_extractor* e, int W, int H, int frames) {
   ORB_CUDA(cudaSetDevice(e->device));
   const bool newGeom = !e->haveGeom || e->g.W != W || e->g.H != H;
@@ -1746,6 +2009,8 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
     ORB_CUDA(cudaMalloc(&e->d_kept, F * e->keptTotal * sizeof(uint2)));
     ORB_CUDA(cudaMalloc(&e->d_keptCount, F * kMaxLevels * sizeof(int)));
     e->wsFrames = frames;
+    const int st = build_desc_maps(e);
+    if (st) return st;
   }
   return ORB_OK;
 }
@@ -1802,9 +2067,14 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   launches++;
   if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);
-  k_describe<<<dim3((slots + kDescSlots - 1) / kDescSlots, B), 256, kDescSmem, s>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride,
-                                                              W.kept, W.keptCount, e->keptTotal, e->d_pattern,
-                                                              d_kps, d_desc, d_counts, cap, e->d_overflow);
+  if (e->descTma)
+    k_describe_tma<<<dim3((slots + kDescSlots - 1) / kDescSlots, B), 256, kDescTmaSmem, s>>>(g, e->descMaps[lane], W.kept, W.keptCount,
+                                                                                            e->keptTotal, e->d_pattern, d_kps, d_desc,
+                                                                                            d_counts, cap, e->d_overflow);
+  else
+    k_describe<<<dim3((slots + kDescSlots - 1) / kDescSlots, B), 256, kDescSmem, s>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride,
+                                                                W.kept, W.keptCount, e->keptTotal, e->d_pattern,
+                                                                d_kps, d_desc, d_counts, cap, e->d_overflow);
   launches++;
   if ((st = stage_mark(e, s))) return st;
   ORB_CUDA(cudaGetLastError());
