@@ -959,6 +959,37 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
 // Integer dot-product instructions do the taps: the horizontal pass is two IDP.4A per pixel on
 // byte windows built with funnel shifts, the vertical pass four IDP.2A per pixel on u16 pairs
 // (two tile rows interleaved per 32-bit word). One CTA blurs a 128 x 32 tile.
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers, used by k_blur7 and k_describe_tma.
+// Measured on B200: the innermost start coordinate of a byte tensor must sit on a 16-byte boundary (an unaligned one
+// raises "illegal instruction"), so boxes are fetched from the aligned column at or left of the wanted one.
+struct PyrMaps {
+  CUtensorMap m[kMaxLevels];
+};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+
 constexpr int kBlurTW = 128, kBlurTH = 64;
 constexpr int kBlurChunks = (kBlurTW + 32) / 16;  // 16-byte chunks per input tile row: image x0-16 .. x0+143
 constexpr int kBlurInP = kBlurChunks * 4 + 4;     // tile pitch in words (16-B aligned rows, 4 words pad)
@@ -966,8 +997,11 @@ constexpr int kBlurRows = kBlurTH + 6;        // input rows y0-3 .. y0+34
 constexpr int kBlurPairs = kBlurRows / 2;
 
 __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
-                                               u8* __restrict__ blur, size_t blurStride) {
-  __shared__ __align__(16) unsigned in[kBlurRows * kBlurInP];
+                                               u8* __restrict__ blur, size_t blurStride,
+                                               const __grid_constant__ PyrMaps bmaps, int useTma) {
+  __shared__ __align__(128) unsigned in[kBlurRows * kBlurInP];
+  __shared__ __align__(8) unsigned long long s_bbar;
+  const int inP = useTma ? kBlurChunks * 4 : kBlurInP;   // the TMA box is dense: 160-byte rows
   __shared__ __align__(16) unsigned hp[kBlurPairs * kBlurTW];  // (H[2p][x], H[2p+1][x]) as u16 pairs
   const int f = blockIdx.y, tid = threadIdx.x;
   int l = 0;
@@ -978,22 +1012,35 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
   const int ty = L.blurTilesX == 1 ? t : (int)__umulhi((unsigned)t, L.blurTilesXMagic), tx = t - ty * L.blurTilesX;   // t < 2^16
   const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
   const u8* src = pyr + (size_t)f * pyrStride + L.off;
-  const int xlast = L.pitch - kLeftPad - 16;  // last 16-byte chunk of a bordered row (covers col w+18)
-  for (int i = tid; i < kBlurRows * kBlurChunks; i += 256) {
-    const int r = i / kBlurChunks, c = i - r * kBlurChunks;
-    const int y = min(y0 + r - 3, L.h + kEdge - 1), x = min(x0 - 16 + 16 * c, xlast);
-    __pipeline_memcpy_async(in + r * kBlurInP + 4 * c, src + (long long)y * L.pitch + x, 16);
+  if (useTma) {
+    // one bulk tensor copy per CTA: rows y0-3 .. y0+66, bytes x0-16 .. x0+143 of the bordered plane (rows / bytes
+    // outside the plane arrive as zeros; they only feed outputs that are not stored)
+    if (tid == 0) {
+      mbar_init(&s_bbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(&s_bbar, kBlurRows * kBlurChunks * 16);
+      tma_load_3d(in, &bmaps.m[l], kLeftPad + x0 - 16, kEdge + y0 - 3, f, &s_bbar);
+    }
+    __syncthreads();
+    mbar_wait(&s_bbar, 0);
+  } else {
+    const int xlast = L.pitch - kLeftPad - 16;  // last 16-byte chunk of a bordered row (covers col w+18)
+    for (int i = tid; i < kBlurRows * kBlurChunks; i += 256) {
+      const int r = i / kBlurChunks, c = i - r * kBlurChunks;
+      const int y = min(y0 + r - 3, L.h + kEdge - 1), x = min(x0 - 16 + 16 * c, xlast);
+      __pipeline_memcpy_async(in + r * kBlurInP + 4 * c, src + (long long)y * L.pitch + x, 16);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
   }
-  __pipeline_commit();
-  __pipeline_wait_prior(0);
-  __syncthreads();
   // horizontal: k = [18,34,48,56,48,34,18]; output x needs tile bytes (x+1 .. x+7)
   for (int i = tid; i < kBlurPairs * (kBlurTW / 4); i += 256) {
     const int rp = i / (kBlurTW / 4), xg = i - rp * (kBlurTW / 4);
     unsigned hrow[2][4];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-      const unsigned* p = in + (2 * rp + q) * kBlurInP + xg + 3;  // image x0+4xg-4 = tile byte 4xg+12
+      const unsigned* p = in + (2 * rp + q) * inP + xg + 3;  // image x0+4xg-4 = tile byte 4xg+12
       // output x+j needs tile bytes (1+j .. 7+j) of (w0,w1,w2): the taps are applied with
       // pre-shifted coefficient words instead of shifting the data
       const unsigned w0 = p[0], w1 = p[1], w2 = p[2];
@@ -1284,30 +1331,6 @@ constexpr int kTmaMomW = 48, kTmaPatchW = 64;   // 31 / 37 px + up to 15 bytes o
 constexpr int kTmaMomBytes = kTmaMomW * 31, kTmaPatchBytes = kTmaPatchW * 37;
 constexpr int kTmaBufBytes = 2432;   // 64 x 37 rounded up to a multiple of 128 (TMA destination alignment)
 constexpr int kDescTmaSmem = kDescSlots * kTmaBufBytes + 128;
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
-}
 
 __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid_constant__ DescMaps maps,
                                                       const uint2* __restrict__ kept, const int* __restrict__ keptCount,
@@ -1725,6 +1748,8 @@ struct orb_extractor {
   // saturates the SMs and one lane is as fast, so 1 is the default.
   int lanes = 1, lastLane = 0;
   DescMaps descMaps[2];          // TMA tensor maps of the two workspace lanes (k_describe_tma)
+  PyrMaps blurMaps[2];           // ... and of the blur input tiles (k_blur7)
+  bool blurTma = false;
   bool descTma = false;          // maps are valid for the current workspace
   cudaStream_t laneStream[2] = {nullptr, nullptr};
   cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
@@ -1928,6 +1953,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 int build_desc_maps(orb_extractor* e) {
   e->descTma = false;
+  e->blurTma = false;
   if (const char* ev = getenv("ORB_B200_DESC_TMA"))
     if (atoi(ev) == 0) return ORB_OK;
   void* sym = nullptr;
@@ -1968,6 +1994,26 @@ int build_desc_maps(orb_extractor* e) {
   }
   ORB_CUDA(cudaFuncSetAttribute(k_describe_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescTmaSmem));
   e->descTma = true;
+  // blur input tiles: (kBlurTW + 32) x (kBlurTH + 6) bytes of the bordered plane
+  bool blurOk = true;
+  if (const char* ev = getenv("ORB_B200_BLUR_TMA"))
+    if (atoi(ev) == 0) blurOk = false;
+  for (int lane = 0; blurOk && lane < e->lanes; lane++) {
+    const Lane W = lane_of(e, lane);
+    for (int l = 0; blurOk && l < g.nlevels; l++) {
+      const LevelGeom& L = g.lv[l];
+      const cuuint32_t ones[3] = {1, 1, 1};
+      u8* base = W.pyr + (L.off - (long long)kEdge * L.pitch - kLeftPad);
+      const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)(L.h + 2 * kEdge), (cuuint64_t)e->wsFrames};
+      const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)e->pyrStride};
+      const cuuint32_t box[3] = {kBlurChunks * 16, kBlurRows, 1};
+      if (encode(&e->blurMaps[lane].m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, ones,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        blurOk = false;
+    }
+  }
+  e->blurTma = blurOk;
   return ORB_OK;
 }
 
@@ -2063,7 +2109,8 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
                                                        e->d_overflow);
   launches++;
   if ((st = stage_mark(e, s))) return st;
-  k_blur7<<<dim3(g.totalBlurTiles, B), 256, 0, s>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride);
+  k_blur7<<<dim3(g.totalBlurTiles, B), 256, 0, s>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride, e->blurMaps[lane],
+                                                    e->blurTma ? 1 : 0);
   launches++;
   if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);

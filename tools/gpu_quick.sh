@@ -4,6 +4,6 @@ timeout 900 python -m pytest tests/test_gpu_extract_parity.py tests/test_gpu_ful
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-latency --allpairs-kf 0 --match-pairs 64 > gpurun_out/b_q.json 2> gpurun_out/b_q.err; tail -2 gpurun_out/b_q.err
 python -c "
 import json; d=json.load(open('gpurun_out/b_q.json')); print('fps', d['value'], 'e2e', d['e2e']['value'], d['stage_ms_per_step'])"
-ORB_B200_DESC_TMA=0 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-latency --allpairs-kf 0 --match-pairs 64 > gpurun_out/b_q0.json 2> gpurun_out/b_q0.err
+ORB_B200_BLUR_TMA=0 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-latency --allpairs-kf 0 --match-pairs 64 > gpurun_out/b_q0.json 2> gpurun_out/b_q0.err
 python -c "
 import json; d=json.load(open('gpurun_out/b_q0.json')); print('noTMA fps', d['value'], 'e2e', d['e2e']['value'], d['stage_ms_per_step'])"
