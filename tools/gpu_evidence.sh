@@ -9,7 +9,7 @@ python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_
 python bench.py --workload euroc --no-cpu-baseline --allpairs-kf 0 --match-pairs 64 > gpurun_out/bench_euroc.json 2> gpurun_out/bench_euroc.err
 python bench.py --workload tum1 --no-cpu-baseline --allpairs-kf 0 --match-pairs 64 > gpurun_out/bench_tum1.json 2> gpurun_out/bench_tum1.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --pairs 256 --match-pairs 512 --allpairs-kf 64 --no-cpu-baseline --no-latency > gpurun_out/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_fast_cells -s 3 -c 1 -o gpurun_out/prof_fast python bench.py --steps 1 --warmup 3 --pairs 128 --chunk 256 --match-pairs 64 --allpairs-kf 0 --no-cpu-baseline > gpurun_out/ncu_fast.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_fast_cells|k_describe_tma|k_blur7" -s 9 -c 3 -o gpurun_out/prof_fast python bench.py --steps 1 --warmup 3 --pairs 128 --chunk 256 --match-pairs 64 --allpairs-kf 0 --no-cpu-baseline > gpurun_out/ncu_fast.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_match_pairs_bf|k_allpairs" -s 1 -c 2 -o gpurun_out/prof_match python bench.py --steps 1 --warmup 3 --pairs 64 --chunk 128 --match-pairs 1024 --allpairs-kf 128 --no-cpu-baseline > gpurun_out/ncu_match.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_cvt|k_remap|k_distinctive|k_undistort|k_grid_assign|k_project|k_search|k_bow" -s 11 -c 11 -o gpurun_out/prof_next python tools/prof_next.py > gpurun_out/ncu_next.log 2>&1
 ls -la gpurun_out
