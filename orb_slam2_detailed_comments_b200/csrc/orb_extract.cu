@@ -566,6 +566,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
             pass = ((fast_bound4(tile + ((i >> 6) + 3) * tp + ((i & 63) + 3), tp) + K) & 0x80008000u) != 0u;
           }
           const unsigned m = __ballot_sync(0xffffffffu, pass);   // every lane has read its entry by now
+          __syncwarp();                                          // (memory ordering of the in-place compaction, for racecheck)
           if (pass) queue[nq1 + __popc(m & ltmask)] = (unsigned short)i;
           nq1 += __popc(m);
         }
