@@ -229,3 +229,18 @@ def test_other_extractor_parameters(oracle, params):
         assert np.array_equal(kps[f], okps[f]), f
     assert np.abs(kps["angle"] - okps["angle"]).max() <= ANGLE_TOL_DEG
     assert (desc == odesc).all(1).mean() >= MIN_IDENTICAL_DESC
+
+
+def test_cp_async_fallback_kernels_match_tma(oracle, monkeypatch):
+    """k_describe / the cp.async tile load of k_blur7 (used when tensor maps cannot be created, selectable with
+    ORB_B200_DESC_TMA=0 / ORB_B200_BLUR_TMA=0) give the same bytes as the TMA kernels."""
+    from orb_slam2_detailed_comments_b200 import ORBextractor
+    from orb_slam2_detailed_comments_b200.synth import synth_frame
+    img = synth_frame(752, 480, 77)
+    ref_k, ref_d = ORBextractor(1200, 1.2, 8, 20, 7)(img)
+    for var in ("ORB_B200_DESC_TMA", "ORB_B200_BLUR_TMA"):
+        monkeypatch.setenv(var, "0")
+        k, d = ORBextractor(1200, 1.2, 8, 20, 7)(img)
+        monkeypatch.delenv(var)
+        assert len(k) == len(ref_k) > 1000
+        assert k.tobytes() == ref_k.tobytes() and np.array_equal(d, ref_d)
