@@ -92,6 +92,14 @@ int orb_extract_batch_host(orb_extractor* h, const uint8_t* images, int batch, i
                            size_t step, size_t frame_stride, orb_keypoint* keypoints, int capacity,
                            int32_t* counts, uint8_t* descriptors);
 
+/* The same, but returns as soon as the copies and kernels are enqueued: consecutive calls continue one
+ * upload / compute / download pipeline (the upload of call k+1 overlaps the kernels of call k). The host
+ * buffers of a call must stay valid, and its outputs must not be read, until orb_synchronize(h, NULL)
+ * returns; capacity overflow is reported there. */
+int orb_extract_batch_host_async(orb_extractor* h, const uint8_t* images, int batch, int width, int height,
+                           size_t step, size_t frame_stride, orb_keypoint* keypoints, int capacity,
+                           int32_t* counts, uint8_t* descriptors);
+
 /* Same, with inputs and outputs RESIDENT IN DEVICE MEMORY of the handle's device. `stream`
  * is a cudaStream_t (NULL = the handle's own stream); the call is asynchronous on it. */
 int orb_extract_batch_device(orb_extractor* h, const uint8_t* d_images, int batch, int width, int height,

@@ -70,7 +70,7 @@ class OrbMatchParams(C.Structure):
 # every symbol include/orb_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "orb_last_error", "orb_device_count", "orb_create", "orb_destroy", "orb_get_scale_tables",
-    "orb_max_keypoints", "orb_extract", "orb_extract_batch_host", "orb_extract_batch_device",
+    "orb_max_keypoints", "orb_extract", "orb_extract_batch_host", "orb_extract_batch_host_async", "orb_extract_batch_device",
     "orb_extract_stereo", "orb_extract_stereo_batch_device",
     "orb_synchronize", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_times", "orb_set_lanes", "orb_stage_level_size", "orb_stage_copy_level",
     "orb_stage_copy_blur", "orb_stage_copy_candidates", "orb_stage_copy_kept",
@@ -109,6 +109,7 @@ def lib():
         L.orb_max_keypoints.argtypes = [vp]
         L.orb_extract.argtypes = [vp, vp, i32, i32, sz, vp, i32, C.POINTER(i32), vp, vp]
         L.orb_extract_batch_host.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp]
+        L.orb_extract_batch_host_async.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp]
         L.orb_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp, vp]
         L.orb_extract_stereo.argtypes = [vp, vp, vp, i32, i32, sz, f32, f32, vp, i32, C.POINTER(i32), vp, vp, C.POINTER(i32), vp, vp, vp]
         L.orb_extract_stereo_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp, f32, f32, vp, vp, vp]

@@ -1723,6 +1723,8 @@ struct orb_extractor {
   // two streams. It paid while some kernels were latency-bound; with the current kernels every stage
   // saturates the SMs and one lane is as fast, so 1 is the default.
   int lanes = 1, lastLane = 0;
+  long long hostChunks = 0;      // chunks issued by the host batch entry points so far (staging buffer parity)
+  bool asyncPending = false;     // orb_extract_batch_host_async work may still be in flight
   DescMaps descMaps[2];          // TMA tensor maps of the two workspace lanes (k_describe_tma)
   PyrMaps blurMaps[2];           // ... and of the blur input tiles (k_blur7)
   bool blurTma = false;
@@ -2285,12 +2287,26 @@ int orb_max_keypoints(const orb_extractor* e) {
   return m;
 }
 
+// The other entry points reuse the staging buffers without events: let asynchronous batches finish first.
+static int drain_async(orb_extractor* e) {
+  if (!e->asyncPending) return ORB_OK;
+  e->asyncPending = false;
+  if (e->sIn) ORB_CUDA(cudaStreamSynchronize(e->sIn));
+  for (int l = 0; l < 2; l++)
+    if (e->laneStream[l]) ORB_CUDA(cudaStreamSynchronize(e->laneStream[l]));
+  ORB_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->sOut) ORB_CUDA(cudaStreamSynchronize(e->sOut));
+  return ORB_OK;
+}
+
 int orb_extract_batch_device(orb_extractor* e, const uint8_t* d_images, int batch, int width, int height, size_t step,
                              size_t frame_stride, orb_keypoint* d_keypoints, int capacity, int32_t* d_counts,
                              uint8_t* d_descriptors, void* stream) {
   if (!e || !d_images || !d_keypoints || !d_counts || !d_descriptors) ORB_FAIL(ORB_ERR_INVALID, "null argument");
   if (batch <= 0 || width <= 0 || height <= 0 || capacity <= 0 || step < (size_t)width) ORB_FAIL(ORB_ERR_INVALID, "bad size");
-  int st = ensure_geom(e, width, height, batch);
+  int st = drain_async(e);
+  if (st) return st;
+  st = ensure_geom(e, width, height, batch);
   if (st) return st;
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   e->lastLaunches = 0;
@@ -2311,6 +2327,14 @@ int orb_extract_batch_device(orb_extractor* e, const uint8_t* d_images, int batc
 int orb_synchronize(orb_extractor* e, void* stream) {
   if (!e) ORB_FAIL(ORB_ERR_INVALID, "null handle");
   ORB_CUDA(cudaSetDevice(e->device));
+  if (!stream) {   // everything the handle has in flight, including the copy streams of the host entry points
+    e->asyncPending = false;
+    if (e->sIn) ORB_CUDA(cudaStreamSynchronize(e->sIn));
+    for (int l = 0; l < 2; l++)
+      if (e->laneStream[l]) ORB_CUDA(cudaStreamSynchronize(e->laneStream[l]));
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->sOut) ORB_CUDA(cudaStreamSynchronize(e->sOut));
+  }
   return check_overflow(e, stream ? (cudaStream_t)stream : e->stream);
 }
 
@@ -2356,9 +2380,9 @@ int orb_get_stage_times(orb_extractor* e, double* ms5, long long* launches5) {
   return ORB_OK;
 }
 
-int orb_extract_batch_host(orb_extractor* e, const uint8_t* images, int batch, int width, int height, size_t step,
+static int batch_host_impl(orb_extractor* e, const uint8_t* images, int batch, int width, int height, size_t step,
                            size_t frame_stride, orb_keypoint* keypoints, int capacity, int32_t* counts,
-                           uint8_t* descriptors) {
+                           uint8_t* descriptors, bool wait) {
   if (!e || !images || !keypoints || !counts || !descriptors) ORB_FAIL(ORB_ERR_INVALID, "null argument");
   if (batch <= 0 || width <= 0 || height <= 0 || capacity <= 0 || step < (size_t)width) ORB_FAIL(ORB_ERR_INVALID, "bad size");
   int st = ensure_geom(e, width, height, batch);
@@ -2369,10 +2393,11 @@ int orb_extract_batch_host(orb_extractor* e, const uint8_t* images, int batch, i
   if (st) return st;
   cudaStream_t s = e->stream;
   e->lastLaunches = 0;
-  int ci = 0;
-  for (int b0 = 0; b0 < batch; b0 += chunk, ci++) {
+  // the chunk counter lives in the handle: consecutive asynchronous calls continue one pipeline
+  for (int b0 = 0; b0 < batch; b0 += chunk, e->hostChunks++) {
+    const long long ci = e->hostChunks;
     const int B = std::min(chunk, batch - b0);
-    const int b = ci & 1;
+    const int b = (int)(ci & 1);
     // H2D of this chunk: its staging buffer must no longer be read by the kernels of chunk ci-2
     if (ci >= 2) ORB_CUDA(cudaStreamWaitEvent(e->sIn, e->evDone[b], 0));
     if (step == (size_t)width && frame_stride == dFrame) {
@@ -2401,9 +2426,26 @@ int orb_extract_batch_host(orb_extractor* e, const uint8_t* images, int batch, i
                              cudaMemcpyDeviceToHost, e->sOut));
     ORB_CUDA(cudaEventRecord(e->evOut[b], e->sOut));
   }
+  if (!wait) {
+    e->asyncPending = true;
+    return ORB_OK;
+  }
+  e->asyncPending = false;
   ORB_CUDA(cudaStreamSynchronize(e->sOut));
   for (int l = 0; l < 2; l++) ORB_CUDA(cudaStreamSynchronize(e->laneStream[l]));
   return check_overflow(e, s);
+}
+
+int orb_extract_batch_host(orb_extractor* e, const uint8_t* images, int batch, int width, int height, size_t step,
+                           size_t frame_stride, orb_keypoint* keypoints, int capacity, int32_t* counts,
+                           uint8_t* descriptors) {
+  return batch_host_impl(e, images, batch, width, height, step, frame_stride, keypoints, capacity, counts, descriptors, true);
+}
+
+int orb_extract_batch_host_async(orb_extractor* e, const uint8_t* images, int batch, int width, int height, size_t step,
+                                 size_t frame_stride, orb_keypoint* keypoints, int capacity, int32_t* counts,
+                                 uint8_t* descriptors) {
+  return batch_host_impl(e, images, batch, width, height, step, frame_stride, keypoints, capacity, counts, descriptors, false);
 }
 
 int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, size_t step, orb_keypoint* keypoints,
@@ -2411,7 +2453,9 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
   if (!e || !n) ORB_FAIL(ORB_ERR_INVALID, "null argument");
   if (!image || width == 0 || height == 0) return ORB_OK;  // empty image: outputs untouched (:1537)
   if (!keypoints || !descriptors || capacity <= 0) ORB_FAIL(ORB_ERR_INVALID, "null output");
-  int st = ensure_geom(e, width, height, 1);
+  int st = drain_async(e);
+  if (st) return st;
+  st = ensure_geom(e, width, height, 1);
   if (st) return st;
   const size_t dFrame = (size_t)width * height;
   st = ensure_stage(e, dFrame, 1, capacity);
@@ -2452,7 +2496,9 @@ int orb_extract_stereo_batch_device(orb_extractor* e, const uint8_t* d_images, i
   if (!e || !d_images || !d_keypoints || !d_counts || !d_descriptors || !d_uright || !d_depth) ORB_FAIL(ORB_ERR_INVALID, "null argument");
   if (pairs <= 0 || width <= 0 || height <= 0 || capacity <= 0 || step < (size_t)width || !(mb > 0.f) || !(mbf > 0.f))
     ORB_FAIL(ORB_ERR_INVALID, "bad size or stereo baseline");
-  int st = ensure_geom(e, width, height, std::max(2, 2 * pairs));
+  int st = drain_async(e);
+  if (st) return st;
+  st = ensure_geom(e, width, height, std::max(2, 2 * pairs));
   if (st) return st;
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   e->lastLaunches = 0;
@@ -2486,7 +2532,9 @@ int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* rig
   if (!kps_left || !kps_right || !desc_left || !desc_right || !uright || !depth || capacity <= 0 || !(mb > 0.f) || !(mbf > 0.f))
     ORB_FAIL(ORB_ERR_INVALID, "null output or bad stereo baseline");
   if (e->maxBatch < 2) ORB_FAIL(ORB_ERR_INVALID, "max_batch must be >= 2 for stereo");
-  int st = ensure_geom(e, width, height, 2);
+  int st = drain_async(e);
+  if (st) return st;
+  st = ensure_geom(e, width, height, 2);
   if (st) return st;
   const size_t dFrame = (size_t)width * height;
   st = ensure_stage(e, dFrame * 2, 2, capacity);

@@ -88,11 +88,13 @@ class ORBextractor:
         check(self._L.orb_extract_batch_host(self._h, ptr(images), B, w, h, w, w * h, ptr(kps), cap, ptr(counts), ptr(desc)))
         return kps, desc, counts
 
-    def extract_batch_host_into(self, images, kps, desc, counts):
-        """Same with caller-provided (e.g. pinned) output arrays: no allocation in the timed path."""
+    def extract_batch_host_into(self, images, kps, desc, counts, wait=True):
+        """Same with caller-provided (e.g. pinned) output arrays: no allocation in the timed path. wait=False returns
+        once everything is enqueued (orb_extract_batch_host_async): call synchronize() before reading the outputs or
+        reusing the buffers; consecutive calls then form one continuous upload / compute / download pipeline."""
         B, h, w = images.shape
-        check(self._L.orb_extract_batch_host(self._h, ptr(images), B, w, h, w, w * h, ptr(kps), kps.shape[1], ptr(counts),
-                                             ptr(desc)))
+        fn = self._L.orb_extract_batch_host if wait else self._L.orb_extract_batch_host_async
+        check(fn(self._h, ptr(images), B, w, h, w, w * h, ptr(kps), kps.shape[1], ptr(counts), ptr(desc)))
 
     def extract_batch_device(self, d_images, d_kps, d_desc, d_counts, stream=None):
         """Device-resident batch: torch uint8 tensors. d_images (B,H,W); d_kps (B,cap,28) u8;

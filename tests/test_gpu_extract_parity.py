@@ -244,3 +244,28 @@ def test_cp_async_fallback_kernels_match_tma(oracle, monkeypatch):
         monkeypatch.delenv(var)
         assert len(k) == len(ref_k) > 1000
         assert k.tobytes() == ref_k.tobytes() and np.array_equal(d, ref_d)
+
+
+def test_async_host_batches_equal_blocking_calls(oracle):
+    """orb_extract_batch_host_async x3 + orb_synchronize gives the bytes of three blocking calls; a blocking
+    single-frame call right after asynchronous work drains the pipeline first."""
+    from orb_slam2_detailed_comments_b200 import KP_DTYPE, ORBextractor
+    from orb_slam2_detailed_comments_b200.synth import synth_batch
+    imgs = synth_batch(640, 480, 10, seed0=500)
+    ext = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=4)     # chunks of 4: 3 chunks per call, the last one partial
+    cap = ext.max_keypoints
+    ref = [ext.extract_batch_host(imgs[::(-1 if i == 1 else 1)].copy()) for i in range(3)]
+    ins = [imgs[::(-1 if i == 1 else 1)].copy() for i in range(3)]
+    outs = [(np.zeros((10, cap), KP_DTYPE), np.zeros((10, cap, 32), np.uint8), np.zeros(10, np.int32)) for _ in range(3)]
+    for i in range(3):
+        ext.extract_batch_host_into(ins[i], *outs[i], wait=False)
+    k1, d1 = ext(imgs[3])            # blocking call while asynchronous work is in flight
+    ext.synchronize()
+    for i in range(3):
+        rk, rd, rc = ref[i]
+        assert np.array_equal(outs[i][2], rc)
+        for f in range(10):
+            n = rc[f]
+            assert outs[i][0][f, :n].tobytes() == rk[f, :n].tobytes() and np.array_equal(outs[i][1][f, :n], rd[f, :n])
+    n3 = ref[0][2][3]
+    assert len(k1) == n3 and k1.tobytes() == ref[0][0][3, :n3].tobytes() and np.array_equal(d1, ref[0][1][3, :n3])
