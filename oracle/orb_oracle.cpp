@@ -444,8 +444,13 @@ std::vector<int> distribute_quadtree(const std::vector<Cand>& c, int minX, int m
           emit_children(ch, nullptr);
           nodes.erase(todo[j].second->self);
           if ((int)nodes.size() >= N) {
-            // the walk stopped inside a run of equal sizes -> result depends on the tie rule
-            if (tie_sensitive && j > 0 && todo[j - 1].first == todo[j].first) *tie_sensitive = 1;
+            // the walk stopped at a member of a run of equal sizes: where the node count crosses N inside
+            // that run depends on the order of its members (each split gains 0..3 nodes), i.e. on the tie
+            // rule. Conservative: flagged whenever the stopping node's run has more than one member
+            // (pinned against the reference under plain malloc, tests/test_oracle_vs_ref.py).
+            if (tie_sensitive && ((j > 0 && todo[j - 1].first == todo[j].first) ||
+                                  (j + 1 < (int)todo.size() && todo[j + 1].first == todo[j].first)))
+              *tie_sensitive = 1;
             break;
           }
         }

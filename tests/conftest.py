@@ -20,6 +20,19 @@ def oracle():
     return orb_oracle
 
 
+@pytest.fixture(scope="session")
+def reference():
+    """The reference's own ORBextractor (oracle/_ref/liborbref.so, see oracle/orb_ref.py). Built from
+    /root/reference in the development container; on the GPU box only the prebuilt binary exists."""
+    from oracle import orb_ref
+    if not orb_ref.available():
+        orb_ref.build()
+    if not orb_ref.available():
+        pytest.skip("oracle/_ref/liborbref.so not built (needs /root/reference)")
+    orb_ref.lib()
+    return orb_ref
+
+
 CONFIGS = {
     # name: (width, height, nfeatures)  -- SURVEY.md §8(a), Examples/*/*.yaml of the reference
     "tum1": (640, 480, 1000),

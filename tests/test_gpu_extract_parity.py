@@ -269,3 +269,31 @@ def test_async_host_batches_equal_blocking_calls(oracle):
             assert outs[i][0][f, :n].tobytes() == rk[f, :n].tobytes() and np.array_equal(outs[i][1][f, :n], rd[f, :n])
     n3 = ref[0][2][3]
     assert len(k1) == n3 and k1.tobytes() == ref[0][0][3, :n3].tobytes() and np.array_equal(d1, ref[0][1][3, :n3])
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_extract_matches_the_reference_itself(reference, name):
+    """The CUDA extractor against the REFERENCE's own ORBextractor.cc (oracle/_ref/liborbref.so: compiled
+    unmodified against the OpenCV stand-in, heap in canonical order - see tests/test_oracle_vs_ref.py), not
+    against the restatement: keypoints (all seven cv::KeyPoint fields except the angle bit-exact, angle within
+    1e-3 deg), mvImagePyramid incl. border, >= 99.9 % identical descriptors."""
+    from orb_slam2_detailed_comments_b200 import ORBextractor
+    from orb_slam2_detailed_comments_b200.synth import synth_frame
+    w, h, nfeat = CONFIGS[name]
+    gpu = ORBextractor(nfeat, 1.2, 8, 20, 7)
+    ref = reference.ReferenceExtractor(nfeat, 1.2, 8, 20, 7)
+    for seed in (21, 22, 23):
+        img = synth_frame(w, h, seed)
+        kps, desc = gpu(img)
+        rk, rd = ref(img)
+        assert len(kps) == len(rk)
+        for f in ("x", "y", "size", "response", "octave", "class_id"):
+            assert np.array_equal(kps[f], rk[f]), f
+        dang = np.abs(kps["angle"] - rk["angle"])
+        assert np.minimum(dang, 360.0 - dang).max() <= ANGLE_TOL_DEG
+        same = (desc == rd).all(1)
+        print(name, seed, "keypoints", len(kps), "descriptor rows differing", int((~same).sum()),
+              "angles bit-identical", bool(np.array_equal(kps["angle"], rk["angle"])))
+        assert same.mean() >= MIN_IDENTICAL_DESC
+        for l in range(8):
+            assert np.array_equal(gpu.stage_level(0, l), ref.level(l)), "mvImagePyramid[%d]" % l

@@ -1,0 +1,138 @@
+"""Pins the oracle against the REFERENCE ITSELF: oracle/_ref/liborbref.so is the reference's own
+src/ORBextractor.cc, compiled unmodified (oracle/Makefile, target `ref`) against the OpenCV stand-in of
+oracle/cvshim/. The stand-in's five primitives are the oracle's cv2-pinned ones (test_oracle_vs_cv2.py),
+so what these tests pin is everything else: the ctor tables, ComputePyramid's chaining, the 30-px cell
+loop with the iniTh/minTh fallback, DistributeOctTree / DivideNode, IC_Angle, computeOrbDescriptor and
+the level scaling - the reference's control flow, run as written.
+
+Two modes (oracle/ref_wrap.cpp): `canonical` = heap addresses grow with creation order, the tie rule of
+the oracle and the CUDA path -> everything must be IDENTICAL, order included; plain malloc = the
+reference as built by its own CMake -> identical wherever the result does not hang on a heap-address tie.
+"""
+import glob
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import CONFIGS
+from orb_slam2_detailed_comments_b200.synth import adversarial_frames, synth_frame
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rows(kps, desc):
+    return [bytes(a) + bytes(b) for a, b in zip(kps.view(np.uint8).reshape(len(kps), 28), desc)]
+
+
+def assert_identical(ko, do, kr, dr):
+    assert len(ko) == len(kr)
+    for f in ko.dtype.names:
+        assert np.array_equal(ko[f], kr[f]), f      # x, y, size, angle, response, octave, class_id: bit-exact
+    assert np.array_equal(do, dr)                    # every descriptor bit
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_tables_match_reference_ctor(oracle, reference, name):
+    w, h, nfeat = CONFIGS[name]
+    for nlevels, sf in ((8, 1.2), (4, 1.5), (12, 1.1)):
+        o = oracle.OracleExtractor(nfeat, sf, nlevels, 20, 7)
+        r = reference.ReferenceExtractor(nfeat, sf, nlevels, 20, 7)
+        for a, b in ((o.scale, r.scale), (o.inv_scale, r.inv_scale), (o.sigma2, r.sigma2), (o.inv_sigma2, r.inv_sigma2)):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_oracle_equals_reference_canonical_heap(oracle, reference, name):
+    w, h, nfeat = CONFIGS[name]
+    o = oracle.OracleExtractor(nfeat, 1.2, 8, 20, 7)
+    r = reference.ReferenceExtractor(nfeat, 1.2, 8, 20, 7)
+    n_tie = 0
+    for seed in range(8):
+        img = synth_frame(w, h, 100 + seed)
+        ko, do = o(img)
+        kr, dr = r(img)
+        assert_identical(ko, do, kr, dr)
+        for l in range(8):
+            assert np.array_equal(o.level(l), r.level(l)), (seed, l)   # mvImagePyramid incl. the 19-px border
+            n_tie += o.stats(l)["tie_sensitive"]
+    assert n_tie > 0  # the tie rule is exercised, not vacuous
+
+
+def test_oracle_equals_reference_other_parameters(oracle, reference):
+    for (nfeat, sf, nlevels, ini, mn, w, h) in ((500, 1.2, 8, 20, 7, 320, 240), (1500, 1.5, 4, 30, 10, 401, 257),
+                                                (800, 1.1, 12, 12, 5, 512, 384), (300, 1.2, 3, 40, 20, 200, 150),
+                                                (4000, 1.2, 8, 20, 7, 640, 480)):
+        o = oracle.OracleExtractor(nfeat, sf, nlevels, ini, mn)
+        r = reference.ReferenceExtractor(nfeat, sf, nlevels, ini, mn)
+        for seed in range(3):
+            img = synth_frame(w, h, 7 + seed)
+            assert_identical(*o(img), *r(img))
+            for l in range(nlevels):
+                assert np.array_equal(o.level(l), r.level(l))
+
+
+def test_oracle_equals_reference_adversarial(oracle, reference):
+    # constant / low contrast (minTh fallback everywhere, few or no corners), checkerboard (masses of equal
+    # responses and equal node sizes), uniform noise
+    for name, img in adversarial_frames(320, 240).items():
+        o = oracle.OracleExtractor(300, 1.2, 8, 20, 7)
+        r = reference.ReferenceExtractor(300, 1.2, 8, 20, 7)
+        assert_identical(*o(img), *r(img))
+    rng = np.random.RandomState(5)
+    img = rng.randint(0, 256, (376, 1241)).astype(np.uint8)
+    o = oracle.OracleExtractor(2000, 1.2, 8, 20, 7)
+    r = reference.ReferenceExtractor(2000, 1.2, 8, 20, 7)
+    assert_identical(*o(img), *r(img))
+
+
+def test_reference_extractor_is_stateless_across_calls(oracle, reference):
+    r = reference.ReferenceExtractor(1000, 1.2, 8, 20, 7)
+    a = synth_frame(640, 480, 1); b = synth_frame(640, 480, 2)
+    ka, da = r(a)
+    r(b)
+    ka2, da2 = r(a)
+    assert ka.tobytes() == ka2.tobytes() and np.array_equal(da, da2)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_reference_with_plain_malloc(oracle, reference, name):
+    """The reference as its own build runs it (glibc malloc decides the (size, pointer) ties): on every level
+    the oracle reports as not tie-sensitive the kept keypoints and their descriptors are the same SET (their
+    order may still follow heap addresses); the pyramid is identical always."""
+    w, h, nfeat = CONFIGS[name]
+    o = oracle.OracleExtractor(nfeat, 1.2, 8, 20, 7)
+    r = reference.ReferenceExtractor(nfeat, 1.2, 8, 20, 7)
+    checked = differing = 0
+    for seed in range(12):
+        img = synth_frame(w, h, 200 + seed)
+        ko, do = o(img)
+        kr, dr = r(img, canonical=False)
+        for l in range(8):
+            assert np.array_equal(o.level(l), r.level(l))
+            mo = ko["octave"] == l; mr = kr["octave"] == l
+            same = set(rows(ko[mo], do[mo])) == set(rows(kr[mr], dr[mr]))
+            if not o.stats(l)["tie_sensitive"]:
+                assert same, (seed, l)
+                checked += 1
+            elif not same:
+                differing += 1
+    print("%s: %d tie-free levels identical; %d tie-sensitive levels resolved differently by malloc" % (name, checked, differing))
+    assert checked > 0
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))))
+def test_golden_vectors_are_what_the_reference_computes(reference, path):
+    g = np.load(path)
+    r = reference.ReferenceExtractor(int(g["nfeatures"]), 1.2, 8, 20, 7)
+    kps, desc = r(g["image"])
+    assert len(kps) == len(g["kp_octave"])
+    assert np.array_equal(np.stack([kps["x"], kps["y"]], 1).reshape(-1, 2), g["kp_xy"].reshape(-1, 2))
+    assert np.array_equal(kps["octave"], g["kp_octave"]) and np.array_equal(kps["response"], g["kp_response"])
+    assert np.array_equal(kps["size"], g["kp_size"])
+    if len(kps):
+        assert np.array_equal(kps["angle"], g["kp_angle"])
+        assert np.array_equal(desc, g["descriptors"])
+    for l in range(8):
+        assert zlib.crc32(r.level(l).tobytes()) == int(g["level_crc"][l])
