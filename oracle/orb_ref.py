@@ -81,6 +81,7 @@ class ReferenceExtractor:
         desc = np.zeros((cap, 32), np.uint8)
         n = self.L.orbref_extract(self.h, _p(img), w, h, img.strides[0], _p(kps), _p(desc), cap, 1 if canonical else 0)
         assert n <= cap
+        self.last_n = n
         return kps[:n].copy(), desc[:n].copy()
 
     def level(self, l):
@@ -98,3 +99,84 @@ def extract_batch_mt(params, imgs, nthreads):
     B, h, w = imgs.shape
     nf, sf, nl, ini, mn = params
     return lib().orbref_extract_batch_mt(nf, C.c_float(sf), nl, ini, mn, _p(imgs), B, w, h, nthreads)
+
+
+# ---- ORBmatcher.cc / Frame.cc of the reference (compiled unmodified into the same library) ------------------
+def descriptor_distance(a, b):
+    """ORBmatcher::DescriptorDistance (ORBmatcher.cc:2083)."""
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orbref_descriptor_distance(_p(a), _p(b))
+
+
+def matcher_constants():
+    a = C.c_int(); b = C.c_int(); c = C.c_int()
+    lib().orbref_matcher_constants(C.byref(a), C.byref(b), C.byref(c))
+    return dict(TH_LOW=a.value, TH_HIGH=b.value, HISTO_LENGTH=c.value)
+
+
+def three_maxima(counts):
+    """ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2035) on histogram bin sizes."""
+    counts = np.ascontiguousarray(counts, np.int32)
+    out = np.zeros(3, np.int32)
+    lib().orbref_three_maxima(_p(counts), len(counts), _p(out))
+    return tuple(int(v) for v in out)
+
+
+class ReferenceFrame:
+    """An ORB_SLAM2::Frame built from given keypoints and descriptors: the reference's own UndistortKeyPoints,
+    ComputeImageBounds, AssignFeaturesToGrid and GetFeaturesInArea (Frame.cc:724, :779, :399, :590).
+    cam9 = fx fy cx cy k1 k2 p1 p2 k3."""
+
+    def __init__(self, kps, desc, cam9, w, h):
+        self.L = lib()
+        self.L.orbref_frame_create.restype = C.c_void_p
+        self.L.orbref_frame_destroy.argtypes = [C.c_void_p]
+        kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+        cam9 = np.ascontiguousarray(cam9, np.float32)
+        assert len(cam9) == 9 and desc.shape == (len(kps), 32)
+        self.n = len(kps)
+        self.h = C.c_void_p(self.L.orbref_frame_create(_p(kps), self.n, _p(desc), _p(cam9), int(w), int(h)))
+
+    def __del__(self):
+        try:
+            self.L.orbref_frame_destroy(self.h)
+        except Exception:
+            pass
+
+    def keys_un(self):
+        out = np.zeros(self.n, KP_DTYPE)
+        self.L.orbref_frame_keys_un(self.h, _p(out))
+        return out
+
+    def bounds(self):
+        b = np.zeros(4, np.float32)
+        self.L.orbref_frame_bounds(self.h, _p(b))
+        return b
+
+    def grid(self):
+        start = np.zeros(64 * 48 + 1, np.int32); items = np.zeros(max(self.n, 1), np.int32)
+        self.L.orbref_frame_grid(self.h, _p(start), _p(items))
+        return start, items[:start[-1]]
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.zeros(max(self.n, 1), np.int32)
+        n = self.L.orbref_frame_features_in_area(self.h, C.c_float(x), C.c_float(y), C.c_float(r), int(min_level), int(max_level),
+                                                 _p(out), len(out))
+        return out[:n].copy()
+
+
+def search_for_initialization(F1, F2, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    """ORBmatcher(nnratio, check_ori).SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, window)
+    (ORBmatcher.cc:573). Returns (nmatches, vnMatches12, vbPrevMatched after the call)."""
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.full(F1.n, -1, np.int32)
+    n = lib().orbref_search_for_initialization(F1.h, F2.h, _p(prev), _p(m12), int(window), C.c_float(nnratio), int(check_ori))
+    return n, m12, prev
+
+
+def stereo_matches(ref_left, ref_right, mbf, mb):
+    """Frame::ComputeStereoMatches (Frame.cc:831) on what the two ReferenceExtractors hold from their last call."""
+    n = max(1, ref_left.last_n)
+    ur = np.zeros(n, np.float32); dp = np.zeros(n, np.float32)
+    kept = lib().orbref_stereo_matches(ref_left.h, ref_right.h, C.c_float(mbf), C.c_float(mb), _p(ur), _p(dp))
+    return ur[:ref_left.last_n], dp[:ref_left.last_n], kept

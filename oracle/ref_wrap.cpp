@@ -15,7 +15,23 @@
 #include <new>
 #include <sys/mman.h>
 
-#include "ORBextractor.h"  // the reference's header: -I/root/reference/include
+#include <list>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+
+#include "cvshim.hpp"
+// The wrapper (and only the wrapper - the reference's own translation units are compiled untouched) reaches
+// Frame's private helpers UndistortKeyPoints / ComputeImageBounds / AssignFeaturesToGrid (Frame.h, `private:`)
+// and ORBmatcher's protected ComputeThreeMaxima directly. Access control does not change layout or mangling.
+#define private public
+#define protected public
+#include "ORBextractor.h"  // the reference's headers: -I/root/reference/include
+#include "Frame.h"
+#include "ORBmatcher.h"
+#undef private
+#undef protected
 
 // ---------------------------------------------------------------------------------------------------
 // Canonical heap order. DistributeOctTree sorts (size, ExtractorNode*) pairs (ORBextractor.cc:926), so
@@ -174,6 +190,135 @@ long orbref_extract_batch_mt(int nfeatures, float sf, int nlevels, int ini, int 
     });
   for (auto& x : th) x.join();
   return total.load();
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// ORBmatcher.cc / Frame.cc of the reference, compiled unmodified (oracle/Makefile). Everything they call in
+// KeyFrame / MapPoint / Map / DBoW2 is outside the pinned path and is satisfied by generated abort() stubs.
+
+int orbref_descriptor_distance(const unsigned char* a, const unsigned char* b) {
+  cv::Mat ma(1, 32, CV_8UC1, (void*)a), mb(1, 32, CV_8UC1, (void*)b);
+  return ORB_SLAM2::ORBmatcher::DescriptorDistance(ma, mb);
+}
+
+int orbref_matcher_constants(int* th_low, int* th_high, int* histo_length) {
+  *th_low = ORB_SLAM2::ORBmatcher::TH_LOW; *th_high = ORB_SLAM2::ORBmatcher::TH_HIGH;
+  *histo_length = ORB_SLAM2::ORBmatcher::HISTO_LENGTH;
+  return 0;
+}
+
+void orbref_three_maxima(const int* counts, int L, int* out3) {
+  std::vector<std::vector<int>> histo(L);
+  for (int i = 0; i < L; i++) histo[i].assign(counts[i], 0);
+  ORB_SLAM2::ORBmatcher m(0.9f, true);
+  out3[0] = out3[1] = out3[2] = -1;  // the function only assigns what it finds; every caller starts from -1 (:696)
+  m.ComputeThreeMaxima(histo.data(), L, out3[0], out3[1], out3[2]);
+}
+
+}  // extern "C"
+
+namespace {
+struct RefFrame {
+  ORB_SLAM2::Frame f;
+  int w, h;
+  // Frame's image bounds and grid cell sizes are static members (Frame.cc:45-48), set by the first constructed
+  // frame (:176-196); the wrapper re-derives them for this frame's camera before every use with the same two
+  // statements as the constructor.
+  void activate() {
+    f.ComputeImageBounds(cv::Mat(h, w, CV_8UC1));
+    ORB_SLAM2::Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (ORB_SLAM2::Frame::mnMaxX - ORB_SLAM2::Frame::mnMinX);
+    ORB_SLAM2::Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (ORB_SLAM2::Frame::mnMaxY - ORB_SLAM2::Frame::mnMinY);
+  }
+};
+}  // namespace
+
+extern "C" {
+
+// A Frame from given keypoints / descriptors: default constructor, members filled in, then the reference's own
+// UndistortKeyPoints (Frame.cc:724) and AssignFeaturesToGrid (:399). cam9 = fx fy cx cy k1 k2 p1 p2 k3.
+void* orbref_frame_create(const void* kps, int n, const unsigned char* desc, const float* cam9, int w, int h) {
+  RefFrame* r = new RefFrame();
+  r->w = w; r->h = h;
+  ORB_SLAM2::Frame& f = r->f;
+  f.N = n;
+  f.mvKeys.assign((const cv::KeyPoint*)kps, (const cv::KeyPoint*)kps + n);
+  f.mDescriptors = cv::Mat(n, 32, CV_8UC1);
+  if (n) memcpy(f.mDescriptors.data, desc, (size_t)n * 32);
+  f.mK = cv::Mat::eye(3, 3, CV_32F);
+  f.mK.at<float>(0, 0) = cam9[0]; f.mK.at<float>(1, 1) = cam9[1]; f.mK.at<float>(0, 2) = cam9[2]; f.mK.at<float>(1, 2) = cam9[3];
+  const int nd = cam9[8] != 0.0f ? 5 : 4;  // Tracking.cc: k3 is appended only when it is non-zero
+  f.mDistCoef = cv::Mat(nd, 1, CV_32F);
+  for (int i = 0; i < nd; i++) f.mDistCoef.at<float>(i) = cam9[4 + i];
+  r->activate();
+  f.UndistortKeyPoints();
+  f.mvpMapPoints.assign(n, (ORB_SLAM2::MapPoint*)nullptr);
+  f.mvbOutlier.assign(n, false);
+  f.AssignFeaturesToGrid();
+  return r;
+}
+void orbref_frame_destroy(void* h) { delete (RefFrame*)h; }
+
+void orbref_frame_keys_un(void* h, void* kps_out) {
+  RefFrame* r = (RefFrame*)h;
+  if (r->f.N) memcpy(kps_out, r->f.mvKeysUn.data(), (size_t)r->f.N * sizeof(cv::KeyPoint));
+}
+void orbref_frame_bounds(void* h, float* b4) {
+  RefFrame* r = (RefFrame*)h;
+  r->activate();
+  b4[0] = ORB_SLAM2::Frame::mnMinX; b4[1] = ORB_SLAM2::Frame::mnMaxX; b4[2] = ORB_SLAM2::Frame::mnMinY; b4[3] = ORB_SLAM2::Frame::mnMaxY;
+}
+// mGrid as CSR: cell = ix*48 + iy, items in the order AssignFeaturesToGrid pushed them
+void orbref_frame_grid(void* h, int* cellStart /* 64*48+1 */, int* items /* N */) {
+  RefFrame* r = (RefFrame*)h;
+  int pos = 0;
+  for (int ix = 0; ix < FRAME_GRID_COLS; ix++)
+    for (int iy = 0; iy < FRAME_GRID_ROWS; iy++) {
+      cellStart[ix * FRAME_GRID_ROWS + iy] = pos;
+      for (size_t idx : r->f.mGrid[ix][iy]) items[pos++] = (int)idx;
+    }
+  cellStart[FRAME_GRID_COLS * FRAME_GRID_ROWS] = pos;
+}
+int orbref_frame_features_in_area(void* h, float x, float y, float rad, int minLevel, int maxLevel, int* out, int cap) {
+  RefFrame* r = (RefFrame*)h;
+  r->activate();
+  std::vector<size_t> v = r->f.GetFeaturesInArea(x, y, rad, minLevel, maxLevel);
+  for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = (int)v[i];
+  return (int)v.size();
+}
+
+// ORBmatcher(nnratio, checkOri).SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), ORBmatcher.cc:573
+int orbref_search_for_initialization(void* h1, void* h2, float* prevMatchedXY /* in/out, N1 x 2 */, int* matches12 /* N1 */,
+                                     int windowSize, float nnratio, int checkOri) {
+  RefFrame *a = (RefFrame*)h1, *b = (RefFrame*)h2;
+  a->activate();
+  std::vector<cv::Point2f> prev(a->f.N);
+  for (int i = 0; i < a->f.N; i++) prev[i] = cv::Point2f(prevMatchedXY[2 * i], prevMatchedXY[2 * i + 1]);
+  std::vector<int> m12;
+  ORB_SLAM2::ORBmatcher matcher(nnratio, checkOri != 0);
+  int n = matcher.SearchForInitialization(a->f, b->f, prev, m12, windowSize);
+  for (int i = 0; i < a->f.N; i++) {
+    prevMatchedXY[2 * i] = prev[i].x; prevMatchedXY[2 * i + 1] = prev[i].y;
+    matches12[i] = m12[i];
+  }
+  return n;
+}
+
+// Frame::ComputeStereoMatches (Frame.cc:831) on the keypoints, descriptors and pyramids the two reference
+// extractors hold from their last orbref_extract call. Returns the number of keypoints with a depth.
+int orbref_stereo_matches(void* hL, void* hR, float mbf, float mb, float* uRight, float* depth) {
+  Ref *L = (Ref*)hL, *R = (Ref*)hR;
+  ORB_SLAM2::Frame f;
+  f.mpORBextractorLeft = &L->ex; f.mpORBextractorRight = &R->ex;
+  f.mvKeys = L->kps; f.mvKeysRight = R->kps;
+  f.N = (int)f.mvKeys.size();
+  f.mDescriptors = L->desc.clone(); f.mDescriptorsRight = R->desc.clone();
+  f.mvScaleFactors = L->ex.GetScaleFactors(); f.mvInvScaleFactors = L->ex.GetInverseScaleFactors();
+  f.mbf = mbf; f.mb = mb;
+  f.ComputeStereoMatches();
+  int kept = 0;
+  for (int i = 0; i < f.N; i++) { uRight[i] = f.mvuRight[i]; depth[i] = f.mvDepth[i]; kept += f.mvDepth[i] > 0; }
+  return kept;
 }
 
 }  // extern "C"

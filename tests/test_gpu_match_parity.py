@@ -170,3 +170,22 @@ def test_int_pipe_peak_runs():
     pk = int_pipe_peak(0)
     print(pk)
     assert pk["popc"] > 1e11 and pk["lop3"] > pk["popc"]
+
+
+@pytest.mark.parametrize("window", [100, 30])
+def test_search_for_initialization_against_the_reference_itself(oracle, reference, window):
+    """The CUDA matcher against the reference's own ORBmatcher::SearchForInitialization + Frame::GetFeaturesInArea
+    (src/ORBmatcher.cc and src/Frame.cc compiled unmodified into oracle/_ref/liborbref.so): vnMatches12, the match
+    count and the updated vbPrevMatched are identical, also on the second call with the updated positions."""
+    from orb_slam2_detailed_comments_b200 import FrameView, ORBmatcher
+    ka, da, kb, db = _frames_from_extraction(oracle)
+    cam = np.array([500, 500, 320, 240, 0, 0, 0, 0, 0], np.float32)   # no distortion: mvKeysUn = mvKeys, bounds = image
+    R1 = reference.ReferenceFrame(ka, da, cam, 640, 480); R2 = reference.ReferenceFrame(kb, db, cam, 640, 480)
+    F1 = FrameView.from_keypoints(ka, da, 640, 480); F2 = FrameView.from_keypoints(kb, db, 640, 480)
+    m = ORBmatcher(0.9, True)
+    prev_gpu = F1.xy.copy(); prev_ref = F1.xy.copy()
+    for call in range(2):
+        n_ref, m_ref, prev_ref = reference.search_for_initialization(R1, R2, prev_ref, window, 0.9, True)
+        n, m12 = m.SearchForInitialization(F1, F2, prev_gpu, window, mode=0)
+        print("window", window, "call", call, "matches", n_ref)
+        assert n == n_ref > 20 and np.array_equal(m12, m_ref) and np.array_equal(prev_gpu, prev_ref)

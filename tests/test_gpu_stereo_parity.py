@@ -79,3 +79,25 @@ def test_stereo_batch_device(oracle):
         assert np.array_equal(ur[p, :len(okl)].view(np.uint32), our.view(np.uint32))
         assert np.array_equal(dp[p, :len(okl)].view(np.uint32), odp.view(np.uint32))
         assert n > len(okl) // 3
+
+
+@pytest.mark.parametrize("name,disp", [("kitti", 17), ("euroc", 31)])
+def test_stereo_against_the_reference_itself(reference, name, disp):
+    """Both eyes + ComputeStereoMatches on the GPU against the reference's own ORBextractor.cc + Frame.cc
+    (oracle/_ref/liborbref.so, compiled unmodified): keypoints, descriptors, mvuRight and mvDepth bit-exact."""
+    from orb_slam2_detailed_comments_b200 import ORBextractor
+    w, h, nfeat = CONFIGS[name]
+    gpu = ORBextractor(nfeat, 1.2, 8, 20, 7, max_batch=4)
+    left, right = stereo_pair(w, h, 6, disp)
+    rL = reference.ReferenceExtractor(nfeat, 1.2, 8, 20, 7); rR = reference.ReferenceExtractor(nfeat, 1.2, 8, 20, 7)
+    rkl, rdl = rL(left); rkr, rdr = rR(right)
+    mbf, mb = 386.1448, 386.1448 / 718.856
+    rur, rdp, rn = reference.stereo_matches(rL, rR, mbf, mb)
+    kl, dl, kr, dr, ur, dp = gpu.extract_stereo(left, right, mbf, mb)
+    for f in ("x", "y", "size", "octave", "response", "class_id"):
+        assert np.array_equal(kl[f], rkl[f]) and np.array_equal(kr[f], rkr[f]), f
+    assert (dl == rdl).all(1).mean() >= 0.999 and (dr == rdr).all(1).mean() >= 0.999
+    assert np.array_equal(ur.view(np.uint32), rur.view(np.uint32)), "mvuRight differs"
+    assert np.array_equal(dp.view(np.uint32), rdp.view(np.uint32)), "mvDepth differs"
+    print(name, "stereo points", rn, "of", len(kl))
+    assert rn > len(kl) // 3
