@@ -6,15 +6,18 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library; the product (orb_slam2_detailed_comments_b200/) never does.
 //
-// PARITY PINNING: the reference holds no golden vectors, tests or fixtures for this
-// path and cannot be compiled here (needs OpenCV C++/Eigen/Pangolin headers), so
-// parity is UNPINNED BY THE REFERENCE ITSELF. What pins this oracle instead:
-//   * every OpenCV primitive it restates (resize INTER_LINEAR, copyMakeBorder
-//     REFLECT_101, FAST 9/16 + NMS, GaussianBlur 7x7 s=2, fastAtan2) is checked
-//     bit-exactly against python cv2 4.13.0 in tests/test_oracle_vs_cv2.py;
-//   * the full operator() is checked end-to-end against a cv2-driven restatement of
-//     the reference control flow (tests/cv2_reference.py) and committed golden vectors.
-// The pixel arithmetic therefore is "reference control flow + OpenCV 4.13 primitives".
+// PARITY PINNING: the reference holds no golden vectors, tests or fixtures for this path.
+// The oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF, run here:
+//   * oracle/_ref/liborbref.so = the reference's own src/ORBextractor.cc, src/ORBmatcher.cc and
+//     src/Frame.cc compiled unmodified (oracle/Makefile target `ref`, wrapper oracle/ref_wrap.cpp,
+//     OpenCV stand-in oracle/cvshim/): tests/test_oracle_vs_ref.py and test_oracle_vs_ref_matcher.py
+//     require bit-identical keypoints, descriptors, pyramids, matches, grids, mvuRight / mvDepth;
+//   * every OpenCV primitive restated below (resize INTER_LINEAR, copyMakeBorder REFLECT_101,
+//     FAST 9/16 + NMS, GaussianBlur 7x7 s=2, fastAtan2, undistortPoints, gemm order) is checked
+//     bit-exactly against python cv2 4.13.0 (tests/test_oracle_vs_cv2.py, test_oracle_frame.py) -
+//     these same functions serve the OpenCV calls of _ref;
+//   * a cv2-driven restatement of the control flow (tests/cv2_reference.py) and golden vectors.
+// The pixel arithmetic therefore is "the reference's code + OpenCV 4.13 primitives".
 //
 // Canonicalised non-determinism: DistributeOctTree sorts (size, node pointer) pairs
 // (ORBextractor.cc:926); ties are broken by heap address in the reference. Canonical
