@@ -258,6 +258,9 @@ class _InputArray {
 class _OutputArray {
  public:
   _OutputArray(Mat& m) : m_(&m) {}
+  // a temporary view (Rwc.copyTo(Twc.rowRange(0,3).colRange(0,3)), KeyFrame.cc): the header is kept by value, and
+  // create() with the view's own size and type keeps writing into the parent's buffer
+  _OutputArray(const Mat& m) : own_(m), m_(&own_) {}
   void create(int r, int c, int type) const { m_->create(r, c, type); }
   void create(Size sz, int type) const { m_->create(sz, type); }
   void release() const { m_->release(); }
@@ -265,6 +268,7 @@ class _OutputArray {
   Mat& getMatRef() const { return *m_; }
 
  private:
+  mutable Mat own_;
   Mat* m_;
 };
 typedef const _InputArray& InputArray;

@@ -180,3 +180,89 @@ def stereo_matches(ref_left, ref_right, mbf, mb):
     ur = np.zeros(n, np.float32); dp = np.zeros(n, np.float32)
     kept = lib().orbref_stereo_matches(ref_left.h, ref_right.h, C.c_float(mbf), C.c_float(mb), _p(ur), _p(dp))
     return ur[:ref_left.last_n], dp[:ref_left.last_n], kept
+
+
+def search_last_frame(cur_frame, uright, occupied0, last_kps, Xw, mp_flags, mp_desc, Tcw, cam4, mbf, mb, th, direction, scale_factors):
+    """ORBmatcher(0.9, true).SearchByProjection(CurrentFrame, LastFrame, th, bMono=false) (ORBmatcher.cc:1710) on live
+    MapPoint objects. Returns (nmatches, CurrentFrame.mvpMapPoints as indices into the last frame, -1 = none)."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    last_kps = np.ascontiguousarray(last_kps, KP_DTYPE)
+    uright, Xw, Tcw, cam4, sf = f32(uright), f32(Xw), f32(Tcw), f32(cam4), f32(scale_factors)
+    occupied0, mp_flags, mp_desc = u8(occupied0), u8(mp_flags), u8(mp_desc)
+    out = np.full(cur_frame.n, -1, np.int32)
+    n = lib().orbref_search_last_frame(cur_frame.h, _p(uright), _p(occupied0), _p(last_kps), len(last_kps), _p(Xw), _p(mp_flags),
+                                       _p(mp_desc), _p(Tcw), _p(cam4), C.c_float(mbf), C.c_float(mb), C.c_float(th), int(direction),
+                                       _p(sf), len(sf), _p(out))
+    return n, out
+
+
+def search_local_map(cur_frame, uright, occupied0, mps, th, nnratio, cam4, mbf, mb, scale_factors):
+    """ORBmatcher(nnratio).SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:72). mps: list of dicts with the
+    MapPoint tracking fields (track_in_view, bad, level, view_cos, x, y, xr, desc, nobs)."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    n = len(mps)
+    tiv = u8([m["track_in_view"] for m in mps]); bad = u8([m["bad"] for m in mps])
+    lvl = np.ascontiguousarray([m["level"] for m in mps], np.int32); nobs = np.ascontiguousarray([m["nobs"] for m in mps], np.int32)
+    vc = f32([m["view_cos"] for m in mps]); x = f32([m["x"] for m in mps]); y = f32([m["y"] for m in mps]); xr = f32([m["xr"] for m in mps])
+    desc = u8(np.stack([m["desc"] for m in mps]))
+    uright, cam4, sf, occupied0 = f32(uright), f32(cam4), f32(scale_factors), u8(occupied0)
+    out = np.full(cur_frame.n, -1, np.int32)
+    k = lib().orbref_search_local_map(cur_frame.h, _p(uright), _p(occupied0), n, _p(tiv), _p(bad), _p(lvl), _p(vc), _p(x), _p(y), _p(xr),
+                                      _p(desc), _p(nobs), C.c_float(th), C.c_float(nnratio), _p(cam4), C.c_float(mbf), C.c_float(mb),
+                                      _p(sf), len(sf), _p(out))
+    return k, out
+
+
+def _bow_args(kps, desc, node, usable):
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    node = np.ascontiguousarray(node, np.int32)
+    usable = None if usable is None else np.ascontiguousarray(usable, np.uint8)
+    return kps, desc, node, usable
+
+
+def search_by_bow_frame(kps1, desc1, node1, usable1, kps2, desc2, node2, nnratio, check_ori, scale_factors):
+    """ORBmatcher(nnratio, check_ori).SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:247) on a live KeyFrame.
+    Returns (nmatches, per frame feature: the keyframe feature it was matched to or -1)."""
+    k1, d1, n1, u1 = _bow_args(kps1, desc1, node1, usable1); k2, d2, n2, _ = _bow_args(kps2, desc2, node2, None)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    out = np.full(len(k2), -1, np.int32)
+    n = lib().orbref_search_by_bow_frame(_p(k1), len(k1), _p(d1), _p(n1), _p(u1), _p(k2), len(k2), _p(d2), _p(n2), C.c_float(nnratio),
+                                         int(check_ori), _p(sf), len(sf), _p(out))
+    return n, out
+
+
+def search_by_bow_keyframes(kps1, desc1, node1, usable1, kps2, desc2, node2, usable2, nnratio, check_ori, scale_factors):
+    """ORBmatcher(nnratio, check_ori).SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (ORBmatcher.cc:729).
+    Returns (nmatches, per keyframe-1 feature: the keyframe-2 feature or -1)."""
+    k1, d1, n1, u1 = _bow_args(kps1, desc1, node1, usable1); k2, d2, n2, u2 = _bow_args(kps2, desc2, node2, usable2)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    out = np.full(len(k1), -1, np.int32)
+    n = lib().orbref_search_by_bow_keyframes(_p(k1), len(k1), _p(d1), _p(n1), _p(u1), _p(k2), len(k2), _p(d2), _p(n2), _p(u2),
+                                             C.c_float(nnratio), int(check_ori), _p(sf), len(sf), _p(out))
+    return n, out
+
+
+def search_for_triangulation(kps1, desc1, node1, has_mp1, ur1, kps2, desc2, node2, has_mp2, ur2, Tcw2, cam4, F12, only_stereo,
+                             check_ori, scale_factors, level_sigma2):
+    """ORBmatcher(0.6, check_ori).SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (ORBmatcher.cc:884),
+    keyframe 1 at the identity pose, keyframe 2 at Tcw2. Returns (nmatches, matches12)."""
+    k1, d1, n1, h1 = _bow_args(kps1, desc1, node1, has_mp1); k2, d2, n2, h2 = _bow_args(kps2, desc2, node2, has_mp2)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u1 = f32(np.full(len(k1), -1) if ur1 is None else ur1); u2 = f32(np.full(len(k2), -1) if ur2 is None else ur2)
+    T, cam4, F12, sf, s2 = f32(Tcw2), f32(cam4), f32(F12), f32(scale_factors), f32(level_sigma2)
+    out = np.full(len(k1), -1, np.int32)
+    n = lib().orbref_search_for_triangulation(_p(k1), len(k1), _p(d1), _p(n1), _p(h1), _p(u1), _p(k2), len(k2), _p(d2), _p(n2), _p(h2),
+                                              _p(u2), _p(T), _p(cam4), _p(F12), int(only_stereo), int(check_ori), _p(sf), _p(s2), len(sf),
+                                              _p(out))
+    return n, out
+
+
+def distinctive_descriptors(desc, offsets):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:365) on live MapPoint / KeyFrame objects, for map points with
+    observations desc[offsets[p]:offsets[p+1]] (every map point needs >= 1). Returns the chosen descriptor of every point."""
+    desc = np.ascontiguousarray(desc, np.uint8); offsets = np.ascontiguousarray(offsets, np.int32)
+    out = np.zeros((len(offsets) - 1, 32), np.uint8)
+    lib().orbref_distinctive_descriptors(_p(desc), _p(offsets), len(out), _p(out))
+    return out

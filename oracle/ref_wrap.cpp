@@ -29,6 +29,9 @@
 #define protected public
 #include "ORBextractor.h"  // the reference's headers: -I/root/reference/include
 #include "Frame.h"
+#include "KeyFrame.h"
+#include "Map.h"
+#include "MapPoint.h"
 #include "ORBmatcher.h"
 #undef private
 #undef protected
@@ -321,4 +324,295 @@ int orbref_stereo_matches(void* hL, void* hR, float mbf, float mb, float* uRight
   return kept;
 }
 
+
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// The projection searches of Tracking (ORBmatcher.cc:72 local map, :1710 last frame) on live ORB_SLAM2::MapPoint
+// objects (src/MapPoint.cc, src/Map.cc compiled unmodified). The wrapper builds the frames and map points from
+// flat arrays in the layout the oracle's entry points use, runs the reference function and flattens
+// CurrentFrame.mvpMapPoints back into indices.
+namespace {
+void set_tracking_state(RefFrame* cur, const float* uright, const unsigned char* occupied0, float mbf, float mb,
+                        const float* scaleFactors, int nlevels, const float* cam4, ORB_SLAM2::Map* map, ORB_SLAM2::Frame& helper,
+                        std::vector<ORB_SLAM2::MapPoint*>& owned) {
+  ORB_SLAM2::Frame& f = cur->f;
+  cur->activate();
+  f.mvuRight.assign(f.N, -1.f);
+  if (uright) f.mvuRight.assign(uright, uright + f.N);
+  f.mbf = mbf; f.mb = mb;
+  f.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+  f.mnScaleLevels = nlevels;
+  ORB_SLAM2::Frame::fx = cam4[0]; ORB_SLAM2::Frame::fy = cam4[1]; ORB_SLAM2::Frame::cx = cam4[2]; ORB_SLAM2::Frame::cy = cam4[3];
+  ORB_SLAM2::Frame::invfx = 1.0f / cam4[0]; ORB_SLAM2::Frame::invfy = 1.0f / cam4[1];
+  // keypoints that already hold an observed map point: one shared MapPoint with Observations() > 0
+  helper.N = 1;
+  helper.mvKeysUn.assign(1, cv::KeyPoint());
+  helper.mvScaleFactors = f.mvScaleFactors; helper.mnScaleLevels = nlevels;
+  helper.mDescriptors = cv::Mat::zeros(1, 32, CV_8UC1);
+  helper.SetPose(cv::Mat::eye(4, 4, CV_32F));
+  cv::Mat pos = (cv::Mat_<float>(3, 1) << 0.f, 0.f, 1.f);
+  ORB_SLAM2::MapPoint* taken = new ORB_SLAM2::MapPoint(pos, map, &helper, 0);
+  taken->nObs = 1;
+  owned.push_back(taken);
+  f.mvpMapPoints.assign(f.N, (ORB_SLAM2::MapPoint*)nullptr);
+  for (int i = 0; i < f.N; i++)
+    if (occupied0 && occupied0[i]) f.mvpMapPoints[i] = taken;
+}
+void flatten(const ORB_SLAM2::Frame& f, const std::vector<ORB_SLAM2::MapPoint*>& queries, int* matchOfKp) {
+  std::map<ORB_SLAM2::MapPoint*, int> index;
+  for (size_t i = 0; i < queries.size(); i++)
+    if (queries[i]) index[queries[i]] = (int)i;
+  for (int i = 0; i < f.N; i++) {
+    auto it = index.find(f.mvpMapPoints[i]);
+    matchOfKp[i] = it == index.end() ? -1 : it->second;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// ORBmatcher(0.9, true).SearchByProjection(CurrentFrame, LastFrame, th, bMono=false), ORBmatcher.cc:1710.
+// mpFlags bit0: LastFrame.mvpMapPoints[i] exists and is no outlier; bit1: its Observations() > 0.
+// direction 0 / 1 / 2 = neither / bForward / bBackward: realised through LastFrame's pose (tlc.z = 0, +3 mb, -3 mb).
+int orbref_search_last_frame(void* hCur, const float* uright, const unsigned char* occupied0, const void* lastKps, int n1,
+                             const float* Xw, const unsigned char* mpFlags, const unsigned char* mpDesc, const float* Tcw16,
+                             const float* cam4, float mbf, float mb, float th, int direction, const float* scaleFactors, int nlevels,
+                             int* matchOfKp) {
+  RefFrame* cur = (RefFrame*)hCur;
+  ORB_SLAM2::Map map;
+  ORB_SLAM2::Frame helper;
+  std::vector<ORB_SLAM2::MapPoint*> owned;
+  set_tracking_state(cur, uright, occupied0, mbf, mb, scaleFactors, nlevels, cam4, &map, helper, owned);
+  cv::Mat Tcw(4, 4, CV_32F);
+  memcpy(Tcw.data, Tcw16, 16 * sizeof(float));
+  cur->f.SetPose(Tcw);
+  ORB_SLAM2::Frame last;
+  last.N = n1;
+  last.mvKeys.assign((const cv::KeyPoint*)lastKps, (const cv::KeyPoint*)lastKps + n1);
+  last.mvKeysUn = last.mvKeys;
+  last.mDescriptors = cv::Mat(n1, 32, CV_8UC1);
+  if (n1) memcpy(last.mDescriptors.data, mpDesc, (size_t)n1 * 32);
+  last.mvScaleFactors = cur->f.mvScaleFactors; last.mnScaleLevels = nlevels;
+  // Rlw = I, tlw = d - twc  =>  tlc = Rlw*twc + tlw = d
+  cv::Mat twc = cur->f.GetCameraCenter();
+  cv::Mat Tlw = cv::Mat::eye(4, 4, CV_32F);
+  const float dz = direction == 1 ? 3.f * mb : (direction == 2 ? -3.f * mb : 0.f);
+  Tlw.at<float>(0, 3) = -twc.at<float>(0); Tlw.at<float>(1, 3) = -twc.at<float>(1); Tlw.at<float>(2, 3) = dz - twc.at<float>(2);
+  last.SetPose(Tlw);
+  last.mvpMapPoints.assign(n1, (ORB_SLAM2::MapPoint*)nullptr);
+  last.mvbOutlier.assign(n1, false);
+  for (int i = 0; i < n1; i++) {
+    if (!(mpFlags[i] & 1)) continue;
+    cv::Mat pos = (cv::Mat_<float>(3, 1) << Xw[3 * i], Xw[3 * i + 1], Xw[3 * i + 2]);
+    ORB_SLAM2::MapPoint* mp = new ORB_SLAM2::MapPoint(pos, &map, &last, i);
+    mp->nObs = (mpFlags[i] & 2) ? 1 : 0;
+    last.mvpMapPoints[i] = mp;
+    owned.push_back(mp);
+  }
+  ORB_SLAM2::ORBmatcher matcher(0.9f, true);
+  const int n = matcher.SearchByProjection(cur->f, last, th, false);
+  flatten(cur->f, last.mvpMapPoints, matchOfKp);
+  for (ORB_SLAM2::MapPoint* p : owned) delete p;
+  cur->f.mvpMapPoints.assign(cur->f.N, (ORB_SLAM2::MapPoint*)nullptr);
+  return n;
+}
+
+// ORBmatcher(nnratio).SearchByProjection(F, vpMapPoints, th), ORBmatcher.cc:72, on map points whose tracking fields
+// (the output of Frame::isInFrustum) are given.
+int orbref_search_local_map(void* hCur, const float* uright, const unsigned char* occupied0, int nmp, const unsigned char* trackInView,
+                            const unsigned char* bad, const int* level, const float* viewCos, const float* projX, const float* projY,
+                            const float* projXR, const unsigned char* desc, const int* nobs, float th, float nnratio,
+                            const float* cam4, float mbf, float mb, const float* scaleFactors, int nlevels, int* matchOfKp) {
+  RefFrame* cur = (RefFrame*)hCur;
+  ORB_SLAM2::Map map;
+  ORB_SLAM2::Frame helper, src;
+  std::vector<ORB_SLAM2::MapPoint*> owned;
+  set_tracking_state(cur, uright, occupied0, mbf, mb, scaleFactors, nlevels, cam4, &map, helper, owned);
+  src.N = nmp;
+  src.mvKeysUn.assign(nmp, cv::KeyPoint());
+  src.mvScaleFactors = cur->f.mvScaleFactors; src.mnScaleLevels = nlevels;
+  src.mDescriptors = cv::Mat(nmp, 32, CV_8UC1);
+  if (nmp) memcpy(src.mDescriptors.data, desc, (size_t)nmp * 32);
+  src.SetPose(cv::Mat::eye(4, 4, CV_32F));
+  std::vector<ORB_SLAM2::MapPoint*> mps(nmp);
+  cv::Mat pos = (cv::Mat_<float>(3, 1) << 0.f, 0.f, 1.f);
+  for (int i = 0; i < nmp; i++) {
+    ORB_SLAM2::MapPoint* mp = new ORB_SLAM2::MapPoint(pos, &map, &src, i);  // mDescriptor = desc row i (MapPoint.cc:107)
+    mp->mbTrackInView = trackInView[i] != 0;
+    mp->mbBad = bad[i] != 0;
+    mp->mnTrackScaleLevel = level[i];
+    mp->mTrackViewCos = viewCos[i];
+    mp->mTrackProjX = projX[i]; mp->mTrackProjY = projY[i]; mp->mTrackProjXR = projXR[i];
+    mp->nObs = nobs[i];
+    mps[i] = mp;
+    owned.push_back(mp);
+  }
+  ORB_SLAM2::ORBmatcher matcher(nnratio, true);
+  const int n = matcher.SearchByProjection(cur->f, mps, th);
+  flatten(cur->f, mps, matchOfKp);
+  for (ORB_SLAM2::MapPoint* p : owned) delete p;
+  cur->f.mvpMapPoints.assign(cur->f.N, (ORB_SLAM2::MapPoint*)nullptr);
+  return n;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// The bag-of-words guided searches (ORBmatcher.cc:247 keyframe -> frame, :729 keyframe -> keyframe, :884
+// triangulation) on live ORB_SLAM2::KeyFrame objects (src/KeyFrame.cc compiled unmodified). A DBoW2::FeatureVector
+// is given as the vocabulary node id of every feature (-1 = none), the layout the oracle and the device use.
+namespace {
+struct Side {
+  ORB_SLAM2::Frame f;
+  ORB_SLAM2::KeyFrame* kf = nullptr;
+  std::vector<ORB_SLAM2::MapPoint*> mps;
+  ~Side() {
+    delete kf;
+    for (ORB_SLAM2::MapPoint* p : mps) delete p;
+  }
+  // hasMp[i]: feature i holds a (good) map point
+  void build(const void* kps, int n, const unsigned char* desc, const int* node, const unsigned char* hasMp, const float* uright,
+             const float* Tcw16, const float* cam4, const float* scaleFactors, const float* levelSigma2, int nlevels,
+             ORB_SLAM2::Map* map, bool asKeyFrame) {
+    f.N = n;
+    f.mvKeys.assign((const cv::KeyPoint*)kps, (const cv::KeyPoint*)kps + n);
+    f.mvKeysUn = f.mvKeys;
+    f.mDescriptors = cv::Mat(n, 32, CV_8UC1);
+    if (n) memcpy(f.mDescriptors.data, desc, (size_t)n * 32);
+    for (int i = 0; i < n; i++)
+      if (node[i] >= 0) f.mFeatVec.addFeature((DBoW2::NodeId)node[i], (unsigned int)i);
+    f.mvuRight.assign(n, -1.f);
+    if (uright) f.mvuRight.assign(uright, uright + n);
+    f.mvDepth.assign(n, -1.f);
+    f.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    f.mvLevelSigma2.assign(levelSigma2, levelSigma2 + nlevels);
+    f.mnScaleLevels = nlevels;
+    f.mb = 0.5f; f.mbf = 40.f;
+    ORB_SLAM2::Frame::fx = cam4[0]; ORB_SLAM2::Frame::fy = cam4[1]; ORB_SLAM2::Frame::cx = cam4[2]; ORB_SLAM2::Frame::cy = cam4[3];
+    ORB_SLAM2::Frame::invfx = 1.0f / cam4[0]; ORB_SLAM2::Frame::invfy = 1.0f / cam4[1];
+    cv::Mat Tcw = cv::Mat::eye(4, 4, CV_32F);
+    if (Tcw16) memcpy(Tcw.data, Tcw16, 16 * sizeof(float));
+    f.SetPose(Tcw);
+    f.mvpMapPoints.assign(n, (ORB_SLAM2::MapPoint*)nullptr);
+    f.mvbOutlier.assign(n, false);
+    cv::Mat pos = (cv::Mat_<float>(3, 1) << 0.f, 0.f, 1.f);
+    for (int i = 0; i < n; i++)
+      if (hasMp && hasMp[i]) {
+        ORB_SLAM2::MapPoint* mp = new ORB_SLAM2::MapPoint(pos, map, &f, i);
+        mps.push_back(mp);
+        f.mvpMapPoints[i] = mp;
+      }
+    if (asKeyFrame) kf = new ORB_SLAM2::KeyFrame(f, map, (ORB_SLAM2::KeyFrameDatabase*)nullptr);
+  }
+  int index_of(ORB_SLAM2::MapPoint* p) const {
+    if (!p) return -1;
+    for (int i = 0; i < f.N; i++)
+      if (f.mvpMapPoints[i] == p) return i;
+    return -1;
+  }
+};
+const float kIdentityCam[4] = {500.f, 500.f, 320.f, 240.f};
+}  // namespace
+
+extern "C" {
+
+// ORBmatcher(nnratio, checkOri).SearchByBoW(pKF, F, vpMapPointMatches), ORBmatcher.cc:247.
+// matchOfKp[j] = keyframe feature whose map point frame feature j received (-1 = none).
+int orbref_search_by_bow_frame(const void* kps1, int n1, const unsigned char* desc1, const int* node1, const unsigned char* usable1,
+                               const void* kps2, int n2, const unsigned char* desc2, const int* node2, float nnratio, int checkOri,
+                               const float* scaleFactors, int nlevels, int* matchOfKp) {
+  ORB_SLAM2::Map map;
+  Side a, b;
+  std::vector<float> s2(scaleFactors, scaleFactors + nlevels);
+  a.build(kps1, n1, desc1, node1, usable1, nullptr, nullptr, kIdentityCam, scaleFactors, s2.data(), nlevels, &map, true);
+  b.build(kps2, n2, desc2, node2, nullptr, nullptr, nullptr, kIdentityCam, scaleFactors, s2.data(), nlevels, &map, false);
+  std::vector<ORB_SLAM2::MapPoint*> matches;
+  ORB_SLAM2::ORBmatcher matcher(nnratio, checkOri != 0);
+  const int n = matcher.SearchByBoW(a.kf, b.f, matches);
+  for (int j = 0; j < n2; j++) matchOfKp[j] = a.index_of(matches[j]);
+  return n;
+}
+
+// ORBmatcher(nnratio, checkOri).SearchByBoW(pKF1, pKF2, vpMatches12), ORBmatcher.cc:729.
+// matches12[i] = keyframe-2 feature whose map point keyframe-1 feature i was matched to (-1 = none).
+int orbref_search_by_bow_keyframes(const void* kps1, int n1, const unsigned char* desc1, const int* node1, const unsigned char* usable1,
+                                   const void* kps2, int n2, const unsigned char* desc2, const int* node2, const unsigned char* usable2,
+                                   float nnratio, int checkOri, const float* scaleFactors, int nlevels, int* matches12) {
+  ORB_SLAM2::Map map;
+  Side a, b;
+  std::vector<float> s2(scaleFactors, scaleFactors + nlevels);
+  a.build(kps1, n1, desc1, node1, usable1, nullptr, nullptr, kIdentityCam, scaleFactors, s2.data(), nlevels, &map, true);
+  b.build(kps2, n2, desc2, node2, usable2, nullptr, nullptr, kIdentityCam, scaleFactors, s2.data(), nlevels, &map, true);
+  std::vector<ORB_SLAM2::MapPoint*> matches;
+  ORB_SLAM2::ORBmatcher matcher(nnratio, checkOri != 0);
+  const int n = matcher.SearchByBoW(a.kf, b.kf, matches);
+  for (int i = 0; i < n1; i++) matches12[i] = b.index_of(matches[i]);
+  return n;
+}
+
+// ORBmatcher(0.6, checkOri).SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo), ORBmatcher.cc:884.
+// Keyframe 1 sits at the identity pose, keyframe 2 at Tcw2 (the epipole :898-908 follows from the two poses).
+int orbref_search_for_triangulation(const void* kps1, int n1, const unsigned char* desc1, const int* node1, const unsigned char* hasMp1,
+                                    const float* ur1, const void* kps2, int n2, const unsigned char* desc2, const int* node2,
+                                    const unsigned char* hasMp2, const float* ur2, const float* Tcw2, const float* cam4, const float* F12,
+                                    int onlyStereo, int checkOri, const float* scaleFactors, const float* levelSigma2, int nlevels,
+                                    int* matches12) {
+  ORB_SLAM2::Map map;
+  Side a, b;
+  a.build(kps1, n1, desc1, node1, hasMp1, ur1, nullptr, cam4, scaleFactors, levelSigma2, nlevels, &map, true);
+  b.build(kps2, n2, desc2, node2, hasMp2, ur2, Tcw2, cam4, scaleFactors, levelSigma2, nlevels, &map, true);
+  cv::Mat F(3, 3, CV_32F);
+  memcpy(F.data, F12, 9 * sizeof(float));
+  std::vector<std::pair<size_t, size_t>> pairs;
+  ORB_SLAM2::ORBmatcher matcher(0.6f, checkOri != 0);
+  const int n = matcher.SearchForTriangulation(a.kf, b.kf, F, pairs, onlyStereo != 0);
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  for (const auto& p : pairs) matches12[p.first] = (int)p.second;
+  return n;
+}
+
+}  // extern "C"
+
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:365) on live objects: map point p is observed by keyframes
+// 0 .. n_p-1 at feature index p, keyframe k holding observation k of every map point. mObservations is a
+// std::map keyed by KeyFrame* (visited in address order), so keyframe k is the k-th lowest address.
+// bestDesc[p] = the 32 bytes mDescriptor holds afterwards.
+extern "C" void orbref_distinctive_descriptors(const unsigned char* desc, const int* offsets, int nPoints, unsigned char* bestDesc) {
+  ORB_SLAM2::Map map;
+  int maxObs = 0;
+  for (int p = 0; p < nPoints; p++) maxObs = std::max(maxObs, offsets[p + 1] - offsets[p]);
+  std::vector<Side*> sides(maxObs);
+  std::vector<cv::KeyPoint> kps(nPoints);
+  std::vector<int> node(nPoints, -1);
+  const float sf[1] = {1.f};
+  for (int k = 0; k < maxObs; k++) {
+    std::vector<unsigned char> d((size_t)nPoints * 32, 0);
+    for (int p = 0; p < nPoints; p++)
+      if (k < offsets[p + 1] - offsets[p]) memcpy(&d[(size_t)p * 32], desc + (size_t)(offsets[p] + k) * 32, 32);
+    sides[k] = new Side();
+    sides[k]->build(kps.data(), nPoints, d.data(), node.data(), nullptr, nullptr, nullptr, kIdentityCam, sf, sf, 1, &map, true);
+  }
+  std::vector<ORB_SLAM2::KeyFrame*> kfs(maxObs);
+  for (int k = 0; k < maxObs; k++) kfs[k] = sides[k]->kf;
+  std::vector<ORB_SLAM2::KeyFrame*> byAddress = kfs;
+  std::sort(byAddress.begin(), byAddress.end());
+  // observation k must live in the k-th lowest keyframe: permute the descriptor rows accordingly
+  for (int k = 0; k < maxObs; k++) {
+    ORB_SLAM2::KeyFrame* target = byAddress[k];
+    for (int p = 0; p < nPoints; p++)
+      if (k < offsets[p + 1] - offsets[p]) memcpy(target->mDescriptors.data + (size_t)p * target->mDescriptors.step, desc + (size_t)(offsets[p] + k) * 32, 32);
+  }
+  cv::Mat pos = (cv::Mat_<float>(3, 1) << 0.f, 0.f, 1.f);
+  for (int p = 0; p < nPoints; p++) {
+    ORB_SLAM2::MapPoint mp(pos, byAddress.empty() ? nullptr : byAddress[0], &map);
+    const int n = offsets[p + 1] - offsets[p];
+    for (int k = 0; k < n; k++) mp.AddObservation(byAddress[k], (size_t)p);
+    mp.ComputeDistinctiveDescriptors();
+    cv::Mat d = mp.GetDescriptor();
+    if (!d.empty()) memcpy(bestDesc + (size_t)p * 32, d.data, 32);
+    else memset(bestDesc + (size_t)p * 32, 0, 32);
+  }
+  for (Side* s_ : sides) delete s_;
+}
+

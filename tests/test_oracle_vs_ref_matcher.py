@@ -141,3 +141,129 @@ def test_compute_stereo_matches(oracle, reference, w, h, nfeat, disp, seed):
     assert np.array_equal(ur.view(np.uint32), rur.view(np.uint32))     # mvuRight, bit-exact
     assert np.array_equal(dp.view(np.uint32), rdp.view(np.uint32))     # mvDepth, bit-exact
     assert n == rn > len(kl) // 3
+
+
+# ---- the projection searches of Tracking, on live ORB_SLAM2::MapPoint objects (src/MapPoint.cc, src/Map.cc) ----
+from orb_slam2_detailed_comments_b200.synth import tracking_scene  # noqa: E402
+from test_oracle_search import SF, local_map_points, local_map_queries  # noqa: E402
+
+
+def _cam9(sc):
+    return np.concatenate([sc["cam4"], np.zeros(5, np.float32)])
+
+
+@pytest.mark.parametrize("seed,direction,th,n_cur,n_last", [(1, 0, 15.0, 600, 500), (2, 1, 15.0, 600, 500), (3, 2, 7.0, 600, 500),
+                                                            (4, 0, 30.0, 600, 500), (5, 0, 15.0, 2000, 2000)])
+def test_search_by_projection_last_frame(oracle, reference, seed, direction, th, n_cur, n_last):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (:1710) incl. its projection (:1734-1775)."""
+    sc = tracking_scene(n_cur, n_last, seed, frac_unobserved=0.2 if seed == 4 else 0.05)
+    q = oracle.project_last_frame(sc["Xw"], sc["mp_flags"], sc["last"], sc["Tcw"], sc["cam4"], sc["bounds"], sc["mbf"], th, SF, direction)
+    nm, mk, mq = oracle.search_by_projection(sc["cur"], sc["cur_desc"], sc["uright"], sc["bounds"], sc["occupied0"], q, sc["mp_desc"],
+                                             oracle.SEARCH_BEST, 100, 0.0, True)
+    F = reference.ReferenceFrame(sc["cur"], sc["cur_desc"], _cam9(sc), 1241, 376)
+    rn, rmk = reference.search_last_frame(F, sc["uright"], sc["occupied0"], sc["last"], sc["Xw"], sc["mp_flags"], sc["mp_desc"], sc["Tcw"],
+                                          sc["cam4"], sc["mbf"], sc["mb"], th, direction, SF)
+    assert rn == nm > 50
+    assert np.array_equal(rmk, mk)
+
+
+@pytest.mark.parametrize("seed,th", [(11, 1.0), (12, 3.0), (13, 5.0)])
+def test_search_by_projection_local_map(oracle, reference, seed, th):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (:72), as Tracking::SearchLocalPoints calls it (nnratio 0.8)."""
+    sc = tracking_scene(600, 700, seed, frac_mapped=0.9)
+    q0 = oracle.project_last_frame(sc["Xw"], sc["mp_flags"] | 1, sc["last"], sc["Tcw"], sc["cam4"], sc["bounds"], sc["mbf"], 1.0, SF, 0)
+    mps = local_map_points(sc, q0, seed)
+    q = local_map_queries(oracle, mps, th)
+    nm, mk, _ = oracle.search_by_projection(sc["cur"], sc["cur_desc"], sc["uright"], sc["bounds"], sc["occupied0"], q, sc["mp_desc"],
+                                            oracle.SEARCH_RATIO_LEVEL, 100, 0.8, False)
+    F = reference.ReferenceFrame(sc["cur"], sc["cur_desc"], _cam9(sc), 1241, 376)
+    rn, rmk = reference.search_local_map(F, sc["uright"], sc["occupied0"], mps, th, 0.8, sc["cam4"], sc["mbf"], sc["mb"], SF)
+    assert rn == nm > 30
+    assert np.array_equal(rmk, mk)
+
+
+# ---- the bag-of-words guided searches, on live ORB_SLAM2::KeyFrame objects (src/KeyFrame.cc) ----
+def _nodes(sc, seed, n1, n2, nodes):
+    rng = np.random.RandomState(seed)
+    node2 = rng.randint(0, nodes, n2).astype(np.int32)
+    node1 = np.where(rng.rand(n1) < 0.85, node2[sc["src"]], rng.randint(0, nodes, n1)).astype(np.int32)
+    node1[rng.rand(n1) < 0.02] = -1; node2[rng.rand(n2) < 0.02] = -1
+    return node1, node2
+
+
+@pytest.mark.parametrize("seed,nodes,ori,n2,n1", [(21, 40, True, 500, 450), (22, 8, True, 500, 450), (23, 200, False, 500, 450),
+                                                  (24, 60, True, 2000, 1800)])
+def test_search_by_bow_keyframe_to_frame(oracle, reference, seed, nodes, ori, n2, n1):
+    """ORBmatcher(0.7, true).SearchByBoW(pKF, F, vpMapPointMatches) (:247), as TrackReferenceKeyFrame calls it."""
+    sc = tracking_scene(n2, n1, seed, flip_bits=40)
+    node1, node2 = _nodes(sc, seed, n1, n2, nodes)
+    usable = sc["mp_flags"] & 1
+    nm, mk, mq = oracle.search_by_bow(sc["last"], sc["mp_desc"], node1, usable, sc["cur"], sc["cur_desc"], node2, 50, 0.7, ori)
+    rn, rmk = reference.search_by_bow_frame(sc["last"], sc["mp_desc"], node1, usable, sc["cur"], sc["cur_desc"], node2, 0.7, ori, SF)
+    assert rn == nm > 20
+    assert np.array_equal(rmk, mk)
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_search_by_bow_keyframe_pair(oracle, reference, seed):
+    """ORBmatcher(0.8, true).SearchByBoW(pKF1, pKF2, vpMatches12) (:729), as LoopClosing calls it."""
+    sc = tracking_scene(500, 450, seed, flip_bits=60)
+    rng = np.random.RandomState(seed)
+    node2 = rng.randint(0, 30, 500).astype(np.int32)
+    node1 = np.where(rng.rand(450) < 0.85, node2[sc["src"]], rng.randint(0, 30, 450)).astype(np.int32)
+    usable1 = sc["mp_flags"] & 1
+    usable2 = (rng.rand(500) < 0.7).astype(np.uint8)
+    nm, mk, mq = oracle.search_by_bow(sc["last"], sc["mp_desc"], node1, usable1, sc["cur"], sc["cur_desc"], node2, 49, 0.8, True,
+                                      unusable2=1 - usable2)
+    rn, rm12 = reference.search_by_bow_keyframes(sc["last"], sc["mp_desc"], node1, usable1, sc["cur"], sc["cur_desc"], node2, usable2,
+                                                 0.8, True, SF)
+    assert rn == nm > 20
+    assert np.array_equal(rm12, mq)
+
+
+@pytest.mark.parametrize("seed,only_stereo,mono", [(41, 0, False), (42, 1, False), (43, 0, True), (44, 0, False)])
+def test_search_for_triangulation(oracle, reference, seed, only_stereo, mono):
+    """ORBmatcher(0.6, false/true).SearchForTriangulation (:884) incl. CheckDistEpipolarLine (:205) and the epipole (:898)."""
+    from orb_slam2_detailed_comments_b200.synth import triangulation_pair
+    sc = tracking_scene(500, 450, seed, flip_bits=50, noise_px=1.0)
+    tp = triangulation_pair(sc, seed)
+    rng = np.random.RandomState(seed)
+    node2 = rng.randint(0, 25, 500).astype(np.int32)
+    node1 = np.where(rng.rand(450) < 0.85, node2[sc["src"]], rng.randint(0, 25, 450)).astype(np.int32)
+    ur1 = None if mono else tp["ur1"]; ur2 = None if mono else sc["uright"]
+    sigma2 = (SF * SF).astype(np.float32)
+    # the epipole exactly as :898-908 computes it for keyframe 1 at the identity: C2 = t2w, float arithmetic
+    f32 = np.float32
+    t = sc["Tcw"][:3, 3].astype(f32); fx, fy, cx, cy = [f32(v) for v in sc["cam4"]]
+    invz = f32(1.0) / t[2]
+    ex = f32(f32(f32(fx * t[0]) * invz) + cx); ey = f32(f32(f32(fy * t[1]) * invz) + cy)
+    pair = np.zeros(1, oracle.TRI_PAIR_DTYPE)
+    pair["F12"][0] = tp["F12"]; pair["ex"], pair["ey"], pair["only_stereo"] = ex, ey, only_stereo
+    nm, m12 = oracle.search_for_triangulation(tp["kps1"], sc["mp_desc"], node1, tp["has_mp1"], ur1, sc["cur"], sc["cur_desc"], node2,
+                                              tp["has_mp2"], ur2, pair, SF, sigma2, True)
+    rn, rm12 = reference.search_for_triangulation(tp["kps1"], sc["mp_desc"], node1, tp["has_mp1"], ur1, sc["cur"], sc["cur_desc"], node2,
+                                                  tp["has_mp2"], ur2, sc["Tcw"], sc["cam4"], tp["F12"], only_stereo, True, SF, sigma2)
+    assert rn == nm > (5 if only_stereo else 15)
+    assert np.array_equal(rm12, m12)
+
+
+def test_compute_distinctive_descriptors(oracle, reference):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:365) on live MapPoint / KeyFrame objects: the descriptor the
+    reference keeps is the one the oracle selects (ties between equal medians included)."""
+    rng = np.random.RandomState(9)
+    counts = [1, 2, 3, 4, 7, 16, 31, 32, 33, 64, 100, 5, 2, 9]
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    desc = rng.randint(0, 256, (offsets[-1], 32)).astype(np.uint8)
+    for p, c in enumerate(counts):
+        if c > 2:   # clustered observations with duplicates: ties in the medians
+            base = desc[offsets[p]].copy()
+            for i in range(c):
+                d = base.copy()
+                bits = rng.randint(0, 256, rng.randint(0, 40))
+                np.bitwise_xor.at(d, bits >> 3, (1 << (bits & 7)).astype(np.uint8))
+                desc[offsets[p] + i] = d
+            desc[offsets[p] + c - 1] = desc[offsets[p]]
+    best = oracle.distinctive_descriptors(desc, offsets)
+    kept = reference.distinctive_descriptors(desc, offsets)
+    for p in range(len(counts)):
+        assert np.array_equal(kept[p], desc[offsets[p] + best[p]]), p
