@@ -309,28 +309,29 @@ __device__ __forceinline__ void fast_load_diffs(const unsigned* p, int tp, FastD
   D.d[12] = c - p[-3];   D.d[13] = c - rp1[-3]; D.d[14] = c - rp2[-2];  D.d[15] = c - rp3[-1];
 }
 
+// Prefilter tests work on the raw pixel pairs, without forming differences. With d_k = c - p_k:
+//   min over pairs of max(d_k, d_k+8) = c - A,  A = max over pairs of min(p_k, p_k+8)
+//   max over pairs of min(d_k, d_k+8) = c - B,  B = min over pairs of max(p_k, p_k+8)
+// and a corner at threshold th needs c - A > th (all of some 9-arc darker ... every arc holds one pixel
+// of each antipodal pair) or B - c > th. Both comparisons are made per 16-bit half with a 0x200 bias so
+// that no borrow crosses the halves: bit 9 of (c + K - A) is set iff A < c - th, K = 0x200 - (th + 1).
 // Cheapest necessary condition: the two antipodal pairs on the axes (4 loads).
-__device__ __forceinline__ unsigned fast_bound2(const unsigned* p, int tp) {
-  const unsigned c = p[0] + 0x00FF00FFu;
-  const unsigned d0 = c - p[3 * tp], d8 = c - p[-3 * tp];
-  const unsigned d4 = c - p[3], d12 = c - p[-3];
-  const unsigned minhi = __vmins2(__vmaxs2(d0, d8), __vmaxs2(d4, d12));
-  const unsigned maxlo = __vmaxs2(__vmins2(d0, d8), __vmins2(d4, d12));
-  return __vmaxs2(minhi, 0x01FE01FEu - maxlo);
+__device__ __forceinline__ unsigned fast_bound2(const unsigned* p, int tp, unsigned K) {
+  const unsigned c = p[0];
+  const unsigned p0 = p[3 * tp], p8 = p[-3 * tp], p4 = p[3], p12 = p[-3];
+  const unsigned A = __vmaxs2(__vmins2(p0, p8), __vmins2(p4, p12));
+  const unsigned B = __vmins2(__vmaxs2(p0, p8), __vmaxs2(p4, p12));
+  return ((c + K - A) | (B + K - c)) & 0x02000200u;
 }
 
-// Cheap necessary condition for a corner at threshold t, on 8 of the 16 circle pixels: every
-// 9-arc holds one pixel of each antipodal pair (k, k+8); here the 4 pairs of the even positions.
-// Returns an upper bound of S + 256 in each half.
-__device__ __forceinline__ unsigned fast_bound4(const unsigned* p, int tp) {
-  const unsigned c = p[0] + 0x00FF00FFu;
-  const unsigned d0 = c - p[3 * tp], d8 = c - p[-3 * tp];
-  const unsigned d4 = c - p[3], d12 = c - p[-3];
-  const unsigned d2 = c - p[2 * tp + 2], d10 = c - p[-2 * tp - 2];
-  const unsigned d6 = c - p[-2 * tp + 2], d14 = c - p[2 * tp - 2];
-  const unsigned minhi = __vmins2(__vimin3_s16x2(__vmaxs2(d0, d8), __vmaxs2(d4, d12), __vmaxs2(d2, d10)), __vmaxs2(d6, d14));
-  const unsigned maxlo = __vmaxs2(__vimax3_s16x2(__vmins2(d0, d8), __vmins2(d4, d12), __vmins2(d2, d10)), __vmins2(d6, d14));
-  return __vmaxs2(minhi, 0x01FE01FEu - maxlo);
+// The same test on 8 of the 16 circle pixels: the 4 pairs of the even positions.
+__device__ __forceinline__ unsigned fast_bound4(const unsigned* p, int tp, unsigned K) {
+  const unsigned c = p[0];
+  const unsigned p0 = p[3 * tp], p8 = p[-3 * tp], p4 = p[3], p12 = p[-3];
+  const unsigned p2 = p[2 * tp + 2], p10 = p[-2 * tp - 2], p6 = p[-2 * tp + 2], p14 = p[2 * tp - 2];
+  const unsigned A = __vmaxs2(__vimax3_s16x2(__vmins2(p0, p8), __vmins2(p4, p12), __vmins2(p2, p10)), __vmins2(p6, p14));
+  const unsigned B = __vmins2(__vimin3_s16x2(__vmaxs2(p0, p8), __vmaxs2(p4, p12), __vmaxs2(p2, p10)), __vmaxs2(p6, p14));
+  return ((c + K - A) | (B + K - c)) & 0x02000200u;
 }
 
 // Exact S + 256 in each half: sliding 9-window min / max over the circular sequence, two
@@ -535,8 +536,8 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
     int th = g.iniTh, nh = 0;
 #pragma unroll 1
     for (;;) {
-      // bit 15 of a half is set iff its bound exceeds th + 255, i.e. a corner at th is possible
-      const unsigned K = 0x7FFF7FFFu - (unsigned)(th + 255) * 0x00010001u;
+      // bit 9 of a half of the prefilter word is set iff a corner at th is possible there (see fast_bound2)
+      const unsigned K = 0x02000200u - (unsigned)(th + 1) * 0x00010001u;
       // ---- prefilter, stage 0 (2 pairs, every pixel pair): lanes cover one row (S > 16) or two
       // rows (S <= 16) per step; stage 1 (4 pairs) runs on the compacted survivors, in place
       int nq = 0;
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
         for (int r0 = 0; r0 < ch; r0 += rstep) {
           const int r = r0 + rsub;
           bool pass = false;
-          if (x < S && r < ch) pass = ((fast_bound2(tile + (r + 3) * tp + (x + 3), tp) + K) & 0x80008000u) != 0u;
+          if (x < S && r < ch) pass = fast_bound2(tile + (r + 3) * tp + (x + 3), tp, K) != 0u;
           const unsigned m = __ballot_sync(0xffffffffu, pass);
           if (pass) queue[nq + __popc(m & ltmask)] = (unsigned short)((r << 6) | x);
           nq += __popc(m);
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
           int i = 0;
           if (e < nq) {
             i = queue[e];
-            pass = ((fast_bound4(tile + ((i >> 6) + 3) * tp + ((i & 63) + 3), tp) + K) & 0x80008000u) != 0u;
+            pass = fast_bound4(tile + ((i >> 6) + 3) * tp + ((i & 63) + 3), tp, K) != 0u;
           }
           const unsigned m = __ballot_sync(0xffffffffu, pass);   // every lane has read its entry by now
           __syncwarp();                                          // (memory ordering of the in-place compaction, for racecheck)
