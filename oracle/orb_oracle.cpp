@@ -24,7 +24,7 @@
 // rule used here and by the CUDA path: addresses grow with creation order, i.e. among
 // equal sizes the LATER-created node is expanded first.
 //
-// Build: g++ -O3 -march=native -ffp-contract=off -shared -fPIC (see oracle/Makefile).
+// Build: g++ -O3 -march=x86-64-v3 -ffp-contract=off -shared -fPIC (see oracle/Makefile).
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
