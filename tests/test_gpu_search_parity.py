@@ -228,3 +228,37 @@ def test_search_for_triangulation(oracle, seed, only_stereo, mono):
         assert np.array_equal(m12[b, :m], r12) and np.all(m12[b, m:] == -1)
         total += rn
     assert total > (60 if only_stereo else 200), total
+
+
+@pytest.mark.parametrize("seed,th,direction", [(110, 15.0, 0), (210, 7.0, 1)])
+def test_last_frame_search_against_the_reference_itself(reference, seed, th, direction):
+    """The tracking matcher on the GPU (projection + SearchByProjection(CurrentFrame, LastFrame)) against the reference's own
+    ORBmatcher.cc running on live ORB_SLAM2::Frame / MapPoint objects (oracle/_ref/liborbref.so, compiled unmodified):
+    CurrentFrame.mvpMapPoints identical, frame by frame of a ragged batch."""
+    import torch
+    from orb_slam2_detailed_comments_b200 import search
+    sc = scenes_ragged(seed)
+    bt = Batch(sc, 2100, 2200)
+    B = len(sc)
+    d_q = torch.zeros((B, bt.qcap, 32), dtype=torch.uint8, device="cuda")
+    d_dir = torch.full((B,), direction, dtype=torch.int32, device="cuda")
+    search.ProjectLastFrame(bt.d_Xw, bt.d_fl, bt.d_last, bt.d_qcounts, bt.d_T, d_dir, sc[0]["cam4"], bt.bounds, sc[0]["mbf"], th, SF, d_q)
+    search.SearchByProjection(bt.frames, d_q, bt.d_mpd, bt.d_qcounts, search.ORB_SEARCH_BEST, search.TH_HIGH, 0.9, True, bt.d_scratch,
+                              bt.d_mk, bt.d_mq, bt.d_nm)
+    torch.cuda.synchronize()
+    mk, nm = bt.d_mk.cpu().numpy(), bt.d_nm.cpu().numpy()
+    total = 0
+    for b, s in enumerate(sc):
+        n = bt.counts[b]
+        if n == 0:
+            assert nm[b] == 0
+            continue
+        cam9 = np.concatenate([s["cam4"], np.zeros(5, np.float32)])
+        F = reference.ReferenceFrame(s["cur"], s["cur_desc"], cam9, 1241, 376)
+        rn, rmk = reference.search_last_frame(F, s["uright"], s["occupied0"], s["last"], s["Xw"], s["mp_flags"], s["mp_desc"], s["Tcw"],
+                                              s["cam4"], s["mbf"], s["mb"], th, direction, SF)
+        assert nm[b] == rn, "nmatches differ in frame %d: %d vs %d" % (b, nm[b], rn)
+        assert np.array_equal(mk[b, :n], rmk)
+        total += rn
+    print("seed", seed, "matches", total)
+    assert total > 1500
