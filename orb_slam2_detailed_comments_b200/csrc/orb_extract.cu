@@ -494,30 +494,31 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
     const int sp = cw + 2;                  // score pitch (1-px zero apron)
     __pipeline_wait_prior(0);
     __syncwarp();
-    // raw bytes -> pair-interleaved tile: word (r, j) = (T[r][j], T[r][j+S]); pixels j+S beyond the tile are zero.
-    // A lane converts 4 consecutive words of a row (9 lanes per row, 3 rows per step): the bytes T[r][4q..4q+3] and
-    // T[r][4q+S..4q+S+3] are each two aligned word loads and a funnel shift, then one PRMT + mask per tile word.
+    // raw bytes -> pair-interleaved tile: word (r, j) = (T[r][j], T[r][j+S])
     {
-      const int rp = lay.rawPitchWords;
-      const int rsub = lane / 9, q4 = 4 * (lane - 9 * rsub);
-      if (rsub < 3 && q4 < tp) {
-        const int aLo = c.ox + q4, aHi = aLo + S;
-        const unsigned shLo = (unsigned)(aLo & 3) * 8, shHi = (unsigned)(aHi & 3) * 8;
-        const int jmax = cw + 6 - S;
-        unsigned msk[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) msk[k] = q4 + k < jmax ? 0x00FF00FFu : 0x000000FFu;
-        const int nw = min(4, tp - q4);
-        const unsigned* pl = raw + rsub * rp + (aLo >> 2);
-        const unsigned* ph = raw + rsub * rp + (aHi >> 2);
-        unsigned* t = tile + rsub * tp + q4;
-        for (int r = rsub; r < ch + 6; r += 3) {
-          const unsigned lo4 = __funnelshift_r(pl[0], pl[1], shLo), hi4 = __funnelshift_r(ph[0], ph[1], shHi);
-          t[0] = __byte_perm(lo4, hi4, 0x0400) & msk[0];
-          if (nw > 1) t[1] = __byte_perm(lo4, hi4, 0x0501) & msk[1];
-          if (nw > 2) t[2] = __byte_perm(lo4, hi4, 0x0602) & msk[2];
-          if (nw > 3) t[3] = __byte_perm(lo4, hi4, 0x0703) & msk[3];
-          pl += 3 * rp; ph += 3 * rp; t += 3 * tp;
+      const u8* rb = reinterpret_cast<const u8*>(raw) + c.ox;
+      const int rp = lay.rawPitchWords * 4;
+      const int jmax = cw + 6 - S;   // pixels j+S beyond the tile are zero
+      if (lane < tp) {               // tp = S+6 <= 36: one row per step, a second sweep for wide cells
+        const u8* q = rb + lane;
+        unsigned* t = tile + lane;
+        const bool hasHi = lane < jmax;
+#pragma unroll 4
+        for (int r = 0; r < ch + 6; r++) {
+          *t = (unsigned)q[0] | ((hasHi ? (unsigned)q[S] : 0u) << 16);
+          q += rp;
+          t += tp;
+        }
+      }
+      if (tp > 32 && lane + 32 < tp) {
+        const int j = lane + 32;
+        const u8* q = rb + j;
+        unsigned* t = tile + j;
+        const bool hasHi = j < jmax;
+        for (int r = 0; r < ch + 6; r++) {
+          *t = (unsigned)q[0] | ((hasHi ? (unsigned)q[S] : 0u) << 16);
+          q += rp;
+          t += tp;
         }
       }
       for (int i = lane; i < (sp * (ch + 2) + 3) / 4; i += 32) reinterpret_cast<unsigned*>(sc)[i] = 0u;
