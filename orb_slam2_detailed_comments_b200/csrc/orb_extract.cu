@@ -1732,6 +1732,12 @@ struct orb_extractor {
   bool descTma = false;          // maps are valid for the current workspace
   cudaStream_t laneStream[2] = {nullptr, nullptr};
   cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
+  // k_blur7 needs only the pyramid: with blurFork != 0 it runs on a side stream of the lane, beside k_quadtree
+  // (blurFork = 2, the latency-bound kernel of the chain) or beside k_fast_cells + k_quadtree (blurFork = 1), and
+  // k_describe waits for both (ORB_B200_BLUR_FORK; off while the per-stage timing of the bench is on)
+  int blurFork = 0;
+  cudaStream_t blurStream[2] = {nullptr, nullptr};
+  cudaEvent_t evBlurGo[2] = {nullptr, nullptr}, evBlurDone[2] = {nullptr, nullptr};
   // staging for the host entry points: two sets, so that the H2D copy of chunk i+1 and the D2H
   // copy of chunk i-1 overlap the kernels of chunk i (copy streams + events)
   int fastTailRun = kFastTailRun, fastTailMul = 1;
@@ -2072,6 +2078,12 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     k_resize_border<<<grid, dim3(32, 8), 0, s>>>(g, l, W.pyr, e->pyrStride, e->d_taps);
     launches++;
   }
+  const int fork = e->profile ? 0 : e->blurFork;
+  cudaStream_t bs = fork ? e->blurStream[lane] : s;
+  if (fork == 1) {
+    ORB_CUDA(cudaEventRecord(e->evBlurGo[lane], s));
+    ORB_CUDA(cudaStreamWaitEvent(bs, e->evBlurGo[lane], 0));
+  }
   ORB_CUDA(cudaMemsetAsync(W.candCount, 0, (size_t)B * nl * sizeof(int), s));
   ORB_CUDA(cudaMemsetAsync(W.work, 0, sizeof(int), s));
   if ((st = stage_mark(e, s))) return st;
@@ -2083,13 +2095,21 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   }
   launches++;
   if ((st = stage_mark(e, s))) return st;
+  if (fork == 2) {
+    ORB_CUDA(cudaEventRecord(e->evBlurGo[lane], s));
+    ORB_CUDA(cudaStreamWaitEvent(bs, e->evBlurGo[lane], 0));
+  }
   k_quadtree<<<dim3(nl, B), kQtThreads, e->qtSmem, s>>>(g, W.cand, W.candCount, W.keyNode, W.kept,
                                                        W.keptCount, e->candTotal, e->keptTotal, e->nodeCap,
                                                        e->d_overflow);
   launches++;
   if ((st = stage_mark(e, s))) return st;
-  k_blur7<<<dim3(g.totalBlurTiles, B), 256, 0, s>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride, e->blurMaps[lane],
-                                                    e->blurTma ? 1 : 0);
+  k_blur7<<<dim3(g.totalBlurTiles, B), 256, 0, bs>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride, e->blurMaps[lane],
+                                                     e->blurTma ? 1 : 0);
+  if (fork) {
+    ORB_CUDA(cudaEventRecord(e->evBlurDone[lane], bs));
+    ORB_CUDA(cudaStreamWaitEvent(s, e->evBlurDone[lane], 0));
+  }
   launches++;
   if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);
@@ -2220,12 +2240,18 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
   e->maxBatch = std::max(1, max_batch);
   build_tables(e);
   if (const char* ev = getenv("ORB_B200_LANES")) e->lanes = atoi(ev) >= 2 ? 2 : 1;
+  if (const char* ev = getenv("ORB_B200_BLUR_FORK")) e->blurFork = std::max(0, std::min(2, atoi(ev)));
   cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   for (int l = 0; l < 2 && err == cudaSuccess; l++) {
     err = cudaStreamCreateWithFlags(&e->laneStream[l], cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evJoin[l], cudaEventDisableTiming);
   }
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
+  for (int l = 0; l < 2 && err == cudaSuccess; l++) {
+    err = cudaStreamCreateWithFlags(&e->blurStream[l], cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evBlurGo[l], cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evBlurDone[l], cudaEventDisableTiming);
+  }
   if (err == cudaSuccess) err = cudaMalloc(&e->d_pattern, sizeof ORB_BIT_PATTERN_31);
   if (err == cudaSuccess) err = cudaMemcpy(e->d_pattern, ORB_BIT_PATTERN_31, sizeof ORB_BIT_PATTERN_31, cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_overflow, sizeof(int));
@@ -2262,6 +2288,11 @@ int orb_destroy(orb_extractor* e) {
     if (e->evJoin[l]) cudaEventDestroy(e->evJoin[l]);
   }
   if (e->evFork) cudaEventDestroy(e->evFork);
+  for (int l = 0; l < 2; l++) {
+    if (e->blurStream[l]) cudaStreamDestroy(e->blurStream[l]);
+    if (e->evBlurGo[l]) cudaEventDestroy(e->evBlurGo[l]);
+    if (e->evBlurDone[l]) cudaEventDestroy(e->evBlurDone[l]);
+  }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return ORB_OK;
