@@ -542,18 +542,39 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
       // rows (S <= 16) per step; stage 1 (4 pairs) runs on the compacted survivors, in place
       int nq = 0;
       {
+        // A lane walks DOWN its column with the 7 rows of the vertical arm in registers (sliding window): per pixel pair
+        // one new row word and the two horizontal neighbours are loaded (3 shared-memory loads instead of 5). Narrow
+        // cells (S <= 16) put the upper and the lower half of the rows on the two half-warps. Every lane evaluates a
+        // clamped position in every step and the validity only masks the result (no divergent guard); a lane of the
+        // lower half may read one row past the tile in the last step (the hit buffer follows; the value is masked).
         const int two = S <= 16;
         const int x = two ? (lane & 15) : lane;
-        const int rsub = two ? (lane >> 4) : 0, rstep = two ? 2 : 1;
-#pragma unroll 2
-        for (int r0 = 0; r0 < ch; r0 += rstep) {
-          const int r = r0 + rsub;
-          bool pass = false;
-          if (x < S && r < ch) pass = fast_bound2(tile + (r + 3) * tp + (x + 3), tp, K) != 0u;
+        const int grp = two ? (lane >> 4) : 0;
+        const int steps = two ? (ch + 1) >> 1 : ch;          // warp-uniform
+        const int rstart = grp ? steps : 0;
+        const int nrows = grp ? ch - steps : steps;
+        const bool xok = x < S;
+        const unsigned* col = tile + rstart * tp + (min(x, S - 1) + 3);   // tile row rstart = image row rstart-3
+        unsigned w0 = col[0], w1 = col[tp], w2 = col[2 * tp], w3 = col[3 * tp], w4 = col[4 * tp], w5 = col[5 * tp];
+        const unsigned* pc = col + 3 * tp;                    // centre of step 0
+        const int tp3 = 3 * tp;
+        unsigned short* qp = queue;
+        int val = (rstart << 6) | x;
+#pragma unroll 7
+        for (int i = 0; i < steps; i++) {
+          const unsigned w6 = pc[tp3];
+          const unsigned pl = pc[-3], pr = pc[3];
+          const unsigned A = __vmaxs2(__vmins2(w6, w0), __vmins2(pr, pl));
+          const unsigned B = __vmins2(__vmaxs2(w6, w0), __vmaxs2(pr, pl));
+          const unsigned b = ((w3 + K - A) | (B + K - w3)) & 0x02000200u;
+          const bool pass = (b != 0u) & xok & (i < nrows);
           const unsigned m = __ballot_sync(0xffffffffu, pass);
-          if (pass) queue[nq + __popc(m & ltmask)] = (unsigned short)((r << 6) | x);
-          nq += __popc(m);
+          if (pass) qp[__popc(m & ltmask)] = (unsigned short)val;
+          qp += __popc(m);
+          w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+          pc += tp; val += 64;
         }
+        nq = (int)(qp - queue);
       }
       __syncwarp();
       {
