@@ -756,7 +756,9 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
   extern __shared__ __align__(16) unsigned char qsm[];
   __shared__ int s_tmp[34];
   __shared__ int s_nc, s_nexp, s_cut, s_roots;
-  const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  // grid = (frames, levels): CTAs are dispatched x-fastest, so all frames of level 0 (the most candidates, the longest
+  // CTAs) start first and the short top levels fill the tail
+  const int l = blockIdx.y, f = blockIdx.x, tid = threadIdx.x;
   const LevelGeom& L = g.lv[l];
   int n = candCount[f * g.nlevels + l];
   if (n > L.candCap) {
@@ -2124,7 +2126,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     ORB_CUDA(cudaEventRecord(e->evBlurGo[lane], s));
     ORB_CUDA(cudaStreamWaitEvent(bs, e->evBlurGo[lane], 0));
   }
-  k_quadtree<<<dim3(nl, B), kQtThreads, e->qtSmem, s>>>(g, W.cand, W.candCount, W.keyNode, W.kept,
+  k_quadtree<<<dim3(B, nl), kQtThreads, e->qtSmem, s>>>(g, W.cand, W.candCount, W.keyNode, W.kept,
                                                        W.keptCount, e->candTotal, e->keptTotal, e->nodeCap,
                                                        e->d_overflow);
   launches++;
