@@ -146,14 +146,16 @@ __device__ __forceinline__ unsigned resize_px_slow(const u8* r0, const u8* r1, i
 }
 
 // one 4-pixel word of bordered row (interior row index y already reflected)
-__device__ __forceinline__ unsigned resize_row_word(const LevelGeom& D, const LevelGeom& S, const u8* src,
-                                                    const int2* __restrict__ taps, int c0, int y) {
+// tightEnd: the source is a caller's image and this is its last frame - the 12-byte windows of the fast paths must not
+// run past the end of the last row (the pyramid planes have 19 px of border and slack after every row instead).
+__device__ __forceinline__ unsigned resize_row_word(const LevelGeom& D, const LevelGeom& S, const u8* src, long long spitch,
+                                                    const int2* __restrict__ taps, int c0, int y, bool tightEnd) {
   const int2 ty = __ldg(taps + D.tapY + y);
   const int sy0 = ty.x, sy1 = min(sy0 + 1, S.h - 1);
   const int cy0 = ty.y & 0xffff, cy1 = ty.y >> 16;
   const unsigned cy0s = (unsigned)cy0 << 16, cy1s = (unsigned)cy1 << 16;
-  const u8* r0 = src + (long long)sy0 * S.pitch;
-  const u8* r1 = src + (long long)sy1 * S.pitch;
+  const u8* r0 = src + (long long)sy0 * spitch;
+  const u8* r1 = src + (long long)sy1 * spitch;
   unsigned out = 0;
   bool fast = c0 >= 0 && c0 + 3 < D.w;
   int4 ta, tb;
@@ -162,6 +164,7 @@ __device__ __forceinline__ unsigned resize_row_word(const LevelGeom& D, const Le
     ta = __ldg(tp4);
     tb = __ldg(tp4 + 1);
     fast = tb.z + 1 - ta.x <= 7;  // the 4 pixels' source span fits one 8-byte window
+    if (tightEnd && sy1 == S.h - 1 && ta.x + 12 > S.w) fast = false;
   }
   if (fast) {
     const int a = ta.x;
@@ -214,8 +217,11 @@ __device__ __forceinline__ bool reflect_group(int p0, int n, int& lo, unsigned& 
 // Thread = 4 columns x 4 rows of the bordered plane. Blocks that do not straddle a reflection
 // turning point share the horizontal pass: the 4 output rows read at most 6 consecutive source
 // rows (scale <= 4/3), each filtered once; border blocks are the mirrored copy of such a block.
+// ext != nullptr: the source level is read from there (frame stride extStride, row pitch extPitch) instead of the
+// pyramid slab - level 1 can be made from the input image itself, so that it does not wait for k_level0_border.
 __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
-                                                       const int2* __restrict__ taps) {
+                                                       const int2* __restrict__ taps, const u8* __restrict__ ext,
+                                                       size_t extStride, int extPitch) {
   const LevelGeom& D = g.lv[l];
   const LevelGeom& S = g.lv[l - 1];
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -223,7 +229,9 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
   const int f = blockIdx.z;
   if (gi * 4 >= D.pitch || by0 >= D.h + 2 * kEdge) return;
   const int c0 = 4 * gi - kLeftPad;
-  const u8* src = pyr + (size_t)f * pyrStride + S.off;
+  const u8* src = ext ? ext + (size_t)f * extStride : pyr + (size_t)f * pyrStride + S.off;
+  const long long spitch = ext ? extPitch : S.pitch;
+  const bool tightEnd = ext != nullptr && f == (int)gridDim.z - 1;
   u8* dst = pyr + (size_t)f * pyrStride + D.off + (long long)(by0 - kEdge) * D.pitch + c0;
   const int nrows = min(4, D.h + 2 * kEdge - by0);
   int xlo = 0, ylo = 0;
@@ -240,6 +248,7 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
     // output row and the block must fit rows base .. base+5
     blockFast = tx[3].x + 1 - tx[0].x <= 7 && ty[1].x - ty[0].x >= 1 && ty[2].x - ty[1].x >= 1 && ty[3].x - ty[2].x >= 1 &&
                 ty[3].x - ty[0].x <= 4;
+    if (tightEnd && ty[0].x + 5 >= S.h - 1 && tx[0].x + 12 > S.w) blockFast = false;
   }
   if (blockFast) {
     // The integer ALU pipe (shifts, selects, logic, byte permutes) bounds this kernel: the choice of the two source rows
@@ -252,7 +261,7 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
     unsigned hq[6][4];   // horizontal pass of source rows base..base+5, already >> 4
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      const u8* q = src + (long long)min(base + i, S.h - 1) * S.pitch + a;
+      const u8* q = src + (long long)min(base + i, S.h - 1) * spitch + a;
       const unsigned mis = (unsigned)(reinterpret_cast<size_t>(q) & 3);
       const unsigned* p = reinterpret_cast<const unsigned*>(q - mis);
       const unsigned u0 = p[0], u1 = p[1], u2 = p[2];
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
   } else {
     for (int k = 0; k < nrows; k++) {
       const int y = reflect101(by0 + k - kEdge, D.h);
-      *reinterpret_cast<unsigned*>(dst + (long long)k * D.pitch) = resize_row_word(D, S, src, taps, c0, y);
+      *reinterpret_cast<unsigned*>(dst + (long long)k * D.pitch) = resize_row_word(D, S, src, spitch, taps, c0, y, tightEnd);
     }
   }
 }
@@ -1765,6 +1774,12 @@ struct orb_extractor {
   int blurFork = 0;
   cudaStream_t blurStream[2] = {nullptr, nullptr};
   cudaEvent_t evBlurGo[2] = {nullptr, nullptr}, evBlurDone[2] = {nullptr, nullptr};
+  // k_level0_border (a copy, HBM-bound) runs on the same side stream beside the resize chain (ALU-bound): level 1 is
+  // made from the input image itself, the pyramid's level 0 is only needed from k_fast_cells on. Measured +0.5 %
+  // device-resident and nothing end to end, so it is a switch (ORB_B200_L0_FORK=1), off by default and off while the
+  // per-stage timing of the bench is on
+  int l0Fork = 0;
+  cudaEvent_t evL0Go[2] = {nullptr, nullptr}, evL0Done[2] = {nullptr, nullptr};
   // staging for the host entry points: two sets, so that the H2D copy of chunk i+1 and the D2H
   // copy of chunk i-1 overlap the kernels of chunk i (copy streams + events)
   int fastTailRun = kFastTailRun, fastTailMul = 1;
@@ -2093,18 +2108,28 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   const int nl = g.nlevels;
   int launches = 0, st;
   if ((st = stage_mark(e, s))) return st;
+  const bool l0fork = !e->profile && e->l0Fork && nl > 1;
   {
     const LevelGeom& L = g.lv[0];
     dim3 grid((L.pitch / 16 + 31) / 32, (L.h + 2 * kEdge + 7) / 8, B);
-    k_level0_border<<<grid, dim3(32, 8), 0, s>>>(g, d_img, step, frameStride, W.pyr, e->pyrStride);
+    cudaStream_t ls = l0fork ? e->blurStream[lane] : s;
+    if (l0fork) {
+      ORB_CUDA(cudaEventRecord(e->evL0Go[lane], s));
+      ORB_CUDA(cudaStreamWaitEvent(ls, e->evL0Go[lane], 0));
+    }
+    k_level0_border<<<grid, dim3(32, 8), 0, ls>>>(g, d_img, step, frameStride, W.pyr, e->pyrStride);
+    if (l0fork) ORB_CUDA(cudaEventRecord(e->evL0Done[lane], ls));
     launches++;
   }
   for (int l = 1; l < nl; l++) {
     const LevelGeom& L = g.lv[l];
     dim3 grid((L.pitch / 4 + 31) / 32, (L.h + 2 * kEdge + 31) / 32, B);
-    k_resize_border<<<grid, dim3(32, 8), 0, s>>>(g, l, W.pyr, e->pyrStride, e->d_taps);
+    const bool fromImage = l0fork && l == 1;
+    k_resize_border<<<grid, dim3(32, 8), 0, s>>>(g, l, W.pyr, e->pyrStride, e->d_taps, fromImage ? d_img : nullptr,
+                                                 fromImage ? frameStride : 0, fromImage ? (int)step : 0);
     launches++;
   }
+  if (l0fork) ORB_CUDA(cudaStreamWaitEvent(s, e->evL0Done[lane], 0));
   const int fork = e->profile ? 0 : e->blurFork;
   cudaStream_t bs = fork ? e->blurStream[lane] : s;
   if (fork == 1) {
@@ -2268,6 +2293,7 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
   build_tables(e);
   if (const char* ev = getenv("ORB_B200_LANES")) e->lanes = atoi(ev) >= 2 ? 2 : 1;
   if (const char* ev = getenv("ORB_B200_BLUR_FORK")) e->blurFork = std::max(0, std::min(2, atoi(ev)));
+  if (const char* ev = getenv("ORB_B200_L0_FORK")) e->l0Fork = atoi(ev) != 0;
   cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   for (int l = 0; l < 2 && err == cudaSuccess; l++) {
     err = cudaStreamCreateWithFlags(&e->laneStream[l], cudaStreamNonBlocking);
@@ -2278,6 +2304,8 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
     err = cudaStreamCreateWithFlags(&e->blurStream[l], cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evBlurGo[l], cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evBlurDone[l], cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evL0Go[l], cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evL0Done[l], cudaEventDisableTiming);
   }
   if (err == cudaSuccess) err = cudaMalloc(&e->d_pattern, sizeof ORB_BIT_PATTERN_31);
   if (err == cudaSuccess) err = cudaMemcpy(e->d_pattern, ORB_BIT_PATTERN_31, sizeof ORB_BIT_PATTERN_31, cudaMemcpyHostToDevice);
@@ -2319,6 +2347,8 @@ int orb_destroy(orb_extractor* e) {
     if (e->blurStream[l]) cudaStreamDestroy(e->blurStream[l]);
     if (e->evBlurGo[l]) cudaEventDestroy(e->evBlurGo[l]);
     if (e->evBlurDone[l]) cudaEventDestroy(e->evBlurDone[l]);
+    if (e->evL0Go[l]) cudaEventDestroy(e->evL0Go[l]);
+    if (e->evL0Done[l]) cudaEventDestroy(e->evL0Done[l]);
   }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
