@@ -1789,6 +1789,11 @@ struct orb_extractor {
   cudaStream_t sIn = nullptr, sOut = nullptr;
   cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
   std::vector<u8> hostPyr;
+  // pinned staging of the single-call entry points (orb_extract / orb_extract_stereo): the image goes up from here and
+  // counts, overflow flag, keypoints, descriptors (and the stereo vectors) come back in one batch of async copies
+  // followed by ONE stream synchronisation, instead of pageable copies with a round trip each
+  u8* h_in = nullptr; size_t h_inBytes = 0;
+  u8* h_out = nullptr; size_t h_outBytes = 0;
   int lastLaunches = 0;
   int lastChunkFrames = 0;
   float* d_invScale = nullptr;          // mvInvScaleFactor on the device (stereo refinement)
@@ -2256,6 +2261,35 @@ int ensure_stage(orb_extractor* e, size_t inBytes, int frames, int cap) {
   return ORB_OK;
 }
 
+int ensure_pinned(orb_extractor* e, size_t inBytes, size_t outBytes) {
+  if (inBytes > e->h_inBytes) {
+    if (e->h_in) cudaFreeHost(e->h_in);
+    e->h_in = nullptr; e->h_inBytes = 0;
+    ORB_CUDA(cudaHostAlloc((void**)&e->h_in, inBytes, cudaHostAllocDefault));
+    e->h_inBytes = inBytes;
+  }
+  if (outBytes > e->h_outBytes) {
+    if (e->h_out) cudaFreeHost(e->h_out);
+    e->h_out = nullptr; e->h_outBytes = 0;
+    ORB_CUDA(cudaHostAlloc((void**)&e->h_out, outBytes, cudaHostAllocDefault));
+    e->h_outBytes = outBytes;
+  }
+  return ORB_OK;
+}
+
+void stage_rows(u8* dst, const u8* src, int width, int height, size_t step) {
+  if (step == (size_t)width) { memcpy(dst, src, (size_t)width * height); return; }
+  for (int y = 0; y < height; y++) memcpy(dst + (size_t)y * width, src + (size_t)y * step, (size_t)width);
+}
+
+int overflow_status(orb_extractor* e, int flag, cudaStream_t s) {
+  if (flag) {
+    cudaMemsetAsync(e->d_overflow, 0, sizeof(int), s);
+    ORB_FAIL(ORB_ERR_CAPACITY, flag & 4 ? "keypoint output capacity too small" : "internal candidate/keypoint list overflow");
+  }
+  return ORB_OK;
+}
+
 int check_overflow(orb_extractor* e, cudaStream_t s) {
   int flag = 0;
   ORB_CUDA(cudaMemcpyAsync(&flag, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -2335,6 +2369,8 @@ int orb_destroy(orb_extractor* e) {
     if (e->evDone[b]) cudaEventDestroy(e->evDone[b]);
     if (e->evOut[b]) cudaEventDestroy(e->evOut[b]);
   }
+  if (e->h_in) cudaFreeHost(e->h_in);
+  if (e->h_out) cudaFreeHost(e->h_out);
   if (e->sIn) cudaStreamDestroy(e->sIn);
   if (e->sOut) cudaStreamDestroy(e->sOut);
   for (cudaEvent_t ev : e->evPool) cudaEventDestroy(ev);
@@ -2551,22 +2587,31 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
   if (st) return st;
   cudaStream_t s = e->stream;
   e->lastLaunches = 0;
-  ORB_CUDA(cudaMemcpy2DAsync(e->d_in[0], width, image, step, width, height, cudaMemcpyHostToDevice, s));
+  const int m = std::min(capacity, e->maxKp);      // entries that can come back
+  const size_t oK = 64, oD = oK + round_up((size_t)m * sizeof(orb_keypoint), (size_t)64);
+  st = ensure_pinned(e, dFrame, oD + (size_t)m * 32);
+  if (st) return st;
+  stage_rows(e->h_in, image, width, height, step);
+  ORB_CUDA(cudaMemcpyAsync(e->d_in[0], e->h_in, dFrame, cudaMemcpyHostToDevice, s));
   st = run_chunk(e, e->d_in[0], 1, width, dFrame, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], s);
   if (st) return st;
-  int cnt = 0;
-  ORB_CUDA(cudaMemcpyAsync(&cnt, e->d_n[0], sizeof(int), cudaMemcpyDeviceToHost, s));
+  int* hc = reinterpret_cast<int*>(e->h_out);
+  ORB_CUDA(cudaMemcpyAsync(hc, e->d_n[0], sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(hc + 1, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + oK, e->d_kps[0], (size_t)m * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + oD, e->d_desc[0], (size_t)m * 32, cudaMemcpyDeviceToHost, s));
   if (pyramid) {
     e->hostPyr.resize(e->pyrStride);
     ORB_CUDA(cudaMemcpyAsync(e->hostPyr.data(), e->d_pyr, e->pyrStride, cudaMemcpyDeviceToHost, s));
   }
   ORB_CUDA(cudaStreamSynchronize(s));
-  if (cnt > 0) {
-    ORB_CUDA(cudaMemcpyAsync(keypoints, e->d_kps[0], (size_t)cnt * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
-    ORB_CUDA(cudaMemcpyAsync(descriptors, e->d_desc[0], (size_t)cnt * 32, cudaMemcpyDeviceToHost, s));
-  }
-  st = check_overflow(e, s);
+  st = overflow_status(e, hc[1], s);
   if (st) return st;
+  const int cnt = std::min(hc[0], m);
+  if (cnt > 0) {
+    memcpy(keypoints, e->h_out + oK, (size_t)cnt * sizeof(orb_keypoint));
+    memcpy(descriptors, e->h_out + oD, (size_t)cnt * 32);
+  }
   *n = cnt;
   if (pyramid)
     for (int l = 0; l < e->g.nlevels; l++) {
@@ -2638,27 +2683,41 @@ int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* rig
   }
   cudaStream_t s = e->stream;
   e->lastLaunches = 0;
-  ORB_CUDA(cudaMemcpy2DAsync(e->d_in[0], width, left, step, width, height, cudaMemcpyHostToDevice, s));
-  ORB_CUDA(cudaMemcpy2DAsync(e->d_in[0] + dFrame, width, right, step, width, height, cudaMemcpyHostToDevice, s));
+  const int m = std::min(capacity, e->maxKp);
+  const size_t szK = round_up((size_t)m * sizeof(orb_keypoint), (size_t)64), szD = (size_t)m * 32, szF = round_up((size_t)m * sizeof(float), (size_t)64);
+  const size_t oKL = 64, oKR = oKL + szK, oDL = oKR + szK, oDR = oDL + szD, oU = oDR + szD, oZ = oU + szF;
+  st = ensure_pinned(e, 2 * dFrame, oZ + szF);
+  if (st) return st;
+  stage_rows(e->h_in, left, width, height, step);
+  stage_rows(e->h_in + dFrame, right, width, height, step);
+  ORB_CUDA(cudaMemcpyAsync(e->d_in[0], e->h_in, 2 * dFrame, cudaMemcpyHostToDevice, s));
   st = run_chunk(e, e->d_in[0], 2, width, dFrame, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], s);
   if (st) return st;
   st = run_stereo(e, 2, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], mbf, mb, e->d_uRight[0], e->d_depth[0], s);
   if (st) return st;
-  int cnt[2] = {0, 0};
-  ORB_CUDA(cudaMemcpyAsync(cnt, e->d_n[0], 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  int* hc = reinterpret_cast<int*>(e->h_out);
+  ORB_CUDA(cudaMemcpyAsync(hc, e->d_n[0], 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(hc + 2, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + oKL, e->d_kps[0], (size_t)m * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + oKR, e->d_kps[0] + capacity, (size_t)m * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + oDL, e->d_desc[0], szD, cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + oDR, e->d_desc[0] + (size_t)capacity * 32, szD, cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + oU, e->d_uRight[0], (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + oZ, e->d_depth[0], (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s));
   ORB_CUDA(cudaStreamSynchronize(s));
+  st = overflow_status(e, hc[2], s);
+  if (st) return st;
+  const int cnt[2] = {std::min(hc[0], m), std::min(hc[1], m)};
   if (cnt[0] > 0) {
-    ORB_CUDA(cudaMemcpyAsync(kps_left, e->d_kps[0], (size_t)cnt[0] * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
-    ORB_CUDA(cudaMemcpyAsync(desc_left, e->d_desc[0], (size_t)cnt[0] * 32, cudaMemcpyDeviceToHost, s));
-    ORB_CUDA(cudaMemcpyAsync(uright, e->d_uRight[0], (size_t)cnt[0] * sizeof(float), cudaMemcpyDeviceToHost, s));
-    ORB_CUDA(cudaMemcpyAsync(depth, e->d_depth[0], (size_t)cnt[0] * sizeof(float), cudaMemcpyDeviceToHost, s));
+    memcpy(kps_left, e->h_out + oKL, (size_t)cnt[0] * sizeof(orb_keypoint));
+    memcpy(desc_left, e->h_out + oDL, (size_t)cnt[0] * 32);
+    memcpy(uright, e->h_out + oU, (size_t)cnt[0] * sizeof(float));
+    memcpy(depth, e->h_out + oZ, (size_t)cnt[0] * sizeof(float));
   }
   if (cnt[1] > 0) {
-    ORB_CUDA(cudaMemcpyAsync(kps_right, e->d_kps[0] + capacity, (size_t)cnt[1] * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
-    ORB_CUDA(cudaMemcpyAsync(desc_right, e->d_desc[0] + (size_t)capacity * 32, (size_t)cnt[1] * 32, cudaMemcpyDeviceToHost, s));
+    memcpy(kps_right, e->h_out + oKR, (size_t)cnt[1] * sizeof(orb_keypoint));
+    memcpy(desc_right, e->h_out + oDR, (size_t)cnt[1] * 32);
   }
-  st = check_overflow(e, s);
-  if (st) return st;
   *n_left = cnt[0];
   *n_right = cnt[1];
   return ORB_OK;
