@@ -1794,6 +1794,13 @@ struct orb_extractor {
   // followed by ONE stream synchronisation, instead of pageable copies with a round trip each
   u8* h_in = nullptr; size_t h_inBytes = 0;
   u8* h_out = nullptr; size_t h_outBytes = 0;
+  // ... and their kernel sequence (2 memsets + 14 launches, all on fixed buffers) is replayed as a CUDA graph, captured
+  // again whenever a pointer, the image size or the capacity changes (ORB_B200_GRAPH=0 launches kernel by kernel)
+  struct GraphKey { const void* p[8]; int w, h, cap, frames, flags; };
+  bool useGraph = true;
+  cudaGraphExec_t callGraph[2] = {nullptr, nullptr};   // [0] one frame, [1] stereo pair
+  GraphKey callKey[2] = {};
+  int callLaunches[2] = {0, 0};
   int lastLaunches = 0;
   int lastChunkFrames = 0;
   float* d_invScale = nullptr;          // mvInvScaleFactor on the device (stereo refinement)
@@ -2261,9 +2268,64 @@ int ensure_stage(orb_extractor* e, size_t inBytes, int frames, int cap) {
   return ORB_OK;
 }
 
+// run_chunk (+ run_stereo for a pair) of a single-call entry point through a captured graph
+int run_call(orb_extractor* e, int frames, int width, int height, size_t dFrame, int capacity, bool stereo, float mbf, float mb,
+             cudaStream_t s) {
+  auto direct = [&]() -> int {
+    int st = run_chunk(e, e->d_in[0], frames, width, dFrame, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], s);
+    if (st) return st;
+    if (stereo) st = run_stereo(e, frames, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], mbf, mb, e->d_uRight[0], e->d_depth[0], s, 0);
+    return st;
+  };
+  if (!e->useGraph || e->profile || e->blurFork || e->l0Fork) return direct();
+  const int slot = stereo ? 1 : 0;
+  const Lane W = lane_of(e, 0);
+  orb_extractor::GraphKey key = {};
+  key.p[0] = W.pyr; key.p[1] = W.blur; key.p[2] = W.cand; key.p[3] = W.kept; key.p[4] = e->d_in[0]; key.p[5] = e->d_kps[0];
+  key.p[6] = e->d_desc[0]; key.p[7] = stereo ? (const void*)e->d_uRight[0] : (const void*)e->d_n[0];
+  key.w = width; key.h = height; key.cap = capacity; key.frames = frames;
+  unsigned fb, mbb;
+  memcpy(&fb, &mbf, 4); memcpy(&mbb, &mb, 4);
+  key.flags = (e->descTma ? 1 : 0) | (e->blurTma ? 2 : 0) | (stereo ? (int)((fb * 2654435761u) ^ mbb) & ~3 : 0);
+  if (!e->callGraph[slot] || memcmp(&key, &e->callKey[slot], sizeof key) != 0) {
+    if (e->callGraph[slot]) { cudaGraphExecDestroy(e->callGraph[slot]); e->callGraph[slot] = nullptr; }
+    const int before = e->lastLaunches;
+    cudaGraph_t graph = nullptr;
+    ORB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int st = direct();
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (st || ce != cudaSuccess || !graph) {   // could not be captured: run it the plain way from now on
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      e->useGraph = false;
+      e->lastLaunches = before;
+      return direct();
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&e->callGraph[slot], graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      cudaGetLastError();
+      e->callGraph[slot] = nullptr;
+      e->useGraph = false;
+      e->lastLaunches = before;
+      return direct();
+    }
+    e->callKey[slot] = key;
+    e->callLaunches[slot] = e->lastLaunches - before;
+    e->lastLaunches = before;
+  }
+  ORB_CUDA(cudaGraphLaunch(e->callGraph[slot], s));
+  e->lastLaunches += e->callLaunches[slot];
+  e->lastChunkFrames = frames;
+  e->lastLane = 0;
+  return ORB_OK;
+}
+
 int ensure_pinned(orb_extractor* e, size_t inBytes, size_t outBytes) {
   if (inBytes > e->h_inBytes) {
-    if (e->h_in) cudaFreeHost(e->h_in);
+    for (int k = 0; k < 2; k++)
+    if (e->callGraph[k]) cudaGraphExecDestroy(e->callGraph[k]);
+  if (e->h_in) cudaFreeHost(e->h_in);
     e->h_in = nullptr; e->h_inBytes = 0;
     ORB_CUDA(cudaHostAlloc((void**)&e->h_in, inBytes, cudaHostAllocDefault));
     e->h_inBytes = inBytes;
@@ -2328,6 +2390,7 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
   if (const char* ev = getenv("ORB_B200_LANES")) e->lanes = atoi(ev) >= 2 ? 2 : 1;
   if (const char* ev = getenv("ORB_B200_BLUR_FORK")) e->blurFork = std::max(0, std::min(2, atoi(ev)));
   if (const char* ev = getenv("ORB_B200_L0_FORK")) e->l0Fork = atoi(ev) != 0;
+  if (const char* ev = getenv("ORB_B200_GRAPH")) e->useGraph = atoi(ev) != 0;
   cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   for (int l = 0; l < 2 && err == cudaSuccess; l++) {
     err = cudaStreamCreateWithFlags(&e->laneStream[l], cudaStreamNonBlocking);
@@ -2593,7 +2656,7 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
   if (st) return st;
   stage_rows(e->h_in, image, width, height, step);
   ORB_CUDA(cudaMemcpyAsync(e->d_in[0], e->h_in, dFrame, cudaMemcpyHostToDevice, s));
-  st = run_chunk(e, e->d_in[0], 1, width, dFrame, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], s);
+  st = run_call(e, 1, width, height, dFrame, capacity, false, 0.f, 0.f, s);
   if (st) return st;
   int* hc = reinterpret_cast<int*>(e->h_out);
   ORB_CUDA(cudaMemcpyAsync(hc, e->d_n[0], sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -2691,9 +2754,7 @@ int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* rig
   stage_rows(e->h_in, left, width, height, step);
   stage_rows(e->h_in + dFrame, right, width, height, step);
   ORB_CUDA(cudaMemcpyAsync(e->d_in[0], e->h_in, 2 * dFrame, cudaMemcpyHostToDevice, s));
-  st = run_chunk(e, e->d_in[0], 2, width, dFrame, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], s);
-  if (st) return st;
-  st = run_stereo(e, 2, e->d_kps[0], capacity, e->d_n[0], e->d_desc[0], mbf, mb, e->d_uRight[0], e->d_depth[0], s);
+  st = run_call(e, 2, width, height, dFrame, capacity, true, mbf, mb, s);
   if (st) return st;
   int* hc = reinterpret_cast<int*>(e->h_out);
   ORB_CUDA(cudaMemcpyAsync(hc, e->d_n[0], 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
