@@ -1530,12 +1530,18 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
                                                            const orb_keypoint* __restrict__ kps, const u8* __restrict__ desc,
                                                            const int* __restrict__ counts, int cap, float mbf, float mb,
                                                            const float* __restrict__ invScale, float* __restrict__ uRight,
-                                                           float* __restrict__ depth, int entCap) {
+                                                           float* __restrict__ depth, int entCap, int2* __restrict__ gsad,
+                                                           int* __restrict__ gcnt) {
+  // gridDim.y = G > 1 (few pairs per call: the latency case): the left keypoints of a pair are dealt to G CTAs, matches go
+  // to a global list, and the CTA that finishes last (ticket) does the median cut over all of them.
   extern __shared__ __align__(16) unsigned char ssm[];
   __shared__ int s_n;
   __shared__ int s_scan[34];
   __shared__ float s_median;
+  __shared__ int s_last;
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int G = gridDim.y, part = blockIdx.y;
+  constexpr int kW = kStereoThreads / 32;
   const int fL = 2 * pair, fR = 2 * pair + 1;
   const int N = counts[fL], Nr = counts[fR];
   float* rx = reinterpret_cast<float*>(ssm);                       // right keypoint x
@@ -1551,7 +1557,8 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
   const u8* DR = desc + (size_t)fR * cap * 32;
   float* uR = uRight + (size_t)pair * cap;
   float* dp = depth + (size_t)pair * cap;
-  for (int i = tid; i < cap; i += kStereoThreads) { uR[i] = -1.0f; dp[i] = -1.0f; }
+  for (int i = tid; i < cap; i += kStereoThreads)
+    if ((i % (kW * G)) / kW == part) { uR[i] = -1.0f; dp[i] = -1.0f; }   // every entry has one owner CTA
   for (int i = tid; i < Nr; i += kStereoThreads) {
     const orb_keypoint k = KR[i];
     const float r = __fmul_rn(2.0f, g.lv[k.octave].scale);         // :858
@@ -1584,7 +1591,7 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
   __syncthreads();
   const float maxD = __fdiv_rn(mbf, mb);   // minZ = mb, minD = 0 (:885-887)
   const int TH_HIGH = 100, thOrbDist = 75;
-  for (int iL = wid; iL < N; iL += kStereoThreads / 32) {
+  for (int iL = wid + kW * part; iL < N; iL += kW * G) {
     const orb_keypoint kl = KL[iL];
     const int levelL = kl.octave, row = (int)kl.y;
     const float uL = kl.x, minU = __fsub_rn(uL, maxD), maxU = uL;
@@ -1674,13 +1681,25 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
             }
             dp[iL] = __fdiv_rn(mbf, disparity);
             uR[iL] = bestuR;
-            sad[atomicAdd(&s_n, 1)] = make_int2(best, iL);
+            if (G == 1) sad[atomicAdd(&s_n, 1)] = make_int2(best, iL);
+            else gsad[(size_t)pair * cap + atomicAdd(&gcnt[2 * pair], 1)] = make_int2(best, iL);
           }
         }
       }
     }
   }
+  if (G > 1) __threadfence();   // this CTA's matches are visible device-wide before its ticket is drawn
   __syncthreads();
+  if (G > 1) {
+    if (tid == 0) s_last = atomicAdd(&gcnt[2 * pair + 1], 1) == G - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int ng = *reinterpret_cast<volatile int*>(&gcnt[2 * pair]);
+    for (int i = tid; i < ng; i += kStereoThreads) sad[i] = __ldcg(&gsad[(size_t)pair * cap + i]);
+    if (tid == 0) s_n = ng;
+    __syncthreads();
+  }
   const int n = s_n;
   if (n == 0) return;
   // median of the SAD values = element n/2 of the sorted list (only the value matters): two-pass
@@ -1797,6 +1816,7 @@ struct orb_extractor {
   // ... and their kernel sequence (2 memsets + 14 launches, all on fixed buffers) is replayed as a CUDA graph, captured
   // again whenever a pointer, the image size or the capacity changes (ORB_B200_GRAPH=0 launches kernel by kernel)
   struct GraphKey { const void* p[8]; int w, h, cap, frames, flags; };
+  u8* d_stereoScratch = nullptr; size_t stereoScratchBytes = 0;   // match list + counters of k_stereo's split mode
   bool useGraph = true;
   cudaGraphExec_t callGraph[2] = {nullptr, nullptr};   // [0] one frame, [1] stereo pair
   GraphKey callKey[2] = {};
@@ -2198,6 +2218,19 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
 
 // Frame::ComputeStereoMatches for the B/2 stereo pairs of the chunk that was just extracted
 // (frames 2p = left, 2p+1 = right; the chunk's pyramids are still in the workspace).
+// match list (32 pairs x cap) + counters of k_stereo's split mode; grown outside of any graph capture
+int ensure_stereo_scratch(orb_extractor* e, int cap, cudaStream_t s) {
+  const size_t need = (size_t)32 * cap * sizeof(int2) + 64 * sizeof(int);
+  if (need <= e->stereoScratchBytes) return ORB_OK;
+  ORB_CUDA(cudaStreamSynchronize(s));
+  cudaFree(e->d_stereoScratch);
+  e->d_stereoScratch = nullptr; e->stereoScratchBytes = 0;
+  if (e->callGraph[1]) { cudaGraphExecDestroy(e->callGraph[1]); e->callGraph[1] = nullptr; }
+  ORB_CUDA(cudaMalloc(&e->d_stereoScratch, need));
+  e->stereoScratchBytes = need;
+  return ORB_OK;
+}
+
 int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, const int* d_counts, const u8* d_desc, float mbf,
                float mb, float* d_uRight, float* d_depth, cudaStream_t s, int lane = 0) {
   // right keypoints (x, row band, octave), SAD list, row index (H+2 ints) and up to 12 index entries
@@ -2210,8 +2243,18 @@ int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, cons
     ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints / rows for the stereo kernel's shared memory");
   if (cap > 65535) ORB_FAIL(ORB_ERR_UNSUPPORTED, "stereo matching supports at most 65535 keypoints per frame");
   ORB_CUDA(cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_stereo<<<B / 2, kStereoThreads, smem, s>>>(e->g, lane_of(e, lane).pyr, e->pyrStride, d_kps, d_desc, d_counts, cap, mbf, mb, e->d_invScale,
-                                                d_uRight, d_depth, entCap);
+  // few pairs per call (the per-frame drop-in case): deal every pair to G CTAs
+  const int pairs = B / 2;
+  const int G = pairs <= 8 ? 16 : (pairs <= 32 ? 4 : 1);
+  if (G > 1) {
+    const int st = ensure_stereo_scratch(e, cap, s);
+    if (st) return st;
+    ORB_CUDA(cudaMemsetAsync(e->d_stereoScratch, 0, 64 * sizeof(int), s));
+  }
+  int* gcnt = reinterpret_cast<int*>(e->d_stereoScratch);
+  int2* gsad = G > 1 ? reinterpret_cast<int2*>(e->d_stereoScratch + 64 * sizeof(int)) : nullptr;
+  k_stereo<<<dim3(pairs, G), kStereoThreads, smem, s>>>(e->g, lane_of(e, lane).pyr, e->pyrStride, d_kps, d_desc, d_counts, cap, mbf, mb,
+                                                        e->d_invScale, d_uRight, d_depth, entCap, gsad, gcnt);
   ORB_CUDA(cudaGetLastError());
   e->lastLaunches++;
   return ORB_OK;
@@ -2325,6 +2368,7 @@ int ensure_pinned(orb_extractor* e, size_t inBytes, size_t outBytes) {
   if (inBytes > e->h_inBytes) {
     for (int k = 0; k < 2; k++)
     if (e->callGraph[k]) cudaGraphExecDestroy(e->callGraph[k]);
+  cudaFree(e->d_stereoScratch);
   if (e->h_in) cudaFreeHost(e->h_in);
     e->h_in = nullptr; e->h_inBytes = 0;
     ORB_CUDA(cudaHostAlloc((void**)&e->h_in, inBytes, cudaHostAllocDefault));
@@ -2750,6 +2794,8 @@ int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* rig
   const size_t szK = round_up((size_t)m * sizeof(orb_keypoint), (size_t)64), szD = (size_t)m * 32, szF = round_up((size_t)m * sizeof(float), (size_t)64);
   const size_t oKL = 64, oKR = oKL + szK, oDL = oKR + szK, oDR = oDL + szD, oU = oDR + szD, oZ = oU + szF;
   st = ensure_pinned(e, 2 * dFrame, oZ + szF);
+  if (st) return st;
+  st = ensure_stereo_scratch(e, capacity, s);
   if (st) return st;
   stage_rows(e->h_in, left, width, height, step);
   stage_rows(e->h_in + dFrame, right, width, height, step);
