@@ -1807,7 +1807,7 @@ struct orb_extractor {
   int stageFrames = 0, stageCap = 0;
   cudaStream_t sIn = nullptr, sOut = nullptr;
   cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
-  std::vector<u8> hostPyr;
+  u8* hostPyr = nullptr; size_t hostPyrBytes = 0;   // pinned copy of the last single-call pyramid (mvImagePyramid views)
   // pinned staging of the single-call entry points (orb_extract / orb_extract_stereo): the image goes up from here and
   // counts, overflow flag, keypoints, descriptors (and the stereo vectors) come back in one batch of async copies
   // followed by ONE stream synchronisation, instead of pageable copies with a round trip each
@@ -2369,6 +2369,7 @@ int ensure_pinned(orb_extractor* e, size_t inBytes, size_t outBytes) {
     for (int k = 0; k < 2; k++)
     if (e->callGraph[k]) cudaGraphExecDestroy(e->callGraph[k]);
   cudaFree(e->d_stereoScratch);
+  if (e->hostPyr) cudaFreeHost(e->hostPyr);
   if (e->h_in) cudaFreeHost(e->h_in);
     e->h_in = nullptr; e->h_inBytes = 0;
     ORB_CUDA(cudaHostAlloc((void**)&e->h_in, inBytes, cudaHostAllocDefault));
@@ -2708,8 +2709,13 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
   ORB_CUDA(cudaMemcpyAsync(e->h_out + oK, e->d_kps[0], (size_t)m * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, s));
   ORB_CUDA(cudaMemcpyAsync(e->h_out + oD, e->d_desc[0], (size_t)m * 32, cudaMemcpyDeviceToHost, s));
   if (pyramid) {
-    e->hostPyr.resize(e->pyrStride);
-    ORB_CUDA(cudaMemcpyAsync(e->hostPyr.data(), e->d_pyr, e->pyrStride, cudaMemcpyDeviceToHost, s));
+    if (e->pyrStride > e->hostPyrBytes) {
+      if (e->hostPyr) cudaFreeHost(e->hostPyr);
+      e->hostPyr = nullptr; e->hostPyrBytes = 0;
+      ORB_CUDA(cudaHostAlloc((void**)&e->hostPyr, e->pyrStride, cudaHostAllocDefault));
+      e->hostPyrBytes = e->pyrStride;
+    }
+    ORB_CUDA(cudaMemcpyAsync(e->hostPyr, e->d_pyr, e->pyrStride, cudaMemcpyDeviceToHost, s));
   }
   ORB_CUDA(cudaStreamSynchronize(s));
   st = overflow_status(e, hc[1], s);
@@ -2722,7 +2728,7 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
   *n = cnt;
   if (pyramid)
     for (int l = 0; l < e->g.nlevels; l++) {
-      pyramid[l].data = e->hostPyr.data() + e->g.lv[l].off;
+      pyramid[l].data = e->hostPyr + e->g.lv[l].off;
       pyramid[l].width = e->g.lv[l].w;
       pyramid[l].height = e->g.lv[l].h;
       pyramid[l].step = e->g.lv[l].pitch;
