@@ -297,3 +297,32 @@ def test_extract_matches_the_reference_itself(reference, name):
         assert same.mean() >= MIN_IDENTICAL_DESC
         for l in range(8):
             assert np.array_equal(gpu.stage_level(0, l), ref.level(l)), "mvImagePyramid[%d]" % l
+
+
+def test_single_call_graph_is_recaptured_when_geometry_changes(oracle):
+    """orb_extract replays its kernel sequence as a CUDA graph on fixed buffers: alternating image sizes (new workspace,
+    new staging), repeated calls (replay) and a stereo call in between must all keep matching the oracle."""
+    from orb_slam2_detailed_comments_b200 import ORBextractor
+    from orb_slam2_detailed_comments_b200.synth import synth_frame
+    from test_oracle_stereo import stereo_pair
+    gpu = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=2)
+    orc = oracle.OracleExtractor(1000, 1.2, 8, 20, 7)
+    sizes = [(640, 480), (752, 480), (640, 480), (400, 300), (752, 480), (640, 480)]
+    for it, (w, h) in enumerate(sizes):
+        for rep in range(3):                       # first call captures, the next ones replay
+            img = synth_frame(w, h, 50 + it * 3 + rep)
+            kps, desc = gpu(img)
+            okps, odesc = orc(img)
+            assert len(kps) == len(okps)
+            for f in ("x", "y", "size", "response", "octave", "angle"):
+                assert np.array_equal(kps[f], okps[f]), (it, rep, f)
+            assert np.array_equal(desc, odesc)
+        if it == 2:                                # a stereo call shares the staging buffers and the workspace
+            left, right = stereo_pair(640, 480, 9, 12)
+            eL = oracle.OracleExtractor(1000, 1.2, 8, 20, 7); eR = oracle.OracleExtractor(1000, 1.2, 8, 20, 7)
+            okl, odl = eL(left); okr, odr = eR(right)
+            our, odp, n = oracle.stereo_matches(eL, eR, okl, odl, okr, odr, 40.0, 0.1)
+            for rep in range(2):
+                kl, dl, kr, dr, ur, dp = gpu.extract_stereo(left, right, 40.0, 0.1)
+                assert np.array_equal(kl["x"], okl["x"]) and np.array_equal(kr["x"], okr["x"])
+                assert np.array_equal(ur.view(np.uint32), our.view(np.uint32)) and np.array_equal(dp.view(np.uint32), odp.view(np.uint32))
