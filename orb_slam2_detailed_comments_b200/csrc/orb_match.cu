@@ -619,9 +619,9 @@ struct orb_matcher {
   int device = 0;
   int maxPairs = 0, maxKp = 0;
   cudaStream_t stream = nullptr;
-  // staging for the host single-pair entry point
-  u8* d_desc = nullptr; float* d_xy = nullptr; float* d_ang = nullptr; int* d_oct = nullptr;
-  float* d_prev = nullptr; int* d_m12 = nullptr; int* d_best = nullptr; int* d_second = nullptr; int* d_nm = nullptr;
+  // staging for the host single-pair entry point: one device block and one pinned host block with the same packed
+  // layout [desc1|desc2|ang1|ang2|xy2|oct1|oct2|prev|m12|best|second|nm] - one upload, one download, one synchronisation
+  u8* d_stage = nullptr; u8* h_stage = nullptr; size_t stageBytes = 0;
 };
 
 extern "C" {
@@ -645,15 +645,9 @@ int orb_matcher_create(int device, int max_pairs, int max_keypoints, orb_matcher
   m->maxKp = max_keypoints;
   const size_t K = (size_t)max_keypoints;
   cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_desc, 2 * K * 32);
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_xy, 2 * K * 2 * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_ang, 2 * K * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_oct, 2 * K * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_prev, K * 2 * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_m12, K * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_best, K * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_second, K * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_nm, sizeof(int));
+  m->stageBytes = K * (2 * 32 + 2 * 4 + 8 + 2 * 4 + 8 + 3 * 4) + 16 * 16;
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_stage, m->stageBytes);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&m->h_stage, m->stageBytes, cudaHostAllocDefault);
   if (e != cudaSuccess) {
     orb_matcher_destroy(m);
     return cuda_fail(e, "orb_matcher_create", __FILE__, __LINE__);
@@ -666,8 +660,8 @@ int orb_matcher_destroy(orb_matcher* m) {
   if (!m) return ORB_OK;
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
-  cudaFree(m->d_desc); cudaFree(m->d_xy); cudaFree(m->d_ang); cudaFree(m->d_oct); cudaFree(m->d_prev);
-  cudaFree(m->d_m12); cudaFree(m->d_best); cudaFree(m->d_second); cudaFree(m->d_nm);
+  cudaFree(m->d_stage);
+  if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
   return ORB_OK;
@@ -689,27 +683,39 @@ int orb_search_for_initialization(orb_matcher* m, const orb_frame_view* f1, cons
   if (n1 == 0 || n2 == 0) return ORB_OK;
   ORB_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = m->stream;
-  const size_t K = (size_t)m->maxKp;
-  ORB_CUDA(cudaMemcpyAsync(m->d_desc, f1->descriptors, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
-  ORB_CUDA(cudaMemcpyAsync(m->d_desc + K * 32, f2->descriptors, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
-  ORB_CUDA(cudaMemcpyAsync(m->d_ang, f1->angle, (size_t)n1 * 4, cudaMemcpyHostToDevice, s));
-  ORB_CUDA(cudaMemcpyAsync(m->d_ang + K, f2->angle, (size_t)n2 * 4, cudaMemcpyHostToDevice, s));
+  const bool windowed = mp->mode == 0;
+  if (windowed && (!f1->octave || !f2->octave || !f2->xy)) ORB_FAIL(ORB_ERR_INVALID, "windowed mode needs octaves and frame-2 positions");
+  // packed layout of this call (16-byte aligned pieces)
+  size_t off = 0;
+  auto piece = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  const size_t oD1 = piece((size_t)n1 * 32), oD2 = piece((size_t)n2 * 32), oA1 = piece((size_t)n1 * 4), oA2 = piece((size_t)n2 * 4);
+  const size_t oXY2 = piece(windowed ? (size_t)n2 * 8 : 0), oO1 = piece(windowed ? (size_t)n1 * 4 : 0);
+  const size_t oO2 = piece(windowed ? (size_t)n2 * 4 : 0), oPrev = piece(windowed ? (size_t)n1 * 8 : 0);
+  const size_t inEnd = off;
+  const size_t oM12 = piece((size_t)n1 * 4), oBest = piece((size_t)n1 * 4), oSecond = piece((size_t)n1 * 4), oNm = piece(16);
+  const size_t outBegin = windowed ? oPrev : oM12, outEnd = off;
+  if (outEnd > m->stageBytes) ORB_FAIL(ORB_ERR_INVALID, "keypoint count exceeds matcher capacity");
+  u8* H = m->h_stage; u8* D = m->d_stage;
+  memcpy(H + oD1, f1->descriptors, (size_t)n1 * 32); memcpy(H + oD2, f2->descriptors, (size_t)n2 * 32);
+  memcpy(H + oA1, f1->angle, (size_t)n1 * 4); memcpy(H + oA2, f2->angle, (size_t)n2 * 4);
+  if (windowed) {
+    memcpy(H + oXY2, f2->xy, (size_t)n2 * 8);
+    memcpy(H + oO1, f1->octave, (size_t)n1 * 4); memcpy(H + oO2, f2->octave, (size_t)n2 * 4);
+    memcpy(H + oPrev, prev_matched, (size_t)n1 * 8);
+  }
+  ORB_CUDA(cudaMemcpyAsync(D, H, inEnd, cudaMemcpyHostToDevice, s));
   PairArgs A;
   memset(&A, 0, sizeof A);
-  A.desc1 = m->d_desc; A.desc2 = m->d_desc + K * 32;
-  A.ang1 = m->d_ang; A.ang2 = m->d_ang + K;
+  A.desc1 = D + oD1; A.desc2 = D + oD2;
+  A.ang1 = reinterpret_cast<float*>(D + oA1); A.ang2 = reinterpret_cast<float*>(D + oA2);
   A.n1 = n1; A.n2 = n2; A.stride1 = 0; A.stride2 = 0;
   A.nnratio = mp->nnratio; A.checkOri = mp->check_orientation; A.window = mp->window;
-  A.matches12 = m->d_m12; A.nmatches = m->d_nm;
-  A.best = m->d_best; A.second = m->d_second;
+  A.matches12 = reinterpret_cast<int*>(D + oM12); A.nmatches = reinterpret_cast<int*>(D + oNm);
+  A.best = reinterpret_cast<int*>(D + oBest); A.second = reinterpret_cast<int*>(D + oSecond);
   int st;
-  if (mp->mode == 0) {
-    if (!f1->octave || !f2->octave || !f2->xy) ORB_FAIL(ORB_ERR_INVALID, "windowed mode needs octaves and frame-2 positions");
-    ORB_CUDA(cudaMemcpyAsync(m->d_xy + K * 2, f2->xy, (size_t)n2 * 8, cudaMemcpyHostToDevice, s));
-    ORB_CUDA(cudaMemcpyAsync(m->d_oct, f1->octave, (size_t)n1 * 4, cudaMemcpyHostToDevice, s));
-    ORB_CUDA(cudaMemcpyAsync(m->d_oct + K, f2->octave, (size_t)n2 * 4, cudaMemcpyHostToDevice, s));
-    ORB_CUDA(cudaMemcpyAsync(m->d_prev, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, s));
-    A.xy2 = m->d_xy + K * 2; A.oct1 = m->d_oct; A.oct2 = m->d_oct + K; A.prev = m->d_prev;
+  if (windowed) {
+    A.xy2 = reinterpret_cast<float*>(D + oXY2); A.oct1 = reinterpret_cast<int*>(D + oO1); A.oct2 = reinterpret_cast<int*>(D + oO2);
+    A.prev = reinterpret_cast<float*>(D + oPrev);
     A.minX = mp->min_x; A.minY = mp->min_y;
     A.invW = 64.f / (mp->max_x - mp->min_x);  // Frame.cc:184-186
     A.invH = 48.f / (mp->max_y - mp->min_y);
@@ -718,12 +724,13 @@ int orb_search_for_initialization(orb_matcher* m, const orb_frame_view* f1, cons
     st = dispatch_match<false>(A, 1, s);
   }
   if (st) return st;
-  ORB_CUDA(cudaMemcpyAsync(matches12, m->d_m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-  ORB_CUDA(cudaMemcpyAsync(nmatches, m->d_nm, 4, cudaMemcpyDeviceToHost, s));
-  if (best) ORB_CUDA(cudaMemcpyAsync(best, m->d_best, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-  if (second) ORB_CUDA(cudaMemcpyAsync(second, m->d_second, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-  if (mp->mode == 0) ORB_CUDA(cudaMemcpyAsync(prev_matched, m->d_prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(H + outBegin, D + outBegin, outEnd - outBegin, cudaMemcpyDeviceToHost, s));
   ORB_CUDA(cudaStreamSynchronize(s));
+  memcpy(matches12, H + oM12, (size_t)n1 * 4);
+  *nmatches = *reinterpret_cast<const int*>(H + oNm);
+  if (best) memcpy(best, H + oBest, (size_t)n1 * 4);
+  if (second) memcpy(second, H + oSecond, (size_t)n1 * 4);
+  if (windowed) memcpy(prev_matched, H + oPrev, (size_t)n1 * 8);
   return ORB_OK;
 }
 
