@@ -1,5 +1,6 @@
 // Compile/link probe for the C++ adapter (no OpenCV in this image: stand-in types).
 // argv[1] == "run" additionally extracts + matches two frames read from stdin-free synthetic data.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -35,6 +36,13 @@ int main(int argc, char** argv) {
     int n = matcher.SearchForInitialization(F1, F2, prev, m12, 100);
     std::printf("keypoints %zu matches %d pyramid0 %dx%d\n", F1.mvKeysUn.size(), n, ex.mvImagePyramid[0].cols, ex.mvImagePyramid[0].rows);
     if (F1.mvKeysUn.empty() || n <= 0) return 3;
+    // latency of the drop-in call itself (operator() of the adapter: keypoints, descriptors and mvImagePyramid views)
+    for (int i = 0; i < 20; i++) ex(img, orbcv::Mat(), F2.mvKeysUn, F2.mDescriptors);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int reps = 200;
+    for (int i = 0; i < reps; i++) ex(img, orbcv::Mat(), F2.mvKeysUn, F2.mDescriptors);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / reps;
+    std::printf("adapter operator() %dx%d, %zu keypoints: %.3f ms per call\n", W, H, F2.mvKeysUn.size(), ms);
   } else {
     try { ORBextractor ex(1000, 1.2f, 8, 20, 7); std::printf("extractor created\n"); }
     catch (const std::exception& e) { std::printf("no device: %s\n", e.what()); }

@@ -30,3 +30,4 @@ def test_adapter_runs_on_gpu(tmp_path):
     out = subprocess.run([exe, "run"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "keypoints" in out.stdout and "pyramid0 640x480" in out.stdout
+    print(out.stdout.strip().splitlines()[-1])   # adapter latency line
