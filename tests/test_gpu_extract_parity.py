@@ -326,3 +326,28 @@ def test_single_call_graph_is_recaptured_when_geometry_changes(oracle):
                 kl, dl, kr, dr, ur, dp = gpu.extract_stereo(left, right, 40.0, 0.1)
                 assert np.array_equal(kl["x"], okl["x"]) and np.array_equal(kr["x"], okr["x"])
                 assert np.array_equal(ur.view(np.uint32), our.view(np.uint32)) and np.array_equal(dp.view(np.uint32), odp.view(np.uint32))
+
+
+def test_random_sizes_and_parameters_against_the_reference_itself(reference):
+    """The CUDA extractor against the reference's own ORBextractor.cc over random image sizes, feature budgets, level
+    counts, scale factors, thresholds and image kinds (every case = a new workspace, new tensor maps, a new graph)."""
+    from orb_slam2_detailed_comments_b200 import ORBextractor
+    from test_oracle_vs_ref import _random_case
+    rng = np.random.RandomState(2027)
+    total = differing = 0
+    for i in range(40):
+        img, prm = _random_case(rng, i)
+        gpu = ORBextractor(*prm)
+        ref = reference.ReferenceExtractor(*prm)
+        kps, desc = gpu(img)
+        rk, rd = ref(img)
+        assert len(kps) == len(rk), (i, prm, img.shape)
+        for f in ("x", "y", "size", "response", "octave", "class_id"):
+            assert np.array_equal(kps[f], rk[f]), (i, f, prm, img.shape)
+        if len(kps):
+            dang = np.abs(kps["angle"] - rk["angle"])
+            assert np.minimum(dang, 360.0 - dang).max() <= ANGLE_TOL_DEG
+            differing += int((desc != rd).any(1).sum())
+        total += len(kps)
+    print("random cases: keypoints", total, "descriptor rows differing", differing)
+    assert total > 20000 and differing <= total // 1000

@@ -136,3 +136,37 @@ def test_golden_vectors_are_what_the_reference_computes(reference, path):
         assert np.array_equal(desc, g["descriptors"])
     for l in range(8):
         assert zlib.crc32(r.level(l).tobytes()) == int(g["level_crc"][l])
+
+
+def _random_case(rng, i):
+    """Random landscape size / extractor parameters / image kind (the generator of tools/ref_stress.py)."""
+    w = int(rng.randint(160, 1300)); h = int(rng.randint(120, 520))
+    if w < h:          # portrait sizes make the reference index an empty root vector (ORBextractor.cc:695-739)
+        w, h = h, w
+    w = min(w, 3 * h)
+    nf = int(rng.choice([200, 500, 1000, 1200, 2000, 3000]))
+    nl = int(rng.choice([8, 8, 8, 5, 10])); sf = float(rng.choice([1.2, 1.2, 1.1, 1.3, 1.5]))
+    ini = int(rng.choice([20, 20, 12, 30])); mn = int(rng.choice([7, 7, 5, 10]))
+    while nl > 1 and min(w, h) / sf ** (nl - 1) < 70:   # the top level must still hold one 30-px cell
+        nl -= 1
+    if rng.randint(4) == 0:
+        img = rng.randint(0, 256, (h, w)).astype(np.uint8)
+    else:
+        img = synth_frame(w, h, 1000 + i, n_rect=int(rng.randint(50, 800)), noise_sigma=float(rng.rand() * 6))
+    return img, (nf, sf, nl, ini, mn)
+
+
+def test_random_sizes_and_parameters(oracle, reference):
+    """80 random (size, nfeatures, levels, scale, thresholds, image kind) cases; tools/ref_stress.py runs thousands
+    (3300 frames / 4.0 M keypoints without a mismatch when this was written)."""
+    rng = np.random.RandomState(77)
+    total = 0
+    for i in range(80):
+        img, prm = _random_case(rng, i)
+        o = oracle.OracleExtractor(*prm); r = reference.ReferenceExtractor(*prm)
+        ko, do = o(img); kr, dr = r(img)
+        assert_identical(ko, do, kr, dr)
+        for l in range(prm[2]):
+            assert np.array_equal(o.level(l), r.level(l)), (i, l)
+        total += len(ko)
+    assert total > 50000
