@@ -212,6 +212,18 @@ def bind_to_gpu_numa_node(props):
             return node
     except Exception:
         pass
+    # no NUMA information (containers often hide it): give every rank its own contiguous block of the visible CPUs, in
+    # GPU order - CPU numbering is socket-contiguous on the usual two-socket boxes and GPUs 0..N/2-1 hang off socket 0, so
+    # pinned staging memory (first touch) and the copy threads of a rank stay on one socket instead of wandering
+    try:
+        world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("LOCAL_RANK", "0"))
+        avail = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(avail) >= 2 * world:
+            per = len(avail) // world
+            os.sched_setaffinity(0, set(avail[rank * per:(rank + 1) * per]))
+            return "cpu-block %d-%d" % (avail[rank * per], avail[(rank + 1) * per - 1])
+    except Exception:
+        pass
     return None
 
 
