@@ -328,15 +328,8 @@ __device__ __forceinline__ void fast_load_diffs(const unsigned* p, int tp, FastD
 // and a corner at threshold th needs c - A > th (all of some 9-arc darker ... every arc holds one pixel
 // of each antipodal pair) or B - c > th. Both comparisons are made per 16-bit half with a 0x200 bias so
 // that no borrow crosses the halves: bit 9 of (c + K - A) is set iff A < c - th, K = 0x200 - (th + 1).
-// Cheapest necessary condition: the two antipodal pairs on the axes (4 loads).
-__device__ __forceinline__ unsigned fast_bound2(const unsigned* p, int tp, unsigned K) {
-  const unsigned c = p[0];
-  const unsigned p0 = p[3 * tp], p8 = p[-3 * tp], p4 = p[3], p12 = p[-3];
-  const unsigned A = __vmaxs2(__vmins2(p0, p8), __vmins2(p4, p12));
-  const unsigned B = __vmins2(__vmaxs2(p0, p8), __vmaxs2(p4, p12));
-  return ((c + K - A) | (B + K - c)) & 0x02000200u;
-}
-
+// Stage 0 applies this test to the two antipodal pairs on the axes, inline in k_fast_cells (the vertical pair comes from
+// a register window that slides down the column); stage 1:
 // The same test on 8 of the 16 circle pixels: the 4 pairs of the even positions.
 __device__ __forceinline__ unsigned fast_bound4(const unsigned* p, int tp, unsigned K) {
   const unsigned c = p[0];
@@ -549,7 +542,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
     int th = g.iniTh, nh = 0;
 #pragma unroll 1
     for (;;) {
-      // bit 9 of a half of the prefilter word is set iff a corner at th is possible there (see fast_bound2)
+      // bit 9 of a half of the prefilter word is set iff a corner at th is possible there (see fast_bound4)
       const unsigned K = 0x02000200u - (unsigned)(th + 1) * 0x00010001u;
       // ---- prefilter, stage 0 (2 pairs, every pixel pair): lanes cover one row (S > 16) or two
       // rows (S <= 16) per step; stage 1 (4 pairs) runs on the compacted survivors, in place
