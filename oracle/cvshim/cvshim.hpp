@@ -1,17 +1,20 @@
 // oracle/cvshim/cvshim.hpp — TEST INFRASTRUCTURE ONLY (part of the oracle).
 //
-// A minimal stand-in for the handful of OpenCV C++ declarations that the reference's
-// src/ORBextractor.cc uses (cv::Mat, KeyPoint, Point_, Size, Rect, InputArray/OutputArray,
-// FAST, resize, copyMakeBorder, GaussianBlur, fastAtan2, cvRound/cvFloor/cvCeil,
-// KeyPointsFilter). OpenCV's C++ headers are not in this image, so the reference cannot be
-// compiled against the real library; with this header it compiles UNMODIFIED, from where it
-// lies under /root/reference (oracle/Makefile, target _ref/liborbref.so), which gives the
-// tests the reference's own control flow (cell loop, iniTh/minTh fallback, DistributeOctTree,
-// IC_Angle, computeOrbDescriptor, level scaling) to pin the oracle restatement against.
+// A minimal stand-in for the OpenCV C++ declarations that the reference's src/ORBextractor.cc,
+// ORBmatcher.cc, Frame.cc, MapPoint.cc, KeyFrame.cc, Map.cc (and the DBoW2 headers they include)
+// use: cv::Mat (8U / 32S / 32F / 64F, views, Mat::zeros / ones / eye expression semantics, small
+// float matrix algebra, Mat_ comma initialiser), KeyPoint, Point_, Size, Rect, InputArray /
+// OutputArray, FAST, resize, copyMakeBorder, GaussianBlur, fastAtan2, undistortPoints, norm,
+// cvRound / cvFloor / cvCeil, KeyPointsFilter, FileStorage / FileNode (declarations only).
+// OpenCV's C++ headers are not in this image, so the reference cannot be compiled against the
+// real library; with this header those files compile UNMODIFIED, from where they lie under
+// /root/reference (oracle/Makefile, target _ref/liborbref.so), which gives the tests the
+// reference's own control flow and arithmetic to pin the oracle restatement against.
 //
-// The pixel arithmetic of the five primitives is NOT OpenCV's code: it is the oracle's
-// restatement (orc_resize_linear, orc_fast, orc_gauss7, orc_fast_atan2 in orb_oracle.cpp),
-// each of which tests/test_oracle_vs_cv2.py pins bit-for-bit against python cv2 4.13.0.
+// The arithmetic of the library primitives is NOT OpenCV's code: it is the oracle's restatement
+// (orc_resize_linear, orc_fast, orc_gauss7, orc_fast_atan2, orc_undistort_keypoints in
+// orb_oracle.cpp; the small-matrix product order below), each pinned bit-for-bit against python
+// cv2 4.13.0 (tests/test_oracle_vs_cv2.py, test_oracle_frame.py, test_oracle_search.py).
 // Nothing here is copied from OpenCV or from the reference.
 #pragma once
 #include <algorithm>

@@ -1,10 +1,12 @@
 """ctypes binding of oracle/_ref/liborbref.so. TEST INFRASTRUCTURE ONLY.
 
-liborbref.so is the REFERENCE's own ORB_SLAM2::ORBextractor (src/ORBextractor.cc compiled unmodified
-from /root/reference by `make -C oracle ref`) behind the C wrapper oracle/ref_wrap.cpp, with the OpenCV
-stand-in of oracle/cvshim/ underneath (primitive arithmetic = the oracle's cv2-pinned restatement).
-It pins the oracle's CONTROL FLOW: cell loop, iniTh/minTh fallback, DistributeOctTree (with the real
-heap-address tie-breaking), IC_Angle, computeOrbDescriptor, level scaling.
+liborbref.so is the REFERENCE's own code - src/ORBextractor.cc, ORBmatcher.cc, Frame.cc, MapPoint.cc, KeyFrame.cc,
+Map.cc compiled unmodified from /root/reference by `make -C oracle ref` - behind the C wrapper oracle/ref_wrap.cpp,
+with the OpenCV stand-in of oracle/cvshim/ underneath (primitive arithmetic = the oracle's cv2-pinned restatement).
+It pins the oracle's CONTROL FLOW AND ARITHMETIC: cell loop, iniTh/minTh fallback, DistributeOctTree (with the real
+heap-address tie-breaking), IC_Angle, computeOrbDescriptor, level scaling; DescriptorDistance, SearchForInitialization,
+the Frame grid / undistortion / area queries, ComputeStereoMatches; the projection / BoW / triangulation searches on
+live MapPoint / KeyFrame objects; ComputeDistinctiveDescriptors.
 
 The library is built in the development container (where /root/reference exists) and travels to the
 GPU box as a prebuilt, git-ignored binary. `available()` says whether it is there; nothing here ever

@@ -1,10 +1,10 @@
 // oracle/ref_wrap.cpp — TEST INFRASTRUCTURE ONLY.
 //
-// C entry points around the REFERENCE's own ORB_SLAM2::ORBextractor, compiled unmodified from
-// /root/reference/src/ORBextractor.cc against the OpenCV stand-in in oracle/cvshim/ (see the
-// header of cvshim.hpp for what that does and does not prove). Built into oracle/_ref/liborbref.so
-// by `make -C oracle ref`; used by tests/test_oracle_vs_ref.py to pin the oracle restatement and
-// by tools/make_golden.py to cross-check the golden vectors. Never loaded by the product.
+// C entry points around the REFERENCE's own ORB_SLAM2::ORBextractor, ORBmatcher, Frame, MapPoint,
+// KeyFrame and Map, compiled unmodified from /root/reference/src/*.cc against the OpenCV stand-in in
+// oracle/cvshim/ (see the header of cvshim.hpp for what that does and does not prove). Built into
+// oracle/_ref/liborbref.so by `make -C oracle ref`; used by tests/test_oracle_vs_ref*.py, the GPU tests
+// named *_the_reference_itself, tools/ref_stress*.py and bench.py's CPU arm. Never loaded by the product.
 #include <atomic>
 #include <cstring>
 #include <thread>
