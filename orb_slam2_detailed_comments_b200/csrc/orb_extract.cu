@@ -2359,11 +2359,7 @@ int run_call(orb_extractor* e, int frames, int width, int height, size_t dFrame,
 
 int ensure_pinned(orb_extractor* e, size_t inBytes, size_t outBytes) {
   if (inBytes > e->h_inBytes) {
-    for (int k = 0; k < 2; k++)
-    if (e->callGraph[k]) cudaGraphExecDestroy(e->callGraph[k]);
-  cudaFree(e->d_stereoScratch);
-  if (e->hostPyr) cudaFreeHost(e->hostPyr);
-  if (e->h_in) cudaFreeHost(e->h_in);
+    if (e->h_in) cudaFreeHost(e->h_in);
     e->h_in = nullptr; e->h_inBytes = 0;
     ORB_CUDA(cudaHostAlloc((void**)&e->h_in, inBytes, cudaHostAllocDefault));
     e->h_inBytes = inBytes;
@@ -2470,6 +2466,10 @@ int orb_destroy(orb_extractor* e) {
     if (e->evDone[b]) cudaEventDestroy(e->evDone[b]);
     if (e->evOut[b]) cudaEventDestroy(e->evOut[b]);
   }
+  for (int k = 0; k < 2; k++)
+    if (e->callGraph[k]) cudaGraphExecDestroy(e->callGraph[k]);
+  cudaFree(e->d_stereoScratch);
+  if (e->hostPyr) cudaFreeHost(e->hostPyr);
   if (e->h_in) cudaFreeHost(e->h_in);
   if (e->h_out) cudaFreeHost(e->h_out);
   if (e->sIn) cudaStreamDestroy(e->sIn);
