@@ -2238,7 +2238,8 @@ int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, cons
   ORB_CUDA(cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // few pairs per call (the per-frame drop-in case): deal every pair to G CTAs
   const int pairs = B / 2;
-  const int G = pairs <= 8 ? 16 : (pairs <= 32 ? 4 : 1);
+  // (one scratch list per extractor: not with two workspace lanes, whose chunks run on two streams at once)
+  const int G = e->lanes >= 2 ? 1 : (pairs <= 8 ? 16 : (pairs <= 32 ? 4 : 1));
   if (G > 1) {
     const int st = ensure_stereo_scratch(e, cap, s);
     if (st) return st;
