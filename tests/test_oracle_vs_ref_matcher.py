@@ -267,3 +267,25 @@ def test_compute_distinctive_descriptors(oracle, reference):
     kept = reference.distinctive_descriptors(desc, offsets)
     for p in range(len(counts)):
         assert np.array_equal(kept[p], desc[offsets[p] + best[p]]), p
+
+
+def test_product_local_map_query_helper_feeds_the_reference_result(oracle, reference):
+    """The product's host helper search.local_map_queries (the radius of ORBmatcher.cc:88-100 / RadiusByViewingCos
+    :171-177 from the MapPoint track fields) builds the same queries as the test-side construction that is pinned against
+    the reference above, and the oracle run on them reproduces the reference's SearchByProjection assignment."""
+    from orb_slam2_detailed_comments_b200 import search
+    for seed, th in ((14, 1.0), (15, 3.0), (16, 5.0)):
+        sc = tracking_scene(700, 800, seed, frac_mapped=0.9)
+        q0 = oracle.project_last_frame(sc["Xw"], sc["mp_flags"] | 1, sc["last"], sc["Tcw"], sc["cam4"], sc["bounds"], sc["mbf"], 1.0, SF, 0)
+        mps = local_map_points(sc, q0, seed)
+        q_test = local_map_queries(oracle, mps, th)
+        q_prod = search.local_map_queries([m["x"] for m in mps], [m["y"] for m in mps], [m["xr"] for m in mps],
+                                          [m["level"] for m in mps], [m["view_cos"] for m in mps],
+                                          [int(m["track_in_view"] and not m["bad"]) for m in mps], [int(m["nobs"] > 0) for m in mps], th, SF)
+        for f in ("u", "v", "radius", "ur", "min_level", "max_level", "flags"):
+            assert np.array_equal(q_prod[f], q_test[f]), f
+        nm, mk, _ = oracle.search_by_projection(sc["cur"], sc["cur_desc"], sc["uright"], sc["bounds"], sc["occupied0"], q_prod.view(oracle.PROJ_QUERY_DTYPE),
+                                                sc["mp_desc"], oracle.SEARCH_RATIO_LEVEL, 100, 0.8, False)
+        F = reference.ReferenceFrame(sc["cur"], sc["cur_desc"], _cam9(sc), 1241, 376)
+        rn, rmk = reference.search_local_map(F, sc["uright"], sc["occupied0"], mps, th, 0.8, sc["cam4"], sc["mbf"], sc["mb"], SF)
+        assert rn == nm > 30 and np.array_equal(rmk, mk)
