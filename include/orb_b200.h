@@ -71,8 +71,12 @@ int orb_destroy(orb_extractor* h);
 int orb_get_scale_tables(const orb_extractor* h, float* scale, float* inv_scale, float* sigma2,
                          float* inv_sigma2, int32_t* features_per_level);
 
-/* Upper bound on keypoints per frame (nfeatures + 3 per level): size outputs with this. */
+/* Upper bound on keypoints per frame: size outputs with this. Per level the quadtree returns at most
+ * max(mnFeaturesPerLevel + 3, 4 * nIni) keypoints, nIni = round(width' / height') roots (src/ORBextractor.cc:695).
+ * orb_max_keypoints: exact for the image size the handle last processed; before the first image a bound valid for
+ * aspect ratios up to 8:1. orb_max_keypoints_for_size: exact for the given image size (0 if the size is unsupported). */
 int orb_max_keypoints(const orb_extractor* h);
+int orb_max_keypoints_for_size(const orb_extractor* h, int width, int height);
 
 /* Replaces ORBextractor::operator()(image, mask, keypoints, descriptors)
  * (src/ORBextractor.cc:1533-1649) for one frame in HOST memory. `image` is CV_8UC1 with row

@@ -70,7 +70,7 @@ class OrbMatchParams(C.Structure):
 # every symbol include/orb_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "orb_last_error", "orb_device_count", "orb_create", "orb_destroy", "orb_get_scale_tables",
-    "orb_max_keypoints", "orb_extract", "orb_extract_batch_host", "orb_extract_batch_host_async", "orb_extract_batch_device",
+    "orb_max_keypoints", "orb_max_keypoints_for_size", "orb_extract", "orb_extract_batch_host", "orb_extract_batch_host_async", "orb_extract_batch_device",
     "orb_extract_stereo", "orb_extract_stereo_batch_device",
     "orb_synchronize", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_times", "orb_set_lanes", "orb_stage_level_size", "orb_stage_copy_level",
     "orb_stage_copy_blur", "orb_stage_copy_candidates", "orb_stage_copy_kept",
@@ -107,6 +107,7 @@ def lib():
         L.orb_destroy.argtypes = [vp]
         L.orb_get_scale_tables.argtypes = [vp, vp, vp, vp, vp, vp]
         L.orb_max_keypoints.argtypes = [vp]
+        L.orb_max_keypoints_for_size.argtypes = [vp, i32, i32]
         L.orb_extract.argtypes = [vp, vp, i32, i32, sz, vp, i32, C.POINTER(i32), vp, vp]
         L.orb_extract_batch_host.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp]
         L.orb_extract_batch_host_async.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp]
@@ -165,3 +166,21 @@ def ptr(a):
     if isinstance(a, np.ndarray):
         return C.c_void_p(a.ctypes.data)
     return C.c_void_p(a.data_ptr())
+
+
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: names the legacy default stream explicitly (NULL means "the handle's own stream" in this ABI)
+
+
+def stream_arg(stream, *tensors):
+    """cudaStream_t to pass for a device entry point. An explicit `stream` (raw cudaStream_t int) wins. Otherwise, when
+    the operands are torch CUDA tensors, the call is ordered on torch's CURRENT stream of their device - the stream the
+    tensors were produced on (torch.zeros, copy_, NCCL work.wait()) - and not on the handle's private non-blocking
+    stream, which is not ordered with it. Without torch tensors: NULL = the handle's own stream."""
+    if stream:
+        return C.c_void_p(int(stream))
+    for t in tensors:
+        if t is not None and not isinstance(t, np.ndarray) and getattr(t, "is_cuda", False):
+            import torch
+            s = torch.cuda.current_stream(t.device).cuda_stream
+            return C.c_void_p(int(s) if s else CUDA_STREAM_LEGACY)
+    return C.c_void_p(0)

@@ -37,6 +37,16 @@ inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line
 template <typename T>
 inline T round_up(T v, T m) { return (v + m - 1) / m * m; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION (per device), not to a handle: several live
+// handles with different geometries (the reference keeps ORBextractor(nFeatures) and ORBextractor(2*nFeatures) alive
+// side by side, src/Tracking.cc:175-188) and several host threads (src/Frame.cc:146-154) share it. It is therefore
+// only ever RAISED, under a lock, to the largest size any launch has asked for so far (defined in orb_extract.cu).
+cudaError_t raise_dynamic_smem_impl(const void* func, size_t bytes);
+template <typename K>
+inline cudaError_t raise_dynamic_smem(K* kernel, size_t bytes) {
+  return raise_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 
 #ifdef __CUDACC__
 // ---- TMA (cp.async.bulk[.tensor]) + mbarrier helpers (sm_90+; this library is sm_100a only)

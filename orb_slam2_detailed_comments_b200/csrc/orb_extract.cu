@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -35,6 +36,21 @@
 namespace orbb200 {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+cudaError_t raise_dynamic_smem_impl(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;   // (device, kernel) -> largest size set so far
+  if (bytes <= 48 * 1024) return cudaSuccess;                     // always launchable
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = granted[std::make_pair(dev, func)];
+  if (bytes <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
 }  // namespace orbb200
 
 using namespace orbb200;
@@ -1808,7 +1824,7 @@ struct orb_extractor {
   u8* h_out = nullptr; size_t h_outBytes = 0;
   // ... and their kernel sequence (2 memsets + 14 launches, all on fixed buffers) is replayed as a CUDA graph, captured
   // again whenever a pointer, the image size or the capacity changes (ORB_B200_GRAPH=0 launches kernel by kernel)
-  struct GraphKey { const void* p[8]; int w, h, cap, frames, flags; };
+  struct GraphKey { const void* p[8]; int w, h, cap, frames, flags; float mbf, mb; };   // mbf / mb are baked into k_stereo's launch
   u8* d_stereoScratch = nullptr; size_t stereoScratchBytes = 0;   // match list + counters of k_stereo's split mode
   bool useGraph = true;
   cudaGraphExec_t callGraph[2] = {nullptr, nullptr};   // [0] one frame, [1] stereo pair
@@ -1818,6 +1834,7 @@ struct orb_extractor {
   int lastChunkFrames = 0;
   float* d_invScale = nullptr;          // mvInvScaleFactor on the device (stereo refinement)
   float* d_uRight[2] = {nullptr, nullptr}; float* d_depth[2] = {nullptr, nullptr};  // host-path staging
+  int stereoOutCap = 0;                 // floats allocated in d_uRight[0] / d_depth[0]
   // optional per-stage CUDA-event timing (bench roofline): 6 boundary events per chunk
   bool profile = false;
   std::vector<cudaEvent_t> evPool;
@@ -1912,7 +1929,7 @@ int build_geom(orb_extractor* e, int W, int H) {
     L.candCap = std::min(1 << 24, std::max(1024, (L.w * L.h) / 6));
     candOff += round_up(L.candCap, 4);
     L.keptOff = keptOff;
-    L.keptCap = std::max(L.nfeat + 3, 4 * L.nIni) + 1;
+    L.keptCap = std::max(L.nfeat + 3, 4 * L.nIni) + 1;   // == level_kept_cap(), orb_max_keypoints_for_size
     keptOff += round_up(L.keptCap, 4);
     maxKp += L.keptCap;
     nodeCap = std::max(nodeCap, L.keptCap + 3);
@@ -2044,7 +2061,7 @@ int build_desc_maps(orb_extractor* e) {
       }
     }
   }
-  ORB_CUDA(cudaFuncSetAttribute(k_describe_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescTmaSmem));
+  ORB_CUDA(raise_dynamic_smem(k_describe_tma, kDescTmaSmem));
   e->descTma = true;
   // blur input tiles: (kBlurTW + 32) x (kBlurTH + 6) bytes of the bordered plane
   bool blurOk = true;
@@ -2080,9 +2097,9 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
     free_workspace(e);
     ORB_CUDA(cudaMalloc(&e->d_taps, std::max<size_t>(1, e->taps.size()) * sizeof(int2)));
     ORB_CUDA(cudaMemcpy(e->d_taps, e->taps.data(), e->taps.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    ORB_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qtSmem));
-    ORB_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->fastSmem));
-    ORB_CUDA(cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescSmem));
+    ORB_CUDA(raise_dynamic_smem(k_quadtree, e->qtSmem));
+    ORB_CUDA(raise_dynamic_smem(k_fast_cells, e->fastSmem));
+    ORB_CUDA(raise_dynamic_smem(k_describe, kDescSmem));
     {
       int perSM = 0, dev = 0, sms = 0;
       ORB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_fast_cells, 32 * e->fastWarps, e->fastSmem));
@@ -2235,7 +2252,7 @@ int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, cons
   if (smem > 200 * 1024 || (size_t)e->g.H * 4 > (size_t)cap * 8)
     ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints / rows for the stereo kernel's shared memory");
   if (cap > 65535) ORB_FAIL(ORB_ERR_UNSUPPORTED, "stereo matching supports at most 65535 keypoints per frame");
-  ORB_CUDA(cudaFuncSetAttribute(k_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ORB_CUDA(raise_dynamic_smem(k_stereo, smem));
   // few pairs per call (the per-frame drop-in case): deal every pair to G CTAs
   const int pairs = B / 2;
   // (one scratch list per extractor: not with two workspace lanes, whose chunks run on two streams at once)
@@ -2321,9 +2338,8 @@ int run_call(orb_extractor* e, int frames, int width, int height, size_t dFrame,
   key.p[0] = W.pyr; key.p[1] = W.blur; key.p[2] = W.cand; key.p[3] = W.kept; key.p[4] = e->d_in[0]; key.p[5] = e->d_kps[0];
   key.p[6] = e->d_desc[0]; key.p[7] = stereo ? (const void*)e->d_uRight[0] : (const void*)e->d_n[0];
   key.w = width; key.h = height; key.cap = capacity; key.frames = frames;
-  unsigned fb, mbb;
-  memcpy(&fb, &mbf, 4); memcpy(&mbb, &mb, 4);
-  key.flags = (e->descTma ? 1 : 0) | (e->blurTma ? 2 : 0) | (stereo ? (int)((fb * 2654435761u) ^ mbb) & ~3 : 0);
+  key.flags = (e->descTma ? 1 : 0) | (e->blurTma ? 2 : 0) | (stereo ? 4 : 0);
+  key.mbf = stereo ? mbf : 0.f; key.mb = stereo ? mb : 0.f;   // compared exactly (bitwise, by the memcmp below)
   if (!e->callGraph[slot] || memcmp(&key, &e->callKey[slot], sizeof key) != 0) {
     if (e->callGraph[slot]) { cudaGraphExecDestroy(e->callGraph[slot]); e->callGraph[slot] = nullptr; }
     const int before = e->lastLaunches;
@@ -2506,11 +2522,28 @@ int orb_get_scale_tables(const orb_extractor* e, float* scale, float* inv_scale,
   return ORB_OK;
 }
 
+// Per level the quadtree returns at most max(nfeatures_l + 3, 4 * nIni) nodes (a split adds <= 3; the first pass turns
+// nIni roots into <= 4 * nIni children), nIni = round(width' / height') roots (ORBextractor.cc:695).
+static int level_kept_cap(int nfeat, int nIni) { return std::max(nfeat + 3, 4 * nIni) + 1; }
+
 int orb_max_keypoints(const orb_extractor* e) {
   if (!e) return 0;
-  // nfeatures + 3 per level, and at least 4 roots' worth per level (<= 16 children on the first pass)
+  if (e->haveGeom) return e->maxKp;   // exact for the image size in use
+  // no image seen yet: valid for aspect ratios up to 8:1 (orb_max_keypoints_for_size is exact)
   int m = 0;
-  for (int l = 0; l < e->p.nlevels; l++) m += std::max(e->perLevel[l] + 3, 16) + 1;
+  for (int l = 0; l < e->p.nlevels; l++) m += level_kept_cap(e->perLevel[l], 8);
+  return m;
+}
+
+int orb_max_keypoints_for_size(const orb_extractor* e, int width, int height) {
+  if (!e || width <= 0 || height <= 0) return 0;
+  int m = 0;
+  for (int l = 0; l < e->p.nlevels; l++) {
+    const int w = cv_round_f((float)width * e->invScale[l]), h = cv_round_f((float)height * e->invScale[l]);
+    const int Wp = w - 32, Hp = h - 32;
+    if (Wp < 30 || Hp < 30) return 0;   // orb_extract would return ORB_ERR_UNSUPPORTED
+    m += level_kept_cap(e->perLevel[l], std::max(1, (int)std::round((float)Wp / (float)Hp)));
+  }
   return m;
 }
 
@@ -2780,13 +2813,14 @@ int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* rig
   const size_t dFrame = (size_t)width * height;
   st = ensure_stage(e, dFrame * 2, 2, capacity);
   if (st) return st;
-  if (!e->d_uRight[0] || e->stageCap < capacity) {
+  if (capacity > e->stereoOutCap) {   // grows only (a new pointer also means a new graph capture)
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
     cudaFree(e->d_uRight[0]); cudaFree(e->d_depth[0]);
     e->d_uRight[0] = e->d_depth[0] = nullptr;
-  }
-  if (!e->d_uRight[0]) {
-    ORB_CUDA(cudaMalloc(&e->d_uRight[0], (size_t)std::max(capacity, e->stageCap) * sizeof(float)));
-    ORB_CUDA(cudaMalloc(&e->d_depth[0], (size_t)std::max(capacity, e->stageCap) * sizeof(float)));
+    e->stereoOutCap = 0;
+    ORB_CUDA(cudaMalloc(&e->d_uRight[0], (size_t)capacity * sizeof(float)));
+    ORB_CUDA(cudaMalloc(&e->d_depth[0], (size_t)capacity * sizeof(float)));
+    e->stereoOutCap = capacity;
   }
   cudaStream_t s = e->stream;
   e->lastLaunches = 0;

@@ -301,7 +301,7 @@ int orb_distinctive_descriptors_device(int device, const uint8_t* d_descriptors,
   const size_t smem = (size_t)kDistWarps * 32 * max_observations * sizeof(unsigned short);
   if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "more than 800 observations per map point");
   ORB_CUDA(cudaSetDevice(device));
-  if (smem > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ORB_CUDA(raise_dynamic_smem(k_distinctive, smem));
   k_distinctive<<<(n_points + kDistWarps - 1) / kDistWarps, 32 * kDistWarps, smem, (cudaStream_t)stream>>>(
       d_descriptors, d_offsets, n_points, max_observations, d_best_index, d_best_descriptor);
   ORB_CUDA(cudaGetLastError());

@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(256) k_int_pipe(unsigned* out, int iters, unsi
 
 template <int CPT, bool W>
 int launch_match(const PairArgs& A, int pairs, size_t smem, cudaStream_t s) {
-  ORB_CUDA(cudaFuncSetAttribute(k_match_pairs<CPT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ORB_CUDA(raise_dynamic_smem(k_match_pairs<CPT, W>, smem));
   k_match_pairs<CPT, W><<<pairs, kMatchThreads, smem, s>>>(A);
   ORB_CUDA(cudaGetLastError());
   return ORB_OK;
@@ -584,7 +584,7 @@ int launch_match(const PairArgs& A, int pairs, size_t smem, cudaStream_t s) {
 
 template <int RPT>
 int launch_match_bf(const PairArgs& A, int pairs, size_t smem, cudaStream_t s) {
-  ORB_CUDA(cudaFuncSetAttribute(k_match_pairs_bf<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ORB_CUDA(raise_dynamic_smem(k_match_pairs_bf<RPT>, smem));
   k_match_pairs_bf<RPT><<<pairs, kBfThreads, smem, s>>>(A);
   ORB_CUDA(cudaGetLastError());
   return ORB_OK;
@@ -610,7 +610,10 @@ int dispatch_match(const PairArgs& A, int pairs, cudaStream_t s) {
   if (cpt <= 4) return launch_match<4, W>(A, pairs, smem, s);
   if (cpt <= 8) return launch_match<8, W>(A, pairs, smem, s);
   if (cpt <= 12) return launch_match<12, W>(A, pairs, smem, s);
-  ORB_FAIL(ORB_ERR_UNSUPPORTED, "more than 3072 keypoints in frame 2");
+  // the monocular initialisation extractor asks for 2*nFeatures (src/Tracking.cc:188): 4000 (+3 per level) on KITTI
+  if (cpt <= 16) return launch_match<16, W>(A, pairs, smem, s);
+  if (cpt <= 20) return launch_match<20, W>(A, pairs, smem, s);
+  ORB_FAIL(ORB_ERR_UNSUPPORTED, "more than 5120 keypoints in frame 2");
 }
 
 }  // namespace
@@ -770,7 +773,7 @@ int orb_match_allpairs_device(orb_matcher* m, const uint8_t* d_all, int n_kf, in
   dim3 grid(spans, rows);
 #define ORB_AP(R)                                                                                                  \
   do {                                                                                                             \
-    ORB_CUDA(cudaFuncSetAttribute(k_allpairs<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    ORB_CUDA(raise_dynamic_smem(k_allpairs<R>, smem));         \
     k_allpairs<R><<<grid, kApThreads, smem, s>>>(d_all, n_kf, n_desc, row_begin, col_begin, col_end, colsPerBlock, nnratio, d_counts); \
   } while (0)
   if (rpt <= 1) ORB_AP(1);

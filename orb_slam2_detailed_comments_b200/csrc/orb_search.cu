@@ -657,7 +657,7 @@ int launch_search(const SearchArgs& A, int batch, cudaStream_t s) {
   ORB_CUDA(cudaGetLastError());
   const size_t smem = ((size_t)((A.cap + 31) >> 5) + (size_t)A.cap + 2 * (size_t)A.qcap) * 4;
   if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "capacity too large for the commit kernel's shared memory");
-  if (smem > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_search_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ORB_CUDA(raise_dynamic_smem(k_search_commit, smem));
   k_search_commit<<<batch, kCommitThreads, smem, s>>>(A);
   ORB_CUDA(cudaGetLastError());
   return ORB_OK;
@@ -728,7 +728,7 @@ int orb_search_by_bow_device(int device, const orb_keypoint* d_keypoints1, const
   while (N < std::max(query_capacity, frames->capacity)) N <<= 1;
   const size_t smem = (size_t)N * 8;
   if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many features for the BoW ordering kernel");
-  if (smem > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_bow_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ORB_CUDA(raise_dynamic_smem(k_bow_prepare, smem));
   k_bow_prepare<<<frames->batch, 256, smem, (cudaStream_t)stream>>>(A, d_node1, d_counts1, d_node2);
   ORB_CUDA(cudaGetLastError());
   return launch_search(A, frames->batch, (cudaStream_t)stream);
@@ -760,7 +760,7 @@ int orb_search_for_triangulation_device(int device, const orb_keypoint* d_keypoi
   while (N < std::max(query_capacity, frames2->capacity)) N <<= 1;
   const size_t smem = (size_t)N * 8;
   if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many features for the BoW ordering kernel");
-  if (smem > 48 * 1024) ORB_CUDA(cudaFuncSetAttribute(k_bow_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ORB_CUDA(raise_dynamic_smem(k_bow_prepare, smem));
   k_bow_prepare<<<frames2->batch, 256, smem, (cudaStream_t)stream>>>(A, d_node1, d_counts1, d_node2);
   ORB_CUDA(cudaGetLastError());
   return launch_search(A, frames2->batch, (cudaStream_t)stream);

@@ -40,7 +40,10 @@ def allpairs_match_counts(local_desc, n_kf, compute_block, group=None, overlap=T
     """local_desc: (rows_local, n_desc, 32) u8 descriptors of this rank's keyframes (block
     `shard_range(n_kf, rank, world)`). compute_block(all_desc, row_begin, row_end, col_begin,
     col_end, out) must fill out[:, col_begin:col_end] for the rank's rows; on the GPU this is
-    ORBmatcher.match_allpairs_device. Returns the rank's (rows_local, n_kf) int32 count block."""
+    ORBmatcher.match_allpairs_device. compute_block MUST enqueue its work on torch's CURRENT stream: `out`, `all_desc`
+    and the NCCL broadcasts (work.wait() only blocks the current stream) are ordered on it. match_allpairs_device does
+    so by default (stream=None -> torch.cuda.current_stream(), see _lib.stream_arg); pass an explicit stream only if it
+    is the current one. Returns the rank's (rows_local, n_kf) int32 count block."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     ranges = [shard_range(n_kf, r, world) for r in range(world)]

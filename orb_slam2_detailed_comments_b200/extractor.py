@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import KP_DTYPE, OrbParams, check, lib, ptr
+from ._lib import stream_arg, KP_DTYPE, OrbParams, check, lib, ptr
 
 
 class ORBextractor:
@@ -31,6 +31,10 @@ class ORBextractor:
                                            ptr(self.mnFeaturesPerLevel)))
         self.max_keypoints = int(self._L.orb_max_keypoints(self._h))
         self.mvImagePyramid = []
+
+    def max_keypoints_for(self, width, height):
+        """Exact output capacity for this image size (per level max(nfeatures_l + 3, 4 * quadtree roots) + 1)."""
+        return int(self._L.orb_max_keypoints_for_size(self._h, int(width), int(height))) or self.max_keypoints
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -61,7 +65,7 @@ class ORBextractor:
         if image.strides[1] != 1:
             image = np.ascontiguousarray(image)
         h, w = image.shape
-        cap = self.max_keypoints
+        cap = self.max_keypoints_for(w, h)
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
         n = C.c_int(0)
@@ -81,7 +85,7 @@ class ORBextractor:
         """images: (B,H,W) u8 numpy (pinned or pageable). H2D/D2H inside. Returns (kps[B,cap], desc[B,cap,32], counts[B])."""
         assert images.dtype == np.uint8 and images.ndim == 3 and images.flags.c_contiguous
         B, h, w = images.shape
-        cap = self.max_keypoints
+        cap = self.max_keypoints_for(w, h)
         kps = np.zeros((B, cap), KP_DTYPE)
         desc = np.zeros((B, cap, 32), np.uint8)
         counts = np.zeros(B, np.int32)
@@ -102,7 +106,7 @@ class ORBextractor:
         B, h, w = d_images.shape
         cap = d_kps.shape[1]
         check(self._L.orb_extract_batch_device(self._h, ptr(d_images), B, w, h, d_images.stride(1), d_images.stride(0),
-                                               ptr(d_kps), cap, ptr(d_counts), ptr(d_desc), C.c_void_p(stream or 0)))
+                                               ptr(d_kps), cap, ptr(d_counts), ptr(d_desc), self._stream(stream, d_images)))
 
     # ---- stereo: both eyes + Frame::ComputeStereoMatches (src/Frame.cc:121-158, 831-1082)
     def extract_stereo(self, left, right, mbf, mb):
@@ -110,7 +114,7 @@ class ORBextractor:
         assert left.shape == right.shape and left.dtype == np.uint8 and right.dtype == np.uint8
         left = np.ascontiguousarray(left); right = np.ascontiguousarray(right)
         h, w = left.shape
-        cap = self.max_keypoints
+        cap = self.max_keypoints_for(w, h)
         kl = np.zeros(cap, KP_DTYPE); kr = np.zeros(cap, KP_DTYPE)
         dl = np.zeros((cap, 32), np.uint8); dr = np.zeros((cap, 32), np.uint8)
         ur = np.zeros(cap, np.float32); dp = np.zeros(cap, np.float32)
@@ -126,9 +130,19 @@ class ORBextractor:
         cap = d_kps.shape[1]
         check(self._L.orb_extract_stereo_batch_device(self._h, ptr(d_images), B // 2, w, h, d_images.stride(1), d_images.stride(0),
                                                       ptr(d_kps), cap, ptr(d_counts), ptr(d_desc), C.c_float(mbf), C.c_float(mb),
-                                                      ptr(d_uright), ptr(d_depth), C.c_void_p(stream or 0)))
+                                                      ptr(d_uright), ptr(d_depth), self._stream(stream, d_images)))
+
+    def _stream(self, stream, tensor):
+        # default = torch's current stream of the operands (see _lib.stream_arg), remembered for synchronize()
+        self._last_stream = stream_arg(stream, tensor)
+        return self._last_stream
 
     def synchronize(self, stream=None):
+        """Waits for `stream`; without one, for everything the handle has in flight and the stream of the last device
+        call. Raises on a capacity overflow (ORB_ERR_CAPACITY)."""
+        last = getattr(self, "_last_stream", None)
+        if not stream and last is not None and last.value:
+            check(self._L.orb_synchronize(self._h, last))
         check(self._L.orb_synchronize(self._h, C.c_void_p(stream or 0)))
 
     def last_launch_count(self):

@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import AREA_QUERY_DTYPE, OrbCamera, check, lib, ptr
+from ._lib import stream_arg, AREA_QUERY_DTYPE, OrbCamera, check, lib, ptr
 
 FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48
 
@@ -25,7 +25,7 @@ def UndistortKeyPoints(d_kps, d_counts, cam, d_kps_un, device=0, stream=None):
     """d_kps / d_kps_un: (B, cap, 28) u8 torch tensors (orb_keypoint records), d_counts (B) int32."""
     B, cap = d_kps.shape[0], d_kps.shape[1]
     check(lib().orb_undistort_keypoints_device(device, ptr(d_kps), ptr(d_counts), B, cap, C.byref(cam), ptr(d_kps_un),
-                                               C.c_void_p(stream or 0)))
+                                               stream_arg(stream, d_kps)))
 
 
 def AssignFeaturesToGrid(d_kps_un, d_counts, bounds, d_cell_start, d_cell_items, device=0, stream=None):
@@ -33,7 +33,7 @@ def AssignFeaturesToGrid(d_kps_un, d_counts, bounds, d_cell_start, d_cell_items,
     B, cap = d_kps_un.shape[0], d_kps_un.shape[1]
     b = np.ascontiguousarray(bounds, np.float32)
     check(lib().orb_assign_features_to_grid_device(device, ptr(d_kps_un), ptr(d_counts), B, cap, ptr(b), ptr(d_cell_start),
-                                                   ptr(d_cell_items), C.c_void_p(stream or 0)))
+                                                   ptr(d_cell_items), stream_arg(stream, d_kps_un)))
 
 
 def GetFeaturesInArea(d_kps_un, bounds, d_cell_start, d_cell_items, d_queries, d_out, d_out_counts, device=0, stream=None):
@@ -42,7 +42,7 @@ def GetFeaturesInArea(d_kps_un, bounds, d_cell_start, d_cell_items, d_queries, d
     b = np.ascontiguousarray(bounds, np.float32)
     check(lib().orb_get_features_in_area_device(device, ptr(d_kps_un), cap, ptr(b), ptr(d_cell_start), ptr(d_cell_items),
                                                 ptr(d_queries), d_queries.shape[0], ptr(d_out), d_out.shape[1],
-                                                ptr(d_out_counts), C.c_void_p(stream or 0)))
+                                                ptr(d_out_counts), stream_arg(stream, d_kps_un)))
 
 
 def make_queries(frames, xs, ys, rs, min_levels, max_levels):

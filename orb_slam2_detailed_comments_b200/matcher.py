@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import OrbFrameView, OrbMatchParams, check, lib, ptr
+from ._lib import stream_arg, OrbFrameView, OrbMatchParams, check, lib, ptr
 
 
 class FrameView:
@@ -88,7 +88,7 @@ class ORBmatcher:
         n = d_desc.shape[1]
         check(self._L.orb_match_pairs_device(self._h, ptr(d_desc), ptr(d_angle), P, n, self.mfNNratio,
                                              int(self.mbCheckOrientation), ptr(d_matches12), ptr(d_nmatches),
-                                             C.c_void_p(stream or 0)))
+                                             self._stream(stream, d_desc)))
 
     def match_allpairs_device(self, d_all, row_begin, row_end, d_counts, stream=None, col_begin=0, col_end=None):
         """d_all (nKF,nDesc,32) u8 holding ALL keyframes; d_counts (row_end-row_begin, nKF) i32.
@@ -96,14 +96,23 @@ class ORBmatcher:
         nkf, nd = d_all.shape[0], d_all.shape[1]
         col_end = nkf if col_end is None else col_end
         check(self._L.orb_match_allpairs_device(self._h, ptr(d_all), nkf, nd, row_begin, row_end, col_begin, col_end,
-                                                self.mfNNratio, ptr(d_counts), C.c_void_p(stream or 0)))
+                                                self.mfNNratio, ptr(d_counts), self._stream(stream, d_all)))
 
     def hamming_matrix_device(self, d_a, d_b, d_out, stream=None):
         check(self._L.orb_hamming_matrix_device(self._h, ptr(d_a), d_a.shape[0], ptr(d_b), d_b.shape[0], ptr(d_out),
-                                                C.c_void_p(stream or 0)))
+                                                self._stream(stream, d_a)))
+
+    def _stream(self, stream, tensor):
+        # default = torch's current stream of the operands (see _lib.stream_arg), remembered for synchronize()
+        self._last_stream = stream_arg(stream, tensor)
+        return self._last_stream
 
     def synchronize(self, stream=None):
+        """Waits for `stream`; without one, for the handle's own stream and the stream of the last device call."""
         check(self._L.orb_matcher_synchronize(self._h, C.c_void_p(stream or 0)))
+        last = getattr(self, "_last_stream", None)
+        if not stream and last is not None and last.value:
+            check(self._L.orb_matcher_synchronize(self._h, last))
 
 
 def int_pipe_peak(device=0):

@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import (ORB_SEARCH_BEST, ORB_SEARCH_RATIO, ORB_SEARCH_RATIO_LEVEL, PROJ_QUERY_DTYPE, TRI_PAIR_DTYPE, OrbDeviceFrames,
+from ._lib import (stream_arg, ORB_SEARCH_BEST, ORB_SEARCH_RATIO, ORB_SEARCH_RATIO_LEVEL, PROJ_QUERY_DTYPE, TRI_PAIR_DTYPE, OrbDeviceFrames,
                    OrbSearchParams, check, lib, ptr)
 
 TH_HIGH, TH_LOW = 100, 50   # src/ORBmatcher.cc:47-49
@@ -73,7 +73,7 @@ def ProjectLastFrame(d_world_pos, d_mp_flags, d_last_kps, d_last_counts, d_Tcw, 
     sf = np.ascontiguousarray(scale_factors, np.float32)
     check(lib().orb_project_last_frame_device(device, ptr(d_world_pos), ptr(d_mp_flags), ptr(d_last_kps), ptr(d_last_counts), B, qcap,
                                               ptr(d_Tcw), ptr(d_direction), ptr(cam), ptr(b), float(mbf), float(th), ptr(sf),
-                                              len(sf), ptr(d_queries), C.c_void_p(stream or 0)))
+                                              len(sf), ptr(d_queries), stream_arg(stream, d_world_pos)))
 
 
 def _params(mode, th, ratio, check_ori):
@@ -86,7 +86,7 @@ def SearchByProjection(frames, d_queries, d_query_desc, d_query_counts, mode, th
     p = _params(mode, th, nn_ratio, check_orientation)
     check(lib().orb_search_by_projection_device(device, C.byref(frames), ptr(d_queries), ptr(d_query_desc), ptr(d_query_counts),
                                                 d_queries.shape[1], C.byref(p), ptr(d_scratch), ptr(d_match_of_keypoint),
-                                                ptr(d_match_of_query), ptr(d_nmatches), C.c_void_p(stream or 0)))
+                                                ptr(d_match_of_query), ptr(d_nmatches), stream_arg(stream, d_queries)))
 
 
 def SearchByBoW(d_kps1, d_desc1, d_node1, d_usable1, d_counts1, frames, d_node2, nn_ratio, check_orientation, d_scratch,
@@ -95,7 +95,7 @@ def SearchByBoW(d_kps1, d_desc1, d_node1, d_usable1, d_counts1, frames, d_node2,
     check(lib().orb_search_by_bow_device(device, ptr(d_kps1), ptr(d_desc1), ptr(d_node1), ptr(d_usable1), ptr(d_counts1),
                                          d_kps1.shape[1], C.byref(frames), ptr(d_node2), C.byref(p), ptr(d_scratch),
                                          ptr(d_match_of_keypoint), ptr(d_match_of_query), ptr(d_nmatches),
-                                         C.c_void_p(stream or 0)))
+                                         stream_arg(stream, d_kps1)))
 
 
 def epipole(K2_fx, K2_fy, K2_cx, K2_cy, R2w, t2w, Cw):
@@ -117,4 +117,4 @@ def SearchForTriangulation(d_kps1, d_desc1, d_node1, d_has_mp1, d_uright1, d_cou
     check(lib().orb_search_for_triangulation_device(device, ptr(d_kps1), ptr(d_desc1), ptr(d_node1), ptr(d_has_mp1), ptr(d_uright1),
                                                     ptr(d_counts1), d_kps1.shape[1], C.byref(frames2), ptr(d_node2), ptr(d_pairs), ptr(sf),
                                                     ptr(s2), len(sf), int(bool(check_orientation)), ptr(d_scratch), ptr(d_matches12),
-                                                    ptr(d_nmatches), C.c_void_p(stream or 0)))
+                                                    ptr(d_nmatches), stream_arg(stream, d_kps1)))
