@@ -384,11 +384,16 @@ __device__ __forceinline__ unsigned fast_exact(const FastDiffs& D) {
 // The cell's detection window is x in [19+j*wCell, min(18+(j+1)*wCell, w-20)] (sub-image
 // [iniX,maxX) minus FAST's own 3-px frame), so windows tile the level and the 3x3 NMS never sees
 // across a cell boundary (scores outside the window count as 0).
-// Per cell: raw bytes arrive by cp.async (prefetched while the previous cell is being scored) ->
-// pair-interleaved tile -> 8-pixel prefilter with ballot compaction -> exact score on the queue
-// (dense, no divergence) -> 3x3 NMS on the hit list -> iniTh / minTh decision -> one atomicAdd
-// per cell reserves the output range. Only __syncwarp() is needed: warps run out of phase and
-// hide each other's latencies.
+// Per cell: raw bytes arrive by 16-byte cp.async (prefetched while the previous cell is being scored) ->
+// pair tile -> 4-pixel prefilter, one lane per column, survivors kept as a bit mask per lane -> queue ->
+// 8-pixel prefilter on the queue -> exact score on the queue (dense, no divergence) -> 3x3 NMS on the hit list ->
+// iniTh / minTh decision -> one atomicAdd per cell reserves the output range. Only __syncwarp() is needed: warps
+// run out of phase and hide each other's latencies.
+//
+// Pair tile: the two pixels of a word are VERTICAL neighbours at distance R = ceil(ch / 2): word (r, T) =
+// (I[r][T], I[r + R][T]), one word per column, R + 6 rows. Both pixels see the 16 circle samples at the same word
+// offsets, and the tile is built from the raw rows word-wise: two aligned 32-bit loads (rows r and r + R), six byte
+// permutes and one 16-byte store per 4 columns (the former (x, x + S) horizontal pairing needed two byte loads per word).
 constexpr int kFastWarps = 11;  // upper bound; the host picks the warps per CTA that pack an SM's shared memory best
 constexpr int kFastThreads = 32 * kFastWarps;
 constexpr int kFastRun = 16;   // consecutive cells a warp grabs per atomic ...
@@ -400,8 +405,8 @@ struct FastSmemLayout {   // per-warp shared memory carve-up (in bytes), sized f
 };
 
 struct CellDesc {
-  const u8* src;          // 4-byte aligned address at or left of tile byte (0,0) = image (x0-3, y0-3)
-  int ox;                 // tile column 0 sits `ox` bytes into a raw row
+  const u8* src;          // 16-byte aligned address at or left of tile byte (0,0) = image (x0-3, y0-3)
+  int ox;                 // image column x0-3 sits `ox` (0..15) bytes into a raw row
   int pitch, cw, ch, x0, y0, l, f, rw;
 };
 
@@ -442,44 +447,50 @@ __device__ __forceinline__ bool fast_cell_desc(const Geom& g, const u8* pyr, siz
   c.l = k.l;
   c.f = k.f;
   c.pitch = L.pitch;
-  const int xs = (c.x0 - 3) & ~7;                 // 8-byte aligned: rows are fetched in 8-byte chunks
+  // interior column 0 sits at byte kLeftPad (a multiple of 16) of a 32-byte aligned row: 16-byte chunks
+  const int xs = (c.x0 - 3) & ~15;
   c.ox = (c.x0 - 3) - xs;
-  c.rw = (c.ox + c.cw + 6 + 7) >> 3;              // chunks per row (<= 10)
+  c.rw = (c.ox + c.cw + 6 + 15) >> 4;             // chunks per row (<= 6)
   c.src = pyr + (size_t)k.f * pyrStride + L.off + (long long)(c.y0 - 3) * L.pitch + xs;
   return c.cw > 0 && c.ch > 0;
 }
 
 __device__ __forceinline__ void fast_prefetch(const CellDesc& c, unsigned* raw, int rawPitchWords, int lane) {
-  // (ch+6) rows x rw (<= 10) 8-byte chunks: two rows per step (16 lanes each)
+  // (ch+6) rows x rw (<= 6) 16-byte chunks: 8 rows x 4 chunks per step (4 rows x 8 chunks for wide cells)
   const int rows = c.ch + 6;
-  const int cx = lane & 15;
+  const int sh = c.rw <= 4 ? 2 : 3;               // warp-uniform
+  const int cx = lane & ((1 << sh) - 1), r0 = lane >> sh, dr = 32 >> sh;
   if (cx < c.rw) {
-    const u8* s = c.src + ((lane >> 4) * c.pitch + 8 * cx);
-    unsigned* d = raw + (lane >> 4) * rawPitchWords + 2 * cx;
-    for (int r = lane >> 4; r < rows; r += 2) {
-      __pipeline_memcpy_async(d, s, 8);
-      s += 2 * c.pitch;
-      d += 2 * rawPitchWords;
+    const u8* s = c.src + (r0 * c.pitch + 16 * cx);
+    unsigned* d = raw + r0 * rawPitchWords + 4 * cx;
+    const int sstep = dr * c.pitch, dstep = dr * rawPitchWords;
+    for (int r = r0; r < rows; r += dr) {
+      __pipeline_memcpy_async(d, s, 16);
+      s += sstep;
+      d += dstep;
     }
   }
   __pipeline_commit();
 }
 
+// flags: bit 0 = skip the 8-pixel prefilter (stage 1)
 __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                              uint2* __restrict__ cand, int* __restrict__ candCount,
                                                              int candTotal, int nItems, const FastSmemLayout lay,
-                                                             int* __restrict__ workCounter, int tailRun, int tailMul) {
+                                                             int* __restrict__ workCounter, int tailRun, int tailMul, int flags) {
   extern __shared__ __align__(16) u8 smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   u8* base = smem + wid * lay.total;
   unsigned* raw = reinterpret_cast<unsigned*>(base);
   unsigned* tile = reinterpret_cast<unsigned*>(base + lay.rawBytes);
   // hits (produced, from the front) and the queue (consumed, stored at the back) share one buffer
-  // of 2*S*ch entries: a batch of 32 queue items yields at most 64 hits, so writes never reach
-  // the unread part of the queue (2*(e0+32) <= 2*S*ch - nq + e0 + 32 whenever nq <= S*ch)
+  // of 2*R*cw entries: a batch of 32 queue items yields at most 64 hits, so writes never reach
+  // the unread part of the queue (2*(e0+32) <= R*cw + e0 + 32 whenever e0 + 32 <= R*cw)
   unsigned short* hits = reinterpret_cast<unsigned short*>(base + lay.rawBytes + lay.tileBytes);
   u8* sc = base + lay.rawBytes + lay.tileBytes + lay.hitsBytes;
   const unsigned ltmask = (1u << lane) - 1u;
+  // the score plane is all zero between cells: cleared once here, and after every cell at the positions it wrote
+  for (int i = lane; i < lay.scBytes / 4; i += 32) reinterpret_cast<unsigned*>(sc)[i] = 0u;
 
   // work distribution: a warp grabs runs of consecutive cells from a global counter of work units
   const int tailItems = min(nItems, (int)(gridDim.x * (blockDim.x >> 5)) * kFastRun * tailMul);
@@ -511,39 +522,35 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
 
   while (have) {
     const int cw = c.cw, ch = c.ch;
-    const int S = (cw + 1) >> 1;            // pair stride
-    const int tp = S + 6;                   // tile pitch in words
+    const int R = (ch + 1) >> 1;            // pair distance: word (r, T) = rows (r, r + R) of the tile
+    const int xoff = (c.ox & 3) + 3;        // tile column of cell column 0
+    const int tp = (xoff + cw + 3 + 3) & ~3; // tile pitch in words (whole raw words: multiple of 4)
     const int sp = cw + 2;                  // score pitch (1-px zero apron)
     __pipeline_wait_prior(0);
     __syncwarp();
-    // raw bytes -> pair-interleaved tile: word (r, j) = (T[r][j], T[r][j+S])
+    // raw rows -> pair tile, word-wise: lane = (row group q, raw word k); 4 tile words per lane and step
     {
-      const u8* rb = reinterpret_cast<const u8*>(raw) + c.ox;
-      const int rp = lay.rawPitchWords * 4;
-      const int jmax = cw + 6 - S;   // pixels j+S beyond the tile are zero
-      if (lane < tp) {               // tp = S+6 <= 36: one row per step, a second sweep for wide cells
-        const u8* q = rb + lane;
-        unsigned* t = tile + lane;
-        const bool hasHi = lane < jmax;
-#pragma unroll 4
-        for (int r = 0; r < ch + 6; r++) {
-          *t = (unsigned)q[0] | ((hasHi ? (unsigned)q[S] : 0u) << 16);
-          q += rp;
-          t += tp;
+      const int wpr = tp >> 2;                       // raw words per tile row (<= 18)
+      const int rps = wpr <= 8 ? 4 : (wpr <= 10 ? 3 : (wpr <= 16 ? 2 : 1));   // rows per step (32 / wpr)
+      const int q = wpr <= 8 ? lane >> 3 : (wpr <= 10 ? lane / 10 : (wpr <= 16 ? lane >> 4 : 0));
+      const int k = wpr <= 8 ? lane & 7 : (wpr <= 10 ? lane - 10 * q : (wpr <= 16 ? lane & 15 : lane));
+      if (q < rps && k < wpr) {
+        const int rpw = lay.rawPitchWords;
+        const unsigned* ra = raw + (c.ox >> 2) + k;
+        uint4* t = reinterpret_cast<uint4*>(tile + q * tp + 4 * k);
+        const int rows = R + 6, last = ch + 5;       // the partner of tile row R+5 does not exist for odd ch: clamped (masked later)
+        for (int r = q; r < rows; r += rps) {
+          const unsigned a = ra[r * rpw], b = ra[min(r + R, last) * rpw];
+          const unsigned x01 = __byte_perm(a, b, 0x5410), x23 = __byte_perm(a, b, 0x7632);
+          uint4 o;
+          o.x = __byte_perm(x01, 0u, 0x4240);
+          o.y = __byte_perm(x01, 0u, 0x4341);
+          o.z = __byte_perm(x23, 0u, 0x4240);
+          o.w = __byte_perm(x23, 0u, 0x4341);
+          *t = o;
+          t += (rps * tp) >> 2;
         }
       }
-      if (tp > 32 && lane + 32 < tp) {
-        const int j = lane + 32;
-        const u8* q = rb + j;
-        unsigned* t = tile + j;
-        const bool hasHi = j < jmax;
-        for (int r = 0; r < ch + 6; r++) {
-          *t = (unsigned)q[0] | ((hasHi ? (unsigned)q[S] : 0u) << 16);
-          q += rp;
-          t += tp;
-        }
-      }
-      for (int i = lane; i < (sp * (ch + 2) + 3) / 4; i += 32) reinterpret_cast<unsigned*>(sc)[i] = 0u;
     }
     __syncwarp();
     // the raw buffer is free again: prefetch the next cell of this warp
@@ -554,52 +561,53 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
     // Two threshold passes like the reference (:1111-1124): cv::FAST(iniTh) first; only if its
     // result (after NMS) is empty, cv::FAST(minTh). Scoring pixels at iniTh first keeps the exact
     // scoring away from the many weak corners of the ~97 % of cells that have a strong one.
-    unsigned short* queue = hits + S * ch;   // the queue fills [S*ch, S*ch + nq), hits grow from 0
-    int th = g.iniTh, nh = 0;
+    unsigned short* queue = hits + R * cw;   // the queue fills [R*cw, R*cw + nq), hits grow from 0
+    int th = g.iniTh, nh = 0, total = 0;
 #pragma unroll 1
     for (;;) {
       // bit 9 of a half of the prefilter word is set iff a corner at th is possible there (see fast_bound4)
       const unsigned K = 0x02000200u - (unsigned)(th + 1) * 0x00010001u;
-      // ---- prefilter, stage 0 (2 pairs, every pixel pair): lanes cover one row (S > 16) or two
-      // rows (S <= 16) per step; stage 1 (4 pairs) runs on the compacted survivors, in place
+      // ---- prefilter, stage 0 (the two antipodal pairs on the axes, every pixel pair). A lane walks DOWN its column with
+      // the 7 rows of the vertical arm in registers (sliding window): per step one new row word and the two horizontal
+      // neighbours are loaded. The outcome of step i is shifted into a per-lane bit mask; the queue is written after the
+      // walk from the masks (one warp scan instead of a ballot, two population counts and a store per step).
       int nq = 0;
-      {
-        // A lane walks DOWN its column with the 7 rows of the vertical arm in registers (sliding window): per pixel pair
-        // one new row word and the two horizontal neighbours are loaded (3 shared-memory loads instead of 5). Narrow
-        // cells (S <= 16) put the upper and the lower half of the rows on the two half-warps. Every lane evaluates a
-        // clamped position in every step and the validity only masks the result (no divergent guard); a lane of the
-        // lower half may read one row past the tile in the last step (the hit buffer follows; the value is masked).
-        const int two = S <= 16;
-        const int x = two ? (lane & 15) : lane;
-        const int grp = two ? (lane >> 4) : 0;
-        const int steps = two ? (ch + 1) >> 1 : ch;          // warp-uniform
-        const int rstart = grp ? steps : 0;
-        const int nrows = grp ? ch - steps : steps;
-        const bool xok = x < S;
-        const unsigned* col = tile + rstart * tp + (min(x, S - 1) + 3);   // tile row rstart = image row rstart-3
+      for (int xb = 0; xb < cw; xb += 32) {        // one sweep (cw <= 32) or two
+        const int x = xb + lane;
+        const unsigned* col = tile + (xoff + min(x, cw - 1));
         unsigned w0 = col[0], w1 = col[tp], w2 = col[2 * tp], w3 = col[3 * tp], w4 = col[4 * tp], w5 = col[5 * tp];
-        const unsigned* pc = col + 3 * tp;                    // centre of step 0
+        const unsigned* pc = col + 3 * tp;           // centre of step 0
         const int tp3 = 3 * tp;
-        unsigned short* qp = queue;
-        int val = (rstart << 6) | x;
-#pragma unroll 7
-        for (int i = 0; i < steps; i++) {
+        unsigned mask = 0;
+#pragma unroll 8
+        for (int i = 0; i < R; i++) {
           const unsigned w6 = pc[tp3];
           const unsigned pl = pc[-3], pr = pc[3];
           const unsigned A = __vmaxs2(__vmins2(w6, w0), __vmins2(pr, pl));
           const unsigned B = __vmins2(__vmaxs2(w6, w0), __vmaxs2(pr, pl));
           const unsigned b = ((w3 + K - A) | (B + K - w3)) & 0x02000200u;
-          const bool pass = (b != 0u) & xok & (i < nrows);
-          const unsigned m = __ballot_sync(0xffffffffu, pass);
-          if (pass) qp[__popc(m & ltmask)] = (unsigned short)val;
-          qp += __popc(m);
+          mask = (mask >> 1) | (b ? 0x80000000u : 0u);
           w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
-          pc += tp; val += 64;
+          pc += tp;
         }
-        nq = (int)(qp - queue);
+        mask = x < cw ? mask >> (32 - R) : 0u;       // bit r = the pair (r, r + R) of this column passed (1 <= R <= 30)
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        unsigned short* qp = queue + nq + (incl - cnt);
+        while (mask) {
+          const int r = __ffs(mask) - 1;
+          mask &= mask - 1;
+          *qp++ = (unsigned short)((r << 6) | x);
+        }
+        nq += __shfl_sync(0xffffffffu, incl, 31);
       }
       __syncwarp();
-      {
+      if (!(flags & 1)) {
         int nq1 = 0;
         for (int e0 = 0; e0 < nq; e0 += 32) {
           const int e = e0 + lane;
@@ -607,7 +615,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
           int i = 0;
           if (e < nq) {
             i = queue[e];
-            pass = fast_bound4(tile + ((i >> 6) + 3) * tp + ((i & 63) + 3), tp, K) != 0u;
+            pass = fast_bound4(tile + ((i >> 6) + 3) * tp + ((i & 63) + xoff), tp, K) != 0u;
           }
           const unsigned m = __ballot_sync(0xffffffffu, pass);   // every lane has read its entry by now
           __syncwarp();                                          // (memory ordering of the in-place compaction, for racecheck)
@@ -615,8 +623,8 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
           nq1 += __popc(m);
         }
         nq = nq1;
+        __syncwarp();
       }
-      __syncwarp();
       // ---- exact score of the queued pairs
       nh = 0;
       for (int e0 = 0; e0 < nq; e0 += 32) {
@@ -626,10 +634,10 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
           const int i = queue[e];
           r = i >> 6; x = i & 63;
           FastDiffs D;
-          fast_load_diffs(tile + (r + 3) * tp + (x + 3), tp, D);
+          fast_load_diffs(tile + (r + 3) * tp + (x + xoff), tp, D);
           const unsigned s2 = fast_exact(D);
           sLo = (int)(s2 & 0xffffu) - 256;
-          sHi = x + S < cw ? (int)(s2 >> 16) - 256 : 0;
+          sHi = r + R < ch ? (int)(s2 >> 16) - 256 : 0;
         }
         const bool hLo = sLo >= th, hHi = sHi >= th;
         const unsigned mLo = __ballot_sync(0xffffffffu, hLo), mHi = __ballot_sync(0xffffffffu, hHi);
@@ -639,67 +647,59 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
         }
         nh += __popc(mLo);
         if (hHi) {
-          sc[(r + 1) * sp + x + S + 1] = (u8)sHi;
-          hits[nh + __popc(mHi & ltmask)] = (unsigned short)((r << 6) | (x + S));
+          sc[(r + R + 1) * sp + x + 1] = (u8)sHi;
+          hits[nh + __popc(mHi & ltmask)] = (unsigned short)(((r + R) << 6) | x);
         }
         nh += __popc(mHi);
       }
       __syncwarp();
-      // ---- strict 3x3 maximum inside the cell (scores below th count as 0, as in cv::FAST)
-      bool found = false;
-      for (int e = lane; e < nh; e += 32) {
-        const int p = hits[e];
-        const int r = p >> 6, cx = p & 63;
-        const u8* q = sc + (r + 1) * sp + cx + 1;
-        const int s = q[0];
-        const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
-        if (s > m) {
-          hits[e] = (unsigned short)(p | 0x8000);
-          found = true;
+      // ---- strict 3x3 maximum inside the cell (scores below th count as 0, as in cv::FAST); every hit scores >= th
+      total = 0;
+      for (int e0 = 0; e0 < nh; e0 += 32) {
+        const int e = e0 + lane;
+        bool keep = false;
+        if (e < nh) {
+          const int p = hits[e];
+          const int r = p >> 6, cx = p & 63;
+          const u8* q = sc + (r + 1) * sp + cx + 1;
+          const int s = q[0];
+          const int m = max(max(max(q[-1], q[1]), max(q[-sp - 1], q[-sp])), max(max(q[-sp + 1], q[sp - 1]), max(q[sp], q[sp + 1])));
+          keep = s > m;
+          if (keep) hits[e] = (unsigned short)(p | 0x8000);
         }
+        total += __popc(__ballot_sync(0xffffffffu, keep));
       }
-      if (__any_sync(0xffffffffu, found) || th == g.minTh) break;
+      if (total > 0 || th == g.minTh) break;
       th = g.minTh;   // nothing at iniTh: redo the cell at minTh (the scores already written stay valid)
       __syncwarp();
     }
-    // ---- emit: count, reserve with one atomic, write
+    // ---- emit: reserve with one atomic, write; give the score plane back all zero
     const LevelGeom& L = g.lv[cur.l];
-    int* cnt = candCount + cur.f * g.nlevels + cur.l;
+    int basei = 0;
+    if (total > 0) {
+      if (lane == 0) basei = atomicAdd(candCount + cur.f * g.nlevels + cur.l, total);
+      basei = __shfl_sync(0xffffffffu, basei, 0);
+    }
     uint2* out = cand + (size_t)cur.f * candTotal + L.candOff;
-    int total = 0;
-    for (int e0 = 0; e0 < nh; e0 += 32) {   // pass 1: count survivors
+    for (int e0 = 0; e0 < nh; e0 += 32) {
       const int e = e0 + lane;
       bool keep = false;
+      int r = 0, cx = 0, s = 0;
       if (e < nh) {
         const int p = hits[e];
-        if (p & 0x8000) keep = sc[(((p >> 6) & 0x1ff) + 1) * sp + (p & 63) + 1] >= th;
+        r = (p >> 6) & 0x1ff; cx = p & 63;
+        u8* q = sc + (r + 1) * sp + cx + 1;
+        s = *q;
+        keep = (p & 0x8000) != 0;
       }
-      total += __popc(__ballot_sync(0xffffffffu, keep));
-    }
-    if (total > 0) {
-      int basei = 0;
-      if (lane == 0) basei = atomicAdd(cnt, total);
-      basei = __shfl_sync(0xffffffffu, basei, 0);
-      int done = 0;
-      for (int e0 = 0; e0 < nh; e0 += 32) {   // pass 2: write
-        const int e = e0 + lane;
-        bool keep = false;
-        int r = 0, cx = 0, s = 0;
-        if (e < nh) {
-          const int p = hits[e];
-          if (p & 0x8000) {
-            r = (p >> 6) & 0x1ff; cx = p & 63;
-            s = sc[(r + 1) * sp + cx + 1];
-            keep = s >= th;
-          }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-          const int idx = basei + done + __popc(m & ltmask);
-          if (idx < L.candCap) out[idx] = make_uint2((unsigned)(cur.x0 + cx) | ((unsigned)(cur.y0 + r) << 16), (unsigned)s);
-        }
-        done += __popc(m);
+      __syncwarp();   // all scores of the batch are read before any is cleared (a position appears once)
+      if (e < nh) sc[(r + 1) * sp + cx + 1] = 0;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int idx = basei + __popc(m & ltmask);
+        if (idx < L.candCap) out[idx] = make_uint2((unsigned)(cur.x0 + cx) | ((unsigned)(cur.y0 + r) << 16), (unsigned)s);
       }
+      basei += __popc(m);
     }
     __syncwarp();
   }
@@ -1810,7 +1810,7 @@ struct orb_extractor {
   cudaEvent_t evL0Go[2] = {nullptr, nullptr}, evL0Done[2] = {nullptr, nullptr};
   // staging for the host entry points: two sets, so that the H2D copy of chunk i+1 and the D2H
   // copy of chunk i-1 overlap the kernels of chunk i (copy streams + events)
-  int fastTailRun = kFastTailRun, fastTailMul = 1;
+  int fastTailRun = kFastTailRun, fastTailMul = 1, fastFlags = 1;   // bit 0: skip the 8-pixel prefilter (measured: -5 % FAST)
   u8* d_in[2] = {nullptr, nullptr}; size_t d_inBytes = 0;
   orb_keypoint* d_kps[2] = {nullptr, nullptr}; u8* d_desc[2] = {nullptr, nullptr}; int* d_n[2] = {nullptr, nullptr};
   int stageFrames = 0, stageCap = 0;
@@ -1958,12 +1958,12 @@ int build_geom(orb_extractor* e, int W, int H) {
   e->maxKp = maxKp;
   {
     if (maxCw > 60 || maxCh > 60) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell larger than 60 px");
-    const int S = (maxCw + 1) / 2;
+    const int Rm = (maxCh + 1) / 2;                              // pair distance of the tallest cell
     FastSmemLayout& y = e->fastLay;
-    y.rawPitchWords = 2 * ((7 + maxCw + 6 + 7) / 8);   // 8-byte chunks
+    y.rawPitchWords = 4 * ((15 + maxCw + 6 + 15) / 16);          // 16-byte chunks
     y.rawBytes = round_up(y.rawPitchWords * 4 * (maxCh + 6), 16);
-    y.tileBytes = round_up(4 * (S + 6) * (maxCh + 6), 16);
-    y.hitsBytes = round_up(2 * (2 * S * maxCh), 16);   // hits + queue share it (see k_fast_cells)
+    y.tileBytes = round_up(4 * ((3 + maxCw + 6 + 3) & ~3) * (Rm + 6), 16);
+    y.hitsBytes = round_up(2 * (2 * Rm * maxCw), 16);            // hits + queue share it (see k_fast_cells)
     y.scBytes = round_up((maxCw + 2) * (maxCh + 2) + 4, 16);
     y.total = y.rawBytes + y.tileBytes + y.hitsBytes + y.scBytes;
     // warps per CTA: maximise resident warps per SM under 227 KB (1 KB reserved per CTA)
@@ -1972,6 +1972,7 @@ int build_geom(orb_extractor* e, int W, int H) {
     if (const char* ev = getenv("ORB_B200_FAST_WARPS")) maxW = std::max(1, std::min(kFastWarps, atoi(ev)));
     if (const char* ev = getenv("ORB_B200_FAST_TAIL_RUN")) e->fastTailRun = std::max(1, std::min(kFastRun, atoi(ev)));
     if (const char* ev = getenv("ORB_B200_FAST_TAIL_MUL")) e->fastTailMul = std::max(0, std::min(64, atoi(ev)));
+    if (const char* ev = getenv("ORB_B200_FAST_FLAGS")) e->fastFlags = atoi(ev);
     for (int w = 1; w <= maxW; w++) {
       const long long perCta = (long long)y.total * w + 1024;
       const int resident = (int)std::min<long long>(32, (227 * 1024) / perCta) * w;
@@ -2185,7 +2186,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     const int nItems = g.totalCells * B;
     const int blocks = std::min(e->fastBlocks, (nItems + e->fastWarps - 1) / e->fastWarps);
     k_fast_cells<<<blocks, 32 * e->fastWarps, e->fastSmem, s>>>(g, W.pyr, e->pyrStride, W.cand, W.candCount,
-                                                          e->candTotal, nItems, e->fastLay, W.work, e->fastTailRun, e->fastTailMul);
+                                                          e->candTotal, nItems, e->fastLay, W.work, e->fastTailRun, e->fastTailMul, e->fastFlags);
   }
   launches++;
   if ((st = stage_mark(e, s))) return st;
