@@ -316,6 +316,205 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
 }
 
 // ------------------------------------------------------------------------------------------
+// Pyramid, second form (the default): no divergent edge paths inside a warp, and the resize as a separable
+// shared-memory tile kernel.
+// ------------------------------------------------------------------------------------------
+// Level 0 (copyMakeBorder :1716). The 16-byte groups of a bordered row are of two kinds: interior groups (an aligned
+// window of the source row, 5 word loads + funnel shifts) and the few groups at either end that hold mirrored or padding
+// bytes (byte loads). Mixed in one warp the long edge path used to run beside 30 idle lanes in two warps of three
+// (11.8 of 32 lanes active); here a warp does ONE kind: blocks [0, nbInt) copy interior groups, one warp per bordered
+// row, the remaining blocks do the edge groups, 4 rows x 8 groups per warp.
+__global__ void __launch_bounds__(256) k_level0_border2(const Geom g, const u8* __restrict__ img, size_t step,
+                                                        size_t frameStride, u8* __restrict__ pyr, size_t pyrStride,
+                                                        int nbInt) {
+  const LevelGeom& L = g.lv[0];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = blockIdx.y;
+  const int rows = L.h + 2 * kEdge, groups = L.pitch >> 4;
+  const int gA = 3, gB = max(gA, (L.w - 20) / 16 + 3);          // interior groups: 16 <= c0 and c0 + 20 <= w
+  const u8* src = img + (size_t)f * frameStride;
+  u8* dstBase = pyr + (size_t)f * pyrStride + L.off - (long long)kEdge * L.pitch - kLeftPad;
+  if ((int)blockIdx.x < nbInt) {
+    const int by = blockIdx.x * 8 + wid;
+    if (by >= rows) return;
+    const u8* row = src + (size_t)reflect101(by - kEdge, L.h) * step;
+    u8* dst = dstBase + (long long)by * L.pitch;
+    for (int gi = gA + lane; gi < gB; gi += 32) {
+      const size_t addr = reinterpret_cast<size_t>(row + 16 * (gi - 2));
+      const unsigned* wp = reinterpret_cast<const unsigned*>(addr & ~(size_t)3);
+      const unsigned sh = (unsigned)(addr & 3) * 8;
+      const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+      uint4 out;
+      out.x = __funnelshift_r(w0, w1, sh);
+      out.y = __funnelshift_r(w1, w2, sh);
+      out.z = __funnelshift_r(w2, w3, sh);
+      out.w = __funnelshift_r(w3, w4, sh);
+      *reinterpret_cast<uint4*>(dst + 16 * gi) = out;
+    }
+  } else {
+    const int nEdge = gA + (groups - gB);                        // <= 8 for every supported width (checked by the host)
+    const int by = (((int)blockIdx.x - nbInt) * 8 + wid) * 4 + (lane >> 3);
+    const int k = lane & 7;
+    if (by >= rows || k >= nEdge) return;
+    const int gi = k < gA ? k : gB + (k - gA);
+    const int c0 = 16 * (gi - 2);
+    const u8* row = src + (size_t)reflect101(by - kEdge, L.h) * step;
+    unsigned v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      unsigned acc = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int x = min(max(reflect101(c0 + 4 * q + j, L.w), 0), L.w - 1);
+        acc |= (unsigned)__ldg(row + x) << (8 * j);
+      }
+      v[q] = acc;
+    }
+    *reinterpret_cast<uint4*>(dstBase + (long long)by * L.pitch + 16 * gi) = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// Level l > 0, interior pixels (resize :1677): a thread owns 4 output columns - their taps, the byte selectors and the
+// shift of its 8-byte source window stay in registers - and walks DOWN the source rows of a band of output rows. Every
+// source row is filtered horizontally exactly once per band ((c0*p[sx] + c1*p[sx+1]) >> 4: 3 aligned words, 2 funnel
+// shifts, PRMT + IDP.2A + shift per pixel), the previous row's result stays in registers, and an output row is emitted
+// when its second source row has arrived (2 IMAD.HI + add + shift per pixel, 3 PRMT pack the word, one aligned STG.32).
+// The next row's words are requested before the current one is used. No shared memory, no barrier, no divergence: all
+// control flow depends on the row only. (The first-round kernel re-filtered 6 source rows per 4x4 block at 20-24 of 32
+// lanes: ~46 thread instructions per pixel; a shared-memory tile version measured slower still - its per-tile set-up
+// and store pass are amortised over only 8 pixels per thread.) The border is written afterwards by k_fill_borders.
+// Per band the warp keeps the rows' vertical taps in registers (lane i: output row j0+i) and a 64-bit mask of the source
+// rows after which an output row is due, so the row loop has a fixed trip count, one predictable branch and no global
+// loads besides the pixels. Output rows use strictly increasing source rows (scale factor > 1; checked by the host).
+constexpr int kRzThreads = 64, kRzBand = 32;
+__global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
+                                                             const int2* __restrict__ taps, int bandRows) {
+  const LevelGeom& D = g.lv[l];
+  const LevelGeom& S = g.lv[l - 1];
+  const int lane = threadIdx.x & 31;
+  const int cFirst = 4 * (blockIdx.x * kRzThreads + (threadIdx.x & ~31));   // first column of this warp
+  const int j0 = blockIdx.y * bandRows, j1 = min(j0 + bandRows, D.h);
+  if (cFirst >= D.w || j0 >= j1) return;                                    // warp-uniform
+  const int f = blockIdx.z;
+  const int cMine = cFirst + 4 * lane;
+  const bool active = cMine < D.w;
+  const int c0 = active ? cMine : ((D.w - 1) & ~3);                         // idle lanes shadow the last column group
+  int2 tx[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) tx[j] = __ldg(taps + D.tapX + min(c0 + j, D.w - 1));
+  const int a0 = kLeftPad + tx[0].x;                               // byte offset of the window inside a bordered source row
+  const unsigned sh = (unsigned)(a0 & 3) * 8;
+  unsigned sel[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) sel[j] = (unsigned)(tx[j].x - tx[0].x) * 0x11u + 0x10u;   // bytes (d, d+1) of the window
+  // vertical taps of the band: lane i holds row j0+i
+  const bool rowValid = j0 + lane < j1;
+  const int2 tyMine = __ldg(taps + D.tapY + min(j0 + lane, j1 - 1));
+  const int r0 = __shfl_sync(0xffffffffu, tyMine.x, 0);            // first source row of the band
+  const int ds = tyMine.x - r0;                                    // < 64 for bands of <= 32 rows (scale factor < 2)
+  const unsigned mlo = __reduce_or_sync(0xffffffffu, rowValid && ds < 32 ? 1u << ds : 0u);
+  const unsigned mhi = __reduce_or_sync(0xffffffffu, rowValid && ds >= 32 ? 1u << (ds - 32) : 0u);
+  unsigned long long due = (unsigned long long)mlo | ((unsigned long long)mhi << 32);   // bit t: a row starts at r0+t
+  const int nIter = __shfl_sync(0xffffffffu, ds, j1 - 1 - j0) + 1; // source rows r0+1 .. r0+nIter are filtered in the loop
+  const int spw = S.pitch >> 2, dpw = D.pitch >> 2;
+  const int lastRow = S.h - 1;
+  const unsigned* q = reinterpret_cast<const unsigned*>(pyr + (size_t)f * pyrStride + S.off - kLeftPad) + (a0 >> 2) +
+                      (long long)r0 * spw;
+  unsigned* dp = reinterpret_cast<unsigned*>(pyr + (size_t)f * pyrStride + D.off + (long long)j0 * D.pitch + c0);
+
+  unsigned hc[4], hn[4];
+  {
+    const unsigned lo = __funnelshift_r(q[0], q[1], sh), hi = __funnelshift_r(q[1], q[2], sh);
+#pragma unroll
+    for (int j = 0; j < 4; j++) hc[j] = __dp2a_lo((unsigned)tx[j].y, __byte_perm(lo, hi, sel[j]), 0u) >> 4;
+  }
+  int r = r0;                                                      // source row held in hc
+  if (r < lastRow) q += spw;                                       // the bottom row is its own successor (:A.2 clamp)
+  unsigned u0 = q[0], u1 = q[1], u2 = q[2];
+  int jj = 0;
+#pragma unroll 2
+  for (int t = 0; t < nIter; t++) {
+    {
+      const unsigned lo = __funnelshift_r(u0, u1, sh), hi = __funnelshift_r(u1, u2, sh);
+#pragma unroll
+      for (int j = 0; j < 4; j++) hn[j] = __dp2a_lo((unsigned)tx[j].y, __byte_perm(lo, hi, sel[j]), 0u) >> 4;
+    }
+    r++;
+    if (r < lastRow) q += spw;                                     // request the row after it now
+    u0 = q[0]; u1 = q[1]; u2 = q[2];
+    if ((unsigned)due & 1u) {                                      // an output row uses (hc, hn); warp-uniform
+      const unsigned cy = (unsigned)__shfl_sync(0xffffffffu, tyMine.y, jj);
+      // ((cy*(h>>4))>>16) == umulhi(cy<<16, h>>4); the sum is <= 1020, so the result needs no clamp
+      const unsigned cy0s = cy << 16, cy1s = cy & 0xffff0000u;
+      unsigned v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = (__umulhi(cy0s, hc[k]) + __umulhi(cy1s, hn[k]) + 2u) >> 2;
+      if (active) *dp = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+      dp += dpw;
+      jj++;
+    }
+    due >>= 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) hc[k] = hn[k];
+  }
+}
+
+// Border of levels 1.. (copyMakeBorder(REFLECT_101) :1695), one launch for all of them after the interiors are written.
+// Same split as k_level0_border2, so that a warp does one kind of work: part A = the 38 top / bottom rows, interior groups
+// (aligned 16-byte copies of the mirrored interior row); part B = the edge groups of every row (byte gathers).
+struct BorderJobs { int base[kMaxLevels + 1]; int nbA[kMaxLevels]; };   // first block of every level; blocks of its part A
+
+__global__ void __launch_bounds__(256) k_fill_borders(const Geom g, u8* __restrict__ pyr, size_t pyrStride, const BorderJobs jobs) {
+  int l = 1;
+#pragma unroll 1
+  while (l + 1 < g.nlevels && (int)blockIdx.x >= jobs.base[l + 1]) l++;
+  const LevelGeom& L = g.lv[l];
+  const int blk = blockIdx.x - jobs.base[l];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rows = L.h + 2 * kEdge, groups = L.pitch >> 4;
+  const int gA = 2, gB = max(gA, L.w / 16 + 2);                  // interior groups: columns 16(g-2) .. 16(g-2)+15 inside [0, w)
+  u8* plane = pyr + (size_t)blockIdx.y * pyrStride + L.off - kLeftPad;   // byte 0 of interior row 0
+  if (blk < jobs.nbA[l]) {
+    const int k = blk * 8 + wid;                                  // 0..37: top rows, then bottom rows
+    if (k >= 2 * kEdge) return;
+    const int by = k < kEdge ? k : L.h + k;                       // bordered row
+    const uint4* srow = reinterpret_cast<const uint4*>(plane + (long long)reflect101(by - kEdge, L.h) * L.pitch);
+    uint4* drow = reinterpret_cast<uint4*>(plane + (long long)(by - kEdge) * L.pitch);
+    for (int gi = gA + lane; gi < gB; gi += 32) drow[gi] = srow[gi];
+  } else {
+    const int nEdge = gA + (groups - gB);                         // <= 8 (checked by the host)
+    const int by = ((blk - jobs.nbA[l]) * 8 + wid) * 4 + (lane >> 3);
+    const int k = lane & 7;
+    if (by >= rows || k >= nEdge) return;
+    const int gi = k < gA ? k : gB + (k - gA);
+    const int c0 = 16 * (gi - 2);
+    const u8* row = plane + (long long)reflect101(by - kEdge, L.h) * L.pitch + kLeftPad;   // interior column 0 (16-byte aligned)
+    const unsigned* row32 = reinterpret_cast<const unsigned*>(row);
+    unsigned v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int cw = c0 + 4 * q;                                   // a multiple of 4: a word never straddles column 0
+      unsigned word = 0;                                            // bytes outside the bordered image are row padding
+      if (cw + 3 < 0) {                                             // left border: columns s+3 .. s reversed, s = -cw-3 = 1 (mod 4)
+        const int s = -cw - 3;
+        if (cw + 3 >= -kEdge) word = __byte_perm(row32[(s - 1) >> 2], row32[(s + 3) >> 2], 0x1234);
+      } else if (cw + 3 <= L.w - 1) {                               // interior
+        word = row32[cw >> 2];
+      } else if (cw >= L.w) {                                       // right border: columns s+3 .. s reversed, s = 2(w-1)-cw-3
+        const int s = 2 * (L.w - 1) - cw - 3;
+        if (cw <= L.w + kEdge - 1 && s >= 0)
+          word = __byte_perm(row32[s >> 2], row32[(s >> 2) + 1], 0x0123u + 0x1111u * (unsigned)(s & 3));
+      } else {                                                      // the word that holds column w-1
+#pragma unroll
+        for (int j = 0; j < 4; j++) word |= (unsigned)row[reflect101(cw + j, L.w)] << (8 * j);
+      }
+      v[q] = word;
+    }
+    *reinterpret_cast<uint4*>(plane + (long long)(by - kEdge) * L.pitch + 16 * gi) = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // FAST-9/16 per 30-px cell with iniTh/minTh fallback
 // ------------------------------------------------------------------------------------------
 // Score S(p) = largest threshold for which p is still a FAST-9 corner
@@ -1775,6 +1974,9 @@ struct orb_extractor {
   int candTotal = 0, keptTotal = 0, nodeCap = 0, maxKp = 0;
   size_t fastSmem = 0, qtSmem = 0;
   FastSmemLayout fastLay;
+  BorderJobs borderJobs = {};    // block ranges of k_fill_borders
+  int borderBlocks = 0;
+  bool pyrTiled = true;          // k_level0_border2 + k_resize_strip + k_fill_borders (ORB_B200_PYR=0: the first-round kernels)
   int fastBlocks = 0, fastWarps = 4;
   std::vector<int2> taps;
 
@@ -1982,6 +2184,38 @@ int build_geom(orb_extractor* e, int W, int H) {
     e->fastWarps = bestW;
     e->fastSmem = (size_t)y.total * bestW;
   }
+  {
+    // k_resize_strip: the 4 columns of a thread must read one 8-byte source window (scale factor < ~1.7)
+    bool ok = true;
+    if (const char* ev = getenv("ORB_B200_PYR")) ok = atoi(ev) != 0;
+    for (int l = 1; l < nl && ok; l++) {
+      const LevelGeom& D = g.lv[l];
+      const int2* tX = e->taps.data() + D.tapX;
+      for (int c = 0; c < D.w; c += 4)
+        if (tX[std::min(c + 3, D.w - 1)].x + 1 - tX[c].x > 7) ok = false;
+      // ... and output rows must start at strictly increasing source rows, at most 63 rows apart within a band
+      const int2* tY = e->taps.data() + D.tapY;
+      for (int j = 1; j < D.h; j++)
+        if (tY[j].x <= tY[j - 1].x) ok = false;
+      for (int j = 0; j < D.h; j += kRzBand)
+        if (tY[std::min(j + kRzBand, D.h) - 1].x - tY[j].x > 63) ok = false;
+    }
+    // k_level0_border2 / k_fill_borders: at most 8 edge groups per bordered row
+    const int groups0 = g.lv[0].pitch >> 4, gB0 = std::max(3, (g.lv[0].w - 20) / 16 + 3);
+    if (3 + (groups0 - gB0) > 8) ok = false;
+    int blocks = 0;
+    for (int l = 1; l < nl; l++) {
+      const LevelGeom& L = g.lv[l];
+      if (2 + ((L.pitch >> 4) - std::max(2, L.w / 16 + 2)) > 8) ok = false;
+      e->borderJobs.base[l] = blocks;
+      e->borderJobs.nbA[l] = (2 * kEdge + 7) / 8;
+      blocks += e->borderJobs.nbA[l] + (L.h + 2 * kEdge + 31) / 32;
+    }
+    e->borderJobs.base[0] = 0;
+    e->borderJobs.base[nl] = blocks;
+    e->borderBlocks = blocks;
+    e->pyrTiled = ok;
+  }
   e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8) + (size_t)kQtSmemKeys * 6;
   if (e->qtSmem > 220 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "features per level too large for the quadtree kernel's shared memory");
   if (e->fastSmem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
@@ -2151,7 +2385,26 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   const int nl = g.nlevels;
   int launches = 0, st;
   if ((st = stage_mark(e, s))) return st;
-  const bool l0fork = !e->profile && e->l0Fork && nl > 1;
+  const bool l0fork = !e->pyrTiled && !e->profile && e->l0Fork && nl > 1;
+  if (e->pyrTiled) {
+    const LevelGeom& L0 = g.lv[0];
+    const int rows0 = L0.h + 2 * kEdge;
+    const int nbInt = (rows0 + 7) / 8, nbEdge = (rows0 + 31) / 32;
+    k_level0_border2<<<dim3(nbInt + nbEdge, B), 256, 0, s>>>(g, d_img, step, frameStride, W.pyr, e->pyrStride, nbInt);
+    launches++;
+    // few frames (the per-frame drop-in call): short bands so that a level still fills the machine
+    const int bandRows = B >= 8 ? kRzBand : 4;
+    for (int l = 1; l < nl; l++) {
+      const LevelGeom& L = g.lv[l];
+      dim3 grid(((L.w + 3) / 4 + kRzThreads - 1) / kRzThreads, (L.h + bandRows - 1) / bandRows, B);
+      k_resize_strip<<<grid, kRzThreads, 0, s>>>(g, l, W.pyr, e->pyrStride, e->d_taps, bandRows);
+      launches++;
+    }
+    if (nl > 1) {
+      k_fill_borders<<<dim3(e->borderBlocks, B), 256, 0, s>>>(g, W.pyr, e->pyrStride, e->borderJobs);
+      launches++;
+    }
+  } else {
   {
     const LevelGeom& L = g.lv[0];
     dim3 grid((L.pitch / 16 + 31) / 32, (L.h + 2 * kEdge + 7) / 8, B);
@@ -2173,6 +2426,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     launches++;
   }
   if (l0fork) ORB_CUDA(cudaStreamWaitEvent(s, e->evL0Done[lane], 0));
+  }
   const int fork = e->profile ? 0 : e->blurFork;
   cudaStream_t bs = fork ? e->blurStream[lane] : s;
   if (fork == 1) {
@@ -2220,7 +2474,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   if ((st = stage_mark(e, s))) return st;
   ORB_CUDA(cudaGetLastError());
   if (e->profile) {
-    e->stageLaunches[0] += nl; e->stageLaunches[1]++; e->stageLaunches[2]++; e->stageLaunches[3]++; e->stageLaunches[4]++;
+    e->stageLaunches[0] += e->pyrTiled && nl > 1 ? nl + 1 : nl; e->stageLaunches[1]++; e->stageLaunches[2]++; e->stageLaunches[3]++; e->stageLaunches[4]++;
   }
   e->lastLaunches += launches;
   e->lastChunkFrames = B;
