@@ -392,21 +392,25 @@ __global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l
   const LevelGeom& D = g.lv[l];
   const LevelGeom& S = g.lv[l - 1];
   const int lane = threadIdx.x & 31;
-  const int cFirst = 4 * (blockIdx.x * kRzThreads + (threadIdx.x & ~31));   // first column of this warp
+  // column groups cover the BORDERED width: columns -20 .. w+18 in aligned words; a border column takes the taps of the
+  // interior column it mirrors (REFLECT_101), so the left / right border of an interior row costs ~10 extra groups per row
+  const int cLast = ((D.w + kEdge - 1 + 20) & ~3) - 20;                     // first column of the last group
+  const int cFirst = 4 * (blockIdx.x * kRzThreads + (threadIdx.x & ~31)) - 20;   // first column of this warp
   const int j0 = blockIdx.y * bandRows, j1 = min(j0 + bandRows, D.h);
-  if (cFirst >= D.w || j0 >= j1) return;                                    // warp-uniform
+  if (cFirst > cLast || j0 >= j1) return;                                   // warp-uniform
   const int f = blockIdx.z;
   const int cMine = cFirst + 4 * lane;
-  const bool active = cMine < D.w;
-  const int c0 = active ? cMine : ((D.w - 1) & ~3);                         // idle lanes shadow the last column group
+  const bool active = cMine <= cLast;
+  const int c0 = active ? cMine : cLast;                                    // idle lanes shadow the last column group
   int2 tx[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) tx[j] = __ldg(taps + D.tapX + min(c0 + j, D.w - 1));
-  const int a0 = kLeftPad + tx[0].x;                               // byte offset of the window inside a bordered source row
+  for (int j = 0; j < 4; j++) tx[j] = __ldg(taps + D.tapX + reflect101(min(max(c0 + j, -kEdge), D.w + kEdge - 1), D.w));
+  const int sxMin = min(min(tx[0].x, tx[1].x), min(tx[2].x, tx[3].x));
+  const int a0 = kLeftPad + sxMin;                                 // byte offset of the window inside a bordered source row
   const unsigned sh = (unsigned)(a0 & 3) * 8;
   unsigned sel[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) sel[j] = (unsigned)(tx[j].x - tx[0].x) * 0x11u + 0x10u;   // bytes (d, d+1) of the window
+  for (int j = 0; j < 4; j++) sel[j] = (unsigned)(tx[j].x - sxMin) * 0x11u + 0x10u;   // bytes (d, d+1) of the window
   // vertical taps of the band: lane i holds row j0+i
   const bool rowValid = j0 + lane < j1;
   const int2 tyMine = __ldg(taps + D.tapY + min(j0 + lane, j1 - 1));
@@ -444,11 +448,13 @@ __global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l
     u0 = q[0]; u1 = q[1]; u2 = q[2];
     if ((unsigned)due & 1u) {                                      // an output row uses (hc, hn); warp-uniform
       const unsigned cy = (unsigned)__shfl_sync(0xffffffffu, tyMine.y, jj);
-      // ((cy*(h>>4))>>16) == umulhi(cy<<16, h>>4); the sum is <= 1020, so the result needs no clamp
-      const unsigned cy0s = cy << 16, cy1s = cy & 0xffff0000u;
+      // (((cy0*h0)>>16) + ((cy1*h1)>>16) + 2) >> 2 with plain 32-bit multiplies (cy*h < 2^27; IMAD.HI is slow): the +2 rides
+      // on the first product as 2<<16, a 16x2 SIMD add sums the two upper halves without the carry of the lower halves,
+      // and the result (<= 255, no clamp needed) sits at bit 18
+      const unsigned cy0 = cy & 0xffffu, cy1 = cy >> 16;
       unsigned v[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) v[k] = (__umulhi(cy0s, hc[k]) + __umulhi(cy1s, hn[k]) + 2u) >> 2;
+      for (int k = 0; k < 4; k++) v[k] = __vadd2(cy0 * hc[k] + 0x20000u, cy1 * hn[k]) >> 18;
       if (active) *dp = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
       dp += dpw;
       jj++;
@@ -459,59 +465,24 @@ __global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l
   }
 }
 
-// Border of levels 1.. (copyMakeBorder(REFLECT_101) :1695), one launch for all of them after the interiors are written.
-// Same split as k_level0_border2, so that a warp does one kind of work: part A = the 38 top / bottom rows, interior groups
-// (aligned 16-byte copies of the mirrored interior row); part B = the edge groups of every row (byte gathers).
-struct BorderJobs { int base[kMaxLevels + 1]; int nbA[kMaxLevels]; };   // first block of every level; blocks of its part A
+// Top / bottom border rows of levels 1.. (copyMakeBorder(REFLECT_101) :1695): the strips have written every interior row
+// over the whole bordered width, so a border row is an aligned 16-byte copy of the interior row it mirrors. One launch for
+// all levels, one warp per row.
+struct BorderJobs { int base[kMaxLevels + 1]; };   // first block of every level (5 blocks of 8 rows each)
 
 __global__ void __launch_bounds__(256) k_fill_borders(const Geom g, u8* __restrict__ pyr, size_t pyrStride, const BorderJobs jobs) {
   int l = 1;
 #pragma unroll 1
   while (l + 1 < g.nlevels && (int)blockIdx.x >= jobs.base[l + 1]) l++;
   const LevelGeom& L = g.lv[l];
-  const int blk = blockIdx.x - jobs.base[l];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int rows = L.h + 2 * kEdge, groups = L.pitch >> 4;
-  const int gA = 2, gB = max(gA, L.w / 16 + 2);                  // interior groups: columns 16(g-2) .. 16(g-2)+15 inside [0, w)
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x - jobs.base[l]) * 8 + (threadIdx.x >> 5);   // 0..37: top rows, then bottom rows
+  if (k >= 2 * kEdge) return;
+  const int by = k < kEdge ? k : L.h + k;                         // bordered row
   u8* plane = pyr + (size_t)blockIdx.y * pyrStride + L.off - kLeftPad;   // byte 0 of interior row 0
-  if (blk < jobs.nbA[l]) {
-    const int k = blk * 8 + wid;                                  // 0..37: top rows, then bottom rows
-    if (k >= 2 * kEdge) return;
-    const int by = k < kEdge ? k : L.h + k;                       // bordered row
-    const uint4* srow = reinterpret_cast<const uint4*>(plane + (long long)reflect101(by - kEdge, L.h) * L.pitch);
-    uint4* drow = reinterpret_cast<uint4*>(plane + (long long)(by - kEdge) * L.pitch);
-    for (int gi = gA + lane; gi < gB; gi += 32) drow[gi] = srow[gi];
-  } else {
-    const int nEdge = gA + (groups - gB);                         // <= 8 (checked by the host)
-    const int by = ((blk - jobs.nbA[l]) * 8 + wid) * 4 + (lane >> 3);
-    const int k = lane & 7;
-    if (by >= rows || k >= nEdge) return;
-    const int gi = k < gA ? k : gB + (k - gA);
-    const int c0 = 16 * (gi - 2);
-    const u8* row = plane + (long long)reflect101(by - kEdge, L.h) * L.pitch + kLeftPad;   // interior column 0 (16-byte aligned)
-    const unsigned* row32 = reinterpret_cast<const unsigned*>(row);
-    unsigned v[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int cw = c0 + 4 * q;                                   // a multiple of 4: a word never straddles column 0
-      unsigned word = 0;                                            // bytes outside the bordered image are row padding
-      if (cw + 3 < 0) {                                             // left border: columns s+3 .. s reversed, s = -cw-3 = 1 (mod 4)
-        const int s = -cw - 3;
-        if (cw + 3 >= -kEdge) word = __byte_perm(row32[(s - 1) >> 2], row32[(s + 3) >> 2], 0x1234);
-      } else if (cw + 3 <= L.w - 1) {                               // interior
-        word = row32[cw >> 2];
-      } else if (cw >= L.w) {                                       // right border: columns s+3 .. s reversed, s = 2(w-1)-cw-3
-        const int s = 2 * (L.w - 1) - cw - 3;
-        if (cw <= L.w + kEdge - 1 && s >= 0)
-          word = __byte_perm(row32[s >> 2], row32[(s >> 2) + 1], 0x0123u + 0x1111u * (unsigned)(s & 3));
-      } else {                                                      // the word that holds column w-1
-#pragma unroll
-        for (int j = 0; j < 4; j++) word |= (unsigned)row[reflect101(cw + j, L.w)] << (8 * j);
-      }
-      v[q] = word;
-    }
-    *reinterpret_cast<uint4*>(plane + (long long)(by - kEdge) * L.pitch + 16 * gi) = make_uint4(v[0], v[1], v[2], v[3]);
-  }
+  const uint4* srow = reinterpret_cast<const uint4*>(plane + (long long)reflect101(by - kEdge, L.h) * L.pitch);
+  uint4* drow = reinterpret_cast<uint4*>(plane + (long long)(by - kEdge) * L.pitch);
+  for (int gi = lane; gi < (L.pitch >> 4); gi += 32) drow[gi] = srow[gi];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2191,8 +2162,15 @@ int build_geom(orb_extractor* e, int W, int H) {
     for (int l = 1; l < nl && ok; l++) {
       const LevelGeom& D = g.lv[l];
       const int2* tX = e->taps.data() + D.tapX;
-      for (int c = 0; c < D.w; c += 4)
-        if (tX[std::min(c + 3, D.w - 1)].x + 1 - tX[c].x > 7) ok = false;
+      auto refl = [](int p, int n) { p = p < 0 ? -p : p; return p >= n ? 2 * (n - 1) - p : p; };
+      for (int c = -20; c <= D.w + kEdge - 1; c += 4) {          // every aligned word of the bordered width
+        int lo = 1 << 30, hi = -1;
+        for (int j = 0; j < 4; j++) {
+          const int sx = tX[refl(std::min(std::max(c + j, -kEdge), D.w + kEdge - 1), D.w)].x;
+          lo = std::min(lo, sx); hi = std::max(hi, sx);
+        }
+        if (hi + 1 - lo > 7) ok = false;
+      }
       // ... and output rows must start at strictly increasing source rows, at most 63 rows apart within a band
       const int2* tY = e->taps.data() + D.tapY;
       for (int j = 1; j < D.h; j++)
@@ -2205,11 +2183,8 @@ int build_geom(orb_extractor* e, int W, int H) {
     if (3 + (groups0 - gB0) > 8) ok = false;
     int blocks = 0;
     for (int l = 1; l < nl; l++) {
-      const LevelGeom& L = g.lv[l];
-      if (2 + ((L.pitch >> 4) - std::max(2, L.w / 16 + 2)) > 8) ok = false;
       e->borderJobs.base[l] = blocks;
-      e->borderJobs.nbA[l] = (2 * kEdge + 7) / 8;
-      blocks += e->borderJobs.nbA[l] + (L.h + 2 * kEdge + 31) / 32;
+      blocks += (2 * kEdge + 7) / 8;
     }
     e->borderJobs.base[0] = 0;
     e->borderJobs.base[nl] = blocks;
@@ -2396,7 +2371,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     const int bandRows = B >= 8 ? kRzBand : 4;
     for (int l = 1; l < nl; l++) {
       const LevelGeom& L = g.lv[l];
-      dim3 grid(((L.w + 3) / 4 + kRzThreads - 1) / kRzThreads, (L.h + bandRows - 1) / bandRows, B);
+      dim3 grid(((L.w + kEdge - 1 + 20) / 4 + 1 + kRzThreads - 1) / kRzThreads, (L.h + bandRows - 1) / bandRows, B);
       k_resize_strip<<<grid, kRzThreads, 0, s>>>(g, l, W.pyr, e->pyrStride, e->d_taps, bandRows);
       launches++;
     }
