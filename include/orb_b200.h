@@ -122,6 +122,14 @@ int orb_extract_stereo(orb_extractor* h, const uint8_t* left, const uint8_t* rig
                        uint8_t* desc_left, orb_keypoint* kps_right, int* n_right, uint8_t* desc_right,
                        float* uright, float* depth);
 
+/* Frame::ComputeStereoMatches (src/Frame.cc:831-1082) for the reference's own call sequence: the stereo Frame constructor
+ * has run one orb_extract per eye on two handles (from two threads, src/Frame.cc:146-154) and joined them; the pyramids,
+ * keypoints and descriptors of both calls are still on the device. This call pairs them (the right eye's results are copied
+ * device-to-device into the left handle's second frame slot) and writes mvuRight / mvDepth for the left keypoints (-1 = no
+ * stereo match); *n_left (may be NULL) = number of left keypoints. Both handles: same device, parameters, image size and
+ * capacity; `left` created with max_batch >= 2; no other call on either handle in between. */
+int orb_stereo_match(orb_extractor* left, orb_extractor* right, float mbf, float mb, float* uright, float* depth, int* n_left);
+
 /* Same for `pairs` stereo pairs RESIDENT IN DEVICE MEMORY, frames interleaved L0,R0,L1,R1,...;
  * d_keypoints / d_descriptors / d_counts as in orb_extract_batch_device over 2*pairs frames,
  * d_uright / d_depth are pairs x capacity floats. Asynchronous on `stream`. */
@@ -259,6 +267,25 @@ int orb_match_pairs_device(orb_matcher* m, const uint8_t* d_descriptors, const f
 int orb_match_allpairs_device(orb_matcher* m, const uint8_t* d_all, int n_kf, int n_desc, int row_begin,
                               int row_end, int col_begin, int col_end, float nnratio, int32_t* d_counts,
                               void* stream);
+
+/* ---- multi-GPU entry of the all-pairs workload: the exchange over NCCL inside the library --------
+ * One process per GPU. NCCL is bound at run time (dlopen of libnccl.so.2), so single-GPU users never need it.
+ * orb_shard_range: contiguous block [begin, end) of `total` units for `rank` (blocks differ by at most one).
+ * orb_nccl_unique_id / orb_nccl_comm_create / orb_nccl_comm_destroy: ncclGetUniqueId (128 bytes; call on one rank and
+ * hand the bytes to the others by any means) / ncclCommInitRank / ncclCommDestroy, for hosts that do not have a
+ * communicator yet. A host that already owns an ncclComm_t of the same NCCL library passes it directly.
+ * orb_match_allpairs_nccl: rank's keyframes are rows [begin, end) = orb_shard_range(n_kf, rank, world); d_local_desc holds
+ * their descriptors ((end-begin) x n_desc x 32), d_all is n_kf x n_desc x 32 of device scratch that receives everyone's,
+ * d_counts the rank's (end-begin) x n_kf block of orb_match_allpairs_device. Every rank's block is broadcast
+ * (ncclBroadcast, root = owner) on a communication stream of the matcher; the all-pairs kernel runs on `stream` for the
+ * own block at once and for every peer block as soon as it has landed, so transfers overlap the compute. Asynchronous
+ * on `stream` (NULL = the matcher's own stream); all ranks must call it with the same n_kf / n_desc. */
+void orb_shard_range(int total, int rank, int world, int* begin, int* end);
+int orb_nccl_unique_id(void* id128);
+int orb_nccl_comm_create(int device, int rank, int world, const void* id128, void** comm);
+int orb_nccl_comm_destroy(void* comm);
+int orb_match_allpairs_nccl(orb_matcher* m, void* nccl_comm /* ncclComm_t */, int rank, int world, const uint8_t* d_local_desc,
+                            int n_kf, int n_desc, float nnratio, uint8_t* d_all, int32_t* d_counts, void* stream);
 
 /* Plain Hamming distance matrix (na x nb ints) on the device: parity aid for the kernels. */
 int orb_hamming_matrix_device(orb_matcher* m, const uint8_t* d_a, int na, const uint8_t* d_b, int nb,

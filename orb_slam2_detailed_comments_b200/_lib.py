@@ -71,13 +71,14 @@ class OrbMatchParams(C.Structure):
 EXPORTS = [
     "orb_last_error", "orb_device_count", "orb_create", "orb_destroy", "orb_get_scale_tables",
     "orb_max_keypoints", "orb_max_keypoints_for_size", "orb_extract", "orb_extract_batch_host", "orb_extract_batch_host_async", "orb_extract_batch_device",
-    "orb_extract_stereo", "orb_extract_stereo_batch_device",
+    "orb_extract_stereo", "orb_stereo_match", "orb_extract_stereo_batch_device",
     "orb_synchronize", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_times", "orb_set_lanes", "orb_stage_level_size", "orb_stage_copy_level",
     "orb_stage_copy_blur", "orb_stage_copy_candidates", "orb_stage_copy_kept",
     "orb_compute_image_bounds", "orb_undistort_keypoints_device", "orb_assign_features_to_grid_device",
     "orb_get_features_in_area_device",
     "orb_descriptor_distance", "orb_matcher_create", "orb_matcher_destroy",
     "orb_search_for_initialization", "orb_match_pairs_device", "orb_match_allpairs_device",
+    "orb_shard_range", "orb_nccl_unique_id", "orb_nccl_comm_create", "orb_nccl_comm_destroy", "orb_match_allpairs_nccl",
     "orb_hamming_matrix_device", "orb_matcher_synchronize", "orb_int_pipe_peak",
     "orb_search_scratch_bytes", "orb_project_last_frame_device", "orb_search_by_projection_device",
     "orb_search_by_bow_device", "orb_search_for_triangulation_device",
@@ -113,6 +114,7 @@ def lib():
         L.orb_extract_batch_host_async.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp]
         L.orb_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp, vp]
         L.orb_extract_stereo.argtypes = [vp, vp, vp, i32, i32, sz, f32, f32, vp, i32, C.POINTER(i32), vp, vp, C.POINTER(i32), vp, vp, vp]
+        L.orb_stereo_match.argtypes = [vp, vp, f32, f32, vp, vp, C.POINTER(i32)]
         L.orb_extract_stereo_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp, f32, f32, vp, vp, vp]
         L.orb_synchronize.argtypes = [vp, vp]
         L.orb_last_launch_count.argtypes = [vp]
@@ -135,6 +137,12 @@ def lib():
                                                     C.POINTER(OrbMatchParams), vp, vp, C.POINTER(i32), vp, vp]
         L.orb_match_pairs_device.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp, vp, vp]
         L.orb_match_allpairs_device.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp]
+        L.orb_shard_range.restype = None
+        L.orb_shard_range.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.orb_nccl_unique_id.argtypes = [vp]
+        L.orb_nccl_comm_create.argtypes = [i32, i32, i32, vp, C.POINTER(vp)]
+        L.orb_nccl_comm_destroy.argtypes = [vp]
+        L.orb_match_allpairs_nccl.argtypes = [vp, vp, i32, i32, vp, i32, i32, f32, vp, vp, vp]
         L.orb_hamming_matrix_device.argtypes = [vp, vp, i32, vp, i32, vp, vp]
         L.orb_matcher_synchronize.argtypes = [vp, vp]
         L.orb_int_pipe_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]

@@ -2008,6 +2008,9 @@ struct orb_extractor {
   float* d_invScale = nullptr;          // mvInvScaleFactor on the device (stereo refinement)
   float* d_uRight[2] = {nullptr, nullptr}; float* d_depth[2] = {nullptr, nullptr};  // host-path staging
   int stereoOutCap = 0;                 // floats allocated in d_uRight[0] / d_depth[0]
+  // the last orb_extract call's results are still on the device (pyramid in workspace frame 0, keypoints / descriptors /
+  // count in the first staging set): what orb_stereo_match pairs up (0 = nothing valid)
+  int singleCap = 0, singleW = 0, singleH = 0;
   // optional per-stage CUDA-event timing (bench roofline): 6 boundary events per chunk
   bool profile = false;
   std::vector<cudaEvent_t> evPool;
@@ -2779,6 +2782,7 @@ int orb_max_keypoints_for_size(const orb_extractor* e, int width, int height) {
 
 // The other entry points reuse the staging buffers without events: let asynchronous batches finish first.
 static int drain_async(orb_extractor* e) {
+  e->singleCap = 0;   // whatever runs next overwrites the single-call results
   if (!e->asyncPending) return ORB_OK;
   e->asyncPending = false;
   if (e->sIn) ORB_CUDA(cudaStreamSynchronize(e->sIn));
@@ -2875,6 +2879,7 @@ static int batch_host_impl(orb_extractor* e, const uint8_t* images, int batch, i
                            uint8_t* descriptors, bool wait) {
   if (!e || !images || !keypoints || !counts || !descriptors) ORB_FAIL(ORB_ERR_INVALID, "null argument");
   if (batch <= 0 || width <= 0 || height <= 0 || capacity <= 0 || step < (size_t)width) ORB_FAIL(ORB_ERR_INVALID, "bad size");
+  e->singleCap = 0;
   int st = ensure_geom(e, width, height, batch);
   if (st) return st;
   const int chunk = e->wsFrames;
@@ -2945,10 +2950,12 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
   if (!keypoints || !descriptors || capacity <= 0) ORB_FAIL(ORB_ERR_INVALID, "null output");
   int st = drain_async(e);
   if (st) return st;
-  st = ensure_geom(e, width, height, 1);
+  // a handle that may serve as the left eye of orb_stereo_match (max_batch >= 2) keeps a second frame slot
+  const int slots = e->maxBatch >= 2 ? 2 : 1;
+  st = ensure_geom(e, width, height, slots);
   if (st) return st;
   const size_t dFrame = (size_t)width * height;
-  st = ensure_stage(e, dFrame, 1, capacity);
+  st = ensure_stage(e, dFrame * slots, slots, capacity);
   if (st) return st;
   cudaStream_t s = e->stream;
   e->lastLaunches = 0;
@@ -2983,6 +2990,7 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
     memcpy(descriptors, e->h_out + oD, (size_t)cnt * 32);
   }
   *n = cnt;
+  e->singleCap = capacity; e->singleW = width; e->singleH = height;
   if (pyramid)
     for (int l = 0; l < e->g.nlevels; l++) {
       pyramid[l].data = e->hostPyr + e->g.lv[l].off;
@@ -3091,6 +3099,58 @@ int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* rig
   }
   *n_left = cnt[0];
   *n_right = cnt[1];
+  return ORB_OK;
+}
+
+int orb_stereo_match(orb_extractor* left, orb_extractor* right, float mbf, float mb, float* uright, float* depth, int* n_left) {
+  if (!left || !right || !uright || !depth || left == right) ORB_FAIL(ORB_ERR_INVALID, "null or identical handles");
+  if (!(mb > 0.f) || !(mbf > 0.f)) ORB_FAIL(ORB_ERR_INVALID, "bad stereo baseline");
+  if (left->device != right->device) ORB_FAIL(ORB_ERR_INVALID, "both extractors must live on the same device");
+  if (!left->singleCap || !right->singleCap)
+    ORB_FAIL(ORB_ERR_INVALID, "orb_stereo_match needs the results of an orb_extract call on both handles");
+  if (left->singleCap != right->singleCap || left->singleW != right->singleW || left->singleH != right->singleH ||
+      memcmp(&left->p, &right->p, sizeof(orb_params)) != 0)
+    ORB_FAIL(ORB_ERR_INVALID, "left and right extractors differ in parameters, image size or capacity");
+  if (left->maxBatch < 2 || left->wsFrames < 2) ORB_FAIL(ORB_ERR_INVALID, "the left extractor must be created with max_batch >= 2");
+  ORB_CUDA(cudaSetDevice(left->device));
+  orb_extractor* e = left;
+  cudaStream_t s = e->stream;
+  const int cap = e->singleCap;
+  const Lane WL = lane_of(left, 0), WR = lane_of(right, 0);
+  // the right eye becomes frame 1 of the left handle's chunk: pyramid, keypoints, descriptors, count (device to device)
+  ORB_CUDA(cudaMemcpyAsync(WL.pyr + e->pyrStride, WR.pyr, e->pyrStride, cudaMemcpyDeviceToDevice, s));
+  ORB_CUDA(cudaMemcpyAsync(e->d_kps[0] + cap, right->d_kps[0], (size_t)cap * sizeof(orb_keypoint), cudaMemcpyDeviceToDevice, s));
+  ORB_CUDA(cudaMemcpyAsync(e->d_desc[0] + (size_t)cap * 32, right->d_desc[0], (size_t)cap * 32, cudaMemcpyDeviceToDevice, s));
+  ORB_CUDA(cudaMemcpyAsync(e->d_n[0] + 1, right->d_n[0], sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (cap > e->stereoOutCap) {
+    ORB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(e->d_uRight[0]); cudaFree(e->d_depth[0]);
+    e->d_uRight[0] = e->d_depth[0] = nullptr;
+    e->stereoOutCap = 0;
+    ORB_CUDA(cudaMalloc(&e->d_uRight[0], (size_t)cap * sizeof(float)));
+    ORB_CUDA(cudaMalloc(&e->d_depth[0], (size_t)cap * sizeof(float)));
+    e->stereoOutCap = cap;
+  }
+  const int m = std::min(cap, e->maxKp);
+  const size_t szF = round_up((size_t)m * sizeof(float), (size_t)64);
+  int st = ensure_pinned(e, 0, 64 + 2 * szF);
+  if (st) return st;
+  st = ensure_stereo_scratch(e, cap, s);
+  if (st) return st;
+  e->lastLaunches = 0;
+  st = run_stereo(e, 2, e->d_kps[0], cap, e->d_n[0], e->d_desc[0], mbf, mb, e->d_uRight[0], e->d_depth[0], s, 0);
+  if (st) return st;
+  int* hc = reinterpret_cast<int*>(e->h_out);
+  ORB_CUDA(cudaMemcpyAsync(hc, e->d_n[0], sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + 64, e->d_uRight[0], (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaMemcpyAsync(e->h_out + 64 + szF, e->d_depth[0], (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaStreamSynchronize(s));
+  const int cnt = std::min(hc[0], m);
+  if (cnt > 0) {
+    memcpy(uright, e->h_out + 64, (size_t)cnt * sizeof(float));
+    memcpy(depth, e->h_out + 64 + szF, (size_t)cnt * sizeof(float));
+  }
+  if (n_left) *n_left = cnt;
   return ORB_OK;
 }
 

@@ -17,6 +17,12 @@
 #include <cmath>
 #include <vector>
 
+#include <dlfcn.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "orb_common.cuh"
 
 using namespace orbb200;
@@ -625,6 +631,10 @@ struct orb_matcher {
   // staging for the host single-pair entry point: one device block and one pinned host block with the same packed
   // layout [desc1|desc2|ang1|ang2|xy2|oct1|oct2|prev|m12|best|second|nm] - one upload, one download, one synchronisation
   u8* d_stage = nullptr; u8* h_stage = nullptr; size_t stageBytes = 0;
+  // orb_match_allpairs_nccl: the exchange runs on its own stream, one event per peer block
+  cudaStream_t commStream = nullptr;
+  cudaEvent_t evReady = nullptr;
+  std::vector<cudaEvent_t> evBlock;
 };
 
 extern "C" {
@@ -666,6 +676,9 @@ int orb_matcher_destroy(orb_matcher* m) {
   cudaFree(m->d_stage);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->stream) cudaStreamDestroy(m->stream);
+  if (m->commStream) cudaStreamDestroy(m->commStream);
+  if (m->evReady) cudaEventDestroy(m->evReady);
+  for (cudaEvent_t ev : m->evBlock) cudaEventDestroy(ev);
   delete m;
   return ORB_OK;
 }
@@ -783,6 +796,142 @@ int orb_match_allpairs_device(orb_matcher* m, const uint8_t* d_all, int n_kf, in
   else ORB_FAIL(ORB_ERR_UNSUPPORTED, "more than 2048 descriptors per keyframe");
 #undef ORB_AP
   ORB_CUDA(cudaGetLastError());
+  return ORB_OK;
+}
+
+// ---- all-pairs with the descriptor exchange over NCCL -------------------------------------------------------------
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy the host process already uses - e.g. the one bundled with
+// PyTorch - or the system's), so liborb_b200.so has no link-time dependency on it and single-GPU users never load it.
+namespace {
+typedef struct { char internal[128]; } orb_nccl_id;   // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(orb_nccl_id*) = nullptr;
+  int (*CommInitRank)(void**, int, orb_nccl_id, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string error;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) { api.error = std::string("libnccl.so.2 cannot be loaded: ") + dlerror(); return; }
+    bool ok = true;
+    auto sym = [&](const char* n) { void* p = dlsym(api.lib, n); if (!p) { ok = false; api.error = std::string("libnccl misses ") + n; } return p; };
+    api.GetUniqueId = (int (*)(orb_nccl_id*))sym("ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, orb_nccl_id, int))sym("ncclCommInitRank");
+    api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    api.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclBroadcast");
+    api.GroupStart = (int (*)())sym("ncclGroupStart");
+    api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!ok) { dlclose(api.lib); api.lib = nullptr; }
+  });
+  return &api;
+}
+int nccl_fail(NcclApi* a, int rc, const char* what) {
+  set_last_error(std::string(what) + " failed: " + (a->GetErrorString ? a->GetErrorString(rc) : "?"));
+  return ORB_ERR_CUDA;
+}
+#define ORB_NCCL(call, what)                          \
+  do {                                                \
+    const int rc_ = (call);                           \
+    if (rc_ != 0) return nccl_fail(api, rc_, what);   \
+  } while (0)
+constexpr int kNcclUint8 = 1;   // ncclUint8 / ncclChar family: ncclInt8 = 0, ncclUint8 = 1
+}  // namespace
+
+void orb_shard_range(int total, int rank, int world, int* begin, int* end) {
+  const int base = total / world, rem = total % world;
+  *begin = rank * base + std::min(rank, rem);
+  *end = *begin + base + (rank < rem ? 1 : 0);
+}
+
+int orb_nccl_unique_id(void* id128) {
+  if (!id128) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  NcclApi* api = nccl_api();
+  if (!api->lib) ORB_FAIL(ORB_ERR_UNSUPPORTED, api->error);
+  ORB_NCCL(api->GetUniqueId(reinterpret_cast<orb_nccl_id*>(id128)), "ncclGetUniqueId");
+  return ORB_OK;
+}
+
+int orb_nccl_comm_create(int device, int rank, int world, const void* id128, void** comm) {
+  if (!id128 || !comm || world < 1 || rank < 0 || rank >= world) ORB_FAIL(ORB_ERR_INVALID, "bad argument");
+  NcclApi* api = nccl_api();
+  if (!api->lib) ORB_FAIL(ORB_ERR_UNSUPPORTED, api->error);
+  ORB_CUDA(cudaSetDevice(device));
+  orb_nccl_id id;
+  memcpy(&id, id128, sizeof id);
+  ORB_NCCL(api->CommInitRank(comm, world, id, rank), "ncclCommInitRank");
+  return ORB_OK;
+}
+
+int orb_nccl_comm_destroy(void* comm) {
+  if (!comm) return ORB_OK;
+  NcclApi* api = nccl_api();
+  if (!api->lib) ORB_FAIL(ORB_ERR_UNSUPPORTED, api->error);
+  ORB_NCCL(api->CommDestroy(comm), "ncclCommDestroy");
+  return ORB_OK;
+}
+
+int orb_match_allpairs_nccl(orb_matcher* m, void* nccl_comm, int rank, int world, const uint8_t* d_local_desc, int n_kf, int n_desc,
+                            float nnratio, uint8_t* d_all, int32_t* d_counts, void* stream) {
+  if (!m || !d_local_desc || !d_all || !d_counts || n_kf <= 0 || n_desc <= 0 || world < 1 || rank < 0 || rank >= world || n_kf < world)
+    ORB_FAIL(ORB_ERR_INVALID, "bad argument");
+  if (world > 1 && !nccl_comm) ORB_FAIL(ORB_ERR_INVALID, "a communicator is needed for more than one rank");
+  ORB_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+  int rb, re;
+  orb_shard_range(n_kf, rank, world, &rb, &re);
+  const size_t kfBytes = (size_t)n_desc * 32;
+  ORB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)(re - rb) * n_kf * sizeof(int32_t), s));
+  if (d_local_desc != d_all + (size_t)rb * kfBytes)
+    ORB_CUDA(cudaMemcpyAsync(d_all + (size_t)rb * kfBytes, d_local_desc, (size_t)(re - rb) * kfBytes, cudaMemcpyDeviceToDevice, s));
+  if (world == 1) return orb_match_allpairs_device(m, d_all, n_kf, n_desc, rb, re, 0, n_kf, nnratio, d_counts, s);
+  NcclApi* api = nccl_api();
+  if (!api->lib) ORB_FAIL(ORB_ERR_UNSUPPORTED, api->error);
+  if (!m->commStream) {
+    ORB_CUDA(cudaStreamCreateWithFlags(&m->commStream, cudaStreamNonBlocking));
+    ORB_CUDA(cudaEventCreateWithFlags(&m->evReady, cudaEventDisableTiming));
+  }
+  while ((int)m->evBlock.size() < world) {
+    cudaEvent_t ev;
+    ORB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    m->evBlock.push_back(ev);
+  }
+  // the exchange starts once this rank's block sits in d_all; every rank issues the broadcasts in the same order
+  // (root 0, 1, ...), each followed by an event, on the communication stream
+  ORB_CUDA(cudaEventRecord(m->evReady, s));
+  ORB_CUDA(cudaStreamWaitEvent(m->commStream, m->evReady, 0));
+  for (int r = 0; r < world; r++) {
+    int a, b;
+    orb_shard_range(n_kf, r, world, &a, &b);
+    uint8_t* blk = d_all + (size_t)a * kfBytes;
+    ORB_NCCL(api->Broadcast(blk, blk, (size_t)(b - a) * kfBytes, kNcclUint8, r, nccl_comm, m->commStream), "ncclBroadcast");
+    ORB_CUDA(cudaEventRecord(m->evBlock[r], m->commStream));
+  }
+  // compute: the own block at once (its broadcast only reads it), then the peers' blocks as they land, k_allpairs on the
+  // compute stream overlapping the remaining transfers
+  int st = orb_match_allpairs_device(m, d_all, n_kf, n_desc, rb, re, rb, re, nnratio, d_counts, s);
+  if (st) return st;
+  for (int k = 1; k < world; k++) {
+    const int r = (rank + k) % world;
+    int a, b;
+    orb_shard_range(n_kf, r, world, &a, &b);
+    ORB_CUDA(cudaStreamWaitEvent(s, m->evBlock[r], 0));
+    st = orb_match_allpairs_device(m, d_all, n_kf, n_desc, rb, re, a, b, nnratio, d_counts, s);
+    if (st) return st;
+  }
+  ORB_CUDA(cudaStreamWaitEvent(s, m->evBlock[rank], 0));   // d_all may be reused once `s` has passed this point
   return ORB_OK;
 }
 

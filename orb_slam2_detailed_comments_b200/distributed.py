@@ -8,8 +8,13 @@
   asynchronous broadcast per peer block and running the all-pairs kernel on each column block
   as soon as it has landed (own block first), on a separate compute stream.
 """
+import ctypes as C
+
+import numpy as np
 import torch
 import torch.distributed as dist
+
+from ._lib import check, lib, ptr, stream_arg
 
 
 def shard_range(total, rank, world):
@@ -72,4 +77,53 @@ def allpairs_match_counts(local_desc, n_kf, compute_block, group=None, overlap=T
         a, b = ranges[r]
         compute_block(all_desc, rb, re, a, b, out)
     works[rank].wait()
+    return out
+
+
+class NcclCommunicator:
+    """An ncclComm_t made through the C ABI (orb_nccl_unique_id / orb_nccl_comm_create): rank 0 draws the unique id and
+    the 128 bytes travel through the existing torch.distributed group (any backend). The library binds NCCL at run time,
+    i.e. the copy PyTorch has already loaded. A C++ host passes its own ncclComm_t to orb_match_allpairs_nccl instead."""
+
+    def __init__(self, device, group=None):
+        self._L = lib()
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        uid = np.zeros(128, np.uint8)
+        if self.rank == 0:
+            check(self._L.orb_nccl_unique_id(ptr(uid)))
+        backend = dist.get_backend(group)
+        t = torch.from_numpy(uid)
+        if backend == "nccl":
+            t = t.cuda(device)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(t, src=src, group=group)
+        uid = t.cpu().numpy().copy()
+        self.comm = C.c_void_p()
+        check(self._L.orb_nccl_comm_create(int(device), self.rank, self.world, ptr(uid), C.byref(self.comm)))
+
+    def close(self):
+        if self.comm:
+            self._L.orb_nccl_comm_destroy(self.comm)
+            self.comm = C.c_void_p()
+
+
+def allpairs_match_counts_nccl(matcher, comm, local_desc, n_kf, all_desc=None, out=None, stream=None):
+    """The all-pairs workload through the library's own multi-GPU entry point (orb_match_allpairs_nccl): per-owner
+    ncclBroadcast on the matcher's communication stream, k_allpairs per landed block on the compute stream.
+    local_desc: (rows_local, n_desc, 32) u8 CUDA tensor, rows = shard_range(n_kf, rank, world). comm: NcclCommunicator or
+    None for a single process. Returns the rank's (rows_local, n_kf) int32 block (asynchronous on `stream`, default
+    torch's current stream)."""
+    rank = comm.rank if comm is not None else 0
+    world = comm.world if comm is not None else 1
+    rb, re = shard_range(n_kf, rank, world)
+    assert local_desc.shape[0] == re - rb and local_desc.is_cuda and local_desc.is_contiguous()
+    n_desc = local_desc.shape[1]
+    if all_desc is None:
+        all_desc = local_desc.new_empty((n_kf, n_desc, 32))
+    if out is None:
+        out = torch.empty((re - rb, n_kf), dtype=torch.int32, device=local_desc.device)
+    check(matcher._L.orb_match_allpairs_nccl(matcher._h, comm.comm if comm is not None else None, rank, world, ptr(local_desc),
+                                             int(n_kf), int(n_desc), matcher.mfNNratio, ptr(all_desc), ptr(out),
+                                             matcher._stream(stream, local_desc)))
     return out

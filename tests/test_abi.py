@@ -60,3 +60,23 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in src.lower() or f == "synth.py" and False, "%s mentions the oracle" % f
+
+
+def test_dropin_reference_build_loads_and_fails_loudly_without_gpu():
+    """oracle/_ref/liborbref_gpu.so = the reference's unmodified Frame.cc / ORBmatcher.cc + the drop-in translation units
+    (compat/orb_b200_*.cpp, compiled against the reference's unmodified headers) + liborb_b200.so."""
+    import torch
+    from oracle import orb_refgpu
+    if not orb_refgpu.available():
+        orb_refgpu.build()
+    if not orb_refgpu.available():
+        pytest.skip("needs /root/reference to build")
+    L = orb_refgpu.lib()
+    for n in orb_refgpu.EXPORTS:
+        assert hasattr(L, n), n
+    a = np.arange(32, dtype=np.uint8); b = a ^ 0x11
+    assert orb_refgpu.descriptor_distance(a, b) == 64     # ORBmatcher::DescriptorDistance through the reference's class
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError) as e:
+            orb_refgpu.DropInExtractor(1000, 1.2, 8, 20, 7)
+        assert "liborb_b200" in str(e.value)

@@ -71,3 +71,17 @@ def test_allpairs_exchange_world2(n_kf, overlap):
         assert ok_gather, "all-gather assembled the keyframes in the wrong order on rank %d" % rank
         assert ok_counts, "row block differs from the oracle on rank %d" % rank
         assert total > 0
+
+
+def test_c_abi_shard_range_matches_the_python_schedule():
+    """orb_shard_range (the block layout orb_match_allpairs_nccl uses) == distributed.shard_range."""
+    import ctypes as C
+    from orb_slam2_detailed_comments_b200._lib import lib
+    from orb_slam2_detailed_comments_b200.distributed import shard_range
+    L = lib()
+    for total in (7, 8, 9, 1000, 4096):
+        for world in (1, 2, 3, 8):
+            for rank in range(world):
+                a, b = C.c_int(), C.c_int()
+                L.orb_shard_range(total, rank, world, C.byref(a), C.byref(b))
+                assert (a.value, b.value) == shard_range(total, rank, world)

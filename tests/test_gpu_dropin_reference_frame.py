@@ -1,0 +1,129 @@
+"""The boundary, for real: the reference's UNMODIFIED src/Frame.cc and src/ORBmatcher.cc, compiled against the reference's
+unmodified headers and linked against the drop-in (compat/orb_b200_extractor.cpp, orb_b200_matcher.cpp, orb_b200_frame.cpp
+over liborb_b200.so) instead of src/ORBextractor.cc - oracle/_ref/liborbref_gpu.so, `make -C oracle refgpu`.
+
+The reference's real Frame constructors run (src/Frame.cc:313-350 monocular, :121-158 stereo with its two extractor threads
+and ComputeStereoMatches); every member they fill is compared with what the all-CPU reference (oracle/_ref/liborbref.so, the
+reference's own ORBextractor.cc / Frame.cc, canonical heap order) computes for the same images.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TUM1 = (517.306408, 516.469215, 318.643040, 255.313989, 0.262383, -0.953104, -0.005358, 0.002628, 1.163314)   # TUM1.yaml
+KITTI = (718.856, 718.856, 607.1928, 185.2157, 0.0, 0.0, 0.0, 0.0, 0.0)                                       # KITTI00-02.yaml
+KITTI_BF = 386.1448
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    from oracle import orb_refgpu
+    if not orb_refgpu.available():
+        orb_refgpu.build()
+    if not orb_refgpu.available():
+        pytest.skip("oracle/_ref/liborbref_gpu.so not built (needs /root/reference)")
+    orb_refgpu.lib()
+    return orb_refgpu
+
+
+def _same_keys(a, b, tag):
+    assert len(a) == len(b), "%s: %d keypoints vs reference %d" % (tag, len(a), len(b))
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(a[f], b[f]), "%s: keypoint field %s differs" % (tag, f)
+    if len(a):
+        d = np.abs(a["angle"] - b["angle"])
+        assert np.minimum(d, 360.0 - d).max() <= 1e-3, tag
+
+
+def _same_desc(a, b, tag):
+    assert a.shape == b.shape, tag
+    if len(a):
+        assert (a == b).all(1).mean() >= 0.999, "%s: %d descriptor rows differ" % (tag, int((~(a == b).all(1)).sum()))
+
+
+def test_monocular_frame_constructor(dropin, reference):
+    """Frame(imGray, ts, extractor, voc, K, distCoef, bf, thDepth): ExtractORB -> UndistortKeyPoints -> AssignFeaturesToGrid."""
+    from orb_slam2_detailed_comments_b200.synth import synth_frame
+    ex = dropin.DropInExtractor(1000, 1.2, 8, 20, 7)
+    rex = reference.ReferenceExtractor(1000, 1.2, 8, 20, 7)
+    for seed in (3, 4):
+        img = synth_frame(640, 480, seed)
+        F = dropin.DropInFrame.mono(ex, img, TUM1)
+        rk, rd = rex(img, canonical=True)
+        RF = reference.ReferenceFrame(rk, rd, TUM1, 640, 480)
+        assert F.n == len(rk) >= 1000
+        _same_keys(F.keys(0), rk, "mvKeys seed %d" % seed)
+        _same_desc(F.descriptors(), rd, "mDescriptors seed %d" % seed)
+        ku, rku = F.keys(1), RF.keys_un()
+        assert np.array_equal(ku["x"], rku["x"]) and np.array_equal(ku["y"], rku["y"]), "mvKeysUn differs"
+        assert np.array_equal(F.bounds(), RF.bounds())
+        (s, it), (rs, rit) = F.grid(), RF.grid()
+        assert np.array_equal(s, rs) and np.array_equal(it, rit), "mGrid differs"
+        ur, dp = F.stereo_vectors()
+        assert (ur == -1).all() and (dp == -1).all()   # :343-344
+        sc = F.scale_tables()
+        for a, b in zip(sc, (rex.scale, rex.inv_scale, rex.sigma2, rex.inv_sigma2)):
+            assert np.array_equal(a, b)
+        for l in (0, 3, 7):
+            assert np.array_equal(ex.level(l), rex.level(l)), "mvImagePyramid[%d] differs" % l
+        F.close()
+    ex.close()
+
+
+def test_stereo_frame_constructor(dropin, reference):
+    """Frame(imLeft, imRight, ...): two ExtractORB threads (:146-154), ComputeStereoMatches (:157), undistortion, grid."""
+    from orb_slam2_detailed_comments_b200.synth import synth_frame
+    w, h = 1241, 376
+    exL, exR = dropin.DropInExtractor(2000, 1.2, 8, 20, 7), dropin.DropInExtractor(2000, 1.2, 8, 20, 7)
+    rL, rR = reference.ReferenceExtractor(2000, 1.2, 8, 20, 7), reference.ReferenceExtractor(2000, 1.2, 8, 20, 7)
+    mb = KITTI_BF / KITTI[0]
+    for seed, disp in ((11, 9), (12, 23)):
+        big = synth_frame(w + 64, h, seed)
+        left, right = np.ascontiguousarray(big[:, disp:disp + w]), np.ascontiguousarray(big[:, :w])
+        F = dropin.DropInFrame.stereo(exL, exR, left, right, KITTI, KITTI_BF)
+        kl, dl = rL(left, canonical=True)
+        kr, dr = rR(right, canonical=True)
+        rur, rdp, kept = reference.stereo_matches(rL, rR, KITTI_BF, mb)
+        _same_keys(F.keys(0), kl, "mvKeys")
+        _same_keys(F.keys(2), kr, "mvKeysRight")
+        _same_desc(F.descriptors(False), dl, "mDescriptors")
+        _same_desc(F.descriptors(True), dr, "mDescriptorsRight")
+        ur, dp = F.stereo_vectors()
+        assert np.array_equal(ur, rur), "mvuRight differs in %d entries" % int((ur != rur).sum())
+        assert np.array_equal(dp, rdp), "mvDepth differs"
+        assert kept > 100 and int((dp > 0).sum()) == kept
+        RF = reference.ReferenceFrame(kl, dl, KITTI, w, h)
+        (s, it), (rs, rit) = F.grid(), RF.grid()
+        assert np.array_equal(s, rs) and np.array_equal(it, rit), "mGrid differs"
+        F.close()
+    exL.close(); exR.close()
+
+
+def test_monocular_initialisation_sequence(dropin, reference):
+    """src/Tracking.cc:175-188 + :895-926: mpIniORBextractor (2 * nFeatures) makes two frames, ORBmatcher(0.9, true)
+    .SearchForInitialization(mInitialFrame, mCurrentFrame, mvbPrevMatched, mvIniMatches, 100); the normal extractor stays
+    alive beside it and is used in between."""
+    from orb_slam2_detailed_comments_b200.synth import synth_frame
+    w, h = 640, 480
+    ini, left = dropin.DropInExtractor(2000, 1.2, 8, 20, 7), dropin.DropInExtractor(1000, 1.2, 8, 20, 7)
+    rini = reference.ReferenceExtractor(2000, 1.2, 8, 20, 7)
+    big = synth_frame(w + 16, h + 16, 5, noise_sigma=0.0).astype(np.float32)
+    rng = np.random.RandomState(2)
+    a = np.clip(np.rint(big[:h, :w] + rng.normal(0, 2, (h, w))), 0, 255).astype(np.uint8)
+    b = np.clip(np.rint(big[5:h + 5, 8:w + 8] + rng.normal(0, 2, (h, w))), 0, 255).astype(np.uint8)
+    F1 = dropin.DropInFrame.mono(ini, a, TUM1)
+    left(a)                                            # the other live extractor, smaller geometry, in between
+    F2 = dropin.DropInFrame.mono(ini, b, TUM1)
+    k1, d1 = rini(a, canonical=True)
+    k2, d2 = rini(b, canonical=True)
+    R1, R2 = reference.ReferenceFrame(k1, d1, TUM1, w, h), reference.ReferenceFrame(k2, d2, TUM1, w, h)
+    prev = np.stack([R1.keys_un()["x"], R1.keys_un()["y"]], 1)
+    n_ref, m_ref, prev_ref = reference.search_for_initialization(R1, R2, prev, 100, 0.9, True)
+    n, m12, prev_out = dropin.search_for_initialization(F1, F2, prev, 100, 0.9, True)
+    assert n == n_ref and np.array_equal(m12, m_ref) and np.array_equal(prev_out, prev_ref), (n, n_ref)
+    assert n > 100
+    assert dropin.descriptor_distance(d1[0], d2[0]) == reference.descriptor_distance(d1[0], d2[0])
+    for F in (F1, F2):
+        F.close()
+    ini.close(); left.close()

@@ -189,3 +189,20 @@ def test_search_for_initialization_against_the_reference_itself(oracle, referenc
         n, m12 = m.SearchForInitialization(F1, F2, prev_gpu, window, mode=0)
         print("window", window, "call", call, "matches", n_ref)
         assert n == n_ref > 20 and np.array_equal(m12, m_ref) and np.array_equal(prev_gpu, prev_ref)
+
+
+def test_allpairs_library_entry_single_rank(oracle):
+    """orb_match_allpairs_nccl with world = 1 (no communicator): the multi-GPU entry point degenerates to the local kernel."""
+    import torch
+    from orb_slam2_detailed_comments_b200 import ORBmatcher
+    from orb_slam2_detailed_comments_b200.distributed import allpairs_match_counts_nccl
+    rng = np.random.RandomState(5)
+    nkf, nd = 7, 300
+    base = rng.randint(0, 256, (nd, 32)).astype(np.uint8)
+    bits = np.unpackbits(base, axis=1)
+    all_np = np.stack([np.packbits(bits ^ (rng.rand(*bits.shape) < 0.02 * (k % 4)).astype(np.uint8), axis=1)[rng.permutation(nd)]
+                       for k in range(nkf)])
+    m = ORBmatcher(0.9, True)
+    counts = allpairs_match_counts_nccl(m, None, torch.from_numpy(all_np).cuda(), nkf)
+    m.synchronize()
+    assert np.array_equal(counts.cpu().numpy(), oracle.allpairs_counts(all_np, 0.9, 0, nkf))

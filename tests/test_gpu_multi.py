@@ -22,7 +22,8 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from oracle import orb_oracle as O
     from orb_slam2_detailed_comments_b200 import ORBextractor, ORBmatcher
-    from orb_slam2_detailed_comments_b200.distributed import allpairs_match_counts, shard_range
+    from orb_slam2_detailed_comments_b200.distributed import (NcclCommunicator, allpairs_match_counts, allpairs_match_counts_nccl,
+                                                              shard_range)
     from orb_slam2_detailed_comments_b200.synth import synth_batch
 
     # ---- all-pairs with the NCCL exchange
@@ -49,6 +50,15 @@ def _worker(rank, world, port, q):
             counts = allpairs_match_counts(local, n_kf, compute_block, overlap=overlap)
         torch.cuda.synchronize()
         ok = ok and bool(np.array_equal(counts.cpu().numpy(), O.allpairs_counts(all_np, 0.9, rb, re)))
+
+    # ---- the same through the library's own multi-GPU entry point (orb_match_allpairs_nccl: exchange inside the C ABI)
+    comm = NcclCommunicator(rank)
+    for rep in range(2):
+        with torch.cuda.stream(ts):
+            counts = allpairs_match_counts_nccl(matcher, comm, local, n_kf)
+        torch.cuda.synchronize()
+        ok = ok and bool(np.array_equal(counts.cpu().numpy(), O.allpairs_counts(all_np, 0.9, rb, re)))
+    comm.close()
 
     # ---- frame-sharded extraction: each rank extracts its contiguous block of the same 6 frames
     imgs = synth_batch(752, 480, 6, seed0=300)
