@@ -227,6 +227,130 @@ def bind_to_gpu_numa_node(props):
     return None
 
 
+def parity_counters(ext, frames):
+    """north_star: "the only allowed differences are cvRound flips ... these must be counted and reported". A sample of the
+    pool's frames is extracted once more through the drop-in call and compared with the CPU oracle, OUTSIDE any timed
+    region: keypoint records (x, y, octave, response, size) must be identical, angles within 1e-3 degrees; descriptor rows
+    that differ and the bits flipped in them are counted; so are the (level, frame) quadtree runs whose result depends on
+    the tie rule for equal-sized nodes (heap-address order in the reference, creation order here and in the oracle)."""
+    import numpy as np
+
+    from oracle import orb_oracle as O
+    orc = O.OracleExtractor(NFEAT, 1.2, 8, 20, 7)
+    out = {"frames_checked": len(frames), "keypoints_compared": 0, "keypoint_records_differing": 0, "max_angle_err_deg": 0.0,
+           "desc_rows_compared": 0, "desc_rows_differing": 0, "desc_bits_flipped": 0, "tie_sensitive_levels": 0, "levels_checked": 0,
+           "checked_against": "CPU oracle (oracle/orb_oracle.cpp, pinned bit-exactly to the reference's own code in oracle/_ref)"}
+    for img in frames:
+        kps, desc = ext(img)
+        okps, odesc = orc(img)
+        n = min(len(kps), len(okps))
+        out["keypoints_compared"] += max(len(kps), len(okps))
+        bad = np.zeros(n, bool)
+        for f in ("x", "y", "octave", "response", "size"):
+            bad |= kps[f][:n] != okps[f][:n]
+        out["keypoint_records_differing"] += int(bad.sum()) + abs(len(kps) - len(okps))
+        if n:
+            d = np.abs(kps["angle"][:n] - okps["angle"][:n])
+            out["max_angle_err_deg"] = max(out["max_angle_err_deg"], float(np.minimum(d, 360.0 - d).max()))
+            x = desc[:n] ^ odesc[:n]
+            out["desc_rows_compared"] += n
+            out["desc_rows_differing"] += int((x != 0).any(1).sum())
+            out["desc_bits_flipped"] += int(np.unpackbits(x).sum())
+        for l in range(8):
+            out["tie_sensitive_levels"] += int(orc.stats(l)["tie_sensitive"] != 0)
+            out["levels_checked"] += 1
+    out["desc_identical_fraction"] = 1.0 - out["desc_rows_differing"] / max(1, out["desc_rows_compared"])
+    return out
+
+
+_CV2_FRAMES = None
+
+
+def _cv2_orb_worker(rng):
+    import cv2
+    cv2.setNumThreads(1)
+    orb = cv2.ORB_create(nfeatures=NFEAT, scaleFactor=1.2, nlevels=8, edgeThreshold=19, fastThreshold=20, scoreType=cv2.ORB_FAST_SCORE)
+    n = 0
+    for i in range(*rng):
+        k, _ = orb.detectAndCompute(_CV2_FRAMES[i], None)
+        n += len(k)
+    return n
+
+
+def opencv_orb_baseline(frames, cores):
+    """A second CPU figure from the REAL (SIMD) OpenCV of this image: cv2.ORB_create(...).detectAndCompute, one process per
+    core. It is OpenCV's own ORB (global FAST + retainBest instead of the per-cell threshold fallback and the quadtree), so
+    its keypoints are not the reference's; it brackets from below what a well-optimised CPU ORB front-end costs, where the
+    reference arm (scalar OpenCV stand-in) brackets from above."""
+    global _CV2_FRAMES
+    try:
+        import multiprocessing as mp
+
+        import cv2
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+    _CV2_FRAMES = frames
+    per = (len(frames) + cores - 1) // cores
+    ranges = [(i, min(i + per, len(frames))) for i in range(0, len(frames), per)]
+    with mp.get_context("fork").Pool(len(ranges)) as pool:
+        pool.map(_cv2_orb_worker, [(0, 1)] * len(ranges))   # start the workers, load cv2
+        t0 = time.perf_counter()
+        kp = sum(pool.map(_cv2_orb_worker, ranges))
+        dt = time.perf_counter() - t0
+    return {"value": len(frames) / dt, "unit": "frames/s", "cores": len(ranges), "mean_keypoints": kp / len(frames),
+            "what": "cv2.ORB_create(%d, 1.2, 8, fastThreshold=20, FAST_SCORE).detectAndCompute, OpenCV %s (SIMD build), one process "
+                    "per core: OpenCV's own ORB, not ORB-SLAM2's extractor - a lower bracket for the GPU / CPU ratio" % (NFEAT, cv2.__version__)}
+
+
+def run_sequence_config3(args, rank, world, local_rank, dev, barrier, max_over_ranks):
+    """BASELINE.json configs[2]: an EuRoC-shape 752x480 sequence of 8192 frames, 1200 features, STRONG-sharded: the 8192
+    frames are split across the ranks (8192 / N each, contiguous blocks, no collective), every rank's share resident in HBM."""
+    import numpy as np
+    import torch
+
+    from orb_slam2_detailed_comments_b200 import ORBextractor
+    from orb_slam2_detailed_comments_b200.distributed import shard_range
+    from orb_slam2_detailed_comments_b200.synth import synth_frame
+    w, h, nfeat = WORKLOADS["euroc"][:3]
+    total = args.sequence_frames
+    fb, fe = shard_range(total, rank, world)
+    mine = fe - fb
+    uniq = min(128, mine)
+    import multiprocessing as mp
+    procs = max(1, min(16, (os.cpu_count() or 2) // max(1, world)))
+    with mp.get_context("fork").Pool(procs) as pool_:
+        frames = np.stack(pool_.starmap(synth_frame, [(w, h, 500000 + 1000 * rank + i) for i in range(uniq)], chunksize=8))
+    ext = ORBextractor(nfeat, 1.2, 8, 20, 7, device=local_rank, max_batch=args.chunk)
+    cap = ext.max_keypoints_for(w, h)
+    d_pool = torch.from_numpy(frames).to(dev)
+    d_imgs = d_pool.repeat((mine + uniq - 1) // uniq, 1, 1)[:mine].contiguous()
+    d_kps = torch.zeros((mine, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((mine, cap, 32), dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros(mine, dtype=torch.int32, device=dev)
+    ts = torch.cuda.Stream(device=dev)
+    ext.extract_batch_device(d_imgs, d_kps, d_desc, d_counts, stream=ts.cuda_stream)
+    ext.synchronize(ts.cuda_stream)
+    barrier()
+    reps = 3
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(ts)
+    for _ in range(reps):
+        ext.extract_batch_device(d_imgs, d_kps, d_desc, d_counts, stream=ts.cuda_stream)
+    e1.record(ts)
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    ext.synchronize(ts.cuda_stream)
+    launches = ext.last_launch_count() * (reps + 1)
+    mean_kp = float(d_counts.float().mean().item())
+    ext.close()
+    return {"what": "BASELINE.json configs[2]: EuRoC-shape %dx%d sequence of %d frames, ORBextractor(%d,1.2,8,20,7), frames sharded "
+                    "across the GPUs in contiguous blocks, no collective; frames resident in HBM" % (w, h, total, nfeat),
+            "frames": total, "frames_per_gpu": mine, "scaling": "strong", "ms_per_sequence": ms,
+            "value": total / (ms * 1e-3), "unit": "frames/s", "mean_keypoints": mean_kp, "unique_frames_per_gpu": uniq,
+            "l2": "inputs larger than L2 (%d MB per GPU)" % (mine * w * h // 1000000)}, launches
+
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -545,6 +669,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_fps = world * frames_per_step * e2e_steps / e2e_s
     e2e_sync_fps = world * frames_per_step * e2e_steps / e2e_sync_s
     e2e_launches = ext.last_launch_count() * e2e_steps * 2
+    # parity counters on a sample of the pool, outside every timed region (rank 0)
+    parity = parity_counters(ext, pool[: args.parity_frames]) if rank == 0 and args.parity_frames > 0 else None
     assert int(np_counts.sum()) == int(counts.sum()), "host path and device path disagree"
     if e2e_steps > 1:
         assert int(outs[1][2].sum()) == int(counts.sum()), "asynchronous host path and device path disagree"
@@ -593,30 +719,41 @@ def run_ours(args, rank, world, local_rank):
     # ---- all-pairs keyframe matching (BASELINE.json configs[4], scaled down): NCCL exchange of the
     # descriptor blocks, consumed block by block (distributed.allpairs_match_counts)
     allpairs = None
-    if args.allpairs_kf > 0:
-        from orb_slam2_detailed_comments_b200.distributed import allpairs_match_counts, shard_range
-        n_kf, n_desc = args.allpairs_kf, 1000
+    ap_kf = args.allpairs_kf if args.allpairs_kf >= 0 else (4096 if world >= 8 else 512)   # config 5 in full on 8 GPUs
+    if ap_kf > 0:
+        from orb_slam2_detailed_comments_b200.distributed import NcclCommunicator, allpairs_match_counts_nccl, shard_range
+        n_kf, n_desc = ap_kf, 1000
         rb, re = shard_range(n_kf, rank, world)
         g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
         local = torch.randint(0, 256, (re - rb, n_desc, 32), dtype=torch.uint8, device=dev, generator=g)
-
-        def compute_block(all_desc, r0, r1, c0, c1, out):
-            matcher.match_allpairs_device(all_desc, r0, r1, out, stream=stream, col_begin=c0, col_end=c1)
-
+        all_desc = torch.empty((n_kf, n_desc, 32), dtype=torch.uint8, device=dev)
+        ap_out = torch.empty((re - rb, n_kf), dtype=torch.int32, device=dev)
+        comm = NcclCommunicator(local_rank) if world > 1 else None
         with torch.cuda.stream(tstream):
-            allpairs_match_counts(local, n_kf, compute_block)   # warm-up
+            allpairs_match_counts_nccl(matcher, comm, local, n_kf, all_desc, ap_out, stream=stream)   # warm-up
             barrier()
             a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
             a0.record(tstream)
-            allpairs_match_counts(local, n_kf, compute_block)
+            allpairs_match_counts_nccl(matcher, comm, local, n_kf, all_desc, ap_out, stream=stream)
             a1.record(tstream)
             torch.cuda.synchronize()
         ap_ms = max_over_ranks(a0.elapsed_time(a1))
+        if comm is not None:
+            comm.close()
         allpairs = {"keyframes": n_kf, "descriptors_per_keyframe": n_desc, "ms": ap_ms,
-                    "value": float(n_kf) * n_kf * n_desc * n_desc / (ap_ms * 1e-3), "unit": "cmp/s",
-                    "exchange": "nccl broadcast per block, overlapped" if world > 1 else "none (1 GPU)",
+                    "value": float(n_kf) * n_kf * n_desc * n_desc / (ap_ms * 1e-3), "unit": "cmp/s", "scaling": "strong",
+                    "api": "orb_match_allpairs_nccl (exchange inside the C ABI)",
+                    "exchange": "ncclBroadcast per owner block on a communication stream, k_allpairs per landed block" if world > 1 else "none (1 GPU)",
                     "note": ("BASELINE config 5 at full size" if n_kf >= 4096 else
-                             "BASELINE config 5 uses 4096 keyframes; scaled down to bound the run (--allpairs-kf 4096 runs it in full)")}
+                             "BASELINE config 5 uses 4096 keyframes; scaled down to bound the run below 8 GPUs (--allpairs-kf 4096 runs it in full)")}
+        del all_desc, ap_out, local
+    # ---- BASELINE config 3: the EuRoC sequence, strong-sharded
+    sequence = None
+    seq_launches = 0
+    if args.sequence_frames > 0:
+        del d_imgs, d_kps, d_desc, d_dsc, d_m12
+        torch.cuda.empty_cache()
+        sequence, seq_launches = run_sequence_config3(args, rank, world, local_rank, dev, barrier, max_over_ranks)
     pipes = int_pipe_peak(local_rank)
     clocks = sampler.stop() if sampler else None
 
@@ -637,13 +774,13 @@ def run_ours(args, rank, world, local_rank):
     dom = max(stage_ms, key=stage_ms.get)
     n_launch = max(1, stages[dom][1])
     frames_total = frames_per_step * args.steps
-    kernels_per_chunk = 8 if dom == "pyramid" else 1
+    kernels_per_chunk = max(1, round(stages[dom][1] / max(1, stages["fast"][1])))   # pyramid: 1 + 7 (+ 1 border) launches
     frames_per_launch = frames_total / (n_launch / kernels_per_chunk)
     dom_ms = stage_ms[dom] / n_launch
     # bytes per launch / average launch duration == stage bytes over all frames / stage time
     achieved = per_stage_b[dom] * frames_total / (stage_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0_border+k_resize_border", "fast": "k_fast_cells", "quadtree": "k_quadtree",
-                                           "blur": "k_blur7", "describe": "k_describe"}[dom],
+    roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0_border2+k_resize_strip+k_fill_borders", "fast": "k_fast_cells", "quadtree": "k_quadtree",
+                                           "blur": "k_blur7", "describe": "k_describe_tma"}[dom],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom),
                 "peak_source": peak_src, "algorithmic_bytes_per_frame": per_stage_b[dom], "frames_per_launch": frames_per_launch,
                 "avg_launch_ms": dom_ms, "share_of_step": stage_ms[dom] / max(1e-9, sum(stage_ms.values()))}
@@ -672,7 +809,8 @@ def run_ours(args, rank, world, local_rank):
             q_ = O.project_last_frame(sc_["Xw"], sc_["mp_flags"], sc_["last"], sc_["Tcw"], sc_["cam4"], sc_["bounds"], sc_["mbf"], 15.0, sfs, 0)
             O.search_by_projection(sc_["cur"], sc_["cur_desc"], sc_["uright"], sc_["bounds"], sc_["occupied0"], q_, sc_["mp_desc"], 0, 100, 0.9, True)
         tracking["cpu_oracle_ms_per_frame_1_thread"] = (time.perf_counter() - t2) / 4 * 1e3
-        cpu = {"value": sample / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+        cv2_orb = opencv_orb_baseline(frames[: max(64, 16 * cores)], cores)
+        cpu = {"value": sample / dt, "unit": "frames/s", "cores": cores, "kind": kind, "opencv_orb": cv2_orb,
                "sample": "%d %s-shape frames, one frame per thread; %s" % (sample, args.workload, what),
                "oracle_port_frames_per_s": sample / dt_port,
                "matching_cmp_per_s": min(pairs, uniq) * MATCH_N * MATCH_N / dtm}
@@ -693,7 +831,7 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_GBps_in_run": e2e_fps / world * W * H / 1e9,
                 "h2d_GBps_copy_engine_alone": h2d_peak,
                 "ceiling_frames_per_s": h2d_peak * 1e9 / (W * H) * world},
-        "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + frame_launches + track_launches + input_launches + m_steps + (2 * world if allpairs else 0),
+        "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + frame_launches + track_launches + input_launches + m_steps + (2 * world if allpairs else 0) + seq_launches,
         "stereo": stereo,
         "frame_helpers": frame_helpers,
         "tracking": tracking,
@@ -719,9 +857,20 @@ def run_ours(args, rank, world, local_rank):
                                   "mix_peak_def": "kernel issues 4 POPC + 16 LOP3 per comparison (carry-save adders); "
                                                   "peak = measured rate of that mix (POPC and LOP3 share the ALU pipe) / 4"}},
     }
+    mix_peak_cmp = pipes["mix_popc_4lop3"] / 4.0
+    line["roofline_matching"] = {"bound": "int-pipe", "kernel": "k_match_pairs_bf", "achieved": cmp_per_s / world, "peak": mix_peak_cmp,
+                                 "unit": "cmp/s", "frac": cmp_per_s / world / mix_peak_cmp,
+                                 "peak_def": "the kernel issues 4 POPC + 16 LOP3 per 256-bit comparison (carry-save adders); peak = the "
+                                             "measured issue rate of that instruction mix on this GPU (orb_int_pipe_peak) / 4"}
     if allpairs:
-        allpairs["roofline_frac"] = allpairs["value"] / world / popc_peak_cmp
+        allpairs["roofline_frac"] = allpairs["value"] / world / mix_peak_cmp
+        allpairs["roofline_frac_of_popc_over_8"] = allpairs["value"] / world / popc_peak_cmp
         line["allpairs"] = allpairs
+    if sequence:
+        sequence["path_roofline_frac"] = None
+        line["sequence_config3"] = sequence
+    if parity:
+        line["parity"] = parity
     if cpu:
         line["cpu_baseline"] = cpu
     emit(line)
@@ -743,7 +892,10 @@ def main():
     ap.add_argument("--no-latency", action="store_true", help="skip the single-call latency loops (profiling runs)")
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP, help="stereo pairs per step per GPU (profiling runs shrink this)")
     ap.add_argument("--match-pairs", type=int, default=MATCH_PAIRS)
-    ap.add_argument("--allpairs-kf", type=int, default=512, help="keyframes of the all-pairs workload (0 = skip)")
+    ap.add_argument("--allpairs-kf", type=int, default=-1,
+                    help="keyframes of the all-pairs workload (0 = skip; default: 4096 = BASELINE config 5 in full on 8 GPUs, 512 below)")
+    ap.add_argument("--sequence-frames", type=int, default=8192, help="frames of the EuRoC sequence of BASELINE config 3, sharded across the GPUs (0 = skip)")
+    ap.add_argument("--parity-frames", type=int, default=8, help="frames re-checked against the CPU oracle outside the timed regions (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     global W, H, NFEAT, METRIC
