@@ -939,7 +939,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
                                                          const int* __restrict__ candCount,
                                                          unsigned short* __restrict__ keyNode,
                                                          uint2* __restrict__ kept, int* __restrict__ keptCount,
-                                                         int candTotal, int keptTotal, int nodeCap,
+                                                         int candTotal, int keptTotal, int nodeCap, int seqWords,
                                                          int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char qsm[];
   __shared__ int s_tmp[34];
@@ -974,6 +974,10 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
   // in every refinement round); larger levels fall back to the global scratch
   unsigned* s_xy = (unsigned*)(key64 + nodeCap);
   unsigned short* s_kn = (unsigned short*)(s_xy + kQtSmemKeys);
+  // ranking by creation sequence without comparing all pairs: a bitmap over the sequence numbers (one bit per number
+  // handed out so far) and the running population count of its words; rank = set bits above
+  unsigned* bm = (unsigned*)(s_kn + kQtSmemKeys);
+  int* bmPre = (int*)(bm + seqWords);
   const bool inSmem = n <= kQtSmemKeys;
   const unsigned* XY;          // generic pointers: shared or global
   unsigned short* KNp;
@@ -1054,10 +1058,31 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
       key64[i] = (partial ? ((unsigned long long)(unsigned)Nd.count << 32) : 0ull) | (unsigned)Nd.seq;
     }
     __syncthreads();
+    // rank of every node to split: by (key count, creation sequence) descending in the sorted partial pass, by
+    // creation sequence descending in a full pass (there the order only fixes the children's sequence numbers)
+    const int words = (seqCounter + 31) >> 5;
+    const bool byBitmap = !partial && words <= seqWords;
+    if (byBitmap) {
+      for (int w = tid; w < words; w += kQtThreads) bm[w] = 0u;
+      __syncthreads();
+      for (int i = tid; i < nc; i += kQtThreads) {
+        const unsigned sq = (unsigned)key64[i];
+        atomicOr(&bm[sq >> 5], 1u << (sq & 31));
+      }
+      __syncthreads();
+      for (int w = tid; w < words; w += kQtThreads) bmPre[w] = __popc(bm[w]);
+      __syncthreads();
+      block_scan_excl(bmPre, words, s_tmp);
+    }
     for (int i = tid; i < nc; i += kQtThreads) {
       const unsigned long long ki = key64[i];
       int r = 0;
-      for (int j = 0; j < nc; j++) r += key64[j] > ki;
+      if (byBitmap) {
+        const unsigned sq = (unsigned)ki;
+        r = nc - 1 - (bmPre[sq >> 5] + __popc(bm[sq >> 5] & ((1u << (sq & 31)) - 1u)));
+      } else {
+        for (int j = 0; j < nc; j++) r += key64[j] > ki;
+      }
       const int nd = candList[i];
       const int ne = (childCnt[4 * nd] > 0) + (childCnt[4 * nd + 1] > 0) + (childCnt[4 * nd + 2] > 0) + (childCnt[4 * nd + 3] > 0);
       nodeRank[nd] = r;
@@ -1156,10 +1181,29 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
     atomicMax(&key64[KNp[k]], pk);
   }
   __syncthreads();
+  // final list order == descending creation sequence
+  const int wordsF = (seqCounter + 31) >> 5;
+  const bool bitmapF = wordsF <= seqWords;
+  if (bitmapF) {
+    for (int w = tid; w < wordsF; w += kQtThreads) bm[w] = 0u;
+    __syncthreads();
+    for (int i = tid; i < numNodes; i += kQtThreads) {
+      const unsigned sq = (unsigned)nodes[i].seq;
+      atomicOr(&bm[sq >> 5], 1u << (sq & 31));
+    }
+    __syncthreads();
+    for (int w = tid; w < wordsF; w += kQtThreads) bmPre[w] = __popc(bm[w]);
+    __syncthreads();
+    block_scan_excl(bmPre, wordsF, s_tmp);
+  }
   for (int i = tid; i < numNodes; i += kQtThreads) {
     const int s = nodes[i].seq;
     int r = 0;
-    for (int j = 0; j < numNodes; j++) r += nodes[j].seq > s;
+    if (bitmapF) {
+      r = numNodes - 1 - (bmPre[s >> 5] + __popc(bm[s >> 5] & ((1u << (s & 31)) - 1u)));
+    } else {
+      for (int j = 0; j < numNodes; j++) r += nodes[j].seq > s;
+    }
     if (r < L.keptCap) K[r] = C[(int)(key64[i] & 0xffffffu)];
   }
   if (tid == 0) {
@@ -1944,6 +1988,7 @@ struct orb_extractor {
   size_t pyrStride = 0, blurStride = 0;
   int candTotal = 0, keptTotal = 0, nodeCap = 0, maxKp = 0;
   size_t fastSmem = 0, qtSmem = 0;
+  int qtSeqWords = 0;
   FastSmemLayout fastLay;
   BorderJobs borderJobs = {};    // block ranges of k_fill_borders
   int borderBlocks = 0;
@@ -2194,7 +2239,14 @@ int build_geom(orb_extractor* e, int W, int H) {
     e->borderBlocks = blocks;
     e->pyrTiled = ok;
   }
-  e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8) + (size_t)kQtSmemKeys * 6;
+  // sequence-number bitmap of k_quadtree: every refinement round hands out 4 numbers per split node; rounds are bounded
+  // by the halvings of the longer side (larger counts fall back to the all-pairs ranking inside the kernel)
+  {
+    int rounds = 2;
+    for (int side = std::max(g.lv[0].w, g.lv[0].h); side > 1; side >>= 1) rounds++;
+    e->qtSeqWords = std::min(2048, (g.lv[0].nIni + 4 * rounds * e->nodeCap + 31) / 32 + 1);
+  }
+  e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8) + (size_t)kQtSmemKeys * 6 + (size_t)e->qtSeqWords * 8;
   if (e->qtSmem > 220 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "features per level too large for the quadtree kernel's shared memory");
   if (e->fastSmem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
   return ORB_OK;
@@ -2427,7 +2479,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     ORB_CUDA(cudaStreamWaitEvent(bs, e->evBlurGo[lane], 0));
   }
   k_quadtree<<<dim3(B, nl), kQtThreads, e->qtSmem, s>>>(g, W.cand, W.candCount, W.keyNode, W.kept,
-                                                       W.keptCount, e->candTotal, e->keptTotal, e->nodeCap,
+                                                       W.keptCount, e->candTotal, e->keptTotal, e->nodeCap, e->qtSeqWords,
                                                        e->d_overflow);
   launches++;
   if ((st = stage_mark(e, s))) return st;
