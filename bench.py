@@ -433,7 +433,7 @@ def run_ours(args, rank, world, local_rank):
     stages = ext.stage_times()
     ext.set_profiling(False)
     ext.synchronize(stream)
-    ext.set_lanes(2 if os.environ.get("ORB_B200_LANES", "1") == "2" else 1)
+    ext.set_lanes(1 if os.environ.get("ORB_B200_LANES", "2") == "1" else 2)
     step_device()
     ext.synchronize(stream)
     launches_per_step = ext.last_launch_count()

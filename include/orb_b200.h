@@ -151,7 +151,7 @@ int orb_last_launch_count(const orb_extractor* h);
  * stages {pyramid, fast, quadtree, blur, describe} and resets them. */
 int orb_set_profiling(orb_extractor* h, int enable);
 
-/* Number of workspace lanes (1 or 2, default 1; env ORB_B200_LANES overrides the default): with 2,
+/* Number of workspace lanes (1 or 2, default 2; env ORB_B200_LANES overrides the default): with 2,
  * consecutive chunks of a batch call run on two internal streams so that kernels of neighbouring
  * chunks can overlap. Results are identical; per-stage timings are only meaningful with 1 lane. */
 int orb_set_lanes(orb_extractor* h, int lanes);

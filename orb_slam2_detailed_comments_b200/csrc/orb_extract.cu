@@ -2002,10 +2002,11 @@ struct orb_extractor {
   uint2* d_kept = nullptr; int* d_keptCount = nullptr; int2* d_taps = nullptr;
   signed char* d_pattern = nullptr; int* d_overflow = nullptr; int* d_work = nullptr;
   int wsFrames = 0;
-  // optional second workspace lane (orb_set_lanes / ORB_B200_LANES=2): consecutive chunks then run on
-  // two streams. It paid while some kernels were latency-bound; with the current kernels every stage
-  // saturates the SMs and one lane is as fast, so 1 is the default.
-  int lanes = 1, lastLane = 0;
+  // two workspace lanes (orb_set_lanes / ORB_B200_LANES=1 for one): consecutive chunks of a batch call run on two
+  // streams, so the tail of every kernel of one chunk and the latency-bound phases (quadtree) overlap the other chunk's
+  // kernels: +6.7 % frames/s, +14 % stereo pairs/s on 256-frame chunks (measured, round 2). Single-call entry points
+  // use lane 0 only.
+  int lanes = 2, lastLane = 0;
   long long hostChunks = 0;      // chunks issued by the host batch entry points so far (staging buffer parity)
   bool asyncPending = false;     // orb_extract_batch_host_async work may still be in flight
   DescMaps descMaps[2];          // TMA tensor maps of the two workspace lanes (k_describe_tma)
@@ -2527,7 +2528,7 @@ int ensure_stereo_scratch(orb_extractor* e, int cap, cudaStream_t s) {
 }
 
 int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, const int* d_counts, const u8* d_desc, float mbf,
-               float mb, float* d_uRight, float* d_depth, cudaStream_t s, int lane = 0) {
+               float mb, float* d_uRight, float* d_depth, cudaStream_t s, int lane = 0, bool concurrentLanes = false) {
   // right keypoints (x, row band, octave), SAD list, row index (H+2 ints) and up to 12 index entries
   // per keypoint (more -> the kernel scans all right keypoints instead of using the index)
   size_t fixed = (size_t)cap * (4 + 4 + 8 + 1) + (size_t)(e->g.H + 2) * 4 + 64;
@@ -2540,8 +2541,8 @@ int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, cons
   ORB_CUDA(raise_dynamic_smem(k_stereo, smem));
   // few pairs per call (the per-frame drop-in case): deal every pair to G CTAs
   const int pairs = B / 2;
-  // (one scratch list per extractor: not with two workspace lanes, whose chunks run on two streams at once)
-  const int G = e->lanes >= 2 ? 1 : (pairs <= 8 ? 16 : (pairs <= 32 ? 4 : 1));
+  // (one scratch list per extractor: not while chunks of this call run on the two lane streams at once)
+  const int G = concurrentLanes ? 1 : (pairs <= 8 ? 16 : (pairs <= 32 ? 4 : 1));
   if (G > 1) {
     const int st = ensure_stereo_scratch(e, cap, s);
     if (st) return st;
@@ -3082,7 +3083,7 @@ int orb_extract_stereo_batch_device(orb_extractor* e, const uint8_t* d_images, i
     if (st) return st;
     st = run_stereo(e, B, d_keypoints + (size_t)b0 * capacity, capacity, d_counts + b0,
                     d_descriptors + (size_t)b0 * capacity * 32, mbf, mb, d_uright + (size_t)(b0 / 2) * capacity,
-                    d_depth + (size_t)(b0 / 2) * capacity, ls, lane);
+                    d_depth + (size_t)(b0 / 2) * capacity, ls, lane, multi);
     if (st) return st;
   }
   return lanes_join(e, s, nChunks);
