@@ -634,6 +634,15 @@ def run_ours(args, rank, world, local_rank):
             t0 = time.perf_counter(); fn(); ts_.append(time.perf_counter() - t0)
         ts_.sort()
         lat[name] = {"median": 1e3 * ts_[len(ts_) // 2], "p90": 1e3 * ts_[int(len(ts_) * 0.9)]}
+    if not args.no_latency:
+        # the same call timed INSIDE the C ABI (orb_last_call_breakdown): what a C++ host pays, without the Python wrapper
+        acc = {}
+        for _ in range(50):
+            ext(one)
+            for k_, v_ in ext.last_call_breakdown().items():
+                acc[k_] = acc.get(k_, 0.0) + v_ / 50
+        acc["total_us"] = sum(acc.values())
+        lat["orb_extract_inside_c_abi_us"] = acc
 
     # ---- end to end through the host entry point of the C ABI (pinned buffers) -----------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))

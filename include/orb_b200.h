@@ -145,6 +145,10 @@ int orb_synchronize(orb_extractor* h, void* stream);
 /* Number of kernel launches the last batch call issued (for bench accounting). */
 int orb_last_launch_count(const orb_extractor* h);
 
+/* Host wall-clock breakdown of the last orb_extract call, microseconds: us4 = {staging copy of the image into pinned
+ * memory, enqueue (H2D + CUDA-graph launch + D2H requests), waiting for the device, copying the results out}. */
+int orb_last_call_breakdown(const orb_extractor* h, double* us4);
+
 /* Per-stage device timing with CUDA events recorded on the launching stream between the
  * stages of every chunk (no host synchronisation is added). orb_get_stage_times synchronises,
  * returns the milliseconds and launch counts accumulated since the previous call for the 5

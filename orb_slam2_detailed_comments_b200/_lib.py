@@ -72,7 +72,7 @@ EXPORTS = [
     "orb_last_error", "orb_device_count", "orb_create", "orb_destroy", "orb_get_scale_tables",
     "orb_max_keypoints", "orb_max_keypoints_for_size", "orb_extract", "orb_extract_batch_host", "orb_extract_batch_host_async", "orb_extract_batch_device",
     "orb_extract_stereo", "orb_stereo_match", "orb_extract_stereo_batch_device",
-    "orb_synchronize", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_times", "orb_set_lanes", "orb_stage_level_size", "orb_stage_copy_level",
+    "orb_synchronize", "orb_last_launch_count", "orb_last_call_breakdown", "orb_set_profiling", "orb_get_stage_times", "orb_set_lanes", "orb_stage_level_size", "orb_stage_copy_level",
     "orb_stage_copy_blur", "orb_stage_copy_candidates", "orb_stage_copy_kept",
     "orb_compute_image_bounds", "orb_undistort_keypoints_device", "orb_assign_features_to_grid_device",
     "orb_get_features_in_area_device",
@@ -118,6 +118,7 @@ def lib():
         L.orb_extract_stereo_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, i32, vp, vp, f32, f32, vp, vp, vp]
         L.orb_synchronize.argtypes = [vp, vp]
         L.orb_last_launch_count.argtypes = [vp]
+        L.orb_last_call_breakdown.argtypes = [vp, vp]
         L.orb_set_profiling.argtypes = [vp, i32]
         L.orb_set_lanes.argtypes = [vp, i32]
         L.orb_get_stage_times.argtypes = [vp, vp, vp]

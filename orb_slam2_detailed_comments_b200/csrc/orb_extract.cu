@@ -20,6 +20,7 @@
 // workspace lanes / streams, see orb_set_lanes).
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -61,7 +62,8 @@ constexpr int kEdge = 19;       // EDGE_THRESHOLD, ORBextractor.cc:81
 constexpr int kLeftPad = 32;    // bytes left of interior column 0 in a bordered row (>= kEdge)
 constexpr int kMaxLevels = 16;
 constexpr int kHalfPatch = 15;  // HALF_PATCH_SIZE, ORBextractor.cc:80
-constexpr int kQtThreads = 256;
+constexpr int kQtThreads = 256;      // k_quadtree: threads per CTA for batches ...
+constexpr int kQtMaxThreads = 1024;  // ... and for the few-frames case (one CTA per level: more threads shorten every phase)
 constexpr int kQtSmemKeys = 4096;   // candidates of a level cached in shared memory by k_quadtree
 
 struct LevelGeom {
@@ -324,53 +326,62 @@ __global__ void __launch_bounds__(256) k_resize_border(const Geom g, int l, u8* 
 // bytes (byte loads). Mixed in one warp the long edge path used to run beside 30 idle lanes in two warps of three
 // (11.8 of 32 lanes active); here a warp does ONE kind: blocks [0, nbInt) copy interior groups, one warp per bordered
 // row, the remaining blocks do the edge groups, 4 rows x 8 groups per warp.
+// one warp: the interior groups of bordered row `by`
+__device__ __forceinline__ void level0_interior_row(const LevelGeom& L, const u8* src, size_t step, u8* dstBase, int by, int lane) {
+  const int gA = 3, gB = max(gA, (L.w - 20) / 16 + 3);          // interior groups: 16 <= c0 and c0 + 20 <= w
+  const u8* row = src + (size_t)reflect101(by - kEdge, L.h) * step;
+  u8* dst = dstBase + (long long)by * L.pitch;
+  for (int gi = gA + lane; gi < gB; gi += 32) {
+    const size_t addr = reinterpret_cast<size_t>(row + 16 * (gi - 2));
+    const unsigned* wp = reinterpret_cast<const unsigned*>(addr & ~(size_t)3);
+    const unsigned sh = (unsigned)(addr & 3) * 8;
+    const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+    uint4 out;
+    out.x = __funnelshift_r(w0, w1, sh);
+    out.y = __funnelshift_r(w1, w2, sh);
+    out.z = __funnelshift_r(w2, w3, sh);
+    out.w = __funnelshift_r(w3, w4, sh);
+    *reinterpret_cast<uint4*>(dst + 16 * gi) = out;
+  }
+}
+// one warp: the edge groups (<= 8) of the 4 bordered rows by4 .. by4+3
+__device__ __forceinline__ void level0_edge_rows(const LevelGeom& L, const u8* src, size_t step, u8* dstBase, int by4, int lane) {
+  const int rows = L.h + 2 * kEdge, groups = L.pitch >> 4;
+  const int gA = 3, gB = max(gA, (L.w - 20) / 16 + 3);
+  const int nEdge = gA + (groups - gB);                          // <= 8 for every supported width (checked by the host)
+  const int by = by4 + (lane >> 3);
+  const int k = lane & 7;
+  if (by >= rows || k >= nEdge) return;
+  const int gi = k < gA ? k : gB + (k - gA);
+  const int c0 = 16 * (gi - 2);
+  const u8* row = src + (size_t)reflect101(by - kEdge, L.h) * step;
+  unsigned v[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    unsigned acc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int x = min(max(reflect101(c0 + 4 * q + j, L.w), 0), L.w - 1);
+      acc |= (unsigned)__ldg(row + x) << (8 * j);
+    }
+    v[q] = acc;
+  }
+  *reinterpret_cast<uint4*>(dstBase + (long long)by * L.pitch + 16 * gi) = make_uint4(v[0], v[1], v[2], v[3]);
+}
+
 __global__ void __launch_bounds__(256) k_level0_border2(const Geom g, const u8* __restrict__ img, size_t step,
                                                         size_t frameStride, u8* __restrict__ pyr, size_t pyrStride,
                                                         int nbInt) {
   const LevelGeom& L = g.lv[0];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = blockIdx.y;
-  const int rows = L.h + 2 * kEdge, groups = L.pitch >> 4;
-  const int gA = 3, gB = max(gA, (L.w - 20) / 16 + 3);          // interior groups: 16 <= c0 and c0 + 20 <= w
   const u8* src = img + (size_t)f * frameStride;
   u8* dstBase = pyr + (size_t)f * pyrStride + L.off - (long long)kEdge * L.pitch - kLeftPad;
   if ((int)blockIdx.x < nbInt) {
     const int by = blockIdx.x * 8 + wid;
-    if (by >= rows) return;
-    const u8* row = src + (size_t)reflect101(by - kEdge, L.h) * step;
-    u8* dst = dstBase + (long long)by * L.pitch;
-    for (int gi = gA + lane; gi < gB; gi += 32) {
-      const size_t addr = reinterpret_cast<size_t>(row + 16 * (gi - 2));
-      const unsigned* wp = reinterpret_cast<const unsigned*>(addr & ~(size_t)3);
-      const unsigned sh = (unsigned)(addr & 3) * 8;
-      const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
-      uint4 out;
-      out.x = __funnelshift_r(w0, w1, sh);
-      out.y = __funnelshift_r(w1, w2, sh);
-      out.z = __funnelshift_r(w2, w3, sh);
-      out.w = __funnelshift_r(w3, w4, sh);
-      *reinterpret_cast<uint4*>(dst + 16 * gi) = out;
-    }
+    if (by < L.h + 2 * kEdge) level0_interior_row(L, src, step, dstBase, by, lane);
   } else {
-    const int nEdge = gA + (groups - gB);                        // <= 8 for every supported width (checked by the host)
-    const int by = (((int)blockIdx.x - nbInt) * 8 + wid) * 4 + (lane >> 3);
-    const int k = lane & 7;
-    if (by >= rows || k >= nEdge) return;
-    const int gi = k < gA ? k : gB + (k - gA);
-    const int c0 = 16 * (gi - 2);
-    const u8* row = src + (size_t)reflect101(by - kEdge, L.h) * step;
-    unsigned v[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      unsigned acc = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int x = min(max(reflect101(c0 + 4 * q + j, L.w), 0), L.w - 1);
-        acc |= (unsigned)__ldg(row + x) << (8 * j);
-      }
-      v[q] = acc;
-    }
-    *reinterpret_cast<uint4*>(dstBase + (long long)by * L.pitch + 16 * gi) = make_uint4(v[0], v[1], v[2], v[3]);
+    level0_edge_rows(L, src, step, dstBase, (((int)blockIdx.x - nbInt) * 8 + wid) * 4, lane);
   }
 }
 
@@ -387,18 +398,18 @@ __global__ void __launch_bounds__(256) k_level0_border2(const Geom g, const u8* 
 // rows after which an output row is due, so the row loop has a fixed trip count, one predictable branch and no global
 // loads besides the pixels. Output rows use strictly increasing source rows (scale factor > 1; checked by the host).
 constexpr int kRzThreads = 64, kRzBand = 32;
-__global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
-                                                             const int2* __restrict__ taps, int bandRows) {
+// One warp: 32 column groups starting at column cFirst, output rows [j0, j1) (at most 32) of level l of one frame
+// (`frame` = the frame's pyramid slab). CG: source pixels are read with ld.global.cg - the single-launch pyramid reads
+// rows another CTA of the same launch has just written, which must not be served from a stale L1 line.
+template <bool CG>
+__device__ __forceinline__ void resize_strip_warp(const Geom& g, int l, u8* __restrict__ frame, const int2* __restrict__ taps,
+                                                  int cFirst, int j0, int j1, int lane) {
   const LevelGeom& D = g.lv[l];
   const LevelGeom& S = g.lv[l - 1];
-  const int lane = threadIdx.x & 31;
   // column groups cover the BORDERED width: columns -20 .. w+18 in aligned words; a border column takes the taps of the
   // interior column it mirrors (REFLECT_101), so the left / right border of an interior row costs ~10 extra groups per row
   const int cLast = ((D.w + kEdge - 1 + 20) & ~3) - 20;                     // first column of the last group
-  const int cFirst = 4 * (blockIdx.x * kRzThreads + (threadIdx.x & ~31)) - 20;   // first column of this warp
-  const int j0 = blockIdx.y * bandRows, j1 = min(j0 + bandRows, D.h);
-  if (cFirst > cLast || j0 >= j1) return;                                   // warp-uniform
-  const int f = blockIdx.z;
+  if (cFirst > cLast || j0 >= j1) return;                                    // warp-uniform
   const int cMine = cFirst + 4 * lane;
   const bool active = cMine <= cLast;
   const int c0 = active ? cMine : cLast;                                    // idle lanes shadow the last column group
@@ -422,19 +433,20 @@ __global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l
   const int nIter = __shfl_sync(0xffffffffu, ds, j1 - 1 - j0) + 1; // source rows r0+1 .. r0+nIter are filtered in the loop
   const int spw = S.pitch >> 2, dpw = D.pitch >> 2;
   const int lastRow = S.h - 1;
-  const unsigned* q = reinterpret_cast<const unsigned*>(pyr + (size_t)f * pyrStride + S.off - kLeftPad) + (a0 >> 2) +
-                      (long long)r0 * spw;
-  unsigned* dp = reinterpret_cast<unsigned*>(pyr + (size_t)f * pyrStride + D.off + (long long)j0 * D.pitch + c0);
+  const unsigned* q = reinterpret_cast<const unsigned*>(frame + S.off - kLeftPad) + (a0 >> 2) + (long long)r0 * spw;
+  unsigned* dp = reinterpret_cast<unsigned*>(frame + D.off + (long long)j0 * D.pitch + c0);
+  auto ld = [](const unsigned* p) { return CG ? __ldcg(p) : *p; };
 
   unsigned hc[4], hn[4];
   {
-    const unsigned lo = __funnelshift_r(q[0], q[1], sh), hi = __funnelshift_r(q[1], q[2], sh);
+    const unsigned q0 = ld(q), q1 = ld(q + 1), q2 = ld(q + 2);
+    const unsigned lo = __funnelshift_r(q0, q1, sh), hi = __funnelshift_r(q1, q2, sh);
 #pragma unroll
     for (int j = 0; j < 4; j++) hc[j] = __dp2a_lo((unsigned)tx[j].y, __byte_perm(lo, hi, sel[j]), 0u) >> 4;
   }
   int r = r0;                                                      // source row held in hc
   if (r < lastRow) q += spw;                                       // the bottom row is its own successor (:A.2 clamp)
-  unsigned u0 = q[0], u1 = q[1], u2 = q[2];
+  unsigned u0 = ld(q), u1 = ld(q + 1), u2 = ld(q + 2);
   int jj = 0;
 #pragma unroll 2
   for (int t = 0; t < nIter; t++) {
@@ -445,7 +457,7 @@ __global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l
     }
     r++;
     if (r < lastRow) q += spw;                                     // request the row after it now
-    u0 = q[0]; u1 = q[1]; u2 = q[2];
+    u0 = ld(q); u1 = ld(q + 1); u2 = ld(q + 2);
     if ((unsigned)due & 1u) {                                      // an output row uses (hc, hn); warp-uniform
       const unsigned cy = (unsigned)__shfl_sync(0xffffffffu, tyMine.y, jj);
       // (((cy0*h0)>>16) + ((cy1*h1)>>16) + 2) >> 2 with plain 32-bit multiplies (cy*h < 2^27; IMAD.HI is slow): the +2 rides
@@ -465,24 +477,95 @@ __global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l
   }
 }
 
+__global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
+                                                             const int2* __restrict__ taps, int bandRows) {
+  const int j0 = blockIdx.y * bandRows;
+  resize_strip_warp<false>(g, l, pyr + (size_t)blockIdx.z * pyrStride, taps, 4 * (blockIdx.x * kRzThreads + (threadIdx.x & ~31)) - 20, j0,
+                           min(j0 + bandRows, g.lv[l].h), threadIdx.x & 31);
+}
+
 // Top / bottom border rows of levels 1.. (copyMakeBorder(REFLECT_101) :1695): the strips have written every interior row
 // over the whole bordered width, so a border row is an aligned 16-byte copy of the interior row it mirrors. One launch for
 // all levels, one warp per row.
 struct BorderJobs { int base[kMaxLevels + 1]; };   // first block of every level (5 blocks of 8 rows each)
 
+// one warp: border row k (0..18 top, 19..37 bottom) of level l of one frame
+template <bool CG>
+__device__ __forceinline__ void border_row_copy(const LevelGeom& L, u8* frame, int k, int lane) {
+  if (k >= 2 * kEdge) return;
+  const int by = k < kEdge ? k : L.h + k;                         // bordered row
+  u8* plane = frame + L.off - kLeftPad;                           // byte 0 of interior row 0
+  const uint4* srow = reinterpret_cast<const uint4*>(plane + (long long)reflect101(by - kEdge, L.h) * L.pitch);
+  uint4* drow = reinterpret_cast<uint4*>(plane + (long long)(by - kEdge) * L.pitch);
+  for (int gi = lane; gi < (L.pitch >> 4); gi += 32) drow[gi] = CG ? __ldcg(srow + gi) : srow[gi];
+}
+
 __global__ void __launch_bounds__(256) k_fill_borders(const Geom g, u8* __restrict__ pyr, size_t pyrStride, const BorderJobs jobs) {
   int l = 1;
 #pragma unroll 1
   while (l + 1 < g.nlevels && (int)blockIdx.x >= jobs.base[l + 1]) l++;
-  const LevelGeom& L = g.lv[l];
-  const int lane = threadIdx.x & 31;
-  const int k = (blockIdx.x - jobs.base[l]) * 8 + (threadIdx.x >> 5);   // 0..37: top rows, then bottom rows
-  if (k >= 2 * kEdge) return;
-  const int by = k < kEdge ? k : L.h + k;                         // bordered row
-  u8* plane = pyr + (size_t)blockIdx.y * pyrStride + L.off - kLeftPad;   // byte 0 of interior row 0
-  const uint4* srow = reinterpret_cast<const uint4*>(plane + (long long)reflect101(by - kEdge, L.h) * L.pitch);
-  uint4* drow = reinterpret_cast<uint4*>(plane + (long long)(by - kEdge) * L.pitch);
-  for (int gi = lane; gi < (L.pitch >> 4); gi += 32) drow[gi] = srow[gi];
+  border_row_copy<false>(g.lv[l], pyr + (size_t)blockIdx.y * pyrStride, (blockIdx.x - jobs.base[l]) * 8 + (threadIdx.x >> 5),
+                         threadIdx.x & 31);
+}
+
+// ------------------------------------------------------------------------------------------
+// The whole pyramid of a few frames in ONE launch (the per-frame drop-in call: 9 dependent launches cost ~45 us of
+// launch latency for ~10 us of work). Persistent CTAs draw work items from a counter, in an order in which every item's
+// producers come earlier: level-0 bands (8 bordered rows), then per level bands of 4 output rows, then the top / bottom
+// border rows. An item waits (one thread polls, acquire) until the bands of the level below that hold its source rows
+// are flagged done (release after a __threadfence of every writer); the waited-for items were drawn earlier, by CTAs that
+// are running and never wait on later items, so the scheme cannot deadlock whatever the number of resident CTAs.
+// ------------------------------------------------------------------------------------------
+struct PyrItem { short kind, level; int band; int depLevel, depFirst, depLast; };   // kind 0 level-0 band, 1 strip band, 2 border rows
+struct PyrPlan { int nItems; int bandBase[kMaxLevels + 1]; };                       // flags of level l start at bandBase[l]
+constexpr int kPyrFusedBand = 4;    // output rows per strip item
+constexpr int kPyrFusedMaxFrames = 4;
+
+__global__ void __launch_bounds__(256) k_pyramid_fused(const Geom g, const u8* __restrict__ img, size_t step, size_t frameStride,
+                                                       u8* __restrict__ pyr, size_t pyrStride, const int2* __restrict__ taps,
+                                                       const PyrItem* __restrict__ items, const PyrPlan plan, int B,
+                                                       int* __restrict__ flags, int* __restrict__ counter) {
+  __shared__ int s_item;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int totalBands = plan.bandBase[g.nlevels];
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
+    __syncthreads();
+    const int gi = s_item;
+    __syncthreads();
+    if (gi >= plan.nItems * B) return;
+    const int f = gi % B;
+    const PyrItem it = items[gi / B];
+    int* fl = flags + (size_t)f * totalBands;
+    if (it.depFirst <= it.depLast) {
+      if (threadIdx.x == 0) {
+        for (int d = it.depFirst; d <= it.depLast; d++) {
+          const int* p = fl + plan.bandBase[it.depLevel] + d;
+          while (atomicAdd(const_cast<int*>(p), 0) == 0) __nanosleep(64);
+        }
+        __threadfence();
+      }
+      __syncthreads();
+    }
+    u8* frame = pyr + (size_t)f * pyrStride;
+    if (it.kind == 0) {
+      const LevelGeom& L = g.lv[0];
+      const u8* src = img + (size_t)f * frameStride;
+      u8* dstBase = frame + L.off - (long long)kEdge * L.pitch - kLeftPad;
+      const int by = it.band * 8 + wid;
+      if (by < L.h + 2 * kEdge) level0_interior_row(L, src, step, dstBase, by, lane);
+      if (wid < 2) level0_edge_rows(L, src, step, dstBase, it.band * 8 + 4 * wid, lane);
+    } else if (it.kind == 1) {
+      const LevelGeom& D = g.lv[it.level];
+      const int j0 = it.band * kPyrFusedBand, j1 = min(j0 + kPyrFusedBand, D.h);
+      for (int c = -20 + 128 * wid; c <= D.w + kEdge - 1; c += 128 * 8) resize_strip_warp<true>(g, it.level, frame, taps, c, j0, j1, lane);
+    } else {
+      for (int k = it.band * 8 + wid; k < min(it.band * 8 + 8, 2 * kEdge); k += 8) border_row_copy<true>(g.lv[it.level], frame, k, lane);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && it.kind != 2) atomicExch(fl + plan.bandBase[it.level] + it.band, 1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -935,7 +1018,7 @@ __device__ int block_scan_excl(int* a, int n, int* tmp /* >= 34 ints */) {
 //    independent of the others, so the stop position is a prefix-sum search;
 //  * every new node is pushed to the list front, so final list order == descending creation seq.
 // Canonical tie rule (the reference sorts by heap address): later-created node first.
-__global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uint2* __restrict__ cand,
+__global__ void __launch_bounds__(kQtMaxThreads) k_quadtree(const Geom g, const uint2* __restrict__ cand,
                                                          const int* __restrict__ candCount,
                                                          unsigned short* __restrict__ keyNode,
                                                          uint2* __restrict__ kept, int* __restrict__ keptCount,
@@ -946,7 +1029,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
   __shared__ int s_nc, s_nexp, s_cut, s_roots;
   // grid = (frames, levels): CTAs are dispatched x-fastest, so all frames of level 0 (the most candidates, the longest
   // CTAs) start first and the short top levels fill the tail
-  const int l = blockIdx.y, f = blockIdx.x, tid = threadIdx.x;
+  const int l = blockIdx.y, f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   const LevelGeom& L = g.lv[l];
   int n = candCount[f * g.nlevels + l];
   if (n > L.candCap) {
@@ -982,7 +1065,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
   const unsigned* XY;          // generic pointers: shared or global
   unsigned short* KNp;
   if (inSmem) {
-    for (int k = tid; k < n; k += kQtThreads) s_xy[k] = C[k].x;
+    for (int k = tid; k < n; k += T) s_xy[k] = C[k].x;
     XY = s_xy;
     KNp = s_kn;
   } else {
@@ -1008,7 +1091,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
     nodes[tid] = r;
   }
   __syncthreads();
-  for (int k = tid; k < n; k += kQtThreads) {
+  for (int k = tid; k < n; k += T) {
     const int xr = (int)((inSmem ? XY[k] : C[k].x) & 0xffffu) - 16;
     int r = (int)__fdiv_rn((float)xr, hX);
     r = min(max(r, 0), nIni - 1);
@@ -1025,7 +1108,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
     s_roots = m;
   }
   __syncthreads();
-  for (int k = tid; k < n; k += kQtThreads) KNp[k] = (unsigned short)slot[KNp[k]];
+  for (int k = tid; k < n; k += T) KNp[k] = (unsigned short)slot[KNp[k]];
   int numNodes = s_roots;
   { QtNode* t = nodes; nodes = nodes2; nodes2 = t; }
   int seqCounter = nIni;
@@ -1034,15 +1117,15 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
 
   for (;;) {
     const int prev = numNodes;
-    for (int i = tid; i < 4 * numNodes; i += kQtThreads) childCnt[i] = 0;
+    for (int i = tid; i < 4 * numNodes; i += T) childCnt[i] = 0;
     if (tid == 0) { s_nc = 0; s_nexp = 0; s_cut = 0x7fffffff; }
     __syncthreads();
-    for (int i = tid; i < numNodes; i += kQtThreads) {
+    for (int i = tid; i < numNodes; i += T) {
       slot[i] = 1;
       nodeRank[i] = -1;
       if (nodes[i].count > 1) candList[atomicAdd(&s_nc, 1)] = i;
     }
-    for (int k = tid; k < n; k += kQtThreads) {
+    for (int k = tid; k < n; k += T) {
       const int nd = KNp[k];
       const QtNode Nd = nodes[nd];
       if (Nd.count > 1) {
@@ -1053,7 +1136,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
     __syncthreads();
     const int nc = s_nc;
     if (nc == 0) break;  // nothing left to split: list size unchanged (:890)
-    for (int i = tid; i < nc; i += kQtThreads) {
+    for (int i = tid; i < nc; i += T) {
       const QtNode& Nd = nodes[candList[i]];
       key64[i] = (partial ? ((unsigned long long)(unsigned)Nd.count << 32) : 0ull) | (unsigned)Nd.seq;
     }
@@ -1063,18 +1146,18 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
     const int words = (seqCounter + 31) >> 5;
     const bool byBitmap = !partial && words <= seqWords;
     if (byBitmap) {
-      for (int w = tid; w < words; w += kQtThreads) bm[w] = 0u;
+      for (int w = tid; w < words; w += T) bm[w] = 0u;
       __syncthreads();
-      for (int i = tid; i < nc; i += kQtThreads) {
+      for (int i = tid; i < nc; i += T) {
         const unsigned sq = (unsigned)key64[i];
         atomicOr(&bm[sq >> 5], 1u << (sq & 31));
       }
       __syncthreads();
-      for (int w = tid; w < words; w += kQtThreads) bmPre[w] = __popc(bm[w]);
+      for (int w = tid; w < words; w += T) bmPre[w] = __popc(bm[w]);
       __syncthreads();
       block_scan_excl(bmPre, words, s_tmp);
     }
-    for (int i = tid; i < nc; i += kQtThreads) {
+    for (int i = tid; i < nc; i += T) {
       const unsigned long long ki = key64[i];
       int r = 0;
       if (byBitmap) {
@@ -1113,14 +1196,14 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
       __syncthreads();
       cut = min(s_cut, nc - 1);
     }
-    for (int i = tid; i < nc; i += kQtThreads) {
+    for (int i = tid; i < nc; i += T) {
       const int nd = candList[i];
       if (nodeRank[nd] <= cut) slot[nd] = byRank[nodeRank[nd]] + 1;
       else nodeRank[nd] = -1;
     }
     __syncthreads();
     const int total = block_scan_excl(slot, numNodes, s_tmp);
-    for (int i = tid; i < numNodes; i += kQtThreads) {
+    for (int i = tid; i < numNodes; i += T) {
       const QtNode Nd = nodes[i];
       const int base = slot[i], r = nodeRank[i];
       if (r < 0) {
@@ -1149,7 +1232,7 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
       }
     }
     __syncthreads();
-    for (int k = tid; k < n; k += kQtThreads) {
+    for (int k = tid; k < n; k += T) {
       const int nd = KNp[k];
       if (nodeRank[nd] < 0) {
         KNp[k] = (unsigned short)slot[nd];
@@ -1170,9 +1253,9 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
 
   // best response per node, earliest candidate wins ties (:1004-1029); the reference's
   // candidate order (cell-row-major, row-major inside a cell) is a function of (x,y).
-  for (int i = tid; i < numNodes; i += kQtThreads) key64[i] = 0ull;
+  for (int i = tid; i < numNodes; i += T) key64[i] = 0ull;
   __syncthreads();
-  for (int k = tid; k < n; k += kQtThreads) {
+  for (int k = tid; k < n; k += T) {
     const uint2 c = C[k];
     const int x = (int)(c.x & 0xffffu) - kEdge, y = (int)(c.x >> 16) - kEdge;
     const int ci = y / L.hCell, cj = x / L.wCell;
@@ -1185,18 +1268,18 @@ __global__ void __launch_bounds__(kQtThreads) k_quadtree(const Geom g, const uin
   const int wordsF = (seqCounter + 31) >> 5;
   const bool bitmapF = wordsF <= seqWords;
   if (bitmapF) {
-    for (int w = tid; w < wordsF; w += kQtThreads) bm[w] = 0u;
+    for (int w = tid; w < wordsF; w += T) bm[w] = 0u;
     __syncthreads();
-    for (int i = tid; i < numNodes; i += kQtThreads) {
+    for (int i = tid; i < numNodes; i += T) {
       const unsigned sq = (unsigned)nodes[i].seq;
       atomicOr(&bm[sq >> 5], 1u << (sq & 31));
     }
     __syncthreads();
-    for (int w = tid; w < wordsF; w += kQtThreads) bmPre[w] = __popc(bm[w]);
+    for (int w = tid; w < wordsF; w += T) bmPre[w] = __popc(bm[w]);
     __syncthreads();
     block_scan_excl(bmPre, wordsF, s_tmp);
   }
-  for (int i = tid; i < numNodes; i += kQtThreads) {
+  for (int i = tid; i < numNodes; i += T) {
     const int s = nodes[i].seq;
     int r = 0;
     if (bitmapF) {
@@ -1991,6 +2074,13 @@ struct orb_extractor {
   int qtSeqWords = 0;
   FastSmemLayout fastLay;
   BorderJobs borderJobs = {};    // block ranges of k_fill_borders
+  // k_pyramid_fused (few frames per call): item table + dependency flags / work counter
+  std::vector<PyrItem> pyrItems;
+  PyrPlan pyrPlan = {};
+  PyrItem* d_pyrItems = nullptr;
+  int* d_pyrFlags = nullptr;     // kPyrFusedMaxFrames x bands flags, then the work counter
+  bool pyrFused = false;         // ORB_B200_PYR_FUSED=1: the single-launch pyramid for <= 4 frames (measured slower: 56 vs 47 us)
+  int numSMs = 148;
   int borderBlocks = 0;
   bool pyrTiled = true;          // k_level0_border2 + k_resize_strip + k_fill_borders (ORB_B200_PYR=0: the first-round kernels)
   int fastBlocks = 0, fastWarps = 4;
@@ -2057,6 +2147,9 @@ struct orb_extractor {
   // the last orb_extract call's results are still on the device (pyramid in workspace frame 0, keypoints / descriptors /
   // count in the first staging set): what orb_stereo_match pairs up (0 = nothing valid)
   int singleCap = 0, singleW = 0, singleH = 0;
+  // host wall-clock breakdown of the last orb_extract call (microseconds): staging copy of the image into pinned memory,
+  // enqueue (H2D + graph launch + D2H requests), wait for the device, copy-out of the results
+  double callUs[4] = {0, 0, 0, 0};
   // optional per-stage CUDA-event timing (bench roofline): 6 boundary events per chunk
   bool profile = false;
   std::vector<cudaEvent_t> evPool;
@@ -2238,6 +2331,48 @@ int build_geom(orb_extractor* e, int W, int H) {
     e->borderJobs.base[0] = 0;
     e->borderJobs.base[nl] = blocks;
     e->borderBlocks = blocks;
+    // item table of k_pyramid_fused: producers before consumers
+    {
+      auto refl = [](int p, int n) { p = p < 0 ? -p : p; return p >= n ? 2 * (n - 1) - p : p; };
+      e->pyrItems.clear();
+      PyrPlan& P = e->pyrPlan;
+      int base = 0;
+      P.bandBase[0] = 0;
+      const int nb0 = (g.lv[0].h + 2 * kEdge + 7) / 8;
+      for (int b = 0; b < nb0; b++) e->pyrItems.push_back(PyrItem{0, 0, b, 0, 1, 0});
+      base += nb0;
+      for (int l = 1; l < nl; l++) {
+        P.bandBase[l] = base;
+        const LevelGeom& D = g.lv[l];
+        const LevelGeom& S = g.lv[l - 1];
+        const int2* tY = e->taps.data() + D.tapY;
+        const int nb = (D.h + kPyrFusedBand - 1) / kPyrFusedBand;
+        for (int b = 0; b < nb; b++) {
+          const int j0 = b * kPyrFusedBand, j1 = std::min(j0 + kPyrFusedBand, D.h);
+          const int sy0 = tY[j0].x, sy1 = std::min(tY[j1 - 1].x + 1, S.h - 1);
+          PyrItem it{1, (short)l, b, l - 1, 0, 0};
+          if (l == 1) { it.depFirst = (sy0 + kEdge) / 8; it.depLast = (sy1 + kEdge) / 8; }
+          else { it.depFirst = sy0 / kPyrFusedBand; it.depLast = sy1 / kPyrFusedBand; }
+          e->pyrItems.push_back(it);
+        }
+        base += nb;
+      }
+      P.bandBase[nl] = base;
+      for (int l = 1; l < nl; l++) {
+        const LevelGeom& D = g.lv[l];
+        for (int b = 0; b * 8 < 2 * kEdge; b++) {
+          int lo = 1 << 30, hi = -1;
+          for (int k = b * 8; k < std::min(b * 8 + 8, 2 * kEdge); k++) {
+            const int by = k < kEdge ? k : D.h + k;
+            const int r = refl(by - kEdge, D.h);
+            lo = std::min(lo, r); hi = std::max(hi, r);
+          }
+          e->pyrItems.push_back(PyrItem{2, (short)l, b, l, lo / kPyrFusedBand, hi / kPyrFusedBand});
+        }
+      }
+      P.nItems = (int)e->pyrItems.size();
+      if (const char* ev = getenv("ORB_B200_PYR_FUSED")) e->pyrFused = atoi(ev) != 0;
+    }
     e->pyrTiled = ok;
   }
   // sequence-number bitmap of k_quadtree: every refinement round hands out 4 numbers per split node; rounds are bounded
@@ -2363,6 +2498,11 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
     free_workspace(e);
     ORB_CUDA(cudaMalloc(&e->d_taps, std::max<size_t>(1, e->taps.size()) * sizeof(int2)));
     ORB_CUDA(cudaMemcpy(e->d_taps, e->taps.data(), e->taps.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    cudaFree(e->d_pyrItems); cudaFree(e->d_pyrFlags);
+    e->d_pyrItems = nullptr; e->d_pyrFlags = nullptr;
+    ORB_CUDA(cudaMalloc(&e->d_pyrItems, std::max<size_t>(1, e->pyrItems.size()) * sizeof(PyrItem)));
+    ORB_CUDA(cudaMemcpy(e->d_pyrItems, e->pyrItems.data(), e->pyrItems.size() * sizeof(PyrItem), cudaMemcpyHostToDevice));
+    ORB_CUDA(cudaMalloc(&e->d_pyrFlags, ((size_t)kPyrFusedMaxFrames * e->pyrPlan.bandBase[e->g.nlevels] + 1) * sizeof(int)));
     ORB_CUDA(raise_dynamic_smem(k_quadtree, e->qtSmem));
     ORB_CUDA(raise_dynamic_smem(k_fast_cells, e->fastSmem));
     ORB_CUDA(raise_dynamic_smem(k_describe, kDescSmem));
@@ -2372,6 +2512,7 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
       ORB_CUDA(cudaGetDevice(&dev));
       ORB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       e->fastBlocks = std::max(1, perSM) * std::max(1, sms);
+      e->numSMs = std::max(1, sms);
     }
     e->haveGeom = true;
   }
@@ -2417,7 +2558,19 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   int launches = 0, st;
   if ((st = stage_mark(e, s))) return st;
   const bool l0fork = !e->pyrTiled && !e->profile && e->l0Fork && nl > 1;
-  if (e->pyrTiled) {
+  int pyrLaunches = nl;
+  if (e->pyrTiled && e->pyrFused && B <= kPyrFusedMaxFrames && lane == 0) {
+    // few frames: the whole pyramid in one dependency-driven launch
+    const size_t flagInts = (size_t)B * e->pyrPlan.bandBase[nl];
+    ORB_CUDA(cudaMemsetAsync(e->d_pyrFlags, 0, ((size_t)kPyrFusedMaxFrames * e->pyrPlan.bandBase[nl] + 1) * sizeof(int), s));
+    (void)flagInts;
+    const int blocks = std::min(e->pyrPlan.nItems * B, 2 * e->numSMs);
+    k_pyramid_fused<<<blocks, 256, 0, s>>>(g, d_img, step, frameStride, W.pyr, e->pyrStride, e->d_taps, e->d_pyrItems, e->pyrPlan, B,
+                                           e->d_pyrFlags, e->d_pyrFlags + (size_t)kPyrFusedMaxFrames * e->pyrPlan.bandBase[nl]);
+    launches++;
+    pyrLaunches = 1;
+  } else if (e->pyrTiled) {
+    pyrLaunches = nl > 1 ? nl + 1 : nl;
     const LevelGeom& L0 = g.lv[0];
     const int rows0 = L0.h + 2 * kEdge;
     const int nbInt = (rows0 + 7) / 8, nbEdge = (rows0 + 31) / 32;
@@ -2479,7 +2632,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     ORB_CUDA(cudaEventRecord(e->evBlurGo[lane], s));
     ORB_CUDA(cudaStreamWaitEvent(bs, e->evBlurGo[lane], 0));
   }
-  k_quadtree<<<dim3(B, nl), kQtThreads, e->qtSmem, s>>>(g, W.cand, W.candCount, W.keyNode, W.kept,
+  k_quadtree<<<dim3(B, nl), B <= 4 ? kQtMaxThreads : kQtThreads, e->qtSmem, s>>>(g, W.cand, W.candCount, W.keyNode, W.kept,
                                                        W.keptCount, e->candTotal, e->keptTotal, e->nodeCap, e->qtSeqWords,
                                                        e->d_overflow);
   launches++;
@@ -2505,7 +2658,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   if ((st = stage_mark(e, s))) return st;
   ORB_CUDA(cudaGetLastError());
   if (e->profile) {
-    e->stageLaunches[0] += e->pyrTiled && nl > 1 ? nl + 1 : nl; e->stageLaunches[1]++; e->stageLaunches[2]++; e->stageLaunches[3]++; e->stageLaunches[4]++;
+    e->stageLaunches[0] += pyrLaunches; e->stageLaunches[1]++; e->stageLaunches[2]++; e->stageLaunches[3]++; e->stageLaunches[4]++;
   }
   e->lastLaunches += launches;
   e->lastChunkFrames = B;
@@ -2762,6 +2915,7 @@ int orb_destroy(orb_extractor* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   free_workspace(e);
   cudaFree(e->d_taps); cudaFree(e->d_pattern); cudaFree(e->d_overflow); cudaFree(e->d_work); cudaFree(e->d_invScale);
+  cudaFree(e->d_pyrItems); cudaFree(e->d_pyrFlags);
   for (int b = 0; b < 2; b++) { cudaFree(e->d_uRight[b]); cudaFree(e->d_depth[b]); }
   for (int b = 0; b < 2; b++) {
     cudaFree(e->d_in[b]); cudaFree(e->d_kps[b]); cudaFree(e->d_desc[b]); cudaFree(e->d_n[b]);
@@ -2886,6 +3040,12 @@ int orb_synchronize(orb_extractor* e, void* stream) {
 }
 
 int orb_last_launch_count(const orb_extractor* e) { return e ? e->lastLaunches : 0; }
+
+int orb_last_call_breakdown(const orb_extractor* e, double* us4) {
+  if (!e || !us4) ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  for (int k = 0; k < 4; k++) us4[k] = e->callUs[k];
+  return ORB_OK;
+}
 
 int orb_set_lanes(orb_extractor* e, int lanes) {
   if (!e || lanes < 1 || lanes > 2) ORB_FAIL(ORB_ERR_INVALID, "lanes must be 1 or 2");
@@ -3016,8 +3176,17 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
   const size_t oK = 64, oD = oK + round_up((size_t)m * sizeof(orb_keypoint), (size_t)64);
   st = ensure_pinned(e, dFrame, oD + (size_t)m * 32);
   if (st) return st;
-  stage_rows(e->h_in, image, width, height, step);
-  ORB_CUDA(cudaMemcpyAsync(e->d_in[0], e->h_in, dFrame, cudaMemcpyHostToDevice, s));
+  const auto t0 = std::chrono::steady_clock::now();
+  {
+    // the image goes up in two halves: the upload of the first overlaps the staging copy of the second
+    const int h0 = height / 2;
+    const size_t b0 = (size_t)h0 * width;
+    stage_rows(e->h_in, image, width, h0, step);
+    if (b0) ORB_CUDA(cudaMemcpyAsync(e->d_in[0], e->h_in, b0, cudaMemcpyHostToDevice, s));
+    stage_rows(e->h_in + b0, image + (size_t)h0 * step, width, height - h0, step);
+    ORB_CUDA(cudaMemcpyAsync(e->d_in[0] + b0, e->h_in + b0, dFrame - b0, cudaMemcpyHostToDevice, s));
+  }
+  const auto t1 = std::chrono::steady_clock::now();
   st = run_call(e, 1, width, height, dFrame, capacity, false, 0.f, 0.f, s);
   if (st) return st;
   int* hc = reinterpret_cast<int*>(e->h_out);
@@ -3034,7 +3203,9 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
     }
     ORB_CUDA(cudaMemcpyAsync(e->hostPyr, e->d_pyr, e->pyrStride, cudaMemcpyDeviceToHost, s));
   }
+  const auto t2 = std::chrono::steady_clock::now();
   ORB_CUDA(cudaStreamSynchronize(s));
+  const auto t3 = std::chrono::steady_clock::now();
   st = overflow_status(e, hc[1], s);
   if (st) return st;
   const int cnt = std::min(hc[0], m);
@@ -3043,6 +3214,13 @@ int orb_extract(orb_extractor* e, const uint8_t* image, int width, int height, s
     memcpy(descriptors, e->h_out + oD, (size_t)cnt * 32);
   }
   *n = cnt;
+  {
+    const auto t4 = std::chrono::steady_clock::now();
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    e->callUs[0] = us(t0, t1); e->callUs[1] = us(t1, t2); e->callUs[2] = us(t2, t3); e->callUs[3] = us(t3, t4);
+  }
   e->singleCap = capacity; e->singleW = width; e->singleH = height;
   if (pyramid)
     for (int l = 0; l < e->g.nlevels; l++) {

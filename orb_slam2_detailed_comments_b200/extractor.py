@@ -65,12 +65,17 @@ class ORBextractor:
         if image.strides[1] != 1:
             image = np.ascontiguousarray(image)
         h, w = image.shape
-        cap = self.max_keypoints_for(w, h)
-        kps = np.zeros(cap, KP_DTYPE)
-        desc = np.zeros((cap, 32), np.uint8)
-        n = C.c_int(0)
+        key = (w, h)
+        if getattr(self, "_call_key", None) != key:   # output staging of the drop-in call, reused while the size stays
+            cap = self.max_keypoints_for(w, h)
+            self._call_key, self._call_cap = key, cap
+            self._call_kps, self._call_desc = np.empty(cap, KP_DTYPE), np.empty((cap, 32), np.uint8)
+            self._call_n = C.c_int(0)
+            self._call_ptrs = (ptr(self._call_kps), ptr(self._call_desc), C.byref(self._call_n))
+        cap, kps, desc, n = self._call_cap, self._call_kps, self._call_desc, self._call_n
+        n.value = 0
         views = (_lib.OrbLevelView * self.nlevels)() if want_pyramid else None
-        check(self._L.orb_extract(self._h, ptr(image), w, h, image.strides[0], ptr(kps), cap, C.byref(n), ptr(desc),
+        check(self._L.orb_extract(self._h, ptr(image), w, h, image.strides[0], self._call_ptrs[0], cap, self._call_ptrs[2], self._call_ptrs[1],
                                   C.cast(views, C.c_void_p) if want_pyramid else None))
         if want_pyramid:
             self.mvImagePyramid = []
@@ -147,6 +152,12 @@ class ORBextractor:
 
     def last_launch_count(self):
         return int(self._L.orb_last_launch_count(self._h))
+
+    def last_call_breakdown(self):
+        """Host wall-clock microseconds of the last __call__: staging copy, enqueue, device wait, copy-out."""
+        us = np.zeros(4, np.float64)
+        check(self._L.orb_last_call_breakdown(self._h, ptr(us)))
+        return dict(zip(("stage_copy_us", "enqueue_us", "device_wait_us", "copy_out_us"), (float(v) for v in us)))
 
     STAGES = ("pyramid", "fast", "quadtree", "blur", "describe")
 

@@ -22,3 +22,9 @@ for (w, h, nf) in ((1241, 376, 2000), (640, 480, 1000)):
         ext(img)
     wall = (time.perf_counter() - t0) / 200 * 1e3
     print(w, h, "wall ms/call %.3f" % wall, {k: round(v[0] / n * 1e3, 1) for k, v in st.items()}, "us per call (device, per stage)")
+    acc = {}
+    for _ in range(100):
+        ext(img)
+        for k, v in ext.last_call_breakdown().items():
+            acc[k] = acc.get(k, 0.0) + v / 100
+    print("   host breakdown (us):", {k: round(v, 1) for k, v in acc.items()})
