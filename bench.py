@@ -227,6 +227,24 @@ def bind_to_gpu_numa_node(props):
     return None
 
 
+def numa_node_of(t):
+    """NUMA node of the first pages of a pinned host tensor (move_pages query), or None where the kernel does not tell."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        n = 8
+        page = os.sysconf("SC_PAGESIZE")
+        base = t.data_ptr() & ~(page - 1)
+        pages = (ctypes.c_void_p * n)(*[base + i * page * 64 for i in range(n)])
+        status = (ctypes.c_int * n)()
+        if libc.syscall(279, 0, n, pages, None, status, 0) != 0:   # __NR_move_pages (x86-64), nodes = NULL: query only
+            return None
+        nodes = sorted(set(int(v) for v in status if v >= 0))
+        return nodes if nodes else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def parity_counters(ext, frames):
     """north_star: "the only allowed differences are cvRound flips ... these must be counted and reported". A sample of the
     pool's frames is extracted once more through the drop-in call and compared with the CPU oracle, OUTSIDE any timed
@@ -685,14 +703,29 @@ def run_ours(args, rank, world, local_rank):
         assert int(outs[1][2].sum()) == int(counts.sum()), "asynchronous host path and device path disagree"
     del h_kps2, h_desc2
     h2d = frames_per_step * W * H
-    # the copy engine alone on the same pinned buffer: the ceiling of any end-to-end number on this box
+    # the copy engines alone on the same pinned buffers, all ranks at once (barrier): the ceiling of any end-to-end number
+    # on this box. First the upload alone, then upload and download TOGETHER in the byte ratio of a step (two streams), which
+    # is the traffic the pipeline really generates (H2D of the frames while the previous chunk's keypoints come back).
     d_probe = torch.empty_like(d_imgs)
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(3):
         d_probe.copy_(h_imgs, non_blocking=True)
     torch.cuda.synchronize()
-    h2d_peak = 3 * h2d / (time.perf_counter() - t0) / 1e9
+    h2d_peak = 3 * h2d / max_over_ranks(time.perf_counter() - t0) / 1e9
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        with torch.cuda.stream(s_up):
+            d_probe.copy_(h_imgs, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_kps.copy_(d_kps, non_blocking=True)
+            h_desc.copy_(d_desc, non_blocking=True)
+    torch.cuda.synchronize()
+    bidir_s = max_over_ranks(time.perf_counter() - t0)
+    bidir_fps = world * 3 * frames_per_step / bidir_s
+    pinned_node = numa_node_of(h_imgs)
     del d_probe
     d2h = frames_per_step * (cap * 60 + 4)
     del h_imgs, h_kps, h_desc
@@ -838,8 +871,14 @@ def run_ours(args, rank, world, local_rank):
                 "api": "orb_extract_batch_host_async per step + orb_synchronize at the end (pinned host buffers)",
                 "value_blocking_calls": e2e_sync_fps, "api_blocking": "orb_extract_batch_host (returns when the step's results are on the host)",
                 "h2d_GBps_in_run": e2e_fps / world * W * H / 1e9,
+                "d2h_GBps_in_run": e2e_fps / world * (cap * 60 + 4) / 1e9,
                 "h2d_GBps_copy_engine_alone": h2d_peak,
-                "ceiling_frames_per_s": h2d_peak * 1e9 / (W * H) * world},
+                "ceiling_frames_per_s": h2d_peak * 1e9 / (W * H) * world,
+                "ceiling_frames_per_s_upload_and_download": bidir_fps,
+                "frac_of_bidirectional_copy_ceiling": e2e_fps / bidir_fps,
+                "limiter": "host <-> device copies: the copy engines alone (upload of the frames and download of the keypoints / descriptors "
+                           "of a step, concurrently, all ranks at once) move a step's bytes at ceiling_frames_per_s_upload_and_download",
+                "pinned_buffer_numa_node": pinned_node},
         "gpu_launches": launches_per_step * args.steps + e2e_launches + stereo_launches + frame_launches + track_launches + input_launches + m_steps + (2 * world if allpairs else 0) + seq_launches,
         "stereo": stereo,
         "frame_helpers": frame_helpers,

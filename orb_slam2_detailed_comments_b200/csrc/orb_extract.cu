@@ -1439,6 +1439,7 @@ constexpr int kPatchWords = 12;   // blurred patch: 37 rows x 48 bytes (37 + 8-b
 constexpr int kMomWords = 10;     // unblurred patch: 31 rows x 40 bytes (31 + 8-byte alignment slack), 5 chunks of 8 B
 constexpr int kDescSlots = 16;    // keypoint slots per CTA (8 warps x 2: 28 KB of patches per CTA keeps 8 CTAs per SM)
 constexpr int kDescPerWarp = kDescSlots / 8;
+constexpr int kDescRounds = 1;    // rounds of kDescSlots keypoints per CTA of k_describe_tma (2 amortises the per-lane set-up but needs 64 registers: 4 instead of 5 CTAs per SM, measured 3.27 vs 3.17 ms)
 constexpr int kPatchBufWords = 37 * kPatchWords;  // one buffer holds either patch
 constexpr int kDescSmem = 8 * kDescPerWarp * kPatchBufWords * 4;
 
@@ -1498,18 +1499,14 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
   {
     const int v = lane - kHalfPatch;
     const int d = lane < 31 ? c_umax[v < 0 ? -v : v] : -1;
+    // columns 15-d .. 15+d of the row as a 31-bit mask; a nibble of it becomes 4 bytes of 0 / 1 with one multiply
+    // (bit j -> bit 8j: the partial products of 0x00204081 do not collide), the weights (u + 15) with a second one
+    const unsigned rowMask = d < 0 ? 0u : ((2u << (2 * d)) - 1u) << (kHalfPatch - d);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      unsigned a = 0, b = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int u = 4 * k + j - kHalfPatch;
-        const bool in = (u < 0 ? -u : u) <= d;
-        a |= (in ? 1u : 0u) << (8 * j);
-        b |= (in ? (unsigned)(u + kHalfPatch) : 0u) << (8 * j);
-      }
-      w1[k] = a;
-      wu[k] = b;
+      const unsigned ones = (((rowMask >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u;
+      w1[k] = ones;
+      wu[k] = (ones * 0xffu) & (0x03020100u + 0x04040404u * (unsigned)k);
     }
   }
   __syncthreads();
@@ -1523,8 +1520,8 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
     const int slotIdx = slot0 + wid * kDescPerWarp + k;
     lvl[k] = -1; px[k] = py[k] = resp[k] = 0;
     if (slotIdx < total) {
-      int l = 0;
-      while (l + 1 < g.nlevels && slotIdx >= s_prefix[l + 1]) l++;
+      // octave of output slot slotIdx: the number of level prefixes it has passed (lane q looks at level q)
+      const int l = __popc(__ballot_sync(0xffffffffu, lane >= 1 && lane < g.nlevels && slotIdx >= s_prefix[lane]));
       const LevelGeom& L = g.lv[l];
       const uint2 rec = kept[(size_t)f * keptTotal + L.keptOff + (slotIdx - s_prefix[l])];
       lvl[k] = l; px[k] = (int)(rec.x & 0xffffu); py[k] = (int)(rec.x >> 16); resp[k] = (int)rec.y;
@@ -1663,7 +1660,6 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
   __shared__ int s_prefix[kMaxLevels + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = blockIdx.y;
-  const int slot0 = blockIdx.x * kDescSlots;
   unsigned char* bufs = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(s_raw) + 127) & ~(size_t)127);
   unsigned char* wbuf = bufs + wid * (kDescPerWarp * kTmaBufBytes);
   if (threadIdx.x == 0) {
@@ -1685,23 +1681,24 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
   {
     const int v = lane - kHalfPatch;
     const int d = lane < 31 ? c_umax[v < 0 ? -v : v] : -1;
+    // columns 15-d .. 15+d of the row as a 31-bit mask; a nibble of it becomes 4 bytes of 0 / 1 with one multiply
+    // (bit j -> bit 8j: the partial products of 0x00204081 do not collide), the weights (u + 15) with a second one
+    const unsigned rowMask = d < 0 ? 0u : ((2u << (2 * d)) - 1u) << (kHalfPatch - d);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      unsigned a = 0, b = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int u = 4 * k + j - kHalfPatch;
-        const bool in = (u < 0 ? -u : u) <= d;
-        a |= (in ? 1u : 0u) << (8 * j);
-        b |= (in ? (unsigned)(u + kHalfPatch) : 0u) << (8 * j);
-      }
-      w1[k] = a;
-      wu[k] = b;
+      const unsigned ones = (((rowMask >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u;
+      w1[k] = ones;
+      wu[k] = (ones * 0xffu) & (0x03020100u + 0x04040404u * (unsigned)k);
     }
   }
   __syncthreads();
   const int total = min(s_prefix[g.nlevels], cap);
-  if (slot0 >= total) return;
+  // a CTA does kDescRounds rounds of 16 keypoints: the per-lane set-up above (disc masks, level prefix) is paid once
+#pragma unroll 1
+  for (int round = 0; round < kDescRounds; round++) {
+  const int slot0 = (blockIdx.x * kDescRounds + round) * kDescSlots;
+  if (slot0 >= total) break;
+  const unsigned par = 0u;   // every barrier completes twice per round: parities 0, 1 in every round
 
   // ---- phase A: fetch the unblurred patches, moments, fastAtan2
   int lvl[kDescPerWarp], px[kDescPerWarp], py[kDescPerWarp], resp[kDescPerWarp];
@@ -1710,8 +1707,8 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
     const int slotIdx = slot0 + wid * kDescPerWarp + k;
     lvl[k] = -1; px[k] = py[k] = resp[k] = 0;
     if (slotIdx < total) {
-      int l = 0;
-      while (l + 1 < g.nlevels && slotIdx >= s_prefix[l + 1]) l++;
+      // octave of output slot slotIdx: the number of level prefixes it has passed (lane q looks at level q)
+      const int l = __popc(__ballot_sync(0xffffffffu, lane >= 1 && lane < g.nlevels && slotIdx >= s_prefix[lane]));
       const LevelGeom& L = g.lv[l];
       const uint2 rec = kept[(size_t)f * keptTotal + L.keptOff + (slotIdx - s_prefix[l])];
       lvl[k] = l; px[k] = (int)(rec.x & 0xffffu); py[k] = (int)(rec.x >> 16); resp[k] = (int)rec.y;
@@ -1727,7 +1724,7 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
   for (int k = 0; k < kDescPerWarp; k++) {
     angle[k] = 0.f;
     if (lvl[k] >= 0) {
-      mbar_wait(&s_bar[wid * kDescPerWarp + k], 0);
+      mbar_wait(&s_bar[wid * kDescPerWarp + k], par);
       const int mis = (px[k] - kHalfPatch) & 15;   // patch byte 0 sits `mis` bytes into the fetched row
       const unsigned* row = reinterpret_cast<const unsigned*>(wbuf + k * kTmaBufBytes + (lane < 31 ? lane : 30) * kTmaMomW) + (mis >> 2);
       const unsigned sh = (unsigned)(mis & 3) * 8;
@@ -1775,7 +1772,8 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
     s_sin[threadIdx.x] = (float)sn;
   }
   __syncthreads();
-  // ---- phase C: steered BRIEF on the blurred patch; lane i produces descriptor byte i
+  // ---- phase C: steered BRIEF on the blurred patch; lane i produces descriptor byte i (its 8 test pairs are re-read
+  // per round, so that they do not stay in registers beside the moment masks)
   const int4* pp = reinterpret_cast<const int4*>(pattern) + lane * 2;
   const int4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
   const int words[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
@@ -1783,7 +1781,7 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
   for (int k = 0; k < kDescPerWarp; k++) {
     if (lvl[k] < 0) continue;
     const int sl = wid * kDescPerWarp + k, slotIdx = slot0 + sl;
-    mbar_wait(&s_bar[sl], 1);
+    mbar_wait(&s_bar[sl], par ^ 1u);
     const LevelGeom& L = g.lv[lvl[k]];
     const int x = px[k], y = py[k];
     const float a = s_cos[sl], b = s_sin[sl];
@@ -1815,6 +1813,8 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
       outK[o] = kp;
     }
   }
+  __syncwarp();
+  }   // round
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2647,7 +2647,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);
   if (e->descTma)
-    k_describe_tma<<<dim3((slots + kDescSlots - 1) / kDescSlots, B), 256, kDescTmaSmem, s>>>(g, e->descMaps[lane], W.kept, W.keptCount,
+    k_describe_tma<<<dim3((slots + kDescSlots * kDescRounds - 1) / (kDescSlots * kDescRounds), B), 256, kDescTmaSmem, s>>>(g, e->descMaps[lane], W.kept, W.keptCount,
                                                                                             e->keptTotal, e->d_pattern, d_kps, d_desc,
                                                                                             d_counts, cap, e->d_overflow);
   else

@@ -7,18 +7,18 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kern],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
-out, tot, seen_fn = [], 0, 0
+out, tot, files, cur = [], 0, set(), None
 for r in rows:
-    if r and r[0] == "Function Name":
-        seen_fn += 1
-        if seen_fn > 1:
-            break   # first launch only
+    if r and r[0] == "File Path":
+        if r[1] in files:
+            break   # the same file again: the next launch - first launch only
+        files.add(r[1]); cur = r[1].rsplit("/", 1)[-1]
     if len(r) >= 8 and r[0].isdigit():
         try:
             n, s = int(r[7]), int(r[4])
         except ValueError:
             continue
-        out.append((n, s, int(r[0]), r[1]))
+        out.append((n, s, int(r[0]), (cur + ": " if cur and not cur.startswith("orb_extract") else "") + r[1]))
         tot += n
 stot = sum(o[1] for o in out) or 1
 print("total warp instructions", tot)
