@@ -1655,8 +1655,6 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
                                                       int* __restrict__ outN, int cap, int* __restrict__ overflow) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ __align__(8) unsigned long long s_bar[kDescSlots];
-  __shared__ int s_lvl[kDescSlots];
-  __shared__ float s_angle[kDescSlots], s_cos[kDescSlots], s_sin[kDescSlots];
   __shared__ int s_prefix[kMaxLevels + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = blockIdx.y;
@@ -1749,29 +1747,34 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
     }
   }
   __syncwarp();
-  // the buffers are free: fetch the blurred patches, then publish the angles
+  // the buffers are free: fetch the blurred patches
 #pragma unroll
   for (int k = 0; k < kDescPerWarp; k++) {
     const int sl = wid * kDescPerWarp + k;
-    if (lane == 0) {
-      if (lvl[k] >= 0) {
-        mbar_expect_tx(&s_bar[sl], kTmaPatchBytes);
-        tma_load_3d(wbuf + k * kTmaBufBytes, &maps.blur[lvl[k]], (px[k] - 18) & ~15, py[k] - 18, f, &s_bar[sl]);
-      }
-      s_lvl[sl] = lvl[k];
-      s_angle[sl] = angle[k];
+    if (lane == 0 && lvl[k] >= 0) {
+      mbar_expect_tx(&s_bar[sl], kTmaPatchBytes);
+      tma_load_3d(wbuf + k * kTmaBufBytes, &maps.blur[lvl[k]], (px[k] - 18) & ~15, py[k] - 18, f, &s_bar[sl]);
     }
   }
-  __syncthreads();
-  // ---- phase B: cos / sin, one thread per keypoint
-  if (threadIdx.x < kDescSlots && s_lvl[threadIdx.x] >= 0) {
-    const float ang = __fmul_rn(s_angle[threadIdx.x], (float)(3.14159265358979323846 / 180.f));
-    double sn, cs;
-    sincos((double)ang, &sn, &cs);
-    s_cos[threadIdx.x] = (float)cs;
-    s_sin[threadIdx.x] = (float)sn;
+  // ---- phase B: cos / sin in double precision, rounded to float (glibc's cosf / sinf): lane k of the warp does the
+  // warp's keypoint k while the patch is in flight. No CTA-wide step: every warp runs on its own from here (a single
+  // warp doing all 16 keypoints of the CTA kept the other seven waiting at two barriers: 13 % of the stall samples).
+  float cosMine = 0.f, sinMine = 0.f;
+  {
+    float myAngle = 0.f;
+    bool mine = false;
+#pragma unroll
+    for (int k = 0; k < kDescPerWarp; k++)
+      if (lane == k) { myAngle = angle[k]; mine = lvl[k] >= 0; }
+    if (mine) {
+      const float ang = __fmul_rn(myAngle, (float)(3.14159265358979323846 / 180.f));
+      double sn, cs;
+      sincos((double)ang, &sn, &cs);
+      cosMine = (float)cs;
+      sinMine = (float)sn;
+    }
   }
-  __syncthreads();
+  __syncwarp();
   // ---- phase C: steered BRIEF on the blurred patch; lane i produces descriptor byte i (its 8 test pairs are re-read
   // per round, so that they do not stay in registers beside the moment masks)
   const int4* pp = reinterpret_cast<const int4*>(pattern) + lane * 2;
@@ -1784,7 +1787,7 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
     mbar_wait(&s_bar[sl], par ^ 1u);
     const LevelGeom& L = g.lv[lvl[k]];
     const int x = px[k], y = py[k];
-    const float a = s_cos[sl], b = s_sin[sl];
+    const float a = __shfl_sync(0xffffffffu, cosMine, k), b = __shfl_sync(0xffffffffu, sinMine, k);
     const u8* cb = wbuf + k * kTmaBufBytes + 18 * kTmaPatchW + 18 + ((x - 18) & 15);
     int val = 0;
 #pragma unroll
