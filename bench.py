@@ -816,7 +816,7 @@ def run_ours(args, rank, world, local_rank):
     dom = max(stage_ms, key=stage_ms.get)
     n_launch = max(1, stages[dom][1])
     frames_total = frames_per_step * args.steps
-    kernels_per_chunk = max(1, round(stages[dom][1] / max(1, stages["fast"][1])))   # pyramid: 1 + 7 (+ 1 border) launches
+    kernels_per_chunk = max(1, round(stages[dom][1] / max(1, stages["quadtree"][1])))   # pyramid: 1 + 7 + 1 border launches; FAST: one per level group
     frames_per_launch = frames_total / (n_launch / kernels_per_chunk)
     dom_ms = stage_ms[dom] / n_launch
     # bytes per launch / average launch duration == stage bytes over all frames / stage time

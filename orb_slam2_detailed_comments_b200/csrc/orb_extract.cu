@@ -663,30 +663,43 @@ struct CellDesc {
   int pitch, cw, ch, x0, y0, l, f, rw;
 };
 
+// The levels can be dealt to two GROUPS by the shared memory their cells need, one launch per group (ORB_B200_FAST_SPLIT=1):
+// a warp's carve-up is sized for the largest cell of its launch, and the few levels with tall cells (e.g. 32 x 40 at KITTI's
+// level 5, where 73 detection rows make two cell rows) cost every warp 1.4 KB, i.e. two resident warps per SM. Off by
+// default (one group holding all levels): the second launch costs more than the occupancy returns, see build_geom.
+struct FastGroup {
+  int nPos;                       // levels of this group
+  int posLevel[kMaxLevels];       // their level indices, in item order
+  int posBase[kMaxLevels + 1];    // first cell of every position in the group's cell numbering; [nPos] = cells per frame
+};
+
 // Walks the (frame, level, cell-row, cell-column) items of a contiguous item range without
 // divisions after the first item.
 struct CellCursor {
-  int f, l, ci, cj;
+  int f, l, ci, cj, p;
 };
 
-__device__ __forceinline__ void cursor_init(const Geom& g, int item, CellCursor& k) {
-  k.f = item / g.totalCells;
-  const int cc = item - k.f * g.totalCells;
-  int l = 0;
+__device__ __forceinline__ void cursor_init(const Geom& g, const FastGroup& G, int item, CellCursor& k) {
+  const int cells = G.posBase[G.nPos];
+  k.f = item / cells;
+  const int cc = item - k.f * cells;
+  int p = 0;
 #pragma unroll 1
-  while (l + 1 < g.nlevels && cc >= g.lv[l + 1].cellBase) l++;
-  const int cell = cc - g.lv[l].cellBase;
-  k.l = l;
-  k.ci = cell / g.lv[l].nCols;
-  k.cj = cell - k.ci * g.lv[l].nCols;
+  while (p + 1 < G.nPos && cc >= G.posBase[p + 1]) p++;
+  const int cell = cc - G.posBase[p];
+  k.p = p;
+  k.l = G.posLevel[p];
+  k.ci = cell / g.lv[k.l].nCols;
+  k.cj = cell - k.ci * g.lv[k.l].nCols;
 }
 
-__device__ __forceinline__ void cursor_next(const Geom& g, CellCursor& k) {
+__device__ __forceinline__ void cursor_next(const Geom& g, const FastGroup& G, CellCursor& k) {
   if (++k.cj == g.lv[k.l].nCols) {
     k.cj = 0;
     if (++k.ci == g.lv[k.l].nRows) {
       k.ci = 0;
-      if (++k.l == g.nlevels) { k.l = 0; k.f++; }
+      if (++k.p == G.nPos) { k.p = 0; k.f++; }
+      k.l = G.posLevel[k.p];
     }
   }
 }
@@ -730,7 +743,8 @@ __device__ __forceinline__ void fast_prefetch(const CellDesc& c, unsigned* raw, 
 __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                              uint2* __restrict__ cand, int* __restrict__ candCount,
                                                              int candTotal, int nItems, const FastSmemLayout lay,
-                                                             int* __restrict__ workCounter, int tailRun, int tailMul, int flags) {
+                                                             const FastGroup G, int* __restrict__ workCounter, int run, int tailRun,
+                                                             int tailMul, int flags) {
   extern __shared__ __align__(16) u8 smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   u8* base = smem + wid * lay.total;
@@ -746,8 +760,8 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
   for (int i = lane; i < lay.scBytes / 4; i += 32) reinterpret_cast<unsigned*>(sc)[i] = 0u;
 
   // work distribution: a warp grabs runs of consecutive cells from a global counter of work units
-  const int tailItems = min(nItems, (int)(gridDim.x * (blockDim.x >> 5)) * kFastRun * tailMul);
-  const int longUnits = (nItems - tailItems) / kFastRun;
+  const int tailItems = min(nItems, (int)(gridDim.x * (blockDim.x >> 5)) * run * tailMul);
+  const int longUnits = (nItems - tailItems) / run;
   CellDesc c;
   CellCursor cur_k;
   int left = 0;          // cells left in the current run
@@ -759,12 +773,12 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
         int unit = 0;
         if (lane == 0) unit = atomicAdd(workCounter, 1);
         unit = __shfl_sync(0xffffffffu, unit, 0);
-        const int start = unit < longUnits ? unit * kFastRun : longUnits * kFastRun + (unit - longUnits) * tailRun;
+        const int start = unit < longUnits ? unit * run : longUnits * run + (unit - longUnits) * tailRun;
         if (start >= nItems) return false;
-        left = min(unit < longUnits ? kFastRun : tailRun, nItems - start);
-        cursor_init(g, start, cur_k);
+        left = min(unit < longUnits ? run : tailRun, nItems - start);
+        cursor_init(g, G, start, cur_k);
       } else {
-        cursor_next(g, cur_k);
+        cursor_next(g, G, cur_k);
       }
       left--;
       if (fast_cell_desc(g, pyr, pyrStride, cur_k, c)) return true;
@@ -2073,9 +2087,14 @@ struct orb_extractor {
   bool haveGeom = false;
   size_t pyrStride = 0, blurStride = 0;
   int candTotal = 0, keptTotal = 0, nodeCap = 0, maxKp = 0;
-  size_t fastSmem = 0, qtSmem = 0;
+  size_t qtSmem = 0;
   int qtSeqWords = 0;
-  FastSmemLayout fastLay;
+  // k_fast_cells: one launch per group of levels (see FastGroup)
+  int fastGroups = 1;
+  FastGroup fastGroup[2] = {};
+  FastSmemLayout fastLayG[2] = {};
+  size_t fastSmemG[2] = {0, 0};
+  int fastWarpsG[2] = {4, 4}, fastBlocksG[2] = {0, 0};
   BorderJobs borderJobs = {};    // block ranges of k_fill_borders
   // k_pyramid_fused (few frames per call): item table + dependency flags / work counter
   std::vector<PyrItem> pyrItems;
@@ -2086,7 +2105,6 @@ struct orb_extractor {
   int numSMs = 148;
   int borderBlocks = 0;
   bool pyrTiled = true;          // k_level0_border2 + k_resize_strip + k_fill_borders (ORB_B200_PYR=0: the first-round kernels)
-  int fastBlocks = 0, fastWarps = 4;
   std::vector<int2> taps;
 
   // device workspace (sized for maxBatch frames of the current geometry)
@@ -2153,6 +2171,10 @@ struct orb_extractor {
   // host wall-clock breakdown of the last orb_extract call (microseconds): staging copy of the image into pinned memory,
   // enqueue (H2D + graph launch + D2H requests), wait for the device, copy-out of the results
   double callUs[4] = {0, 0, 0, 0};
+  // last work enqueued on a caller's stream (device entry points): recorded here so that the handle can wait for it
+  // without a device-wide synchronisation (which would also wait for - and fail on - other handles' capturing streams)
+  cudaEvent_t evUser = nullptr;
+  bool userPending = false;
   // optional per-stage CUDA-event timing (bench roofline): 6 boundary events per chunk
   bool profile = false;
   std::vector<cudaEvent_t> evPool;
@@ -2162,6 +2184,31 @@ struct orb_extractor {
 };
 
 namespace {
+
+// Waits for everything THIS handle has in flight: its own streams and the last work it enqueued on a caller's stream.
+// Never cudaDeviceSynchronize: another handle may be capturing a CUDA graph on another host thread (src/Frame.cc:146-154
+// runs two extractors from two threads), and a device-wide wait on a capturing stream is an error.
+int sync_handle(orb_extractor* e) {
+  cudaStream_t ss[] = {e->stream, e->laneStream[0], e->laneStream[1], e->blurStream[0], e->blurStream[1], e->sIn, e->sOut};
+  for (cudaStream_t s : ss)
+    if (s) ORB_CUDA(cudaStreamSynchronize(s));
+  if (e->userPending && e->evUser) {
+    ORB_CUDA(cudaEventSynchronize(e->evUser));
+    e->userPending = false;
+  }
+  return ORB_OK;
+}
+
+// Remembers work enqueued on a caller's stream (see sync_handle).
+int mark_user_stream(orb_extractor* e, cudaStream_t s) {
+  if (s == e->stream) return ORB_OK;
+  if (!e->evUser) ORB_CUDA(cudaEventCreateWithFlags(&e->evUser, cudaEventDisableTiming));
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return ORB_OK; }
+  ORB_CUDA(cudaEventRecord(e->evUser, s));
+  e->userPending = true;
+  return ORB_OK;
+}
 
 void build_tables(orb_extractor* e) {
   // ORBextractor.cc:469-526. scaleFactor is a double member initialised from the float argument.
@@ -2276,29 +2323,77 @@ int build_geom(orb_extractor* e, int W, int H) {
   e->maxKp = maxKp;
   {
     if (maxCw > 60 || maxCh > 60) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell larger than 60 px");
-    const int Rm = (maxCh + 1) / 2;                              // pair distance of the tallest cell
-    FastSmemLayout& y = e->fastLay;
-    y.rawPitchWords = 4 * ((15 + maxCw + 6 + 15) / 16);          // 16-byte chunks
-    y.rawBytes = round_up(y.rawPitchWords * 4 * (maxCh + 6), 16);
-    y.tileBytes = round_up(4 * ((3 + maxCw + 6 + 3) & ~3) * (Rm + 6), 16);
-    y.hitsBytes = round_up(2 * (2 * Rm * maxCw), 16);            // hits + queue share it (see k_fast_cells)
-    y.scBytes = round_up((maxCw + 2) * (maxCh + 2) + 4, 16);
-    y.total = y.rawBytes + y.tileBytes + y.hitsBytes + y.scBytes;
-    // warps per CTA: maximise resident warps per SM under 227 KB (1 KB reserved per CTA)
-    int bestW = 1, bestResident = 0;
     int maxW = kFastWarps;
     if (const char* ev = getenv("ORB_B200_FAST_WARPS")) maxW = std::max(1, std::min(kFastWarps, atoi(ev)));
     if (const char* ev = getenv("ORB_B200_FAST_TAIL_RUN")) e->fastTailRun = std::max(1, std::min(kFastRun, atoi(ev)));
     if (const char* ev = getenv("ORB_B200_FAST_TAIL_MUL")) e->fastTailMul = std::max(0, std::min(64, atoi(ev)));
     if (const char* ev = getenv("ORB_B200_FAST_FLAGS")) e->fastFlags = atoi(ev);
-    for (int w = 1; w <= maxW; w++) {
-      const long long perCta = (long long)y.total * w + 1024;
-      const int resident = (int)std::min<long long>(32, (227 * 1024) / perCta) * w;
-      if (perCta <= 200 * 1024 && resident > bestResident) { bestResident = resident; bestW = w; }
+    // one group by default: measured on KITTI, giving the 11 % of cells that are 38-40 rows tall their own launch lets the
+    // rest run at 22 instead of 20 resident warps per SM, but the second launch's ragged end costs more (4.56 vs 4.45 ms)
+    bool allowSplit = false;
+    if (const char* ev = getenv("ORB_B200_FAST_SPLIT")) allowSplit = atoi(ev) != 0;
+    // per-warp carve-up for cells up to cw x ch, and the warps per CTA that keep most warps resident under 227 KB
+    auto layout = [&](int cw, int ch, FastSmemLayout& y, int& warps, int& resident) {
+      const int Rm = (ch + 1) / 2;                               // pair distance of the tallest cell
+      y.rawPitchWords = 4 * ((15 + cw + 6 + 15) / 16);           // 16-byte chunks
+      y.rawBytes = round_up(y.rawPitchWords * 4 * (ch + 6), 16);
+      y.tileBytes = round_up(4 * ((3 + cw + 6 + 3) & ~3) * (Rm + 6), 16);
+      y.hitsBytes = round_up(2 * (2 * Rm * cw), 16);             // hits + queue share it (see k_fast_cells)
+      y.scBytes = round_up((cw + 2) * (ch + 2) + 4, 16);
+      y.total = y.rawBytes + y.tileBytes + y.hitsBytes + y.scBytes;
+      warps = 1; resident = 0;
+      for (int w = 1; w <= maxW; w++) {
+        const long long perCta = (long long)y.total * w + 1024;
+        const int r = (int)std::min<long long>(32, (227 * 1024) / perCta) * w;
+        if (perCta <= 200 * 1024 && r > resident) { resident = r; warps = w; }
+      }
+    };
+    // levels by the size of their cells (what one warp needs), smallest first; every prefix is a candidate first group
+    std::vector<int> order(nl);
+    for (int l = 0; l < nl; l++) order[l] = l;
+    auto need = [&](int l) { FastSmemLayout y; int w, r; layout(g.lv[l].wCell, g.lv[l].hCell, y, w, r); return y.total; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return need(a) < need(b); });
+    auto cellsOf = [&](int l) { return g.lv[l].nCols * g.lv[l].nRows; };
+    double bestCost = 1e300;
+    int bestSplit = nl;                                           // levels order[0 .. split) form the first group
+    for (int split = 1; split <= nl; split++) {
+      if (!allowSplit && split != nl) continue;
+      double cost = 0;
+      bool ok = true;
+      for (int gi = 0; gi < 2; gi++) {
+        const int a = gi == 0 ? 0 : split, b = gi == 0 ? split : nl;
+        if (a >= b) continue;
+        int cw = 0, ch = 0, cells = 0;
+        for (int k = a; k < b; k++) { cw = std::max(cw, g.lv[order[k]].wCell); ch = std::max(ch, g.lv[order[k]].hCell); cells += cellsOf(order[k]); }
+        FastSmemLayout y; int w, r;
+        layout(cw, ch, y, w, r);
+        if (r == 0) { ok = false; break; }
+        // a launch's time ~ cells / resident warps (measured: 18 -> 20 resident warps = -6 %), plus a tail per launch
+        cost += (double)cells / r + 0.02 * g.totalCells / 20.0;
+      }
+      if (ok && cost < bestCost) { bestCost = cost; bestSplit = split; }
     }
-    if (bestResident == 0) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
-    e->fastWarps = bestW;
-    e->fastSmem = (size_t)y.total * bestW;
+    if (bestCost >= 1e300) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
+    e->fastGroups = bestSplit == nl ? 1 : 2;
+    for (int gi = 0; gi < e->fastGroups; gi++) {
+      const int a = gi == 0 ? 0 : bestSplit, b = gi == 0 ? bestSplit : nl;
+      FastGroup& G = e->fastGroup[gi];
+      memset(&G, 0, sizeof G);
+      std::vector<int> lv(order.begin() + a, order.begin() + b);
+      std::sort(lv.begin(), lv.end());                            // inside a group: ascending level (large levels first)
+      int cw = 0, ch = 0, base = 0;
+      for (int l : lv) {
+        G.posLevel[G.nPos] = l;
+        G.posBase[G.nPos++] = base;
+        base += cellsOf(l);
+        cw = std::max(cw, g.lv[l].wCell); ch = std::max(ch, g.lv[l].hCell);
+      }
+      G.posBase[G.nPos] = base;
+      int resident = 0;
+      layout(cw, ch, e->fastLayG[gi], e->fastWarpsG[gi], resident);
+      e->fastSmemG[gi] = (size_t)e->fastLayG[gi].total * e->fastWarpsG[gi];
+      if (e->fastSmemG[gi] > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
+    }
   }
   {
     // k_resize_strip: the 4 columns of a thread must read one 8-byte source window (scale factor < ~1.7)
@@ -2387,7 +2482,6 @@ int build_geom(orb_extractor* e, int W, int H) {
   }
   e->qtSmem = (size_t)e->nodeCap * (2 * sizeof(QtNode) + 4 * 4 * 2 + 4 * 4 + 8) + (size_t)kQtSmemKeys * 6 + (size_t)e->qtSeqWords * 8;
   if (e->qtSmem > 220 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "features per level too large for the quadtree kernel's shared memory");
-  if (e->fastSmem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "FAST cell too large");
   return ORB_OK;
 }
 
@@ -2405,7 +2499,7 @@ Lane lane_of(const orb_extractor* e, int lane) {
   L.keyNode = e->d_keyNode + F * e->candTotal;
   L.kept = e->d_kept + F * e->keptTotal;
   L.keptCount = e->d_keptCount + F * kMaxLevels;
-  L.work = e->d_work + lane;
+  L.work = e->d_work + 2 * lane;
   return L;
 }
 
@@ -2497,7 +2591,7 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
     e->haveGeom = false;
     int st = build_geom(e, W, H);
     if (st) return st;
-    ORB_CUDA(cudaDeviceSynchronize());
+    { const int ss_ = sync_handle(e); if (ss_) return ss_; }
     free_workspace(e);
     ORB_CUDA(cudaMalloc(&e->d_taps, std::max<size_t>(1, e->taps.size()) * sizeof(int2)));
     ORB_CUDA(cudaMemcpy(e->d_taps, e->taps.data(), e->taps.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -2507,21 +2601,23 @@ int ensure_geom(orb_extractor* e, int W, int H, int frames) {
     ORB_CUDA(cudaMemcpy(e->d_pyrItems, e->pyrItems.data(), e->pyrItems.size() * sizeof(PyrItem), cudaMemcpyHostToDevice));
     ORB_CUDA(cudaMalloc(&e->d_pyrFlags, ((size_t)kPyrFusedMaxFrames * e->pyrPlan.bandBase[e->g.nlevels] + 1) * sizeof(int)));
     ORB_CUDA(raise_dynamic_smem(k_quadtree, e->qtSmem));
-    ORB_CUDA(raise_dynamic_smem(k_fast_cells, e->fastSmem));
+    ORB_CUDA(raise_dynamic_smem(k_fast_cells, std::max(e->fastSmemG[0], e->fastSmemG[1])));
     ORB_CUDA(raise_dynamic_smem(k_describe, kDescSmem));
     {
       int perSM = 0, dev = 0, sms = 0;
-      ORB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_fast_cells, 32 * e->fastWarps, e->fastSmem));
       ORB_CUDA(cudaGetDevice(&dev));
       ORB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      e->fastBlocks = std::max(1, perSM) * std::max(1, sms);
+      for (int gi = 0; gi < e->fastGroups; gi++) {
+        ORB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_fast_cells, 32 * e->fastWarpsG[gi], e->fastSmemG[gi]));
+        e->fastBlocksG[gi] = std::max(1, perSM) * std::max(1, sms);
+      }
       e->numSMs = std::max(1, sms);
     }
     e->haveGeom = true;
   }
   frames = std::min(frames, e->maxBatch);
   if (frames > e->wsFrames) {
-    ORB_CUDA(cudaDeviceSynchronize());
+    { const int ss_ = sync_handle(e); if (ss_) return ss_; }
     int2* keepTaps = e->d_taps; e->d_taps = nullptr;
     free_workspace(e);
     e->d_taps = keepTaps;
@@ -2621,15 +2717,21 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     ORB_CUDA(cudaStreamWaitEvent(bs, e->evBlurGo[lane], 0));
   }
   ORB_CUDA(cudaMemsetAsync(W.candCount, 0, (size_t)B * nl * sizeof(int), s));
-  ORB_CUDA(cudaMemsetAsync(W.work, 0, sizeof(int), s));
+  ORB_CUDA(cudaMemsetAsync(W.work, 0, 2 * sizeof(int), s));
   if ((st = stage_mark(e, s))) return st;
-  {
-    const int nItems = g.totalCells * B;
-    const int blocks = std::min(e->fastBlocks, (nItems + e->fastWarps - 1) / e->fastWarps);
-    k_fast_cells<<<blocks, 32 * e->fastWarps, e->fastSmem, s>>>(g, W.pyr, e->pyrStride, W.cand, W.candCount,
-                                                          e->candTotal, nItems, e->fastLay, W.work, e->fastTailRun, e->fastTailMul, e->fastFlags);
+  for (int gi = 0; gi < e->fastGroups; gi++) {
+    const FastGroup& G = e->fastGroup[gi];
+    const int nItems = G.posBase[G.nPos] * B;
+    if (nItems == 0) continue;
+    const int blocks = std::min(e->fastBlocksG[gi], (nItems + e->fastWarpsG[gi] - 1) / e->fastWarpsG[gi]);
+    // cells per grab: long runs amortise the atomic and keep a warp on neighbouring cells, but every warp should get
+    // at least ~6 grabs or the launch ends ragged (the small group of tall cells has ~12 cells per warp)
+    const int run = std::max(1, std::min(kFastRun, nItems / (blocks * e->fastWarpsG[gi] * 6)));
+    k_fast_cells<<<blocks, 32 * e->fastWarpsG[gi], e->fastSmemG[gi], s>>>(g, W.pyr, e->pyrStride, W.cand, W.candCount, e->candTotal, nItems,
+                                                                    e->fastLayG[gi], G, W.work + gi, run, std::min(run, e->fastTailRun),
+                                                                    e->fastTailMul, e->fastFlags);
+    launches++;
   }
-  launches++;
   if ((st = stage_mark(e, s))) return st;
   if (fork == 2) {
     ORB_CUDA(cudaEventRecord(e->evBlurGo[lane], s));
@@ -2661,7 +2763,7 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   if ((st = stage_mark(e, s))) return st;
   ORB_CUDA(cudaGetLastError());
   if (e->profile) {
-    e->stageLaunches[0] += pyrLaunches; e->stageLaunches[1]++; e->stageLaunches[2]++; e->stageLaunches[3]++; e->stageLaunches[4]++;
+    e->stageLaunches[0] += pyrLaunches; e->stageLaunches[1] += e->fastGroups; e->stageLaunches[2]++; e->stageLaunches[3]++; e->stageLaunches[4]++;
   }
   e->lastLaunches += launches;
   e->lastChunkFrames = B;
@@ -2741,7 +2843,7 @@ int ensure_stage(orb_extractor* e, size_t inBytes, int frames, int cap) {
     }
   }
   if (inBytes > e->d_inBytes) {
-    ORB_CUDA(cudaDeviceSynchronize());
+    { const int ss_ = sync_handle(e); if (ss_) return ss_; }
     for (int b = 0; b < 2; b++) {
       cudaFree(e->d_in[b]);
       e->d_in[b] = nullptr;
@@ -2750,7 +2852,7 @@ int ensure_stage(orb_extractor* e, size_t inBytes, int frames, int cap) {
     e->d_inBytes = inBytes;
   }
   if ((size_t)frames * cap > (size_t)e->stageFrames * e->stageCap || frames > e->stageFrames) {
-    ORB_CUDA(cudaDeviceSynchronize());
+    { const int ss_ = sync_handle(e); if (ss_) return ss_; }
     for (int b = 0; b < 2; b++) {
       cudaFree(e->d_kps[b]); cudaFree(e->d_desc[b]); cudaFree(e->d_n[b]);
       e->d_kps[b] = nullptr; e->d_desc[b] = nullptr; e->d_n[b] = nullptr;
@@ -2900,7 +3002,7 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
   if (err == cudaSuccess) err = cudaMalloc(&e->d_pattern, sizeof ORB_BIT_PATTERN_31);
   if (err == cudaSuccess) err = cudaMemcpy(e->d_pattern, ORB_BIT_PATTERN_31, sizeof ORB_BIT_PATTERN_31, cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMalloc(&e->d_overflow, sizeof(int));
-  if (err == cudaSuccess) err = cudaMalloc(&e->d_work, 2 * sizeof(int));
+  if (err == cudaSuccess) err = cudaMalloc(&e->d_work, 4 * sizeof(int));
   if (err == cudaSuccess) err = cudaMalloc(&e->d_invScale, kMaxLevels * sizeof(float));
   if (err == cudaSuccess) err = cudaMemcpy(e->d_invScale, e->invScale.data(), e->invScale.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMemset(e->d_overflow, 0, sizeof(int));
@@ -2947,6 +3049,7 @@ int orb_destroy(orb_extractor* e) {
     if (e->evL0Go[l]) cudaEventDestroy(e->evL0Go[l]);
     if (e->evL0Done[l]) cudaEventDestroy(e->evL0Done[l]);
   }
+  if (e->evUser) cudaEventDestroy(e->evUser);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return ORB_OK;
@@ -3025,7 +3128,9 @@ int orb_extract_batch_device(orb_extractor* e, const uint8_t* d_images, int batc
                    capacity, d_counts + b0, d_descriptors + (size_t)b0 * capacity * 32, multi ? e->laneStream[lane] : s, lane);
     if (st) return st;
   }
-  return lanes_join(e, s, nChunks);
+  st = lanes_join(e, s, nChunks);
+  if (st) return st;
+  return mark_user_stream(e, s);
 }
 
 int orb_synchronize(orb_extractor* e, void* stream) {
@@ -3053,7 +3158,7 @@ int orb_last_call_breakdown(const orb_extractor* e, double* us4) {
 int orb_set_lanes(orb_extractor* e, int lanes) {
   if (!e || lanes < 1 || lanes > 2) ORB_FAIL(ORB_ERR_INVALID, "lanes must be 1 or 2");
   ORB_CUDA(cudaSetDevice(e->device));
-  ORB_CUDA(cudaDeviceSynchronize());
+  { const int ss_ = sync_handle(e); if (ss_) return ss_; }
   if (lanes != e->lanes) {
     // the workspace is sized per lane count: drop it, it is re-allocated by the next call
     int2* keepTaps = e->d_taps; e->d_taps = nullptr;
@@ -3073,7 +3178,7 @@ int orb_set_profiling(orb_extractor* e, int enable) {
 int orb_get_stage_times(orb_extractor* e, double* ms5, long long* launches5) {
   if (!e || !ms5 || !launches5) ORB_FAIL(ORB_ERR_INVALID, "null argument");
   ORB_CUDA(cudaSetDevice(e->device));
-  ORB_CUDA(cudaDeviceSynchronize());
+  { const int ss_ = sync_handle(e); if (ss_) return ss_; }
   for (size_t i = 0; i + 5 < e->evUsed; i += 6)
     for (int k = 0; k < 5; k++) {
       float ms = 0.f;
@@ -3267,7 +3372,9 @@ int orb_extract_stereo_batch_device(orb_extractor* e, const uint8_t* d_images, i
                     d_depth + (size_t)(b0 / 2) * capacity, ls, lane, multi);
     if (st) return st;
   }
-  return lanes_join(e, s, nChunks);
+  st = lanes_join(e, s, nChunks);
+  if (st) return st;
+  return mark_user_stream(e, s);
 }
 
 int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* right, int width, int height, size_t step,
@@ -3406,7 +3513,7 @@ int orb_stage_copy_level(orb_extractor* e, int frame, int level, uint8_t* dst) {
   int st = stage_check(e, frame, level);
   if (st) return st;
   ORB_CUDA(cudaSetDevice(e->device));
-  ORB_CUDA(cudaDeviceSynchronize());
+  { const int ss_ = sync_handle(e); if (ss_) return ss_; }
   const LevelGeom& L = e->g.lv[level];
   const u8* src = lane_of(e, e->lastLane).pyr + (size_t)frame * e->pyrStride + L.off - (long long)kEdge * L.pitch - kEdge;
   ORB_CUDA(cudaMemcpy2D(dst, L.w + 2 * kEdge, src, L.pitch, L.w + 2 * kEdge, L.h + 2 * kEdge, cudaMemcpyDeviceToHost));
@@ -3417,7 +3524,7 @@ int orb_stage_copy_blur(orb_extractor* e, int frame, int level, uint8_t* dst) {
   int st = stage_check(e, frame, level);
   if (st) return st;
   ORB_CUDA(cudaSetDevice(e->device));
-  ORB_CUDA(cudaDeviceSynchronize());
+  { const int ss_ = sync_handle(e); if (ss_) return ss_; }
   const LevelGeom& L = e->g.lv[level];
   ORB_CUDA(cudaMemcpy2D(dst, L.w, lane_of(e, e->lastLane).blur + (size_t)frame * e->blurStride + L.boff, L.bpitch, L.w, L.h,
                         cudaMemcpyDeviceToHost));
@@ -3443,7 +3550,7 @@ int orb_stage_copy_candidates(orb_extractor* e, int frame, int level, int32_t* x
   int st = stage_check(e, frame, level);
   if (st) return st;
   ORB_CUDA(cudaSetDevice(e->device));
-  ORB_CUDA(cudaDeviceSynchronize());
+  { const int ss_ = sync_handle(e); if (ss_) return ss_; }
   int cnt = 0;
   ORB_CUDA(cudaMemcpy(&cnt, lane_of(e, e->lastLane).candCount + frame * e->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
   cnt = std::min(cnt, e->g.lv[level].candCap);
@@ -3456,7 +3563,7 @@ int orb_stage_copy_kept(orb_extractor* e, int frame, int level, int32_t* xs, int
   int st = stage_check(e, frame, level);
   if (st) return st;
   ORB_CUDA(cudaSetDevice(e->device));
-  ORB_CUDA(cudaDeviceSynchronize());
+  { const int ss_ = sync_handle(e); if (ss_) return ss_; }
   int cnt = 0;
   ORB_CUDA(cudaMemcpy(&cnt, lane_of(e, e->lastLane).keptCount + frame * e->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
   *n = cnt;
