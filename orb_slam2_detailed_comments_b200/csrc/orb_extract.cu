@@ -1329,34 +1329,45 @@ constexpr int kBlurInP = kBlurChunks * 4 + 4;     // tile pitch in words (16-B a
 constexpr int kBlurRows = kBlurTH + 6;        // input rows y0-3 .. y0+34
 constexpr int kBlurPairs = kBlurRows / 2;
 
+template <bool TMA>
 __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restrict__ pyr, size_t pyrStride,
                                                u8* __restrict__ blur, size_t blurStride,
-                                               const __grid_constant__ PyrMaps bmaps, int useTma) {
+                                               const __grid_constant__ PyrMaps bmaps) {
   __shared__ __align__(128) unsigned in[kBlurRows * kBlurInP];
   __shared__ __align__(8) unsigned long long s_bbar;
-  const int inP = useTma ? kBlurChunks * 4 : kBlurInP;   // the TMA box is dense: 160-byte rows
+  __shared__ int s_level;
+  constexpr int inP = TMA ? kBlurChunks * 4 : kBlurInP;   // the TMA box is dense: 160-byte rows
   __shared__ __align__(16) unsigned hp[kBlurPairs * kBlurTW];  // (H[2p][x], H[2p+1][x]) as u16 pairs
   const int f = blockIdx.y, tid = threadIdx.x;
-  int l = 0;
+  // one thread finds the tile's level (a dependent chain of parameter loads) and starts the fetch; the rest read it
+  // after the barrier they wait at anyway
+  if (tid == 0) {
+    int l = 0;
 #pragma unroll 1
-  while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blurTileBase) l++;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blurTileBase) l++;
+    s_level = l;
+    if (TMA) {
+      // one bulk tensor copy per CTA: rows y0-3 .. y0+66, bytes x0-16 .. x0+143 of the bordered plane (rows / bytes
+      // outside the plane arrive as zeros; they only feed outputs that are not stored)
+      const LevelGeom& L0 = g.lv[l];
+      const int t0 = blockIdx.x - L0.blurTileBase;
+      const int ty0 = L0.blurTilesX == 1 ? t0 : (int)__umulhi((unsigned)t0, L0.blurTilesXMagic), tx0 = t0 - ty0 * L0.blurTilesX;
+      mbar_init(&s_bbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(&s_bbar, kBlurRows * kBlurChunks * 16);
+      tma_load_3d(in, &bmaps.m[l], kLeftPad + tx0 * kBlurTW - 16, kEdge + ty0 * kBlurTH - 3, f, &s_bbar);
+    }
+  }
+  __syncthreads();
+  const int l = s_level;
   const LevelGeom& L = g.lv[l];
   const int t = blockIdx.x - L.blurTileBase;
   const int ty = L.blurTilesX == 1 ? t : (int)__umulhi((unsigned)t, L.blurTilesXMagic), tx = t - ty * L.blurTilesX;   // t < 2^16
   const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
-  const u8* src = pyr + (size_t)f * pyrStride + L.off;
-  if (useTma) {
-    // one bulk tensor copy per CTA: rows y0-3 .. y0+66, bytes x0-16 .. x0+143 of the bordered plane (rows / bytes
-    // outside the plane arrive as zeros; they only feed outputs that are not stored)
-    if (tid == 0) {
-      mbar_init(&s_bbar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      mbar_expect_tx(&s_bbar, kBlurRows * kBlurChunks * 16);
-      tma_load_3d(in, &bmaps.m[l], kLeftPad + x0 - 16, kEdge + y0 - 3, f, &s_bbar);
-    }
-    __syncthreads();
+  if (TMA) {
     mbar_wait(&s_bbar, 0);
   } else {
+    const u8* src = pyr + (size_t)f * pyrStride + L.off;
     const int xlast = L.pitch - kLeftPad - 16;  // last 16-byte chunk of a bordered row (covers col w+18)
     for (int i = tid; i < kBlurRows * kBlurChunks; i += 256) {
       const int r = i / kBlurChunks, c = i - r * kBlurChunks;
@@ -1367,39 +1378,50 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
     __pipeline_wait_prior(0);
     __syncthreads();
   }
+  // thread = a fixed group of 4 columns (xg) and every 8th row pair: all addresses advance by compile-time strides
+  const int xg = tid & 31, r8 = tid >> 5;
   // horizontal: k = [18,34,48,56,48,34,18]; output x needs tile bytes (x+1 .. x+7)
-  for (int i = tid; i < kBlurPairs * (kBlurTW / 4); i += 256) {
-    const int rp = i / (kBlurTW / 4), xg = i - rp * (kBlurTW / 4);
-    unsigned hrow[2][4];
+  {
+    const unsigned* p = in + (2 * r8) * inP + xg + 3;   // image x0+4xg-4 = tile byte 4xg+12
+    unsigned* ho = hp + r8 * kBlurTW + 4 * xg;
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const unsigned* p = in + (2 * rp + q) * inP + xg + 3;  // image x0+4xg-4 = tile byte 4xg+12
-      // output x+j needs tile bytes (1+j .. 7+j) of (w0,w1,w2): the taps are applied with
-      // pre-shifted coefficient words instead of shifting the data
-      const unsigned w0 = p[0], w1 = p[1], w2 = p[2];
-      hrow[q][0] = __dp4a(w0, 0x30221200u, __dp4a(w1, 0x12223038u, 0u));
-      hrow[q][1] = __dp4a(w0, 0x22120000u, __dp4a(w1, 0x22303830u, __dp4a(w2, 0x00000012u, 0u)));
-      hrow[q][2] = __dp4a(w0, 0x12000000u, __dp4a(w1, 0x30383022u, __dp4a(w2, 0x00001222u, 0u)));
-      hrow[q][3] = __dp4a(w1, 0x38302212u, __dp4a(w2, 0x00122230u, 0u));
+    for (int it = 0; it < (kBlurPairs + 7) / 8; it++) {
+      if (8 * it + r8 < kBlurPairs) {
+        unsigned hrow[2][4];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          // output x+j needs tile bytes (1+j .. 7+j) of (w0,w1,w2): the taps are applied with
+          // pre-shifted coefficient words instead of shifting the data
+          const unsigned w0 = p[(16 * it + q) * inP], w1 = p[(16 * it + q) * inP + 1], w2 = p[(16 * it + q) * inP + 2];
+          hrow[q][0] = __dp4a(w0, 0x30221200u, __dp4a(w1, 0x12223038u, 0u));
+          hrow[q][1] = __dp4a(w0, 0x22120000u, __dp4a(w1, 0x22303830u, __dp4a(w2, 0x00000012u, 0u)));
+          hrow[q][2] = __dp4a(w0, 0x12000000u, __dp4a(w1, 0x30383022u, __dp4a(w2, 0x00001222u, 0u)));
+          hrow[q][3] = __dp4a(w1, 0x38302212u, __dp4a(w2, 0x00122230u, 0u));
+        }
+        uint4 o;
+        o.x = hrow[0][0] | (hrow[1][0] << 16);
+        o.y = hrow[0][1] | (hrow[1][1] << 16);
+        o.z = hrow[0][2] | (hrow[1][2] << 16);
+        o.w = hrow[0][3] | (hrow[1][3] << 16);
+        *reinterpret_cast<uint4*>(ho + 8 * it * kBlurTW) = o;
+      }
     }
-    uint4 o;
-    o.x = hrow[0][0] | (hrow[1][0] << 16);
-    o.y = hrow[0][1] | (hrow[1][1] << 16);
-    o.z = hrow[0][2] | (hrow[1][2] << 16);
-    o.w = hrow[0][3] | (hrow[1][3] << 16);
-    *reinterpret_cast<uint4*>(hp + rp * kBlurTW + 4 * xg) = o;
   }
   __syncthreads();
   // vertical: out rows 2yp, 2yp+1 need tile rows 2yp .. 2yp+7 = row pairs yp .. yp+3
-  u8* dst = blur + (size_t)f * blurStride + L.boff;
-  for (int i = tid; i < (kBlurTH / 2) * (kBlurTW / 4); i += 256) {
-    const int yp = i / (kBlurTW / 4), xg = i - yp * (kBlurTW / 4);
-    const int x = x0 + 4 * xg, y = y0 + 2 * yp;
-    if (x >= L.w || y >= L.h) continue;
-    const uint4 q0 = *reinterpret_cast<const uint4*>(hp + (yp + 0) * kBlurTW + 4 * xg);
-    const uint4 q1 = *reinterpret_cast<const uint4*>(hp + (yp + 1) * kBlurTW + 4 * xg);
-    const uint4 q2 = *reinterpret_cast<const uint4*>(hp + (yp + 2) * kBlurTW + 4 * xg);
-    const uint4 q3 = *reinterpret_cast<const uint4*>(hp + (yp + 3) * kBlurTW + 4 * xg);
+  const int x = x0 + 4 * xg;
+  if (x >= L.w) return;
+  u8* d0 = blur + (size_t)f * blurStride + L.boff + (long long)(y0 + 2 * r8) * L.bpitch + x;
+  const long long dstep = 16LL * L.bpitch;
+  const unsigned* hq = hp + r8 * kBlurTW + 4 * xg;
+#pragma unroll
+  for (int it = 0; it < kBlurTH / 16; it++) {
+    const int y = y0 + 2 * (8 * it + r8);
+    if (y >= L.h) break;
+    const uint4 q0 = *reinterpret_cast<const uint4*>(hq + (8 * it + 0) * kBlurTW);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(hq + (8 * it + 1) * kBlurTW);
+    const uint4 q2 = *reinterpret_cast<const uint4*>(hq + (8 * it + 2) * kBlurTW);
+    const uint4 q3 = *reinterpret_cast<const uint4*>(hq + (8 * it + 3) * kBlurTW);
     const unsigned c0[4] = {q0.x, q0.y, q0.z, q0.w}, c1[4] = {q1.x, q1.y, q1.z, q1.w};
     const unsigned c2[4] = {q2.x, q2.y, q2.z, q2.w}, c3[4] = {q3.x, q3.y, q3.z, q3.w};
     unsigned ev[4], od[4];
@@ -1419,9 +1441,9 @@ __global__ void __launch_bounds__(256) k_blur7(const Geom g, const u8* __restric
     // the result of pixel j is byte 2 of its accumulator (sum / 2^16, < 256): three PRMT pack four of them
     const unsigned o0 = __byte_perm(__byte_perm(ev[0], ev[1], 0x0062), __byte_perm(ev[2], ev[3], 0x0062), 0x5410);
     const unsigned o1 = __byte_perm(__byte_perm(od[0], od[1], 0x0062), __byte_perm(od[2], od[3], 0x0062), 0x5410);
-    u8* d0 = dst + (long long)y * L.bpitch + x;
     *reinterpret_cast<unsigned*>(d0) = o0;
     if (y + 1 < L.h) *reinterpret_cast<unsigned*>(d0 + L.bpitch) = o1;
+    d0 += dstep;
   }
 }
 
@@ -2742,8 +2764,10 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
                                                        e->d_overflow);
   launches++;
   if ((st = stage_mark(e, s))) return st;
-  k_blur7<<<dim3(g.totalBlurTiles, B), 256, 0, bs>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride, e->blurMaps[lane],
-                                                     e->blurTma ? 1 : 0);
+  if (e->blurTma)
+    k_blur7<true><<<dim3(g.totalBlurTiles, B), 256, 0, bs>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride, e->blurMaps[lane]);
+  else
+    k_blur7<false><<<dim3(g.totalBlurTiles, B), 256, 0, bs>>>(g, W.pyr, e->pyrStride, W.blur, e->blurStride, e->blurMaps[lane]);
   if (fork) {
     ORB_CUDA(cudaEventRecord(e->evBlurDone[lane], bs));
     ORB_CUDA(cudaStreamWaitEvent(s, e->evBlurDone[lane], 0));
