@@ -805,9 +805,14 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Geom g, const
         const int rpw = lay.rawPitchWords;
         const unsigned* ra = raw + (c.ox >> 2) + k;
         uint4* t = reinterpret_cast<uint4*>(tile + q * tp + 4 * k);
-        const int rows = R + 6, last = ch + 5;       // the partner of tile row R+5 does not exist for odd ch: clamped (masked later)
-        for (int r = q; r < rows; r += rps) {
-          const unsigned a = ra[r * rpw], b = ra[min(r + R, last) * rpw];
+        // rows r and r + R of the raw buffer; for odd ch the partner of tile row R+5 would be raw row ch+6, which is not
+        // fetched (one more raw row would cost a resident warp per SM): the row above stands in, its half of the word
+        // only feeds a pixel that is masked later
+        const int rows = R + 6, last = ch + 5;
+        const unsigned* pa = ra + q * rpw;
+        const int hiOff = R * rpw, stepA = rps * rpw;
+        for (int r = q; r < rows; r += rps, pa += stepA) {
+          const unsigned a = pa[0], b = pa[r + R > last ? hiOff - rpw : hiOff];
           const unsigned x01 = __byte_perm(a, b, 0x5410), x23 = __byte_perm(a, b, 0x7632);
           uint4 o;
           o.x = __byte_perm(x01, 0u, 0x4240);
