@@ -368,6 +368,35 @@ int orb_search_by_projection_device(int device, const orb_device_frames* frames,
                                     int32_t* d_match_of_keypoint, int32_t* d_match_of_query, int32_t* d_nmatches,
                                     void* stream);
 
+/* Host-memory form of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:1710-1860) for ONE
+ * frame pair - what a drop-in body of that method calls once per tracked frame (compat/orb_b200_matcher.cpp). All pointers are
+ * HOST pointers; one packed upload, orb_assign_features_to_grid_device + orb_project_last_frame_device +
+ * orb_search_by_projection_device(ORB_SEARCH_BEST), one packed download, one synchronisation (staging is cached per host
+ * thread). match_of_keypoint (n_cur) = index of the last-frame map point given to each current keypoint or -1
+ * (CurrentFrame.mvpMapPoints), *nmatches = the method's return value. */
+typedef struct orb_last_frame_search {
+  int32_t n_cur;
+  const orb_keypoint* cur_keypoints_un;  /* CurrentFrame.mvKeysUn */
+  const uint8_t* cur_descriptors;        /* CurrentFrame.mDescriptors (n_cur x 32) */
+  const float* cur_uright;               /* CurrentFrame.mvuRight, NULL = monocular */
+  const uint8_t* cur_occupied;           /* 1 = CurrentFrame.mvpMapPoints[i] && Observations() > 0 (:1795), NULL = none */
+  const float* bounds4;                  /* mnMinX, mnMaxX, mnMinY, mnMaxY */
+  int32_t n_last;
+  const orb_keypoint* last_keypoints;    /* LastFrame.mvKeys (octave, angle) */
+  const float* last_world_pos;           /* n_last x 3: LastFrame.mvpMapPoints[i]->GetWorldPos() */
+  const uint8_t* last_mp_flags;          /* bit 0: map point exists and !mvbOutlier[i]; bit 1: its Observations() > 0 */
+  const uint8_t* last_mp_descriptors;    /* n_last x 32: GetDescriptor() */
+  const float* Tcw;                      /* CurrentFrame.mTcw, row-major 4x4 */
+  int32_t direction;                     /* 0 neither, 1 bForward, 2 bBackward (:1723-1730) */
+  const float* cam4;                     /* fx, fy, cx, cy */
+  float mbf, th;                         /* CurrentFrame.mbf; the search radius factor th */
+  const float* scale_factors; int32_t nlevels;   /* CurrentFrame.mvScaleFactors */
+  int32_t th_dist;                       /* TH_HIGH */
+  float nn_ratio;                        /* mfNNratio (unused by ORB_SEARCH_BEST, kept for symmetry) */
+  int32_t check_orientation;             /* mbCheckOrientation */
+} orb_last_frame_search;
+int orb_search_by_projection_last_frame(int device, const orb_last_frame_search* args, int32_t* match_of_keypoint, int* nmatches);
+
 /* Replaces ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (src/ORBmatcher.cc:247-420).
  * The DBoW2 FeatureVectors (node id -> feature indices) are passed as the node id of every feature
  * (d_node1 / d_node2, -1 = none). Keyframe side: (batch, query_capacity) features with d_usable1 = 1

@@ -185,3 +185,25 @@ def search_for_initialization(F1, F2, prev_matched, window=100, nnratio=0.9, che
 def descriptor_distance(a, b):
     a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
     return lib().orbgpu_descriptor_distance(_p(a), _p(b))
+
+
+_API = None
+
+
+def reference_api():
+    """The whole oracle/orb_ref.py binding (frames from given keypoints, the searches on live MapPoint / KeyFrame objects ...)
+    bound to liborbref_gpu.so instead of liborbref.so: oracle/ref_wrap.cpp is compiled into both libraries, so every orbref_*
+    entry point exists in both with the same signature - here the reference's code runs with the drop-in bodies
+    (extractor, DescriptorDistance, SearchForInitialization, SearchByProjection(CurrentFrame, LastFrame), ComputeStereoMatches)
+    linked in, and its own CPU bodies for everything else."""
+    global _API
+    if _API is None:
+        import importlib.util
+        from . import orb_ref
+        spec = importlib.util.spec_from_file_location("oracle._orb_ref_on_dropin", orb_ref.__file__)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod._PATH = _PATH
+        mod._LIB = None
+        _API = mod
+    return _API

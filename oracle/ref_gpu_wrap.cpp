@@ -19,9 +19,9 @@
 #undef private
 #undef protected
 
-// hooks of the OpenCV stand-in (the all-CPU library uses them for its canonical allocator; nothing to do here)
-extern "C" void* cvshim_primitive_enter() { return nullptr; }
-extern "C" void cvshim_primitive_leave(void*) {}
+// (oracle/ref_wrap.cpp is compiled into this library too: its orbref_* entry points - frames from given keypoints, the
+// searches on live MapPoint / KeyFrame objects - then run the drop-in for the replaced members and the reference's CPU
+// code for everything else, with the same signatures as in the all-CPU library.)
 
 namespace {
 struct GpuFrame {

@@ -1,8 +1,9 @@
-// orb_b200_matcher.cpp — the two ORBmatcher members of the hot path, for the reference's build.
+// orb_b200_matcher.cpp — the ORBmatcher members of the hot path, for the reference's build.
 //
 // Compiled against the reference's own, UNMODIFIED include/ORBmatcher.h (all eleven methods stay declared there). A
-// maintainer deletes the bodies of ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2083-2103) and
-// ORBmatcher::SearchForInitialization (:573-717) from src/ORBmatcher.cc and adds this file; the other nine methods keep
+// maintainer deletes the bodies of ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2083-2103),
+// ORBmatcher::SearchForInitialization (:573-717) and ORBmatcher::SearchByProjection(Frame&, const Frame&, float, bool)
+// (:1710-1860, the per-frame tracking search) from src/ORBmatcher.cc and adds this file; the other eight methods keep
 // their CPU bodies in ORBmatcher.cc. (This repository's test build of the reference does the same without touching the
 // source: it weakens the two symbols in the compiled ORBmatcher.o, see INTEGRATION.md.)
 #include <algorithm>
@@ -69,6 +70,77 @@ int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Po
   const int st = orb_search_for_initialization(t_matcher.get(std::max(n1, n2)), &v1, &v2, &mp, reinterpret_cast<float*>(vbPrevMatched.data()),
                                                vnMatches12.data(), &nmatches, nullptr, nullptr);
   if (st != ORB_OK) throw std::runtime_error(std::string("ORBmatcher::SearchForInitialization (liborb_b200): ") + orb_last_error());
+  return nmatches;
+}
+
+// src/ORBmatcher.cc:1710-1860 (called at src/Tracking.cc:1047 TrackWithMotionModel): every map point of the last frame is
+// projected with the current pose and takes the best keypoint in its window that no earlier map point holds; rotation
+// histogram at the end. One call of the library's host-memory entry point does the projection, the grid, the scan and the
+// in-order commit on the GPU.
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+  // bForward / bBackward exactly as :1717-1730 (the caller's own cv::Mat arithmetic)
+  const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+  const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+  const cv::Mat twc = -Rcw.t() * tcw;
+  const cv::Mat Rlw = LastFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+  const cv::Mat tlw = LastFrame.mTcw.rowRange(0, 3).col(3);
+  const cv::Mat tlc = Rlw * twc + tlw;
+  const bool bForward = tlc.at<float>(2) > CurrentFrame.mb && !bMono;
+  const bool bBackward = -tlc.at<float>(2) > CurrentFrame.mb && !bMono;
+
+  const int nc = CurrentFrame.N, nl = LastFrame.N;
+  if (nc == 0 || nl == 0) return 0;
+  static_assert(sizeof(cv::KeyPoint) == sizeof(orb_keypoint), "cv::KeyPoint must be the 28-byte record of orb_keypoint");
+  std::vector<unsigned char> curDesc((size_t)nc * 32), occupied(nc, 0), flags(nl, 0), mpDesc((size_t)nl * 32, 0);
+  std::vector<float> Xw((size_t)nl * 3, 0.f);
+  for (int i = 0; i < nc; i++) {
+    std::memcpy(&curDesc[(size_t)i * 32], CurrentFrame.mDescriptors.ptr(i), 32);
+    MapPoint* p = CurrentFrame.mvpMapPoints[i];
+    occupied[i] = p && p->Observations() > 0;                       // :1795-1797
+  }
+  for (int i = 0; i < nl; i++) {
+    MapPoint* p = LastFrame.mvpMapPoints[i];
+    if (!p || LastFrame.mvbOutlier[i]) continue;                    // :1736-1740
+    const cv::Mat x3Dw = p->GetWorldPos();
+    Xw[3 * i] = x3Dw.at<float>(0); Xw[3 * i + 1] = x3Dw.at<float>(1); Xw[3 * i + 2] = x3Dw.at<float>(2);
+    const cv::Mat d = p->GetDescriptor();
+    std::memcpy(&mpDesc[(size_t)i * 32], d.ptr(0), 32);
+    flags[i] = (unsigned char)(1 | (p->Observations() > 0 ? 2 : 0));
+  }
+  float Tcw[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) Tcw[4 * r + c] = CurrentFrame.mTcw.at<float>(r, c);
+  const float cam4[4] = {Frame::fx, Frame::fy, Frame::cx, Frame::cy};
+  const float bounds4[4] = {Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY};
+  orb_last_frame_search a;
+  std::memset(&a, 0, sizeof a);
+  a.n_cur = nc;
+  a.cur_keypoints_un = reinterpret_cast<const orb_keypoint*>(CurrentFrame.mvKeysUn.data());
+  a.cur_descriptors = curDesc.data();
+  a.cur_uright = CurrentFrame.mvuRight.empty() ? nullptr : CurrentFrame.mvuRight.data();
+  a.cur_occupied = occupied.data();
+  a.bounds4 = bounds4;
+  a.n_last = nl;
+  a.last_keypoints = reinterpret_cast<const orb_keypoint*>(LastFrame.mvKeys.data());
+  a.last_world_pos = Xw.data();
+  a.last_mp_flags = flags.data();
+  a.last_mp_descriptors = mpDesc.data();
+  a.Tcw = Tcw;
+  a.direction = bForward ? 1 : (bBackward ? 2 : 0);
+  a.cam4 = cam4;
+  a.mbf = CurrentFrame.mbf;
+  a.th = th;
+  a.scale_factors = CurrentFrame.mvScaleFactors.data();
+  a.nlevels = (int)CurrentFrame.mvScaleFactors.size();
+  a.th_dist = TH_HIGH;
+  a.nn_ratio = mfNNratio;
+  a.check_orientation = mbCheckOrientation ? 1 : 0;
+  std::vector<int32_t> matchOfKp(nc, -1);
+  int nmatches = 0;
+  const int st = orb_search_by_projection_last_frame(0, &a, matchOfKp.data(), &nmatches);
+  if (st != ORB_OK) throw std::runtime_error(std::string("ORBmatcher::SearchByProjection (liborb_b200): ") + orb_last_error());
+  for (int i = 0; i < nc; i++)
+    if (matchOfKp[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[matchOfKp[i]];   // :1813
   return nmatches;
 }
 

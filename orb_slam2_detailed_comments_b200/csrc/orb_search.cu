@@ -766,4 +766,99 @@ int orb_search_for_triangulation_device(int device, const orb_keypoint* d_keypoi
   return launch_search(A, frames2->batch, (cudaStream_t)stream);
 }
 
+// ---- host-memory form of the last-frame search: what a drop-in ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th,
+// bMono) calls once per tracked frame. One packed upload, grid + projection + scan + commit, one packed download.
+namespace {
+struct HostSearchCache {   // per host thread and device: staging buffers and a stream
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  u8* d = nullptr; u8* h = nullptr; size_t bytes = 0;
+  ~HostSearchCache() {
+    if (device >= 0) { cudaSetDevice(device); cudaFree(d); if (h) cudaFreeHost(h); if (stream) cudaStreamDestroy(stream); }
+  }
+};
+thread_local HostSearchCache t_hs;
+}  // namespace
+
+int orb_search_by_projection_last_frame(int device, const orb_last_frame_search* a, int32_t* match_of_keypoint, int* nmatches) {
+  if (!a || !match_of_keypoint || !nmatches || !a->cur_keypoints_un || !a->cur_descriptors || !a->last_keypoints || !a->last_world_pos ||
+      !a->last_mp_flags || !a->last_mp_descriptors || !a->Tcw || !a->cam4 || !a->bounds4 || !a->scale_factors)
+    ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  const int nc = a->n_cur, nl = a->n_last;
+  if (nc < 0 || nl < 0) ORB_FAIL(ORB_ERR_INVALID, "negative count");
+  *nmatches = 0;
+  for (int i = 0; i < nc; i++) match_of_keypoint[i] = -1;
+  if (nc == 0 || nl == 0) return ORB_OK;
+  ORB_CUDA(cudaSetDevice(device));
+  HostSearchCache& C = t_hs;
+  if (C.device != device) {
+    if (C.device >= 0) { cudaSetDevice(C.device); cudaFree(C.d); if (C.h) cudaFreeHost(C.h); if (C.stream) cudaStreamDestroy(C.stream); cudaSetDevice(device); }
+    C = HostSearchCache();
+    C.device = device;
+    ORB_CUDA(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
+  }
+  // packed layout (256-byte aligned pieces): inputs first (one H2D), then device-only scratch, then outputs (one D2H)
+  size_t off = 0;
+  auto piece = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t oCK = piece((size_t)nc * sizeof(orb_keypoint)), oCD = piece((size_t)nc * 32), oCU = piece((size_t)nc * 4), oCO = piece((size_t)nc);
+  const size_t oLK = piece((size_t)nl * sizeof(orb_keypoint)), oLX = piece((size_t)nl * 12), oLF = piece((size_t)nl), oLD = piece((size_t)nl * 32);
+  const size_t oHdr = piece(256);   // n_cur, n_last, direction, Tcw[16]
+  const size_t inEnd = off;
+  const size_t oCS = piece((size_t)(kGridCells + 1) * 4), oCI = piece((size_t)nc * 4), oQ = piece((size_t)nl * sizeof(orb_proj_query));
+  const size_t scratchBytes = orb_search_scratch_bytes(1, nl, nc);
+  const size_t oScr = piece(scratchBytes);
+  const size_t outBegin = off;
+  const size_t oMK = piece((size_t)nc * 4), oMQ = piece((size_t)nl * 4), oNM = piece(256);
+  const size_t total = off;
+  if (total > C.bytes) {
+    ORB_CUDA(cudaStreamSynchronize(C.stream));
+    cudaFree(C.d); if (C.h) cudaFreeHost(C.h);
+    C.d = nullptr; C.h = nullptr; C.bytes = 0;
+    const size_t want = total + total / 2;
+    ORB_CUDA(cudaMalloc(&C.d, want));
+    ORB_CUDA(cudaHostAlloc((void**)&C.h, want, cudaHostAllocDefault));
+    C.bytes = want;
+  }
+  u8 *H = C.h, *D = C.d;
+  memcpy(H + oCK, a->cur_keypoints_un, (size_t)nc * sizeof(orb_keypoint));
+  memcpy(H + oCD, a->cur_descriptors, (size_t)nc * 32);
+  if (a->cur_uright) memcpy(H + oCU, a->cur_uright, (size_t)nc * 4);
+  if (a->cur_occupied) memcpy(H + oCO, a->cur_occupied, (size_t)nc); else memset(H + oCO, 0, (size_t)nc);
+  memcpy(H + oLK, a->last_keypoints, (size_t)nl * sizeof(orb_keypoint));
+  memcpy(H + oLX, a->last_world_pos, (size_t)nl * 12);
+  memcpy(H + oLF, a->last_mp_flags, (size_t)nl);
+  memcpy(H + oLD, a->last_mp_descriptors, (size_t)nl * 32);
+  int32_t* hdr = reinterpret_cast<int32_t*>(H + oHdr);
+  hdr[0] = nc; hdr[1] = nl; hdr[2] = a->direction;
+  memcpy(hdr + 4, a->Tcw, 16 * sizeof(float));
+  cudaStream_t s = C.stream;
+  ORB_CUDA(cudaMemcpyAsync(D, H, inEnd, cudaMemcpyHostToDevice, s));
+  const int32_t* dHdr = reinterpret_cast<const int32_t*>(D + oHdr);
+  int st = orb_assign_features_to_grid_device(device, reinterpret_cast<const orb_keypoint*>(D + oCK), dHdr, 1, nc, a->bounds4,
+                                              reinterpret_cast<int32_t*>(D + oCS), reinterpret_cast<int32_t*>(D + oCI), s);
+  if (st) return st;
+  st = orb_project_last_frame_device(device, reinterpret_cast<const float*>(D + oLX), D + oLF, reinterpret_cast<const orb_keypoint*>(D + oLK),
+                                     dHdr + 1, 1, nl, reinterpret_cast<const float*>(dHdr + 4), dHdr + 2, a->cam4, a->bounds4, a->mbf, a->th,
+                                     a->scale_factors, a->nlevels, reinterpret_cast<orb_proj_query*>(D + oQ), s);
+  if (st) return st;
+  orb_device_frames fr;
+  memset(&fr, 0, sizeof fr);
+  fr.keypoints_un = reinterpret_cast<const orb_keypoint*>(D + oCK); fr.descriptors = D + oCD;
+  fr.uright = a->cur_uright ? reinterpret_cast<const float*>(D + oCU) : nullptr;
+  fr.occupied = D + oCO; fr.counts = dHdr;
+  fr.cell_start = reinterpret_cast<const int32_t*>(D + oCS); fr.cell_items = reinterpret_cast<const int32_t*>(D + oCI);
+  for (int i = 0; i < 4; i++) fr.bounds[i] = a->bounds4[i];
+  fr.batch = 1; fr.capacity = nc;
+  orb_search_params sp = {ORB_SEARCH_BEST, a->th_dist, a->nn_ratio, a->check_orientation};
+  st = orb_search_by_projection_device(device, &fr, reinterpret_cast<const orb_proj_query*>(D + oQ), D + oLD, dHdr + 1, nl, &sp, D + oScr,
+                                       reinterpret_cast<int32_t*>(D + oMK), reinterpret_cast<int32_t*>(D + oMQ),
+                                       reinterpret_cast<int32_t*>(D + oNM), s);
+  if (st) return st;
+  ORB_CUDA(cudaMemcpyAsync(H + outBegin, D + outBegin, total - outBegin, cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaStreamSynchronize(s));
+  memcpy(match_of_keypoint, H + oMK, (size_t)nc * 4);
+  *nmatches = *reinterpret_cast<const int32_t*>(H + oNM);
+  return ORB_OK;
+}
+
 }  // extern "C"

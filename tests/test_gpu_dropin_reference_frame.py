@@ -127,3 +127,33 @@ def test_monocular_initialisation_sequence(dropin, reference):
     for F in (F1, F2):
         F.close()
     ini.close(); left.close()
+
+
+def _tracking_scenes(seed):
+    from orb_slam2_detailed_comments_b200.synth import tracking_scene
+    return [tracking_scene(n, q, seed + i, w=1241, h=376, distinct=0.9) for i, (n, q) in enumerate(((1500, 1400), (2000, 2000), (400, 900)))]
+
+
+@pytest.mark.parametrize("seed,th,direction", [(310, 15.0, 0), (410, 7.0, 1), (510, 15.0, 2)])
+def test_tracking_search_through_the_reference_class(dropin, reference, seed, th, direction):
+    """ORBmatcher(0.9, true).SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:1710-1860, called once per
+    tracked frame at src/Tracking.cc:1047) on live ORB_SLAM2::Frame / MapPoint objects: in liborbref_gpu.so the method's body is
+    the drop-in (compat/orb_b200_matcher.cpp -> orb_search_by_projection_last_frame: projection, grid, scan and in-order
+    commit on the GPU), in liborbref.so the reference's own CPU body. CurrentFrame.mvpMapPoints and the return value must be
+    identical."""
+    gref = dropin.reference_api()
+    sf = np.cumprod(np.concatenate([[1.0], np.full(7, np.float32(1.2), np.float32)]).astype(np.float32)).astype(np.float32)
+    total = 0
+    for s in _tracking_scenes(seed):
+        cam9 = np.concatenate([s["cam4"], np.zeros(5, np.float32)])
+        args = (s["uright"], s["occupied0"], s["last"], s["Xw"], s["mp_flags"], s["mp_desc"], s["Tcw"], s["cam4"], s["mbf"], s["mb"], th,
+                direction, sf)
+        Fc = reference.ReferenceFrame(s["cur"], s["cur_desc"], cam9, 1241, 376)
+        rn, rmk = reference.search_last_frame(Fc, *args)
+        Fg = gref.ReferenceFrame(s["cur"], s["cur_desc"], cam9, 1241, 376)
+        gn, gmk = gref.search_last_frame(Fg, *args)
+        assert gn == rn, "return value differs: %d vs %d" % (gn, rn)
+        assert np.array_equal(gmk, rmk), "CurrentFrame.mvpMapPoints differs in %d entries" % int((gmk != rmk).sum())
+        total += rn
+    print("seed", seed, "matches", total)
+    assert total > 1000
