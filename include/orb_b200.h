@@ -397,6 +397,16 @@ typedef struct orb_last_frame_search {
 } orb_last_frame_search;
 int orb_search_by_projection_last_frame(int device, const orb_last_frame_search* args, int32_t* match_of_keypoint, int* nmatches);
 
+/* Host-memory form of ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) (src/ORBmatcher.cc:72-169,
+ * the local-map search of Tracking::SearchLocalPoints) for ONE frame: `queries` are built by the caller from the MapPoint track
+ * fields Frame::isInFrustum wrote (mTrackProjX / Y / XR, mnTrackScaleLevel, mTrackViewCos, mbTrackInView && !isBad(); radius as
+ * :88-100), in map-point order; params = {ORB_SEARCH_RATIO_LEVEL, TH_HIGH, mfNNratio, 0}. Same staging and outputs as the
+ * last-frame form. */
+int orb_search_by_projection_host(int device, int n_cur, const orb_keypoint* cur_keypoints_un, const uint8_t* cur_descriptors,
+                                  const float* cur_uright, const uint8_t* cur_occupied, const float* bounds4, int n_queries,
+                                  const orb_proj_query* queries, const uint8_t* query_descriptors, const orb_search_params* params,
+                                  int32_t* match_of_keypoint, int* nmatches);
+
 /* Replaces ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (src/ORBmatcher.cc:247-420).
  * The DBoW2 FeatureVectors (node id -> feature indices) are passed as the node id of every feature
  * (d_node1 / d_node2, -1 = none). Keyframe side: (batch, query_capacity) features with d_usable1 = 1

@@ -2,9 +2,10 @@
 //
 // Compiled against the reference's own, UNMODIFIED include/ORBmatcher.h (all eleven methods stay declared there). A
 // maintainer deletes the bodies of ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2083-2103),
-// ORBmatcher::SearchForInitialization (:573-717) and ORBmatcher::SearchByProjection(Frame&, const Frame&, float, bool)
-// (:1710-1860, the per-frame tracking search) from src/ORBmatcher.cc and adds this file; the other eight methods keep
-// their CPU bodies in ORBmatcher.cc. (This repository's test build of the reference does the same without touching the
+// ORBmatcher::SearchForInitialization (:573-717), ORBmatcher::SearchByProjection(Frame&, const Frame&, float, bool)
+// (:1710-1860, the per-frame tracking search) and ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, float)
+// (:72-169, the local-map search) from src/ORBmatcher.cc and adds this file; the other seven methods keep their CPU
+// bodies in ORBmatcher.cc (RadiusByViewingCos :171 stays there too and is used here). (This repository's test build of the reference does the same without touching the
 // source: it weakens the two symbols in the compiled ORBmatcher.o, see INTEGRATION.md.)
 #include <algorithm>
 #include <cstring>
@@ -141,6 +142,47 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
   if (st != ORB_OK) throw std::runtime_error(std::string("ORBmatcher::SearchByProjection (liborb_b200): ") + orb_last_error());
   for (int i = 0; i < nc; i++)
     if (matchOfKp[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[matchOfKp[i]];   // :1813
+  return nmatches;
+}
+
+// src/ORBmatcher.cc:72-169 (called at src/Tracking.cc:1463 SearchLocalPoints): every local map point that Frame::isInFrustum
+// marked visible takes the best keypoint of its predicted level (or the one below) inside its window, unless an observed map
+// point already holds it; ratio test only when best and second best share a level.
+int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+  const bool bFactor = th != 1.0;
+  const int nc = F.N, nq = (int)vpMapPoints.size();
+  if (nc == 0 || nq == 0) return 0;
+  std::vector<orb_proj_query> q(nq);
+  std::vector<unsigned char> qdesc((size_t)nq * 32, 0), curDesc((size_t)nc * 32), occupied(nc, 0);
+  std::memset(q.data(), 0, (size_t)nq * sizeof(orb_proj_query));
+  for (int i = 0; i < nq; i++) {
+    MapPoint* pMP = vpMapPoints[i];
+    if (!pMP->mbTrackInView || pMP->isBad()) continue;              // :80-84: flags stay 0, the query is skipped
+    const int level = pMP->mnTrackScaleLevel;
+    float r = RadiusByViewingCos(pMP->mTrackViewCos);               // :88
+    if (bFactor) r *= th;
+    q[i].u = pMP->mTrackProjX; q[i].v = pMP->mTrackProjY; q[i].ur = pMP->mTrackProjXR;
+    q[i].radius = r * F.mvScaleFactors[level];                      // :95
+    q[i].min_level = level - 1; q[i].max_level = level;             // :96
+    q[i].flags = 1 | (pMP->Observations() > 0 ? 2 : 0);
+    const cv::Mat d = pMP->GetDescriptor();
+    std::memcpy(&qdesc[(size_t)i * 32], d.ptr(0), 32);
+  }
+  for (int i = 0; i < nc; i++) {
+    std::memcpy(&curDesc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+    MapPoint* p = F.mvpMapPoints[i];
+    occupied[i] = p && p->Observations() > 0;                       // :116-118
+  }
+  const float bounds4[4] = {Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY};
+  const orb_search_params sp = {ORB_SEARCH_RATIO_LEVEL, TH_HIGH, mfNNratio, 0};
+  std::vector<int32_t> matchOfKp(nc, -1);
+  int nmatches = 0;
+  const int st = orb_search_by_projection_host(0, nc, reinterpret_cast<const orb_keypoint*>(F.mvKeysUn.data()), curDesc.data(),
+                                               F.mvuRight.empty() ? nullptr : F.mvuRight.data(), occupied.data(), bounds4, nq, q.data(),
+                                               qdesc.data(), &sp, matchOfKp.data(), &nmatches);
+  if (st != ORB_OK) throw std::runtime_error(std::string("ORBmatcher::SearchByProjection (liborb_b200): ") + orb_last_error());
+  for (int i = 0; i < nc; i++)
+    if (matchOfKp[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[matchOfKp[i]];   // :161
   return nmatches;
 }
 

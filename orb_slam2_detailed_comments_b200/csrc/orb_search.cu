@@ -780,35 +780,36 @@ struct HostSearchCache {   // per host thread and device: staging buffers and a 
 thread_local HostSearchCache t_hs;
 }  // namespace
 
-int orb_search_by_projection_last_frame(int device, const orb_last_frame_search* a, int32_t* match_of_keypoint, int* nmatches) {
-  if (!a || !match_of_keypoint || !nmatches || !a->cur_keypoints_un || !a->cur_descriptors || !a->last_keypoints || !a->last_world_pos ||
-      !a->last_mp_flags || !a->last_mp_descriptors || !a->Tcw || !a->cam4 || !a->bounds4 || !a->scale_factors)
-    ORB_FAIL(ORB_ERR_INVALID, "null argument");
-  const int nc = a->n_cur, nl = a->n_last;
-  if (nc < 0 || nl < 0) ORB_FAIL(ORB_ERR_INVALID, "negative count");
+// Shared body: `nq` queries either given on the host (queries != NULL: the local-map search) or produced on the device by
+// the projection kernel from the last frame's map points (last != NULL).
+static int host_projection_search(int device, int nc, const orb_keypoint* cur_kps, const uint8_t* cur_desc, const float* cur_uright,
+                                  const uint8_t* cur_occupied, const float* bounds4, int nq, const orb_proj_query* queries,
+                                  const uint8_t* qdesc, const orb_last_frame_search* last, const orb_search_params* sp,
+                                  int32_t* match_of_keypoint, int* nmatches) {
   *nmatches = 0;
   for (int i = 0; i < nc; i++) match_of_keypoint[i] = -1;
-  if (nc == 0 || nl == 0) return ORB_OK;
+  if (nc <= 0 || nq <= 0) return ORB_OK;
   ORB_CUDA(cudaSetDevice(device));
   HostSearchCache& C = t_hs;
   if (C.device != device) {
     if (C.device >= 0) { cudaSetDevice(C.device); cudaFree(C.d); if (C.h) cudaFreeHost(C.h); if (C.stream) cudaStreamDestroy(C.stream); cudaSetDevice(device); }
-    C = HostSearchCache();
-    C.device = device;
+    C.device = device; C.stream = nullptr; C.d = nullptr; C.h = nullptr; C.bytes = 0;
     ORB_CUDA(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
   }
   // packed layout (256-byte aligned pieces): inputs first (one H2D), then device-only scratch, then outputs (one D2H)
   size_t off = 0;
   auto piece = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t oCK = piece((size_t)nc * sizeof(orb_keypoint)), oCD = piece((size_t)nc * 32), oCU = piece((size_t)nc * 4), oCO = piece((size_t)nc);
-  const size_t oLK = piece((size_t)nl * sizeof(orb_keypoint)), oLX = piece((size_t)nl * 12), oLF = piece((size_t)nl), oLD = piece((size_t)nl * 32);
-  const size_t oHdr = piece(256);   // n_cur, n_last, direction, Tcw[16]
+  const size_t oLK = piece(last ? (size_t)nq * sizeof(orb_keypoint) : 0), oLX = piece(last ? (size_t)nq * 12 : 0), oLF = piece(last ? (size_t)nq : 0);
+  const size_t oQD = piece((size_t)nq * 32);
+  const size_t oQH = piece(last ? 0 : (size_t)nq * sizeof(orb_proj_query));   // queries given by the host
+  const size_t oHdr = piece(256);   // n_cur, n_q, direction, Tcw[16]
   const size_t inEnd = off;
-  const size_t oCS = piece((size_t)(kGridCells + 1) * 4), oCI = piece((size_t)nc * 4), oQ = piece((size_t)nl * sizeof(orb_proj_query));
-  const size_t scratchBytes = orb_search_scratch_bytes(1, nl, nc);
-  const size_t oScr = piece(scratchBytes);
+  const size_t oCS = piece((size_t)(kGridCells + 1) * 4), oCI = piece((size_t)nc * 4);
+  const size_t oQ = last ? piece((size_t)nq * sizeof(orb_proj_query)) : oQH;
+  const size_t oScr = piece(orb_search_scratch_bytes(1, nq, nc));
   const size_t outBegin = off;
-  const size_t oMK = piece((size_t)nc * 4), oMQ = piece((size_t)nl * 4), oNM = piece(256);
+  const size_t oMK = piece((size_t)nc * 4), oMQ = piece((size_t)nq * 4), oNM = piece(256);
   const size_t total = off;
   if (total > C.bytes) {
     ORB_CUDA(cudaStreamSynchronize(C.stream));
@@ -820,37 +821,43 @@ int orb_search_by_projection_last_frame(int device, const orb_last_frame_search*
     C.bytes = want;
   }
   u8 *H = C.h, *D = C.d;
-  memcpy(H + oCK, a->cur_keypoints_un, (size_t)nc * sizeof(orb_keypoint));
-  memcpy(H + oCD, a->cur_descriptors, (size_t)nc * 32);
-  if (a->cur_uright) memcpy(H + oCU, a->cur_uright, (size_t)nc * 4);
-  if (a->cur_occupied) memcpy(H + oCO, a->cur_occupied, (size_t)nc); else memset(H + oCO, 0, (size_t)nc);
-  memcpy(H + oLK, a->last_keypoints, (size_t)nl * sizeof(orb_keypoint));
-  memcpy(H + oLX, a->last_world_pos, (size_t)nl * 12);
-  memcpy(H + oLF, a->last_mp_flags, (size_t)nl);
-  memcpy(H + oLD, a->last_mp_descriptors, (size_t)nl * 32);
+  memcpy(H + oCK, cur_kps, (size_t)nc * sizeof(orb_keypoint));
+  memcpy(H + oCD, cur_desc, (size_t)nc * 32);
+  if (cur_uright) memcpy(H + oCU, cur_uright, (size_t)nc * 4);
+  if (cur_occupied) memcpy(H + oCO, cur_occupied, (size_t)nc); else memset(H + oCO, 0, (size_t)nc);
+  memcpy(H + oQD, qdesc, (size_t)nq * 32);
   int32_t* hdr = reinterpret_cast<int32_t*>(H + oHdr);
-  hdr[0] = nc; hdr[1] = nl; hdr[2] = a->direction;
-  memcpy(hdr + 4, a->Tcw, 16 * sizeof(float));
+  hdr[0] = nc; hdr[1] = nq; hdr[2] = 0;
+  if (last) {
+    memcpy(H + oLK, last->last_keypoints, (size_t)nq * sizeof(orb_keypoint));
+    memcpy(H + oLX, last->last_world_pos, (size_t)nq * 12);
+    memcpy(H + oLF, last->last_mp_flags, (size_t)nq);
+    hdr[2] = last->direction;
+    memcpy(hdr + 4, last->Tcw, 16 * sizeof(float));
+  } else {
+    memcpy(H + oQH, queries, (size_t)nq * sizeof(orb_proj_query));
+  }
   cudaStream_t s = C.stream;
   ORB_CUDA(cudaMemcpyAsync(D, H, inEnd, cudaMemcpyHostToDevice, s));
   const int32_t* dHdr = reinterpret_cast<const int32_t*>(D + oHdr);
-  int st = orb_assign_features_to_grid_device(device, reinterpret_cast<const orb_keypoint*>(D + oCK), dHdr, 1, nc, a->bounds4,
+  int st = orb_assign_features_to_grid_device(device, reinterpret_cast<const orb_keypoint*>(D + oCK), dHdr, 1, nc, bounds4,
                                               reinterpret_cast<int32_t*>(D + oCS), reinterpret_cast<int32_t*>(D + oCI), s);
   if (st) return st;
-  st = orb_project_last_frame_device(device, reinterpret_cast<const float*>(D + oLX), D + oLF, reinterpret_cast<const orb_keypoint*>(D + oLK),
-                                     dHdr + 1, 1, nl, reinterpret_cast<const float*>(dHdr + 4), dHdr + 2, a->cam4, a->bounds4, a->mbf, a->th,
-                                     a->scale_factors, a->nlevels, reinterpret_cast<orb_proj_query*>(D + oQ), s);
-  if (st) return st;
+  if (last) {
+    st = orb_project_last_frame_device(device, reinterpret_cast<const float*>(D + oLX), D + oLF, reinterpret_cast<const orb_keypoint*>(D + oLK),
+                                       dHdr + 1, 1, nq, reinterpret_cast<const float*>(dHdr + 4), dHdr + 2, last->cam4, bounds4, last->mbf,
+                                       last->th, last->scale_factors, last->nlevels, reinterpret_cast<orb_proj_query*>(D + oQ), s);
+    if (st) return st;
+  }
   orb_device_frames fr;
   memset(&fr, 0, sizeof fr);
   fr.keypoints_un = reinterpret_cast<const orb_keypoint*>(D + oCK); fr.descriptors = D + oCD;
-  fr.uright = a->cur_uright ? reinterpret_cast<const float*>(D + oCU) : nullptr;
+  fr.uright = cur_uright ? reinterpret_cast<const float*>(D + oCU) : nullptr;
   fr.occupied = D + oCO; fr.counts = dHdr;
   fr.cell_start = reinterpret_cast<const int32_t*>(D + oCS); fr.cell_items = reinterpret_cast<const int32_t*>(D + oCI);
-  for (int i = 0; i < 4; i++) fr.bounds[i] = a->bounds4[i];
+  for (int i = 0; i < 4; i++) fr.bounds[i] = bounds4[i];
   fr.batch = 1; fr.capacity = nc;
-  orb_search_params sp = {ORB_SEARCH_BEST, a->th_dist, a->nn_ratio, a->check_orientation};
-  st = orb_search_by_projection_device(device, &fr, reinterpret_cast<const orb_proj_query*>(D + oQ), D + oLD, dHdr + 1, nl, &sp, D + oScr,
+  st = orb_search_by_projection_device(device, &fr, reinterpret_cast<const orb_proj_query*>(D + oQ), D + oQD, dHdr + 1, nq, sp, D + oScr,
                                        reinterpret_cast<int32_t*>(D + oMK), reinterpret_cast<int32_t*>(D + oMQ),
                                        reinterpret_cast<int32_t*>(D + oNM), s);
   if (st) return st;
@@ -859,6 +866,27 @@ int orb_search_by_projection_last_frame(int device, const orb_last_frame_search*
   memcpy(match_of_keypoint, H + oMK, (size_t)nc * 4);
   *nmatches = *reinterpret_cast<const int32_t*>(H + oNM);
   return ORB_OK;
+}
+
+int orb_search_by_projection_last_frame(int device, const orb_last_frame_search* a, int32_t* match_of_keypoint, int* nmatches) {
+  if (!a || !match_of_keypoint || !nmatches || !a->cur_keypoints_un || !a->cur_descriptors || !a->last_keypoints || !a->last_world_pos ||
+      !a->last_mp_flags || !a->last_mp_descriptors || !a->Tcw || !a->cam4 || !a->bounds4 || !a->scale_factors)
+    ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (a->n_cur < 0 || a->n_last < 0) ORB_FAIL(ORB_ERR_INVALID, "negative count");
+  const orb_search_params sp = {ORB_SEARCH_BEST, a->th_dist, a->nn_ratio, a->check_orientation};
+  return host_projection_search(device, a->n_cur, a->cur_keypoints_un, a->cur_descriptors, a->cur_uright, a->cur_occupied, a->bounds4,
+                                a->n_last, nullptr, a->last_mp_descriptors, a, &sp, match_of_keypoint, nmatches);
+}
+
+int orb_search_by_projection_host(int device, int n_cur, const orb_keypoint* cur_keypoints_un, const uint8_t* cur_descriptors,
+                                  const float* cur_uright, const uint8_t* cur_occupied, const float* bounds4, int n_queries,
+                                  const orb_proj_query* queries, const uint8_t* query_descriptors, const orb_search_params* params,
+                                  int32_t* match_of_keypoint, int* nmatches) {
+  if (!match_of_keypoint || !nmatches || !cur_keypoints_un || !cur_descriptors || !bounds4 || !queries || !query_descriptors || !params)
+    ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (n_cur < 0 || n_queries < 0) ORB_FAIL(ORB_ERR_INVALID, "negative count");
+  return host_projection_search(device, n_cur, cur_keypoints_un, cur_descriptors, cur_uright, cur_occupied, bounds4, n_queries, queries,
+                                query_descriptors, nullptr, params, match_of_keypoint, nmatches);
 }
 
 }  // extern "C"

@@ -157,3 +157,26 @@ def test_tracking_search_through_the_reference_class(dropin, reference, seed, th
         total += rn
     print("seed", seed, "matches", total)
     assert total > 1000
+
+
+@pytest.mark.parametrize("seed,th", [(21, 1.0), (22, 3.0), (23, 5.0)])
+def test_local_map_search_through_the_reference_class(dropin, reference, oracle, seed, th):
+    """ORBmatcher(0.8).SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:72-169, Tracking::SearchLocalPoints) on live
+    MapPoint objects whose track fields were filled as Frame::isInFrustum does: drop-in body (orb_search_by_projection_host)
+    against the reference's own CPU body - F.mvpMapPoints and the return value identical."""
+    from orb_slam2_detailed_comments_b200.synth import tracking_scene
+    from test_oracle_search import SF, local_map_points
+    gref = dropin.reference_api()
+    total = 0
+    for k, (n_cur, n_mp) in enumerate(((600, 700), (2000, 2200))):
+        sc = tracking_scene(n_cur, n_mp, seed + 100 * k, frac_mapped=0.9)
+        q0 = oracle.project_last_frame(sc["Xw"], sc["mp_flags"] | 1, sc["last"], sc["Tcw"], sc["cam4"], sc["bounds"], sc["mbf"], 1.0, SF, 0)
+        mps = local_map_points(sc, q0, seed)
+        cam9 = np.concatenate([sc["cam4"], np.zeros(5, np.float32)])
+        args = (sc["uright"], sc["occupied0"], mps, th, 0.8, sc["cam4"], sc["mbf"], sc["mb"], SF)
+        rn, rmk = reference.search_local_map(reference.ReferenceFrame(sc["cur"], sc["cur_desc"], cam9, 1241, 376), *args)
+        gn, gmk = gref.search_local_map(gref.ReferenceFrame(sc["cur"], sc["cur_desc"], cam9, 1241, 376), *args)
+        assert gn == rn, "return value differs: %d vs %d" % (gn, rn)
+        assert np.array_equal(gmk, rmk), "F.mvpMapPoints differs in %d entries" % int((gmk != rmk).sum())
+        total += rn
+    assert total > 100
