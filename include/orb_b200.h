@@ -423,6 +423,16 @@ int orb_search_by_bow_device(int device, const orb_keypoint* d_keypoints1, const
                              const orb_search_params* params, void* d_scratch, int32_t* d_match_of_keypoint,
                              int32_t* d_match_of_query, int32_t* d_nmatches, void* stream);
 
+/* Host-memory form of orb_search_by_bow_device for ONE pair (all pointers HOST pointers; one packed upload, the kernels, one
+ * packed download, one synchronisation): what the drop-in bodies of ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)
+ * (src/ORBmatcher.cc:247-420: occupied2 = NULL, th = TH_LOW, vpMapPointMatches from match_of_keypoint2) and
+ * ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) (:729-880: occupied2[i] = !vpMapPoints2[i] || isBad(), th = TH_LOW - 1,
+ * vpMatches12 from match_of_query1) call. node1 / node2 = DBoW2 node id of every feature (mFeatVec inverted), -1 = none. */
+int orb_search_by_bow_host(int device, int n1, const orb_keypoint* keypoints1_un, const uint8_t* descriptors1, const int32_t* node1,
+                           const uint8_t* usable1, int n2, const orb_keypoint* keypoints2_un, const uint8_t* descriptors2,
+                           const int32_t* node2, const uint8_t* occupied2, const orb_search_params* params, int32_t* match_of_keypoint2,
+                           int32_t* match_of_query1, int* nmatches);
+
 /* Per keyframe pair of SearchForTriangulation. */
 typedef struct orb_triangulation_pair {
   float F12[9];        /* fundamental matrix, row-major (F12.at<float>(r, c) = F12[3*r + c]) */
@@ -445,6 +455,15 @@ int orb_search_for_triangulation_device(int device, const orb_keypoint* d_keypoi
                                         const float* scale_factors, const float* level_sigma2, int nlevels,
                                         int check_orientation, void* d_scratch, int32_t* d_matches12, int32_t* d_nmatches,
                                         void* stream);
+
+/* Host-memory form of orb_search_for_triangulation_device for ONE keyframe pair (the drop-in body of
+ * ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:884-1100); pair / scale_factors / level_sigma2 are host pointers too. */
+int orb_search_for_triangulation_host(int device, int n1, const orb_keypoint* keypoints1_un, const uint8_t* descriptors1,
+                                      const int32_t* node1, const uint8_t* has_mappoint1, const float* uright1, int n2,
+                                      const orb_keypoint* keypoints2_un, const uint8_t* descriptors2, const int32_t* node2,
+                                      const uint8_t* has_mappoint2, const float* uright2, const orb_triangulation_pair* pair,
+                                      const float* scale_factors, const float* level_sigma2, int nlevels, int check_orientation,
+                                      int32_t* matches12, int* nmatches);
 
 /* ---- Input stage and map-point descriptors (the callers either side of the path) ------ */
 

@@ -81,7 +81,7 @@ EXPORTS = [
     "orb_shard_range", "orb_nccl_unique_id", "orb_nccl_comm_create", "orb_nccl_comm_destroy", "orb_match_allpairs_nccl",
     "orb_hamming_matrix_device", "orb_matcher_synchronize", "orb_int_pipe_peak",
     "orb_search_scratch_bytes", "orb_project_last_frame_device", "orb_search_by_projection_device", "orb_search_by_projection_last_frame", "orb_search_by_projection_host",
-    "orb_search_by_bow_device", "orb_search_for_triangulation_device",
+    "orb_search_by_bow_device", "orb_search_for_triangulation_device", "orb_search_by_bow_host", "orb_search_for_triangulation_host",
     "orb_cvt_color_gray_device", "orb_remap_linear_device", "orb_distinctive_descriptors_device",
 ]
 

@@ -4,8 +4,10 @@
 // maintainer deletes the bodies of ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2083-2103),
 // ORBmatcher::SearchForInitialization (:573-717), ORBmatcher::SearchByProjection(Frame&, const Frame&, float, bool)
 // (:1710-1860, the per-frame tracking search) and ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, float)
-// (:72-169, the local-map search) from src/ORBmatcher.cc and adds this file; the other seven methods keep their CPU
-// bodies in ORBmatcher.cc (RadiusByViewingCos :171 stays there too and is used here). (This repository's test build of the reference does the same without touching the
+// (:72-169, the local-map search), both ORBmatcher::SearchByBoW (:247-420, :729-880) and ORBmatcher::SearchForTriangulation
+// (:884-1100) from src/ORBmatcher.cc and adds this file; the four methods that write into live MapPoint / KeyFrame objects
+// (SearchByProjection keyframe / loop variants, Fuse x2, SearchBySim3) keep their CPU bodies in ORBmatcher.cc, and so do
+// RadiusByViewingCos (:171), CheckDistEpipolarLine (:205) and ComputeThreeMaxima (:2035). (This repository's test build of the reference does the same without touching the
 // source: it weakens the two symbols in the compiled ORBmatcher.o, see INTEGRATION.md.)
 #include <algorithm>
 #include <cstring>
@@ -36,6 +38,21 @@ struct MatcherCache {   // one C-ABI matcher per host thread (ORBmatcher objects
   }
 };
 thread_local MatcherCache t_matcher;
+
+// DBoW2::FeatureVector (node id -> feature indices) inverted: the node id of every feature, -1 = none
+std::vector<int32_t> node_of_features(const DBoW2::FeatureVector& fv, size_t n) {
+  std::vector<int32_t> node(n, -1);
+  for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it)
+    for (size_t k = 0; k < it->second.size(); k++)
+      if (it->second[k] < n) node[it->second[k]] = (int32_t)it->first;
+  return node;
+}
+
+std::vector<unsigned char> rows_of(const cv::Mat& descriptors, size_t n) {
+  std::vector<unsigned char> d(n * 32);
+  for (size_t i = 0; i < n; i++) std::memcpy(&d[i * 32], descriptors.ptr((int)i), 32);
+  return d;
+}
 
 void pack(const Frame& F, std::vector<float>& xy, std::vector<int32_t>& oct, std::vector<float>& ang, std::vector<unsigned char>& desc) {
   const size_t n = F.mvKeysUn.size();
@@ -183,6 +200,93 @@ int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMap
   if (st != ORB_OK) throw std::runtime_error(std::string("ORBmatcher::SearchByProjection (liborb_b200): ") + orb_last_error());
   for (int i = 0; i < nc; i++)
     if (matchOfKp[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[matchOfKp[i]];   // :161
+  return nmatches;
+}
+
+// src/ORBmatcher.cc:247-420 (Tracking::TrackReferenceKeyFrame, Relocalization): features of the keyframe that hold a good map
+// point are matched, inside their vocabulary node, against the frame's features; ratio test, one map point per frame feature,
+// rotation histogram.
+int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+  const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+  vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+  const int n1 = (int)vpMapPointsKF.size(), n2 = F.N;
+  if (n1 == 0 || n2 == 0) return 0;
+  std::vector<unsigned char> usable(n1, 0);
+  for (int i = 0; i < n1; i++) usable[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();   // :283-287
+  const std::vector<int32_t> node1 = node_of_features(pKF->mFeatVec, n1), node2 = node_of_features(F.mFeatVec, n2);
+  const std::vector<unsigned char> d1 = rows_of(pKF->mDescriptors, n1), d2 = rows_of(F.mDescriptors, n2);
+  const orb_search_params sp = {ORB_SEARCH_RATIO, TH_LOW, mfNNratio, mbCheckOrientation ? 1 : 0};
+  std::vector<int32_t> ofKp(n2, -1), ofQ(n1, -1);
+  int nmatches = 0;
+  const int st = orb_search_by_bow_host(0, n1, reinterpret_cast<const orb_keypoint*>(pKF->mvKeysUn.data()), d1.data(), node1.data(),
+                                        usable.data(), n2, reinterpret_cast<const orb_keypoint*>(F.mvKeysUn.data()), d2.data(), node2.data(),
+                                        nullptr, &sp, ofKp.data(), ofQ.data(), &nmatches);
+  if (st != ORB_OK) throw std::runtime_error(std::string("ORBmatcher::SearchByBoW (liborb_b200): ") + orb_last_error());
+  for (int i = 0; i < n2; i++)
+    if (ofKp[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[ofKp[i]];   // :343
+  return nmatches;
+}
+
+// src/ORBmatcher.cc:729-880 (LoopClosing::ComputeSim3): map points of keyframe 1 against map points of keyframe 2.
+int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+  const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+  const std::vector<MapPoint*> vpMapPoints2 = pKF2->GetMapPointMatches();
+  vpMatches12 = std::vector<MapPoint*>(vpMapPoints1.size(), static_cast<MapPoint*>(NULL));
+  const int n1 = (int)vpMapPoints1.size(), n2 = (int)vpMapPoints2.size();
+  if (n1 == 0 || n2 == 0) return 0;
+  std::vector<unsigned char> usable(n1, 0), notCandidate(n2, 0);
+  for (int i = 0; i < n1; i++) usable[i] = vpMapPoints1[i] && !vpMapPoints1[i]->isBad();            // :770-774
+  for (int i = 0; i < n2; i++) notCandidate[i] = !vpMapPoints2[i] || vpMapPoints2[i]->isBad();      // :788-793
+  const std::vector<int32_t> node1 = node_of_features(pKF1->mFeatVec, n1), node2 = node_of_features(pKF2->mFeatVec, n2);
+  const std::vector<unsigned char> d1 = rows_of(pKF1->mDescriptors, n1), d2 = rows_of(pKF2->mDescriptors, n2);
+  const orb_search_params sp = {ORB_SEARCH_RATIO, TH_LOW - 1, mfNNratio, mbCheckOrientation ? 1 : 0};   // :813 tests bestDist1 < TH_LOW
+  std::vector<int32_t> ofKp(n2, -1), ofQ(n1, -1);
+  int nmatches = 0;
+  const int st = orb_search_by_bow_host(0, n1, reinterpret_cast<const orb_keypoint*>(pKF1->mvKeysUn.data()), d1.data(), node1.data(),
+                                        usable.data(), n2, reinterpret_cast<const orb_keypoint*>(pKF2->mvKeysUn.data()), d2.data(),
+                                        node2.data(), notCandidate.data(), &sp, ofKp.data(), ofQ.data(), &nmatches);
+  if (st != ORB_OK) throw std::runtime_error(std::string("ORBmatcher::SearchByBoW (liborb_b200): ") + orb_last_error());
+  for (int i = 0; i < n1; i++)
+    if (ofQ[i] >= 0) vpMatches12[i] = vpMapPoints2[ofQ[i]];   // :818
+  return nmatches;
+}
+
+// src/ORBmatcher.cc:884-1100 (LocalMapping::CreateNewMapPoints): features of keyframe 1 without a map point against features of
+// keyframe 2 without one, inside their vocabulary node, best distance <= TH_LOW, epipole and epipolar-line tests.
+int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
+                                       const bool bOnlyStereo) {
+  // the epipole: keyframe 1's camera centre in keyframe 2's image, :893-901 (the caller's own cv::Mat arithmetic)
+  cv::Mat Cw = pKF1->GetCameraCenter();
+  cv::Mat R2w = pKF2->GetRotation();
+  cv::Mat t2w = pKF2->GetTranslation();
+  cv::Mat C2 = R2w * Cw + t2w;
+  const float invz = 1.0f / C2.at<float>(2);
+  orb_triangulation_pair pr;
+  pr.ex = pKF2->fx * C2.at<float>(0) * invz + pKF2->cx;
+  pr.ey = pKF2->fy * C2.at<float>(1) * invz + pKF2->cy;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) pr.F12[3 * r + c] = F12.at<float>(r, c);
+  pr.only_stereo = bOnlyStereo ? 1 : 0;
+  vMatchedPairs.clear();
+  const int n1 = pKF1->N, n2 = pKF2->N;
+  if (n1 == 0 || n2 == 0) return 0;
+  std::vector<unsigned char> has1(n1, 0), has2(n2, 0);
+  for (int i = 0; i < n1; i++) has1[i] = pKF1->GetMapPoint(i) != NULL;    // :928-933
+  for (int i = 0; i < n2; i++) has2[i] = pKF2->GetMapPoint(i) != NULL;    // :963-967
+  const std::vector<int32_t> node1 = node_of_features(pKF1->mFeatVec, n1), node2 = node_of_features(pKF2->mFeatVec, n2);
+  const std::vector<unsigned char> d1 = rows_of(pKF1->mDescriptors, n1), d2 = rows_of(pKF2->mDescriptors, n2);
+  std::vector<int32_t> m12(n1, -1);
+  int nmatches = 0;
+  const int st = orb_search_for_triangulation_host(0, n1, reinterpret_cast<const orb_keypoint*>(pKF1->mvKeysUn.data()), d1.data(),
+                                                   node1.data(), has1.data(), pKF1->mvuRight.data(), n2,
+                                                   reinterpret_cast<const orb_keypoint*>(pKF2->mvKeysUn.data()), d2.data(), node2.data(),
+                                                   has2.data(), pKF2->mvuRight.data(), &pr, pKF2->mvScaleFactors.data(),
+                                                   pKF2->mvLevelSigma2.data(), (int)pKF2->mvScaleFactors.size(), mbCheckOrientation ? 1 : 0,
+                                                   m12.data(), &nmatches);
+  if (st != ORB_OK) throw std::runtime_error(std::string("ORBmatcher::SearchForTriangulation (liborb_b200): ") + orb_last_error());
+  vMatchedPairs.reserve(nmatches);
+  for (int i = 0; i < n1; i++)
+    if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));   // :1089-1094
   return nmatches;
 }
 

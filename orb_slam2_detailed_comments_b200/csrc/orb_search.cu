@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstring>
+#include <vector>
 
 #include "orb_common.cuh"
 
@@ -887,6 +888,146 @@ int orb_search_by_projection_host(int device, int n_cur, const orb_keypoint* cur
   if (n_cur < 0 || n_queries < 0) ORB_FAIL(ORB_ERR_INVALID, "negative count");
   return host_projection_search(device, n_cur, cur_keypoints_un, cur_descriptors, cur_uright, cur_occupied, bounds4, n_queries, queries,
                                 query_descriptors, nullptr, params, match_of_keypoint, nmatches);
+}
+
+// ---- host-memory forms of the vocabulary-guided searches ------------------------------------------------------------
+namespace {
+// Packs host arrays into the thread's pinned staging block / device block (256-byte aligned pieces).
+struct HostPack {
+  HostSearchCache& C;
+  size_t off = 0, inEnd = 0, outBegin = 0;
+  struct Piece { size_t off, bytes; const void* src; };
+  std::vector<Piece> in;
+  explicit HostPack(HostSearchCache& c) : C(c) {}
+  size_t add(size_t bytes, const void* src = nullptr) {
+    const size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    if (src) in.push_back(Piece{o, bytes, src});
+    return o;
+  }
+  int prepare(int device) {   // call after every piece has been added
+    if (C.device != device) {
+      if (C.device >= 0) { cudaSetDevice(C.device); cudaFree(C.d); if (C.h) cudaFreeHost(C.h); if (C.stream) cudaStreamDestroy(C.stream); cudaSetDevice(device); }
+      C.device = device; C.stream = nullptr; C.d = nullptr; C.h = nullptr; C.bytes = 0;
+      ORB_CUDA(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
+    }
+    if (off > C.bytes) {
+      ORB_CUDA(cudaStreamSynchronize(C.stream));
+      cudaFree(C.d); if (C.h) cudaFreeHost(C.h);
+      C.d = nullptr; C.h = nullptr; C.bytes = 0;
+      const size_t want = off + off / 2;
+      ORB_CUDA(cudaMalloc(&C.d, want));
+      ORB_CUDA(cudaHostAlloc((void**)&C.h, want, cudaHostAllocDefault));
+      C.bytes = want;
+    }
+    for (const Piece& p : in) memcpy(C.h + p.off, p.src, p.bytes);
+    return ORB_OK;
+  }
+};
+}  // namespace
+
+int orb_search_by_bow_host(int device, int n1, const orb_keypoint* keypoints1_un, const uint8_t* descriptors1, const int32_t* node1,
+                           const uint8_t* usable1, int n2, const orb_keypoint* keypoints2_un, const uint8_t* descriptors2,
+                           const int32_t* node2, const uint8_t* occupied2, const orb_search_params* params, int32_t* match_of_keypoint2,
+                           int32_t* match_of_query1, int* nmatches) {
+  if (!keypoints1_un || !descriptors1 || !node1 || !usable1 || !keypoints2_un || !descriptors2 || !node2 || !params || !nmatches ||
+      !match_of_keypoint2 || !match_of_query1)
+    ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (n1 < 0 || n2 < 0) ORB_FAIL(ORB_ERR_INVALID, "negative count");
+  *nmatches = 0;
+  for (int i = 0; i < n2; i++) match_of_keypoint2[i] = -1;
+  for (int i = 0; i < n1; i++) match_of_query1[i] = -1;
+  if (n1 == 0 || n2 == 0) return ORB_OK;
+  ORB_CUDA(cudaSetDevice(device));
+  HostPack P(t_hs);
+  std::vector<uint8_t> occ0;
+  if (!occupied2) { occ0.assign(n2, 0); occupied2 = occ0.data(); }
+  const int32_t counts[2] = {n1, n2};
+  const size_t oK1 = P.add((size_t)n1 * sizeof(orb_keypoint), keypoints1_un), oD1 = P.add((size_t)n1 * 32, descriptors1);
+  const size_t oN1 = P.add((size_t)n1 * 4, node1), oU1 = P.add((size_t)n1, usable1);
+  const size_t oK2 = P.add((size_t)n2 * sizeof(orb_keypoint), keypoints2_un), oD2 = P.add((size_t)n2 * 32, descriptors2);
+  const size_t oN2 = P.add((size_t)n2 * 4, node2), oO2 = P.add((size_t)n2, occupied2);
+  const size_t oCnt = P.add(256, counts);
+  const size_t inEnd = P.off;
+  const size_t oScr = P.add(orb_search_scratch_bytes(1, n1, n2));
+  const size_t outBegin = P.off;
+  const size_t oMK = P.add((size_t)n2 * 4), oMQ = P.add((size_t)n1 * 4), oNM = P.add(256);
+  int st = P.prepare(device);
+  if (st) return st;
+  HostSearchCache& C = t_hs;
+  u8 *H = C.h, *D = C.d;
+  memcpy(H + oCnt, counts, sizeof counts);
+  cudaStream_t s = C.stream;
+  ORB_CUDA(cudaMemcpyAsync(D, H, inEnd, cudaMemcpyHostToDevice, s));
+  const int32_t* dCnt = reinterpret_cast<const int32_t*>(D + oCnt);
+  orb_device_frames fr;
+  memset(&fr, 0, sizeof fr);
+  fr.keypoints_un = reinterpret_cast<const orb_keypoint*>(D + oK2); fr.descriptors = D + oD2;
+  fr.occupied = D + oO2; fr.counts = dCnt + 1;
+  fr.batch = 1; fr.capacity = n2;
+  st = orb_search_by_bow_device(device, reinterpret_cast<const orb_keypoint*>(D + oK1), D + oD1, reinterpret_cast<const int32_t*>(D + oN1),
+                                D + oU1, dCnt, n1, &fr, reinterpret_cast<const int32_t*>(D + oN2), params, D + oScr,
+                                reinterpret_cast<int32_t*>(D + oMK), reinterpret_cast<int32_t*>(D + oMQ), reinterpret_cast<int32_t*>(D + oNM), s);
+  if (st) return st;
+  ORB_CUDA(cudaMemcpyAsync(H + outBegin, D + outBegin, P.off - outBegin, cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaStreamSynchronize(s));
+  memcpy(match_of_keypoint2, H + oMK, (size_t)n2 * 4);
+  memcpy(match_of_query1, H + oMQ, (size_t)n1 * 4);
+  *nmatches = *reinterpret_cast<const int32_t*>(H + oNM);
+  return ORB_OK;
+}
+
+int orb_search_for_triangulation_host(int device, int n1, const orb_keypoint* keypoints1_un, const uint8_t* descriptors1,
+                                      const int32_t* node1, const uint8_t* has_mappoint1, const float* uright1, int n2,
+                                      const orb_keypoint* keypoints2_un, const uint8_t* descriptors2, const int32_t* node2,
+                                      const uint8_t* has_mappoint2, const float* uright2, const orb_triangulation_pair* pair,
+                                      const float* scale_factors, const float* level_sigma2, int nlevels, int check_orientation,
+                                      int32_t* matches12, int* nmatches) {
+  if (!keypoints1_un || !descriptors1 || !node1 || !has_mappoint1 || !keypoints2_un || !descriptors2 || !node2 || !has_mappoint2 ||
+      !pair || !scale_factors || !level_sigma2 || !matches12 || !nmatches)
+    ORB_FAIL(ORB_ERR_INVALID, "null argument");
+  if (n1 < 0 || n2 < 0) ORB_FAIL(ORB_ERR_INVALID, "negative count");
+  *nmatches = 0;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  if (n1 == 0 || n2 == 0) return ORB_OK;
+  ORB_CUDA(cudaSetDevice(device));
+  HostPack P(t_hs);
+  const int32_t counts[2] = {n1, n2};
+  const size_t oK1 = P.add((size_t)n1 * sizeof(orb_keypoint), keypoints1_un), oD1 = P.add((size_t)n1 * 32, descriptors1);
+  const size_t oN1 = P.add((size_t)n1 * 4, node1), oH1 = P.add((size_t)n1, has_mappoint1), oR1 = P.add((size_t)n1 * 4, uright1);
+  const size_t oK2 = P.add((size_t)n2 * sizeof(orb_keypoint), keypoints2_un), oD2 = P.add((size_t)n2 * 32, descriptors2);
+  const size_t oN2 = P.add((size_t)n2 * 4, node2), oH2 = P.add((size_t)n2, has_mappoint2), oR2 = P.add((size_t)n2 * 4, uright2);
+  const size_t oPair = P.add(256, pair), oCnt = P.add(256, counts);
+  const size_t inEnd = P.off;
+  const size_t oScr = P.add(orb_search_scratch_bytes(1, n1, n2));
+  const size_t outBegin = P.off;
+  const size_t oM12 = P.add((size_t)n1 * 4), oNM = P.add(256);
+  int st = P.prepare(device);
+  if (st) return st;
+  HostSearchCache& C = t_hs;
+  u8 *H = C.h, *D = C.d;
+  memcpy(H + oPair, pair, sizeof(orb_triangulation_pair));
+  memcpy(H + oCnt, counts, sizeof counts);
+  cudaStream_t s = C.stream;
+  ORB_CUDA(cudaMemcpyAsync(D, H, inEnd, cudaMemcpyHostToDevice, s));
+  const int32_t* dCnt = reinterpret_cast<const int32_t*>(D + oCnt);
+  orb_device_frames fr;
+  memset(&fr, 0, sizeof fr);
+  fr.keypoints_un = reinterpret_cast<const orb_keypoint*>(D + oK2); fr.descriptors = D + oD2;
+  fr.uright = uright2 ? reinterpret_cast<const float*>(D + oR2) : nullptr;
+  fr.occupied = D + oH2; fr.counts = dCnt + 1;
+  fr.batch = 1; fr.capacity = n2;
+  st = orb_search_for_triangulation_device(device, reinterpret_cast<const orb_keypoint*>(D + oK1), D + oD1, reinterpret_cast<const int32_t*>(D + oN1),
+                                           D + oH1, uright1 ? reinterpret_cast<const float*>(D + oR1) : nullptr, dCnt, n1, &fr,
+                                           reinterpret_cast<const int32_t*>(D + oN2), reinterpret_cast<const orb_triangulation_pair*>(D + oPair),
+                                           scale_factors, level_sigma2, nlevels, check_orientation, D + oScr,
+                                           reinterpret_cast<int32_t*>(D + oM12), reinterpret_cast<int32_t*>(D + oNM), s);
+  if (st) return st;
+  ORB_CUDA(cudaMemcpyAsync(H + outBegin, D + outBegin, P.off - outBegin, cudaMemcpyDeviceToHost, s));
+  ORB_CUDA(cudaStreamSynchronize(s));
+  memcpy(matches12, H + oM12, (size_t)n1 * 4);
+  *nmatches = *reinterpret_cast<const int32_t*>(H + oNM);
+  return ORB_OK;
 }
 
 }  // extern "C"

@@ -180,3 +180,70 @@ def test_local_map_search_through_the_reference_class(dropin, reference, oracle,
         assert np.array_equal(gmk, rmk), "F.mvpMapPoints differs in %d entries" % int((gmk != rmk).sum())
         total += rn
     assert total > 100
+
+
+def _bow_nodes(sc, seed, n1, n2, nodes):
+    rng = np.random.RandomState(seed)
+    node2 = rng.randint(0, nodes, n2).astype(np.int32)
+    node1 = np.where(rng.rand(n1) < 0.85, node2[sc["src"]], rng.randint(0, nodes, n1)).astype(np.int32)
+    node1[rng.rand(n1) < 0.02] = -1; node2[rng.rand(n2) < 0.02] = -1
+    return node1, node2
+
+
+@pytest.mark.parametrize("seed,nodes,ori,n2,n1", [(21, 40, True, 500, 450), (22, 8, True, 500, 450), (23, 200, False, 500, 450),
+                                                  (24, 60, True, 2000, 1800)])
+def test_bow_search_keyframe_to_frame_through_the_reference_class(dropin, reference, seed, nodes, ori, n2, n1):
+    """ORBmatcher(0.7, true).SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:247-420, Tracking::TrackReferenceKeyFrame)
+    on a live ORB_SLAM2::KeyFrame with live MapPoints: drop-in body (orb_search_by_bow_host) against the reference's CPU body."""
+    from orb_slam2_detailed_comments_b200.synth import tracking_scene
+    from test_oracle_search import SF
+    gref = dropin.reference_api()
+    sc = tracking_scene(n2, n1, seed, flip_bits=40)
+    node1, node2 = _bow_nodes(sc, seed, n1, n2, nodes)
+    args = (sc["last"], sc["mp_desc"], node1, sc["mp_flags"] & 1, sc["cur"], sc["cur_desc"], node2, 0.7, ori, SF)
+    rn, rmk = reference.search_by_bow_frame(*args)
+    gn, gmk = gref.search_by_bow_frame(*args)
+    assert gn == rn > 20
+    assert np.array_equal(gmk, rmk), "vpMapPointMatches differs in %d entries" % int((gmk != rmk).sum())
+
+
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_bow_search_keyframe_pair_through_the_reference_class(dropin, reference, seed):
+    """ORBmatcher(0.8, true).SearchByBoW(pKF1, pKF2, vpMatches12) (src/ORBmatcher.cc:729-880, LoopClosing::ComputeSim3)."""
+    from orb_slam2_detailed_comments_b200.synth import tracking_scene
+    from test_oracle_search import SF
+    gref = dropin.reference_api()
+    n2, n1 = (500, 450) if seed < 33 else (1800, 1700)
+    sc = tracking_scene(n2, n1, seed, flip_bits=60)
+    rng = np.random.RandomState(seed)
+    node2 = rng.randint(0, 30, n2).astype(np.int32)
+    node1 = np.where(rng.rand(n1) < 0.85, node2[sc["src"]], rng.randint(0, 30, n1)).astype(np.int32)
+    usable2 = (rng.rand(n2) < 0.7).astype(np.uint8)
+    args = (sc["last"], sc["mp_desc"], node1, sc["mp_flags"] & 1, sc["cur"], sc["cur_desc"], node2, usable2, 0.8, True, SF)
+    rn, rm12 = reference.search_by_bow_keyframes(*args)
+    gn, gm12 = gref.search_by_bow_keyframes(*args)
+    assert gn == rn > 20
+    assert np.array_equal(gm12, rm12), "vpMatches12 differs in %d entries" % int((gm12 != rm12).sum())
+
+
+@pytest.mark.parametrize("seed,only_stereo,mono,n2,n1", [(41, 0, False, 500, 450), (42, 1, False, 500, 450), (43, 0, True, 500, 450),
+                                                         (44, 0, False, 2000, 1900)])
+def test_triangulation_search_through_the_reference_class(dropin, reference, seed, only_stereo, mono, n2, n1):
+    """ORBmatcher(0.6, true).SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (src/ORBmatcher.cc:884-1100,
+    LocalMapping::CreateNewMapPoints): the epipole from the live keyframes' poses, CheckDistEpipolarLine on the GPU."""
+    from orb_slam2_detailed_comments_b200.synth import tracking_scene, triangulation_pair
+    from test_oracle_search import SF
+    gref = dropin.reference_api()
+    sc = tracking_scene(n2, n1, seed, flip_bits=50, noise_px=1.0)
+    tp = triangulation_pair(sc, seed)
+    rng = np.random.RandomState(seed)
+    node2 = rng.randint(0, 25, n2).astype(np.int32)
+    node1 = np.where(rng.rand(n1) < 0.85, node2[sc["src"]], rng.randint(0, 25, n1)).astype(np.int32)
+    ur1 = None if mono else tp["ur1"]; ur2 = None if mono else sc["uright"]
+    sigma2 = (SF * SF).astype(np.float32)
+    args = (tp["kps1"], sc["mp_desc"], node1, tp["has_mp1"], ur1, sc["cur"], sc["cur_desc"], node2, tp["has_mp2"], ur2, sc["Tcw"],
+            sc["cam4"], tp["F12"], only_stereo, True, SF, sigma2)
+    rn, rm12 = reference.search_for_triangulation(*args)
+    gn, gm12 = gref.search_for_triangulation(*args)
+    assert gn == rn > (5 if only_stereo else 15)
+    assert np.array_equal(gm12, rm12), "vMatchedPairs differs in %d entries" % int((gm12 != rm12).sum())
