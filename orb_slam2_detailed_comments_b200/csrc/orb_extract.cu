@@ -97,6 +97,27 @@ struct Geom {
 };
 
 __constant__ int c_umax[kHalfPatch + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+// The same disc as per-row byte weights for IC_Angle with dp4a (k_describe_tma): row v = r - 15 of the 31 x 31 patch, word q =
+// patch bytes 4q .. 4q+3; w[r][q] = 1 per byte inside the disc, w[r][8 + q] = (u + 15) per byte inside the disc. Row 31 is empty.
+struct DiscWeights { unsigned w[32][16]; };
+constexpr DiscWeights make_disc_weights() {
+  constexpr int umax[kHalfPatch + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+  DiscWeights t{};
+  for (int r = 0; r < 31; r++) {
+    const int v = r - kHalfPatch, d = umax[v < 0 ? -v : v];
+    for (int q = 0; q < 8; q++) {
+      unsigned ones = 0, wu = 0;
+      for (int j = 0; j < 4; j++) {
+        const int col = 4 * q + j;   // u + 15
+        if (col >= kHalfPatch - d && col <= kHalfPatch + d) { ones |= 1u << (8 * j); wu |= (unsigned)col << (8 * j); }
+      }
+      t.w[r][q] = ones;
+      t.w[r][8 + q] = wu;
+    }
+  }
+  return t;
+}
+__device__ const DiscWeights d_discWeights = make_disc_weights();
 
 // ------------------------------------------------------------------------------------------
 // Pyramid
@@ -1683,12 +1704,14 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
 struct DescMaps {
   CUtensorMap pyr[kMaxLevels];
   CUtensorMap blur[kMaxLevels];
+  CUtensorMap blur48[kMaxLevels];   // 48-byte wide boxes: enough when the patch starts <= 11 bytes into its 16-byte chunk
 };
 constexpr int kTmaMomW = 48, kTmaPatchW = 64;   // 31 / 37 px + up to 15 bytes of alignment slack
 constexpr int kTmaMomBytes = kTmaMomW * 31, kTmaPatchBytes = kTmaPatchW * 37;
 constexpr int kTmaBufBytes = 2432;   // 64 x 37 rounded up to a multiple of 128 (TMA destination alignment)
 constexpr int kDescTmaSmem = kDescSlots * kTmaBufBytes + 128;
 
+template <int V>   // A/B switches: bit 0 = disc weights from the constant table, bit 1 = magic-number rounding, bit 2 = 16-byte moment loads
 __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid_constant__ DescMaps maps,
                                                       const uint2* __restrict__ kept, const int* __restrict__ keptCount,
                                                       int keptTotal, const signed char* __restrict__ pattern,
@@ -1699,7 +1722,9 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
   __shared__ int s_prefix[kMaxLevels + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = blockIdx.y;
-  unsigned char* bufs = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(s_raw) + 127) & ~(size_t)127);
+  // aligned by an OFFSET, not by integer arithmetic on the pointer: the compiler keeps the shared state space (LDS with 32-bit
+  // addresses; the former round trip through size_t made every patch load a generic 64-bit LD)
+  unsigned char* bufs = s_raw + ((128u - (smem_u32(s_raw) & 127u)) & 127u);
   unsigned char* wbuf = bufs + wid * (kDescPerWarp * kTmaBufBytes);
   if (threadIdx.x == 0) {
     int total = 0;
@@ -1715,9 +1740,14 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
   }
   if (threadIdx.x < kDescSlots) mbar_init(&s_bar[threadIdx.x], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  // disc mask / (u+15) weights of this lane's patch row v = lane-15: 8 words of 4 bytes
+  // disc mask / (u+15) weights of this lane's patch row v = lane-15: 8 + 8 words of 4 bytes
   unsigned w1[8], wu[8];
-  {
+  if (V & 1) {
+    const uint4* t = reinterpret_cast<const uint4*>(d_discWeights.w[lane]);
+    const uint4 a0 = __ldg(t), a1 = __ldg(t + 1), b0 = __ldg(t + 2), b1 = __ldg(t + 3);
+    w1[0] = a0.x; w1[1] = a0.y; w1[2] = a0.z; w1[3] = a0.w; w1[4] = a1.x; w1[5] = a1.y; w1[6] = a1.z; w1[7] = a1.w;
+    wu[0] = b0.x; wu[1] = b0.y; wu[2] = b0.z; wu[3] = b0.w; wu[4] = b1.x; wu[5] = b1.y; wu[6] = b1.z; wu[7] = b1.w;
+  } else {
     const int v = lane - kHalfPatch;
     const int d = lane < 31 ? c_umax[v < 0 ? -v : v] : -1;
     // columns 15-d .. 15+d of the row as a 31-bit mask; a nibble of it becomes 4 bytes of 0 / 1 with one multiply
@@ -1765,17 +1795,40 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
     if (lvl[k] >= 0) {
       mbar_wait(&s_bar[wid * kDescPerWarp + k], par);
       const int mis = (px[k] - kHalfPatch) & 15;   // patch byte 0 sits `mis` bytes into the fetched row
-      const unsigned* row = reinterpret_cast<const unsigned*>(wbuf + k * kTmaBufBytes + (lane < 31 ? lane : 30) * kTmaMomW) + (mis >> 2);
+      const unsigned char* rowb = wbuf + k * kTmaBufBytes + (lane < 31 ? lane : 30) * kTmaMomW;
       const unsigned sh = (unsigned)(mis & 3) * 8;
       unsigned s1 = 0, s2 = 0;
-      unsigned prev = row[0];
+      if (V & 4) {
+        // the whole 48-byte row with three 16-byte loads (rows are 12 words apart: a quarter warp covers all 32 banks, no
+        // conflicts; one word per load was a 4-way conflict), then a warp-uniform shift by mis / 4 words
+        const uint4* r4 = reinterpret_cast<const uint4*>(rowb);
+        const uint4 A = r4[0], B = r4[1], C = r4[2];
+        unsigned W[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
+        if (mis & 8) {
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const unsigned nxt = row[q + 1];
-        const unsigned wv = __funnelshift_r(prev, nxt, sh);   // patch bytes 4q .. 4q+3 of this row
-        s1 = __dp4a(wv, w1[q], s1);
-        s2 = __dp4a(wv, wu[q], s2);
-        prev = nxt;
+          for (int j = 0; j < 10; j++) W[j] = W[j + 2];
+        }
+        if (mis & 4) {
+#pragma unroll
+          for (int j = 0; j < 9; j++) W[j] = W[j + 1];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const unsigned wv = __funnelshift_r(W[q], W[q + 1], sh);   // patch bytes 4q .. 4q+3 of this row
+          s1 = __dp4a(wv, w1[q], s1);
+          s2 = __dp4a(wv, wu[q], s2);
+        }
+      } else {
+        const unsigned* row = reinterpret_cast<const unsigned*>(rowb) + (mis >> 2);
+        unsigned prev = row[0];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const unsigned nxt = row[q + 1];
+          const unsigned wv = __funnelshift_r(prev, nxt, sh);   // patch bytes 4q .. 4q+3 of this row
+          s1 = __dp4a(wv, w1[q], s1);
+          s2 = __dp4a(wv, wu[q], s2);
+          prev = nxt;
+        }
       }
       int m10 = (int)s2 - kHalfPatch * (int)s1;               // sum u*I
       int m01 = (lane - kHalfPatch) * (int)s1;                // sum v*I
@@ -1836,11 +1889,20 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
       const int wd = words[bit];
       const float x0 = (float)(signed char)(wd & 0xff), y0 = (float)(signed char)((wd >> 8) & 0xff);
       const float x1 = (float)(signed char)((wd >> 16) & 0xff), y1 = (float)(signed char)((wd >> 24) & 0xff);
-      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-      const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-      const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-      const int t0 = cb[r0 * kTmaPatchW + c0], t1 = cb[r1 * kTmaPatchW + c1];
+      const float fr0 = __fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)), fc0 = __fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b));
+      const float fr1 = __fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)), fc1 = __fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b));
+      int t0, t1;
+      if (V & 2) {
+        // cvRound = round to nearest even = what adding 1.5 * 2^23 does to the mantissa (|v| < 2^22): the integer is the low
+        // bits of the sum. Keeps the conversions off the 16-lane XU pipe; the bias 65 * 0x4B400000 leaves with the base address.
+        constexpr float kMagic = 12582912.f;
+        constexpr unsigned kBias = 65u * 0x4B400000u;
+        const unsigned i0 = (unsigned)__float_as_int(__fadd_rn(fr0, kMagic)) * (unsigned)kTmaPatchW + (unsigned)__float_as_int(__fadd_rn(fc0, kMagic));
+        const unsigned i1 = (unsigned)__float_as_int(__fadd_rn(fr1, kMagic)) * (unsigned)kTmaPatchW + (unsigned)__float_as_int(__fadd_rn(fc1, kMagic));
+        t0 = cb[(int)(i0 - kBias)]; t1 = cb[(int)(i1 - kBias)];
+      } else {
+        t0 = cb[__float2int_rn(fr0) * kTmaPatchW + __float2int_rn(fc0)]; t1 = cb[__float2int_rn(fr1) * kTmaPatchW + __float2int_rn(fc1)];
+      }
       val |= (t0 < t1) << bit;
     }
     const size_t o = (size_t)f * cap + slotIdx;
@@ -1859,6 +1921,255 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
   }
   __syncwarp();
   }   // round
+}
+
+// ------------------------------------------------------------------------------------------
+// k_describe_ring: the arithmetic of k_describe_tma as a per-warp software pipeline. A warp owns KPW consecutive output
+// slots and no CTA-wide step exists. ncu on k_describe_tma (16 keypoints per CTA, two per warp) showed a chain of four
+// dependent memory latencies per CTA (level counts -> kept record -> moment patch -> blurred patch) that only other CTAs
+// could hide (58 % of the warp slots active), and lane-serial work done per keypoint: cos / sin in double precision on 2
+// of 32 lanes, fastAtan2 and the keypoint record on one. Here
+//   * lane j loads the record of the warp's keypoint j (one coalesced load) and finds its level from a warp scan of the
+//     level counts;
+//   * phase A streams the 48 x 31 moment patches through a ring of three buffers (TMA two keypoints ahead), lane j keeps
+//     (m01, m10) of keypoint j;
+//   * fastAtan2, cos / sin run once for all KPW keypoints, one per lane, while the first blurred patches are in flight;
+//   * phase C streams the 64 x 37 blurred patches through a ring of two buffers in the same memory (TMA one keypoint ahead);
+//   * lane j writes the keypoint record of keypoint j.
+// The moment rows are read with three 16-byte loads per lane (conflict free; one word per load was a 4-way bank conflict)
+// and the BRIEF coordinates are rounded by the magic-number addition instead of F2I (the 16-lane XU pipe was 67 % busy).
+// ------------------------------------------------------------------------------------------
+constexpr int kMomBufBytes = 1536;                 // 48 x 31 rounded up to a multiple of 128
+// per warp: DEPTH blurred patches or DEPTH + 1 moment patches in the same memory
+constexpr int desc_ring_smem(int depth) { return 8 * depth * kTmaBufBytes + 128; }
+
+template <int KPW, int MINB, int DEPTH>
+__global__ void __launch_bounds__(256, MINB) k_describe_ring(const Geom g, const __grid_constant__ DescMaps maps,
+                                                       const uint2* __restrict__ kept, const int* __restrict__ keptCount,
+                                                       int keptTotal, const signed char* __restrict__ pattern,
+                                                       orb_keypoint* __restrict__ outK, u8* __restrict__ outD,
+                                                       int* __restrict__ outN, int cap, int* __restrict__ overflow) {
+  static_assert(KPW >= 2 && KPW <= 32, "one lane per keypoint");
+  constexpr int kRingBytes = DEPTH * kTmaBufBytes, NA = DEPTH + 1;   // NA moment buffers / barriers
+  static_assert(NA * kMomBufBytes <= kRingBytes, "moment ring must fit in the blurred-patch ring");
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[8 * NA];
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = blockIdx.y;
+  unsigned char* ring = s_raw + ((128u - (smem_u32(s_raw) & 127u)) & 127u) + wid * kRingBytes;
+  unsigned long long* bar = s_bar + wid * NA;
+  const unsigned ringA = smem_u32(ring), barA = smem_u32(bar);   // shared-window addresses for the TMA / mbarrier instructions
+  // level prefix by a warp scan: lane q holds the number of kept keypoints on levels < q
+  const int cnt = lane < g.nlevels ? keptCount[f * g.nlevels + lane] : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < kMaxLevels; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int excl = incl - cnt;
+  const int totalAll = __shfl_sync(kFull, incl, kMaxLevels - 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    outN[f] = min(totalAll, cap);
+    if (totalAll > cap) atomicOr(overflow, 4);
+  }
+  const int base = (blockIdx.x * 8 + wid) * KPW;
+  const int n = min(KPW, min(totalAll, cap) - base);
+  if (n <= 0) return;   // the whole warp leaves; nothing below is CTA-wide
+  if (lane < NA) mbar_init(&bar[lane], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  // lane j: record of keypoint base + j (lanes >= n repeat the last one; they never write)
+  int myL = 0, myResp;
+  unsigned myRec;   // x | y << 14 | level << 28 (coordinates < 16384: the host launches k_describe_tma for larger images)
+  {
+    const int slot = base + min(lane, n - 1);
+#pragma unroll 1
+    for (int q = 1; q < g.nlevels; q++) myL += slot >= __shfl_sync(kFull, excl, q);
+    const int first = __shfl_sync(kFull, excl, myL);
+    const uint2 rec = kept[(size_t)f * keptTotal + g.lv[myL].keptOff + (slot - first)];
+    myRec = (rec.x & 0x3fffu) | ((rec.x >> 16) << 14) | ((unsigned)myL << 28);
+    myResp = (int)rec.y;
+  }
+  auto fetch_moment = [&](int j, int slot) {
+    const unsigned rec = __shfl_sync(kFull, myRec, j);
+    if (lane == 0) {
+      const int x = (int)(rec & 0x3fffu), y = (int)((rec >> 14) & 0x3fffu);
+      const unsigned b = barA + 8u * slot;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(kTmaMomBytes) : "memory");
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                   ::"r"(ringA + slot * kMomBufBytes), "l"(&maps.pyr[rec >> 28]), "r"(kLeftPad + ((x - kHalfPatch) & ~15)),
+                     "r"(kEdge + y - kHalfPatch), "r"(f), "r"(b) : "memory");
+    }
+  };
+  // the blurred patch: columns x-18 .. x+18 from the 16-byte chunk at or left of x-18; a 48-byte box holds them when the
+  // patch starts <= 11 bytes into the chunk (3 of 4 keypoints: fewer L2 sectors, and rows 12 words apart spread the BRIEF
+  // samples over all banks where 16 words fold them onto two sets of 16)
+  auto fetch_blurred = [&](int j, int slot) {
+    const unsigned rec = __shfl_sync(kFull, myRec, j);
+    if (lane == 0) {
+      const int x = (int)(rec & 0x3fffu), y = (int)((rec >> 14) & 0x3fffu);
+      const bool narrow = ((x - 18) & 15) <= 11;
+      const unsigned b = barA + 8u * slot;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((narrow ? 48 : kTmaPatchW) * 37) : "memory");
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                   ::"r"(ringA + slot * kTmaBufBytes), "l"(narrow ? &maps.blur48[rec >> 28] : &maps.blur[rec >> 28]), "r"((x - 18) & ~15),
+                     "r"(y - 18), "r"(f), "r"(b) : "memory");
+    }
+  };
+  auto wait_bar = [&](int slot, unsigned par) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(barA + 8u * slot), "r"(par) : "memory");
+  };
+#pragma unroll
+  for (int j = 0; j < DEPTH; j++)
+    if (j < n) fetch_moment(j, j);
+  unsigned parity = 0;   // bit b: the phase bar[b] completes next
+  // ---- phase A: intensity-centroid moments of every keypoint
+  int myM10 = 0, myM01 = 0;
+  {
+    // disc mask / (u + 15) weights of this lane's patch row v = lane - 15: 8 + 8 words of 4 bytes (computed, not loaded: the
+    // first patches are in flight meanwhile, and a table read from global memory measured slower)
+    unsigned w1[8], wu[8];
+    {
+      const int v = lane - kHalfPatch;
+      const int d = lane < 31 ? c_umax[v < 0 ? -v : v] : -1;
+      const unsigned rowMask = d < 0 ? 0u : ((2u << (2 * d)) - 1u) << (kHalfPatch - d);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const unsigned ones = (((rowMask >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u;
+        w1[k] = ones;
+        wu[k] = (ones * 0xffu) & (0x03020100u + 0x04040404u * (unsigned)k);
+      }
+    }
+    int rs = 0;   // ring slot of keypoint j = j % NA
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+      if (j + DEPTH < n) fetch_moment(j + DEPTH, rs == 0 ? NA - 1 : rs - 1);   // the slot keypoint j - 1 was read from, one __syncwarp ago
+      wait_bar(rs, (parity >> rs) & 1u);
+      parity ^= 1u << rs;
+      const int mis = ((int)(__shfl_sync(kFull, myRec, j) & 0x3fffu) - kHalfPatch) & 15;   // patch byte 0 sits `mis` bytes into the fetched row
+      const uint4* r4 = reinterpret_cast<const uint4*>(ring + rs * kMomBufBytes + (lane < 31 ? lane : 30) * kTmaMomW);
+      const uint4 A = r4[0], B = r4[1], C = r4[2];
+      unsigned W[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
+      if (mis & 8) {
+#pragma unroll
+        for (int q = 0; q < 10; q++) W[q] = W[q + 2];
+      }
+      if (mis & 4) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) W[q] = W[q + 1];
+      }
+      const unsigned sh = (unsigned)(mis & 3) * 8;
+      unsigned s1 = 0, s2 = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const unsigned wv = __funnelshift_r(W[q], W[q + 1], sh);   // patch bytes 4q .. 4q+3 of this row
+        s1 = __dp4a(wv, w1[q], s1);
+        s2 = __dp4a(wv, wu[q], s2);
+      }
+      // sum u*I, sum v*I over the rows: one REDUX each
+      const int m10 = __reduce_add_sync(kFull, (int)s2 - kHalfPatch * (int)s1);
+      const int m01 = __reduce_add_sync(kFull, (lane - kHalfPatch) * (int)s1);
+      if (lane == j) { myM10 = m10; myM01 = m01; }
+      __syncwarp();
+      rs = rs == NA - 1 ? 0 : rs + 1;
+    }
+  }
+  // ---- the ring is free (every moment row was read before the last __syncwarp): start on the blurred patches
+#pragma unroll
+  for (int j = 0; j < DEPTH; j++)
+    if (j < n) fetch_blurred(j, j);
+  // ---- phase B, one keypoint per lane: fastAtan2; cos / sin in double precision, rounded to float (glibc's cosf / sinf)
+  const float myAngle = fast_atan2_deg((float)myM01, (float)myM10);
+  float myCos, mySin;
+  {
+    const float ang = __fmul_rn(myAngle, (float)(3.14159265358979323846 / 180.f));
+    double sn, cs;
+    sincos((double)ang, &sn, &cs);
+    myCos = (float)cs;
+    mySin = (float)sn;
+  }
+  // ---- phase C: steered BRIEF on the blurred patch; lane i produces descriptor byte i
+  {
+    const int4* pp = reinterpret_cast<const int4*>(pattern) + lane * 2;
+    const int4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+    const int words[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    int bs = 0;
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+      wait_bar(bs, (parity >> bs) & 1u);
+      parity ^= 1u << bs;
+      const float a = __shfl_sync(kFull, myCos, j), b = __shfl_sync(kFull, mySin, j);
+      const int m = ((int)(__shfl_sync(kFull, myRec, j) & 0x3fffu) - 18) & 15;
+      const unsigned pitch = m <= 11 ? 48u : (unsigned)kTmaPatchW;
+      // cvRound = round to nearest even = what adding 1.5 * 2^23 does to the mantissa (|v| < 2^22): the integer is in the low
+      // bits of the sum; the bias (pitch + 1) * 0x4B400000 of (row * pitch + column) leaves with the base address
+      constexpr float kMagic = 12582912.f;
+      // (a warp-wide reduction hands the compiler a value it knows to be uniform: the base goes into a uniform register and
+      // the loads address [index + base] without an add each)
+      const unsigned ubase = __reduce_max_sync(kFull, (unsigned)(bs * kTmaBufBytes + 18 + m) + 18u * pitch - (pitch + 1u) * 0x4B400000u);
+      const u8* cb = ring + (int)ubase;
+      int val = 0;
+#pragma unroll
+      for (int bit = 0; bit < 8; bit++) {
+        const int wd = words[bit];
+        const float x0 = (float)(signed char)(wd & 0xff), y0 = (float)(signed char)((wd >> 8) & 0xff);
+        const float x1 = (float)(signed char)((wd >> 16) & 0xff), y1 = (float)(signed char)((wd >> 24) & 0xff);
+        const float fr0 = __fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)), fc0 = __fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b));
+        const float fr1 = __fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)), fc1 = __fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b));
+        const unsigned i0 = (unsigned)__float_as_int(__fadd_rn(fr0, kMagic)) * pitch + (unsigned)__float_as_int(__fadd_rn(fc0, kMagic));
+        const unsigned i1 = (unsigned)__float_as_int(__fadd_rn(fr1, kMagic)) * pitch + (unsigned)__float_as_int(__fadd_rn(fc1, kMagic));
+        const int t0 = cb[(int)i0], t1 = cb[(int)i1];
+        val |= (t0 < t1) << bit;
+      }
+      outD[((size_t)f * cap + base + j) * 32 + lane] = (u8)val;
+      __syncwarp();   // every lane has read its samples: the buffer may be refilled
+      if (j + DEPTH < n) fetch_blurred(j + DEPTH, bs);
+      bs = bs == DEPTH - 1 ? 0 : bs + 1;
+    }
+  }
+  if (lane < n) {
+    const LevelGeom& L = g.lv[myL];
+    orb_keypoint kp;
+    const int myX = (int)(myRec & 0x3fffu), myY = (int)((myRec >> 14) & 0x3fffu);
+    kp.x = myL ? __fmul_rn((float)myX, L.scale) : (float)myX;
+    kp.y = myL ? __fmul_rn((float)myY, L.scale) : (float)myY;
+    kp.size = L.patch;
+    kp.angle = myAngle;
+    kp.response = (float)myResp;
+    kp.octave = myL;
+    kp.class_id = -1;
+    outK[(size_t)f * cap + base + lane] = kp;
+  }
+}
+
+typedef void (*DescribeTmaFn)(const Geom, const DescMaps, const uint2*, const int*, int, const signed char*, orb_keypoint*, u8*, int*, int, int*);
+static DescribeTmaFn describe_ring_variant(int kpw, int minb, int depth) {
+  if (depth == 3) return kpw == 4 ? k_describe_ring<4, 3, 3> : (kpw == 8 ? k_describe_ring<8, 3, 3> : k_describe_ring<16, 3, 3>);
+  if (kpw == 4) return minb == 3 ? k_describe_ring<4, 3, 2> : k_describe_ring<4, 4, 2>;
+  if (kpw == 8) return minb == 3 ? k_describe_ring<8, 3, 2> : k_describe_ring<8, 4, 2>;
+  return minb == 3 ? k_describe_ring<16, 3, 2> : k_describe_ring<16, 4, 2>;
+}
+static DescribeTmaFn describe_tma_variant(int v) {
+  switch (v & 7) {
+    case 0: return k_describe_tma<0>;
+    case 1: return k_describe_tma<1>;
+    case 2: return k_describe_tma<2>;
+    case 3: return k_describe_tma<3>;
+    case 4: return k_describe_tma<4>;
+    case 5: return k_describe_tma<5>;
+    case 6: return k_describe_tma<6>;
+    default: return k_describe_tma<7>;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2148,6 +2459,7 @@ struct orb_extractor {
   long long hostChunks = 0;      // chunks issued by the host batch entry points so far (staging buffer parity)
   bool asyncPending = false;     // orb_extract_batch_host_async work may still be in flight
   DescMaps descMaps[2];          // TMA tensor maps of the two workspace lanes (k_describe_tma)
+  int descVariant = 6, descRing = 8, descMinB = 3, descDepth = 2;
   PyrMaps blurMaps[2];           // ... and of the blur input tiles (k_blur7)
   bool blurTma = false;
   bool descTma = false;          // maps are valid for the current workspace
@@ -2583,10 +2895,25 @@ int build_desc_maps(orb_extractor* e) {
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
           return ORB_OK;
+        const cuuint32_t box48[3] = {48, 37, 1};
+        if (encode(&e->descMaps[lane].blur48[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box48, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return ORB_OK;
       }
     }
   }
-  ORB_CUDA(raise_dynamic_smem(k_describe_tma, kDescTmaSmem));
+  e->descVariant = 6;
+  if (const char* ev = getenv("ORB_B200_DESC_VARIANT")) e->descVariant = atoi(ev) & 7;
+  e->descRing = 8;   // keypoints per warp of k_describe_ring; 0 = k_describe_tma
+  if (const char* ev = getenv("ORB_B200_DESC_RING")) e->descRing = atoi(ev);
+  if (e->descRing != 0 && e->descRing != 4 && e->descRing != 8 && e->descRing != 16) e->descRing = 8;
+  e->descMinB = 3;
+  if (const char* ev = getenv("ORB_B200_DESC_MINB")) e->descMinB = std::max(3, std::min(4, atoi(ev)));
+  e->descDepth = 2;
+  if (const char* ev = getenv("ORB_B200_DESC_DEPTH")) e->descDepth = atoi(ev) == 3 ? 3 : 2;
+  ORB_CUDA(raise_dynamic_smem(describe_ring_variant(e->descRing ? e->descRing : 8, e->descMinB, e->descDepth), desc_ring_smem(e->descDepth)));
+  ORB_CUDA(raise_dynamic_smem(describe_tma_variant(e->descVariant), kDescTmaSmem));
   e->descTma = true;
   // blur input tiles: (kBlurTW + 32) x (kBlurTH + 6) bytes of the bordered plane
   bool blurOk = true;
@@ -2780,8 +3107,13 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   launches++;
   if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);
-  if (e->descTma)
-    k_describe_tma<<<dim3((slots + kDescSlots * kDescRounds - 1) / (kDescSlots * kDescRounds), B), 256, kDescTmaSmem, s>>>(g, e->descMaps[lane], W.kept, W.keptCount,
+  if (e->descTma && e->descRing && g.lv[0].w < 16384 && g.lv[0].h < 16384) {
+    const int per = 8 * e->descRing;
+    auto kfn = describe_ring_variant(e->descRing, e->descMinB, e->descDepth);
+    kfn<<<dim3((slots + per - 1) / per, B), 256, desc_ring_smem(e->descDepth), s>>>(g, e->descMaps[lane], W.kept, W.keptCount, e->keptTotal, e->d_pattern, d_kps,
+                                                                     d_desc, d_counts, cap, e->d_overflow);
+  } else if (e->descTma)
+    describe_tma_variant(e->descVariant)<<<dim3((slots + kDescSlots * kDescRounds - 1) / (kDescSlots * kDescRounds), B), 256, kDescTmaSmem, s>>>(g, e->descMaps[lane], W.kept, W.keptCount,
                                                                                             e->keptTotal, e->d_pattern, d_kps, d_desc,
                                                                                             d_counts, cap, e->d_overflow);
   else
