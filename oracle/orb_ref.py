@@ -55,6 +55,14 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def last_call_us():
+    """Wall time (us) of the last call into the reference's class made by this module (the matcher / stereo member only,
+    measured inside ref_wrap.cpp around the member call)."""
+    f = lib().orbref_last_call_us
+    f.restype = C.c_double
+    return float(f())
+
+
 class ReferenceExtractor:
     """ORB_SLAM2::ORBextractor of the reference itself (include/ORBextractor.h:93)."""
 

@@ -6,6 +6,7 @@
 // oracle/_ref/liborbref.so by `make -C oracle ref`; used by tests/test_oracle_vs_ref*.py, the GPU tests
 // named *_the_reference_itself, tools/ref_stress*.py and bench.py's CPU arm. Never loaded by the product.
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -33,6 +34,16 @@
 #include "Map.h"
 #include "MapPoint.h"
 #include "ORBmatcher.h"
+
+// Wall time of the last call into the reference's class (the matcher / stereo member only, not the construction of the
+// live objects around it): the same wrapper is linked into liborbref.so (CPU bodies) and liborbref_gpu.so (drop-in bodies),
+// so tools/gpu_dropin_latency.py reads both sides of the comparison from one clock.
+static double g_lastCallUs = 0.0;
+struct CallTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~CallTimer() { g_lastCallUs = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); }
+};
+extern "C" double orbref_last_call_us() { return g_lastCallUs; }
 #undef private
 #undef protected
 
@@ -53,10 +64,12 @@ struct Arena {
 };
 const int kMaxArenas = 256;
 std::atomic<char*> g_arena_base[kMaxArenas];
+std::atomic<int> g_arena_hi{0};   // slots >= g_arena_hi were never used: operator delete only scans the used ones
 thread_local Arena* tl_arena = nullptr;
 
 inline bool in_arena(void* p) {
-  for (int i = 0; i < kMaxArenas; i++) {
+  const int hi = g_arena_hi.load(std::memory_order_acquire);
+  for (int i = 0; i < hi; i++) {
     char* b = g_arena_base[i].load(std::memory_order_relaxed);
     if (b && (char*)p >= b && (char*)p < b + kArenaBytes) return true;
   }
@@ -102,7 +115,12 @@ struct ArenaOwner {  // first member of Ref: constructed first, destroyed last
     a.base = (char*)m;
     for (int i = 0; i < kMaxArenas; i++) {
       char* expect = nullptr;
-      if (g_arena_base[i].compare_exchange_strong(expect, a.base)) { slot = i; return; }
+      if (g_arena_base[i].compare_exchange_strong(expect, a.base)) {
+        slot = i;
+        int hi = g_arena_hi.load();
+        while (hi < i + 1 && !g_arena_hi.compare_exchange_weak(hi, i + 1)) {}
+        return;
+      }
     }
     abort();
   }
@@ -299,7 +317,8 @@ int orbref_search_for_initialization(void* h1, void* h2, float* prevMatchedXY /*
   for (int i = 0; i < a->f.N; i++) prev[i] = cv::Point2f(prevMatchedXY[2 * i], prevMatchedXY[2 * i + 1]);
   std::vector<int> m12;
   ORB_SLAM2::ORBmatcher matcher(nnratio, checkOri != 0);
-  int n = matcher.SearchForInitialization(a->f, b->f, prev, m12, windowSize);
+  int n;
+  { CallTimer t; n = matcher.SearchForInitialization(a->f, b->f, prev, m12, windowSize); }
   for (int i = 0; i < a->f.N; i++) {
     prevMatchedXY[2 * i] = prev[i].x; prevMatchedXY[2 * i + 1] = prev[i].y;
     matches12[i] = m12[i];
@@ -318,7 +337,7 @@ int orbref_stereo_matches(void* hL, void* hR, float mbf, float mb, float* uRight
   f.mDescriptors = L->desc.clone(); f.mDescriptorsRight = R->desc.clone();
   f.mvScaleFactors = L->ex.GetScaleFactors(); f.mvInvScaleFactors = L->ex.GetInverseScaleFactors();
   f.mbf = mbf; f.mb = mb;
-  f.ComputeStereoMatches();
+  { CallTimer t; f.ComputeStereoMatches(); }
   int kept = 0;
   for (int i = 0; i < f.N; i++) { uRight[i] = f.mvuRight[i]; depth[i] = f.mvDepth[i]; kept += f.mvDepth[i] > 0; }
   return kept;
@@ -411,7 +430,8 @@ int orbref_search_last_frame(void* hCur, const float* uright, const unsigned cha
     owned.push_back(mp);
   }
   ORB_SLAM2::ORBmatcher matcher(0.9f, true);
-  const int n = matcher.SearchByProjection(cur->f, last, th, false);
+  int n;
+  { CallTimer t; n = matcher.SearchByProjection(cur->f, last, th, false); }
   flatten(cur->f, last.mvpMapPoints, matchOfKp);
   for (ORB_SLAM2::MapPoint* p : owned) delete p;
   cur->f.mvpMapPoints.assign(cur->f.N, (ORB_SLAM2::MapPoint*)nullptr);
@@ -449,7 +469,8 @@ int orbref_search_local_map(void* hCur, const float* uright, const unsigned char
     owned.push_back(mp);
   }
   ORB_SLAM2::ORBmatcher matcher(nnratio, true);
-  const int n = matcher.SearchByProjection(cur->f, mps, th);
+  int n;
+  { CallTimer t; n = matcher.SearchByProjection(cur->f, mps, th); }
   flatten(cur->f, mps, matchOfKp);
   for (ORB_SLAM2::MapPoint* p : owned) delete p;
   cur->f.mvpMapPoints.assign(cur->f.N, (ORB_SLAM2::MapPoint*)nullptr);
@@ -529,7 +550,8 @@ int orbref_search_by_bow_frame(const void* kps1, int n1, const unsigned char* de
   b.build(kps2, n2, desc2, node2, nullptr, nullptr, nullptr, kIdentityCam, scaleFactors, s2.data(), nlevels, &map, false);
   std::vector<ORB_SLAM2::MapPoint*> matches;
   ORB_SLAM2::ORBmatcher matcher(nnratio, checkOri != 0);
-  const int n = matcher.SearchByBoW(a.kf, b.f, matches);
+  int n;
+  { CallTimer t; n = matcher.SearchByBoW(a.kf, b.f, matches); }
   for (int j = 0; j < n2; j++) matchOfKp[j] = a.index_of(matches[j]);
   return n;
 }
@@ -546,7 +568,8 @@ int orbref_search_by_bow_keyframes(const void* kps1, int n1, const unsigned char
   b.build(kps2, n2, desc2, node2, usable2, nullptr, nullptr, kIdentityCam, scaleFactors, s2.data(), nlevels, &map, true);
   std::vector<ORB_SLAM2::MapPoint*> matches;
   ORB_SLAM2::ORBmatcher matcher(nnratio, checkOri != 0);
-  const int n = matcher.SearchByBoW(a.kf, b.kf, matches);
+  int n;
+  { CallTimer t; n = matcher.SearchByBoW(a.kf, b.kf, matches); }
   for (int i = 0; i < n1; i++) matches12[i] = b.index_of(matches[i]);
   return n;
 }
@@ -566,7 +589,8 @@ int orbref_search_for_triangulation(const void* kps1, int n1, const unsigned cha
   memcpy(F.data, F12, 9 * sizeof(float));
   std::vector<std::pair<size_t, size_t>> pairs;
   ORB_SLAM2::ORBmatcher matcher(0.6f, checkOri != 0);
-  const int n = matcher.SearchForTriangulation(a.kf, b.kf, F, pairs, onlyStereo != 0);
+  int n;
+  { CallTimer t; n = matcher.SearchForTriangulation(a.kf, b.kf, F, pairs, onlyStereo != 0); }
   for (int i = 0; i < n1; i++) matches12[i] = -1;
   for (const auto& p : pairs) matches12[p.first] = (int)p.second;
   return n;

@@ -97,27 +97,6 @@ struct Geom {
 };
 
 __constant__ int c_umax[kHalfPatch + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-// The same disc as per-row byte weights for IC_Angle with dp4a (k_describe_tma): row v = r - 15 of the 31 x 31 patch, word q =
-// patch bytes 4q .. 4q+3; w[r][q] = 1 per byte inside the disc, w[r][8 + q] = (u + 15) per byte inside the disc. Row 31 is empty.
-struct DiscWeights { unsigned w[32][16]; };
-constexpr DiscWeights make_disc_weights() {
-  constexpr int umax[kHalfPatch + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-  DiscWeights t{};
-  for (int r = 0; r < 31; r++) {
-    const int v = r - kHalfPatch, d = umax[v < 0 ? -v : v];
-    for (int q = 0; q < 8; q++) {
-      unsigned ones = 0, wu = 0;
-      for (int j = 0; j < 4; j++) {
-        const int col = 4 * q + j;   // u + 15
-        if (col >= kHalfPatch - d && col <= kHalfPatch + d) { ones |= 1u << (8 * j); wu |= (unsigned)col << (8 * j); }
-      }
-      t.w[r][q] = ones;
-      t.w[r][8 + q] = wu;
-    }
-  }
-  return t;
-}
-__device__ const DiscWeights d_discWeights = make_disc_weights();
 
 // ------------------------------------------------------------------------------------------
 // Pyramid
@@ -1711,7 +1690,6 @@ constexpr int kTmaMomBytes = kTmaMomW * 31, kTmaPatchBytes = kTmaPatchW * 37;
 constexpr int kTmaBufBytes = 2432;   // 64 x 37 rounded up to a multiple of 128 (TMA destination alignment)
 constexpr int kDescTmaSmem = kDescSlots * kTmaBufBytes + 128;
 
-template <int V>   // A/B switches: bit 0 = disc weights from the constant table, bit 1 = magic-number rounding, bit 2 = 16-byte moment loads
 __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid_constant__ DescMaps maps,
                                                       const uint2* __restrict__ kept, const int* __restrict__ keptCount,
                                                       int keptTotal, const signed char* __restrict__ pattern,
@@ -1740,14 +1718,10 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
   }
   if (threadIdx.x < kDescSlots) mbar_init(&s_bar[threadIdx.x], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  // disc mask / (u+15) weights of this lane's patch row v = lane-15: 8 + 8 words of 4 bytes
+  // disc mask / (u+15) weights of this lane's patch row v = lane-15: 8 + 8 words of 4 bytes (computed while the first patch is
+  // in flight; a constant table read from global memory measured slower: 3.16 vs 2.88 ms)
   unsigned w1[8], wu[8];
-  if (V & 1) {
-    const uint4* t = reinterpret_cast<const uint4*>(d_discWeights.w[lane]);
-    const uint4 a0 = __ldg(t), a1 = __ldg(t + 1), b0 = __ldg(t + 2), b1 = __ldg(t + 3);
-    w1[0] = a0.x; w1[1] = a0.y; w1[2] = a0.z; w1[3] = a0.w; w1[4] = a1.x; w1[5] = a1.y; w1[6] = a1.z; w1[7] = a1.w;
-    wu[0] = b0.x; wu[1] = b0.y; wu[2] = b0.z; wu[3] = b0.w; wu[4] = b1.x; wu[5] = b1.y; wu[6] = b1.z; wu[7] = b1.w;
-  } else {
+  {
     const int v = lane - kHalfPatch;
     const int d = lane < 31 ? c_umax[v < 0 ? -v : v] : -1;
     // columns 15-d .. 15+d of the row as a 31-bit mask; a nibble of it becomes 4 bytes of 0 / 1 with one multiply
@@ -1798,7 +1772,7 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
       const unsigned char* rowb = wbuf + k * kTmaBufBytes + (lane < 31 ? lane : 30) * kTmaMomW;
       const unsigned sh = (unsigned)(mis & 3) * 8;
       unsigned s1 = 0, s2 = 0;
-      if (V & 4) {
+      {
         // the whole 48-byte row with three 16-byte loads (rows are 12 words apart: a quarter warp covers all 32 banks, no
         // conflicts; one word per load was a 4-way conflict), then a warp-uniform shift by mis / 4 words
         const uint4* r4 = reinterpret_cast<const uint4*>(rowb);
@@ -1817,17 +1791,6 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
           const unsigned wv = __funnelshift_r(W[q], W[q + 1], sh);   // patch bytes 4q .. 4q+3 of this row
           s1 = __dp4a(wv, w1[q], s1);
           s2 = __dp4a(wv, wu[q], s2);
-        }
-      } else {
-        const unsigned* row = reinterpret_cast<const unsigned*>(rowb) + (mis >> 2);
-        unsigned prev = row[0];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const unsigned nxt = row[q + 1];
-          const unsigned wv = __funnelshift_r(prev, nxt, sh);   // patch bytes 4q .. 4q+3 of this row
-          s1 = __dp4a(wv, w1[q], s1);
-          s2 = __dp4a(wv, wu[q], s2);
-          prev = nxt;
         }
       }
       int m10 = (int)s2 - kHalfPatch * (int)s1;               // sum u*I
@@ -1892,7 +1855,7 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
       const float fr0 = __fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)), fc0 = __fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b));
       const float fr1 = __fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)), fc1 = __fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b));
       int t0, t1;
-      if (V & 2) {
+      {
         // cvRound = round to nearest even = what adding 1.5 * 2^23 does to the mantissa (|v| < 2^22): the integer is the low
         // bits of the sum. Keeps the conversions off the 16-lane XU pipe; the bias 65 * 0x4B400000 leaves with the base address.
         constexpr float kMagic = 12582912.f;
@@ -1900,8 +1863,6 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
         const unsigned i0 = (unsigned)__float_as_int(__fadd_rn(fr0, kMagic)) * (unsigned)kTmaPatchW + (unsigned)__float_as_int(__fadd_rn(fc0, kMagic));
         const unsigned i1 = (unsigned)__float_as_int(__fadd_rn(fr1, kMagic)) * (unsigned)kTmaPatchW + (unsigned)__float_as_int(__fadd_rn(fc1, kMagic));
         t0 = cb[(int)(i0 - kBias)]; t1 = cb[(int)(i1 - kBias)];
-      } else {
-        t0 = cb[__float2int_rn(fr0) * kTmaPatchW + __float2int_rn(fc0)]; t1 = cb[__float2int_rn(fr1) * kTmaPatchW + __float2int_rn(fc1)];
       }
       val |= (t0 < t1) << bit;
     }
@@ -2153,23 +2114,11 @@ __global__ void __launch_bounds__(256, MINB) k_describe_ring(const Geom g, const
 }
 
 typedef void (*DescribeTmaFn)(const Geom, const DescMaps, const uint2*, const int*, int, const signed char*, orb_keypoint*, u8*, int*, int, int*);
-static DescribeTmaFn describe_ring_variant(int kpw, int minb, int depth) {
-  if (depth == 3) return kpw == 4 ? k_describe_ring<4, 3, 3> : (kpw == 8 ? k_describe_ring<8, 3, 3> : k_describe_ring<16, 3, 3>);
-  if (kpw == 4) return minb == 3 ? k_describe_ring<4, 3, 2> : k_describe_ring<4, 4, 2>;
-  if (kpw == 8) return minb == 3 ? k_describe_ring<8, 3, 2> : k_describe_ring<8, 4, 2>;
-  return minb == 3 ? k_describe_ring<16, 3, 2> : k_describe_ring<16, 4, 2>;
-}
-static DescribeTmaFn describe_tma_variant(int v) {
-  switch (v & 7) {
-    case 0: return k_describe_tma<0>;
-    case 1: return k_describe_tma<1>;
-    case 2: return k_describe_tma<2>;
-    case 3: return k_describe_tma<3>;
-    case 4: return k_describe_tma<4>;
-    case 5: return k_describe_tma<5>;
-    case 6: return k_describe_tma<6>;
-    default: return k_describe_tma<7>;
-  }
+// Measured (KITTI, 2048 frames): 8 keypoints per warp 2.33 ms, 4: 2.76, 16: 2.47; a ring one buffer deeper: 2.76; a register
+// budget for 4 CTAs per SM (64 registers, 4 bytes spilled): 4.0 ms.
+constexpr int kDescRingDepth = 2;
+static DescribeTmaFn describe_ring_variant(int kpw) {
+  return kpw == 4 ? k_describe_ring<4, 3, kDescRingDepth> : (kpw == 16 ? k_describe_ring<16, 3, kDescRingDepth> : k_describe_ring<8, 3, kDescRingDepth>);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2459,7 +2408,7 @@ struct orb_extractor {
   long long hostChunks = 0;      // chunks issued by the host batch entry points so far (staging buffer parity)
   bool asyncPending = false;     // orb_extract_batch_host_async work may still be in flight
   DescMaps descMaps[2];          // TMA tensor maps of the two workspace lanes (k_describe_tma)
-  int descVariant = 6, descRing = 8, descMinB = 3, descDepth = 2;
+  int descRing = 8;   // keypoints per warp of k_describe_ring (4, 8, 16); 0 = k_describe_tma
   PyrMaps blurMaps[2];           // ... and of the blur input tiles (k_blur7)
   bool blurTma = false;
   bool descTma = false;          // maps are valid for the current workspace
@@ -2903,17 +2852,11 @@ int build_desc_maps(orb_extractor* e) {
       }
     }
   }
-  e->descVariant = 6;
-  if (const char* ev = getenv("ORB_B200_DESC_VARIANT")) e->descVariant = atoi(ev) & 7;
   e->descRing = 8;   // keypoints per warp of k_describe_ring; 0 = k_describe_tma
   if (const char* ev = getenv("ORB_B200_DESC_RING")) e->descRing = atoi(ev);
   if (e->descRing != 0 && e->descRing != 4 && e->descRing != 8 && e->descRing != 16) e->descRing = 8;
-  e->descMinB = 3;
-  if (const char* ev = getenv("ORB_B200_DESC_MINB")) e->descMinB = std::max(3, std::min(4, atoi(ev)));
-  e->descDepth = 2;
-  if (const char* ev = getenv("ORB_B200_DESC_DEPTH")) e->descDepth = atoi(ev) == 3 ? 3 : 2;
-  ORB_CUDA(raise_dynamic_smem(describe_ring_variant(e->descRing ? e->descRing : 8, e->descMinB, e->descDepth), desc_ring_smem(e->descDepth)));
-  ORB_CUDA(raise_dynamic_smem(describe_tma_variant(e->descVariant), kDescTmaSmem));
+  ORB_CUDA(raise_dynamic_smem(describe_ring_variant(e->descRing ? e->descRing : 8), desc_ring_smem(kDescRingDepth)));
+  ORB_CUDA(raise_dynamic_smem(k_describe_tma, kDescTmaSmem));
   e->descTma = true;
   // blur input tiles: (kBlurTW + 32) x (kBlurTH + 6) bytes of the bordered plane
   bool blurOk = true;
@@ -3109,11 +3052,11 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   const int slots = std::min(cap, e->maxKp);
   if (e->descTma && e->descRing && g.lv[0].w < 16384 && g.lv[0].h < 16384) {
     const int per = 8 * e->descRing;
-    auto kfn = describe_ring_variant(e->descRing, e->descMinB, e->descDepth);
-    kfn<<<dim3((slots + per - 1) / per, B), 256, desc_ring_smem(e->descDepth), s>>>(g, e->descMaps[lane], W.kept, W.keptCount, e->keptTotal, e->d_pattern, d_kps,
+    auto kfn = describe_ring_variant(e->descRing);
+    kfn<<<dim3((slots + per - 1) / per, B), 256, desc_ring_smem(kDescRingDepth), s>>>(g, e->descMaps[lane], W.kept, W.keptCount, e->keptTotal, e->d_pattern, d_kps,
                                                                      d_desc, d_counts, cap, e->d_overflow);
   } else if (e->descTma)
-    describe_tma_variant(e->descVariant)<<<dim3((slots + kDescSlots * kDescRounds - 1) / (kDescSlots * kDescRounds), B), 256, kDescTmaSmem, s>>>(g, e->descMaps[lane], W.kept, W.keptCount,
+    k_describe_tma<<<dim3((slots + kDescSlots * kDescRounds - 1) / (kDescSlots * kDescRounds), B), 256, kDescTmaSmem, s>>>(g, e->descMaps[lane], W.kept, W.keptCount,
                                                                                             e->keptTotal, e->d_pattern, d_kps, d_desc,
                                                                                             d_counts, cap, e->d_overflow);
   else

@@ -258,6 +258,237 @@ __global__ void __launch_bounds__(kMatchThreads) k_match_pairs(const PairArgs A)
 }
 
 // ------------------------------------------------------------------------------------------
+// Windowed SearchForInitialization, latency form (one pair per call: Tracking::MonocularInitialization, Tracking.cc:915-926).
+// k_match_pairs walks the rows of frame 1 inside ONE CTA with a block reduction per row: 0.65 us per row, 1.3 ms for 2000
+// keypoints - no faster than the reference's own loop on a host core. The distances are not sequential, only
+// vMatchedDistance (:627) and the steal (:650-654) are. So:
+//   k_sfi_scan  every active row (octave 0, :599) gets a warp somewhere on the machine: all frame-2 keypoints are tested
+//               against the window exactly as GetFeaturesInArea does (cell range, octave 0, circle), and the candidates
+//               with distance <= dmax are stored sorted, up to kSfiK per row. dmax is the largest distance that can still
+//               change a decision: a best above TH_LOW is rejected anyway, and a second best with
+//               (dmax + 1) * nnratio > TH_LOW accepts every best <= TH_LOW (:644-647), exactly as "no second" does.
+//   k_sfi_walk  one warp per pair walks the rows in order over the stored lists (shared memory): a candidate is skipped
+//               iff vMatchedDistance[i2] <= its distance, the first two that are not give best and second. A row whose
+//               list overflowed and ran out is re-scored exactly by the warp. Then the rotation histogram and the
+//               outputs, as in k_match_pairs.
+// The per-row best / second distances (a test aid of this library, not part of the reference's interface) need the exact
+// second best: callers that ask for them get k_match_pairs.
+// ------------------------------------------------------------------------------------------
+constexpr int kSfiK = 8;               // stored candidates per row
+constexpr int kSfiRowsPerWarp = 2;
+constexpr int kSfiChunk = 1024;        // rows staged per step of the walk
+
+struct SfiRow {   // GetFeaturesInArea window of row i1 (Frame.cc:603-634)
+  float qx, qy, r2;
+  int gx0, gx1, gy0, gy1;
+  bool active;
+};
+
+__device__ __forceinline__ SfiRow sfi_row(const PairArgs& A, int p, int i1) {
+  SfiRow R;
+  const int o1 = (A.oct1 + (size_t)p * A.stride1)[i1];
+  const float* pv = A.prev + (size_t)p * A.stride1 * 2;
+  R.qx = pv[2 * i1]; R.qy = pv[2 * i1 + 1];
+  const float r = (float)A.window;
+  R.r2 = __fmul_rn(r, r);
+  R.gx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(R.qx, A.minX), r), A.invW)));
+  R.gx1 = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(R.qx, A.minX), r), A.invW)));
+  R.gy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(R.qy, A.minY), r), A.invH)));
+  R.gy1 = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(R.qy, A.minY), r), A.invH)));
+  R.active = o1 <= 0 && R.gx0 < 64 && R.gx1 >= 0 && R.gy0 < 48 && R.gy1 >= 0;   // level1 > 0 -> continue (:599)
+  return R;
+}
+
+// candidate i2 of the row's window? (octave 0, Frame::PosInGrid Frame.cc:682-698, cell range, circle Frame.cc:664)
+__device__ __forceinline__ bool sfi_in_window(const PairArgs& A, int p, const SfiRow& R, int i2) {
+  if ((A.oct2 + (size_t)p * A.stride2)[i2] != 0) return false;
+  const float* xy2 = A.xy2 + (size_t)p * A.stride2 * 2;
+  const float x = xy2[2 * i2], y = xy2[2 * i2 + 1];
+  const int gx = (int)roundf(__fmul_rn(__fsub_rn(x, A.minX), A.invW));
+  const int gy = (int)roundf(__fmul_rn(__fsub_rn(y, A.minY), A.invH));
+  if (gx < 0 || gx >= 64 || gy < 0 || gy >= 48) return false;
+  if (gx < R.gx0 || gx > R.gx1 || gy < R.gy0 || gy > R.gy1) return false;
+  const float dx = __fsub_rn(x, R.qx), dy = __fsub_rn(y, R.qy);
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < R.r2;
+}
+
+__device__ __forceinline__ int sfi_distance(const unsigned a[8], const u8* D2, int i2) {
+  const uint4 lo = __ldg(reinterpret_cast<const uint4*>(D2 + (size_t)i2 * 32));
+  const uint4 hi = __ldg(reinterpret_cast<const uint4*>(D2 + (size_t)i2 * 32) + 1);
+  const unsigned b[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  return hamming8(a, b);
+}
+
+__global__ void __launch_bounds__(256) k_sfi_scan(const PairArgs A, unsigned* __restrict__ keys, int* __restrict__ cnt, int dmax) {
+  __shared__ unsigned s_list[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, p = blockIdx.y;
+  const unsigned lt = (1u << lane) - 1u;
+  const u8* D1 = A.desc1 + (size_t)p * A.stride1 * 32;
+  const u8* D2 = A.desc2 + (size_t)p * A.stride2 * 32;
+  for (int r = 0; r < kSfiRowsPerWarp; r++) {
+    const int i1 = (blockIdx.x * 8 + wid) * kSfiRowsPerWarp + r;
+    if (i1 >= A.n1) break;
+    const SfiRow R = sfi_row(A, p, i1);
+    int total = 0;
+    if (R.active) {
+      const uint4 lo = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32));
+      const uint4 hi = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32) + 1);
+      const unsigned a[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      for (int base = 0; base < A.n2; base += 32) {
+        const int i2 = base + lane;
+        bool ok = i2 < A.n2 && sfi_in_window(A, p, R, i2);
+        unsigned key = kNoKey;
+        if (ok) {
+          const int dist = sfi_distance(a, D2, i2);
+          ok = dist <= dmax;
+          key = ((unsigned)dist << 16) | (unsigned)i2;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const int pos = total + __popc(m & lt);
+          if (pos < 32) s_list[wid][pos] = key;
+        }
+        total += __popc(m);
+      }
+      __syncwarp();
+      // sort the (<= 32) stored keys by counting; keys are distinct (they hold the index)
+      const int have = min(total, 32);
+      const unsigned mine = lane < have ? s_list[wid][lane] : kNoKey;
+      int rank = 0;
+      for (int j = 0; j < have; j++) rank += s_list[wid][j] < mine;
+      if (lane < have && rank < kSfiK) keys[((size_t)p * A.n1 + i1) * kSfiK + rank] = mine;
+      __syncwarp();
+    }
+    // more than 32 candidates <= dmax: the stored ones are not the smallest - the walk re-scores the row (flag 0x200)
+    if (lane == 0) cnt[(size_t)p * A.n1 + i1] = total > 32 ? 0x200 : (min(total, kSfiK) | (total > kSfiK ? 0x100 : 0));
+  }
+}
+
+// dynamic smem: m12[n1] int, m21[n2] int, vmd[n2] u16 (4-byte padded), binOf[n1] u8 (4-byte padded), keys[kSfiChunk * kSfiK], cnt[kSfiChunk]
+__global__ void __launch_bounds__(256) k_sfi_walk(const PairArgs A, const unsigned* __restrict__ keys, const int* __restrict__ cnt,
+                                                   int dmax) {
+  extern __shared__ __align__(16) int wsm[];
+  __shared__ int s_hist[HISTO_LENGTH];
+  __shared__ int s_nmatch;
+  __shared__ int s_keep[3];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, p = blockIdx.x;
+  const int n1 = A.n1, n2 = A.n2;
+  int* m12 = wsm;
+  int* m21 = m12 + n1;
+  unsigned short* vmd = reinterpret_cast<unsigned short*>(m21 + n2);
+  u8* binOf = reinterpret_cast<u8*>(vmd + ((n2 + 1) & ~1));
+  unsigned* skeys = reinterpret_cast<unsigned*>(binOf + ((n1 + 3) & ~3));
+  int* scnt = reinterpret_cast<int*>(skeys + kSfiChunk * kSfiK);
+  const u8* D1 = A.desc1 + (size_t)p * A.stride1 * 32;
+  const u8* D2 = A.desc2 + (size_t)p * A.stride2 * 32;
+  const float* ang1 = A.ang1 + (size_t)p * A.stride1;
+  const float* ang2 = A.ang2 + (size_t)p * A.stride2;
+  for (int i = tid; i < n1; i += 256) { m12[i] = -1; binOf[i] = 255; }
+  for (int i = tid; i < n2; i += 256) { m21[i] = -1; vmd[i] = 0xffffu; }
+  if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+  const float factor = HISTO_LENGTH / 360.0f;
+  int nmatches = 0;   // warp 0
+  for (int c0 = 0; c0 < n1; c0 += kSfiChunk) {
+    const int rows = min(kSfiChunk, n1 - c0);
+    __syncthreads();
+    for (int i = tid; i < rows; i += 256) scnt[i] = cnt[(size_t)p * n1 + c0 + i];
+    for (int i = tid; i < rows * kSfiK; i += 256) skeys[i] = keys[((size_t)p * n1 + c0) * kSfiK + i];
+    __syncthreads();
+    if (wid != 0) continue;
+    for (int base = 0; base < rows; base += 32) {
+      const int c = base + lane < rows ? scnt[base + lane] : 0;
+      unsigned todo = __ballot_sync(0xffffffffu, c != 0);
+      while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int i1 = c0 + base + r;
+        const int ci = __shfl_sync(0xffffffffu, c, r);
+        const int nk = ci & 0xff;
+        unsigned key = lane < nk ? skeys[(base + r) * kSfiK + lane] : kNoKey;
+        bool free_ = key != kNoKey && (int)vmd[key & 0xffffu] > (int)(key >> 16);   // vMatchedDistance[i2] <= dist -> skip (:627)
+        unsigned m = __ballot_sync(0xffffffffu, free_);
+        unsigned kb = kNoKey, ks = kNoKey;
+        if ((ci & 0x300) && (__popc(m) < 2 || (ci & 0x200))) {
+          // the stored list ran out (or never held the smallest): exact top two of the row against the current state
+          const SfiRow R = sfi_row(A, p, i1);
+          const uint4 lo = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32));
+          const uint4 hi = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32) + 1);
+          const unsigned a[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          unsigned k1 = kNoKey, k2 = kNoKey;
+          for (int i2 = lane; i2 < n2; i2 += 32) {
+            if (!sfi_in_window(A, p, R, i2)) continue;
+            const int dist = sfi_distance(a, D2, i2);
+            if (dist > dmax || !((int)vmd[i2] > dist)) continue;
+            merge2(k1, k2, ((unsigned)dist << 16) | (unsigned)i2, kNoKey);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+            merge2(k1, k2, o1, o2);
+          }
+          kb = k1; ks = k2;
+        } else {
+          if (m) { kb = __shfl_sync(0xffffffffu, key, __ffs(m) - 1); m &= m - 1; }
+          if (m) ks = __shfl_sync(0xffffffffu, key, __ffs(m) - 1);
+        }
+        const int best = kb == kNoKey ? INT_MAX : (int)(kb >> 16);
+        const int second = ks == kNoKey ? INT_MAX : (int)(ks >> 16);
+        if (best <= TH_LOW && (float)best < __fmul_rn((float)second, A.nnratio)) {   // :644-647
+          const int bestIdx = (int)(kb & 0xffffu);
+          if (lane == 0) {
+            vmd[bestIdx] = (unsigned short)best;   // vMatchedDistance[bestIdx2] = bestDist
+            const int prevOwner = m21[bestIdx];
+            if (prevOwner >= 0) { m12[prevOwner] = -1; nmatches--; }   // :650-654
+            m12[i1] = bestIdx;
+            m21[bestIdx] = i1;
+            nmatches++;
+            if (A.checkOri) {
+              float rot = __fsub_rn(ang1[i1], ang2[bestIdx]);
+              if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+              int bin = (int)roundf(__fmul_rn(rot, factor));
+              if (bin == HISTO_LENGTH) bin = 0;
+              if (bin >= 0 && bin < HISTO_LENGTH) { binOf[i1] = (u8)bin; s_hist[bin]++; }
+            }
+          }
+          __syncwarp();   // the next row reads vmd
+        }
+      }
+    }
+  }
+  if (tid == 0) {
+    s_nmatch = nmatches;
+    int a = -1, b2 = -1, c = -1;
+    if (A.checkOri) three_maxima(s_hist, HISTO_LENGTH, a, b2, c);
+    s_keep[0] = a; s_keep[1] = b2; s_keep[2] = c;
+  }
+  __syncthreads();
+  if (A.checkOri) {
+    int dropped = 0;
+    for (int i = tid; i < n1; i += 256) {
+      const int bin = binOf[i];
+      if (bin != 255 && bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2] && m12[i] >= 0) {
+        m12[i] = -1;  // :692-706
+        dropped++;
+      }
+    }
+    if (dropped) atomicSub(&s_nmatch, dropped);
+  }
+  __syncthreads();
+  int* out12 = A.matches12 + (size_t)p * n1;
+  for (int i = tid; i < n1; i += 256) {
+    const int mm = m12[i];
+    out12[i] = mm;
+    if (mm >= 0) {  // :712-714
+      float* pv = A.prev + (size_t)p * A.stride1 * 2;
+      const float* xy2 = A.xy2 + (size_t)p * A.stride2 * 2;
+      pv[2 * i] = xy2[2 * mm];
+      pv[2 * i + 1] = xy2[2 * mm + 1];
+    }
+  }
+  if (tid == 0) A.nmatches[p] = s_nmatch;
+}
+
+// ------------------------------------------------------------------------------------------
 // Brute-force SearchForInitialization, throughput form. The reference's row walk is sequential only
 // through vMatchedDistance (:627) and the steal (:650-654); the distances themselves are not. So:
 //   phase 1  every thread owns RPT rows of frame 1 (descriptors + the two smallest keys in
@@ -658,7 +889,7 @@ int orb_matcher_create(int device, int max_pairs, int max_keypoints, orb_matcher
   m->maxKp = max_keypoints;
   const size_t K = (size_t)max_keypoints;
   cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
-  m->stageBytes = K * (2 * 32 + 2 * 4 + 8 + 2 * 4 + 8 + 3 * 4) + 16 * 16;
+  m->stageBytes = K * (2 * 32 + 2 * 4 + 8 + 2 * 4 + 8 + 3 * 4 + kSfiK * 4 + 4) + 18 * 16;
   if (e == cudaSuccess) e = cudaMalloc(&m->d_stage, m->stageBytes);
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&m->h_stage, m->stageBytes, cudaHostAllocDefault);
   if (e != cudaSuccess) {
@@ -710,7 +941,10 @@ int orb_search_for_initialization(orb_matcher* m, const orb_frame_view* f1, cons
   const size_t inEnd = off;
   const size_t oM12 = piece((size_t)n1 * 4), oBest = piece((size_t)n1 * 4), oSecond = piece((size_t)n1 * 4), oNm = piece(16);
   const size_t outBegin = windowed ? oPrev : oM12, outEnd = off;
-  if (outEnd > m->stageBytes) ORB_FAIL(ORB_ERR_INVALID, "keypoint count exceeds matcher capacity");
+  // device-only scratch of the latency form (k_sfi_scan / k_sfi_walk): candidate lists of the rows
+  const bool latencyForm = windowed && !best && !second && n2 <= 65535;
+  const size_t oKeys = piece(latencyForm ? (size_t)n1 * kSfiK * 4 : 0), oCnt = piece(latencyForm ? (size_t)n1 * 4 : 0);
+  if (off > m->stageBytes) ORB_FAIL(ORB_ERR_INVALID, "keypoint count exceeds matcher capacity");
   u8* H = m->h_stage; u8* D = m->d_stage;
   memcpy(H + oD1, f1->descriptors, (size_t)n1 * 32); memcpy(H + oD2, f2->descriptors, (size_t)n2 * 32);
   memcpy(H + oA1, f1->angle, (size_t)n1 * 4); memcpy(H + oA2, f2->angle, (size_t)n2 * 4);
@@ -735,7 +969,24 @@ int orb_search_for_initialization(orb_matcher* m, const orb_frame_view* f1, cons
     A.minX = mp->min_x; A.minY = mp->min_y;
     A.invW = 64.f / (mp->max_x - mp->min_x);  // Frame.cc:184-186
     A.invH = 48.f / (mp->max_y - mp->min_y);
-    st = dispatch_match<true>(A, 1, s);
+    if (latencyForm) {
+      // the largest distance that can change a decision (see k_sfi_scan)
+      int dmax = 255;
+      for (int d = TH_LOW; d < 256; d++)
+        if ((float)(d + 1) * mp->nnratio > (float)TH_LOW) { dmax = d; break; }
+      unsigned* keys = reinterpret_cast<unsigned*>(D + oKeys);
+      int* cnt = reinterpret_cast<int*>(D + oCnt);
+      const size_t smem = (size_t)(n1 + n2) * 4 + (size_t)((n2 + 1) & ~1) * 2 + (size_t)((n1 + 3) & ~3) + (size_t)kSfiChunk * (kSfiK + 1) * 4;
+      if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints per frame for the matcher's shared memory");
+      ORB_CUDA(raise_dynamic_smem(k_sfi_walk, smem));
+      const int rowsPerCta = 8 * kSfiRowsPerWarp;
+      k_sfi_scan<<<dim3((n1 + rowsPerCta - 1) / rowsPerCta, 1), 256, 0, s>>>(A, keys, cnt, dmax);
+      k_sfi_walk<<<1, 256, smem, s>>>(A, keys, cnt, dmax);
+      ORB_CUDA(cudaGetLastError());
+      st = ORB_OK;
+    } else {
+      st = dispatch_match<true>(A, 1, s);
+    }
   } else {
     st = dispatch_match<false>(A, 1, s);
   }

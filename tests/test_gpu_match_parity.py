@@ -62,6 +62,71 @@ def test_search_for_initialization_reference_mode(oracle, window):
     assert n2 == n2_ref and np.array_equal(m2, m2_ref) and np.array_equal(prev_gpu, prev2_ref)
 
 
+def _clustered_level0_frames(n, seed, w=640, h=480, clusters=6, flips=6):
+    """Two frames of level-0 keypoints whose descriptors come from a few prototypes (repetitive texture): most rows see many
+    candidates at small distances, rows steal each other's matches, candidate lists overflow."""
+    from orb_slam2_detailed_comments_b200._lib import KP_DTYPE
+    rng = np.random.RandomState(seed)
+    proto = rng.randint(0, 256, (clusters, 32)).astype(np.uint8)
+
+    def frame(m, jitter):
+        k = np.zeros(m, KP_DTYPE)
+        k["x"] = rng.uniform(20, w - 20, m).astype(np.float32); k["y"] = rng.uniform(20, h - 20, m).astype(np.float32)
+        k["octave"] = (rng.rand(m) < 0.15).astype(np.int32) * rng.randint(1, 4, m)    # 85 % on level 0
+        k["angle"] = rng.uniform(0, 360, m).astype(np.float32)
+        k["size"] = 31.0; k["class_id"] = -1
+        d = proto[rng.randint(0, clusters, m)].copy()
+        for i in range(m):
+            bits = rng.randint(0, 256, rng.randint(0, flips + 1))
+            np.bitwise_xor.at(d[i], bits >> 3, (1 << (bits & 7)).astype(np.uint8))
+        return k, d
+    ka, da = frame(n, 0)
+    kb, db = frame(n + 37, 1)
+    m = min(n, 200)
+    kb["x"][:m] = ka["x"][:m] + 3.0; kb["y"][:m] = ka["y"][:m] - 2.0; kb["octave"][:m] = ka["octave"][:m]
+    db[:m] = da[:m]                                     # exact duplicates: distance 0, ties between rows
+    return ka, da, kb, db
+
+
+@pytest.mark.parametrize("case", ["extraction", "extraction_narrow", "clustered", "clustered_wide", "ratio_1", "ratio_small", "tiny"])
+def test_search_for_initialization_latency_form(oracle, case):
+    """The form a drop-in caller gets (no per-row distances requested): k_sfi_scan + k_sfi_walk. Same vnMatches12, return
+    value and vbPrevMatched as the oracle, over three consecutive calls (vbPrevMatched moves, Tracking.cc:915-926), on real
+    extractions and on repetitive descriptors that overflow the stored candidate lists (exact re-scoring path)."""
+    from orb_slam2_detailed_comments_b200 import FrameView, ORBmatcher
+    ratio, window, ori = 0.9, 100, True
+    if case.startswith("extraction"):
+        ka, da, kb, db = _frames_from_extraction(oracle, nfeat=2000 if case == "extraction" else 1000)
+        window = 100 if case == "extraction" else 12
+    elif case == "tiny":
+        ka, da, kb, db = _clustered_level0_frames(9, 3)
+    else:
+        ka, da, kb, db = _clustered_level0_frames(1500 if case != "clustered_wide" else 900, 11, clusters=4 if case == "clustered" else 2,
+                                                  flips=10 if case == "clustered" else 4)
+        window = 100 if case == "clustered" else 400
+        ratio = {"ratio_1": 1.0, "ratio_small": 0.3}.get(case, 0.9)
+        ori = case != "ratio_1"
+    F1 = FrameView.from_keypoints(ka, da, 640, 480)
+    F2 = FrameView.from_keypoints(kb, db, 640, 480)
+    m = ORBmatcher(ratio, ori)
+    prev_ref = F1.xy.copy()
+    prev_gpu = F1.xy.copy()
+    total = 0
+    for call in range(3):
+        n_ref, m_ref, prev_ref, _, _ = oracle.search_for_initialization(
+            F1.xy, F1.octave, F1.angle, F1.descriptors, F2.xy, F2.octave, F2.angle, F2.descriptors, (0, 640, 0, 480), prev_ref,
+            window=window, nnratio=ratio, check_ori=ori, mode=0)
+        n, m12 = m.SearchForInitialization(F1, F2, prev_gpu, window, mode=0)
+        assert n == n_ref, "%s call %d: %d matches vs %d" % (case, call, n, n_ref)
+        assert np.array_equal(m12, m_ref), "%s call %d: vnMatches12 differs in %d rows" % (case, call, int((m12 != m_ref).sum()))
+        assert np.array_equal(prev_gpu, prev_ref)
+        total += n_ref
+    print(case, "matches over three calls", total)
+    if case != "tiny":
+        assert total > 30
+    m.close()
+
+
 @pytest.mark.parametrize("n", [2600, 2048, 2000, 1000, 777, 130, 33])
 @pytest.mark.parametrize("check_ori", [True, False])
 def test_bruteforce_single_pair(oracle, n, check_ori):
