@@ -822,7 +822,7 @@ def run_ours(args, rank, world, local_rank):
     # bytes per launch / average launch duration == stage bytes over all frames / stage time
     achieved = per_stage_b[dom] * frames_total / (stage_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0_border2+k_resize_strip+k_fill_borders", "fast": "k_fast_cells", "quadtree": "k_quadtree",
-                                           "blur": "k_blur7", "describe": "k_describe_tma"}[dom],
+                                           "blur": "k_blur7", "describe": "k_describe_ring"}[dom],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom),
                 "peak_source": peak_src, "algorithmic_bytes_per_frame": per_stage_b[dom], "frames_per_launch": frames_per_launch,
                 "avg_launch_ms": dom_ms, "share_of_step": stage_ms[dom] / max(1e-9, sum(stage_ms.values()))}

@@ -3050,7 +3050,8 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
   launches++;
   if ((st = stage_mark(e, s))) return st;
   const int slots = std::min(cap, e->maxKp);
-  if (e->descTma && e->descRing && g.lv[0].w < 16384 && g.lv[0].h < 16384) {
+  // a few frames per launch: the ring's serial chain of 8 keypoints per warp is the long pole (15 vs 11 us for one frame)
+  if (e->descTma && e->descRing && B >= 8 && g.lv[0].w < 16384 && g.lv[0].h < 16384) {
     const int per = 8 * e->descRing;
     auto kfn = describe_ring_variant(e->descRing);
     kfn<<<dim3((slots + per - 1) / per, B), 256, desc_ring_smem(kDescRingDepth), s>>>(g, e->descMaps[lane], W.kept, W.keptCount, e->keptTotal, e->d_pattern, d_kps,

@@ -46,7 +46,7 @@ class Batch:
         self.counts, self.qcounts = counts, qcounts
 
 
-def scenes_ragged(seed0, **kw):
+def scenes_ragged(seed0, rep=1, **kw):
     sc = [tracking_scene(2000, 1900, seed0, **kw), tracking_scene(1337, 2100, seed0 + 1, **kw), tracking_scene(700, 650, seed0 + 2, **kw),
           tracking_scene(900, 800, seed0 + 3, **kw), tracking_scene(800, 900, seed0 + 4, **kw)]
     # frame 3: no keypoints in the current frame; frame 4: no map points
@@ -54,7 +54,7 @@ def scenes_ragged(seed0, **kw):
         sc[3][k] = sc[3][k][:0]
     for k in ("last", "Xw", "mp_flags", "mp_desc"):
         sc[4][k] = sc[4][k][:0]
-    return sc
+    return sc * rep   # rep = 2: ten pairs per call - the batch form of the vocabulary ordering (one CTA per pair)
 
 
 @pytest.mark.parametrize("seed,th,direction", [(100, 15.0, 0), (200, 7.0, 1), (300, 15.0, 2), (400, 40.0, 0)])
@@ -118,11 +118,11 @@ def test_local_map_search(oracle, seed, th):
     assert total > 1000
 
 
-@pytest.mark.parametrize("seed,nodes,ori", [(800, 100, True), (900, 12, True), (1000, 3000, False)])
-def test_search_by_bow(oracle, seed, nodes, ori):
+@pytest.mark.parametrize("seed,nodes,ori,rep", [(800, 100, True, 1), (900, 12, True, 1), (1000, 3000, False, 1), (810, 100, True, 2)])
+def test_search_by_bow(oracle, seed, nodes, ori, rep):
     import torch
     from orb_slam2_detailed_comments_b200 import search
-    sc = scenes_ragged(seed, flip_bits=40)
+    sc = scenes_ragged(seed, rep, flip_bits=40)
     bt = Batch(sc, 2100, 2200)
     B = len(sc)
     rng = np.random.RandomState(seed)
@@ -185,13 +185,13 @@ def test_search_by_bow_keyframe_pair(oracle):
     assert total > 200
 
 
-@pytest.mark.parametrize("seed,only_stereo,mono", [(1200, 0, False), (1300, 1, False), (1400, 0, True)])
-def test_search_for_triangulation(oracle, seed, only_stereo, mono):
+@pytest.mark.parametrize("seed,only_stereo,mono,rep", [(1200, 0, False, 1), (1300, 1, False, 1), (1400, 0, True, 1), (1210, 0, False, 2)])
+def test_search_for_triangulation(oracle, seed, only_stereo, mono, rep):
     import torch
     from orb_slam2_detailed_comments_b200 import search
     from orb_slam2_detailed_comments_b200._lib import TRI_PAIR_DTYPE
     from orb_slam2_detailed_comments_b200.synth import triangulation_pair
-    sc = scenes_ragged(seed, flip_bits=50, noise_px=1.0)
+    sc = [dict(s) for s in scenes_ragged(seed, rep, flip_bits=50, noise_px=1.0)]
     tps = [triangulation_pair(s, seed + i) for i, s in enumerate(sc)]
     for s, tp in zip(sc, tps):          # keyframe 1 = the scene's map-point side, seen from the identity pose
         tp["kps1"] = tp["kps1"][:len(s["last"])]; tp["has_mp1"] = tp["has_mp1"][:len(s["last"])]; tp["ur1"] = tp["ur1"][:len(s["last"])]
