@@ -36,6 +36,19 @@ int main(int argc, char** argv) {
     int n = matcher.SearchForInitialization(F1, F2, prev, m12, 100);
     std::printf("keypoints %zu matches %d pyramid0 %dx%d\n", F1.mvKeysUn.size(), n, ex.mvImagePyramid[0].cols, ex.mvImagePyramid[0].rows);
     if (F1.mvKeysUn.empty() || n <= 0) return 3;
+    if (argc > 2) {   // what the adapter returned, for the value comparison with the oracle (tests/test_compat_build.py)
+      static_assert(sizeof(orbcv::KeyPoint) == 28, "cv::KeyPoint layout");
+      FILE* f = std::fopen(argv[2], "wb");
+      if (!f) return 4;
+      const int nk = (int)F1.mvKeysUn.size(), nm = (int)m12.size();
+      std::fwrite(&nk, 4, 1, f);
+      std::fwrite(F1.mvKeysUn.data(), 28, nk, f);
+      for (int i = 0; i < nk; i++) std::fwrite(F1.mDescriptors.data + (size_t)i * 32, 1, 32, f);
+      std::fwrite(&n, 4, 1, f);
+      std::fwrite(&nm, 4, 1, f);
+      std::fwrite(m12.data(), 4, nm, f);
+      std::fclose(f);
+    }
     // latency of the drop-in call itself (operator() of the adapter: keypoints, descriptors and mvImagePyramid views)
     for (int i = 0; i < 20; i++) ex(img, orbcv::Mat(), F2.mvKeysUn, F2.mDescriptors);
     const auto t0 = std::chrono::steady_clock::now();
