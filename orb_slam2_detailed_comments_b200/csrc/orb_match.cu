@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(256) k_sfi_scan(const PairArgs A, unsigned* __
   }
 }
 
-// dynamic smem: m12[n1] int, m21[n2] int, vmd[n2] u16 (4-byte padded), binOf[n1] u8 (4-byte padded), keys[kSfiChunk * kSfiK], cnt[kSfiChunk]
+// dynamic smem: m12[n1] int, m21[n2] int, vmd[n2] u16 (4-byte padded), binOf[n1] u8 (4-byte padded), keys[kSfiChunk * kSfiK], cnt[kSfiChunk],
+// act[kSfiChunk] u16
 __global__ void __launch_bounds__(256) k_sfi_walk(const PairArgs A, const unsigned* __restrict__ keys, const int* __restrict__ cnt,
                                                    int dmax) {
   extern __shared__ __align__(16) int wsm[];
@@ -379,6 +380,7 @@ __global__ void __launch_bounds__(256) k_sfi_walk(const PairArgs A, const unsign
   u8* binOf = reinterpret_cast<u8*>(vmd + ((n2 + 1) & ~1));
   unsigned* skeys = reinterpret_cast<unsigned*>(binOf + ((n1 + 3) & ~3));
   int* scnt = reinterpret_cast<int*>(skeys + kSfiChunk * kSfiK);
+  unsigned short* act = reinterpret_cast<unsigned short*>(scnt + kSfiChunk);
   const u8* D1 = A.desc1 + (size_t)p * A.stride1 * 32;
   const u8* D2 = A.desc2 + (size_t)p * A.stride2 * 32;
   const float* ang1 = A.ang1 + (size_t)p * A.stride1;
@@ -395,64 +397,96 @@ __global__ void __launch_bounds__(256) k_sfi_walk(const PairArgs A, const unsign
     for (int i = tid; i < rows * kSfiK; i += 256) skeys[i] = keys[((size_t)p * n1 + c0) * kSfiK + i];
     __syncthreads();
     if (wid != 0) continue;
+    // the chunk's active rows, in order
+    int nAct = 0;
     for (int base = 0; base < rows; base += 32) {
-      const int c = base + lane < rows ? scnt[base + lane] : 0;
-      unsigned todo = __ballot_sync(0xffffffffu, c != 0);
-      while (todo) {
-        const int r = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int i1 = c0 + base + r;
-        const int ci = __shfl_sync(0xffffffffu, c, r);
-        const int nk = ci & 0xff;
-        unsigned key = lane < nk ? skeys[(base + r) * kSfiK + lane] : kNoKey;
-        bool free_ = key != kNoKey && (int)vmd[key & 0xffffu] > (int)(key >> 16);   // vMatchedDistance[i2] <= dist -> skip (:627)
-        unsigned m = __ballot_sync(0xffffffffu, free_);
-        unsigned kb = kNoKey, ks = kNoKey;
-        if ((ci & 0x300) && (__popc(m) < 2 || (ci & 0x200))) {
-          // the stored list ran out (or never held the smallest): exact top two of the row against the current state
-          const SfiRow R = sfi_row(A, p, i1);
-          const uint4 lo = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32));
-          const uint4 hi = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32) + 1);
-          const unsigned a[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-          unsigned k1 = kNoKey, k2 = kNoKey;
-          for (int i2 = lane; i2 < n2; i2 += 32) {
-            if (!sfi_in_window(A, p, R, i2)) continue;
-            const int dist = sfi_distance(a, D2, i2);
-            if (dist > dmax || !((int)vmd[i2] > dist)) continue;
-            merge2(k1, k2, ((unsigned)dist << 16) | (unsigned)i2, kNoKey);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const unsigned o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
-            merge2(k1, k2, o1, o2);
-          }
-          kb = k1; ks = k2;
-        } else {
-          if (m) { kb = __shfl_sync(0xffffffffu, key, __ffs(m) - 1); m &= m - 1; }
-          if (m) ks = __shfl_sync(0xffffffffu, key, __ffs(m) - 1);
+      const bool on = base + lane < rows && scnt[base + lane] != 0;
+      const unsigned mm = __ballot_sync(0xffffffffu, on);
+      if (on) act[nAct + __popc(mm & ((1u << lane) - 1u))] = (unsigned short)(base + lane);
+      nAct += __popc(mm);
+    }
+    __syncwarp();
+    // Four rows per step, eight lanes each (a stored list has <= 8 entries). Rows of a step are independent unless an
+    // earlier row of the step takes a keypoint that a later one has among its candidates (vMatchedDistance :627, the steal
+    // :650-654): the step then ends before that row. A row that needs the exact re-scoring is done alone by the warp.
+    const int g = lane >> 3, gl = lane & 7;
+    int pos = 0;
+    while (pos < nAct) {
+      const int row = pos + g < nAct ? (int)act[pos + g] : -1;
+      const int ci = row >= 0 ? scnt[row] : 0;
+      const int nk = ci & 0xff;
+      const unsigned key = gl < nk ? skeys[row * kSfiK + gl] : kNoKey;
+      const bool free_ = key != kNoKey && (int)vmd[key & 0xffffu] > (int)(key >> 16);   // vMatchedDistance[i2] <= dist -> skip (:627)
+      const unsigned mAll = __ballot_sync(0xffffffffu, free_);
+      unsigned m = (mAll >> (8 * g)) & 0xffu;
+      const bool exactNeeded = (ci & 0x300) && (__popc(m) < 2 || (ci & 0x200));
+      unsigned kb = kNoKey, ks = kNoKey;
+      int L = 1;
+      if (__shfl_sync(0xffffffffu, (int)exactNeeded, 0)) {
+        // the stored list of the first row ran out (or never held the smallest): exact top two against the current state
+        const int i1 = c0 + (int)act[pos];
+        const SfiRow R = sfi_row(A, p, i1);
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32));
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(D1 + (size_t)i1 * 32) + 1);
+        const unsigned a[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        unsigned k1 = kNoKey, k2 = kNoKey;
+        for (int i2 = lane; i2 < n2; i2 += 32) {
+          if (!sfi_in_window(A, p, R, i2)) continue;
+          const int dist = sfi_distance(a, D2, i2);
+          if (dist > dmax || !((int)vmd[i2] > dist)) continue;
+          merge2(k1, k2, ((unsigned)dist << 16) | (unsigned)i2, kNoKey);
         }
-        const int best = kb == kNoKey ? INT_MAX : (int)(kb >> 16);
-        const int second = ks == kNoKey ? INT_MAX : (int)(ks >> 16);
-        if (best <= TH_LOW && (float)best < __fmul_rn((float)second, A.nnratio)) {   // :644-647
-          const int bestIdx = (int)(kb & 0xffffu);
-          if (lane == 0) {
-            vmd[bestIdx] = (unsigned short)best;   // vMatchedDistance[bestIdx2] = bestDist
-            const int prevOwner = m21[bestIdx];
-            if (prevOwner >= 0) { m12[prevOwner] = -1; nmatches--; }   // :650-654
-            m12[i1] = bestIdx;
-            m21[bestIdx] = i1;
-            nmatches++;
-            if (A.checkOri) {
-              float rot = __fsub_rn(ang1[i1], ang2[bestIdx]);
-              if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-              int bin = (int)roundf(__fmul_rn(rot, factor));
-              if (bin == HISTO_LENGTH) bin = 0;
-              if (bin >= 0 && bin < HISTO_LENGTH) { binOf[i1] = (u8)bin; s_hist[bin]++; }
-            }
-          }
-          __syncwarp();   // the next row reads vmd
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+          merge2(k1, k2, o1, o2);
+        }
+        kb = g == 0 ? k1 : kNoKey; ks = g == 0 ? k2 : kNoKey;   // only the first row is decided in this step
+      } else {
+        // best / second of every group: its first two free entries (the lists are sorted)
+        const int f1 = m ? __ffs(m) - 1 : 0;
+        const unsigned k1 = __shfl_sync(0xffffffffu, key, 8 * g + f1);
+        if (m) { kb = k1; m &= m - 1; }
+        const int f2 = m ? __ffs(m) - 1 : 0;
+        const unsigned k2 = __shfl_sync(0xffffffffu, key, 8 * g + f2);
+        if (m) ks = k2;
+      }
+      const int best = kb == kNoKey ? INT_MAX : (int)(kb >> 16);
+      const int second = ks == kNoKey ? INT_MAX : (int)(ks >> 16);
+      const bool accept = row >= 0 && best <= TH_LOW && (float)best < __fmul_rn((float)second, A.nnratio);   // :644-647
+      const int bestIdx = (int)(kb & 0xffffu);
+      if (!__shfl_sync(0xffffffffu, (int)exactNeeded, 0)) {
+        // how many leading rows of the step stand: row k + 1 falls if it needs the exact path or a standing row takes one of
+        // its candidates
+        unsigned hit = 0;
+#pragma unroll
+        for (int gp = 0; gp < 3; gp++) {
+          const int accP = __shfl_sync(0xffffffffu, (int)accept, 8 * gp), bP = __shfl_sync(0xffffffffu, bestIdx, 8 * gp);
+          hit |= __ballot_sync(0xffffffffu, g > gp && accP && key != kNoKey && (int)(key & 0xffffu) == bP);
+          const int okNext = __shfl_sync(0xffffffffu, (int)(row >= 0 && !exactNeeded), 8 * (gp + 1));
+          if (L == gp + 1 && okNext && !((hit >> (8 * (gp + 1))) & 0xffu)) L = gp + 2;
         }
       }
+      int delta = 0;
+      if (gl == 0 && g < L && accept) {
+        const int i1 = c0 + row;
+        vmd[bestIdx] = (unsigned short)best;   // vMatchedDistance[bestIdx2] = bestDist
+        const int prevOwner = m21[bestIdx];
+        if (prevOwner >= 0) { m12[prevOwner] = -1; delta--; }   // :650-654
+        m12[i1] = bestIdx;
+        m21[bestIdx] = i1;
+        delta++;
+        if (A.checkOri) {
+          float rot = __fsub_rn(ang1[i1], ang2[bestIdx]);
+          if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+          int bin = (int)roundf(__fmul_rn(rot, factor));
+          if (bin == HISTO_LENGTH) bin = 0;
+          if (bin >= 0 && bin < HISTO_LENGTH) { binOf[i1] = (u8)bin; atomicAdd(&s_hist[bin], 1); }
+        }
+      }
+      nmatches += __reduce_add_sync(0xffffffffu, delta);
+      __syncwarp();   // the next step reads vmd
+      pos += L;
     }
   }
   if (tid == 0) {
@@ -976,7 +1010,7 @@ int orb_search_for_initialization(orb_matcher* m, const orb_frame_view* f1, cons
         if ((float)(d + 1) * mp->nnratio > (float)TH_LOW) { dmax = d; break; }
       unsigned* keys = reinterpret_cast<unsigned*>(D + oKeys);
       int* cnt = reinterpret_cast<int*>(D + oCnt);
-      const size_t smem = (size_t)(n1 + n2) * 4 + (size_t)((n2 + 1) & ~1) * 2 + (size_t)((n1 + 3) & ~3) + (size_t)kSfiChunk * (kSfiK + 1) * 4;
+      const size_t smem = (size_t)(n1 + n2) * 4 + (size_t)((n2 + 1) & ~1) * 2 + (size_t)((n1 + 3) & ~3) + (size_t)kSfiChunk * (kSfiK + 1) * 4 + (size_t)kSfiChunk * 2;
       if (smem > 200 * 1024) ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints per frame for the matcher's shared memory");
       ORB_CUDA(raise_dynamic_smem(k_sfi_walk, smem));
       const int rowsPerCta = 8 * kSfiRowsPerWarp;
