@@ -2409,6 +2409,7 @@ struct orb_extractor {
   bool asyncPending = false;     // orb_extract_batch_host_async work may still be in flight
   DescMaps descMaps[2];          // TMA tensor maps of the two workspace lanes (k_describe_tma)
   int descRing = 8;   // keypoints per warp of k_describe_ring (4, 8, 16); 0 = k_describe_tma
+  int rzSmallFrom = 3, rzSmallBand = 16;   // k_resize_strip: levels >= rzSmallFrom use bands of rzSmallBand rows (measured: pyramid 2.77 -> 2.71 ms)
   PyrMaps blurMaps[2];           // ... and of the blur input tiles (k_blur7)
   bool blurTma = false;
   bool descTma = false;          // maps are valid for the current workspace
@@ -2973,9 +2974,10 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
     k_level0_border2<<<dim3(nbInt + nbEdge, B), 256, 0, s>>>(g, d_img, step, frameStride, W.pyr, e->pyrStride, nbInt);
     launches++;
     // few frames (the per-frame drop-in call): short bands so that a level still fills the machine
-    const int bandRows = B >= 8 ? kRzBand : 4;
     for (int l = 1; l < nl; l++) {
       const LevelGeom& L = g.lv[l];
+      // the upper levels have few strips: shorter bands there keep more than one wave of CTAs in flight
+      const int bandRows = B >= 8 ? (l >= e->rzSmallFrom ? e->rzSmallBand : kRzBand) : 4;
       dim3 grid(((L.w + kEdge - 1 + 20) / 4 + 1 + kRzThreads - 1) / kRzThreads, (L.h + bandRows - 1) / bandRows, B);
       k_resize_strip<<<grid, kRzThreads, 0, s>>>(g, l, W.pyr, e->pyrStride, e->d_taps, bandRows);
       launches++;
@@ -3288,6 +3290,8 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
   e->maxBatch = std::max(1, max_batch);
   build_tables(e);
   if (const char* ev = getenv("ORB_B200_LANES")) e->lanes = atoi(ev) >= 2 ? 2 : 1;
+  if (const char* ev = getenv("ORB_B200_RZ_SMALL_FROM")) e->rzSmallFrom = std::max(1, atoi(ev));
+  if (const char* ev = getenv("ORB_B200_RZ_SMALL_BAND")) e->rzSmallBand = std::max(4, std::min(kRzBand, atoi(ev)));
   if (const char* ev = getenv("ORB_B200_BLUR_FORK")) e->blurFork = std::max(0, std::min(2, atoi(ev)));
   if (const char* ev = getenv("ORB_B200_L0_FORK")) e->l0Fork = atoi(ev) != 0;
   if (const char* ev = getenv("ORB_B200_GRAPH")) e->useGraph = atoi(ev) != 0;
