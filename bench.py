@@ -890,6 +890,7 @@ def run_ours(args, rank, world, local_rank):
         "path_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": total_b, "achieved": path_gbs, "peak": peak, "unit": "GB/s",
                           "frac": path_gbs / peak},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+        "stage_roofline_frac": {k: per_stage_b[k] * frames_total / (max(1e-9, stage_ms[k]) * 1e-3) / 1e9 / peak for k in stage_ms},
         "stage_timing": {"how": "second pass of the same steps, chunks serialised on one stream, CUDA events between stages",
                          "ms_per_step_serialised": ms_serial / args.steps},
         "mean_keypoints": mean_kp, "mean_candidates": mean_cand,
