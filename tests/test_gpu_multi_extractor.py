@@ -152,5 +152,9 @@ def test_initialisation_extractor_feeds_the_matcher_at_4000_keypoints(oracle):
         assert np.array_equal(best, best_ref) and np.array_equal(second, second_ref)
         if mode == 0:
             assert np.array_equal(prev, prev_ref)
+            # the form a drop-in caller gets (no per-row distances): k_sfi_scan + k_sfi_walk at 4000 x 4000
+            prev2 = F1.xy.copy()
+            n2, m2 = m.SearchForInitialization(F1, F2, prev2, 100, mode=0)
+            assert n2 == n_ref and np.array_equal(m2, m_ref) and np.array_equal(prev2, prev_ref)
         assert n > 100
     ex.close(); m.close()
