@@ -129,6 +129,24 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def issue_roofline(fps_per_gpu, clocks):
+    """The extraction path is bound by instruction issue, not by HBM: warp instructions per frame (committed ncu capture of one
+    256-frame chunk, profiles/traffic.json) x frames/s against the SM's issue rate (4 warp instructions per clock and SM)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        wi = {k: v for k, v in t["warp_instructions"].items() if not k.startswith("_")}
+        per_frame = sum(wi.values()) / float(t.get("_frames_per_launch", 256))
+        mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        peak = 4.0 * 148 * mhz * 1e6
+        return {"bound": "issue", "warp_instructions_per_frame": per_frame, "achieved": per_frame * fps_per_gpu, "peak": peak,
+                "unit": "warp instructions/s", "frac": per_frame * fps_per_gpu / peak,
+                "peak_def": "4 warp instructions per clock per SM x 148 SMs x the SM clock sampled during the timed region",
+                "source": "profiles/traffic.json (smsp__inst_executed.sum per stage, ncu --set full)"}
+    except Exception:
+        return None
+
+
 def ncu_traffic(stage):
     """dram bytes per launch of a stage's kernel from the committed ncu --set full capture, or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -890,6 +908,7 @@ def run_ours(args, rank, world, local_rank):
         "path_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": total_b, "achieved": path_gbs, "peak": peak, "unit": "GB/s",
                           "frac": path_gbs / peak},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+        "issue_roofline": issue_roofline(fps / world, clocks),
         "stage_roofline_frac": {k: per_stage_b[k] * frames_total / (max(1e-9, stage_ms[k]) * 1e-3) / 1e9 / peak for k in stage_ms},
         "stage_timing": {"how": "second pass of the same steps, chunks serialised on one stream, CUDA events between stages",
                          "ms_per_step_serialised": ms_serial / args.steps},
