@@ -209,6 +209,46 @@ def test_lanes_do_not_change_results(oracle):
         assert n == len(orc(imgs[b])[0])
 
 
+@pytest.mark.parametrize("shape", [(640, 480, 1000, 1.2, 8), (333, 257, 700, 1.2, 8), (1241, 376, 2000, 1.2, 8), (1920, 1080, 3000, 1.2, 8),
+                                   (801, 603, 1500, 1.1, 12), (500, 400, 37, 1.3, 5)])
+def test_describe_ring_batches(oracle, shape, monkeypatch):
+    """Chunks of >= 8 frames take k_describe_ring (a warp streams 8 keypoints through TMA rings; 48- or 64-byte blurred boxes by
+    the patch's alignment): 11 frames in one chunk on odd shapes, feature budgets that leave the last warps partly or wholly
+    empty, more levels. Keypoints and descriptors equal the oracle's and, byte for byte, what k_describe_tma produces."""
+    import torch
+    from orb_slam2_detailed_comments_b200 import KP_DTYPE, ORBextractor
+    from orb_slam2_detailed_comments_b200.synth import synth_batch
+    w, h, nf, sf, nl = shape
+    imgs = synth_batch(w, h, 11, seed0=900 + w)
+    outs = []
+    for ring in ("8", "0"):
+        monkeypatch.setenv("ORB_B200_DESC_RING", ring)
+        gpu = ORBextractor(nf, sf, nl, 20, 7, max_batch=16)
+        cap = gpu.max_keypoints_for(w, h)
+        d_kps = torch.zeros((11, cap, 28), dtype=torch.uint8, device="cuda")
+        d_desc = torch.zeros((11, cap, 32), dtype=torch.uint8, device="cuda")
+        d_counts = torch.zeros(11, dtype=torch.int32, device="cuda")
+        gpu.extract_batch_device(torch.from_numpy(imgs).cuda(), d_kps, d_desc, d_counts)
+        gpu.synchronize()
+        outs.append((d_counts.cpu().numpy(), d_kps.cpu().numpy().view(KP_DTYPE).reshape(11, cap), d_desc.cpu().numpy()))
+        gpu.close()
+    monkeypatch.delenv("ORB_B200_DESC_RING")
+    (c8, k8, d8), (c0, k0, d0) = outs
+    assert np.array_equal(c8, c0)
+    for b in range(11):
+        n = c8[b]
+        assert k8[b, :n].tobytes() == k0[b, :n].tobytes() and np.array_equal(d8[b, :n], d0[b, :n]), "frame %d: ring != tma" % b
+    orc = oracle.OracleExtractor(nf, sf, nl, 20, 7)
+    for b in (0, 10):
+        okps, odesc = orc(imgs[b])
+        n = c8[b]
+        assert n == len(okps) > 0
+        for f in ("x", "y", "octave", "response", "size"):
+            assert np.array_equal(k8[b, :n][f], okps[f]), f
+        assert np.abs(k8[b, :n]["angle"] - okps["angle"]).max() <= ANGLE_TOL_DEG
+        assert (d8[b, :n] == odesc).all(1).mean() >= MIN_IDENTICAL_DESC
+
+
 @pytest.mark.parametrize("params", [(500, 1.5, 4, 30, 10), (1500, 1.1, 12, 15, 5), (300, 2.0, 3, 20, 7), (800, 1.2, 1, 20, 20)])
 def test_other_extractor_parameters(oracle, params):
     """Generality: other feature budgets, scale factors (incl. > 4/3, where the resize kernel leaves
