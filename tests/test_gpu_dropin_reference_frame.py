@@ -247,3 +247,18 @@ def test_triangulation_search_through_the_reference_class(dropin, reference, see
     gn, gm12 = gref.search_for_triangulation(*args)
     assert gn == rn > (5 if only_stereo else 15)
     assert np.array_equal(gm12, rm12), "vMatchedPairs differs in %d entries" % int((gm12 != rm12).sum())
+
+
+def test_stereo_and_initialisation_without_the_host_pyramid_copy():
+    """ORB_B200_COMPAT_PYRAMID=0 (read once per process): the drop-in extractor leaves mvImagePyramid empty; the reference's stereo
+    Frame constructor (ComputeStereoMatches is the drop-in, on the device-resident pyramid) and the initialisation sequence must
+    still equal the all-CPU reference. Run in a child process because the switch is latched at the first call."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ORB_B200_COMPAT_PYRAMID="0")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                          "stereo_frame_constructor or monocular_initialisation_sequence"], env=env, capture_output=True, text=True,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "2 passed" in out.stdout, out.stdout[-500:]
