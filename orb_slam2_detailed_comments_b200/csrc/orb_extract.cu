@@ -331,17 +331,33 @@ __device__ __forceinline__ void level0_interior_row(const LevelGeom& L, const u8
   const int gA = 3, gB = max(gA, (L.w - 20) / 16 + 3);          // interior groups: 16 <= c0 and c0 + 20 <= w
   const u8* row = src + (size_t)reflect101(by - kEdge, L.h) * step;
   u8* dst = dstBase + (long long)by * L.pitch;
-  for (int gi = gA + lane; gi < gB; gi += 32) {
-    const size_t addr = reinterpret_cast<size_t>(row + 16 * (gi - 2));
-    const unsigned* wp = reinterpret_cast<const unsigned*>(addr & ~(size_t)3);
-    const unsigned sh = (unsigned)(addr & 3) * 8;
-    const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
-    uint4 out;
-    out.x = __funnelshift_r(w0, w1, sh);
-    out.y = __funnelshift_r(w1, w2, sh);
-    out.z = __funnelshift_r(w2, w3, sh);
-    out.w = __funnelshift_r(w3, w4, sh);
-    *reinterpret_cast<uint4*>(dst + 16 * gi) = out;
+  // the row's groups in rounds of 4 x 32: all loads of a round are issued before its first store (a warp lives for one row:
+  // with a load - store chain per group it spent its life waiting, long-scoreboard stalls 22 warps per issue slot)
+  const unsigned sh = (unsigned)(reinterpret_cast<size_t>(row) & 3) * 8;   // 16 * (gi - 2) keeps the alignment of `row`
+  const unsigned* wrow = reinterpret_cast<const unsigned*>(reinterpret_cast<size_t>(row) & ~(size_t)3);
+  for (int g0 = gA + lane; g0 < gB; g0 += 128) {
+    unsigned w[4][5];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int gi = g0 + 32 * k;
+      if (gi < gB) {
+        const unsigned* wp = wrow + 4 * (gi - 2);
+#pragma unroll
+        for (int j = 0; j < 5; j++) w[k][j] = __ldg(wp + j);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int gi = g0 + 32 * k;
+      if (gi < gB) {
+        uint4 out;
+        out.x = __funnelshift_r(w[k][0], w[k][1], sh);
+        out.y = __funnelshift_r(w[k][1], w[k][2], sh);
+        out.z = __funnelshift_r(w[k][2], w[k][3], sh);
+        out.w = __funnelshift_r(w[k][3], w[k][4], sh);
+        *reinterpret_cast<uint4*>(dst + 16 * gi) = out;
+      }
+    }
   }
 }
 // one warp: the edge groups (<= 8) of the 4 bordered rows by4 .. by4+3
