@@ -2460,7 +2460,7 @@ struct orb_extractor {
   // ... and their kernel sequence (2 memsets + 14 launches, all on fixed buffers) is replayed as a CUDA graph, captured
   // again whenever a pointer, the image size or the capacity changes (ORB_B200_GRAPH=0 launches kernel by kernel)
   struct GraphKey { const void* p[8]; int w, h, cap, frames, flags; float mbf, mb; };   // mbf / mb are baked into k_stereo's launch
-  u8* d_stereoScratch = nullptr; size_t stereoScratchBytes = 0;   // match list + counters of k_stereo's split mode
+  u8* d_stereoScratch[2] = {nullptr, nullptr}; size_t stereoScratchBytes[2] = {0, 0};   // per workspace lane: match lists + counters of k_stereo's split mode
   bool useGraph = true;
   cudaGraphExec_t callGraph[2] = {nullptr, nullptr};   // [0] one frame, [1] stereo pair
   GraphKey callKey[2] = {};
@@ -3095,21 +3095,29 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
 
 // Frame::ComputeStereoMatches for the B/2 stereo pairs of the chunk that was just extracted
 // (frames 2p = left, 2p+1 = right; the chunk's pyramids are still in the workspace).
-// match list (32 pairs x cap) + counters of k_stereo's split mode; grown outside of any graph capture
-int ensure_stereo_scratch(orb_extractor* e, int cap, cudaStream_t s) {
-  const size_t need = (size_t)32 * cap * sizeof(int2) + 64 * sizeof(int);
-  if (need <= e->stereoScratchBytes) return ORB_OK;
+// match lists (pairs x cap) + counters (2 per pair) of k_stereo's split mode, one block per workspace lane; grown outside of any
+// graph capture and before the lanes of a multi-chunk call are forked
+static size_t stereo_counter_bytes(int pairs) { return round_up((size_t)2 * pairs * sizeof(int), (size_t)256); }
+// CTAs per pair: a pair alone in a call is a latency problem (16 CTAs), a chunk of 128 pairs at one CTA per pair is less than
+// one wave of the machine (2 CTAs per pair), many more pairs fill it by themselves
+// (128-pair chunks, ms per 1024 pairs incl. extraction: 1 CTA per pair 13.41, 2: 13.27, 3: 13.36, 4: 13.43, 8: 13.61 - every CTA of
+// a pair repeats the pair's set-up)
+static int stereo_split(int pairs) { return pairs <= 8 ? 16 : (pairs <= 32 ? 4 : (pairs <= 192 ? 2 : 1)); }
+int ensure_stereo_scratch(orb_extractor* e, int cap, int pairs, int lane, cudaStream_t s) {
+  const size_t need = (size_t)pairs * cap * sizeof(int2) + stereo_counter_bytes(pairs);
+  if (need <= e->stereoScratchBytes[lane]) return ORB_OK;
   ORB_CUDA(cudaStreamSynchronize(s));
-  cudaFree(e->d_stereoScratch);
-  e->d_stereoScratch = nullptr; e->stereoScratchBytes = 0;
+  { const int ss_ = sync_handle(e); if (ss_) return ss_; }
+  cudaFree(e->d_stereoScratch[lane]);
+  e->d_stereoScratch[lane] = nullptr; e->stereoScratchBytes[lane] = 0;
   if (e->callGraph[1]) { cudaGraphExecDestroy(e->callGraph[1]); e->callGraph[1] = nullptr; }
-  ORB_CUDA(cudaMalloc(&e->d_stereoScratch, need));
-  e->stereoScratchBytes = need;
+  ORB_CUDA(cudaMalloc(&e->d_stereoScratch[lane], need));
+  e->stereoScratchBytes[lane] = need;
   return ORB_OK;
 }
 
 int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, const int* d_counts, const u8* d_desc, float mbf,
-               float mb, float* d_uRight, float* d_depth, cudaStream_t s, int lane = 0, bool concurrentLanes = false) {
+               float mb, float* d_uRight, float* d_depth, cudaStream_t s, int lane = 0) {
   // right keypoints (x, row band, octave), SAD list, row index (H+2 ints) and up to 12 index entries
   // per keypoint (more -> the kernel scans all right keypoints instead of using the index)
   size_t fixed = (size_t)cap * (4 + 4 + 8 + 1) + (size_t)(e->g.H + 2) * 4 + 64;
@@ -3120,17 +3128,13 @@ int run_stereo(orb_extractor* e, int B, const orb_keypoint* d_kps, int cap, cons
     ORB_FAIL(ORB_ERR_UNSUPPORTED, "too many keypoints / rows for the stereo kernel's shared memory");
   if (cap > 65535) ORB_FAIL(ORB_ERR_UNSUPPORTED, "stereo matching supports at most 65535 keypoints per frame");
   ORB_CUDA(raise_dynamic_smem(k_stereo, smem));
-  // few pairs per call (the per-frame drop-in case): deal every pair to G CTAs
+  // deal every pair to G CTAs (see stereo_split); without a scratch block of this lane that is large enough: one CTA per pair
   const int pairs = B / 2;
-  // (one scratch list per extractor: not while chunks of this call run on the two lane streams at once)
-  const int G = concurrentLanes ? 1 : (pairs <= 8 ? 16 : (pairs <= 32 ? 4 : 1));
-  if (G > 1) {
-    const int st = ensure_stereo_scratch(e, cap, s);
-    if (st) return st;
-    ORB_CUDA(cudaMemsetAsync(e->d_stereoScratch, 0, 64 * sizeof(int), s));
-  }
-  int* gcnt = reinterpret_cast<int*>(e->d_stereoScratch);
-  int2* gsad = G > 1 ? reinterpret_cast<int2*>(e->d_stereoScratch + 64 * sizeof(int)) : nullptr;
+  int G = stereo_split(pairs);
+  if (G > 1 && e->stereoScratchBytes[lane] < (size_t)pairs * cap * sizeof(int2) + stereo_counter_bytes(pairs)) G = 1;
+  if (G > 1) ORB_CUDA(cudaMemsetAsync(e->d_stereoScratch[lane], 0, (size_t)2 * pairs * sizeof(int), s));
+  int* gcnt = reinterpret_cast<int*>(e->d_stereoScratch[lane]);
+  int2* gsad = G > 1 ? reinterpret_cast<int2*>(e->d_stereoScratch[lane] + stereo_counter_bytes(pairs)) : nullptr;
   k_stereo<<<dim3(pairs, G), kStereoThreads, smem, s>>>(e->g, lane_of(e, lane).pyr, e->pyrStride, d_kps, d_desc, d_counts, cap, mbf, mb,
                                                         e->d_invScale, d_uRight, d_depth, entCap, gsad, gcnt);
   ORB_CUDA(cudaGetLastError());
@@ -3355,7 +3359,7 @@ int orb_destroy(orb_extractor* e) {
   }
   for (int k = 0; k < 2; k++)
     if (e->callGraph[k]) cudaGraphExecDestroy(e->callGraph[k]);
-  cudaFree(e->d_stereoScratch);
+  cudaFree(e->d_stereoScratch[0]); cudaFree(e->d_stereoScratch[1]);
   if (e->hostPyr) cudaFreeHost(e->hostPyr);
   if (e->h_in) cudaFreeHost(e->h_in);
   if (e->h_out) cudaFreeHost(e->h_out);
@@ -3683,6 +3687,12 @@ int orb_extract_stereo_batch_device(orb_extractor* e, const uint8_t* d_images, i
   const int batch = 2 * pairs;
   const int nChunks = (batch + chunk - 1) / chunk;
   const bool multi = e->lanes >= 2 && nChunks >= 2;
+  {
+    const int chunkPairs = std::min(chunk, batch) / 2;
+    if (stereo_split(chunkPairs) > 1)
+      for (int l = 0; l < (multi ? 2 : 1); l++)
+        if ((st = ensure_stereo_scratch(e, capacity, chunkPairs, l, s))) return st;
+  }
   if ((st = lanes_fork(e, s, nChunks))) return st;
   int ci = 0;
   for (int b0 = 0; b0 < batch; b0 += chunk, ci++) {
@@ -3694,7 +3704,7 @@ int orb_extract_stereo_batch_device(orb_extractor* e, const uint8_t* d_images, i
     if (st) return st;
     st = run_stereo(e, B, d_keypoints + (size_t)b0 * capacity, capacity, d_counts + b0,
                     d_descriptors + (size_t)b0 * capacity * 32, mbf, mb, d_uright + (size_t)(b0 / 2) * capacity,
-                    d_depth + (size_t)(b0 / 2) * capacity, ls, lane, multi);
+                    d_depth + (size_t)(b0 / 2) * capacity, ls, lane);
     if (st) return st;
   }
   st = lanes_join(e, s, nChunks);
@@ -3733,7 +3743,7 @@ int orb_extract_stereo(orb_extractor* e, const uint8_t* left, const uint8_t* rig
   const size_t oKL = 64, oKR = oKL + szK, oDL = oKR + szK, oDR = oDL + szD, oU = oDR + szD, oZ = oU + szF;
   st = ensure_pinned(e, 2 * dFrame, oZ + szF);
   if (st) return st;
-  st = ensure_stereo_scratch(e, capacity, s);
+  st = ensure_stereo_scratch(e, capacity, 1, 0, s);
   if (st) return st;
   stage_rows(e->h_in, left, width, height, step);
   stage_rows(e->h_in + dFrame, right, width, height, step);
@@ -3801,7 +3811,7 @@ int orb_stereo_match(orb_extractor* left, orb_extractor* right, float mbf, float
   const size_t szF = round_up((size_t)m * sizeof(float), (size_t)64);
   int st = ensure_pinned(e, 0, 64 + 2 * szF);
   if (st) return st;
-  st = ensure_stereo_scratch(e, cap, s);
+  st = ensure_stereo_scratch(e, cap, 1, 0, s);
   if (st) return st;
   e->lastLaunches = 0;
   st = run_stereo(e, 2, e->d_kps[0], cap, e->d_n[0], e->d_desc[0], mbf, mb, e->d_uRight[0], e->d_depth[0], s, 0);
