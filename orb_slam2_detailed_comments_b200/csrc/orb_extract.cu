@@ -2282,10 +2282,7 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
       }
     }
 #pragma unroll
-    for (int q = 0; q < 11; q++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-    }
+    for (int q = 0; q < 11; q++) acc[q] = __reduce_add_sync(0xffffffffu, acc[q]);   // one REDUX per shift (ten instructions as a shuffle tree)
     if (lane == 0) {
       int best = 0x7fffffff, bestinc = 0;
 #pragma unroll
