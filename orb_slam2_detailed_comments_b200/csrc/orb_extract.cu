@@ -1609,13 +1609,8 @@ __global__ void __launch_bounds__(256) k_describe(const Geom g, const u8* __rest
         s2 = __dp4a(wv, wu[q], s2);
         prev = nxt;
       }
-      int m10 = (int)s2 - kHalfPatch * (int)s1;               // sum u*I
-      int m01 = (lane - kHalfPatch) * (int)s1;                // sum v*I
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-      }
+      const int m10 = __reduce_add_sync(0xffffffffu, (int)s2 - kHalfPatch * (int)s1);   // sum u*I
+      const int m01 = __reduce_add_sync(0xffffffffu, (lane - kHalfPatch) * (int)s1);    // sum v*I
       angle[k] = fast_atan2_deg((float)m01, (float)m10);
     }
   }
@@ -1809,13 +1804,8 @@ __global__ void __launch_bounds__(256) k_describe_tma(const Geom g, const __grid
           s2 = __dp4a(wv, wu[q], s2);
         }
       }
-      int m10 = (int)s2 - kHalfPatch * (int)s1;               // sum u*I
-      int m01 = (lane - kHalfPatch) * (int)s1;                // sum v*I
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-      }
+      const int m10 = __reduce_add_sync(0xffffffffu, (int)s2 - kHalfPatch * (int)s1);   // sum u*I
+      const int m01 = __reduce_add_sync(0xffffffffu, (lane - kHalfPatch) * (int)s1);    // sum v*I
       angle[k] = fast_atan2_deg((float)m01, (float)m10);
     }
   }
@@ -2249,8 +2239,7 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
         }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    key = __reduce_min_sync(0xffffffffu, key);
     if (key == 0xffffffffu || (int)(key >> 16) >= thOrbDist) continue;
     const int bestIdxR = (int)(key & 0xffffu);
     // ---- SAD refinement on pyramid level levelL

@@ -797,8 +797,7 @@ __global__ void __launch_bounds__(kApThreads) k_allpairs(const u8* __restrict__ 
 #pragma unroll
     for (int r = 0; r < RPT; r++)
       if (tid + r * kApThreads < nDesc && best[r] <= TH_LOW && (float)best[r] < __fmul_rn((float)second[r], nnratio)) cnt++;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) s_cnt[wid] = cnt;
     __syncthreads();
     if (tid == 0) {
