@@ -2253,21 +2253,19 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo(const Geom g, const u
     const u8* IL = pyr + (size_t)fL * pyrStride + L.off + (long long)cv * L.pitch + cu;
     const u8* IR = pyr + (size_t)fR * pyrStride + L.off + (long long)cv * L.pitch + cr;
     const int cL = IL[0];
-    int acc[11];
+    // |(IL - cL) - (IR_q - cR_q)| = |(IL + (cR_q - cL)) - IR_q|: one add and one SAD instruction per pixel and shift
+    int acc[11], kq[11];
 #pragma unroll
-    for (int q = 0; q < 11; q++) acc[q] = 0;
+    for (int q = 0; q < 11; q++) { acc[q] = 0; kq[q] = (int)IR[q - 5] - cL; }
 #pragma unroll
     for (int t = 0; t < 4; t++) {
       const int pI = lane + 32 * t;
       if (pI < 121) {
         const int dy = pI / 11 - 5, dx = pI % 11 - 5;
-        const int av = (int)IL[dy * L.pitch + dx] - cL;
+        const int il = (int)IL[dy * L.pitch + dx];
         const u8* rrow = IR + dy * L.pitch + dx;
 #pragma unroll
-        for (int q = 0; q < 11; q++) {
-          const int bv = (int)rrow[q - 5] - (int)IR[q - 5];
-          acc[q] += abs(av - bv);
-        }
+        for (int q = 0; q < 11; q++) acc[q] = (int)__sad(il + kq[q], (int)rrow[q - 5], (unsigned)acc[q]);
       }
     }
 #pragma unroll
