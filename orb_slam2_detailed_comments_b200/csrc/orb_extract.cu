@@ -417,7 +417,7 @@ constexpr int kRzThreads = 64, kRzBand = 32;
 // One warp: 32 column groups starting at column cFirst, output rows [j0, j1) (at most 32) of level l of one frame
 // (`frame` = the frame's pyramid slab). CG: source pixels are read with ld.global.cg - the single-launch pyramid reads
 // rows another CTA of the same launch has just written, which must not be served from a stale L1 line.
-template <bool CG>
+template <bool CG, bool WAIT = false>
 __device__ __forceinline__ void resize_strip_warp(const Geom& g, int l, u8* __restrict__ frame, const int2* __restrict__ taps,
                                                   int cFirst, int j0, int j1, int lane) {
   const LevelGeom& D = g.lv[l];
@@ -453,6 +453,9 @@ __device__ __forceinline__ void resize_strip_warp(const Geom& g, int l, u8* __re
   unsigned* dp = reinterpret_cast<unsigned*>(frame + D.off + (long long)j0 * D.pitch + c0);
   auto ld = [](const unsigned* p) { return CG ? __ldcg(p) : *p; };
 
+  // programmatic dependent launch (k_resize_strip_pdl): everything above read only the tap tables; the pixels of the level
+  // below are complete once the launch before this one has finished
+  if (WAIT) asm volatile("griddepcontrol.wait;" ::: "memory");
   unsigned hc[4], hn[4];
   {
     const unsigned q0 = ld(q), q1 = ld(q + 1), q2 = ld(q + 2);
@@ -498,6 +501,17 @@ __global__ void __launch_bounds__(kRzThreads) k_resize_strip(const Geom g, int l
   const int j0 = blockIdx.y * bandRows;
   resize_strip_warp<false>(g, l, pyr + (size_t)blockIdx.z * pyrStride, taps, 4 * (blockIdx.x * kRzThreads + (threadIdx.x & ~31)) - 20, j0,
                            min(j0 + bandRows, g.lv[l].h), threadIdx.x & 31);
+}
+
+// The same kernel for the per-frame call, where a level is a few microseconds of work and the chain of eight dependent
+// launches is the long pole: launched with programmatic stream serialization, it lets the next level's CTAs start and set
+// up their taps while this one is still running; they wait for this grid to finish before they touch its pixels.
+__global__ void __launch_bounds__(kRzThreads) k_resize_strip_pdl(const Geom g, int l, u8* __restrict__ pyr, size_t pyrStride,
+                                                                 const int2* __restrict__ taps, int bandRows) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int j0 = blockIdx.y * bandRows;
+  resize_strip_warp<false, true>(g, l, pyr + (size_t)blockIdx.z * pyrStride, taps, 4 * (blockIdx.x * kRzThreads + (threadIdx.x & ~31)) - 20,
+                                 j0, min(j0 + bandRows, g.lv[l].h), threadIdx.x & 31);
 }
 
 // Top / bottom border rows of levels 1.. (copyMakeBorder(REFLECT_101) :1695): the strips have written every interior row
@@ -2409,6 +2423,7 @@ struct orb_extractor {
   bool asyncPending = false;     // orb_extract_batch_host_async work may still be in flight
   DescMaps descMaps[2];          // TMA tensor maps of the two workspace lanes (k_describe_tma)
   int descRing = 8;   // keypoints per warp of k_describe_ring (4, 8, 16); 0 = k_describe_tma
+  bool pdl = true;   // per-frame calls: the resize chain as programmatic dependent launches (ORB_B200_PDL=0: plain launches)
   int rzSmallFrom = 3, rzSmallBand = 16;   // k_resize_strip: levels >= rzSmallFrom use bands of rzSmallBand rows (measured: pyramid 2.77 -> 2.71 ms)
   PyrMaps blurMaps[2];           // ... and of the blur input tiles (k_blur7)
   bool blurTma = false;
@@ -2979,7 +2994,17 @@ int run_chunk(orb_extractor* e, const u8* d_img, int B, size_t step, size_t fram
       // the upper levels have few strips: shorter bands there keep more than one wave of CTAs in flight
       const int bandRows = B >= 8 ? (l >= e->rzSmallFrom ? e->rzSmallBand : kRzBand) : 4;
       dim3 grid(((L.w + kEdge - 1 + 20) / 4 + 1 + kRzThreads - 1) / kRzThreads, (L.h + bandRows - 1) / bandRows, B);
-      k_resize_strip<<<grid, kRzThreads, 0, s>>>(g, l, W.pyr, e->pyrStride, e->d_taps, bandRows);
+      if (B < 8 && e->pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(kRzThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        ORB_CUDA(cudaLaunchKernelEx(&cfg, k_resize_strip_pdl, g, l, W.pyr, e->pyrStride, (const int2*)e->d_taps, bandRows));
+      } else {
+        k_resize_strip<<<grid, kRzThreads, 0, s>>>(g, l, W.pyr, e->pyrStride, e->d_taps, bandRows);
+      }
       launches++;
     }
     if (nl > 1) {
@@ -3294,6 +3319,7 @@ int orb_create(const orb_params* params, int device, int max_batch, orb_extracto
   e->maxBatch = std::max(1, max_batch);
   build_tables(e);
   if (const char* ev = getenv("ORB_B200_LANES")) e->lanes = atoi(ev) >= 2 ? 2 : 1;
+  if (const char* ev = getenv("ORB_B200_PDL")) e->pdl = atoi(ev) != 0;
   if (const char* ev = getenv("ORB_B200_RZ_SMALL_FROM")) e->rzSmallFrom = std::max(1, atoi(ev));
   if (const char* ev = getenv("ORB_B200_RZ_SMALL_BAND")) e->rzSmallBand = std::max(4, std::min(kRzBand, atoi(ev)));
   if (const char* ev = getenv("ORB_B200_BLUR_FORK")) e->blurFork = std::max(0, std::min(2, atoi(ev)));
